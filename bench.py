@@ -1,0 +1,303 @@
+#!/usr/bin/env python
+"""bench.py — ρ·RHS evaluations per second on BASELINE.json's headline configuration.
+
+Workload (config C3 of SURVEY §8d, BASELINE.json configs[2]): 10-qubit (1024×1024) DaviesGenerator/AME
+RHS with an Ohmic bath — eigenbasis transform, γ(ω_ab) Hadamard, back-transform — on a batch of 64
+ComplexF64 density matrices per GPU.  One "step" = one batched RHS call (64 evaluations per GPU).
+
+  value     device-resident states, CUDA-event timed (whole job: all ranks' evaluations ÷ max time)
+  e2e       same call through the host-buffer entry point (pinned host u/du, H2D+D2H inside)
+  roofline  the ZGEMM kernel (FP64 DMMA) timed per launch with CUDA events inside the timed region
+  cpu_baseline  reference-structured CPU restatement on a bounded sample (oracle/cpu_baseline.py)
+
+`--impl reference` times only the CPU restatement of the reference path (Julia is not installed here or
+on the GPU box, so the reference package itself cannot run).
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NQ, N, BATCH, KCOUP = 10, 1024, 64, 10
+S_POINT, TF = 0.5, 10.0
+ETA, FC, TMK = 1e-4, 4.0, 16.0
+METRIC = "rho_rhs_evals_per_sec_10q_ame_batch64"
+UNIT = "evals/s"
+
+
+def build_c3(seed=3000):
+    """Synthetic C3 operators (host): H(s) = −(1−s)ΣX_i + s·Σ J_ij Z_i Z_j (J ~ U[−1,1)), couplings Z_k,
+    all multiplied by 2π (unit :h).  Qubit 1 is the most significant bit (kron ordering)."""
+    rng = np.random.default_rng(seed)
+    idx = np.arange(N)
+    Hd = np.zeros((N, N), dtype=np.complex128)
+    for q in range(NQ):
+        Hd[idx ^ (1 << q), idx] = -1.0
+    z = [1.0 - 2.0 * ((idx >> (NQ - 1 - q)) & 1) for q in range(NQ)]
+    diag = np.zeros(N)
+    for i in range(NQ):
+        for j in range(i + 1, NQ):
+            diag += (2 * rng.random() - 1) * z[i] * z[j]
+    Hp = np.diag(diag).astype(np.complex128)
+    coup = [np.diag(zq).astype(np.complex128) for zq in z]
+    return Hd, Hp, coup
+
+
+def fA(s):
+    return 1 - s
+
+
+def fB(s):
+    return s
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop = threading.Event()
+
+    def run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {getattr(nv, k): k for k in dir(nv) if k.startswith("nvmlClocksEventReason") or k.startswith("nvmlClocksThrottleReason")}
+            while not self._stop.is_set():
+                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, name in names.items():
+                    if isinstance(bit, int) and bit and (r & bit) == bit:
+                        self.reasons.add(name.replace("nvmlClocksEventReason", "").replace("nvmlClocksThrottleReason", ""))
+                time.sleep(0.05)
+        except Exception as e:  # NVML unavailable: report that instead of inventing numbers
+            self.reasons.add(f"nvml_unavailable:{type(e).__name__}")
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=2)
+        med = float(np.median(self.samples)) if self.samples else None
+        reasons = sorted(x for x in self.reasons if x not in ("GpuIdle", "None", "ApplicationsClocksSetting"))
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": reasons}
+
+
+def cpu_reference_arm(steps, warmup, evals_per_step=1):
+    """The reference's CPU path (restatement, see oracle/cpu_baseline.py) on a bounded sample."""
+    from oracle import cpu_baseline as CB
+    Hd, Hp, coup = build_c3()
+    terms = [2 * np.pi * Hd, 2 * np.pi * Hp]
+    coef = [fA(S_POINT), fB(S_POINT)]
+    cps = [2 * np.pi * c for c in coup]
+    beta = 5 * 6.62607004 / 1.38064852 / np.pi / TMK
+    bath = (ETA, 2 * np.pi * FC, beta)
+    rng = np.random.default_rng(1)
+    g = rng.standard_normal((N, 16)) + 1j * rng.standard_normal((N, 16))
+    rho = g @ g.conj().T
+    rho /= np.trace(rho).real
+    states = [rho] * evals_per_step
+    for _ in range(warmup):
+        CB.time_ame_reference(terms, coef, cps, bath, states[:1])
+    t = 0.0
+    for _ in range(steps):
+        dt, _n = CB.time_ame_reference(terms, coef, cps, bath, states)
+        t += dt
+    return steps * evals_per_step / t, t / steps * 1e3, CB.host_threads()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    config = {"workload": "C3: 10-qubit (1024x1024) DaviesGenerator/AME RHS, Ohmic bath, 64 rho per GPU, K=10 Z_k couplings, s=0.5, lvl=1024",
+              "batch_per_gpu": BATCH, "n": N, "inputs_exceed_l2": True,
+              "l2_note": "u and du are 1 GiB each per GPU (> 126 MB L2); no flush needed"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        steps = max(1, min(args.steps, 5))
+        warm = max(0, min(args.warmup, 1))
+        val, ms, cores = cpu_reference_arm(steps, warm)
+        line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+                "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64 (complex128)", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                                 "sample": f"{steps} steps x 1 rho: reference-structured AME RHS per call (H(s) assembly, LAPACK eigh, gap grouping, "
+                                           "10 coupling rotations, closed-form Davies, back-transform); numpy/OpenBLAS; Julia unavailable"},
+                "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "note": "steps/warmup clamped so the CPU arm finishes in minutes"}
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+    import oqb_b200 as Q
+    ctx = Q.get_context(local_rank)
+    lib = ctx.lib
+
+    # ---- operators (host closures evaluated on the host, everything else on the device) ----
+    Hd, Hp, coup = build_c3()
+    H = Q.DenseHamiltonian([fA, fB], [Hd, Hp], unit="h", ctx=ctx)
+    dav = Q.DaviesGenerator(Q.ConstantCouplings(coup, unit="h"), Q.Ohmic(ETA, FC, TMK), Q.ZERO_LAMBSHIFT)
+    op = Q.DiffEqLiouvillian(H, [dav], [], N)
+    p = Q.ODEParams(H, TF)
+    t_setup0 = time.perf_counter()
+    op._prepare_ame(S_POINT)  # eigen-system (host LAPACK), gap groups, γ tables → device (shared by the batch)
+    ctx.sync()
+    setup_s = time.perf_counter() - t_setup0
+
+    # ---- synthetic states: 64 random density matrices per rank, generated on the device ----
+    gen = torch.Generator(device=f"cuda:{local_rank}").manual_seed(3000 + rank)
+    g = torch.randn((BATCH, N, 32), dtype=torch.complex128, device=f"cuda:{local_rank}", generator=gen)
+    rho = g @ g.conj().transpose(1, 2)
+    rho = rho / torch.diagonal(rho, dim1=1, dim2=2).sum(-1).real[:, None, None]
+    u = Q.DeviceBatch(BATCH, N, N, ctx, rho.transpose(1, 2).contiguous())  # column-major blocks
+    du = u.zeros_like()
+    del g, rho
+
+    def step():
+        ctx.check(lib.oqb_ame_rhs(op._ame, BATCH, u.ptr, du.ptr))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    import ctypes as C
+    l0 = ctx.launch_count()
+    ctx.check(lib.oqb_profile_begin(ctx.h))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    zg_ms, zg_n, zg_fl = C.c_double(), C.c_uint64(), C.c_double()
+    ctx.check(lib.oqb_profile_end(ctx.h, C.byref(zg_ms), C.byref(zg_n), C.byref(zg_fl)))
+    launches = ctx.launch_count() - l0
+    clocks = sampler.stop()
+    tmax = torch.tensor([ms_total], dtype=torch.float64, device=f"cuda:{local_rank}")
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms_total_max = float(tmax.item())
+    value = world * BATCH * args.steps / (ms_total_max * 1e-3)
+
+    # ---- end to end: pinned host buffers, H2D + D2H inside the call ----
+    uh = torch.empty((BATCH, N, N), dtype=torch.complex128, pin_memory=True)
+    duh = torch.empty((BATCH, N, N), dtype=torch.complex128, pin_memory=True)
+    uh.copy_(u.t)
+    torch.cuda.synchronize()
+    e2e_steps = max(2, min(args.steps, 5))
+    ctx.check(lib.oqb_ame_rhs_host(op._ame, BATCH, C.c_void_p(uh.data_ptr()), C.c_void_p(duh.data_ptr())))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        ctx.check(lib.oqb_ame_rhs_host(op._ame, BATCH, C.c_void_p(uh.data_ptr()), C.c_void_p(duh.data_ptr())))
+    torch.cuda.synchronize()
+    te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=f"cuda:{local_rank}")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_val = world * BATCH * e2e_steps / float(te.item())
+    e2e_check = float((duh.to(f"cuda:{local_rank}") - du.t).abs().max().item())  # same result as the resident path
+
+    # ---- ensemble-average observable reduce (the only collective of the path), timed separately ----
+    obs_ms = None
+    if world > 1:
+        zs = [np.diag(np.diag(c)) for c in coup[:3]] + [np.eye(N)]
+        ev = Q.expect(zs, u).sum(dim=0)
+        torch.cuda.synchronize()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        dist.all_reduce(ev)
+        a1.record()
+        torch.cuda.synchronize()
+        obs_ms = a0.elapsed_time(a1)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- FP64 ceilings measured in this run (MEASURED_PEAKS.json only has bf16 and HBM) ----
+    a = torch.randn((8192, 8192), dtype=torch.float64, device=f"cuda:{local_rank}")
+    b = torch.randn((8192, 8192), dtype=torch.float64, device=f"cuda:{local_rank}")
+    best = 1e9
+    for _ in range(6):
+        x0, x1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        x0.record(); torch.matmul(a, b); x1.record(); torch.cuda.synchronize()
+        best = min(best, x0.elapsed_time(x1))
+    dgemm_tf = 2 * 8192 ** 3 / (best * 1e-3) / 1e12
+    del a, b
+    za = torch.randn((4096, 4096), dtype=torch.complex128, device=f"cuda:{local_rank}")
+    best = 1e9
+    for _ in range(6):
+        x0, x1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        x0.record(); torch.matmul(za, za); x1.record(); torch.cuda.synchronize()
+        best = min(best, x0.elapsed_time(x1))
+    zgemm_tf = 8 * 4096 ** 3 / (best * 1e-3) / 1e12
+    del za
+    dmma_tf, dfma_tf = ctx.probe_fp64()
+
+    achieved = zg_fl.value / (zg_ms.value * 1e-3) / 1e12 if zg_ms.value > 0 else None
+    peak = max(dgemm_tf, dmma_tf)
+    roofline = {"bound": "tensor", "kernel": "zgemm_kernel (FP64 DMMA.8x8x4, 4 launches/step)",
+                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if achieved else None,
+                "traffic": None,
+                "peak_source": "measured in this run: max(cuBLAS DGEMM 8192^3 best-of-6, DMMA issue probe); MEASURED_PEAKS.json has no FP64 figure",
+                "cublas_dgemm_tflops": dgemm_tf, "cublas_zgemm_4096_tflops": zgemm_tf,
+                "dmma_probe_tflops": dmma_tf, "dfma_probe_tflops": dfma_tf,
+                "kernel_ms_per_launch": zg_ms.value / max(zg_n.value, 1), "kernel_launches_timed": zg_n.value,
+                "kernel_share_of_step": zg_ms.value / ms_total if ms_total > 0 else None,
+                "algorithmic_flops_per_launch": zg_fl.value / max(zg_n.value, 1)}
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        cval, cms, cores = cpu_reference_arm(2, 1)
+        cpu = {"value": cval, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": "2 rho through the reference-structured per-call AME RHS (eigh + rotations + closed-form Davies), numpy/OpenBLAS; see oracle/cpu_baseline.py"}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_total_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64 (complex128)", "data": "synthetic", "config": config,
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": BATCH * N * N * 16, "d2h_bytes_per_step": BATCH * N * N * 16,
+                    "steps": e2e_steps, "max_abs_diff_vs_resident": e2e_check},
+            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+            "setup_s_not_timed": setup_s, "obs_allreduce_ms": obs_ms}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,207 @@
+/* oqb.h — C ABI of the B200-native master-equation RHS evaluator for OpenQuantumBase.jl.
+ *
+ * The reference (/root/reference, pure Julia, v0.7.9) has no FFI today: its "operator API" is
+ * the callable-struct protocol `op(du,u,p,t)`, `update_cache!`, `update_vectorized_cache!`.
+ * Each entry point below names the reference method(s) it evaluates (file:line relative to
+ * /root/reference); INTEGRATION.md shows the Julia `ccall` methods a maintainer adds so that the
+ * unchanged Julia types dispatch here for device-resident batches.
+ *
+ * Conventions
+ *  - Every function returns 0 on success, non-zero on failure; oqb_last_error(ctx) gives the
+ *    message.  Nothing throws, nothing calls back into the host language.
+ *  - Layouts are Julia-native: column-major, interleaved ComplexF64 (re,im doubles).  A batch
+ *    of nb matrices is nb consecutive n×n blocks (a Julia Array{ComplexF64,3} of size n×n×nb);
+ *    a batch of state vectors is n×nb.
+ *  - Pointers prefixed d_ are DEVICE pointers (from oqb_malloc or any CUDA allocator), h_ are
+ *    HOST pointers.  Per-call scalar coefficient arrays (closure values f_i(s_b), γ_k(s_b) that
+ *    the host language evaluated) are small HOST arrays, row-major [nb][count]; passing
+ *    nb_coef == 1 rows with the *_shared flag set shares one row across the whole batch.
+ *  - All work is enqueued on the context's CUDA stream; call oqb_sync before reading results
+ *    on the host (the *_host entry points synchronise themselves).
+ *  - A context is not thread-safe; use one per (host thread, GPU) — the reference's functors are
+ *    not re-entrant either (src/hamiltonian/dense_hamiltonian.jl:61 mutates an internal cache).
+ *  - There is no CPU fallback anywhere in this library.
+ */
+#ifndef OQB_H
+#define OQB_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OQB_VERSION 100
+
+typedef struct oqb_ctx oqb_ctx;       /* stream + workspace                                   */
+typedef struct oqb_dense oqb_dense;   /* DenseHamiltonian terms + Lindblad operators          */
+typedef struct oqb_sparse oqb_sparse; /* SparseHamiltonian terms + sparse Lindblad operators  */
+typedef struct oqb_ame oqb_ame;       /* eigenbasis (Davies / one-sided AME) Liouvillian      */
+
+enum { OQB_OP_N = 0, OQB_OP_T = 1, OQB_OP_C = 2 };
+enum { OQB_OK = 0, OQB_EINVAL = 1, OQB_ECUDA = 2, OQB_ENOMEM = 3 };
+
+/* ------------------------------------------------------------------ context / memory ------ */
+int oqb_version(void);
+int oqb_create(int device, oqb_ctx** out);
+int oqb_destroy(oqb_ctx* ctx);
+const char* oqb_last_error(const oqb_ctx* ctx);
+int oqb_sync(oqb_ctx* ctx);
+int oqb_set_stream(oqb_ctx* ctx, void* cuda_stream); /* borrow an existing cudaStream_t        */
+int oqb_get_stream(oqb_ctx* ctx, void** cuda_stream);
+int oqb_launch_count(const oqb_ctx* ctx, uint64_t* n); /* kernels launched through this ctx    */
+
+int oqb_malloc(oqb_ctx* ctx, size_t nbytes, void** d_ptr);
+int oqb_free(oqb_ctx* ctx, void* d_ptr);
+int oqb_malloc_host(oqb_ctx* ctx, size_t nbytes, void** h_ptr); /* pinned                      */
+int oqb_free_host(oqb_ctx* ctx, void* h_ptr);
+int oqb_upload(oqb_ctx* ctx, void* d_dst, const void* h_src, size_t nbytes);   /* synchronous */
+int oqb_download(oqb_ctx* ctx, void* h_dst, const void* d_src, size_t nbytes); /* synchronous */
+
+/* --------------------------------------------------------------- K1: batched ZGEMM -------- */
+/* C[b] = alpha*opA(A[b])*opB(B[b]) + beta*C[b] on the FP64 tensor pipe.  Replaces LinearAlgebra
+ * `gemm!`/`mul!` on batches (src/hamiltonian/dense_hamiltonian.jl:87-88).  Strides in complex
+ * elements; stride 0 shares the operand.  alpha/beta point to (re,im). */
+int oqb_zgemm_batched(oqb_ctx* ctx, int opA, int opB, int M, int N, int K, const double* alpha,
+                      const void* d_A, int64_t lda, int64_t strideA, const void* d_B, int64_t ldb,
+                      int64_t strideB, const double* beta, void* d_C, int64_t ldc, int64_t strideC,
+                      int batch);
+
+/* ------------------------------------ DenseHamiltonian + LindbladLiouvillian (+ Redfield) -- */
+/* h_mats: nterms n×n matrices m_i exactly as DenseHamiltonian stores them (already unit-scaled,
+ * src/hamiltonian/dense_hamiltonian.jl:38).  h_lops: K Lindblad operators L_k (may be NULL/K=0),
+ * src/opensys/lindblad.jl:76-92.  Uploads once and precomputes L_k'L_k on the device. */
+int oqb_dense_create(oqb_ctx* ctx, int n, int nterms, const void* h_mats, int K, const void* h_lops,
+                     oqb_dense** out);
+int oqb_dense_destroy(oqb_dense* op);
+
+/* out[b] = Σ_i coefH[b][i] m_i                      — (h::DenseHamiltonian)(s), :60-66          */
+int oqb_dense_hamiltonian(oqb_dense* op, int nb, const double* h_coefH, int coef_shared, void* d_out);
+/* cache[b] = Σ_i (-i coefH[b][i]) m_i − ½ Σ_k gamma[b][k] L_k'L_k   (OVERWRITES)
+ *   — update_cache!(cache, H::DenseHamiltonian, p, s) :71-76 followed by
+ *     update_cache!(cache, lind::LindbladLiouvillian, p, t) src/opensys/lindblad.jl:103-109,
+ *     i.e. update_cache!(cache, Op::DiffEqLiouvillian{false,false}, p, t)
+ *     src/opensys/diffeq_liouvillian.jl:78-83.  h_gamma may be NULL (Hamiltonian only). */
+int oqb_dense_update_cache(oqb_dense* op, int nb, const double* h_coefH, int coef_shared,
+                           const double* h_gamma, int gamma_shared, void* d_cache);
+/* cache[b] (n²×n²) = i(H'ᵀ⊗I − I⊗H)                — update_vectorized_cache! :78-82          */
+int oqb_dense_update_vectorized_cache(oqb_dense* op, int nb, const double* h_coefH, int coef_shared,
+                                      void* d_cache);
+/* du[b] = −i[H(s_b),u[b]] + Σ_k γ_k (L_k u L_k' − ½{L_k'L_k,u})     (OVERWRITES du)
+ *   — (Op::DiffEqLiouvillian{false,false})(du,u,p,t) src/opensys/diffeq_liouvillian.jl:70-76 =
+ *     (h::DenseHamiltonian)(du,u,p,s) :84-89 + (Lind::LindbladLiouvillian)(du,u,p,t)
+ *     src/opensys/lindblad.jl:94-101.  h_gamma NULL ⇒ commutator only. */
+int oqb_dense_rhs(oqb_dense* op, int nb, const double* h_coefH, int coef_shared,
+                  const double* h_gamma, int gamma_shared, const void* d_u, void* d_du);
+/* same, with HOST state buffers (pinned or pageable); chunks are pipelined H2D→RHS→D2H. */
+int oqb_dense_rhs_host(oqb_dense* op, int nb, const double* h_coefH, int coef_shared,
+                       const double* h_gamma, int gamma_shared, const void* h_u, void* h_du);
+/* du[b] += Σ_k γ_k (L_k u L_k' − ½{L_k'L_k,u})      (ACCUMULATES) — src/opensys/lindblad.jl:94 */
+int oqb_lindblad_acc(oqb_dense* op, int nb, const double* h_gamma, int gamma_shared,
+                     const void* d_u, void* d_du);
+/* du[b] −= K₂+K₂', K₂ = S_α Λ_α u − Λ_α u S_α summed over α<K  (ACCUMULATES)
+ *   — the ρ-dependent half of (R::RedfieldLiouvillian)(du,u,p,t) src/opensys/redfield.jl:65-68.
+ *   d_S: K n×n coupling matrices (shared, or nb×K when S_shared==0); d_Lambda: nb×K n×n. */
+int oqb_redfield_apply_acc(oqb_ctx* ctx, int n, int K, const void* d_S, int S_shared,
+                           const void* d_Lambda, int nb, const void* d_u, void* d_du);
+/* cache[b] (n²×n²) −= I⊗SΛ + conj(SΛ)⊗I − Sᵀ⊗Λ − conj(Λ)⊗S   (ACCUMULATES)
+ *   — update_vectorized_cache!(cache, R::RedfieldLiouvillian, p, t) src/opensys/redfield.jl:97-102 */
+int oqb_redfield_vectorized_acc(oqb_ctx* ctx, int n, int K, const void* d_S, int S_shared,
+                                const void* d_Lambda, int nb, void* d_cache);
+
+/* ------------------------------------------ eigenbasis Liouvillian: DiffEqLiouvillian{true,·} */
+/* n: Hilbert dimension; lvl: kept levels (src/opensys/diffeq_liouvillian.jl:45-54);
+ * h_couplings: K coupling matrices A_α (n×n, unit-scaled, src/coupling/coupling.jl:42,66). */
+int oqb_ame_create(oqb_ctx* ctx, int n, int lvl, int K, const void* h_couplings, oqb_ame** out);
+int oqb_ame_destroy(oqb_ame* ame);
+/* (w, v) exactly as haml_eigs returned them on the host (src/hamiltonian/hamiltonian_base.jl:155);
+ * h_v NULL ⇒ adiabatic frame (v = I, n == lvl).  Rotates the couplings on the device
+ * (src/opensys/davies.jl:24). */
+int oqb_ame_set_eigen(oqb_ame* ame, const double* h_w, const void* h_v);
+/* Davies generator tables (src/opensys/davies.jl:21-47, closed form of SURVEY App. A.5):
+ *  h_gam[a+b*lvl] = γ(ω̃_ab), h_S[a+b*lvl] = S(ω̃_ab) at the signed ROUNDED gaps of GapIndices
+ *  (src/opensys/opensys_util.jl:25-61; 0 inside the zero group), evaluated by the host closures.
+ *  Cross terms of non-singleton gap groups: ncross entries (a,b,a2,b2) 0-based int32 quadruples
+ *  with rate h_cross_rate, meaning du[a,a2] += rate·Σ_α A_α[a,b]·conj(A_α[a2,b2])·ρ[b,b2];
+ *  nlamb entries (a,b,b2) with (rate,S) meaning (L'L)[b,b2] gets conj(A[a,b])A[a,b2]. */
+int oqb_ame_set_davies(oqb_ame* ame, const double* h_gam, const double* h_S, int64_t ncross,
+                       const int32_t* h_cross_idx, const double* h_cross_rate, int64_t nlamb,
+                       const int32_t* h_lamb_idx, const double* h_lamb_rate_S);
+int oqb_ame_clear_davies(oqb_ame* ame);
+/* One-sided AME (src/opensys/davies.jl:367-379): npairs (α,β) 0-based; tables at the UNROUNDED
+ * gap matrix ω_ba[i,j] = w[j]−w[i] (src/opensys/opensys_util.jl:65): h_gam/h_S are lvl×lvl per pair,
+ * or one shared table when tables_shared != 0 (SingleFunctionMatrix). */
+int oqb_ame_set_onesided(oqb_ame* ame, int npairs, const int32_t* h_alpha, const int32_t* h_beta,
+                         const double* h_gam, const double* h_S, int tables_shared);
+int oqb_ame_clear_onesided(oqb_ame* ame);
+/* du[b] = v·( −i[diag w, ρ̃] + Σ eigenbasis terms(ρ̃) )·v',  ρ̃ = v' u[b] v   (OVERWRITES du)
+ *   — (Op::DiffEqLiouvillian{true,false})(du,u,p,t) src/opensys/diffeq_liouvillian.jl:92-105.
+ *   Non-eigenbasis terms (:106-108) are added by the caller with oqb_lindblad_acc. */
+int oqb_ame_rhs(oqb_ame* ame, int nb, const void* d_u, void* d_du);
+int oqb_ame_rhs_host(oqb_ame* ame, int nb, const void* h_u, void* h_du);
+/* eigenbasis terms only, on ρ̃ given in the eigenbasis (ACCUMULATES into du):
+ *   (D::DaviesGenerator)(du,ρ,gap_idx,v,s) src/opensys/davies.jl:21 /
+ *   (A::OneSidedAMELiouvillian)(dρ,ρ,g_idx,v,s) :367; with_hamiltonian adds −i[diag w,ρ̃]. */
+int oqb_ame_eig_acc(oqb_ame* ame, int nb, const void* d_rho_eig, void* d_du_eig, int with_hamiltonian);
+/* cache (n×n) = v·(diag(−i w) − Σ_x (iS(x)+½γ(x)) L_x'L_x)·v'   (OVERWRITES)
+ *   — update_cache!(cache, Op::DiffEqLiouvillian{true,false}, p, t) :111-125 with
+ *     update_cache!(cache, D::DaviesGenerator, gap_idx, v, s) src/opensys/davies.jl:76-99. */
+int oqb_ame_update_cache(oqb_ame* ame, void* d_cache);
+
+/* ------------------------------------------- SparseHamiltonian + trajectories (ψ ensembles) */
+/* Terms and Lindblad operators as Julia SparseMatrixCSC{ComplexF64,Int64}: 1-based colptr
+ * (n+1) / rowval / nzval per matrix, concatenated; *_nnz_off[i] is the offset of matrix i in the
+ * concatenated rowval/nzval arrays (length count+1).  src/hamiltonian/sparse_hamiltonian.jl:10-37. */
+int oqb_sparse_create(oqb_ctx* ctx, int n, int nterms, const int64_t* h_colptr, const int64_t* h_rowval,
+                      const void* h_nzval, const int64_t* h_nnz_off, int K, const int64_t* h_l_colptr,
+                      const int64_t* h_l_rowval, const void* h_l_nzval, const int64_t* h_l_nnz_off,
+                      oqb_sparse** out);
+int oqb_sparse_destroy(oqb_sparse* sp);
+/* union sparsity pattern of the cache (src/hamiltonian/sparse_hamiltonian.jl:33-34) as CSC,
+ * 1-based, so Julia can wrap the value array in a SparseMatrixCSC: query nnz, then fetch. */
+int oqb_sparse_pattern_nnz(oqb_sparse* sp, int64_t* nnz);
+int oqb_sparse_pattern(oqb_sparse* sp, int64_t* h_colptr, int64_t* h_rowval);
+/* nzval[b] on the union pattern = Σ_i (-i coefH[b][i]) m_i − ½ Σ_k γ_k L_k'L_k   (OVERWRITES)
+ *   — update_cache!(cache, H::SparseHamiltonian, p, s) :70-75 + src/opensys/lindblad.jl:103-109 */
+int oqb_sparse_update_cache(oqb_sparse* sp, int nb, const double* h_coefH, int coef_shared,
+                            const double* h_gamma, int gamma_shared, void* d_nzval);
+/* du[b] = −i(H u[b] − u[b] H)  (OVERWRITES)  — (h::SparseHamiltonian)(du,u,p,s) :83-91 */
+int oqb_sparse_commutator(oqb_sparse* sp, int nb, const double* h_coefH, int coef_shared,
+                          const void* d_u, void* d_du);
+/* dψ[b] = (−iH(s_b) − ½Σ_k γ_k L_k'L_k) ψ[b]  — the `cache*u` matvec the external solver performs
+ *   with the cache of src/opensys/diffeq_liouvillian.jl:78-83. */
+int oqb_traj_matvec(oqb_sparse* sp, int nb, const double* h_coefH, int coef_shared,
+                    const double* h_gamma, int gamma_shared, const void* d_psi, void* d_dpsi);
+int oqb_traj_matvec_host(oqb_sparse* sp, int nb, const double* h_coefH, int coef_shared,
+                         const double* h_gamma, int gamma_shared, const void* h_psi, void* h_dpsi);
+/* out[b] = ‖ψ[b]‖²  (jump condition of the external callback) */
+int oqb_traj_norm2(oqb_sparse* sp, int nb, const void* d_psi, double* d_out);
+/* lind_jump / lindblad_jump{false,false}: prob[b][k] = γ_k‖L_k ψ[b]‖² (src/opensys/trajectory_jump.jl:2-12),
+ * choice[b] by StatsBase's inverse-CDF scan with the supplied uniform d_uniform[b];
+ * d_mask (may be NULL) selects which members jump; apply != 0 additionally does
+ * ψ ← L_kψ/‖L_kψ‖ in place (what the external affect! does). */
+int oqb_traj_jump(oqb_sparse* sp, int nb, const double* h_gamma, int gamma_shared, void* d_psi,
+                  const double* d_uniform, const uint8_t* d_mask, int32_t* d_choice, double* d_prob,
+                  int apply);
+
+/* ------------------------------------------------------------------------- observables ----- */
+/* out[b][o] = tr(O_o ρ[b]) (is_vector==0, state n×n) or ψ[b]'O_oψ[b] (is_vector!=0); complex
+ * (re,im) pairs; d_obs: nobs dense n×n matrices.  Partial sums for the NCCL ensemble average. */
+int oqb_expect(oqb_ctx* ctx, int n, int nobs, const void* d_obs, int nb, const void* d_state,
+               int is_vector, double* d_out);
+
+/* ------------------------------------------------------------------------------ probes ----- */
+/* Measures FP64 DMMA / DFMA issue throughput of this device (TFLOP/s) — used by bench.py to state
+ * the FP64 tensor ceiling next to the cuBLAS DGEMM figure. */
+int oqb_probe_fp64(oqb_ctx* ctx, double* dmma_tflops, double* dfma_tflops);
+/* Per-launch CUDA-event timing of the ZGEMM kernel (the dominant kernel of every dense path) on the
+ * context stream: between begin and end every ZGEMM launch is bracketed by an event pair;
+ * end returns the summed kernel time, the launch count and the algorithmic flops (8·M·N·K·batch). */
+int oqb_profile_begin(oqb_ctx* ctx);
+int oqb_profile_end(oqb_ctx* ctx, double* zgemm_ms, uint64_t* zgemm_launches, double* zgemm_flops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OQB_H */

@@ -1,0 +1,101 @@
+"""ctypes binding of liboqb_b200.so (the C ABI declared in include/oqb.h).
+
+There is no CPU fallback: importing this module without the built library, or creating a
+context without a B200, raises.
+"""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "liboqb_b200.so")
+
+c_void_p, c_int, c_i64, c_size_t = C.c_void_p, C.c_int, C.c_int64, C.c_size_t
+c_dp = C.POINTER(C.c_double)
+c_i32p = C.POINTER(C.c_int32)
+c_i64p = C.POINTER(C.c_int64)
+c_u8p = C.POINTER(C.c_uint8)
+
+# name -> argtypes (restype is int unless listed in _RESTYPE); mirrors include/oqb.h 1:1
+SIGNATURES = {
+    "oqb_version": [],
+    "oqb_create": [c_int, C.POINTER(c_void_p)],
+    "oqb_destroy": [c_void_p],
+    "oqb_last_error": [c_void_p],
+    "oqb_sync": [c_void_p],
+    "oqb_set_stream": [c_void_p, c_void_p],
+    "oqb_get_stream": [c_void_p, C.POINTER(c_void_p)],
+    "oqb_launch_count": [c_void_p, C.POINTER(C.c_uint64)],
+    "oqb_malloc": [c_void_p, c_size_t, C.POINTER(c_void_p)],
+    "oqb_free": [c_void_p, c_void_p],
+    "oqb_malloc_host": [c_void_p, c_size_t, C.POINTER(c_void_p)],
+    "oqb_free_host": [c_void_p, c_void_p],
+    "oqb_upload": [c_void_p, c_void_p, c_void_p, c_size_t],
+    "oqb_download": [c_void_p, c_void_p, c_void_p, c_size_t],
+    "oqb_zgemm_batched": [c_void_p, c_int, c_int, c_int, c_int, c_int, c_dp, c_void_p, c_i64, c_i64, c_void_p,
+                          c_i64, c_i64, c_dp, c_void_p, c_i64, c_i64, c_int],
+    "oqb_dense_create": [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, C.POINTER(c_void_p)],
+    "oqb_dense_destroy": [c_void_p],
+    "oqb_dense_hamiltonian": [c_void_p, c_int, c_dp, c_int, c_void_p],
+    "oqb_dense_update_cache": [c_void_p, c_int, c_dp, c_int, c_dp, c_int, c_void_p],
+    "oqb_dense_update_vectorized_cache": [c_void_p, c_int, c_dp, c_int, c_void_p],
+    "oqb_dense_rhs": [c_void_p, c_int, c_dp, c_int, c_dp, c_int, c_void_p, c_void_p],
+    "oqb_dense_rhs_host": [c_void_p, c_int, c_dp, c_int, c_dp, c_int, c_void_p, c_void_p],
+    "oqb_lindblad_acc": [c_void_p, c_int, c_dp, c_int, c_void_p, c_void_p],
+    "oqb_redfield_apply_acc": [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p],
+    "oqb_redfield_vectorized_acc": [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p],
+    "oqb_ame_create": [c_void_p, c_int, c_int, c_int, c_void_p, C.POINTER(c_void_p)],
+    "oqb_ame_destroy": [c_void_p],
+    "oqb_ame_set_eigen": [c_void_p, c_dp, c_void_p],
+    "oqb_ame_set_davies": [c_void_p, c_dp, c_dp, c_i64, c_i32p, c_dp, c_i64, c_i32p, c_dp],
+    "oqb_ame_clear_davies": [c_void_p],
+    "oqb_ame_set_onesided": [c_void_p, c_int, c_i32p, c_i32p, c_dp, c_dp, c_int],
+    "oqb_ame_clear_onesided": [c_void_p],
+    "oqb_ame_rhs": [c_void_p, c_int, c_void_p, c_void_p],
+    "oqb_ame_rhs_host": [c_void_p, c_int, c_void_p, c_void_p],
+    "oqb_ame_eig_acc": [c_void_p, c_int, c_void_p, c_void_p, c_int],
+    "oqb_ame_update_cache": [c_void_p, c_void_p],
+    "oqb_sparse_create": [c_void_p, c_int, c_int, c_i64p, c_i64p, c_void_p, c_i64p, c_int, c_i64p, c_i64p, c_void_p,
+                          c_i64p, C.POINTER(c_void_p)],
+    "oqb_sparse_destroy": [c_void_p],
+    "oqb_sparse_pattern_nnz": [c_void_p, c_i64p],
+    "oqb_sparse_pattern": [c_void_p, c_i64p, c_i64p],
+    "oqb_sparse_update_cache": [c_void_p, c_int, c_dp, c_int, c_dp, c_int, c_void_p],
+    "oqb_sparse_commutator": [c_void_p, c_int, c_dp, c_int, c_void_p, c_void_p],
+    "oqb_traj_matvec": [c_void_p, c_int, c_dp, c_int, c_dp, c_int, c_void_p, c_void_p],
+    "oqb_traj_matvec_host": [c_void_p, c_int, c_dp, c_int, c_dp, c_int, c_void_p, c_void_p],
+    "oqb_traj_norm2": [c_void_p, c_int, c_void_p, c_void_p],
+    "oqb_traj_jump": [c_void_p, c_int, c_dp, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int],
+    "oqb_expect": [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p],
+    "oqb_probe_fp64": [c_void_p, c_dp, c_dp],
+    "oqb_profile_begin": [c_void_p],
+    "oqb_profile_end": [c_void_p, c_dp, C.POINTER(C.c_uint64), c_dp],
+}
+_RESTYPE = {"oqb_last_error": C.c_char_p}
+
+_lib = None
+
+
+class OQBError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the shared library (raises if it has not been built — no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise OQBError(f"{LIB_PATH} is missing: run `python __graft_entry__.py` (build()) first; "
+                       "this package has no CPU fallback")
+    lib = C.CDLL(LIB_PATH)
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if include/oqb.h and the .so disagree
+        fn.argtypes = argtypes
+        fn.restype = _RESTYPE.get(name, c_int)
+    _lib = lib
+    return lib
+
+
+def dptr(a):
+    """double* view of a C-contiguous float64 numpy array (or None)."""
+    return None if a is None else a.ctypes.data_as(c_dp)

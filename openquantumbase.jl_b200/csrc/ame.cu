@@ -1,0 +1,415 @@
+// Eigenbasis Liouvillian: DiffEqLiouvillian{true,false} with DaviesGenerator and/or
+// OneSidedAMELiouvillian terms (reference src/opensys/diffeq_liouvillian.jl:92-128,
+// src/opensys/davies.jl:21-99, :356-393).  Host orchestration of zgemm.cu + elementwise.cu.
+//
+// Davies uses the closed form of SURVEY App. A.5 (algebraically identical to the reference's
+// per-gap-group loop):   X = C∘ρ̃ + diag(W·diag ρ̃) + cross terms of non-singleton gap groups.
+#include <cstring>
+#include <vector>
+
+#include "../../include/oqb.h"
+#include "common.cuh"
+
+using namespace oqb;
+
+struct oqb_ame {
+    oqb_ctx* ctx = nullptr;
+    int n = 0, lvl = 0, K = 0;
+    bool has_v = false, have_eigen = false;
+    c128* d_coup = nullptr;  // K n×n couplings as given
+    c128* d_V = nullptr;     // n × lvl
+    double* d_w = nullptr;   // lvl
+    c128* d_A = nullptr;     // K lvl×lvl rotated couplings v' A v
+    c128* d_Cm = nullptr;    // lvl×lvl Hadamard coefficients (always includes −i(w_a−w_b))
+    // Davies
+    bool davies = false;
+    double *d_gam = nullptr, *d_S = nullptr, *d_Gam = nullptr, *d_hls = nullptr, *d_Wt = nullptr;
+    long long ncross = 0, nlamb = 0;
+    int32_t* d_cross_idx = nullptr;
+    double* d_cross_rate = nullptr;
+    c128* d_Moff = nullptr;  // dense lvl×lvl off-diagonal part of −½G − iH_LS (nullptr when empty)
+    // one-sided AME
+    int npairs = 0;
+    std::vector<int32_t> h_beta;
+    c128* d_Lam = nullptr;  // npairs lvl×lvl
+};
+
+namespace {
+
+const size_t kAmeBudget = (size_t)3 << 30;
+
+template <class T>
+void dfree(T*& p) {
+    if (p) cudaFree(p);
+    p = nullptr;
+}
+
+int dalloc(oqb_ctx* c, void** p, size_t bytes) {
+    cudaError_t e = cudaMalloc(p, bytes ? bytes : 16);
+    if (e != cudaSuccess) return set_error(c, OQB_ENOMEM, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+    return 0;
+}
+
+bool needs_general_path(const oqb_ame* a) { return a->ncross > 0 || a->d_Moff || a->npairs > 0; }
+
+// Eigenbasis terms on ρ̃ = R (lvl×lvl per member).  overwrite: X = …, else X += ….
+// with_h: include −i[diag w, ρ̃].  scratch: (1 + 2*(npairs>0)) · nb·l² + nb·l complex.
+int eig_apply(oqb_ame* a, int nb, const c128* R, c128* X, bool overwrite, bool with_h, c128* scratch) {
+    oqb_ctx* c = a->ctx;
+    const int l = a->lvl;
+    const long long ll = (long long)l * l;
+    OQB_TRY(hadamard(c, l, a->d_Cm, with_h ? nullptr : a->d_w, R, X, nb, !overwrite));
+    c128* pop = scratch;
+    c128* M1 = scratch + (size_t)nb * l;
+    c128* Kb = M1 + (size_t)nb * ll;
+    if (a->davies) {
+        OQB_TRY(extract_diag(c, l, R, pop, nb));
+        OQB_TRY(davies_diag(c, l, a->d_Wt, pop, X, nb));
+        OQB_TRY(davies_cross(c, l, a->K, a->d_A, a->ncross, a->d_cross_idx, a->d_cross_rate, R, X, nb));
+        if (a->d_Moff) {
+            ZgemmParams p;  // X += Moff R
+            p.M = p.N = p.K = l; p.batch = nb;
+            p.A = a->d_Moff; p.lda = l; p.strideA = 0;
+            p.B = R; p.ldb = l; p.strideB = ll;
+            p.C = X; p.ldc = l; p.strideC = ll;
+            p.beta = make_double2(1.0, 0.0);
+            OQB_TRY(zgemm(c, p));
+            ZgemmParams q;  // X += R Moff'
+            q.M = q.N = q.K = l; q.batch = nb;
+            q.A = R; q.lda = l; q.strideA = ll;
+            q.B = a->d_Moff; q.ldb = l; q.strideB = 0; q.opB = OP_C;
+            q.C = X; q.ldc = l; q.strideC = ll;
+            q.beta = make_double2(1.0, 0.0);
+            OQB_TRY(zgemm(c, q));
+        }
+    }
+    for (int pidx = 0; pidx < a->npairs; ++pidx) {  // src/opensys/davies.jl:369-378
+        const c128* Lam = a->d_Lam + (long long)pidx * ll;
+        const c128* Ab = a->d_A + (long long)a->h_beta[pidx] * ll;
+        ZgemmParams p;  // M1 = Λ ρ̃
+        p.M = p.N = p.K = l; p.batch = nb;
+        p.A = Lam; p.lda = l; p.strideA = 0;
+        p.B = R; p.ldb = l; p.strideB = ll;
+        p.C = M1; p.ldc = l; p.strideC = ll;
+        OQB_TRY(zgemm(c, p));
+        ZgemmParams q = p;  // Kb = A_β M1
+        q.A = Ab; q.B = M1; q.C = Kb;
+        OQB_TRY(zgemm(c, q));
+        ZgemmParams r;  // Kb −= M1 A_β
+        r.M = r.N = r.K = l; r.batch = nb;
+        r.A = M1; r.lda = l; r.strideA = ll;
+        r.B = Ab; r.ldb = l; r.strideB = 0;
+        r.C = Kb; r.ldc = l; r.strideC = ll;
+        r.alpha = make_double2(-1.0, 0.0);
+        r.beta = make_double2(1.0, 0.0);
+        OQB_TRY(zgemm(c, r));
+        OQB_TRY(add_adjoint(c, l, 1, -1.0, Kb, X, nb));  // dρ −= K₂ + K₂'
+    }
+    return 0;
+}
+
+size_t eig_scratch_elems(const oqb_ame* a, int nb) {
+    const size_t ll = (size_t)a->lvl * a->lvl;
+    return (size_t)nb * a->lvl + (a->npairs > 0 ? 2 * (size_t)nb * ll : 0);
+}
+
+int ame_rhs_impl(oqb_ame* a, int nb, const c128* u, c128* du) {
+    oqb_ctx* c = a->ctx;
+    if (nb <= 0) return 0;
+    if (!a->have_eigen) return set_error(c, OQB_EINVAL, "oqb_ame_rhs: call oqb_ame_set_eigen first");
+    if (!u || !du) return set_error(c, OQB_EINVAL, "oqb_ame_rhs: null state pointer");
+    const int n = a->n, l = a->lvl;
+    const long long nn = (long long)n * n, ll = (long long)l * l, ln = (long long)l * n;
+    const bool general = needs_general_path(a);
+    // per-member scratch: T (l×n) + X (l×l) [+ R (l×l)] + eig scratch
+    const size_t per = ((size_t)ln + ll + (general ? ll : 0) + eig_scratch_elems(a, 1)) * sizeof(c128);
+    int chunk = (int)(kAmeBudget / per);
+    if (chunk < 1) chunk = 1;
+    if (chunk > nb) chunk = nb;
+    OQB_TRY(ws_reserve(c, (size_t)chunk * per));
+    c128* T = (c128*)c->ws;
+    c128* X = T + (size_t)chunk * ln;
+    c128* R = X + (size_t)chunk * ll;
+    c128* scratch = general ? R + (size_t)chunk * ll : R;
+
+    for (int b0 = 0; b0 < nb; b0 += chunk) {
+        const int cnt = nb - b0 < chunk ? nb - b0 : chunk;
+        const c128* ub = u + (long long)b0 * nn;
+        c128* dub = du + (long long)b0 * nn;
+        if (!a->has_v) {
+            // adiabatic frame: v = I, ρ̃ = u   (src/opensys/diffeq_liouvillian.jl:130-140 with diagonal H)
+            OQB_TRY(eig_apply(a, cnt, ub, dub, true, true, scratch));
+            continue;
+        }
+        ZgemmParams p;  // T = v' u            (l × n)
+        p.M = l; p.N = n; p.K = n; p.batch = cnt;
+        p.opA = OP_C;
+        p.A = a->d_V; p.lda = n; p.strideA = 0;
+        p.B = ub; p.ldb = n; p.strideB = nn;
+        p.C = T; p.ldc = l; p.strideC = ln;
+        OQB_TRY(zgemm(c, p));
+        ZgemmParams q;  // ρ̃ = T v            (l × l)
+        q.M = l; q.N = l; q.K = n; q.batch = cnt;
+        q.A = T; q.lda = l; q.strideA = ln;
+        q.B = a->d_V; q.ldb = n; q.strideB = 0;
+        q.ldc = l; q.strideC = ll;
+        if (!general) {
+            // fused: X = C∘ρ̃ in the GEMM epilogue, diagonal of ρ̃ captured for the W·pop term
+            q.C = X;
+            q.E = a->d_Cm; q.lde = l; q.strideE = 0;
+            if (a->davies) { q.diag_out = scratch; q.strideDiag = l; }
+            OQB_TRY(zgemm(c, q));
+            if (a->davies) OQB_TRY(davies_diag(c, l, a->d_Wt, scratch, X, cnt));
+        } else {
+            q.C = R;
+            OQB_TRY(zgemm(c, q));
+            OQB_TRY(eig_apply(a, cnt, R, X, true, true, scratch));
+        }
+        ZgemmParams r;  // T = X v'           (l × n)
+        r.M = l; r.N = n; r.K = l; r.batch = cnt;
+        r.A = X; r.lda = l; r.strideA = ll;
+        r.B = a->d_V; r.ldb = n; r.strideB = 0; r.opB = OP_C;
+        r.C = T; r.ldc = l; r.strideC = ln;
+        OQB_TRY(zgemm(c, r));
+        ZgemmParams s;  // du = v T           (n × n), OVERWRITES  (diffeq_liouvillian.jl:105)
+        s.M = n; s.N = n; s.K = l; s.batch = cnt;
+        s.A = a->d_V; s.lda = n; s.strideA = 0;
+        s.B = T; s.ldb = l; s.strideB = ln;
+        s.C = dub; s.ldc = n; s.strideC = nn;
+        OQB_TRY(zgemm(c, s));
+    }
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int oqb_ame_create(oqb_ctx* c, int n, int lvl, int K, const void* h_couplings, oqb_ame** out) {
+    if (!c || !out) return OQB_EINVAL;
+    *out = nullptr;
+    if (n <= 0 || lvl <= 0 || lvl > n || K < 0 || (K > 0 && !h_couplings))
+        return set_error(c, OQB_EINVAL, "oqb_ame_create: bad arguments (n=%d lvl=%d K=%d)", n, lvl, K);
+    oqb_ame* a = new oqb_ame();
+    a->ctx = c; a->n = n; a->lvl = lvl; a->K = K;
+    const size_t nn = (size_t)n * n, ll = (size_t)lvl * lvl;
+    int s = dalloc(c, (void**)&a->d_coup, (K + 1) * nn * sizeof(c128));
+    if (!s) s = dalloc(c, (void**)&a->d_V, (size_t)n * lvl * sizeof(c128));
+    if (!s) s = dalloc(c, (void**)&a->d_w, lvl * sizeof(double));
+    if (!s) s = dalloc(c, (void**)&a->d_A, (K + 1) * ll * sizeof(c128));
+    if (!s) s = dalloc(c, (void**)&a->d_Cm, ll * sizeof(c128));
+    if (s) { oqb_ame_destroy(a); return s; }
+    if (K) {
+        OQB_CUDA(c, cudaMemcpyAsync(a->d_coup, h_couplings, K * nn * sizeof(c128), cudaMemcpyHostToDevice, c->stream));
+        OQB_CUDA(c, cudaStreamSynchronize(c->stream));
+    }
+    *out = a;
+    return OQB_OK;
+}
+
+int oqb_ame_clear_davies(oqb_ame* a) {
+    cudaStreamSynchronize(a->ctx->stream);
+    dfree(a->d_gam); dfree(a->d_S); dfree(a->d_Gam); dfree(a->d_hls); dfree(a->d_Wt);
+    dfree(a->d_cross_idx); dfree(a->d_cross_rate); dfree(a->d_Moff);
+    a->davies = false; a->ncross = a->nlamb = 0;
+    if (a->have_eigen)  // Hamiltonian-only Hadamard coefficients
+        return davies_tables(a->ctx, a->lvl, a->K, a->d_A, nullptr, nullptr, a->d_w, 0, nullptr, nullptr, nullptr, a->d_Cm);
+    return 0;
+}
+
+int oqb_ame_clear_onesided(oqb_ame* a) {
+    cudaStreamSynchronize(a->ctx->stream);
+    dfree(a->d_Lam);
+    a->npairs = 0;
+    a->h_beta.clear();
+    return 0;
+}
+
+int oqb_ame_destroy(oqb_ame* a) {
+    if (!a) return OQB_OK;
+    bool he = a->have_eigen;
+    a->have_eigen = false;
+    oqb_ame_clear_davies(a);
+    oqb_ame_clear_onesided(a);
+    (void)he;
+    dfree(a->d_coup); dfree(a->d_V); dfree(a->d_w); dfree(a->d_A); dfree(a->d_Cm);
+    delete a;
+    return OQB_OK;
+}
+
+int oqb_ame_set_eigen(oqb_ame* a, const double* h_w, const void* h_v) {
+    oqb_ctx* c = a->ctx;
+    if (!h_w) return set_error(c, OQB_EINVAL, "oqb_ame_set_eigen: null w");
+    const int n = a->n, l = a->lvl, K = a->K;
+    const long long nn = (long long)n * n, ll = (long long)l * l, ln = (long long)l * n;
+    if (!h_v && l != n) return set_error(c, OQB_EINVAL, "oqb_ame_set_eigen: adiabatic frame needs lvl == n");
+    // tables of a previous eigen-system are stale
+    a->have_eigen = false;
+    OQB_TRY(oqb_ame_clear_davies(a));
+    OQB_TRY(oqb_ame_clear_onesided(a));
+    OQB_CUDA(c, cudaMemcpyAsync(a->d_w, h_w, l * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    a->has_v = h_v != nullptr;
+    if (a->has_v) {
+        OQB_CUDA(c, cudaMemcpyAsync(a->d_V, h_v, (size_t)ln * sizeof(c128), cudaMemcpyHostToDevice, c->stream));
+        if (K) {  // A_α = v' c_α v   (src/opensys/davies.jl:24)
+            OQB_TRY(ws_reserve(c, (size_t)K * ln * sizeof(c128)));
+            c128* T = (c128*)c->ws;
+            ZgemmParams p;  // T_α = c_α v   (n × l)
+            p.M = n; p.N = l; p.K = n; p.batch = K;
+            p.A = a->d_coup; p.lda = n; p.strideA = nn;
+            p.B = a->d_V; p.ldb = n; p.strideB = 0;
+            p.C = T; p.ldc = n; p.strideC = ln;
+            OQB_TRY(zgemm(c, p));
+            ZgemmParams q;  // A_α = v' T_α  (l × l)
+            q.M = l; q.N = l; q.K = n; q.batch = K;
+            q.opA = OP_C;
+            q.A = a->d_V; q.lda = n; q.strideA = 0;
+            q.B = T; q.ldb = n; q.strideB = ln;
+            q.C = a->d_A; q.ldc = l; q.strideC = ll;
+            OQB_TRY(zgemm(c, q));
+        }
+    } else if (K) {
+        OQB_CUDA(c, cudaMemcpyAsync(a->d_A, a->d_coup, (size_t)K * nn * sizeof(c128), cudaMemcpyDeviceToDevice, c->stream));
+    }
+    OQB_CUDA(c, cudaStreamSynchronize(c->stream));  // h_w / h_v may be reused by the caller
+    a->have_eigen = true;
+    return davies_tables(c, l, K, a->d_A, nullptr, nullptr, a->d_w, 0, nullptr, nullptr, nullptr, a->d_Cm);
+}
+
+int oqb_ame_set_davies(oqb_ame* a, const double* h_gam, const double* h_S, int64_t ncross, const int32_t* h_cross_idx,
+                       const double* h_cross_rate, int64_t nlamb, const int32_t* h_lamb_idx,
+                       const double* h_lamb_rate_S) {
+    oqb_ctx* c = a->ctx;
+    if (!a->have_eigen) return set_error(c, OQB_EINVAL, "oqb_ame_set_davies: call oqb_ame_set_eigen first");
+    if (!h_gam || !h_S) return set_error(c, OQB_EINVAL, "oqb_ame_set_davies: null table");
+    if ((ncross > 0 && (!h_cross_idx || !h_cross_rate)) || (nlamb > 0 && (!h_lamb_idx || !h_lamb_rate_S)))
+        return set_error(c, OQB_EINVAL, "oqb_ame_set_davies: null cross-term arrays");
+    OQB_TRY(oqb_ame_clear_davies(a));
+    const int l = a->lvl;
+    const size_t ll = (size_t)l * l;
+    OQB_TRY(dalloc(c, (void**)&a->d_gam, ll * sizeof(double)));
+    OQB_TRY(dalloc(c, (void**)&a->d_S, ll * sizeof(double)));
+    OQB_TRY(dalloc(c, (void**)&a->d_Gam, l * sizeof(double)));
+    OQB_TRY(dalloc(c, (void**)&a->d_hls, l * sizeof(double)));
+    OQB_TRY(dalloc(c, (void**)&a->d_Wt, ll * sizeof(double)));
+    OQB_CUDA(c, cudaMemcpyAsync(a->d_gam, h_gam, ll * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    OQB_CUDA(c, cudaMemcpyAsync(a->d_S, h_S, ll * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    OQB_TRY(davies_tables(c, l, a->K, a->d_A, a->d_gam, a->d_S, a->d_w, 1, a->d_Gam, a->d_hls, a->d_Wt, a->d_Cm));
+    if (ncross > 0) {
+        OQB_TRY(dalloc(c, (void**)&a->d_cross_idx, (size_t)ncross * 4 * sizeof(int32_t)));
+        OQB_TRY(dalloc(c, (void**)&a->d_cross_rate, (size_t)ncross * sizeof(double)));
+        OQB_CUDA(c, cudaMemcpyAsync(a->d_cross_idx, h_cross_idx, (size_t)ncross * 4 * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+        OQB_CUDA(c, cudaMemcpyAsync(a->d_cross_rate, h_cross_rate, (size_t)ncross * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        a->ncross = ncross;
+    }
+    if (nlamb > 0) {
+        OQB_TRY(dalloc(c, (void**)&a->d_Moff, ll * sizeof(c128)));
+        OQB_CUDA(c, cudaMemsetAsync(a->d_Moff, 0, ll * sizeof(c128), c->stream));
+        int32_t* d_idx = nullptr;
+        double* d_rs = nullptr;
+        OQB_TRY(dalloc(c, (void**)&d_idx, (size_t)nlamb * 3 * sizeof(int32_t)));
+        OQB_TRY(dalloc(c, (void**)&d_rs, (size_t)nlamb * 2 * sizeof(double)));
+        OQB_CUDA(c, cudaMemcpyAsync(d_idx, h_lamb_idx, (size_t)nlamb * 3 * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+        OQB_CUDA(c, cudaMemcpyAsync(d_rs, h_lamb_rate_S, (size_t)nlamb * 2 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        int s = davies_lamb_build(c, l, a->K, a->d_A, nlamb, d_idx, d_rs, a->d_Moff);
+        cudaStreamSynchronize(c->stream);
+        cudaFree(d_idx);
+        cudaFree(d_rs);
+        if (s) return s;
+        a->nlamb = nlamb;
+    }
+    OQB_CUDA(c, cudaStreamSynchronize(c->stream));
+    a->davies = true;
+    return 0;
+}
+
+int oqb_ame_set_onesided(oqb_ame* a, int npairs, const int32_t* h_alpha, const int32_t* h_beta, const double* h_gam,
+                         const double* h_S, int tables_shared) {
+    oqb_ctx* c = a->ctx;
+    if (!a->have_eigen) return set_error(c, OQB_EINVAL, "oqb_ame_set_onesided: call oqb_ame_set_eigen first");
+    if (npairs <= 0 || !h_alpha || !h_beta || !h_gam || !h_S) return set_error(c, OQB_EINVAL, "oqb_ame_set_onesided: bad arguments");
+    for (int p = 0; p < npairs; ++p)
+        if (h_alpha[p] < 0 || h_alpha[p] >= a->K || h_beta[p] < 0 || h_beta[p] >= a->K)
+            return set_error(c, OQB_EINVAL, "oqb_ame_set_onesided: coupling index out of range");
+    OQB_TRY(oqb_ame_clear_onesided(a));
+    const int l = a->lvl;
+    const size_t ll = (size_t)l * l;
+    const size_t nt = tables_shared ? 1 : (size_t)npairs;
+    double *d_g = nullptr, *d_s = nullptr;
+    int32_t* d_alpha = nullptr;
+    OQB_TRY(dalloc(c, (void**)&a->d_Lam, (size_t)npairs * ll * sizeof(c128)));
+    OQB_TRY(dalloc(c, (void**)&d_g, nt * ll * sizeof(double)));
+    OQB_TRY(dalloc(c, (void**)&d_s, nt * ll * sizeof(double)));
+    OQB_TRY(dalloc(c, (void**)&d_alpha, npairs * sizeof(int32_t)));
+    OQB_CUDA(c, cudaMemcpyAsync(d_g, h_gam, nt * ll * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    OQB_CUDA(c, cudaMemcpyAsync(d_s, h_S, nt * ll * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    OQB_CUDA(c, cudaMemcpyAsync(d_alpha, h_alpha, npairs * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+    int s = onesided_lambda(c, l, npairs, d_alpha, a->d_A, d_g, d_s, tables_shared ? 0 : (long long)ll, a->d_Lam);
+    cudaStreamSynchronize(c->stream);
+    cudaFree(d_g); cudaFree(d_s); cudaFree(d_alpha);
+    if (s) return s;
+    a->npairs = npairs;
+    a->h_beta.assign(h_beta, h_beta + npairs);
+    return 0;
+}
+
+int oqb_ame_rhs(oqb_ame* a, int nb, const void* d_u, void* d_du) {
+    return ame_rhs_impl(a, nb, (const c128*)d_u, (c128*)d_du);
+}
+
+int oqb_ame_rhs_host(oqb_ame* a, int nb, const void* h_u, void* h_du) {
+    oqb_ctx* c = a->ctx;
+    const size_t bytes = (size_t)a->n * a->n * sizeof(c128);
+    int chunk = (int)(((size_t)256 << 20) / bytes);
+    if (chunk < 1) chunk = 1;
+    return host_pipeline(c, nb, bytes, bytes, h_u, h_du, chunk, [&](int, int cnt, const void* din, void* dout) {
+        return ame_rhs_impl(a, cnt, (const c128*)din, (c128*)dout);
+    });
+}
+
+int oqb_ame_eig_acc(oqb_ame* a, int nb, const void* d_rho_eig, void* d_du_eig, int with_hamiltonian) {
+    oqb_ctx* c = a->ctx;
+    if (nb <= 0) return 0;
+    if (!a->have_eigen) return set_error(c, OQB_EINVAL, "oqb_ame_eig_acc: call oqb_ame_set_eigen first");
+    const size_t ll = (size_t)a->lvl * a->lvl;
+    const size_t per = (ll * 0 + eig_scratch_elems(a, 1)) * sizeof(c128);
+    int chunk = (int)(kAmeBudget / (per ? per : 1));
+    if (chunk < 1) chunk = 1;
+    if (chunk > nb) chunk = nb;
+    OQB_TRY(ws_reserve(c, (size_t)chunk * per + 16));
+    for (int b0 = 0; b0 < nb; b0 += chunk) {
+        const int cnt = nb - b0 < chunk ? nb - b0 : chunk;
+        OQB_TRY(eig_apply(a, cnt, (const c128*)d_rho_eig + (size_t)b0 * ll, (c128*)d_du_eig + (size_t)b0 * ll, false,
+                          with_hamiltonian != 0, (c128*)c->ws));
+    }
+    return 0;
+}
+
+int oqb_ame_update_cache(oqb_ame* a, void* d_cache) {
+    oqb_ctx* c = a->ctx;
+    if (!a->have_eigen) return set_error(c, OQB_EINVAL, "oqb_ame_update_cache: call oqb_ame_set_eigen first");
+    if (!d_cache) return set_error(c, OQB_EINVAL, "oqb_ame_update_cache: null cache");
+    const int n = a->n, l = a->lvl;
+    const long long ll = (long long)l * l, ln = (long long)l * n;
+    if (!a->has_v)
+        return davies_heff_diag(c, l, a->d_w, a->davies ? a->d_Gam : nullptr, a->davies ? a->d_hls : nullptr,
+                                a->d_Moff, (c128*)d_cache);
+    OQB_TRY(ws_reserve(c, (size_t)(ll + ln) * sizeof(c128)));
+    c128* D = (c128*)c->ws;
+    c128* T = D + ll;
+    OQB_TRY(davies_heff_diag(c, l, a->d_w, a->davies ? a->d_Gam : nullptr, a->davies ? a->d_hls : nullptr, a->d_Moff, D));
+    ZgemmParams p;  // T = D v'   (l × n)
+    p.M = l; p.N = n; p.K = l;
+    p.A = D; p.lda = l;
+    p.B = a->d_V; p.ldb = n; p.opB = OP_C;
+    p.C = T; p.ldc = l;
+    OQB_TRY(zgemm(c, p));
+    ZgemmParams q;  // cache = v T   (src/opensys/diffeq_liouvillian.jl:124)
+    q.M = n; q.N = n; q.K = l;
+    q.A = a->d_V; q.lda = n;
+    q.B = T; q.ldb = l;
+    q.C = (c128*)d_cache; q.ldc = n;
+    return zgemm(c, q);
+}
+
+}  // extern "C"

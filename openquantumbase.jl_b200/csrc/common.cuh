@@ -1,0 +1,179 @@
+// Shared declarations for the B200-native OpenQuantumBase RHS library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+namespace oqb {
+
+typedef double2 c128;  // interleaved (re, im) == Julia ComplexF64 == numpy complex128
+
+enum Op : int { OP_N = 0, OP_T = 1, OP_C = 2 };
+
+struct Ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    cudaStream_t copy_stream[2] = {nullptr, nullptr};
+    cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    std::string err;
+    uint64_t launches = 0;
+    // grow-only device workspace
+    void* ws = nullptr;
+    size_t ws_bytes = 0;
+    // pinned staging for small per-call coefficient arrays
+    void* pin = nullptr;
+    size_t pin_bytes = 0;
+    void* dcoef = nullptr;
+    size_t dcoef_bytes = 0;
+    size_t coef_head = 0;
+    // optional per-launch timing of the ZGEMM kernel (oqb_profile_begin / oqb_profile_end)
+    bool profiling = false;
+    std::vector<cudaEvent_t> prof_events;  // pairs (start, stop)
+    double prof_flops = 0.0;
+    // grow-only device staging for the *_host entry points (double-buffered u / du chunks)
+    void* io = nullptr;
+    size_t io_bytes = 0;
+};
+
+int set_error(Ctx* c, int code, const char* fmt, ...);
+int ws_reserve(Ctx* c, size_t bytes);
+int io_reserve(Ctx* c, size_t bytes);
+int coef_upload(Ctx* c, const void* host, size_t bytes, void** dptr);  // async on c->stream
+
+#define OQB_CUDA(c, call)                                                                      \
+    do {                                                                                       \
+        cudaError_t _e = (call);                                                               \
+        if (_e != cudaSuccess)                                                                 \
+            return oqb::set_error((c), 2, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), \
+                                  __FILE__, __LINE__);                                         \
+    } while (0)
+
+#define OQB_LAUNCH_CHECK(c)                                                                    \
+    do {                                                                                       \
+        (c)->launches++;                                                                       \
+        cudaError_t _e = cudaGetLastError();                                                   \
+        if (_e != cudaSuccess)                                                                 \
+            return oqb::set_error((c), 2, "kernel launch failed: %s (%s:%d)",                  \
+                                  cudaGetErrorString(_e), __FILE__, __LINE__);                 \
+    } while (0)
+
+#define OQB_TRY(expr)            \
+    do {                         \
+        int _s = (expr);         \
+        if (_s != 0) return _s;  \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// Batched complex GEMM on the FP64 tensor pipe (DMMA.8x8x4).  zgemm.cu
+//   C[b] = epi( alpha * opA(A[b]) * opB(B[b]) ) + beta * C[b]
+// All matrices column-major, interleaved complex128; strides in complex elements; a batch
+// stride of 0 shares the operand across the batch.
+// ---------------------------------------------------------------------------------------------
+struct ZgemmParams {
+    int M = 0, N = 0, K = 0, batch = 1;
+    int opA = OP_N, opB = OP_N;
+    // batch index z = b * batch2 + k (b < batch, k < batch2); offset = b*stride + k*stride2
+    int batch2 = 1;
+    const c128* A = nullptr; long long lda = 0, strideA = 0, strideA2 = 0;
+    const c128* B = nullptr; long long ldb = 0, strideB = 0, strideB2 = 0;
+    c128* C = nullptr;       long long ldc = 0, strideC = 0, strideC2 = 0;
+    c128 alpha = {1.0, 0.0}, beta = {0.0, 0.0};
+    // optional Hadamard epilogue: result(m,n) *= E(m,n)   (E col-major, lde, batch stride strideE)
+    const c128* E = nullptr; long long lde = 0, strideE = 0;
+    // optional: capture the diagonal of alpha*opA(A)opB(B) (before the Hadamard factor)
+    c128* diag_out = nullptr; long long strideDiag = 0;
+    // optional per-(b,k) real scale of alpha: alpha_z = alpha * alpha_scale[z]   (device pointer)
+    //   (index z % alpha_scale_mod when alpha_scale_mod > 0)
+    const double* alpha_scale = nullptr;
+    int alpha_scale_mod = 0;
+};
+int zgemm(Ctx* c, const ZgemmParams& p);
+
+// Double-buffered H2D → compute → D2H pipeline over batch chunks (the *_host entry points).
+// compute(b0, cnt, d_in, d_out) enqueues work for members [b0, b0+cnt) on c->stream.
+template <class F>
+int host_pipeline(Ctx* c, int nb, size_t in_bytes, size_t out_bytes, const void* h_in, void* h_out, int chunk,
+                  F compute) {
+    if (nb <= 0) return 0;
+    if (chunk > nb) chunk = nb;
+    const size_t inb = (size_t)chunk * in_bytes, outb = (size_t)chunk * out_bytes;
+    OQB_TRY(io_reserve(c, 2 * (inb + outb)));
+    char* base = (char*)c->io;
+    char* d_in[2] = {base, base + inb};
+    char* d_out[2] = {base + 2 * inb, base + 2 * inb + outb};
+    cudaStream_t up = c->copy_stream[0], down = c->copy_stream[1];
+    cudaEvent_t* ev_up = &c->ev[0];
+    cudaEvent_t* ev_comp = &c->ev[2];
+    cudaEvent_t* ev_down = &c->ev[4];
+    // order the pipeline after whatever is already queued on the compute stream
+    OQB_CUDA(c, cudaEventRecord(c->ev[6], c->stream));
+    OQB_CUDA(c, cudaStreamWaitEvent(up, c->ev[6], 0));
+    int i = 0;
+    for (int b0 = 0; b0 < nb; b0 += chunk, ++i) {
+        const int cnt = nb - b0 < chunk ? nb - b0 : chunk;
+        const int s = i & 1;
+        if (i >= 2) OQB_CUDA(c, cudaStreamWaitEvent(up, ev_comp[s], 0));
+        OQB_CUDA(c, cudaMemcpyAsync(d_in[s], (const char*)h_in + (size_t)b0 * in_bytes, (size_t)cnt * in_bytes,
+                                    cudaMemcpyHostToDevice, up));
+        OQB_CUDA(c, cudaEventRecord(ev_up[s], up));
+        OQB_CUDA(c, cudaStreamWaitEvent(c->stream, ev_up[s], 0));
+        if (i >= 2) OQB_CUDA(c, cudaStreamWaitEvent(c->stream, ev_down[s], 0));
+        OQB_TRY(compute(b0, cnt, (const void*)d_in[s], (void*)d_out[s]));
+        OQB_CUDA(c, cudaEventRecord(ev_comp[s], c->stream));
+        OQB_CUDA(c, cudaStreamWaitEvent(down, ev_comp[s], 0));
+        OQB_CUDA(c, cudaMemcpyAsync((char*)h_out + (size_t)b0 * out_bytes, d_out[s], (size_t)cnt * out_bytes,
+                                    cudaMemcpyDeviceToHost, down));
+        OQB_CUDA(c, cudaEventRecord(ev_down[s], down));
+    }
+    OQB_CUDA(c, cudaStreamSynchronize(down));
+    OQB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+}  // namespace oqb
+
+// ---------------------------------------------------------------------------------------------
+// elementwise / reduction kernels (elementwise.cu) — launched on c->stream
+// ---------------------------------------------------------------------------------------------
+namespace oqb {
+// out[b][e] (+)= Σ_j coef[b*coef_ld + j] * mats[j*len + e],  e < len, b < nb   (coef complex, device)
+int lincomb(Ctx* c, int nmat, long long len, const c128* mats, const c128* coef, long long coef_ld,
+            c128* out, int nb, bool accumulate);
+// X[b][a+b'*l] (+)= (Cm[a+b'*l] + (w_sub ? i(w_sub[a]-w_sub[b']) : 0)) * R[b][a+b'*l]
+int hadamard(Ctx* c, int l, const c128* Cm, const double* w_sub, const c128* R, c128* X, int nb,
+             bool accumulate);
+// X[b][a + a*l] += Σ_b' Wt[b' + a*l] * pop[b*l + b']      (Wt real)
+int davies_diag(Ctx* c, int l, const double* Wt, const c128* pop, c128* X, int nb);
+// pop[b*l + a] = R[b][a + a*l]
+int extract_diag(Ctx* c, int l, const c128* R, c128* pop, int nb);
+// X[b][i+j*l] += alpha * Σ_{k<nk} (Kb[(b*nk+k)][i+j*l] + conj(Kb[(b*nk+k)][j+i*l]))
+int add_adjoint(Ctx* c, int l, int nk, double alpha, const c128* Kb, c128* X, int nb);
+// Davies tables from rotated couplings A (K l×l), gam/S (l×l real), w (l):
+//   Gam[b], hls[b] (column sums), Wt (l×l, transposed, zero diagonal), Cm (l×l complex)
+int davies_tables(Ctx* c, int l, int K, const c128* A, const double* gam, const double* S,
+                  const double* w, int with_davies, double* Gam, double* hls, double* Wt, c128* Cm);
+// cross terms: X[b][a + a2*l] += rate * Σ_α A[a,b] conj(A[a2,b2]) * R[b][b + b2*l]
+int davies_cross(Ctx* c, int l, int K, const c128* A, long long ncross, const int32_t* idx,
+                 const double* rate, const c128* R, c128* X, int nb);
+// Moff[b + b2*l] += (-rate/2 - i S) Σ_α conj(A[a,b]) A[a,b2]   for entries (a,b,b2)
+int davies_lamb_build(Ctx* c, int l, int K, const c128* A, long long nlamb, const int32_t* idx,
+                      const double* rate_S, c128* Moff);
+// D (l×l) = diag(-i w - i hls - Gam/2) + (Moff ? Moff : 0)
+int davies_heff_diag(Ctx* c, int l, const double* w, const double* Gam, const double* hls,
+                     const c128* Moff, c128* D);
+// Lam[p][i+j*l] = (0.5*gam[p][i+j*l] + i S[p][i+j*l]) * A[alpha[p]][i+j*l]
+int onesided_lambda(Ctx* c, int l, int npairs, const int32_t* alpha, const c128* A, const double* gam,
+                    const double* S, long long table_stride, c128* Lam);
+// out[b][(p*n+q) + (r*n+s)*n*n] = i(H[b][r,p] δ(q,s) − δ(p,r) H[b][q,s])
+int vectorized_commutator(Ctx* c, int n, const c128* H, long long strideH, c128* out, int nb);
+// cache[b] −= I⊗SL + conj(SL)⊗I − Sᵀ⊗Λ − conj(Λ)⊗S   for one coupling
+int redfield_superop_acc(Ctx* c, int n, const c128* S, long long strideS, const c128* Lam,
+                         long long strideLam, const c128* SL, long long strideSL, c128* cache, int nb);
+// out[(b*nobs+o)] = tr(O_o ρ_b) or ψ_b' O_o ψ_b
+int expect(Ctx* c, int n, int nobs, const c128* obs, int nb, const c128* state, int is_vector, c128* out);
+}  // namespace oqb
+
+struct oqb_ctx : oqb::Ctx {};

@@ -1,0 +1,307 @@
+// DenseHamiltonian + LindbladLiouvillian + Redfield-apply entry points (include/oqb.h).
+// Everything dense is composed from the DMMA ZGEMM (zgemm.cu) and the streaming kernels of
+// elementwise.cu; this file is host orchestration only.
+#include <cstring>
+#include <vector>
+
+#include "../../include/oqb.h"
+#include "common.cuh"
+
+using namespace oqb;
+
+struct oqb_dense {
+    oqb_ctx* ctx = nullptr;
+    int n = 0, nterms = 0, K = 0;
+    c128* d_mats = nullptr;  // (nterms + K) n×n : m_1..m_nterms, L_1'L_1..L_K'L_K
+    c128* d_lops = nullptr;  // K n×n == the n × (K n) matrix [L_1 | … | L_K]
+};
+
+namespace {
+
+const size_t kWorkspaceBudget = (size_t)3 << 30;  // bytes of scratch per batch chunk
+
+// Complex coefficient rows for lincomb: row b = [hs * coefH[b][i] …, gs * gamma[b][k] …]
+// Returns the number of rows (1 when everything is shared across the batch).
+int build_coef(const oqb_dense* op, int nb, const double* coefH, int coef_shared, c128 hs, const double* gamma,
+               int gamma_shared, c128 gs, bool with_h, std::vector<c128>& out) {
+    const int nt = with_h ? op->nterms : 0, K = gamma ? op->K : 0;
+    const bool shared = (!with_h || coef_shared) && (!gamma || gamma_shared);
+    const int rows = shared ? 1 : nb;
+    out.resize((size_t)rows * (nt + K));
+    for (int b = 0; b < rows; ++b) {
+        c128* r = out.data() + (size_t)b * (nt + K);
+        for (int i = 0; i < nt; ++i) {
+            double f = coefH[(coef_shared ? 0 : (size_t)b * nt) + i];
+            r[i] = make_double2(hs.x * f, hs.y * f);
+        }
+        for (int k = 0; k < K; ++k) {
+            double g = gamma[(gamma_shared ? 0 : (size_t)b * op->K) + k];
+            r[nt + k] = make_double2(gs.x * g, gs.y * g);
+        }
+    }
+    return rows;
+}
+
+// du[b] += Σ_k γ_bk L_k u_b L_k'   for members [0,cnt) of the given chunk; T is scratch cnt×K n×n
+int sandwich(oqb_dense* op, int cnt, const double* d_gamma, int gamma_mod, const c128* u, c128* du, c128* T) {
+    oqb_ctx* c = op->ctx;
+    const long long n = op->n, nn = n * n;
+    const int K = op->K;
+    ZgemmParams p;  // T[b,k] = γ_bk L_k u_b
+    p.M = p.N = p.K = (int)n;
+    p.batch = cnt; p.batch2 = K;
+    p.A = op->d_lops; p.lda = n; p.strideA = 0; p.strideA2 = nn;
+    p.B = u; p.ldb = n; p.strideB = nn; p.strideB2 = 0;
+    p.C = T; p.ldc = n; p.strideC = K * nn; p.strideC2 = nn;
+    p.alpha_scale = d_gamma; p.alpha_scale_mod = gamma_mod;
+    OQB_TRY(zgemm(c, p));
+    ZgemmParams q;  // du[b] += [T_b1 | … | T_bK] · [L_1 | … | L_K]'
+    q.M = q.N = (int)n; q.K = (int)(K * n);
+    q.batch = cnt;
+    q.A = T; q.lda = n; q.strideA = K * nn;
+    q.B = op->d_lops; q.ldb = n; q.strideB = 0; q.opB = OP_C;
+    q.C = du; q.ldc = n; q.strideC = nn;
+    q.beta = make_double2(1.0, 0.0);
+    return zgemm(c, q);
+}
+
+// shared implementation of oqb_dense_rhs (with_h) and oqb_lindblad_acc (!with_h)
+int dense_rhs_impl(oqb_dense* op, int nb, const double* coefH, int coef_shared, const double* gamma,
+                   int gamma_shared, const c128* u, c128* du, bool with_h) {
+    oqb_ctx* c = op->ctx;
+    if (nb <= 0) return 0;
+    if (!u || !du) return set_error(c, OQB_EINVAL, "dense rhs: null state pointer");
+    if (with_h && !coefH) return set_error(c, OQB_EINVAL, "dense rhs: null coefH");
+    const long long n = op->n, nn = n * n;
+    const int K = (gamma && op->K > 0) ? op->K : 0;
+    if (!with_h && K == 0) return 0;
+
+    // He_b = H(s_b) − (i/2) Σ γ_bk L_k'L_k    (or G_b = −½ Σ γ L'L for the accumulate form)
+    std::vector<c128> coef;
+    const c128 gs = with_h ? make_double2(0.0, -0.5) : make_double2(-0.5, 0.0);
+    const int rows = build_coef(op, nb, coefH, coef_shared, make_double2(1.0, 0.0), K ? gamma : nullptr,
+                                gamma_shared, gs, with_h, coef);
+    const int nmat = (with_h ? op->nterms : 0) + K;
+    const c128* mats = with_h ? op->d_mats : op->d_mats + (long long)op->nterms * nn;
+    // lincomb needs [m…, LdL…] contiguous: true when with_h (terms then LdL) and when !with_h (LdL only)
+    // one staged upload: [complex coefficient rows | raw γ rows]
+    const size_t coef_bytes = coef.size() * sizeof(c128);
+    const size_t gam_elems = K ? (gamma_shared ? (size_t)K : (size_t)nb * K) : 0;
+    std::vector<char> stage(coef_bytes + gam_elems * sizeof(double));
+    memcpy(stage.data(), coef.data(), coef_bytes);
+    if (gam_elems) memcpy(stage.data() + coef_bytes, gamma, gam_elems * sizeof(double));
+    void* d_stage = nullptr;
+    OQB_TRY(coef_upload(c, stage.data(), stage.size(), &d_stage));
+    void* d_coef = d_stage;
+    void* d_gamma = (char*)d_stage + coef_bytes;
+
+    const size_t per = (size_t)(1 + K) * nn * sizeof(c128);
+    int chunk = (int)(kWorkspaceBudget / per);
+    if (chunk < 1) chunk = 1;
+    if (chunk > nb) chunk = nb;
+    const size_t he_elems = (size_t)(rows == 1 ? 1 : chunk) * nn;
+    OQB_TRY(ws_reserve(c, (he_elems + (size_t)chunk * K * nn) * sizeof(c128)));
+    c128* He = (c128*)c->ws;
+    c128* T = He + he_elems;
+
+    if (rows == 1) OQB_TRY(lincomb(c, nmat, nn, mats, (const c128*)d_coef, 0, He, 1, false));
+    for (int b0 = 0; b0 < nb; b0 += chunk) {
+        const int cnt = nb - b0 < chunk ? nb - b0 : chunk;
+        const c128* ub = u + (long long)b0 * nn;
+        c128* dub = du + (long long)b0 * nn;
+        if (rows != 1)
+            OQB_TRY(lincomb(c, nmat, nn, mats, (const c128*)d_coef + (long long)b0 * nmat, nmat, He, cnt, false));
+        ZgemmParams p;  // du = (−i) He u      [accumulate form: du += G u]
+        p.M = p.N = p.K = (int)n; p.batch = cnt;
+        p.A = He; p.lda = n; p.strideA = rows == 1 ? 0 : nn;
+        p.B = ub; p.ldb = n; p.strideB = nn;
+        p.C = dub; p.ldc = n; p.strideC = nn;
+        p.alpha = with_h ? make_double2(0.0, -1.0) : make_double2(1.0, 0.0);
+        p.beta = with_h ? make_double2(0.0, 0.0) : make_double2(1.0, 0.0);
+        OQB_TRY(zgemm(c, p));
+        ZgemmParams q;  // du += (+i) u He'    [accumulate form: du += u G]
+        q.M = q.N = q.K = (int)n; q.batch = cnt;
+        q.A = ub; q.lda = n; q.strideA = nn;
+        q.B = He; q.ldb = n; q.strideB = rows == 1 ? 0 : nn; q.opB = with_h ? OP_C : OP_N;
+        q.C = dub; q.ldc = n; q.strideC = nn;
+        q.alpha = with_h ? make_double2(0.0, 1.0) : make_double2(1.0, 0.0);
+        q.beta = make_double2(1.0, 0.0);
+        OQB_TRY(zgemm(c, q));
+        if (K) {
+            const double* dg = (const double*)d_gamma + (gamma_shared ? 0 : (long long)b0 * K);
+            OQB_TRY(sandwich(op, cnt, dg, gamma_shared ? K : 0, ub, dub, T));
+        }
+    }
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int oqb_dense_create(oqb_ctx* c, int n, int nterms, const void* h_mats, int K, const void* h_lops, oqb_dense** out) {
+    if (!c || !out) return OQB_EINVAL;
+    *out = nullptr;
+    if (n <= 0 || nterms < 0 || K < 0 || (nterms > 0 && !h_mats) || (K > 0 && !h_lops))
+        return set_error(c, OQB_EINVAL, "oqb_dense_create: bad arguments");
+    oqb_dense* op = new oqb_dense();
+    op->ctx = c; op->n = n; op->nterms = nterms; op->K = K;
+    const size_t nn = (size_t)n * n;
+    cudaError_t e = cudaMalloc((void**)&op->d_mats, (nterms + K + 1) * nn * sizeof(c128));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&op->d_lops, (K + 1) * nn * sizeof(c128));
+    if (e != cudaSuccess) { oqb_dense_destroy(op); return set_error(c, OQB_ENOMEM, "oqb_dense_create: %s", cudaGetErrorString(e)); }
+    if (nterms) OQB_CUDA(c, cudaMemcpyAsync(op->d_mats, h_mats, nterms * nn * sizeof(c128), cudaMemcpyHostToDevice, c->stream));
+    if (K) {
+        OQB_CUDA(c, cudaMemcpyAsync(op->d_lops, h_lops, K * nn * sizeof(c128), cudaMemcpyHostToDevice, c->stream));
+        ZgemmParams p;  // L_k' L_k   (src/opensys/lindblad.jl:99,107)
+        p.M = p.N = p.K = n; p.batch = K;
+        p.opA = OP_C;
+        p.A = op->d_lops; p.lda = n; p.strideA = (long long)nn;
+        p.B = op->d_lops; p.ldb = n; p.strideB = (long long)nn;
+        p.C = op->d_mats + (size_t)nterms * nn; p.ldc = n; p.strideC = (long long)nn;
+        int s = zgemm(c, p);
+        if (s) { oqb_dense_destroy(op); return s; }
+    }
+    OQB_CUDA(c, cudaStreamSynchronize(c->stream));
+    *out = op;
+    return OQB_OK;
+}
+
+int oqb_dense_destroy(oqb_dense* op) {
+    if (!op) return OQB_OK;
+    cudaStreamSynchronize(op->ctx->stream);
+    if (op->d_mats) cudaFree(op->d_mats);
+    if (op->d_lops) cudaFree(op->d_lops);
+    delete op;
+    return OQB_OK;
+}
+
+int oqb_dense_hamiltonian(oqb_dense* op, int nb, const double* h_coefH, int coef_shared, void* d_out) {
+    oqb_ctx* c = op->ctx;
+    if (nb <= 0) return 0;
+    if (!h_coefH || !d_out) return set_error(c, OQB_EINVAL, "oqb_dense_hamiltonian: null argument");
+    std::vector<c128> coef;
+    const int rows = build_coef(op, nb, h_coefH, coef_shared, make_double2(1.0, 0.0), nullptr, 1,
+                                make_double2(0.0, 0.0), true, coef);
+    void* d_coef = nullptr;
+    OQB_TRY(coef_upload(c, coef.data(), coef.size() * sizeof(c128), &d_coef));
+    return lincomb(c, op->nterms, (long long)op->n * op->n, op->d_mats, (const c128*)d_coef,
+                   rows == 1 ? 0 : op->nterms, (c128*)d_out, nb, false);
+}
+
+int oqb_dense_update_cache(oqb_dense* op, int nb, const double* h_coefH, int coef_shared, const double* h_gamma,
+                           int gamma_shared, void* d_cache) {
+    oqb_ctx* c = op->ctx;
+    if (nb <= 0) return 0;
+    if (!h_coefH || !d_cache) return set_error(c, OQB_EINVAL, "oqb_dense_update_cache: null argument");
+    const bool lind = h_gamma && op->K > 0;
+    std::vector<c128> coef;
+    const int rows = build_coef(op, nb, h_coefH, coef_shared, make_double2(0.0, -1.0), lind ? h_gamma : nullptr,
+                                gamma_shared, make_double2(-0.5, 0.0), true, coef);
+    const int nmat = op->nterms + (lind ? op->K : 0);
+    void* d_coef = nullptr;
+    OQB_TRY(coef_upload(c, coef.data(), coef.size() * sizeof(c128), &d_coef));
+    return lincomb(c, nmat, (long long)op->n * op->n, op->d_mats, (const c128*)d_coef, rows == 1 ? 0 : nmat,
+                   (c128*)d_cache, nb, false);
+}
+
+int oqb_dense_update_vectorized_cache(oqb_dense* op, int nb, const double* h_coefH, int coef_shared, void* d_cache) {
+    oqb_ctx* c = op->ctx;
+    if (nb <= 0) return 0;
+    const long long nn = (long long)op->n * op->n;
+    const int rows = coef_shared ? 1 : nb;
+    OQB_TRY(ws_reserve(c, (size_t)rows * nn * sizeof(c128)));
+    OQB_TRY(oqb_dense_hamiltonian(op, rows, h_coefH, coef_shared, c->ws));
+    return vectorized_commutator(c, op->n, (const c128*)c->ws, rows == 1 ? 0 : nn, (c128*)d_cache, nb);
+}
+
+int oqb_dense_rhs(oqb_dense* op, int nb, const double* h_coefH, int coef_shared, const double* h_gamma,
+                  int gamma_shared, const void* d_u, void* d_du) {
+    return dense_rhs_impl(op, nb, h_coefH, coef_shared, h_gamma, gamma_shared, (const c128*)d_u, (c128*)d_du, true);
+}
+
+int oqb_lindblad_acc(oqb_dense* op, int nb, const double* h_gamma, int gamma_shared, const void* d_u, void* d_du) {
+    return dense_rhs_impl(op, nb, nullptr, 1, h_gamma, gamma_shared, (const c128*)d_u, (c128*)d_du, false);
+}
+
+int oqb_dense_rhs_host(oqb_dense* op, int nb, const double* h_coefH, int coef_shared, const double* h_gamma,
+                       int gamma_shared, const void* h_u, void* h_du) {
+    oqb_ctx* c = op->ctx;
+    const size_t bytes = (size_t)op->n * op->n * sizeof(c128);
+    int chunk = (int)(((size_t)256 << 20) / bytes);
+    if (chunk < 1) chunk = 1;
+    const int nt = op->nterms, K = op->K;
+    return host_pipeline(c, nb, bytes, bytes, h_u, h_du, chunk, [&](int b0, int cnt, const void* din, void* dout) {
+        const double* cf = coef_shared ? h_coefH : h_coefH + (size_t)b0 * nt;
+        const double* gm = (!h_gamma || gamma_shared) ? h_gamma : h_gamma + (size_t)b0 * K;
+        return dense_rhs_impl(op, cnt, cf, coef_shared, gm, gamma_shared, (const c128*)din, (c128*)dout, true);
+    });
+}
+
+int oqb_redfield_apply_acc(oqb_ctx* c, int n, int K, const void* d_S, int S_shared, const void* d_Lambda, int nb,
+                           const void* d_u, void* d_du) {
+    if (nb <= 0 || K <= 0) return 0;
+    if (!d_S || !d_Lambda || !d_u || !d_du) return set_error(c, OQB_EINVAL, "oqb_redfield_apply_acc: null argument");
+    const long long nn = (long long)n * n;
+    const size_t per = (size_t)2 * K * nn * sizeof(c128);
+    int chunk = (int)(kWorkspaceBudget / per);
+    if (chunk < 1) chunk = 1;
+    if (chunk > nb) chunk = nb;
+    OQB_TRY(ws_reserve(c, (size_t)chunk * per));
+    c128* M1 = (c128*)c->ws;
+    c128* Kb = M1 + (size_t)chunk * K * nn;
+    for (int b0 = 0; b0 < nb; b0 += chunk) {
+        const int cnt = nb - b0 < chunk ? nb - b0 : chunk;
+        const c128* u = (const c128*)d_u + (long long)b0 * nn;
+        const c128* Lam = (const c128*)d_Lambda + (long long)b0 * K * nn;
+        const c128* S = (const c128*)d_S + (S_shared ? 0 : (long long)b0 * K * nn);
+        ZgemmParams p;  // M1[b,α] = Λ[b,α] u_b
+        p.M = p.N = p.K = n; p.batch = cnt; p.batch2 = K;
+        p.A = Lam; p.lda = n; p.strideA = K * nn; p.strideA2 = nn;
+        p.B = u; p.ldb = n; p.strideB = nn; p.strideB2 = 0;
+        p.C = M1; p.ldc = n; p.strideC = K * nn; p.strideC2 = nn;
+        OQB_TRY(zgemm(c, p));
+        ZgemmParams q = p;  // Kb[b,α] = S_α M1[b,α]
+        q.A = S; q.strideA = S_shared ? 0 : K * nn; q.strideA2 = nn;
+        q.B = M1; q.strideB = K * nn; q.strideB2 = nn;
+        q.C = Kb;
+        OQB_TRY(zgemm(c, q));
+        ZgemmParams r = p;  // Kb[b,α] −= M1[b,α] S_α
+        r.A = M1; r.strideA = K * nn; r.strideA2 = nn;
+        r.B = S; r.strideB = S_shared ? 0 : K * nn; r.strideB2 = nn;
+        r.C = Kb;
+        r.alpha = make_double2(-1.0, 0.0);
+        r.beta = make_double2(1.0, 0.0);
+        OQB_TRY(zgemm(c, r));
+        OQB_TRY(add_adjoint(c, n, K, -1.0, Kb, (c128*)d_du + (long long)b0 * nn, cnt));  // du −= K₂ + K₂'
+    }
+    return 0;
+}
+
+int oqb_redfield_vectorized_acc(oqb_ctx* c, int n, int K, const void* d_S, int S_shared, const void* d_Lambda,
+                                int nb, void* d_cache) {
+    if (nb <= 0 || K <= 0) return 0;
+    const long long nn = (long long)n * n;
+    OQB_TRY(ws_reserve(c, (size_t)nb * nn * sizeof(c128)));
+    c128* SL = (c128*)c->ws;
+    for (int a = 0; a < K; ++a) {
+        const c128* S = (const c128*)d_S + a * nn;
+        const c128* Lam = (const c128*)d_Lambda + a * nn;
+        ZgemmParams p;  // SΛ
+        p.M = p.N = p.K = n; p.batch = nb;
+        p.A = S; p.lda = n; p.strideA = S_shared ? 0 : K * nn;
+        p.B = Lam; p.ldb = n; p.strideB = K * nn;
+        p.C = SL; p.ldc = n; p.strideC = nn;
+        OQB_TRY(zgemm(c, p));
+        OQB_TRY(redfield_superop_acc(c, n, S, S_shared ? 0 : K * nn, Lam, K * nn, SL, nn, (c128*)d_cache, nb));
+    }
+    return 0;
+}
+
+int oqb_expect(oqb_ctx* c, int n, int nobs, const void* d_obs, int nb, const void* d_state, int is_vector,
+               double* d_out) {
+    if (!d_obs || !d_state || !d_out) return set_error(c, OQB_EINVAL, "oqb_expect: null argument");
+    return expect(c, n, nobs, (const c128*)d_obs, nb, (const c128*)d_state, is_vector, (c128*)d_out);
+}
+
+}  // extern "C"

@@ -1,0 +1,133 @@
+"""Host-side gap preprocessing for the Davies generator (what the Julia host does with
+`GapIndices`, reference src/opensys/opensys_util.jl:25-61), in the sort-based O(l² log l) form the
+device tables need.
+
+Produces, for an energy vector w:
+  * omega[a,b]: the SIGNED ROUNDED gap the reference evaluates γ and S at for the pair (row a, col b):
+    for i<j the key is round(w[j]-w[i], sigdigits) and the pair (j,i) inherits −key; pairs with
+    |gap| ≤ 10^-digits (and the diagonal) form the zero group with omega = 0;
+  * the cross terms of gap groups that hold more than one pair (accidental 8-digit coincidences,
+    degeneracies): `cross` rows (a,b,a2,b2) and `lamb` rows (a,b,b2), see include/oqb.h.
+This is index bookkeeping on l² scalars; no state arithmetic happens on the host.
+"""
+import math
+
+import numpy as np
+
+_POW10_TABLE = np.array([float(f"1e{k}") for k in range(0, 31)])
+
+
+def round_sigdigits(x: np.ndarray, sigdigits: int) -> np.ndarray:
+    """Vectorised Julia `round(x, sigdigits=n)` for Float64 (Base floatfuncs.jl):
+    h = 1+floor(log10|x|); d = n−h; d ≥ 0 ? rint(x·10^d)/10^d : rint(x/10^-d)·10^-d."""
+    x = np.asarray(x, dtype=np.float64)
+    out = np.array(x, copy=True)
+    nz = (x != 0) & np.isfinite(x)
+    if not nz.any():
+        return out
+    xv = x[nz]
+    h = 1 + np.floor(np.log10(np.abs(xv))).astype(np.int64)
+    d = sigdigits - h
+    scale = _POW10_TABLE[np.minimum(np.abs(d), 30)]  # exact powers of ten (10^k is exact for k ≤ 22)
+    pos = d >= 0
+    r = np.empty_like(xv)
+    r[pos] = np.rint(xv[pos] * scale[pos]) / scale[pos]
+    r[~pos] = np.rint(xv[~pos] / scale[~pos]) * scale[~pos]
+    bad = ~np.isfinite(r)
+    r[bad] = xv[bad]
+    out[nz] = r
+    return out
+
+
+class GapGroups:
+    def __init__(self, w, digits=8, sigdigits=8, max_cross=50_000_000):
+        w = np.asarray(w, dtype=np.float64)
+        l = len(w)
+        self.w, self.lvl = w, l
+        iu, ju = np.triu_indices(l, 1)  # (i,j), i<j, lexicographic — the reference's loop order
+        gap = w[ju] - w[iu]
+        zero = np.abs(gap) <= 10.0 ** (-digits)
+        key = np.zeros_like(gap)
+        key[~zero] = round_sigdigits(gap[~zero], sigdigits)
+        omega = np.zeros((l, l))
+        omega[iu, ju] = key
+        omega[ju, iu] = -key
+        self.omega = omega
+        self.gap_matrix = w[None, :] - w[:, None]  # UNROUNDED (opensys_util.jl:65), one-sided AME only
+        # ---- groups with more than one pair --------------------------------------------------
+        cross, cross_key, lamb, lamb_key = [], [], [], []
+        nzi, nzj, nzk = iu[~zero], ju[~zero], key[~zero]
+        if nzk.size:
+            order = np.argsort(nzk, kind="stable")
+            ks = nzk[order]
+            starts = np.flatnonzero(np.r_[True, ks[1:] != ks[:-1]])
+            ends = np.r_[starts[1:], ks.size]
+            multi = np.flatnonzero(ends - starts > 1)
+            est = int(np.sum((ends[multi] - starts[multi]).astype(np.int64) ** 2)) * 2
+            if est > max_cross:
+                raise NotImplementedError(
+                    f"gap spectrum is too degenerate for the cross-term list ({est} entries); "
+                    "the dense per-group path is not implemented")
+            for g in multi:
+                mem = order[starts[g]:ends[g]]
+                ii, jj, kk = nzi[mem], nzj[mem], float(ks[starts[g]])
+                for (aa, bb, kval) in ((ii, jj, kk), (jj, ii, -kk)):  # L₊ then L₋ (davies.jl:30-31)
+                    self._pairs(aa, bb, kval, cross, cross_key, lamb, lamb_key)
+        # ---- zero group: degenerate pairs (both orders) + the diagonal ---------------------------
+        zi, zj = iu[zero], ju[zero]
+        if zi.size:
+            aa = np.r_[zi, zj, np.arange(l)]
+            bb = np.r_[zj, zi, np.arange(l)]
+            if (len(aa)) ** 2 > max_cross:
+                raise NotImplementedError("zero-gap group too large for the cross-term list")
+            self._pairs(aa, bb, 0.0, cross, cross_key, lamb, lamb_key, skip_diag_diag=True)
+        self.cross_idx = np.array(cross, dtype=np.int32).reshape(-1, 4)
+        self.cross_key = np.array(cross_key, dtype=np.float64)
+        self.lamb_idx = np.array(lamb, dtype=np.int32).reshape(-1, 3)
+        self.lamb_key = np.array(lamb_key, dtype=np.float64)
+
+    @staticmethod
+    def _pairs(aa, bb, kval, cross, cross_key, lamb, lamb_key, skip_diag_diag=False):
+        m = len(aa)
+        for p in range(m):
+            for q in range(m):
+                if p == q:
+                    continue
+                if skip_diag_diag and aa[p] == bb[p] and aa[q] == bb[q]:
+                    continue  # (k,k)×(k',k') is the γ(0)·A_kk·conj(A_k'k') Hadamard term
+                cross.append((aa[p], bb[p], aa[q], bb[q]))
+                cross_key.append(kval)
+                if aa[p] == aa[q]:
+                    lamb.append((aa[p], bb[p], bb[q]))
+                    lamb_key.append(kval)
+
+    def tables(self, gamma, S):
+        """γ and S evaluated at omega (l×l, column-major flattening is done by the caller) and at the
+        cross-term keys."""
+        uniq, inv = np.unique(np.r_[self.omega.ravel(), self.cross_key, self.lamb_key], return_inverse=True)
+        gv = _eval(gamma, uniq)
+        sv = _eval(S, uniq)
+        n2 = self.lvl * self.lvl
+        nc = len(self.cross_key)
+        gam = gv[inv[:n2]].reshape(self.lvl, self.lvl)
+        Sm = sv[inv[:n2]].reshape(self.lvl, self.lvl)
+        cross_rate = gv[inv[n2:n2 + nc]]
+        lamb_rate_S = np.stack([gv[inv[n2 + nc:]], sv[inv[n2 + nc:]]], axis=1) if len(self.lamb_key) else np.zeros((0, 2))
+        return gam, Sm, np.ascontiguousarray(cross_rate), np.ascontiguousarray(lamb_rate_S)
+
+
+def _eval(f, x):
+    """Evaluate a scalar host closure on an array (vectorised when the object offers it)."""
+    if hasattr(f, "vectorized"):
+        return np.asarray(f.vectorized(x), dtype=np.float64)
+    return np.array([float(f(float(v))) for v in x], dtype=np.float64)
+
+
+def ohmic_spectrum_vec(eta, wc, beta, w):
+    """Vectorised src/bath/ohmic.jl:35-41."""
+    w = np.asarray(w, dtype=np.float64)
+    out = np.full(w.shape, 2 * math.pi * eta / beta)
+    nz = np.abs(w) > 1e-9
+    wv = w[nz]
+    out[nz] = 2 * math.pi * eta * wv * np.exp(-np.abs(wv) / wc) / (1 - np.exp(-beta * wv))
+    return out

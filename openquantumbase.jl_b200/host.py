@@ -1,0 +1,906 @@
+"""Host-side mirror of the reference's operator interface for the master-equation RHS path.
+
+Same names, argument meaning and error behaviour as OpenQuantumBase.jl (reference file:line in
+each docstring); Julia's `update_cache!` is spelled `update_cache_` here.  Every numerical
+operation on a state is executed by the CUDA library through the C ABI (include/oqb.h); the host
+only evaluates the user's scalar closures f_i(s), γ_k(s), γ(ω), S(ω) — exactly what the Julia glue
+of INTEGRATION.md does — and ships them as small coefficient arrays / tables.
+
+States live on the GPU as `DeviceBatch` objects (n×n×B ComplexF64, column-major like Julia).
+numpy arrays are accepted as well and are routed through the *_host entry points (host buffers,
+copies inside the call).  There is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Callable, List, Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from .gaps import GapGroups, ohmic_spectrum_vec
+
+C128 = np.complex128
+
+
+# --------------------------------------------------------------------------------------------
+# context / device batches
+# --------------------------------------------------------------------------------------------
+class Context:
+    """One CUDA stream + workspace (oqb_ctx).  Not thread-safe, like the reference's functors."""
+
+    def __init__(self, device: int = 0):
+        self.lib = _lib.load()
+        h = C.c_void_p()
+        st = self.lib.oqb_create(device, C.byref(h))
+        if st != 0 or not h:
+            raise _lib.OQBError(f"oqb_create(device={device}) failed with status {st}: a B200 (sm_100) "
+                                "is required and there is no CPU fallback")
+        self.h = h
+        self.device = device
+        # run on torch's current stream so that torch allocations/copies and our kernels are ordered
+        import torch
+        with torch.cuda.device(device):
+            self.check(self.lib.oqb_set_stream(self.h, C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+
+    def check(self, st):
+        if st != 0:
+            raise _lib.OQBError(self.lib.oqb_last_error(self.h).decode())
+
+    def sync(self):
+        self.check(self.lib.oqb_sync(self.h))
+
+    def launch_count(self) -> int:
+        n = C.c_uint64()
+        self.lib.oqb_launch_count(self.h, C.byref(n))
+        return n.value
+
+    def stream_ptr(self) -> int:
+        s = C.c_void_p()
+        self.lib.oqb_get_stream(self.h, C.byref(s))
+        return s.value or 0
+
+    def probe_fp64(self):
+        a, b = C.c_double(), C.c_double()
+        self.check(self.lib.oqb_probe_fp64(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+
+_CTX = {}
+
+
+def get_context(device: Optional[int] = None) -> Context:
+    if device is None:
+        import torch
+        device = torch.cuda.current_device() if torch.cuda.is_available() else 0
+    if device not in _CTX:
+        _CTX[device] = Context(device)
+    return _CTX[device]
+
+
+class DeviceBatch:
+    """A batch of B (rows×cols) ComplexF64 matrices resident in HBM, each column-major — the
+    memory image of a Julia Array{ComplexF64,3} of size rows×cols×B.  Backed by a torch tensor
+    (PyTorch is only the allocator here)."""
+
+    def __init__(self, B: int, rows: int, cols: int = 1, ctx: Optional[Context] = None, tensor=None):
+        import torch
+        self.ctx = ctx or get_context()
+        self.B, self.rows, self.cols = B, rows, cols
+        if tensor is None:
+            tensor = torch.zeros((B, cols, rows), dtype=torch.complex128, device=f"cuda:{self.ctx.device}")
+        self.t = tensor
+
+    @property
+    def ptr(self):
+        return C.c_void_p(self.t.data_ptr())
+
+    @classmethod
+    def from_host(cls, a: np.ndarray, ctx: Optional[Context] = None) -> "DeviceBatch":
+        """a: (B, rows, cols) or (B, n) for state vectors, ordinary math indexing."""
+        import torch
+        a = np.asarray(a, dtype=C128)
+        if a.ndim == 2:
+            a = a[:, :, None]
+        B, r, c = a.shape
+        ctx = ctx or get_context()
+        t = torch.from_numpy(np.ascontiguousarray(a.transpose(0, 2, 1))).to(f"cuda:{ctx.device}")
+        return cls(B, r, c, ctx, t)
+
+    def to_host(self) -> np.ndarray:
+        self.ctx.sync()
+        a = self.t.cpu().numpy().transpose(0, 2, 1)
+        return a[:, :, 0].copy() if self.cols == 1 else np.ascontiguousarray(a)
+
+    def zeros_like(self) -> "DeviceBatch":
+        return DeviceBatch(self.B, self.rows, self.cols, self.ctx)
+
+    def copy(self) -> "DeviceBatch":
+        self.ctx.sync()
+        return DeviceBatch(self.B, self.rows, self.cols, self.ctx, self.t.clone())
+
+
+def _colmajor_stack(mats: Sequence[np.ndarray]) -> np.ndarray:
+    """K matrices → one C-contiguous buffer holding each matrix column-major."""
+    return np.ascontiguousarray(np.stack([np.asarray(m, dtype=C128).T for m in mats]))
+
+
+def _svec(s, B):
+    """Annealing parameter(s): scalar (shared by the batch) or length-B vector."""
+    s = np.atleast_1d(np.asarray(s, dtype=np.float64))
+    if s.size not in (1, B):
+        raise ValueError(f"expected 1 or {B} annealing parameters, got {s.size}")
+    return s
+
+
+def _coef(funcs, svals) -> np.ndarray:
+    """rows = members (1 if shared), cols = closures: [f_i(s_b)] evaluated on the host."""
+    return np.ascontiguousarray([[float(np.real(f(float(s)))) for f in funcs] for s in svals], dtype=np.float64)
+
+
+class _HostIO:
+    """Adapts numpy states to the device entry points: (n,n)/(B,n,n) numpy in → DeviceBatch."""
+
+    def __init__(self, u, du=None):
+        self.is_dev = isinstance(u, DeviceBatch)
+        if self.is_dev:
+            self.u, self.du = u, du
+            return
+        a = np.asarray(u, dtype=C128)
+        self.single = a.ndim == 2
+        self.u = DeviceBatch.from_host(a[None] if self.single else a)
+        self.du_host = du
+        if du is None:
+            self.du = self.u.zeros_like()
+        else:
+            d = np.asarray(du, dtype=C128)
+            self.du = DeviceBatch.from_host(d[None] if self.single else d)
+
+    def finish(self):
+        if self.is_dev:
+            return self.du
+        out = self.du.to_host()
+        out = out[0] if self.single else out
+        if self.du_host is not None:
+            self.du_host[...] = out
+            return self.du_host
+        return out
+
+
+def unit_scale(u) -> float:
+    """src/base_util.jl:14-22."""
+    if u in ("h", ":h"):
+        return 2 * math.pi
+    if u in ("hbar", "ħ", ":ħ"):
+        return 1.0
+    raise ValueError("The unit can only be :h or :ħ.")
+
+
+class ODEParams:
+    """src/annealing/annealing_type.jl:53-67.  p(t) = annealing_parameter(tf, t).  `t` may be an
+    array (one time per batch member)."""
+
+    def __init__(self, L, tf, annealing_parameter=lambda tf, t: t / tf, **kwargs):
+        self.L, self.tf, self.annealing_parameter, self.accepted_kwargs = L, tf, annealing_parameter, kwargs
+
+    def __call__(self, t):
+        if np.ndim(t) == 0:
+            return self.annealing_parameter(self.tf, t)
+        return np.array([self.annealing_parameter(self.tf, x) for x in np.asarray(t)])
+
+
+# --------------------------------------------------------------------------------------------
+# Hamiltonians
+# --------------------------------------------------------------------------------------------
+class DenseHamiltonian:
+    """src/hamiltonian/dense_hamiltonian.jl:10-89 (also the arithmetic of StaticDenseHamiltonian,
+    src/hamiltonian/static_array_hamiltonian.jl, which only differs in storage)."""
+
+    def __init__(self, funcs, mats, unit="h", dimensionless_time=True, ctx: Optional[Context] = None):
+        mats = [np.asarray(m) for m in mats]
+        if any(m.shape != mats[0].shape for m in mats):
+            raise ValueError("Matrices in the list do not have the same size.")  # :31-33
+        self.f = list(funcs)
+        self.m = [unit_scale(unit) * m.astype(C128) for m in mats]  # :38
+        self.size = mats[0].shape
+        self.dimensionless_time = dimensionless_time
+        self.ctx = ctx or get_context()
+        self._op = None
+        self._lind_key = None
+
+    # one device operator per (Hamiltonian, Lindblad set); uploaded lazily, immutable afterwards
+    def _dense_op(self, lops="keep"):
+        if isinstance(lops, str):  # "keep": reuse whatever operator set is already on the device
+            if self._op is not None:
+                return self._op
+            lops = None
+        key = None if lops is None else tuple(id(x) for x in lops)
+        if self._op is not None and key == self._lind_key:
+            return self._op
+        if self._op is not None:
+            self.ctx.lib.oqb_dense_destroy(self._op)
+        h = C.c_void_p()
+        n = self.size[0]
+        mats = _colmajor_stack(self.m)
+        K = 0 if lops is None else len(lops)
+        lbuf = _colmajor_stack(lops) if K else None
+        self.ctx.check(self.ctx.lib.oqb_dense_create(self.ctx.h, n, len(self.m), mats.ctypes.data, K,
+                                                     lbuf.ctypes.data if K else None, C.byref(h)))
+        self._op, self._lind_key, self._lops_ref = h, key, lops
+        return h
+
+    def __call__(self, *args):
+        if len(args) == 1:
+            return self.evaluate_device(args[0])
+        du, u, p, s = args
+        return self.commutator(du, u, s)
+
+    def evaluate_device(self, s):
+        """(h::DenseHamiltonian)(s) :60-66, computed on the device; returns a host matrix."""
+        n = self.size[0]
+        sv = _svec(s, 1)
+        out = DeviceBatch(1, n, n, self.ctx)
+        cf = _coef(self.f, sv)
+        self.ctx.check(self.ctx.lib.oqb_dense_hamiltonian(self._dense_op(), 1,
+                                                          _lib.dptr(cf), 1, out.ptr))
+        return out.to_host()[0]
+
+    def commutator(self, du, u, s):
+        """(h::DenseHamiltonian)(du,u,p,s) :84-89 — du = −i[H(s),u], OVERWRITES du."""
+        io = _HostIO(u, du)
+        B = io.u.B
+        sv = _svec(s, B)
+        cf = _coef(self.f, sv)
+        self.ctx.check(self.ctx.lib.oqb_dense_rhs(self._dense_op(), B,
+                                                  _lib.dptr(cf), int(sv.size == 1), None, 1, io.u.ptr, io.du.ptr))
+        return io.finish()
+
+    def update_cache(self, cache, s):
+        """update_cache!(cache, H, p, s) :71-76 — cache = −iH(s), OVERWRITES."""
+        io = _HostIO(cache, cache)
+        B = io.u.B
+        sv = _svec(s, B)
+        cf = _coef(self.f, sv)
+        self.ctx.check(self.ctx.lib.oqb_dense_update_cache(self._dense_op(), B,
+                                                           _lib.dptr(cf), int(sv.size == 1), None, 1, io.du.ptr))
+        return io.finish()
+
+    def update_vectorized_cache(self, cache, s):
+        """update_vectorized_cache!(cache, H, p, s) :78-82 — i(Hᵀ⊗I − I⊗H), OVERWRITES."""
+        io = _HostIO(cache, cache)
+        B = io.u.B
+        sv = _svec(s, B)
+        cf = _coef(self.f, sv)
+        self.ctx.check(self.ctx.lib.oqb_dense_update_vectorized_cache(
+            self._dense_op(), B, _lib.dptr(cf), int(sv.size == 1), io.du.ptr))
+        return io.finish()
+
+    _lops_ref = None
+
+    def host_matrix(self, s: float) -> np.ndarray:
+        """Σ f_i(s) m_i on the host — only for feeding LAPACK (haml_eigs); never applied to a state."""
+        H = np.zeros(self.size, dtype=C128)
+        for f, m in zip(self.f, self.m):
+            H += f(s) * m
+        return H
+
+
+class SparseHamiltonian:
+    """src/hamiltonian/sparse_hamiltonian.jl:10-91.  mats: scipy.sparse matrices."""
+
+    def __init__(self, funcs, mats, unit="h", ctx: Optional[Context] = None):
+        import scipy.sparse as sps
+        if any(m.shape != mats[0].shape for m in mats):
+            raise ValueError("Matrices in the list do not have the same size.")
+        self.f = list(funcs)
+        self.m = [sps.csc_matrix(unit_scale(unit) * sps.csc_matrix(m).astype(C128)) for m in mats]
+        for m in self.m:
+            m.sort_indices()
+        self.size = self.m[0].shape
+        self.ctx = ctx or get_context()
+        self._sp = None
+        self._lkey = None
+        self._lops_ref = None
+
+    @staticmethod
+    def _pack(mats):
+        n = mats[0].shape[0]
+        colptr = np.concatenate([np.asarray(m.indptr, dtype=np.int64) + 1 for m in mats])  # 1-based like Julia
+        off = np.zeros(len(mats) + 1, dtype=np.int64)
+        off[1:] = np.cumsum([m.nnz for m in mats])
+        rowval = np.concatenate([np.asarray(m.indices, dtype=np.int64) + 1 for m in mats]) if off[-1] else np.zeros(1, np.int64)
+        nzval = np.concatenate([np.asarray(m.data, dtype=C128) for m in mats]) if off[-1] else np.zeros(1, C128)
+        return (np.ascontiguousarray(colptr), np.ascontiguousarray(rowval), np.ascontiguousarray(nzval), off)
+
+    def _sparse_op(self, lops=None):
+        import scipy.sparse as sps
+        key = None if lops is None else tuple(id(x) for x in lops)
+        if self._sp is not None and key == self._lkey:
+            return self._sp
+        if self._sp is not None:
+            self.ctx.lib.oqb_sparse_destroy(self._sp)
+        n = self.size[0]
+        cp, rv, nz, off = self._pack(self.m)
+        K = 0 if lops is None else len(lops)
+        h = C.c_void_p()
+        i64 = lambda a: a.ctypes.data_as(_lib.c_i64p)
+        if K:
+            lm = [sps.csc_matrix(sps.csc_matrix(L).astype(C128)) for L in lops]
+            for m in lm:
+                m.sort_indices()
+            lcp, lrv, lnz, loff = self._pack(lm)
+            st = self.ctx.lib.oqb_sparse_create(self.ctx.h, n, len(self.m), i64(cp), i64(rv), nz.ctypes.data, i64(off),
+                                                K, i64(lcp), i64(lrv), lnz.ctypes.data, i64(loff), C.byref(h))
+        else:
+            st = self.ctx.lib.oqb_sparse_create(self.ctx.h, n, len(self.m), i64(cp), i64(rv), nz.ctypes.data, i64(off),
+                                                0, None, None, None, None, C.byref(h))
+        self.ctx.check(st)
+        self._sp, self._lkey, self._lops_ref = h, key, lops
+        return h
+
+    def pattern(self):
+        """Union sparsity pattern of the cache as (colptr, rowval), 1-based like SparseMatrixCSC."""
+        sp = self._sparse_op(self._lops_ref)
+        nnz = C.c_int64()
+        self.ctx.lib.oqb_sparse_pattern_nnz(sp, C.byref(nnz))
+        cp = np.zeros(self.size[0] + 1, dtype=np.int64)
+        rv = np.zeros(max(nnz.value, 1), dtype=np.int64)
+        self.ctx.lib.oqb_sparse_pattern(sp, cp.ctypes.data_as(_lib.c_i64p), rv.ctypes.data_as(_lib.c_i64p))
+        return cp, rv[:nnz.value]
+
+    def _cache_to_scipy(self, vals: np.ndarray):
+        import scipy.sparse as sps
+        cp, rv = self.pattern()
+        return sps.csc_matrix((vals, rv - 1, cp - 1), shape=self.size)
+
+    def update_cache(self, s, gamma=None):
+        """update_cache!(cache, H::SparseHamiltonian, p, s) :70-75 (+ lindblad.jl:103-109 when γ given):
+        returns the cache as a scipy CSC matrix on the union pattern."""
+        sp = self._sparse_op(self._lops_ref)
+        cp, rv = self.pattern()
+        out = DeviceBatch(1, max(len(rv), 1), 1, self.ctx)
+        cf = _coef(self.f, _svec(s, 1))
+        g = None if gamma is None else np.ascontiguousarray(gamma, dtype=np.float64)
+        self.ctx.check(self.ctx.lib.oqb_sparse_update_cache(sp, 1, _lib.dptr(cf), 1, _lib.dptr(g), 1, out.ptr))
+        return self._cache_to_scipy(out.to_host()[0][:len(rv)])
+
+    def __call__(self, *args):
+        if len(args) == 1:  # H(s) = i · (−iH)
+            return 1j * self.update_cache(args[0])
+        du, u, p, s = args
+        return self.commutator(du, u, s)
+
+    def commutator(self, du, u, s):
+        """(h::SparseHamiltonian)(du,u,p,s) :83-91 — du = −i(H u − u H), OVERWRITES."""
+        io = _HostIO(u, du)
+        B = io.u.B
+        sv = _svec(s, B)
+        cf = _coef(self.f, sv)
+        self.ctx.check(self.ctx.lib.oqb_sparse_commutator(self._sparse_op(self._lops_ref), B, _lib.dptr(cf),
+                                                          int(sv.size == 1), io.u.ptr, io.du.ptr))
+        return io.finish()
+
+    def host_matrix(self, s: float):
+        H = None
+        for f, m in zip(self.f, self.m):
+            H = f(s) * m if H is None else H + f(s) * m
+        return H
+
+
+def haml_eigs(H, s: float, lvl: Optional[int]):
+    """src/hamiltonian/hamiltonian_base.jl:155-160 — LAPACK on the host, as in the reference
+    ((w, v) are INPUTS of the device path so that gap grouping cannot flip)."""
+    import scipy.linalg as sla
+    import scipy.sparse as sps
+    h = H.host_matrix(s)
+    h = h.toarray() if sps.issparse(h) else h
+    n = h.shape[0]
+    if lvl is None or lvl >= n:
+        return sla.eigh(h)
+    return sla.eigh(h, subset_by_index=[0, lvl - 1])
+
+
+# --------------------------------------------------------------------------------------------
+# Lindblad
+# --------------------------------------------------------------------------------------------
+class Lindblad:
+    """src/coupling/interaction.jl:32-55."""
+
+    def __init__(self, gamma, L):
+        if callable(gamma):
+            if not isinstance(gamma(0.0), (int, float, complex, np.number)):
+                raise ValueError("γ should return a number.")  # :45-47
+            self.gamma = gamma
+        else:
+            self.gamma = lambda s, g=gamma: g
+        if callable(L):
+            raise NotImplementedError("time-dependent Lindblad operators L(s) are not on the device path yet")
+        self.L = L
+        self.size = L.shape
+
+
+class LindbladLiouvillian:
+    """src/opensys/lindblad.jl:76-109."""
+
+    def __init__(self, linds: Sequence[Lindblad]):
+        if any(l.size != linds[0].size for l in linds):
+            raise ValueError("All Lindblad operators should have the same size.")  # :88-90
+        self.g = [l.gamma for l in linds]
+        self.L = [l.L for l in linds]
+        self.size = linds[0].size
+        self._holder = None
+
+    def __len__(self):
+        return len(self.g)
+
+    def gammas(self, svals):
+        return _coef(self.g, svals)
+
+    def _op(self, ctx):
+        if self._holder is None:  # a Hamiltonian-less dense operator that only carries the L_k
+            self._holder = _LindHolder(self, ctx)
+        return self._holder
+
+    def __call__(self, du, u, p, t):
+        """(Lind::LindbladLiouvillian)(du,u,p,t) :94-101 — ACCUMULATES into du."""
+        io = _HostIO(u, du)
+        B = io.u.B
+        sv = _svec(p(t), B)
+        g = self.gammas(sv)
+        hold = self._op(io.u.ctx)
+        hold.ctx.check(hold.ctx.lib.oqb_lindblad_acc(hold.h, B, _lib.dptr(g), int(sv.size == 1), io.u.ptr, io.du.ptr))
+        return io.finish()
+
+    def update_cache(self, cache, p, t):
+        """update_cache!(cache, lind, p, t) :103-109 — cache −= ½γL'L (ACCUMULATES): evaluated as the
+        Lindblad part of oqb_dense_update_cache with zero Hamiltonian terms, then added."""
+        io = _HostIO(cache, cache)
+        B = io.u.B
+        sv = _svec(p(t), B)
+        g = self.gammas(sv)
+        hold = self._op(io.u.ctx)
+        tmp = io.u.zeros_like()
+        cf = np.zeros((1, 1))
+        hold.ctx.check(hold.ctx.lib.oqb_dense_update_cache(hold.h, B, _lib.dptr(cf), 1, _lib.dptr(g),
+                                                           int(sv.size == 1), tmp.ptr))
+        hold.ctx.sync()
+        io.du.t += tmp.t
+        return io.finish()
+
+
+class _LindHolder:
+    def __init__(self, lind: LindbladLiouvillian, ctx: Context):
+        self.ctx = ctx
+        n = lind.size[0]
+        zero = np.zeros((1, n, n), dtype=C128)
+        lbuf = _colmajor_stack([L.toarray() if hasattr(L, "toarray") else L for L in lind.L])
+        h = C.c_void_p()
+        ctx.check(ctx.lib.oqb_dense_create(ctx.h, n, 1, zero.ctypes.data, len(lind.L), lbuf.ctypes.data, C.byref(h)))
+        self.h = h
+
+
+# --------------------------------------------------------------------------------------------
+# couplings / baths
+# --------------------------------------------------------------------------------------------
+class ConstantCouplings:
+    """src/coupling/coupling.jl:10-71 (matrix form; strings are a fixture-builder concern)."""
+
+    def __init__(self, mats, unit="h"):
+        self.mats = [unit_scale(unit) * np.asarray(m, dtype=C128) for m in mats]
+
+    def __call__(self, s):
+        return self.mats
+
+    def __len__(self):
+        return len(self.mats)
+
+
+class OhmicBath:
+    """src/bath/ohmic.jl:13-41."""
+
+    def __init__(self, eta, wc, beta):
+        self.eta, self.wc, self.beta = eta, wc, beta
+
+    def spectrum(self, w):
+        if abs(w) <= 1e-9:  # isapprox(ω, 0, atol=1e-9)
+            return 2 * math.pi * self.eta / self.beta
+        return 2 * math.pi * self.eta * w * math.exp(-abs(w) / self.wc) / (1 - math.exp(-self.beta * w))
+
+    __call__ = spectrum
+
+    def vectorized(self, w):
+        return ohmic_spectrum_vec(self.eta, self.wc, self.beta, w)
+
+
+def Ohmic(eta, fc, T) -> OhmicBath:
+    """src/bath/ohmic.jl:24-28 with temperature_2_β of src/unit_util.jl:13-15."""
+    return OhmicBath(eta, 2 * math.pi * fc, 5 * 6.62607004 / 1.38064852 / math.pi / T)
+
+
+class _Zero:
+    def __call__(self, w):
+        return 0.0
+
+    def vectorized(self, w):
+        return np.zeros(np.shape(w))
+
+
+ZERO_LAMBSHIFT = _Zero()  # build_lambshift(..., turn_on=false) → (ω)->0.0, src/bath/bath_util.jl:36-38
+
+
+# --------------------------------------------------------------------------------------------
+# eigenbasis Liouvillians
+# --------------------------------------------------------------------------------------------
+class DaviesGenerator:
+    """src/opensys/davies.jl:12-19.  coupling: ConstantCouplings (or a list of matrices, already
+    unit-scaled); γ, S: host closures (objects with `.vectorized` are evaluated array-wise)."""
+
+    def __init__(self, coupling, gamma, S):
+        self.coupling = coupling if callable(coupling) else ConstantCouplings(coupling, unit="ħ")
+        self.gamma, self.S = gamma, S
+
+
+class OneSidedAMELiouvillian:
+    """src/opensys/davies.jl:356-365.  inds: 1-based (α,β) pairs like the reference."""
+
+    def __init__(self, coupling, gamma, S, inds):
+        self.coupling = coupling if callable(coupling) else ConstantCouplings(coupling, unit="ħ")
+        self.gamma, self.S, self.inds = gamma, S, [tuple(x) for x in inds]
+
+
+class GapIndices:
+    """src/opensys/opensys_util.jl:10-67 — carried as the sort-based GapGroups (same grouping)."""
+
+    def __init__(self, w, digits=8, sigdigits=8):
+        self.groups = GapGroups(w, digits, sigdigits)
+        self.w = self.groups.w
+
+
+class DiffEqLiouvillian:
+    """src/opensys/diffeq_liouvillian.jl:11-128.
+
+    {false,false}: Hamiltonian commutator + `opensys` terms (Lindblad, Redfield).
+    {true,false}:  eigenbasis terms (`opensys_eig`: Davies / one-sided AME) + `opensys`.
+    """
+
+    def __init__(self, H, opensys_eig, opensys, lvl, digits=8, sigdigits=8):
+        n = H.size[0]
+        if (not isinstance(H, SparseHamiltonian)) and n <= 10:
+            lvl = n  # :46-48
+        else:
+            lvl = min(n, lvl)  # :50
+        self.H, self.opensys_eig, self.opensys = H, list(opensys_eig), list(opensys)
+        self.lvl, self.digits, self.sigdigits = lvl, digits, sigdigits
+        self.diagonalization = len(self.opensys_eig) > 0
+        self.ctx = H.ctx
+        self._ame = None
+        self._ame_s = None
+        self._lind = [x for x in self.opensys if isinstance(x, LindbladLiouvillian)]
+        self._other = [x for x in self.opensys if not isinstance(x, LindbladLiouvillian)]
+
+    # ---- {false,false} ------------------------------------------------------------------
+    def _fused_lindblad(self):
+        return (isinstance(self.H, DenseHamiltonian) and len(self._lind) == 1)
+
+    def __call__(self, du, u, p, t):
+        if self.diagonalization:
+            return self._rhs_eig(du, u, p, t)
+        io = _HostIO(u, du)
+        B = io.u.B
+        sv = _svec(p(t), B)
+        rest = list(self.opensys)
+        if self._fused_lindblad():
+            lind = self._lind[0]
+            cf = _coef(self.H.f, sv)
+            g = lind.gammas(sv)
+            op = self.H._dense_op(lind.L)
+            self.ctx.check(self.ctx.lib.oqb_dense_rhs(op, B, _lib.dptr(cf), int(sv.size == 1), _lib.dptr(g),
+                                                      int(sv.size == 1), io.u.ptr, io.du.ptr))
+            rest = self._other
+        else:
+            self.H.commutator(io.du, io.u, sv if sv.size > 1 else sv[0])  # :72
+        for lv in rest:  # :73-75, each ACCUMULATES
+            lv(io.du, io.u, p, t)
+        return io.finish()
+
+    def rhs_host(self, du: np.ndarray, u: np.ndarray, p, t):
+        """Same RHS with HOST buffers laid out like Julia arrays (B blocks of column-major n×n):
+        the H2D/D2H copies are inside the call and pipelined against the kernels."""
+        B = u.shape[0]
+        sv = _svec(p(t), B)
+        if self.diagonalization:
+            self._prepare_ame(float(sv[0]))
+            self.ctx.check(self.ctx.lib.oqb_ame_rhs_host(self._ame, B, u.ctypes.data, du.ctypes.data))
+            return du
+        if not self._fused_lindblad() and (self.opensys or not isinstance(self.H, DenseHamiltonian)):
+            raise NotImplementedError("rhs_host supports DenseHamiltonian (+ one LindbladLiouvillian) or AME")
+        cf = _coef(self.H.f, sv)
+        lind = self._lind[0] if self._lind else None
+        g = lind.gammas(sv) if lind else None
+        op = self.H._dense_op(lind.L if lind else None)
+        self.ctx.check(self.ctx.lib.oqb_dense_rhs_host(op, B, _lib.dptr(cf), int(sv.size == 1), _lib.dptr(g),
+                                                       int(sv.size == 1), u.ctypes.data, du.ctypes.data))
+        return du
+
+    # ---- {true,false} -------------------------------------------------------------------
+    def _prepare_ame(self, s: float, w=None, v=None):
+        """Everything that is shared by the batch for one value of s: eigen-system (host LAPACK, or
+        supplied), gap groups, γ/S tables, device tables."""
+        key = (s, None if w is None else id(w))
+        if self._ame is not None and self._ame_s == key:
+            return
+        lib, ctx = self.ctx.lib, self.ctx
+        if w is None:
+            w, v = haml_eigs(self.H, s, self.lvl)  # :94
+        w = np.ascontiguousarray(np.real(w), dtype=np.float64)
+        n, lvl = self.H.size[0], len(w)
+        # couplings of all eigenbasis terms, concatenated; remember each term's slice
+        coup, slices = [], []
+        for lv in self.opensys_eig:
+            c = [np.asarray(m, dtype=C128) for m in lv.coupling(s)]
+            slices.append((len(coup), len(coup) + len(c)))
+            coup += c
+        if self._ame is not None:
+            lib.oqb_ame_destroy(self._ame)
+        h = C.c_void_p()
+        cbuf = _colmajor_stack(coup)
+        ctx.check(lib.oqb_ame_create(ctx.h, n, lvl, len(coup), cbuf.ctypes.data, C.byref(h)))
+        vbuf = np.ascontiguousarray(np.asarray(v, dtype=C128).T)  # column-major n×lvl
+        ctx.check(lib.oqb_ame_set_eigen(h, _lib.dptr(w), vbuf.ctypes.data))
+        groups = GapGroups(w, self.digits, self.sigdigits)  # :96
+        ndav = 0
+        for lv, (c0, c1) in zip(self.opensys_eig, slices):
+            if isinstance(lv, DaviesGenerator):
+                if ndav or c0 != 0 or c1 != len(coup):
+                    raise NotImplementedError("one DaviesGenerator per DiffEqLiouvillian (it owns all couplings)")
+                ndav += 1
+                gam, Sm, crate, lrs = groups.tables(lv.gamma, lv.S)
+                gam = np.ascontiguousarray(gam.T)  # column-major [a + b*l]
+                Sm = np.ascontiguousarray(Sm.T)
+                ci = np.ascontiguousarray(groups.cross_idx)
+                li = np.ascontiguousarray(groups.lamb_idx)
+                ctx.check(lib.oqb_ame_set_davies(
+                    h, _lib.dptr(gam), _lib.dptr(Sm), len(ci), ci.ctypes.data_as(_lib.c_i32p) if len(ci) else None,
+                    _lib.dptr(crate) if len(ci) else None, len(li),
+                    li.ctypes.data_as(_lib.c_i32p) if len(li) else None, _lib.dptr(lrs) if len(li) else None))
+            elif isinstance(lv, OneSidedAMELiouvillian):
+                from .gaps import _eval
+                gm = groups.gap_matrix  # UNROUNDED, davies.jl:368
+                uniq, inv = np.unique(gm.ravel(), return_inverse=True)
+                shared = not isinstance(lv.gamma, dict)
+                pairs = lv.inds
+                if shared:
+                    g1 = _eval(lv.gamma, uniq)[inv].reshape(lvl, lvl)
+                    s1 = _eval(lv.S, uniq)[inv].reshape(lvl, lvl)
+                    gt = np.ascontiguousarray(g1.T)[None]
+                    st_ = np.ascontiguousarray(s1.T)[None]
+                else:
+                    gt = np.stack([np.ascontiguousarray(_eval(lv.gamma[pq], uniq)[inv].reshape(lvl, lvl).T) for pq in pairs])
+                    st_ = np.stack([np.ascontiguousarray(_eval(lv.S[pq], uniq)[inv].reshape(lvl, lvl).T) for pq in pairs])
+                al = np.ascontiguousarray([c0 + a - 1 for a, _ in pairs], dtype=np.int32)
+                be = np.ascontiguousarray([c0 + b - 1 for _, b in pairs], dtype=np.int32)
+                gt, st_ = np.ascontiguousarray(gt), np.ascontiguousarray(st_)
+                ctx.check(lib.oqb_ame_set_onesided(h, len(pairs), al.ctypes.data_as(_lib.c_i32p),
+                                                   be.ctypes.data_as(_lib.c_i32p), _lib.dptr(gt), _lib.dptr(st_),
+                                                   int(shared)))
+            else:
+                raise NotImplementedError(f"eigenbasis term {type(lv).__name__} is not on the device path")
+        self._ame, self._ame_s = h, key
+        self._w, self._v = w, v
+
+    def _rhs_eig(self, du, u, p, t, w=None, v=None):
+        """(Op::DiffEqLiouvillian{true,false})(du,u,p,t) :92-109.  All members share s (one
+        eigen-system per call, like the reference's single haml_eigs)."""
+        io = _HostIO(u, du)
+        B = io.u.B
+        sv = _svec(p(t), B)
+        if sv.size > 1 and np.any(sv != sv[0]):
+            raise NotImplementedError("AME batches must share the annealing parameter s (one eigen-system per call)")
+        self._prepare_ame(float(sv[0]), w, v)
+        self.ctx.check(self.ctx.lib.oqb_ame_rhs(self._ame, B, io.u.ptr, io.du.ptr))
+        for lv in self.opensys:  # :106-108
+            lv(io.du, io.u, p, t)
+        return io.finish()
+
+    def rhs_with_eig(self, du, u, p, t, w, v):
+        """Same as the call operator with (w, v) supplied by the caller (identical inputs to the oracle)."""
+        return self._rhs_eig(du, u, p, t, w, v)
+
+    # ---- update_cache! ------------------------------------------------------------------
+    def update_cache(self, cache, p, t, w=None, v=None):
+        """update_cache!(cache, Op, p, t): :78-83 ({false,false}) or :111-128 ({true,false}) — OVERWRITES."""
+        s = float(np.atleast_1d(p(t))[0])
+        if self.diagonalization:
+            io = _HostIO(cache, cache)
+            self._prepare_ame(s, w, v)
+            self.ctx.check(self.ctx.lib.oqb_ame_update_cache(self._ame, io.du.ptr))
+            for lv in self.opensys:
+                lv.update_cache(io.du, p, t)
+            return io.finish()
+        if isinstance(self.H, SparseHamiltonian):
+            lind = self._lind[0] if self._lind else None
+            if lind is not None:
+                self.H._sparse_op(lind.L)
+            g = lind.gammas(_svec(s, 1))[0] if lind else None
+            return self.H.update_cache(s, g)
+        io = _HostIO(cache, cache)
+        B = io.u.B
+        sv = _svec(p(t), B)
+        cf = _coef(self.H.f, sv)
+        lind = self._lind[0] if self._lind else None
+        g = lind.gammas(sv) if lind else None
+        op = self.H._dense_op(lind.L if lind else None)
+        self.ctx.check(self.ctx.lib.oqb_dense_update_cache(op, B, _lib.dptr(cf), int(sv.size == 1), _lib.dptr(g),
+                                                           int(sv.size == 1), io.du.ptr))
+        return io.finish()
+
+    def update_vectorized_cache(self, cache, p, t):
+        """update_vectorized_cache!(cache, Op{false,false}, p, t) :85-90."""
+        io = _HostIO(cache, cache)
+        self.H.update_vectorized_cache(io.du, p(t))
+        for lv in self.opensys:
+            lv.update_vectorized_cache(io.du, p, t)
+        return io.finish()
+
+
+def update_cache_(cache, op, p, t, **kw):
+    """Julia's `update_cache!` generic (src/OpenQuantumBase.jl:134)."""
+    if isinstance(op, (DenseHamiltonian,)):
+        return op.update_cache(cache, t)
+    if isinstance(op, LindbladLiouvillian):
+        return op.update_cache(cache, p, t)
+    return op.update_cache(cache, p, t, **kw)
+
+
+def update_vectorized_cache_(cache, op, p, t):
+    """Julia's `update_vectorized_cache!` generic (src/OpenQuantumBase.jl:135)."""
+    if isinstance(op, (DenseHamiltonian, SparseHamiltonian)):
+        return op.update_vectorized_cache(cache, t)
+    return op.update_vectorized_cache(cache, p, t)
+
+
+# --------------------------------------------------------------------------------------------
+# Redfield
+# --------------------------------------------------------------------------------------------
+class RedfieldLiouvillian:
+    """src/opensys/redfield.jl:12-105.  The ρ-dependent half (K₂ = SΛρ − ΛρS; du −= K₂+K₂') runs on
+    the device.  Λ(t) = ∫ C(t,x) U(t)U(x)'S(p(x))U(x)U(t)' dx is closure-driven (U, cfun are host
+    functions) and ρ-independent: it is integrated on the host by `lambda_host` with the same
+    adaptive G7K15 scheme QuadGK uses, or supplied directly per batch member through `apply`."""
+
+    def __init__(self, kernels, unitary, Ta, atol, rtol):
+        self.kernels, self.unitary, self.Ta, self.atol, self.rtol = kernels, unitary, Ta, atol, rtol
+
+    def lambda_host(self, p, t):
+        from .quadrature import quadgk_matrix
+        out, Ss = [], []
+        s = p(t)
+        for (inds, coupling, cfun) in self.kernels:
+            for (i, j) in inds:
+                cf = cfun[(i, j)] if isinstance(cfun, dict) else cfun
+                cj = coupling[j - 1]
+                Ut = self.unitary(t)
+
+                def integrand(x, cj=cj, cf=cf, Ut=Ut):
+                    W = Ut @ self.unitary(x).conj().T
+                    Sx = cj(p(x)) if callable(cj) else cj
+                    return cf(t, x) * (W @ Sx @ W.conj().T)
+                out.append(quadgk_matrix(integrand, max(0.0, t - self.Ta), t, self.rtol, self.atol))
+                ci = coupling[i - 1]
+                Ss.append(ci(s) if callable(ci) else ci)
+        return Ss, out
+
+    def apply(self, du, u, S_list, Lam):
+        """du −= K₂+K₂' with Λ given: Lam (B, K, n, n) host array or DeviceBatch of B·K matrices."""
+        io = _HostIO(u, du)
+        B, n = io.u.B, io.u.rows
+        K = len(S_list)
+        ctx = io.u.ctx
+        Sd = DeviceBatch.from_host(np.stack([np.asarray(x, dtype=C128) for x in S_list]), ctx)
+        Ld = Lam if isinstance(Lam, DeviceBatch) else DeviceBatch.from_host(np.asarray(Lam, dtype=C128).reshape(B * K, n, n), ctx)
+        ctx.check(ctx.lib.oqb_redfield_apply_acc(ctx.h, n, K, Sd.ptr, 1, Ld.ptr, B, io.u.ptr, io.du.ptr))
+        ctx.sync()
+        return io.finish()
+
+    def __call__(self, du, u, p, t):
+        """(R::RedfieldLiouvillian)(du,u,p,t) :42-71 — ACCUMULATES.  One Λ set shared by the batch."""
+        io = _HostIO(u, du)
+        B, n = io.u.B, io.u.rows
+        Ss, Ls = self.lambda_host(p, float(np.atleast_1d(t)[0]))
+        Lam = np.broadcast_to(np.stack(Ls)[None], (B, len(Ls), n, n))
+        self.apply(io.du, io.u, Ss, Lam)
+        return io.finish()
+
+    def update_vectorized_cache(self, cache, p, t):
+        """update_vectorized_cache!(cache, R, p, t) :73-105 — ACCUMULATES."""
+        io = _HostIO(cache, cache)
+        ctx = io.u.ctx
+        Ss, Ls = self.lambda_host(p, float(t))
+        n = Ss[0].shape[0]
+        Sd = DeviceBatch.from_host(np.stack(Ss), ctx)
+        Ld = DeviceBatch.from_host(np.stack(Ls), ctx)
+        ctx.check(ctx.lib.oqb_redfield_vectorized_acc(ctx.h, n, len(Ss), Sd.ptr, 1, Ld.ptr, io.u.B, io.du.ptr))
+        ctx.sync()
+        return io.finish()
+
+
+# --------------------------------------------------------------------------------------------
+# trajectories
+# --------------------------------------------------------------------------------------------
+class TrajectoryEnsemble:
+    """ψ-ensemble view of a DiffEqLiouvillian{false,false} over a SparseHamiltonian with one
+    LindbladLiouvillian: the `cache*u` matvec the external solver performs with the cache of
+    src/opensys/diffeq_liouvillian.jl:78-83, ‖ψ‖², and lindblad_jump (src/opensys/trajectory_jump.jl:71-74)."""
+
+    def __init__(self, op: DiffEqLiouvillian):
+        if not isinstance(op.H, SparseHamiltonian):
+            raise TypeError("TrajectoryEnsemble needs a SparseHamiltonian")
+        self.op, self.H, self.ctx = op, op.H, op.ctx
+        self.lind = op._lind[0] if op._lind else None
+        self.sp = self.H._sparse_op(self.lind.L if self.lind else None)
+
+    def _coefs(self, p, t, B):
+        sv = _svec(p(t), B)
+        cf = _coef(self.H.f, sv)
+        g = self.lind.gammas(sv) if self.lind else None
+        gshared = 1
+        if g is not None:
+            if np.all(g == g[0]):
+                g = np.ascontiguousarray(g[:1])
+            else:
+                gshared = 0
+        return cf, int(sv.size == 1), g, gshared
+
+    def matvec(self, dpsi: DeviceBatch, psi: DeviceBatch, p, t):
+        cf, cshared, g, gshared = self._coefs(p, t, psi.B)
+        self.ctx.check(self.ctx.lib.oqb_traj_matvec(self.sp, psi.B, _lib.dptr(cf), cshared, _lib.dptr(g), gshared,
+                                                    psi.ptr, dpsi.ptr))
+        return dpsi
+
+    def matvec_host(self, dpsi: np.ndarray, psi: np.ndarray, p, t):
+        """HOST buffers (B, n) complex128, C-contiguous."""
+        cf, cshared, g, gshared = self._coefs(p, t, psi.shape[0])
+        self.ctx.check(self.ctx.lib.oqb_traj_matvec_host(self.sp, psi.shape[0], _lib.dptr(cf), cshared, _lib.dptr(g),
+                                                         gshared, psi.ctypes.data, dpsi.ctypes.data))
+        return dpsi
+
+    def norm2(self, psi: DeviceBatch):
+        import torch
+        out = torch.zeros(psi.B, dtype=torch.float64, device=psi.t.device)
+        self.ctx.check(self.ctx.lib.oqb_traj_norm2(self.sp, psi.B, psi.ptr, C.c_void_p(out.data_ptr())))
+        self.ctx.sync()
+        return out
+
+    def lindblad_jump(self, psi: DeviceBatch, p, t, uniforms, mask=None, apply=False):
+        """lindblad_jump(Op{false,false}, u, p, t): returns (choice[B] 0-based, prob[B,K]).  `uniforms`
+        are the numbers `rand()` would have produced (one per member); apply=True also performs the
+        ψ ← L_kψ/‖L_kψ‖ update of the external affect!."""
+        import torch
+        B, K = psi.B, len(self.lind)
+        dev = psi.t.device
+        _, _, g, gshared = self._coefs(p, t, B)
+        u_d = torch.as_tensor(np.asarray(uniforms, dtype=np.float64), device=dev)
+        m_d = None if mask is None else torch.as_tensor(np.asarray(mask, dtype=np.uint8), device=dev)
+        choice = torch.zeros(B, dtype=torch.int32, device=dev)
+        prob = torch.zeros((B, K), dtype=torch.float64, device=dev)
+        self.ctx.check(self.ctx.lib.oqb_traj_jump(
+            self.sp, B, _lib.dptr(g), gshared, psi.ptr, C.c_void_p(u_d.data_ptr()),
+            None if m_d is None else C.c_void_p(m_d.data_ptr()), C.c_void_p(choice.data_ptr()),
+            C.c_void_p(prob.data_ptr()), int(apply)))
+        self.ctx.sync()
+        return choice, prob
+
+
+def expect(obs: Sequence[np.ndarray], state: DeviceBatch):
+    """⟨O⟩ per member: tr(Oρ_b) for matrices, ψ_b'Oψ_b for vectors → complex tensor (B, nobs) on
+    the device (the per-GPU partial result that is then reduced with NCCL)."""
+    import torch
+    ctx = state.ctx
+    n = state.rows
+    Od = DeviceBatch.from_host(np.stack([np.asarray(o, dtype=C128) for o in obs]), ctx)
+    out = torch.zeros((state.B, len(obs)), dtype=torch.complex128, device=state.t.device)
+    ctx.check(ctx.lib.oqb_expect(ctx.h, n, len(obs), Od.ptr, state.B, state.ptr, int(state.cols == 1),
+                                 C.c_void_p(out.data_ptr())))
+    ctx.sync()
+    return out

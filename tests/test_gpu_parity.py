@@ -1,0 +1,462 @@
+"""GPU parity tests: the CUDA path (through the C ABI, via the host mirror) against the CPU oracle on
+identical seeded inputs.  Tolerance: relative Frobenius error ≤ 1e-12 (BASELINE.json north_star);
+discrete outputs (jump indices) must match exactly.  Run on the B200 box with `-m gpu`."""
+import numpy as np
+import pytest
+import scipy.linalg as sla
+import scipy.sparse as sps
+
+from oracle import fixtures as F
+from oracle import oqb_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-12
+sx, sy, sz, si = F.sx, F.sy, F.sz, F.si
+A = lambda s: 1 - s
+B = lambda s: s
+
+
+def gamma(x):  # mock bath of reference test/opensys/davies.jl:7-8
+    return x + 1 if x >= 0 else (1 - x) * np.exp(x)
+
+
+def lamb(x):
+    return x + 0.1
+
+
+@pytest.fixture(scope="module")
+def Q():
+    import oqb_b200
+    oqb_b200.get_context()
+    return oqb_b200
+
+
+def relerr(a, b):
+    a = np.asarray(a); b = np.asarray(b)
+    nb = np.linalg.norm(b)
+    return np.linalg.norm(a - b) / (nb if nb > 0 else 1.0)
+
+
+def rand_c(rng, *shape):
+    return rng.standard_normal(shape) + 1j * rng.standard_normal(shape)
+
+
+def rand_rho(rng, B_, n):
+    return np.stack([F.random_density_matrix(n, rng) for _ in range(B_)])
+
+
+# ---------------------------------------------------------------------------------------------
+# K1: batched ZGEMM
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("M,N,K,batch", [(2, 2, 2, 1), (4, 3, 5, 3), (16, 16, 16, 2), (33, 65, 17, 2),
+                                         (64, 64, 64, 3), (128, 64, 72, 2), (130, 70, 9, 2), (256, 256, 256, 2)])
+@pytest.mark.parametrize("opA,opB", [(0, 0), (2, 0), (0, 2), (2, 2), (1, 1)])
+def test_zgemm(Q, M, N, K, batch, opA, opB):
+    import ctypes as C
+    rng = np.random.default_rng(M * 1000 + N * 10 + K + opA * 7 + opB)
+    ctx = Q.get_context()
+    a_shape = (K, M) if opA else (M, K)
+    b_shape = (N, K) if opB else (K, N)
+    Ah = rand_c(rng, batch, *a_shape)
+    Bh = rand_c(rng, *b_shape)  # shared across the batch (stride 0)
+    Ch = rand_c(rng, batch, M, N)
+    alpha, beta = 0.7 - 0.3j, -0.2 + 1.1j
+    op = {0: lambda x: x, 1: lambda x: x.transpose(0, 2, 1) if x.ndim == 3 else x.T,
+          2: lambda x: x.conj().transpose(0, 2, 1) if x.ndim == 3 else x.conj().T}
+    ref = alpha * (op[opA](Ah) @ op[opB](Bh)) + beta * Ch
+    Ad, Bd, Cd = Q.DeviceBatch.from_host(Ah), Q.DeviceBatch.from_host(Bh[None]), Q.DeviceBatch.from_host(Ch)
+    al = np.array([alpha.real, alpha.imag]); be = np.array([beta.real, beta.imag])
+    dp = lambda x: x.ctypes.data_as(C.POINTER(C.c_double))
+    ctx.check(ctx.lib.oqb_zgemm_batched(ctx.h, opA, opB, M, N, K, dp(al), Ad.ptr, a_shape[0], a_shape[0] * a_shape[1],
+                                        Bd.ptr, b_shape[0], 0, dp(be), Cd.ptr, M, M * N, batch))
+    assert relerr(Cd.to_host(), ref) < 1e-13
+
+
+# ---------------------------------------------------------------------------------------------
+# H-d: DenseHamiltonian  (reference test/hamiltonian/dense_hamiltonian.jl:23-38)
+# ---------------------------------------------------------------------------------------------
+def test_dense_hamiltonian_golden(Q):
+    H = Q.DenseHamiltonian([A, B], [sx, sz])
+    assert np.array_equal(H(0.5), np.pi * (sx + sz))
+    Cc = H.update_cache(np.zeros((2, 2), complex), 0.5)
+    assert np.array_equal(Cc, -1j * np.pi * (sx + sz))
+    T = -1j * np.pi * (sx + sz)
+    V = H.update_vectorized_cache(np.zeros((4, 4), complex), 0.5)
+    assert np.array_equal(V, np.kron(si, T) - np.kron(T.T, si))
+    rho = np.outer(F.PauliVec[0][0], F.PauliVec[0][0].conj())
+    du = np.array([[1.0 + 0j, 0], [0, 0]])  # pre-filled with garbage: the call must OVERWRITE
+    H(du, rho, 2, 0.5)
+    assert relerr(du, -1j * np.pi * ((sx + sz) @ rho - rho @ (sx + sz))) < 1e-15
+    with pytest.raises(ValueError):
+        Q.DenseHamiltonian([A, B], [sx, sz], unit="hh")
+
+
+@pytest.mark.parametrize("n,nb", [(3, 4), (16, 5), (100, 3), (256, 6)])
+def test_dense_commutator_batched_per_member_s(Q, n, nb):
+    rng = np.random.default_rng(n)
+    m1, m2, m3 = [(lambda g: g + g.conj().T)(rand_c(rng, n, n)) for _ in range(3)]
+    fs = [lambda s: 1 - s, lambda s: s, lambda s: np.sin(3 * s)]
+    Hg = Q.DenseHamiltonian(fs, [m1, m2, m3], unit="ħ")
+    Ho = O.DenseHamiltonian(fs, [m1, m2, m3], unit="ħ")
+    u = rand_c(rng, nb, n, n)  # no Hermiticity assumed
+    s = rng.random(nb)
+    du = Hg(np.full_like(u, 7.0), u, None, s)
+    ref = np.stack([Ho.rhs(u[b], s[b]) for b in range(nb)])
+    assert relerr(du, ref) < TOL
+    c = Hg.update_cache(np.zeros_like(u), s)
+    assert relerr(c, np.stack([Ho.update_cache(x) for x in s])) < 1e-15
+    if n <= 16:
+        v = Hg.update_vectorized_cache(np.zeros((nb, n * n, n * n), complex), s)
+        assert relerr(v, np.stack([Ho.update_vectorized_cache(x) for x in s])) < 1e-15
+
+
+# ---------------------------------------------------------------------------------------------
+# L: Lindblad  (reference test/opensys/lindblad.jl:25-46)
+# ---------------------------------------------------------------------------------------------
+def test_lindblad_golden(Q):
+    p = Q.ODEParams(None, 5.0, lambda tf, t: t / tf)
+    rho = np.outer(F.PauliVec[0][0], F.PauliVec[0][0].conj())
+    L1 = Q.LindbladLiouvillian([Q.Lindblad(0.5, sz)])
+    d = L1(np.zeros((2, 2), complex), rho, p, 5.0)
+    assert np.allclose(d, [[0, -0.5], [-0.5, 0]], atol=1e-15)
+    c = Q.update_cache_(np.zeros((2, 2), complex), L1, p, 5.0)
+    assert np.array_equal(c, -0.25 * sz.conj().T @ sz)
+    L2 = Q.LindbladLiouvillian([Q.Lindblad(0.5, sz), Q.Lindblad(0.2, sx)])
+    rho_y = np.outer(F.PauliVec[1][0], F.PauliVec[1][0].conj())
+    d = L2(np.zeros((2, 2), complex), rho_y, p, 5.0)
+    assert np.allclose(d, [[0, 0.7j], [-0.7j, 0]], atol=1e-15)
+    c = Q.update_cache_(np.zeros((2, 2), complex), L2, p, 5.0)
+    assert np.allclose(c, -0.25 * sz.conj().T @ sz - 0.1 * sx.conj().T @ sx, atol=1e-16)
+    with pytest.raises(ValueError):
+        Q.LindbladLiouvillian([Q.Lindblad(0.5, sz), Q.Lindblad(0.2, np.eye(3))])
+
+
+@pytest.mark.parametrize("n,K,nb,dense_L", [(4, 2, 3, True), (16, 3, 5, True), (64, 8, 4, False), (128, 4, 3, True)])
+def test_lindblad_full_rhs_vs_oracle(Q, n, K, nb, dense_L):
+    """DiffEqLiouvillian{false,false} = commutator + Lindblad, per-member s (config C2 shape)."""
+    rng = np.random.default_rng(100 + n)
+    m1, m2 = [(lambda g: g + g.conj().T)(rand_c(rng, n, n)) for _ in range(2)]
+    fs = [lambda s: -(1 - s), lambda s: s]
+    if dense_L:
+        Ls = [rand_c(rng, n, n) / np.sqrt(n) for _ in range(K)]
+    else:
+        nq = int(np.log2(n))
+        Ls = [F.single_clause(["z"], [k % nq + 1], 1.0, nq) for k in range(K)]
+    gfs = [lambda s, k=k: 0.1 * (1 + k / 8) * (1 + s) for k in range(K)]
+    Hg = Q.DenseHamiltonian(fs, [m1, m2], unit="ħ")
+    lg = Q.LindbladLiouvillian([Q.Lindblad(g, L) for g, L in zip(gfs, Ls)])
+    opg = Q.DiffEqLiouvillian(Hg, [], [lg], n)
+    Ho = O.DenseHamiltonian(fs, [m1, m2], unit="ħ")
+    lo = O.LindbladLiouvillian([O.Lindblad(g, L) for g, L in zip(gfs, Ls)])
+    opo = O.DiffEqLiouvillian(Ho, [], [lo], n)
+    u = rand_c(rng, nb, n, n)
+    tf = 10.0
+    t = rng.random(nb) * tf
+    pg = Q.ODEParams(None, tf)
+    du = opg(np.zeros_like(u), u, pg, t)
+    ref = np.stack([opo.rhs(u[b], O.ODEParams(None, tf), t[b]) for b in range(nb)])
+    assert relerr(du, ref) < TOL
+    # shared s
+    du = opg(np.zeros_like(u), u, pg, 2.5)
+    ref = np.stack([opo.rhs(u[b], O.ODEParams(None, tf), 2.5) for b in range(nb)])
+    assert relerr(du, ref) < TOL
+    # accumulate-only form and update_cache!
+    acc0 = rand_c(rng, nb, n, n)
+    d2 = lg(acc0.copy(), u, pg, 2.5)
+    ref2 = np.stack([lo.rhs_acc(acc0[b].copy(), u[b], O.ODEParams(None, tf), 2.5) for b in range(nb)])
+    assert relerr(d2, ref2) < TOL
+    cache = opg.update_cache(np.zeros((n, n), complex), pg, 2.5)
+    assert relerr(cache, opo.update_cache(O.ODEParams(None, tf), 2.5)) < 1e-13
+    # host-buffer entry point (column-major blocks, like a Julia Array{ComplexF64,3})
+    uh = np.ascontiguousarray(u.transpose(0, 2, 1))
+    duh = np.zeros_like(uh)
+    opg.rhs_host(duh, uh, pg, t)
+    ref = np.stack([opo.rhs(u[b], O.ODEParams(None, tf), t[b]) for b in range(nb)])
+    assert relerr(duh.transpose(0, 2, 1), ref) < TOL
+
+
+# ---------------------------------------------------------------------------------------------
+# D1 / DV / OS: AME   (reference test/opensys/davies.jl)
+# ---------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def ame2q():
+    mats = [-F.standard_driver(2), 0.1 * np.kron(sz, si) + 0.5 * np.kron(sz, sz)]
+    Ho = O.DenseHamiltonian([A, B], mats)
+    coup = [2 * np.pi * F.q_translate("ZI+IZ")]
+    w, v = O.haml_eigs(Ho, 0.5, 4)
+    psi = (v[:, 0] + v[:, 1] + v[:, 2]) / np.sqrt(3)
+    rho = np.outer(psi, psi.conj())
+    return dict(mats=mats, Ho=Ho, coup=coup, w=w, v=v, rho=rho)
+
+
+def test_ame_2qubit_fixture(Q, ame2q):
+    d = ame2q
+    Hg = Q.DenseHamiltonian([A, B], d["mats"])
+    dav_g = Q.DaviesGenerator(d["coup"], gamma, lamb)
+    opg = Q.DiffEqLiouvillian(Hg, [dav_g], [], 4)
+    dav_o = O.DaviesGenerator(d["coup"], gamma, lamb)
+    opo = O.DiffEqLiouvillian(d["Ho"], [dav_o], [], 4)
+    pg, po = Q.ODEParams(None, 2.0), O.ODEParams(None, 2.0)
+    rng = np.random.default_rng(5)
+    u = np.concatenate([d["rho"][None], rand_rho(rng, 4, 4), rand_c(rng, 2, 4, 4)])
+    du = opg.rhs_with_eig(np.zeros_like(u), u, pg, 1.0, d["w"], d["v"])
+    ref = np.stack([opo.rhs_with_eig(x, po, 1.0, d["w"], d["v"]) for x in u])
+    assert relerr(du, ref) < TOL
+    assert np.linalg.norm(du[0]) == pytest.approx(451.9527156261307, rel=1e-9)
+    # the reference's own expectation (atol=rtol=1e-6, test/opensys/davies.jl:57-61)
+    w2 = d["w"]
+    drho = O.ame_update_test([2 * np.pi * (np.kron(sz, si) + np.kron(si, sz))], d["rho"], w2, d["v"], gamma, lamb)
+    h = d["Ho"](0.5)
+    assert relerr(du[0], drho - 1j * (h @ d["rho"] - d["rho"] @ h)) < 1e-6
+    # own host LAPACK path
+    du2 = opg(np.zeros_like(u), u, pg, 1.0)
+    ref2 = np.stack([opo.rhs(x, po, 1.0) for x in u])
+    assert relerr(du2, ref2) < 1e-9  # eigenvector gauge may differ between two eigh calls
+    # update_cache! (test/opensys/davies.jl:49-55)
+    cache = opg.update_cache(np.zeros((4, 4), complex), pg, 1.0, d["w"], d["v"])
+    assert relerr(cache, opo.update_cache(po, 1.0, d["w"], d["v"])) < TOL
+
+
+def test_onesided_ame(Q, ame2q):
+    d = ame2q
+    Hg = Q.DenseHamiltonian([A, B], d["mats"])
+    one_g = Q.OneSidedAMELiouvillian(d["coup"], gamma, lamb, [(1, 1)])
+    one_o = O.OneSidedAMELiouvillian(d["coup"], gamma, lamb, [(1, 1)])
+    opg = Q.DiffEqLiouvillian(Hg, [one_g], [], 4)
+    opo = O.DiffEqLiouvillian(d["Ho"], [one_o], [], 4)
+    rng = np.random.default_rng(6)
+    u = np.concatenate([d["rho"][None], rand_c(rng, 3, 4, 4)])
+    du = opg.rhs_with_eig(np.zeros_like(u), u, Q.ODEParams(None, 2.0), 1.0, d["w"], d["v"])
+    ref = np.stack([opo.rhs_with_eig(x, O.ODEParams(None, 2.0), 1.0, d["w"], d["v"]) for x in u])
+    assert relerr(du, ref) < TOL
+
+
+@pytest.mark.parametrize("spectrum", ["generic", "equal_spaced", "degenerate", "unsorted"])
+@pytest.mark.parametrize("K", [1, 2])
+def test_davies_closed_form_vs_literal_loop(Q, spectrum, K):
+    """The device closed form (+ cross terms) against the oracle's literal per-gap-group loop
+    (src/opensys/davies.jl:21-47) on spectra that exercise singleton, multi-pair and zero-gap groups."""
+    rng = np.random.default_rng({"generic": 1, "equal_spaced": 2, "degenerate": 3, "unsorted": 4}[spectrum] * 10 + K)
+    l = 7
+    w = {"generic": np.sort(rng.standard_normal(l) * 3),
+         "equal_spaced": np.arange(l) * 0.75 - 2.0,
+         "degenerate": np.array([-2.0, -2.0, -0.5, 0.3, 0.3, 0.3, 1.9]),
+         "unsorted": np.array([0.4, -1.0, 2.0, 0.4 + 1.5, 1.0, -1.0 + 1.5, 0.0])}[spectrum]
+    g = rand_c(rng, l, l)
+    v = np.linalg.qr(g)[0]
+    Hmat = v @ np.diag(w) @ v.conj().T
+    coup = [(lambda x: x + x.conj().T)(rand_c(rng, l, l)) for _ in range(K)]
+    one = lambda s: 1.0
+    Hg = Q.DenseHamiltonian([one], [Hmat], unit="ħ")
+    Ho = O.DenseHamiltonian([one], [Hmat], unit="ħ")
+    opg = Q.DiffEqLiouvillian(Hg, [Q.DaviesGenerator(coup, gamma, lamb)], [], l)
+    opo = O.DiffEqLiouvillian(Ho, [O.DaviesGenerator(coup, gamma, lamb)], [], l)
+    u = rand_c(rng, 3, l, l)
+    pg, po = Q.ODEParams(None, 1.0), O.ODEParams(None, 1.0)
+    du = opg.rhs_with_eig(np.zeros_like(u), u, pg, 0.5, w, v)
+    ref = np.stack([opo.rhs_with_eig(x, po, 0.5, w, v) for x in u])
+    assert relerr(du, ref) < TOL
+    cache = opg.update_cache(np.zeros((l, l), complex), pg, 0.5, w, v)
+    assert relerr(cache, opo.update_cache(po, 0.5, w, v)) < TOL
+
+
+def test_ame_sparse_truncated(Q):
+    """4-qubit SparseHamiltonian, lvl = 4 of 16 (reference test/opensys/davies.jl:112-145)."""
+    Hd = sps.csc_matrix(F.standard_driver(4))
+    Hp = sps.csc_matrix(F.q_translate("-0.9ZZII+IZZI-0.9IIZZ"))
+    coup = [2 * np.pi * F.q_translate("ZIII+IZII+IIZI+IIIZ")]
+    Hg = Q.SparseHamiltonian([A, B], [Hd, Hp])
+    Ho = O.SparseHamiltonian([A, B], [Hd, Hp])
+    opg = Q.DiffEqLiouvillian(Hg, [Q.DaviesGenerator(coup, gamma, lamb)], [], 4)
+    opo = O.DiffEqLiouvillian(Ho, [O.DaviesGenerator(coup, gamma, lamb)], [], 4)
+    assert opg.lvl == 4
+    w, v = O.haml_eigs(Ho, 0.5, 4)
+    psi = (v[:, 0] + v[:, 1] + v[:, 2]) / np.sqrt(3)
+    rng = np.random.default_rng(8)
+    u = np.concatenate([np.outer(psi, psi.conj())[None], rand_rho(rng, 2, 16)])
+    pg, po = Q.ODEParams(None, 2.0), O.ODEParams(None, 2.0)
+    du = opg.rhs_with_eig(np.zeros_like(u), u, pg, 1.0, w, v)
+    ref = np.stack([opo.rhs_with_eig(x, po, 1.0, w, v) for x in u])
+    assert relerr(du, ref) < TOL
+    cache = opg.update_cache(np.zeros((16, 16), complex), pg, 1.0, w, v)
+    assert relerr(cache, opo.update_cache(po, 1.0, w, v)) < TOL
+
+
+def test_c1_single_qubit_ohmic_anchor(Q):
+    """Config C1: H(s) = −(1−s)σx + sσz, Ohmic bath, 2×2 ρ (SURVEY App. C anchors)."""
+    fs = [lambda s: -(1 - s), lambda s: s]
+    Hg = Q.DenseHamiltonian(fs, [sx, sz])
+    bath = Q.Ohmic(1e-4, 4, 16)
+    opg = Q.DiffEqLiouvillian(Hg, [Q.DaviesGenerator([2 * np.pi * sz], bath, Q.ZERO_LAMBSHIFT)], [], 2)
+    Ho = O.DenseHamiltonian(fs, [sx, sz])
+    ob = O.Ohmic(1e-4, 4, 16)
+    opo = O.DiffEqLiouvillian(Ho, [O.DaviesGenerator([2 * np.pi * sz], ob.spectrum, lambda w: 0.0)], [], 2)
+    rng = np.random.default_rng(9)
+    rho = np.outer(F.PauliVec[0][0], F.PauliVec[0][0].conj())
+    u = np.concatenate([rho[None], rand_rho(rng, 16, 2)])
+    pg, po = Q.ODEParams(None, 10.0), O.ODEParams(None, 10.0)
+    for t in (0.0, 2.5, 5.0, 7.5, 10.0):
+        w, v = O.haml_eigs(Ho, po(t), 2)
+        du = opg.rhs_with_eig(np.zeros_like(u), u, pg, t, w, v)
+        ref = np.stack([opo.rhs_with_eig(x, po, t, w, v) for x in u])
+        assert relerr(du, ref) < TOL
+        if t == 5.0:
+            assert du[0][0, 0] == pytest.approx(-0.030394341407546568, rel=1e-10)
+            assert du[0][0, 1] == pytest.approx(-0.015496302491821998 - 3.1415926535897922j, rel=1e-10)
+
+
+@pytest.mark.parametrize("nq,lvl,K", [(5, 32, 1), (6, 64, 6), (6, 20, 2)])
+def test_ame_medium_vs_oracle(Q, nq, lvl, K):
+    """Davies + Lindblad `opensys` term on 5–6 qubits with the literal-loop oracle; Ohmic bath."""
+    rng = np.random.default_rng(nq * 100 + lvl)
+    n = 2 ** nq
+    Hd = -F.standard_driver(nq)
+    Hp = F.random_ising(nq, rng)
+    fs = [A, B]
+    coup = [2 * np.pi * F.collective_operator("z", nq)] if K == 1 else \
+        [2 * np.pi * F.single_clause(["z"], [k + 1], 1.0, nq) for k in range(K)]
+    bath_g, bath_o = Q.Ohmic(1e-4, 4, 16), O.Ohmic(1e-4, 4, 16)
+    Hg = Q.DenseHamiltonian(fs, [Hd, Hp])
+    Ho = O.DenseHamiltonian(fs, [Hd, Hp])
+    opg = Q.DiffEqLiouvillian(Hg, [Q.DaviesGenerator(coup, bath_g, lamb)], [], lvl)
+    opo = O.DiffEqLiouvillian(Ho, [O.DaviesGenerator(coup, bath_o.spectrum, lamb)], [], lvl)
+    w, v = O.haml_eigs(Ho, 0.5, lvl)
+    u = rand_rho(rng, 3, n)
+    pg, po = Q.ODEParams(None, 2.0), O.ODEParams(None, 2.0)
+    du = opg.rhs_with_eig(np.zeros_like(u), u, pg, 1.0, w, v)
+    ref = np.stack([opo.rhs_with_eig(x, po, 1.0, w, v) for x in u])
+    assert relerr(du, ref) < TOL
+
+
+# ---------------------------------------------------------------------------------------------
+# R: Redfield   (reference test/opensys/redfield.jl:3-24)
+# ---------------------------------------------------------------------------------------------
+def test_redfield_golden_and_apply(Q):
+    unitary = lambda t: sla.expm(-1j * t * sx)
+    cfun = lambda t1, t2: 1.0
+    kernels = [(((1, 1),), [sz], cfun)]
+    rg = Q.RedfieldLiouvillian(kernels, unitary, 5.0, 1e-8, 1e-6)
+    ro = O.RedfieldLiouvillian(kernels, unitary, 5.0, 1e-8, 1e-6)
+    pg, po = Q.ODEParams(None, 5.0), O.ODEParams(None, 5.0)
+    rho = np.outer(F.PauliVec[0][0], F.PauliVec[0][0].conj())
+    d = rg(np.zeros((2, 2), complex), rho, pg, 5.0)
+    assert np.allclose(d, -np.sin(10) * sx, atol=1e-7)  # dρ = +0.544021 σx
+    ref = ro.rhs_acc(np.zeros((2, 2), complex), rho, po, 5.0)
+    assert relerr(d, ref) < 1e-10
+    Ac = rg.update_vectorized_cache(np.zeros((4, 4), complex), pg, 5.0)
+    Ao = ro.update_vectorized_cache_acc(np.zeros((4, 4), complex), po, 5.0)
+    assert relerr(Ac, Ao) < 1e-10
+    assert np.allclose(Ac @ rho.flatten(order="F"), ref.flatten(order="F"), atol=1e-9)
+
+
+@pytest.mark.parametrize("n,K,nb", [(4, 2, 3), (32, 3, 4), (128, 7, 3)])
+def test_redfield_apply_vs_oracle(Q, n, K, nb):
+    rng = np.random.default_rng(n + K)
+    S = [(lambda x: x + x.conj().T)(rand_c(rng, n, n)) for _ in range(K)]
+    Lam = rand_c(rng, nb, K, n, n) / n
+    u = rand_c(rng, nb, n, n)
+    du0 = rand_c(rng, nb, n, n)
+    rg = Q.RedfieldLiouvillian(None, None, 0, 0, 0)
+    du = rg.apply(du0.copy(), u, S, Lam)
+    ref = np.stack([O.redfield_apply_acc(du0[b].copy(), u[b], S, list(Lam[b])) for b in range(nb)])
+    assert relerr(du, ref) < TOL
+
+
+# ---------------------------------------------------------------------------------------------
+# H-s + J: SparseHamiltonian and trajectories
+# ---------------------------------------------------------------------------------------------
+def test_sparse_hamiltonian_golden(Q):
+    H = Q.SparseHamiltonian([A, B], [sps.csc_matrix(sx), sps.csc_matrix(sz)])
+    assert np.allclose(H(0.5).toarray(), np.pi * (sx + sz), atol=1e-15)
+    c = H.update_cache(0.5)
+    assert np.array_equal(c.toarray(), -1j * np.pi * (sx + sz))
+    u = np.array([1.0 + 0j, 1]) / np.sqrt(2)
+    rho = np.outer(u, u.conj())
+    du = np.array([[1.0 + 0j, 0], [0, 0]])
+    H(du, rho, 1.0, 0.5)
+    assert relerr(du, -1j * np.pi * ((sx + sz) @ rho - rho @ (sx + sz))) < 1e-15
+
+
+def _tfim_sparse(nq):
+    Hx = sps.csc_matrix(-F.standard_driver(nq))
+    J = [1.0] * (nq - 1)
+    Hz = sps.csc_matrix(-F.two_local_term(J, [[i, i + 1] for i in range(1, nq)], nq))
+    Ls = [sps.csc_matrix(F.single_clause(["z"], [k], 1.0, nq)) for k in range(1, nq + 1)]
+    return Hx, Hz, Ls
+
+
+@pytest.mark.parametrize("nq,nb", [(3, 5), (6, 9), (8, 33)])
+def test_trajectory_matvec_and_jump(Q, nq, nb):
+    rng = np.random.default_rng(nq)
+    n = 2 ** nq
+    Hx, Hz, Ls = _tfim_sparse(nq)
+    fs = [A, B]
+    Hg = Q.SparseHamiltonian(fs, [Hx, Hz], unit="ħ")
+    Ho = O.SparseHamiltonian(fs, [Hx, Hz], unit="ħ")
+    for per_member_gamma in (False, True):
+        gfs = [(lambda s, k=k: 0.05 * (1 + (k + s if per_member_gamma else 0))) for k in range(nq)]
+        lg = Q.LindbladLiouvillian([Q.Lindblad(g, L) for g, L in zip(gfs, Ls)])
+        lo = O.LindbladLiouvillian([O.Lindblad(g, L.toarray()) for g, L in zip(gfs, Ls)])
+        opg = Q.DiffEqLiouvillian(Hg, [], [lg], n)
+        opo = O.DiffEqLiouvillian(Ho, [], [lo], n)
+        ens = Q.TrajectoryEnsemble(opg)
+        psi = rand_c(rng, nb, n)
+        psi /= np.linalg.norm(psi, axis=1, keepdims=True)
+        tf = 4.0
+        t = rng.random(nb) * tf
+        pg, po = Q.ODEParams(None, tf), O.ODEParams(None, tf)
+        pd = Q.DeviceBatch.from_host(psi)
+        dpsi = ens.matvec(pd.zeros_like(), pd, pg, t).to_host()
+        ref = np.stack([opo.update_cache(po, t[b]) @ psi[b] for b in range(nb)])
+        assert relerr(dpsi, ref) < TOL
+        # update_cache! on the union pattern
+        cache = opg.update_cache(None, pg, t[0])
+        assert relerr(cache.toarray(), opo.update_cache(po, t[0])) < 1e-14
+        # ‖ψ‖²
+        assert np.allclose(ens.norm2(pd).cpu().numpy(), 1.0, atol=1e-14)
+        # jump decision: identical index sequence for identical uniforms
+        r = rng.random(nb)
+        choice, prob = ens.lindblad_jump(pd, pg, t, r, apply=False)
+        choice, prob = choice.cpu().numpy(), prob.cpu().numpy()
+        for b in range(nb):
+            k, pr = O.lindblad_jump(opo, psi[b], po, t[b], r[b])
+            assert k == choice[b]
+            assert np.allclose(pr, prob[b], rtol=1e-13)
+        # apply: ψ ← Lψ/‖Lψ‖ for a masked subset
+        mask = (np.arange(nb) % 2 == 0)
+        choice2, _ = ens.lindblad_jump(pd, pg, t, r, mask=mask, apply=True)
+        out = pd.to_host()
+        choice2 = choice2.cpu().numpy()
+        for b in range(nb):
+            if mask[b]:
+                y = Ls[choice[b]].toarray() @ psi[b]
+                assert relerr(out[b], y / np.linalg.norm(y)) < TOL
+            else:
+                assert choice2[b] == -1 and np.array_equal(out[b], psi[b])
+
+
+def test_sparse_commutator_vs_oracle(Q):
+    rng = np.random.default_rng(77)
+    Hx, Hz, _ = _tfim_sparse(5)
+    Hg = Q.SparseHamiltonian([A, B], [Hx, Hz])
+    Ho = O.SparseHamiltonian([A, B], [Hx, Hz])
+    u = rand_c(rng, 4, 32, 32)
+    s = rng.random(4)
+    du = Hg(np.zeros_like(u), u, None, s)
+    ref = np.stack([Ho.rhs(u[b], s[b]) for b in range(4)])
+    assert relerr(du, ref) < TOL
+
+
+def test_expect(Q):
+    rng = np.random.default_rng(3)
+    n = 16
+    obs = [rand_c(rng, n, n) for _ in range(3)]
+    rho = rand_c(rng, 5, n, n)
+    out = Q.expect(obs, Q.DeviceBatch.from_host(rho)).cpu().numpy()
+    ref = np.array([[np.trace(o @ r) for o in obs] for r in rho])
+    assert relerr(out, ref) < 1e-13
+    psi = rand_c(rng, 5, n)
+    out = Q.expect(obs, Q.DeviceBatch.from_host(psi)).cpu().numpy()
+    ref = np.array([[p.conj() @ o @ p for o in obs] for p in psi])
+    assert relerr(out, ref) < 1e-13

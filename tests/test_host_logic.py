@@ -1,0 +1,122 @@
+"""CPU tests of the host-side logic (no GPU, no compute calls into the CUDA library):
+ * the C-ABI library loads and exports every symbol include/oqb.h declares;
+ * the product's gap preprocessing (gaps.py) reproduces the oracle's literal GapIndices grouping,
+   and the closed-form Davies tables it feeds to the device (emulated here in numpy, operation for
+   operation as csrc/elementwise.cu does them) equal the oracle's per-gap-group loop;
+ * the product's host quadrature equals the oracle's QuadGK mirror;
+ * creating a context without a GPU fails loudly (no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import oqb_b200
+from oqb_b200 import _lib
+from oqb_b200.gaps import GapGroups, round_sigdigits
+from oqb_b200.quadrature import quadgk_matrix
+from oracle import oqb_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "oqb.h")).read()
+    declared = set(re.findall(r"\b(oqb_[a-z0-9_]+)\s*\(", hdr))
+    lib = _lib.load()
+    assert declared, "no declarations parsed"
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/oqb.h but not exported"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    assert lib.oqb_version() == 100
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    h = ctypes.c_void_p()
+    assert _lib.load().oqb_create(0, ctypes.byref(h)) != 0
+    with pytest.raises(_lib.OQBError):
+        oqb_b200.Context(0)
+
+
+def test_round_sigdigits_matches_oracle():
+    rng = np.random.default_rng(0)
+    x = np.concatenate([rng.standard_normal(2000) * 10.0 ** rng.integers(-6, 6, 2000),
+                        [8.05669612345, 12.9873017464, 1e-7, 123456789.0, 0.5, 9.99999995, 99999999.5]])
+    ref = np.array([O.round_sigdigits(float(v), 8) for v in x])
+    assert np.array_equal(round_sigdigits(x, 8), ref)
+
+
+def _mock_gamma(x):
+    return x + 1 if x >= 0 else (1 - x) * np.exp(x)
+
+
+def _mock_S(x):
+    return x + 0.1
+
+
+def closed_form_numpy(w, A_list, groups, gamma, S, rho):
+    """numpy emulation of the device Davies path (davies_tables + hadamard + davies_diag + davies_cross +
+    davies_lamb_build in csrc/elementwise.cu) — eigenbasis, includes −i[diag w, ρ]."""
+    l = len(w)
+    gam, Sm, crate, lrs = groups.tables(gamma, S)
+    m2 = sum(np.abs(A) ** 2 for A in A_list)
+    Gam = (gam * m2).sum(axis=0)
+    hls = (Sm * m2).sum(axis=0)
+    W = gam * m2
+    np.fill_diagonal(W, 0.0)
+    dA = sum(np.outer(np.diag(A), np.diag(A).conj()) for A in A_list)
+    Cm = -0.5 * (Gam[:, None] + Gam[None, :]) - 1j * (hls[:, None] - hls[None, :]) \
+        - 1j * (w[:, None] - w[None, :]) + gam[0, 0] * dA
+    X = Cm * rho
+    X[np.diag_indices(l)] += W @ np.diag(rho)
+    for (a, b, a2, b2), r in zip(groups.cross_idx, crate):
+        X[a, a2] += r * sum(A[a, b] * np.conj(A[a2, b2]) for A in A_list) * rho[b, b2]
+    if len(groups.lamb_idx):
+        M = np.zeros((l, l), complex)
+        for (a, b, b2), (r, s) in zip(groups.lamb_idx, lrs):
+            M[b, b2] += (-0.5 * r - 1j * s) * sum(np.conj(A[a, b]) * A[a, b2] for A in A_list)
+        X += M @ rho + rho @ M.conj().T
+    return X
+
+
+@pytest.mark.parametrize("spectrum", ["generic", "equal_spaced", "degenerate", "unsorted", "ref_util_test"])
+def test_gap_groups_closed_form_equals_literal_loop(spectrum):
+    rng = np.random.default_rng(11)
+    w = {"generic": np.sort(rng.standard_normal(8) * 3),
+         "equal_spaced": np.arange(7) * 0.75 - 2.0,
+         "degenerate": np.array([-2.0, -2.0, -0.5, 0.3, 0.3, 0.3, 1.9]),
+         "unsorted": np.array([0.4, -1.0, 2.0, 1.9, 1.0, 0.5, 0.0]),
+         "ref_util_test": np.array([-3, 1, 3, 3, 4.5, 5.5, 8.0])}[spectrum]  # reference test/opensys/util.jl:3
+    l = len(w)
+    A_list = [(lambda g: g + g.conj().T)(rng.standard_normal((l, l)) + 1j * rng.standard_normal((l, l))) for _ in range(2)]
+    rho = rng.standard_normal((l, l)) + 1j * rng.standard_normal((l, l))
+    groups = GapGroups(w, 8, 8)
+    gi = O.build_gap_indices(w, 8, 8)
+    # the signed rounded gap matrix agrees with the oracle's literal grouping
+    om = np.zeros((l, l))
+    for key, aa, bb in gi.positive_gap_indices():
+        for a, b in zip(aa, bb):
+            om[a - 1, b - 1] = key
+            om[b - 1, a - 1] = -key
+    assert np.array_equal(groups.omega, om)
+    # closed form == literal loop (davies.jl:21-47) + Hamiltonian commutator
+    dav = O.DaviesGenerator(A_list, _mock_gamma, _mock_S)
+    ref = -1j * (np.diag(w) @ rho - rho @ np.diag(w))
+    ref = dav.rhs_acc(ref.astype(complex), rho, gi, None, 0.0)
+    got = closed_form_numpy(w, A_list, groups, _mock_gamma, _mock_S, rho)
+    assert np.linalg.norm(got - ref) / np.linalg.norm(ref) < 1e-13
+
+
+def test_host_quadrature_matches_oracle_mirror():
+    import scipy.linalg as sla
+    sx = np.array([[0, 1], [1, 0]], complex)
+    sz = np.array([[1, 0], [0, -1]], complex)
+    U = lambda t: sla.expm(-1j * t * sx)
+    f = lambda x: np.cos(3 * x) * (U(5.0) @ U(x).conj().T @ sz @ U(x) @ U(5.0).conj().T)
+    a = quadgk_matrix(f, 0.0, 5.0, 1e-6, 1e-8)
+    b, _ = O.quadgk(f, 0.0, 5.0, 1e-6, 1e-8)
+    assert np.linalg.norm(a - b) < 1e-14
