@@ -64,7 +64,7 @@ class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
-        self._stop = threading.Event()
+        self._halt = threading.Event()
 
     def run(self):
         try:
@@ -73,7 +73,7 @@ class ClockSampler(threading.Thread):
             h = nv.nvmlDeviceGetHandleByIndex(self.index)
             self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
             names = {getattr(nv, k): k for k in dir(nv) if k.startswith("nvmlClocksEventReason") or k.startswith("nvmlClocksThrottleReason")}
-            while not self._stop.is_set():
+            while not self._halt.is_set():
                 self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
                 try:
                     r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
@@ -87,7 +87,7 @@ class ClockSampler(threading.Thread):
             self.reasons.add(f"nvml_unavailable:{type(e).__name__}")
 
     def stop(self):
-        self._stop.set()
+        self._halt.set()
         self.join(timeout=2)
         med = float(np.median(self.samples)) if self.samples else None
         reasons = sorted(x for x in self.reasons if x not in ("GpuIdle", "None", "ApplicationsClocksSetting"))

@@ -91,6 +91,7 @@ struct ZgemmParams {
     int alpha_scale_mod = 0;
 };
 int zgemm(Ctx* c, const ZgemmParams& p);
+int zgemm_tma(Ctx* c, const ZgemmParams& p, bool* used);  // zgemm_tma.cu
 
 // Double-buffered H2D → compute → D2H pipeline over batch chunks (the *_host entry points).
 // compute(b0, cnt, d_in, d_out) enqueues work for members [b0, b0+cnt) on c->stream.

@@ -267,6 +267,11 @@ int zgemm(Ctx* c, const ZgemmParams& p) {
     if (p.M <= 0 || p.N <= 0 || p.batch <= 0 || p.batch2 <= 0) return 0;
     if (p.K < 0) return set_error(c, 1, "zgemm: negative K");
     if (!p.A || !p.B || !p.C) return set_error(c, 1, "zgemm: null operand");
+    {
+        bool used = false;  // TMA-staged warp-specialised kernel first; cp.async kernel is the fallback
+        OQB_TRY(zgemm_tma(c, p, &used));
+        if (used) return 0;
+    }
     const bool ta = p.opA != OP_N, tb = p.opB != OP_N;
     if (!ta && !tb) return dispatch_tile<false, false>(c, p);
     if (ta && !tb) return dispatch_tile<true, false>(c, p);
