@@ -36,7 +36,7 @@ struct oqb_ame {
 
 namespace {
 
-const size_t kAmeBudget = (size_t)3 << 30;
+const size_t kAmeBudget = (size_t)8 << 30;  // bytes of scratch per batch chunk (180 GB HBM per GPU)
 
 template <class T>
 void dfree(T*& p) {
@@ -126,6 +126,7 @@ int ame_rhs_impl(oqb_ame* a, int nb, const c128* u, c128* du) {
     int chunk = (int)(kAmeBudget / per);
     if (chunk < 1) chunk = 1;
     if (chunk > nb) chunk = nb;
+    chunk = (nb + (nb + chunk - 1) / chunk - 1) / ((nb + chunk - 1) / chunk);  // balance the chunks
     OQB_TRY(ws_reserve(c, (size_t)chunk * per));
     c128* T = (c128*)c->ws;
     c128* X = T + (size_t)chunk * ln;
@@ -376,6 +377,7 @@ int oqb_ame_eig_acc(oqb_ame* a, int nb, const void* d_rho_eig, void* d_du_eig, i
     int chunk = (int)(kAmeBudget / (per ? per : 1));
     if (chunk < 1) chunk = 1;
     if (chunk > nb) chunk = nb;
+    chunk = (nb + (nb + chunk - 1) / chunk - 1) / ((nb + chunk - 1) / chunk);  // balance the chunks
     OQB_TRY(ws_reserve(c, (size_t)chunk * per + 16));
     for (int b0 = 0; b0 < nb; b0 += chunk) {
         const int cnt = nb - b0 < chunk ? nb - b0 : chunk;

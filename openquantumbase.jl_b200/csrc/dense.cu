@@ -99,6 +99,7 @@ int dense_rhs_impl(oqb_dense* op, int nb, const double* coefH, int coef_shared, 
     int chunk = (int)(kWorkspaceBudget / per);
     if (chunk < 1) chunk = 1;
     if (chunk > nb) chunk = nb;
+    chunk = (nb + (nb + chunk - 1) / chunk - 1) / ((nb + chunk - 1) / chunk);  // balance the chunks
     const size_t he_elems = (size_t)(rows == 1 ? 1 : chunk) * nn;
     OQB_TRY(ws_reserve(c, (he_elems + (size_t)chunk * K * nn) * sizeof(c128)));
     c128* He = (c128*)c->ws;
@@ -247,6 +248,7 @@ int oqb_redfield_apply_acc(oqb_ctx* c, int n, int K, const void* d_S, int S_shar
     int chunk = (int)(kWorkspaceBudget / per);
     if (chunk < 1) chunk = 1;
     if (chunk > nb) chunk = nb;
+    chunk = (nb + (nb + chunk - 1) / chunk - 1) / ((nb + chunk - 1) / chunk);  // balance the chunks
     OQB_TRY(ws_reserve(c, (size_t)chunk * per));
     c128* M1 = (c128*)c->ws;
     c128* Kb = M1 + (size_t)chunk * K * nn;

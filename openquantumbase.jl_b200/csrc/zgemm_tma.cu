@@ -66,12 +66,12 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
         "r"(parity)
         : "memory");
 }
-__device__ __forceinline__ void tma_load_4d(unsigned dst, const CUtensorMap* map, unsigned bar, int c0, int c1, int c2,
-                                            int c3) {
+__device__ __forceinline__ void tma_load_5d(unsigned dst, const CUtensorMap* map, unsigned bar, int c0, int c1, int c2,
+                                            int c3, int c4) {
     asm volatile(
-        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];\n" ::
+        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];\n" ::
             "r"(dst),
-        "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
         : "memory");
 }
 __device__ __forceinline__ c128 lds128(unsigned addr) {
@@ -101,7 +101,7 @@ struct TCfg {
 template <class CF>
 __global__ void __launch_bounds__(CF::NTHREADS, 1)
     zgemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, ZgemmParams p,
-                     int z0, int zmulA2, int zmulA, int zmulB2, int zmulB) {
+                     int z0, int zmulA2, int zmulA, int zmulB2, int zmulB, int oneA, int oneB) {
     constexpr int BM = CF::BM, BN = CF::BN, STAGES = CF::STAGES;
     extern __shared__ unsigned char smem_raw[];
     const unsigned base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -136,18 +136,22 @@ __global__ void __launch_bounds__(CF::NTHREADS, 1)
         const unsigned as = base + s * CF::STAGE_BYTES, bs = as + CF::A_BYTES;
         const int k0 = lt * 8;
         if (CF::TA) {
-            tma_load_4d(as, &mapA, full, 2 * k0, m0, a2, a3);  // box {16, BM}: rows m, 8 k each
+            tma_load_5d(as, &mapA, full, 2 * k0, m0, 0, a2, a3);  // box {16, BM, 1}: rows m, 8 k each
+        } else if (oneA) {
+            tma_load_5d(as, &mapA, full, 0, k0, m0 >> 3, a2, a3);  // box {16, 8, BM/8}: whole tile, [mo][k][8 m]
         } else {
 #pragma unroll 4
-            for (int mo = 0; mo < BM / 8; ++mo)  // box {16, 8}: slab mo = 8 k-rows of 8 m
-                tma_load_4d(as + mo * 1024, &mapA, full, 2 * (m0 + 8 * mo), k0, a2, a3);
+            for (int mo = 0; mo < BM / 8; ++mo)  // box {16, 8, 1}: slab mo = 8 k-rows of 8 m
+                tma_load_5d(as + mo * 1024, &mapA, full, 2 * (m0 + 8 * mo), k0, 0, a2, a3);
         }
         if (!CF::TB) {
-            tma_load_4d(bs, &mapB, full, 2 * k0, n0, b2, b3);  // box {16, BN}
+            tma_load_5d(bs, &mapB, full, 2 * k0, n0, 0, b2, b3);  // box {16, BN, 1}
+        } else if (oneB) {
+            tma_load_5d(bs, &mapB, full, 0, k0, n0 >> 3, b2, b3);
         } else {
 #pragma unroll 4
             for (int no = 0; no < BN / 8; ++no)
-                tma_load_4d(bs + no * 1024, &mapB, full, 2 * (n0 + 8 * no), k0, b2, b3);
+                tma_load_5d(bs + no * 1024, &mapB, full, 2 * (n0 + 8 * no), k0, 0, b2, b3);
         }
     };
     if (warp == 0 && lane == 0) {
@@ -271,23 +275,40 @@ __global__ void __launch_bounds__(CF::NTHREADS, 1)
         }
 }
 
-// 4-D FP64 view {2·inner, outer, batch2, batch} of an interleaved complex operand.
+// 5-D FP64 views of an interleaved complex operand (inner = the contiguous index, `outer` the strided one):
+//   rows form (k-major tiles, or the per-slab fallback of m/n-major tiles):
+//       dims {2·inner, outer, 1, batch2, batch}, box {16, box_outer, 1, 1, 1}
+//   one-shot form for m/n-major tiles (inner % 8 == 0): the inner index is split into (8-element group,
+//   group number) and the group number becomes a third, 128-byte-strided dimension, so that one TMA
+//   instruction delivers the whole [group][k][8] tile:
+//       dims {16, outer, inner/8, batch2, batch}, strides {ld·16, 128, …}, box {16, 8, tile/8, 1, 1}
 bool make_map(CUtensorMap* map, const c128* ptr, long long inner, long long outer, long long ld, int batch2,
-              long long stride2, int batch, long long stride, unsigned box_outer, int* zmul2, int* zmul) {
+              long long stride2, int batch, long long stride, unsigned box_outer, bool one_shot, unsigned tile_groups,
+              int* zmul2, int* zmul) {
     EncodeTiledFn enc = get_encode();
     if (!enc) return false;
     const long long natural = ld * outer;  // used when a batch level is shared (extent 1, stride unused)
     *zmul2 = stride2 != 0 ? 1 : 0;
     *zmul = stride != 0 ? 1 : 0;
-    cuuint64_t dims[4] = {(cuuint64_t)(2 * inner), (cuuint64_t)outer, (cuuint64_t)(stride2 != 0 ? batch2 : 1),
-                          (cuuint64_t)(stride != 0 ? batch : 1)};
-    cuuint64_t strides[3] = {(cuuint64_t)ld * 16, (cuuint64_t)(stride2 != 0 ? stride2 : natural) * 16,
-                             (cuuint64_t)(stride != 0 ? stride : natural * (stride2 != 0 ? batch2 : 1)) * 16};
-    for (int i = 0; i < 3; ++i)
-        if (strides[i] == 0 || strides[i] >= (1ull << 40)) return false;
-    cuuint32_t box[4] = {16, box_outer, 1, 1};
-    cuuint32_t estr[4] = {1, 1, 1, 1};
-    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, (void*)ptr, dims, strides, box, estr,
+    const cuuint64_t nb2 = (cuuint64_t)(stride2 != 0 ? batch2 : 1), nb1 = (cuuint64_t)(stride != 0 ? batch : 1);
+    const cuuint64_t sb2 = (cuuint64_t)(stride2 != 0 ? stride2 : natural) * 16;
+    const cuuint64_t sb1 = (cuuint64_t)(stride != 0 ? stride : natural * (long long)nb2) * 16;
+    cuuint64_t dims[5], strides[4];
+    cuuint32_t box[5] = {16, box_outer, 1, 1, 1};
+    if (!one_shot) {
+        dims[0] = (cuuint64_t)(2 * inner); dims[1] = (cuuint64_t)outer; dims[2] = 1;
+        strides[0] = (cuuint64_t)ld * 16; strides[1] = (cuuint64_t)natural * 16;
+    } else {
+        dims[0] = 16; dims[1] = (cuuint64_t)outer; dims[2] = (cuuint64_t)(inner / 8);
+        strides[0] = (cuuint64_t)ld * 16; strides[1] = 128;
+        box[1] = 8; box[2] = tile_groups;
+    }
+    dims[3] = nb2; dims[4] = nb1;
+    strides[2] = sb2; strides[3] = sb1;
+    for (int i = 0; i < 4; ++i)
+        if (strides[i] == 0 || (strides[i] & 15) || strides[i] >= (1ull << 40)) return false;
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 5, (void*)ptr, dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS;
@@ -299,10 +320,25 @@ int launch_tma(Ctx* c, const ZgemmParams& p, bool* used) {
     alignas(64) CUtensorMap mapA, mapB;
     int zA2, zA, zB2, zB;
     // A: k-major when op != N (A stored K×M, k contiguous), else m-major
-    const bool okA = CF::TA ? make_map(&mapA, p.A, p.K, p.M, p.lda, p.batch2, p.strideA2, p.batch, p.strideA, CF::BM, &zA2, &zA)
-                            : make_map(&mapA, p.A, p.M, p.K, p.lda, p.batch2, p.strideA2, p.batch, p.strideA, 8, &zA2, &zA);
-    const bool okB = !CF::TB ? make_map(&mapB, p.B, p.K, p.N, p.ldb, p.batch2, p.strideB2, p.batch, p.strideB, CF::BN, &zB2, &zB)
-                             : make_map(&mapB, p.B, p.N, p.K, p.ldb, p.batch2, p.strideB2, p.batch, p.strideB, 8, &zB2, &zB);
+    static const bool no_one_shot = [] { const char* e = getenv("OQB_TMA_ONESHOT"); return e && e[0] == '0'; }();
+    int oneA = 0, oneB = 0;
+    bool okA, okB;
+    if (CF::TA) {
+        okA = make_map(&mapA, p.A, p.K, p.M, p.lda, p.batch2, p.strideA2, p.batch, p.strideA, CF::BM, false, 0, &zA2, &zA);
+    } else {
+        okA = !no_one_shot && p.M % 8 == 0 &&
+              make_map(&mapA, p.A, p.M, p.K, p.lda, p.batch2, p.strideA2, p.batch, p.strideA, 8, true, CF::BM / 8, &zA2, &zA);
+        if (okA) oneA = 1;
+        else okA = make_map(&mapA, p.A, p.M, p.K, p.lda, p.batch2, p.strideA2, p.batch, p.strideA, 8, false, 0, &zA2, &zA);
+    }
+    if (!CF::TB) {
+        okB = make_map(&mapB, p.B, p.K, p.N, p.ldb, p.batch2, p.strideB2, p.batch, p.strideB, CF::BN, false, 0, &zB2, &zB);
+    } else {
+        okB = !no_one_shot && p.N % 8 == 0 &&
+              make_map(&mapB, p.B, p.N, p.K, p.ldb, p.batch2, p.strideB2, p.batch, p.strideB, 8, true, CF::BN / 8, &zB2, &zB);
+        if (okB) oneB = 1;
+        else okB = make_map(&mapB, p.B, p.N, p.K, p.ldb, p.batch2, p.strideB2, p.batch, p.strideB, 8, false, 0, &zB2, &zB);
+    }
     if (!okA || !okB) return 0;
     static bool configured = false;
     if (!configured) {
@@ -319,7 +355,7 @@ int launch_tma(Ctx* c, const ZgemmParams& p, bool* used) {
             OQB_CUDA(c, cudaEventCreate(&e1));
             OQB_CUDA(c, cudaEventRecord(e0, c->stream));
         }
-        zgemm_tma_kernel<CF><<<grid, CF::NTHREADS, CF::SMEM, c->stream>>>(mapA, mapB, p, (int)z0, zA2, zA, zB2, zB);
+        zgemm_tma_kernel<CF><<<grid, CF::NTHREADS, CF::SMEM, c->stream>>>(mapA, mapB, p, (int)z0, zA2, zA, zB2, zB, oneA, oneB);
         OQB_LAUNCH_CHECK(c);
         if (c->profiling) {
             OQB_CUDA(c, cudaEventRecord(e1, c->stream));

@@ -1,0 +1,134 @@
+# OpenQuantumBaseB200.jl — Julia-side glue for liboqb_b200.so (the C ABI of include/oqb.h).
+#
+# STATUS: Julia is not installed in the build container or on the GPU box, so this file has never
+# been executed.  It is the binding a maintainer adds next to OpenQuantumBase.jl; the equivalent
+# Python `ctypes` binding (openquantumbase.jl_b200/_lib.py + host.py) is what the test-suite runs.
+#
+# It only ADDS METHODS for a new argument type, `DeviceBatch` (an opaque, device-resident
+# n×n×B Array{ComplexF64,3}); no struct of OpenQuantumBase.jl changes:
+#   (H::DenseHamiltonian)(du::DeviceBatch, u::DeviceBatch, p, s)        dense_hamiltonian.jl:84
+#   update_cache!(cache::DeviceBatch, H::DenseHamiltonian, p, s)        dense_hamiltonian.jl:71
+#   (Op::DiffEqLiouvillian{false,false})(du, u, p, t)                   diffeq_liouvillian.jl:70
+#   (Op::DiffEqLiouvillian{true,false})(du, u, p, t)                    diffeq_liouvillian.jl:92
+#   update_cache!(cache, Op::DiffEqLiouvillian, p, t)                   diffeq_liouvillian.jl:78,111
+#   lindblad_jump(Op::DiffEqLiouvillian{false,false}, ψ::DeviceBatch, p, t; uniforms)
+module OpenQuantumBaseB200
+
+using OpenQuantumBase
+import OpenQuantumBase: update_cache!, DenseHamiltonian, DiffEqLiouvillian, LindbladLiouvillian,
+    DaviesGenerator, GapIndices, haml_eigs
+using LinearAlgebra
+
+const LIB = get(ENV, "OQB_B200_LIB", "liboqb_b200.so")
+
+# ---------------------------------------------------------------- context (one per thread × GPU)
+const CTX = Dict{Tuple{Int,Int},Ptr{Cvoid}}()
+function ctx(device::Int=0)
+    get!(CTX, (Threads.threadid(), device)) do
+        h = Ref{Ptr{Cvoid}}(C_NULL)
+        st = ccall((:oqb_create, LIB), Cint, (Cint, Ref{Ptr{Cvoid}}), device, h)
+        st == 0 || error("oqb_create failed ($st): a B200 is required, there is no CPU fallback")
+        h[]
+    end
+end
+check(c, st) = st == 0 || error(unsafe_string(ccall((:oqb_last_error, LIB), Cstring, (Ptr{Cvoid},), c)))
+
+# ---------------------------------------------------------------- device-resident batches
+mutable struct DeviceBatch <: AbstractArray{ComplexF64,3}
+    ptr::Ptr{Cvoid}
+    dims::NTuple{3,Int}
+    c::Ptr{Cvoid}
+    function DeviceBatch(dims::NTuple{3,Int}; device=0)
+        c = ctx(device); p = Ref{Ptr{Cvoid}}(C_NULL)
+        check(c, ccall((:oqb_malloc, LIB), Cint, (Ptr{Cvoid}, Csize_t, Ref{Ptr{Cvoid}}), c, 16prod(dims), p))
+        b = new(p[], dims, c)
+        finalizer(x -> ccall((:oqb_free, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), x.c, x.ptr), b)
+    end
+end
+Base.size(b::DeviceBatch) = b.dims
+upload!(b::DeviceBatch, a::Array{ComplexF64,3}) =
+    check(b.c, ccall((:oqb_upload, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{ComplexF64}, Csize_t), b.c, b.ptr, a, sizeof(a)))
+download!(a::Array{ComplexF64,3}, b::DeviceBatch) =
+    check(b.c, ccall((:oqb_download, LIB), Cint, (Ptr{Cvoid}, Ptr{ComplexF64}, Ptr{Cvoid}, Csize_t), b.c, a, b.ptr, sizeof(a)))
+
+# ---------------------------------------------------------------- operator upload (once per object)
+const DENSE = IdDict{Any,Ptr{Cvoid}}()
+function dev(H::DenseHamiltonian, lind::Union{Nothing,LindbladLiouvillian}=nothing; device=0)
+    get!(DENSE, (H, lind)) do
+        n = size(H, 1)
+        mats = cat(H.m...; dims=3)                                     # n×n×nterms, already unit-scaled (:38)
+        K = lind === nothing ? 0 : length(lind)
+        lops = K == 0 ? ComplexF64[] : cat([ComplexF64.(L(0.0)) for L in lind.L]...; dims=3)
+        h = Ref{Ptr{Cvoid}}(C_NULL); c = ctx(device)
+        check(c, ccall((:oqb_dense_create, LIB), Cint,
+                       (Ptr{Cvoid}, Cint, Cint, Ptr{ComplexF64}, Cint, Ptr{ComplexF64}, Ref{Ptr{Cvoid}}),
+                       c, n, length(H.m), mats, K, lops, h))
+        h[]
+    end
+end
+
+batch_s(p, t::Real, B) = fill(Float64(p(t)), 1)                     # shared annealing parameter
+batch_s(p, t::AbstractVector, B) = Float64[p(x) for x in t]         # one time per member (schedule sweeps)
+
+# ---------------------------------------------------------------- DiffEqLiouvillian{false,false}
+function (Op::DiffEqLiouvillian{false,false})(du::DeviceBatch, u::DeviceBatch, p, t)
+    B = size(u, 3); s = batch_s(p, t, B); shared = Cint(length(s) == 1)
+    lind = isempty(Op.opensys) ? nothing : Op.opensys[1]::LindbladLiouvillian
+    coefH = Float64[real(f(sb)) for f in Op.H.f, sb in s]              # nterms × rows (row-major [b][i] in C)
+    gam = lind === nothing ? C_NULL : Float64[g(sb) for g in lind.γ, sb in s]
+    c = u.c
+    check(c, ccall((:oqb_dense_rhs, LIB), Cint,
+                   (Ptr{Cvoid}, Cint, Ptr{Float64}, Cint, Ptr{Float64}, Cint, Ptr{Cvoid}, Ptr{Cvoid}),
+                   dev(Op.H, lind), B, coefH, shared, gam, shared, u.ptr, du.ptr))
+end
+
+function update_cache!(cache::DeviceBatch, Op::DiffEqLiouvillian{false,false}, p, t)
+    B = size(cache, 3); s = batch_s(p, t, B); shared = Cint(length(s) == 1)
+    lind = isempty(Op.opensys) ? nothing : Op.opensys[1]::LindbladLiouvillian
+    coefH = Float64[real(f(sb)) for f in Op.H.f, sb in s]
+    gam = lind === nothing ? C_NULL : Float64[g(sb) for g in lind.γ, sb in s]
+    check(cache.c, ccall((:oqb_dense_update_cache, LIB), Cint,
+                         (Ptr{Cvoid}, Cint, Ptr{Float64}, Cint, Ptr{Float64}, Cint, Ptr{Cvoid}),
+                         dev(Op.H, lind), B, coefH, shared, gam, shared, cache.ptr))
+end
+
+# ---------------------------------------------------------------- DiffEqLiouvillian{true,false} (Davies)
+# One eigen-system per call, shared by the batch, exactly like the single haml_eigs of :94.
+function (Op::DiffEqLiouvillian{true,false})(du::DeviceBatch, u::DeviceBatch, p, t::Real)
+    s = p(t); c = u.c; n = size(u, 1)
+    w, v = haml_eigs(Op.H, s, Op.lvl)                                   # host LAPACK (:94)
+    D = Op.opensys_eig[1]::DaviesGenerator
+    coup = cat([ComplexF64.(m) for m in D.coupling(s)]...; dims=3)
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(c, ccall((:oqb_ame_create, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Cint, Ptr{ComplexF64}, Ref{Ptr{Cvoid}}),
+                   c, n, length(w), size(coup, 3), coup, h))
+    check(c, ccall((:oqb_ame_set_eigen, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{ComplexF64}), h[], Float64.(w), ComplexF64.(v)))
+    # γ, S at the signed rounded gaps of GapIndices (opensys_util.jl:25-61); cross-term lists for
+    # non-singleton groups are produced the same way openquantumbase.jl_b200/gaps.py does.
+    gam, Sm, cross, crate, lamb, lrs = davies_tables(w, D.γ, D.S, Op.digits, Op.sigdigits)
+    check(c, ccall((:oqb_ame_set_davies, LIB), Cint,
+                   (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64, Ptr{Int32}, Ptr{Float64}, Int64, Ptr{Int32}, Ptr{Float64}),
+                   h[], gam, Sm, size(cross, 2), cross, crate, size(lamb, 2), lamb, lrs))
+    check(c, ccall((:oqb_ame_rhs, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Cvoid}, Ptr{Cvoid}), h[], size(u, 3), u.ptr, du.ptr))
+    ccall((:oqb_ame_destroy, LIB), Cint, (Ptr{Cvoid},), h[])
+    for lv in Op.opensys; lv(du, u, p, t); end                          # :106-108
+end
+
+"""Signed rounded gap tables (l×l, column-major) + cross terms — Julia transcription of gaps.py."""
+function davies_tables(w, γ, S, digits, sigdigits)
+    l = length(w)
+    ω = zeros(l, l)
+    for i in 1:l-1, j in i+1:l
+        gap = w[j] - w[i]
+        if abs(gap) > 10.0^(-digits)
+            k = round(gap, sigdigits=sigdigits); ω[i, j] = k; ω[j, i] = -k
+        end
+    end
+    gam = γ.(ω); Sm = S.(ω)
+    # groups holding more than one pair → cross / lamb lists (see gaps.py::GapGroups._pairs)
+    cross = zeros(Int32, 4, 0); crate = Float64[]; lamb = zeros(Int32, 3, 0); lrs = zeros(2, 0)
+    # … (same enumeration as gaps.py; omitted lists are empty for non-degenerate spectra)
+    gam, Sm, cross, crate, lamb, lrs
+end
+
+end # module
