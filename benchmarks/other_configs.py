@@ -1,0 +1,198 @@
+#!/usr/bin/env python
+"""Measurements of the other BASELINE.json configurations (C2 Lindblad, C4 trajectories, C5 Redfield)
+on one GPU, same timing hygiene as bench.py (≥3 warm-ups, CUDA events, inputs larger than L2).
+One JSON line per configuration.  bench.py (the driver contract) stays on the headline C3 workload.
+
+  python benchmarks/other_configs.py [--configs c2,c2dense,c4,c5] [--steps K]
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    hbm = 6650.0
+    src = "fallback 6.65 TB/s (B200_PROFILING.md)"
+    if os.path.exists(p):
+        hbm = json.load(open(p))["hbm_gbs"]
+        src = "MEASURED_PEAKS.json hbm_gbs"
+    return hbm, src
+
+
+def tfim_dense(nq):
+    n = 1 << nq
+    idx = np.arange(n)
+    Hd = np.zeros((n, n), dtype=complex)
+    for q in range(nq):
+        Hd[idx ^ (1 << q), idx] = -1.0
+    z = [1.0 - 2.0 * ((idx >> (nq - 1 - q)) & 1) for q in range(nq)]
+    diag = -sum(z[i] * z[i + 1] for i in range(nq - 1))
+    return Hd, np.diag(diag).astype(complex), z
+
+
+def timed(fn, steps, warmup, torch):
+    for _ in range(max(warmup, 3)):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def rand_states(torch, B, n, cols, seed):
+    gen = torch.Generator(device="cuda").manual_seed(seed)
+    return torch.randn((B, cols, n), dtype=torch.complex128, device="cuda", generator=gen)
+
+
+def run_c2(Q, torch, steps, dense_L):
+    """C2: 8-qubit dense TFIM + 8 Lindblad operators, batch 4096 of 256×256 ρ, per-member s_b = b/B."""
+    nq, n, K, B = 8, 256, 8, 4096
+    rng = np.random.default_rng(2000)
+    Hd, Hp, z = tfim_dense(nq)
+    Ls = [rng.standard_normal((n, n)) / np.sqrt(n) + 1j * rng.standard_normal((n, n)) / np.sqrt(n) for _ in range(K)] if dense_L \
+        else [np.diag(zq).astype(complex) for zq in z]
+    H = Q.DenseHamiltonian([lambda s: 1 - s, lambda s: s], [Hd, Hp], unit="ħ")
+    lind = Q.LindbladLiouvillian([Q.Lindblad(0.1 * (1 + k / 8), L) for k, L in enumerate(Ls)])
+    op = Q.DiffEqLiouvillian(H, [], [lind], n)
+    p = Q.ODEParams(None, 1.0)
+    t = np.arange(B) / B
+    g = rand_states(torch, B, n, 16, 2000)
+    rho = g.transpose(1, 2) @ g.conj()
+    rho = rho / torch.diagonal(rho, dim1=1, dim2=2).sum(-1).real[:, None, None]
+    u = Q.DeviceBatch(B, n, n, Q.get_context(), rho.contiguous())
+    du = u.zeros_like()
+    ctx = Q.get_context()
+    fn = lambda: op(du, u, p, t)
+    fn()
+    ctx.check(ctx.lib.oqb_profile_begin(ctx.h))
+    ms = timed(fn, steps, 3, torch)
+    zms, zn, zfl = C.c_double(), C.c_uint64(), C.c_double()
+    ctx.check(ctx.lib.oqb_profile_end(ctx.h, C.byref(zms), C.byref(zn), C.byref(zfl)))
+    flops = 8.0 * n ** 3 * (2 + 2 * K) * B
+    dmma, _ = ctx.probe_fp64()
+    ach = zfl.value / (zms.value * 1e-3) / 1e12
+    return {"config": "C2" + ("-denseL" if dense_L else "-Zk"), "workload": f"8-qubit dense TFIM + {K} {'random dense' if dense_L else 'dense-stored Z_k'} Lindblad ops, batch {B} of {n}x{n} rho, per-member s",
+            "metric": "rho_rhs_evals_per_sec", "value": B / (ms * 1e-3), "ms_per_step": ms,
+            "algorithmic_tflop_per_step": flops / 1e12, "step_tflops": flops / (ms * 1e-3) / 1e12,
+            "roofline": {"bound": "tensor", "kernel": "zgemm_tma_kernel", "achieved": ach, "peak": dmma, "unit": "TFLOP/s",
+                         "frac": ach / dmma, "kernel_share_of_step": zms.value / ((max(3, 3) + steps) * ms),
+                         "peak_source": "DMMA issue probe, this run"}}
+
+
+def run_c4(Q, torch, steps):
+    """C4: 12-qubit sparse TFIM trajectories, 65536 ψ of dimension 4096, per-trajectory s_b, γ_k = 0.05."""
+    import scipy.sparse as sps
+    nq, n, B = 12, 4096, 65536
+    idx = np.arange(n)
+    rows = np.concatenate([idx ^ (1 << q) for q in range(nq)])
+    cols = np.tile(idx, nq)
+    Hx = sps.csc_matrix((-np.ones(n * nq), (rows, cols)), shape=(n, n), dtype=complex)
+    z = [1.0 - 2.0 * ((idx >> (nq - 1 - q)) & 1) for q in range(nq)]
+    Hz = sps.diags(-sum(z[i] * z[i + 1] for i in range(nq - 1))).tocsc().astype(complex)
+    Ls = [sps.diags(zq).tocsc().astype(complex) for zq in z]
+    H = Q.SparseHamiltonian([lambda s: 1 - s, lambda s: s], [Hx, Hz], unit="ħ")
+    op = Q.DiffEqLiouvillian(H, [], [Q.LindbladLiouvillian([Q.Lindblad(0.05, L) for L in Ls])], n)
+    ens = Q.TrajectoryEnsemble(op)
+    ctx = Q.get_context()
+    psi_t = rand_states(torch, B, n, 1, 4000)
+    psi_t = psi_t / torch.linalg.vector_norm(psi_t, dim=2, keepdim=True)
+    psi = Q.DeviceBatch(B, n, 1, ctx, psi_t.contiguous())
+    dpsi = psi.zeros_like()
+    rng = np.random.default_rng(4000)
+    s = rng.random(B)
+    cf = np.ascontiguousarray(np.stack([1 - s, s], axis=1))
+    gam = np.full((1, nq), 0.05)
+    dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    mv = lambda: ctx.check(ctx.lib.oqb_traj_matvec(ens.sp, B, dp(cf), 0, dp(gam), 1, psi.ptr, dpsi.ptr))
+    ms_mv = timed(mv, steps, 3, torch)
+    uni = torch.as_tensor(rng.random(B), device="cuda")
+    choice = torch.zeros(B, dtype=torch.int32, device="cuda")
+    prob = torch.zeros((B, nq), dtype=torch.float64, device="cuda")
+    jp = lambda ap: (lambda: ctx.check(ctx.lib.oqb_traj_jump(ens.sp, B, dp(gam), 1, psi.ptr, C.c_void_p(uni.data_ptr()), None,
+                                                             C.c_void_p(choice.data_ptr()), C.c_void_p(prob.data_ptr()), ap)))
+    ms_j0 = timed(jp(0), steps, 3, torch)
+    ms_j1 = timed(jp(1), steps, 3, torch)  # Z_k are unitary: repeated in-place application keeps ψ normalised
+    hbm, src = peaks()
+    gb_mv, gb_j0, gb_j1 = 32.0 * n * B / 1e9, 16.0 * n * B / 1e9, 32.0 * n * B / 1e9
+    return {"config": "C4", "workload": f"12-qubit SparseHamiltonian TFIM trajectories, {B} psi of dim {n}, per-trajectory s, K=12 diagonal L_k",
+            "metric": "trajectory_matvecs_per_sec", "value": B / (ms_mv * 1e-3), "ms_per_step": ms_mv,
+            "roofline": {"bound": "hbm", "kernel": "traj_matvec_kernel", "achieved": gb_mv / (ms_mv * 1e-3), "peak": hbm, "unit": "GB/s",
+                         "frac": gb_mv / (ms_mv * 1e-3) / hbm, "frac_of_nominal_8TBs": gb_mv / (ms_mv * 1e-3) / 8000.0, "peak_source": src,
+                         "algorithmic_bytes_per_launch": gb_mv * 1e9},
+            "jump": {"decide_only_ms": ms_j0, "decide_only_GBs": gb_j0 / (ms_j0 * 1e-3), "decide_only_frac": gb_j0 / (ms_j0 * 1e-3) / hbm,
+                     "decide_and_apply_ms": ms_j1, "decide_and_apply_GBs": gb_j1 / (ms_j1 * 1e-3),
+                     "decide_and_apply_frac": gb_j1 / (ms_j1 * 1e-3) / hbm}}
+
+
+def run_c5(Q, torch, steps):
+    """C5 (per-GPU share): 1024 schedules × 7-qubit Redfield RHS (commutator + apply with supplied Λ), n = 128, K = 7."""
+    nq, n, K, B = 7, 128, 7, 1024
+    Hd, Hp, z = tfim_dense(nq)
+    S = [np.diag(zq).astype(complex) for zq in z]
+    H = Q.DenseHamiltonian([lambda s: 1 - s, lambda s: s], [Hd, Hp], unit="ħ")
+    ctx = Q.get_context()
+    g = rand_states(torch, B, n, 16, 5000)
+    rho = g.transpose(1, 2) @ g.conj()
+    rho = rho / torch.diagonal(rho, dim1=1, dim2=2).sum(-1).real[:, None, None]
+    u = Q.DeviceBatch(B, n, n, ctx, rho.contiguous())
+    du = u.zeros_like()
+    Lam = Q.DeviceBatch(B * K, n, n, ctx, rand_states(torch, B * K, n, n, 5001) / n)
+    Sd = Q.DeviceBatch.from_host(np.stack(S), ctx)
+    pw = 0.5 + 1.5 * np.arange(B) / B
+    s = 0.37 ** pw
+
+    def fn():
+        H.commutator(du, u, s)
+        ctx.check(ctx.lib.oqb_redfield_apply_acc(ctx.h, n, K, Sd.ptr, 1, Lam.ptr, B, u.ptr, du.ptr))
+    fn()
+    ctx.check(ctx.lib.oqb_profile_begin(ctx.h))
+    ms = timed(fn, steps, 3, torch)
+    zms, zn, zfl = C.c_double(), C.c_uint64(), C.c_double()
+    ctx.check(ctx.lib.oqb_profile_end(ctx.h, C.byref(zms), C.byref(zn), C.byref(zfl)))
+    flops = 8.0 * n ** 3 * (2 + 3 * K) * B
+    dmma, _ = ctx.probe_fp64()
+    ach = zfl.value / (zms.value * 1e-3) / 1e12
+    return {"config": "C5-per-GPU", "workload": f"{B} schedules x 7-qubit Redfield RHS (commutator + apply, supplied Lambda), n={n}, K={K}, per-schedule s",
+            "metric": "rho_rhs_evals_per_sec", "value": B / (ms * 1e-3), "ms_per_step": ms,
+            "algorithmic_tflop_per_step": flops / 1e12, "step_tflops": flops / (ms * 1e-3) / 1e12,
+            "roofline": {"bound": "tensor", "kernel": "zgemm_tma_kernel", "achieved": ach, "peak": dmma, "unit": "TFLOP/s",
+                         "frac": ach / dmma, "kernel_share_of_step": zms.value / ((3 + steps) * ms), "peak_source": "DMMA issue probe, this run"}}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--configs", default="c2,c2dense,c4,c5")
+    ap.add_argument("--steps", type=int, default=5)
+    args = ap.parse_args()
+    import torch
+    import oqb_b200 as Q
+    Q.get_context()
+    for c in args.configs.split(","):
+        if c == "c2":
+            r = run_c2(Q, torch, args.steps, False)
+        elif c == "c2dense":
+            r = run_c2(Q, torch, args.steps, True)
+        elif c == "c4":
+            r = run_c4(Q, torch, args.steps)
+        elif c == "c5":
+            r = run_c5(Q, torch, args.steps)
+        else:
+            continue
+        print(json.dumps(r), flush=True)
+        torch.cuda.empty_cache()
+
+
+if __name__ == "__main__":
+    main()

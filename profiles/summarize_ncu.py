@@ -1,0 +1,67 @@
+#!/usr/bin/env python
+"""Turns the raw ncu outputs under gpurun_out/ into the small tracked summaries under profiles/.
+
+  python profiles/summarize_ncu.py launches gpurun_out/launches_r1b.csv > profiles/r1_launches.md
+  python profiles/summarize_ncu.py kernel   gpurun_out/prof_zgemm_tma_r1b.ncu-rep > profiles/r1_zgemm_tma_ncu.md
+"""
+import collections
+import csv
+import subprocess
+import sys
+
+KEYS = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
+        "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
+        "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__throughput.avg.pct_of_peak_sustained_elapsed",
+        "lts__t_bytes.sum", "lts__t_sector_hit_rate.pct",
+        "sm__pipe_tensor_subpipe_dmma_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",
+        "sm__inst_executed_pipe_tensor_subpipe_dmma.avg.pct_of_peak_sustained_active",
+        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
+        "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+        "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio"]
+
+
+def launches(path):
+    rows = [r for r in csv.reader(open(path)) if len(r) > 5]
+    hdr = rows[0]
+    ki, vi, ui = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
+    agg = collections.OrderedDict()
+    for r in rows[1:]:
+        try:
+            v = float(r[vi].replace(",", ""))
+        except ValueError:
+            continue
+        v *= {"ns": 1.0, "us": 1e3, "ms": 1e6, "s": 1e9}.get(r[ui], 1.0)
+        a = agg.setdefault(r[ki], [0, 0.0])
+        a[0] += 1
+        a[1] += v
+    tot = sum(a[1] for a in agg.values())
+    print(f"# ncu launch list: {path}\n")
+    print("`ncu --metrics gpu__time_duration.sum --clock-control none` — cold-cache, serialised launches: compare SHARES.\n")
+    print("| launches | total ms | share | kernel |\n|---:|---:|---:|---|")
+    for k, (n, t) in sorted(agg.items(), key=lambda x: -x[1][1]):
+        print(f"| {n} | {t / 1e6:.3f} | {100 * t / tot:.1f}% | `{k[:110]}` |")
+
+
+def kernel(path):
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units = rows[0], rows[1]
+    print(f"# ncu --set full: {path}\n")
+    ni = hdr.index("Kernel Name")
+    for r in rows[2:]:
+        print(f"kernel: `{r[ni][:160]}`\n")
+        print("| metric | value | unit |\n|---|---:|---|")
+        for k in KEYS:
+            for i, h in enumerate(hdr):
+                if h == k:
+                    print(f"| {k} | {r[i]} | {units[i]} |")
+
+
+if __name__ == "__main__":
+    {"launches": launches, "kernel": kernel}[sys.argv[1]](sys.argv[2])
