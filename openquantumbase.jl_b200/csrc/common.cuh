@@ -39,6 +39,26 @@ struct Ctx {
 };
 
 int set_error(Ctx* c, int code, const char* fmt, ...);
+
+// Brackets one launch of a path's dominant kernel with a CUDA-event pair while profiling is on
+// (oqb_profile_begin/end); `work` is the launch's algorithmic flops or bytes.
+struct ProfScope {
+    Ctx* c;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    double work;
+    ProfScope(Ctx* ctx, double w) : c(ctx), work(w) {
+        if (c->profiling && cudaEventCreate(&e0) == cudaSuccess && cudaEventCreate(&e1) == cudaSuccess)
+            cudaEventRecord(e0, c->stream);
+    }
+    ~ProfScope() {
+        if (c->profiling && e0 && e1) {
+            cudaEventRecord(e1, c->stream);
+            c->prof_events.push_back(e0);
+            c->prof_events.push_back(e1);
+            c->prof_flops += work;
+        }
+    }
+};
 int ws_reserve(Ctx* c, size_t bytes);
 int io_reserve(Ctx* c, size_t bytes);
 int coef_upload(Ctx* c, const void* host, size_t bytes, void** dptr);  // async on c->stream

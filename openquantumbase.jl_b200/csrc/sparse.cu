@@ -18,6 +18,7 @@
 
 #include "../../include/oqb.h"
 #include "common.cuh"
+#include "sparse_terms.cuh"
 
 using namespace oqb;
 
@@ -30,12 +31,6 @@ struct HostCsc {  // 0-based, rows sorted within a column
     std::vector<int64_t> colptr;
     std::vector<int32_t> row;
     std::vector<c128> val;
-};
-
-struct TermDev {  // one operator term on the device
-    int is_diag = 0, is_real = 0, width = 0;
-    c128* vals = nullptr;  // diag: n ; ELL: width*n (column-major: [j*n + r])
-    int32_t* cols = nullptr;  // ELL only
 };
 
 struct TermDesc {  // POD passed to kernels
@@ -115,6 +110,8 @@ struct oqb_sparse {
     TermDev ldl_comb;                // −½Σγ_k L_k'L_k on the L'L-union pattern (shared-γ fast path)
     c128* d_ldl_src = nullptr;       // K × (comb entries): L_k'L_k expanded on the comb pattern
     long long comb_len = 0;
+    bool ldl_all_const = false;      // every L_k'L_k is c_k·I (e.g. Pauli jump operators)
+    std::vector<double> ldl_const;   // the c_k
 };
 
 namespace {
@@ -122,8 +119,14 @@ namespace {
 void free_term(TermDev& t) {
     if (t.vals) cudaFree(t.vals);
     if (t.cols) cudaFree(t.cols);
+    if (t.rvals) cudaFree(t.rvals);
+    if (t.absq) cudaFree(t.absq);
+    t.absq = nullptr;
+    if (t.cols16) cudaFree(t.cols16);
     t.vals = nullptr;
     t.cols = nullptr;
+    t.rvals = nullptr;
+    t.cols16 = nullptr;
 }
 
 // Build the device representation (diag or ELL) for a CSC matrix; `pattern_of` (optional) forces
@@ -147,6 +150,23 @@ int make_term(oqb_ctx* c, const HostCsc& m, TermDev& out) {
         out.width = 1;
         OQB_CUDA(c, cudaMalloc((void**)&out.vals, (size_t)n * sizeof(c128)));
         OQB_CUDA(c, cudaMemcpy(out.vals, d.data(), (size_t)n * sizeof(c128), cudaMemcpyHostToDevice));
+        {
+            std::vector<double> aq(n);
+            out.absq_const = true;
+            for (int j = 0; j < n; ++j) {
+                aq[j] = d[j].x * d[j].x + d[j].y * d[j].y;
+                if (aq[j] != aq[0]) out.absq_const = false;
+            }
+            out.absq_val = n ? aq[0] : 0.0;
+            OQB_CUDA(c, cudaMalloc((void**)&out.absq, (size_t)n * sizeof(double)));
+            OQB_CUDA(c, cudaMemcpy(out.absq, aq.data(), (size_t)n * sizeof(double), cudaMemcpyHostToDevice));
+        }
+        if (real) {
+            std::vector<double> dr(n);
+            for (int j = 0; j < n; ++j) dr[j] = d[j].x;
+            OQB_CUDA(c, cudaMalloc((void**)&out.rvals, (size_t)n * sizeof(double)));
+            OQB_CUDA(c, cudaMemcpy(out.rvals, dr.data(), (size_t)n * sizeof(double), cudaMemcpyHostToDevice));
+        }
         return 0;
     }
     int width = 0;
@@ -169,6 +189,47 @@ int make_term(oqb_ctx* c, const HostCsc& m, TermDev& out) {
     OQB_CUDA(c, cudaMalloc((void**)&out.cols, ci.size() * sizeof(int32_t)));
     OQB_CUDA(c, cudaMemcpy(out.vals, v.data(), v.size() * sizeof(c128), cudaMemcpyHostToDevice));
     OQB_CUDA(c, cudaMemcpy(out.cols, ci.data(), ci.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    // XOR form: group the entries by mask = row ^ col
+    {
+        std::map<int, std::pair<long long, c128>> byMask;
+        bool ok = true;
+        for (int j = 0; j < n && ok; ++j)
+            for (int64_t p = m.colptr[j]; p < m.colptr[j + 1] && ok; ++p) {
+                const int mask = m.row[p] ^ j;
+                auto it = byMask.find(mask);
+                if (it == byMask.end()) {
+                    if ((int)byMask.size() >= 16) { ok = false; break; }
+                    byMask[mask] = {1, m.val[p]};
+                } else {
+                    if (it->second.second.x != m.val[p].x || it->second.second.y != m.val[p].y) ok = false;
+                    it->second.first++;
+                }
+            }
+        for (auto& e : byMask) ok = ok && e.second.first == n;
+        if (ok && !byMask.empty()) {
+            out.xor_form = true;
+            for (auto& e : byMask) { out.xor_masks.push_back(e.first); out.xor_vals.push_back(e.second.second); }
+        }
+    }
+    // compressed forms for the fast trajectory kernel
+    bool full = true;
+    for (int r = 0; r < n; ++r) full = full && cnt[r] == width;
+    if (full && n <= 65536) {
+        std::vector<uint16_t> c16(ci.size());
+        for (size_t i = 0; i < ci.size(); ++i) c16[i] = (uint16_t)ci[i];
+        OQB_CUDA(c, cudaMalloc((void**)&out.cols16, c16.size() * sizeof(uint16_t)));
+        OQB_CUDA(c, cudaMemcpy(out.cols16, c16.data(), c16.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+        out.slot_const = true;
+        out.slot_vals.resize(width);
+        for (int j = 0; j < width && out.slot_const; ++j) {
+            out.slot_vals[j] = v[(size_t)j * n];
+            for (int r = 1; r < n; ++r)
+                if (v[(size_t)j * n + r].x != out.slot_vals[j].x || v[(size_t)j * n + r].y != out.slot_vals[j].y) {
+                    out.slot_const = false;
+                    break;
+                }
+        }
+    }
     return 0;
 }
 
@@ -250,7 +311,7 @@ __global__ void __launch_bounds__(512) traj_matvec_kernel(int n, int nb, TermLis
 
 // combined dissipator values: out[e] = Σ_k (−½γ_k) src[k*len + e]
 __global__ void ldl_combine_kernel(int K, long long len, const double* __restrict__ gamma, const c128* __restrict__ src,
-                                   c128* __restrict__ out) {
+                                   c128* __restrict__ out, double* __restrict__ out_real) {
     long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (e >= len) return;
     double sr = 0.0, si = 0.0;
@@ -261,6 +322,7 @@ __global__ void ldl_combine_kernel(int K, long long len, const double* __restric
         si = fma(g, v.y, si);
     }
     out[e] = make_double2(sr, si);
+    if (out_real) out_real[e] = sr;  // diagonal of a Hermitian L'L is real: compressed copy for the fast kernel
 }
 
 __global__ void norm2_kernel(int n, const c128* __restrict__ psi, double* __restrict__ out) {
@@ -368,6 +430,104 @@ __global__ void __launch_bounds__(512) traj_jump_kernel(int n, int nb, TermList 
     }
 }
 
+// K8 for diagonal jump operators (e.g. Z_k dephasing): no gathers, so ψ never touches shared memory — every
+// thread keeps its R rows in registers, the K norms are reduced by a fixed-order shuffle tree, and the
+// selected operator is applied from registers.  DRAM traffic: 16n read (+16n written when applied).
+struct DiagJumpDesc {
+    int K, all_const;
+    const double* absq[kMaxTerms];
+    const c128* d[kMaxTerms];
+    const double* dreal[kMaxTerms];
+    double cabs[kMaxTerms];
+};
+
+template <int R, int NT>
+__global__ void __launch_bounds__(NT) traj_jump_diag_kernel(int n, int nb, DiagJumpDesc dj, const double* __restrict__ gamma,
+                                                            long long gamma_ld, c128* __restrict__ psi,
+                                                            const double* __restrict__ uniform,
+                                                            const unsigned char* __restrict__ mask, int32_t* __restrict__ choice,
+                                                            double* __restrict__ prob, int apply) {
+    __shared__ double red[kMaxTerms][NT / 32];
+    __shared__ double s_norm2;
+    __shared__ int s_choice;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int K = dj.K;
+    for (int b = blockIdx.x; b < nb; b += gridDim.x) {
+        if (mask && !mask[b]) {
+            if (tid == 0 && choice) choice[b] = -1;
+            continue;
+        }
+        c128* pb = psi + (size_t)b * n;
+        c128 x[R];
+        double a2[R];
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+            const int r = tid + k * NT;
+            x[k] = r < n ? pb[r] : make_double2(0.0, 0.0);
+            a2[k] = fma(x[k].x, x[k].x, x[k].y * x[k].y);
+        }
+        __syncthreads();  // red / s_* of the previous trajectory fully consumed
+        const int nacc = dj.all_const ? 1 : K;
+        for (int k = 0; k < nacc; ++k) {
+            double s = 0.0;
+            if (dj.all_const) {
+#pragma unroll
+                for (int q = 0; q < R; ++q) s += a2[q];
+            } else {
+#pragma unroll
+                for (int q = 0; q < R; ++q) {
+                    const int r = tid + q * NT;
+                    if (r < n) s = fma(__ldg(dj.absq[k] + r), a2[q], s);
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (lane == 0) red[k][warp] = s;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            const double* g = gamma + b * gamma_ld;
+            double nrm[kMaxTerms];
+            for (int k = 0; k < nacc; ++k) {
+                double a = 0.0;
+                for (int i = 0; i < NT / 32; ++i) a += red[k][i];
+                nrm[k] = a;
+            }
+            double total = 0.0, pk[kMaxTerms];
+            for (int k = 0; k < K; ++k) {
+                const double n2 = dj.all_const ? dj.cabs[k] * nrm[0] : nrm[k];  // ‖L_kψ‖²
+                nrm[k == 0 ? 0 : k] = dj.all_const ? nrm[0] : nrm[k];
+                pk[k] = g[k] * n2;  // γ_k · norm(L_k u)^2   (trajectory_jump.jl:8)
+                if (prob) prob[(size_t)b * K + k] = pk[k];
+                total += pk[k];
+            }
+            const double tthr = uniform[b] * total;  // StatsBase.sample(rng, wv)
+            int i = 0;
+            double cw = pk[0];
+            while (cw < tthr && i < K - 1) { ++i; cw += pk[i]; }
+            s_choice = i;
+            s_norm2 = dj.all_const ? dj.cabs[i] * nrm[0] : nrm[i];
+            if (choice) choice[b] = i;
+        }
+        if (apply) {
+            __syncthreads();
+            const int kc = s_choice;
+            const double inv = s_norm2 > 0.0 ? 1.0 / sqrt(s_norm2) : 0.0;
+#pragma unroll
+            for (int k = 0; k < R; ++k) {
+                const int r = tid + k * NT;
+                if (r < n) {
+                    c128 dv;
+                    if (dj.dreal[kc]) dv = make_double2(__ldg(dj.dreal[kc] + r), 0.0);
+                    else dv = __ldg(dj.d[kc] + r);
+                    const double yr = dv.x * x[k].x - dv.y * x[k].y, yi = dv.x * x[k].y + dv.y * x[k].x;
+                    pb[r] = make_double2(yr * inv, yi * inv);
+                }
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // sparse commutator on density matrices: du = −i(H u − u H), H given by values on the union pattern
 // ------------------------------------------------------------------------------------------
@@ -424,7 +584,15 @@ int traj_matvec_impl(oqb_sparse* sp, int nb, const double* coefH, int coef_share
     std::vector<const TermDev*> ts;
     for (int i = 0; i < nt; ++i) ts.push_back(&sp->h_terms[i]);
     const bool comb = K > 0 && gamma_shared;
-    if (comb) ts.push_back(&sp->ldl_comb);
+    if (comb) {
+        sp->ldl_comb.diag_const = sp->ldl_all_const;
+        sp->ldl_comb.const_coef_one = true;
+        double cv = 0.0;
+        if (sp->ldl_all_const)
+            for (int k = 0; k < K; ++k) cv = fma(-0.5 * gamma[k], sp->ldl_const[k], cv);
+        sp->ldl_comb.const_val = make_double2(cv, 0.0);
+        ts.push_back(&sp->ldl_comb);
+    }
     else for (int k = 0; k < K; ++k) ts.push_back(&sp->ldl_terms[k]);
     TermList tl;
     OQB_TRY(term_list(ts, tl, c));
@@ -446,8 +614,19 @@ int traj_matvec_impl(oqb_sparse* sp, int nb, const double* coefH, int coef_share
     if (comb) {
         const double* dg = (const double*)((char*)d_stage + (size_t)rows * ncoef * sizeof(c128));
         ldl_combine_kernel<<<(unsigned)((sp->comb_len + 255) / 256), 256, 0, c->stream>>>(K, sp->comb_len, dg, sp->d_ldl_src,
-                                                                                       sp->ldl_comb.vals);
+                                                                                       sp->ldl_comb.vals,
+                                                                                       sp->ldl_comb.is_diag ? sp->ldl_comb.rvals : nullptr);
         OQB_LAUNCH_CHECK(c);
+    }
+    {
+        bool used = false;  // implicit-column (XOR-structured) operator, 3-deep ψ ring, no CTA barrier
+        OQB_TRY(traj_matvec_xor(c, n, nb, ts, (const c128*)d_stage, shared ? 0 : ncoef, psi, dpsi, &used));
+        if (used) return 0;
+    }
+    {
+        bool used = false;  // register-resident operator + bulk-async ψ staging when the term list allows it
+        OQB_TRY(traj_matvec_fast(c, n, nb, ts, (const c128*)d_stage, shared ? 0 : ncoef, psi, dpsi, &used));
+        if (used) return 0;
     }
     const size_t smem = (size_t)n * sizeof(c128);
     const int threads = n >= 2048 ? 512 : (n >= 256 ? 256 : 64);
@@ -457,6 +636,7 @@ int traj_matvec_impl(oqb_sparse* sp, int nb, const double* coefH, int coef_share
         if (!cfg) { OQB_CUDA(c, cudaFuncSetAttribute(traj_matvec_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); cfg = true; }
         int per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (220 * 1024) / (smem + 1024)));
         int grid = std::min(nb, sms * per_sm);
+        ProfScope prof(c, 32.0 * n * (double)nb);
         traj_matvec_kernel<true><<<grid, threads, smem, c->stream>>>(n, nb, tl, (const c128*)d_stage, shared ? 0 : ncoef, psi, dpsi);
     } else {
         int grid = std::min(nb, sms * 4);
@@ -551,6 +731,20 @@ int oqb_sparse_create(oqb_ctx* c, int n, int nterms, const int64_t* h_colptr, co
     for (int k = 0; k < K && !s; ++k) s = make_term(c, ldl[k], sp->ldl_terms[k]);
     for (int k = 0; k < K && !s; ++k) s = make_term(c, lm[k], sp->l_terms[k]);
     if (!s && K > 0) {
+        sp->ldl_all_const = true;
+        sp->ldl_const.assign(K, 0.0);
+        for (int k = 0; k < K && sp->ldl_all_const; ++k) {
+            const HostCsc& m = ldl[k];
+            if ((int64_t)m.row.size() != n) { sp->ldl_all_const = false; break; }
+            for (int j = 0; j < n; ++j) {
+                const int64_t p0 = m.colptr[j];
+                if (m.colptr[j + 1] - p0 != 1 || m.row[p0] != j || m.val[p0].y != 0.0 || m.val[p0].x != m.val[0].x) {
+                    sp->ldl_all_const = false;
+                    break;
+                }
+            }
+            sp->ldl_const[k] = m.val.empty() ? 0.0 : m.val[0].x;
+        }
         // shared-γ fast path: every L_k'L_k expanded on their common pattern so that −½Σγ_k L_k'L_k is one term
         std::vector<const HostCsc*> ls;
         for (auto& m : ldl) ls.push_back(&m);
@@ -675,6 +869,39 @@ int oqb_traj_jump(oqb_sparse* sp, int nb, const double* h_gamma, int gamma_share
     OQB_TRY(term_list(ts, tl, c));
     void* d_gamma = nullptr;
     OQB_TRY(coef_upload(c, h_gamma, sizeof(double) * (gamma_shared ? K : (size_t)nb * K), &d_gamma));
+    {
+        bool all_diag = true, all_const = true;
+        for (int k = 0; k < K; ++k) {
+            all_diag = all_diag && sp->l_terms[k].is_diag && sp->l_terms[k].absq;
+            all_const = all_const && sp->l_terms[k].absq_const;
+        }
+        static const bool no_fast = [] { const char* e = getenv("OQB_TRAJ"); return e && e[0] == 'g'; }();
+        if (all_diag && !no_fast && n <= 512 * 16) {
+            DiagJumpDesc dj;
+            dj.K = K;
+            dj.all_const = all_const ? 1 : 0;
+            for (int k = 0; k < K; ++k) {
+                dj.absq[k] = sp->l_terms[k].absq;
+                dj.d[k] = sp->l_terms[k].vals;
+                dj.dreal[k] = sp->l_terms[k].is_real ? sp->l_terms[k].rvals : nullptr;
+                dj.cabs[k] = sp->l_terms[k].absq_val;
+            }
+            const int sms2 = sm_count(c);
+            const int grid = std::min(nb, sms2 * 16);
+            ProfScope prof(c, (apply ? 32.0 : 16.0) * n * (double)nb);
+#define OQB_DJ(RR, TT)                                                                                          \
+    traj_jump_diag_kernel<RR, TT><<<grid, TT, 0, c->stream>>>(n, nb, dj, (const double*)d_gamma, gamma_shared ? 0 : K, \
+                                                              (c128*)d_psi, d_uniform, d_mask, d_choice, d_prob, apply)
+            if (n <= 256) OQB_DJ(2, 128);
+            else if (n <= 1024) OQB_DJ(4, 256);
+            else if (n <= 2048) OQB_DJ(8, 256);
+            else if (n <= 4096) OQB_DJ(8, 512);
+            else OQB_DJ(16, 512);
+#undef OQB_DJ
+            OQB_LAUNCH_CHECK(c);
+            return 0;
+        }
+    }
     const size_t smem = (size_t)n * sizeof(c128);
     const int threads = n >= 2048 ? 512 : (n >= 256 ? 256 : 64);
     const int sms = sm_count(c);
@@ -683,6 +910,7 @@ int oqb_traj_jump(oqb_sparse* sp, int nb, const double* h_gamma, int gamma_share
         if (!cfg) { OQB_CUDA(c, cudaFuncSetAttribute(traj_jump_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); cfg = true; }
         int per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (200 * 1024) / (smem + 8 * 1024)));
         int grid = std::min(nb, sms * per_sm);
+        ProfScope prof(c, (apply ? 32.0 : 16.0) * n * (double)nb);
         traj_jump_kernel<true><<<grid, threads, smem, c->stream>>>(n, nb, tl, (const double*)d_gamma, gamma_shared ? 0 : K,
                                                                    (c128*)d_psi, d_uniform, d_mask, d_choice, d_prob, apply);
     } else {

@@ -1,0 +1,40 @@
+// Device representation of one sparse operator term (shared by sparse.cu and traj_fast.cu).
+#pragma once
+#include <vector>
+
+#include "common.cuh"
+
+namespace oqb {
+
+struct TermDev {
+    int is_diag = 0, is_real = 0, width = 0;
+    c128* vals = nullptr;     // diag: n ; ELL: width*n (column-major: [j*n + r])
+    int32_t* cols = nullptr;  // ELL only
+    // compressed forms used by the fast trajectory kernel (traj_fast.cu)
+    double* rvals = nullptr;         // diag && is_real: n real values
+    double* absq = nullptr;          // diag: |d_r|² (jump probabilities)
+    bool absq_const = false;         // … identical for every row (unit-modulus diagonals: Pauli Z strings)
+    double absq_val = 0.0;
+    uint16_t* cols16 = nullptr;      // ELL && n ≤ 65536 && every row full: 16-bit column indices
+    bool slot_const = false;         // ELL: every slot j holds one value for all rows (Pauli-string structure)
+    std::vector<c128> slot_vals;     // … those values
+    // constant diagonal (value·I) whose coefficient is 1 for every member: folds into one scalar per call
+    bool diag_const = false, const_coef_one = false;
+    c128 const_val = {0.0, 0.0};
+    // XOR form: M[r, r ^ mask_j] = val_j for every row r (Pauli X-type strings): no per-row data at all
+    bool xor_form = false;
+    std::vector<int> xor_masks;
+    std::vector<c128> xor_vals;
+};
+
+// dψ_b = Σ_t coef[b][t] · M_t ψ_b with the operator held in registers (see traj_fast.cu).
+// *used == false ⇒ the term list does not fit the fast path; the caller runs the generic kernel.
+int traj_matvec_fast(Ctx* c, int n, int nb, const std::vector<const TermDev*>& ts, const c128* d_coef,
+                     long long coef_ld, const c128* psi, c128* dpsi, bool* used);
+
+// Same contract for terms in XOR form + real diagonal terms (implicit columns, 3-deep bulk-async ψ ring,
+// no CTA-wide barrier): traj_xor.cu.
+int traj_matvec_xor(Ctx* c, int n, int nb, const std::vector<const TermDev*>& ts, const c128* d_coef,
+                    long long coef_ld, const c128* psi, c128* dpsi, bool* used);
+
+}  // namespace oqb
