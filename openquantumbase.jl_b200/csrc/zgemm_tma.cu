@@ -243,36 +243,54 @@ __global__ void __launch_bounds__(CF::NTHREADS, 1)
     c128* __restrict__ C = p.C + zb * p.strideC + zk * p.strideC2;
     const c128* __restrict__ E = p.E ? p.E + zb * p.strideE : nullptr;
     c128* __restrict__ D = p.diag_out ? p.diag_out + zb * p.strideDiag : nullptr;
+    // Loads (old C for beta != 0, Hadamard factors) are issued for a whole j-slab (8 elements) before any
+    // dependent arithmetic or store, so their L2 latencies overlap instead of serialising element by element.
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
+    for (int j = 0; j < 4; ++j) {
+        c128 oldc[2][4], fac[2][4];
+        bool ok[2][4];
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
             const int col = n0 + wn0 + j * 8 + t + 4 * e;
-            if (col >= p.N) continue;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const int row = m0 + wm0 + i * 8 + pg;
-                if (row >= p.M) continue;
+                ok[e][i] = (col < p.N) && (row < p.M);
+                oldc[e][i] = make_double2(0.0, 0.0);
+                fac[e][i] = make_double2(1.0, 0.0);
+                if (ok[e][i]) {
+                    if (has_beta) oldc[e][i] = C[row + (long long)col * p.ldc];
+                    if (E) fac[e][i] = E[row + (long long)col * p.lde];
+                }
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int col = n0 + wn0 + j * 8 + t + 4 * e;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                if (!ok[e][i]) continue;
+                const int row = m0 + wm0 + i * 8 + pg;
                 const double xr = acc_re[i][j][e], xi = acc_im[i][j][e];
                 c128 v;
                 v.x = alpha.x * xr - alpha.y * xi;
                 v.y = alpha.x * xi + alpha.y * xr;
                 if (D && row == col) D[row] = v;
                 if (E) {
-                    const c128 f = E[row + (long long)col * p.lde];
+                    const c128 f = fac[e][i];
                     const double r2 = v.x * f.x - v.y * f.y, i2 = v.x * f.y + v.y * f.x;
                     v.x = r2;
                     v.y = i2;
                 }
-                c128* dst = C + row + (long long)col * p.ldc;
                 if (has_beta) {
-                    const c128 o = *dst;
+                    const c128 o = oldc[e][i];
                     v.x += beta.x * o.x - beta.y * o.y;
                     v.y += beta.x * o.y + beta.y * o.x;
                 }
-                *dst = v;
+                C[row + (long long)col * p.ldc] = v;
             }
         }
+    }
 }
 
 // 5-D FP64 views of an interleaved complex operand (inner = the contiguous index, `outer` the strided one):
