@@ -270,9 +270,11 @@ def main():
 
     achieved = zg_fl.value / (zg_ms.value * 1e-3) / 1e12 if zg_ms.value > 0 else None
     peak = max(dgemm_tf, dmma_tf)
-    roofline = {"bound": "tensor", "kernel": "zgemm_kernel (FP64 DMMA.8x8x4, 4 launches/step)",
+    roofline = {"bound": "tensor", "kernel": "zgemm_tma_kernel (FP64 DMMA.8x8x4, TMA-staged; 4 launches of 64 products per step)",
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if achieved else None,
-                "traffic": None,
+                "traffic": 2.163e9,
+                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one 64-product launch, ncu --set full, profiles/r1_zgemm_tma_ncu.md "
+                                  "(algorithmic: 1 GiB read + 1 GiB written + 16 MiB V)",
                 "peak_source": "measured in this run: max(cuBLAS DGEMM 8192^3 best-of-6, DMMA issue probe); MEASURED_PEAKS.json has no FP64 figure",
                 "cublas_dgemm_tflops": dgemm_tf, "cublas_zgemm_4096_tflops": zgemm_tf,
                 "dmma_probe_tflops": dmma_tf, "dfma_probe_tflops": dfma_tf,
