@@ -166,6 +166,10 @@ int oqb_sparse_pattern(oqb_sparse* sp, int64_t* h_colptr, int64_t* h_rowval);
  *   — update_cache!(cache, H::SparseHamiltonian, p, s) :70-75 + src/opensys/lindblad.jl:103-109 */
 int oqb_sparse_update_cache(oqb_sparse* sp, int nb, const double* h_coefH, int coef_shared,
                             const double* h_gamma, int gamma_shared, void* d_nzval);
+/* cache[b] (dense n²×n²) = i(Hᵀ⊗I − I⊗H)  (OVERWRITES) — update_vectorized_cache!(cache, H::SparseHamiltonian, p, s)
+ *   :77-81; the reference returns a sparse matrix with the same entries (small n only). */
+int oqb_sparse_update_vectorized_cache(oqb_sparse* sp, int nb, const double* h_coefH, int coef_shared,
+                                       void* d_cache);
 /* du[b] = −i(H u[b] − u[b] H)  (OVERWRITES)  — (h::SparseHamiltonian)(du,u,p,s) :83-91 */
 int oqb_sparse_commutator(oqb_sparse* sp, int nb, const double* h_coefH, int coef_shared,
                           const void* d_u, void* d_du);

@@ -60,6 +60,7 @@ SIGNATURES = {
     "oqb_sparse_pattern_nnz": [c_void_p, c_i64p],
     "oqb_sparse_pattern": [c_void_p, c_i64p, c_i64p],
     "oqb_sparse_update_cache": [c_void_p, c_int, c_dp, c_int, c_dp, c_int, c_void_p],
+    "oqb_sparse_update_vectorized_cache": [c_void_p, c_int, c_dp, c_int, c_void_p],
     "oqb_sparse_commutator": [c_void_p, c_int, c_dp, c_int, c_void_p, c_void_p],
     "oqb_traj_matvec": [c_void_p, c_int, c_dp, c_int, c_dp, c_int, c_void_p, c_void_p],
     "oqb_traj_matvec_host": [c_void_p, c_int, c_dp, c_int, c_dp, c_int, c_void_p, c_void_p],

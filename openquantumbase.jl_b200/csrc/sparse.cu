@@ -557,6 +557,20 @@ __global__ void sparse_commutator_kernel(int n, const int32_t* __restrict__ rowp
     du[(size_t)b * n * n + r + (size_t)cidx * n] = make_double2(si, -sr);  // −i (sr + i si)
 }
 
+// dense[b][row + col*n] = vals[b][p] for the CSC entry p (column found by binary search in colptr)
+__global__ void csc_densify_kernel(int n, long long nnz, const int32_t* __restrict__ colptr, const int32_t* __restrict__ rowidx,
+                                   const c128* __restrict__ vals, c128* __restrict__ dense) {
+    const int b = blockIdx.y;
+    long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (p >= nnz) return;
+    int lo = 0, hi = n;  // largest col with colptr[col] <= p
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (colptr[mid] <= p) lo = mid; else hi = mid;
+    }
+    dense[(size_t)b * n * n + rowidx[p] + (size_t)lo * n] = vals[(size_t)b * nnz + p];
+}
+
 int term_list(const std::vector<const TermDev*>& ts, TermList& tl, oqb_ctx* c) {
     if ((int)ts.size() > kMaxTerms) return set_error(c, OQB_EINVAL, "too many operator terms (%zu > %d)", ts.size(), kMaxTerms);
     tl.count = (int)ts.size();
@@ -803,6 +817,31 @@ int oqb_sparse_update_cache(oqb_sparse* sp, int nb, const double* h_coefH, int c
     void* d_coef = nullptr;
     OQB_TRY(coef_upload(c, coef.data(), coef.size() * sizeof(c128), &d_coef));
     return lincomb(c, nmat, sp->nnzU, sp->d_termvals, (const c128*)d_coef, shared ? 0 : nmat, (c128*)d_nzval, nb, false);
+}
+
+int oqb_sparse_update_vectorized_cache(oqb_sparse* sp, int nb, const double* h_coefH, int coef_shared, void* d_cache) {
+    oqb_ctx* c = sp->ctx;
+    if (nb <= 0) return 0;
+    if (!h_coefH || !d_cache) return set_error(c, OQB_EINVAL, "oqb_sparse_update_vectorized_cache: null argument");
+    const int n = sp->n, nt = sp->nterms;
+    const int rows = coef_shared ? 1 : nb;
+    const long long nn = (long long)n * n;
+    std::vector<c128> coef((size_t)rows * nt);
+    for (size_t i = 0; i < coef.size(); ++i) coef[i] = make_double2(h_coefH[i], 0.0);  // H(s) = Σ f_i m_i
+    void* d_coef = nullptr;
+    OQB_TRY(coef_upload(c, coef.data(), coef.size() * sizeof(c128), &d_coef));
+    const size_t nnzb = (size_t)std::max<int64_t>(sp->nnzU, 1);
+    OQB_TRY(ws_reserve(c, (size_t)rows * (nnzb + nn) * sizeof(c128)));
+    c128* vals = (c128*)c->ws;
+    c128* dense = vals + (size_t)rows * nnzb;
+    OQB_TRY(lincomb(c, nt, sp->nnzU, sp->d_termvals, (const c128*)d_coef, coef_shared ? 0 : nt, vals, rows, false));
+    OQB_CUDA(c, cudaMemsetAsync(dense, 0, (size_t)rows * nn * sizeof(c128), c->stream));
+    if (sp->nnzU > 0) {
+        dim3 grid((unsigned)((sp->nnzU + 255) / 256), rows);
+        csc_densify_kernel<<<grid, 256, 0, c->stream>>>(n, sp->nnzU, sp->d_u_colptr, sp->d_u_row, vals, dense);
+        OQB_LAUNCH_CHECK(c);
+    }
+    return vectorized_commutator(c, n, dense, coef_shared ? 0 : nn, (c128*)d_cache, nb);
 }
 
 int oqb_sparse_commutator(oqb_sparse* sp, int nb, const double* h_coefH, int coef_shared, const void* d_u, void* d_du) {

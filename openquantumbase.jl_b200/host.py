@@ -381,10 +381,38 @@ class SparseHamiltonian:
                                                           int(sv.size == 1), io.u.ptr, io.du.ptr))
         return io.finish()
 
+    def update_vectorized_cache(self, cache, s):
+        """update_vectorized_cache!(cache, H::SparseHamiltonian, p, s) :77-81 — dense n²×n² result, OVERWRITES."""
+        io = _HostIO(cache, cache)
+        B = io.u.B
+        sv = _svec(s, B)
+        cf = _coef(self.f, sv)
+        self.ctx.check(self.ctx.lib.oqb_sparse_update_vectorized_cache(self._sparse_op(self._lops_ref), B, _lib.dptr(cf),
+                                                                       int(sv.size == 1), io.du.ptr))
+        return io.finish()
+
     def host_matrix(self, s: float):
         H = None
         for f, m in zip(self.f, self.m):
             H = f(s) * m if H is None else H + f(s) * m
+        return H
+
+
+class AdiabaticFrameHamiltonian:
+    """src/hamiltonian/adiabatic_frame_hamiltonian.jl:84-130: H(tf, s) = 2π·diag(ω(s)) + G(s)/tf.
+    `omega_fun(s)` returns the eigen-energies (GHz), `geo_fun(s)` the geometric matrix or None.  The
+    matrix itself is closure-driven and assembled on the host; it is only ever APPLIED on the device."""
+
+    def __init__(self, omega_fun, geo_fun=None, ctx: Optional[Context] = None):
+        self.omega_fun, self.geo_fun = omega_fun, geo_fun
+        n = len(np.atleast_1d(omega_fun(0.0)))
+        self.size = (n, n)
+        self.ctx = ctx or get_context()
+
+    def __call__(self, tf, s):
+        H = np.diag(2 * math.pi * np.asarray(self.omega_fun(s), dtype=np.float64)).astype(C128)
+        if self.geo_fun is not None:
+            H = H + np.asarray(self.geo_fun(s), dtype=C128) / tf
         return H
 
 
@@ -573,6 +601,7 @@ class DiffEqLiouvillian:
         self.H, self.opensys_eig, self.opensys = H, list(opensys_eig), list(opensys)
         self.lvl, self.digits, self.sigdigits = lvl, digits, sigdigits
         self.diagonalization = len(self.opensys_eig) > 0
+        self.adiabatic_frame = isinstance(H, AdiabaticFrameHamiltonian)  # :57
         self.ctx = H.ctx
         self._ame = None
         self._ame_s = None
@@ -583,7 +612,32 @@ class DiffEqLiouvillian:
     def _fused_lindblad(self):
         return (isinstance(self.H, DenseHamiltonian) and len(self._lind) == 1)
 
+    def _rhs_adiabatic_frame(self, du, u, p, t):
+        """(Op::DiffEqLiouvillian{true,true})(du,u,p,t) :130-140 — du = −i[H,u] then the eigenbasis terms in the
+        frame form lv(du, u, gap_ind, s) with gaps from diag(H) (unsorted energies allowed)."""
+        io = _HostIO(u, du)
+        B = io.u.B
+        s = float(np.atleast_1d(p(t))[0])
+        Hm = self.H(p.tf, s)
+        lib, ctx = self.ctx.lib, self.ctx
+        h = C.c_void_p()
+        hbuf = _colmajor_stack([Hm])
+        ctx.check(lib.oqb_dense_create(ctx.h, Hm.shape[0], 1, hbuf.ctypes.data, 0, None, C.byref(h)))
+        one = np.ones((1, 1))
+        ctx.check(lib.oqb_dense_rhs(h, B, _lib.dptr(one), 1, None, 1, io.u.ptr, io.du.ptr))  # :136 (OVERWRITES)
+        ctx.sync()
+        lib.oqb_dense_destroy(h)
+        if not self.diagonalization:
+            if self.opensys:
+                raise NotImplementedError("adiabatic-frame `opensys` terms (ConstDaviesGenerator) are not on the device path")
+            return io.finish()
+        self._prepare_ame(s, np.real(np.diag(Hm)).copy(), None)
+        ctx.check(lib.oqb_ame_eig_acc(self._ame, B, io.u.ptr, io.du.ptr, 0))
+        return io.finish()
+
     def __call__(self, du, u, p, t):
+        if self.adiabatic_frame:
+            return self._rhs_adiabatic_frame(du, u, p, t)
         if self.diagonalization:
             return self._rhs_eig(du, u, p, t)
         io = _HostIO(u, du)
@@ -627,7 +681,7 @@ class DiffEqLiouvillian:
     def _prepare_ame(self, s: float, w=None, v=None):
         """Everything that is shared by the batch for one value of s: eigen-system (host LAPACK, or
         supplied), gap groups, γ/S tables, device tables."""
-        key = (s, None if w is None else id(w))
+        key = (s, None if w is None else (id(w) if v is not None else tuple(np.asarray(w).tolist())))
         if self._ame is not None and self._ame_s == key:
             return
         lib, ctx = self.ctx.lib, self.ctx
@@ -646,8 +700,11 @@ class DiffEqLiouvillian:
         h = C.c_void_p()
         cbuf = _colmajor_stack(coup)
         ctx.check(lib.oqb_ame_create(ctx.h, n, lvl, len(coup), cbuf.ctypes.data, C.byref(h)))
-        vbuf = np.ascontiguousarray(np.asarray(v, dtype=C128).T)  # column-major n×lvl
-        ctx.check(lib.oqb_ame_set_eigen(h, _lib.dptr(w), vbuf.ctypes.data))
+        if v is None:  # adiabatic frame: the state already is in the eigenbasis
+            ctx.check(lib.oqb_ame_set_eigen(h, _lib.dptr(w), None))
+        else:
+            vbuf = np.ascontiguousarray(np.asarray(v, dtype=C128).T)  # column-major n×lvl
+            ctx.check(lib.oqb_ame_set_eigen(h, _lib.dptr(w), vbuf.ctypes.data))
         groups = GapGroups(w, self.digits, self.sigdigits)  # :96
         ndav = 0
         for lv, (c0, c1) in zip(self.opensys_eig, slices):
