@@ -1,29 +1,37 @@
 // K7 for Pauli-structured operators: dψ_b = Σ_t c_bt M_t ψ_b where every non-diagonal term is in XOR
 // form, M[r, r ^ mask_j] = v_j (X-type Pauli strings: transverse fields, XX couplings, …) and the
-// diagonal terms (Z-type strings, −½Σγ_k L_k'L_k) are real vectors.
+// diagonal terms (Z-type strings, −½Σγ_k L_k'L_k) are real vectors or constants.
 //
 // The operator then needs NO per-row storage: columns are implicit (r ^ mask_j), values are per-slot
-// scalars in the kernel parameters, real diagonals are cached in registers.  Memory traffic per
-// trajectory is exactly the algorithmic 32n bytes (ψ in, dψ out).  ψ is staged by cp.async.bulk (UBLKCP)
-// into a 3-deep shared-memory ring guarded by full/empty mbarriers; warps run free of any CTA-wide
-// barrier and may be up to two trajectories apart, so HBM reads, shared-memory gathers and the
-// coalesced dψ stores of neighbouring trajectories overlap.
+// scalars, real diagonals are cached in registers.  Memory traffic per trajectory is exactly the
+// algorithmic 32n bytes (ψ in, dψ out).  ψ and the trajectory's coefficient row are staged by
+// cp.async.bulk (UBLKCP, mbarrier complete_tx) into a 3-deep shared-memory ring guarded by full/empty
+// mbarriers; warps run free of any CTA-wide barrier and may be up to two trajectories apart, so HBM
+// reads, shared-memory gathers and the coalesced dψ stores of neighbouring trajectories overlap.
+// A thread owns the R rows that differ only in the top log2(R) index bits: XOR partners across those
+// bits are its own registers; the remaining partners are gathered two slots at a time (2·8 independent
+// LDS.128 in flight per thread).
+#include <cstring>
+
 #include "sparse_terms.cuh"
 
 namespace oqb {
 
 namespace {
 
-constexpr int kXSlots = 16, kXTerms = 4, kXDiag = 6;
+#ifndef OQB_XOR_SPR
+#define OQB_XOR_SPR 4
+#endif
+constexpr int kSPR = OQB_XOR_SPR;  // gather slots issued back to back per round
+constexpr int kXSlots = 16, kXTerms = 4, kXDiag = 2, kCoefPad = 16;  // coefficient area: 16 complex per stage
 
 struct XorDesc {
-    int n_x, n_diag;
+    int n_x, n_diag, ncoef, coef_shared;
     int x_begin[kXTerms + 1];
-    int x_nrem[kXTerms];  // slots [begin, begin+nrem) need a shared-memory gather,
-    int x_nlane[kXTerms]; // the next nlane are warp-local (mask < 32: shuffles), the rest thread-local (registers)
+    int x_nrem[kXTerms];  // slots [begin, begin+nrem) are shared-memory gathers (count padded to even), rest thread-local
     int x_coef[kXTerms];
-    int mask[kXSlots];
-    double vre[kXSlots], vim[kXSlots];
+    int mask[kXSlots + 4];
+    double vre[kXSlots + 4], vim[kXSlots + 4];
     const double* diag_r[kXDiag];
     int diag_coef[kXDiag];
     double fconst_re, fconst_im;  // constant diagonal contribution (e.g. −½Σγ_k when every L_k'L_k = c_k·I)
@@ -58,58 +66,114 @@ __device__ __forceinline__ void xb_bulk(unsigned dst, const void* src, unsigned 
                  : "memory");
 }
 
-// acc[kk] += v · xo[(c·CH + kk) ^ HK]  — partner rows that live in this thread's own registers
-template <int R, int CH, int HK, bool RV>
-__device__ __forceinline__ void local_acc(const c128 (&xo)[R], int c, double (&ar)[CH], double (&ai)[CH], double vr, double vi) {
-#pragma unroll
-    for (int cc = 0; cc < R / CH; ++cc) {
-        if (cc != c) continue;
-#pragma unroll
-        for (int kk = 0; kk < CH; ++kk) {
-            const c128 v = xo[(cc * CH + kk) ^ HK];
-            if (RV) {
-                ar[kk] = fma(vr, v.x, ar[kk]);
-                ai[kk] = fma(vr, v.y, ai[kk]);
-            } else {
-                ar[kk] = fma(vr, v.x, ar[kk]); ar[kk] = fma(-vi, v.y, ar[kk]);
-                ai[kk] = fma(vr, v.y, ai[kk]); ai[kk] = fma(vi, v.x, ai[kk]);
-            }
-        }
+template <bool RV>
+__device__ __forceinline__ void cacc(double& ar, double& ai, double vr, double vi, const c128 v) {
+    if (RV) {
+        ar = fma(vr, v.x, ar);
+        ai = fma(vr, v.y, ai);
+    } else {
+        ar = fma(vr, v.x, ar); ar = fma(-vi, v.y, ar);
+        ai = fma(vr, v.y, ai); ai = fma(vi, v.x, ai);
     }
 }
-template <int R, int CH, bool RV>
-__device__ __forceinline__ void local_dispatch(int hk, const c128 (&xo)[R], int c, double (&ar)[CH], double (&ai)[CH], double vr,
-                                               double vi) {
-#define OQB_LC(H) case H: if (H < R) local_acc<R, CH, (H < R ? H : 0), RV>(xo, c, ar, ai, vr, vi); break;
-    switch (hk) {
-        OQB_LC(1) OQB_LC(2) OQB_LC(3) OQB_LC(4) OQB_LC(5) OQB_LC(6) OQB_LC(7) OQB_LC(8)
-        OQB_LC(9) OQB_LC(10) OQB_LC(11) OQB_LC(12) OQB_LC(13) OQB_LC(14) OQB_LC(15)
-        default: break;
+
+// acc[kk] += v · xo[(C0 + kk) ^ HK]  — partner rows that live in this thread's own registers
+template <int R, int CH, int C0, int HK, bool RV>
+__device__ __forceinline__ void local_acc(const c128 (&xo)[R], double (&ar)[CH], double (&ai)[CH], double vr, double vi) {
+#pragma unroll
+    for (int kk = 0; kk < CH; ++kk) cacc<RV>(ar[kk], ai[kk], vr, vi, xo[((C0 + kk) ^ HK) % R]);
+}
+template <int R, int CH, int C0, bool RV>
+__device__ __forceinline__ void local_dispatch(int hk, const c128 (&xo)[R], double (&ar)[CH], double (&ai)[CH], double vr, double vi) {
+#define OQB_LC(H) case H: local_acc<R, CH, C0, H, RV>(xo, ar, ai, vr, vi); break;
+    if (hk < 4) {
+        switch (hk) { OQB_LC(1) OQB_LC(2) OQB_LC(3) default: break; }
+    } else if (R > 4 && hk < 8) {
+        switch (hk) { OQB_LC(4) OQB_LC(5) OQB_LC(6) OQB_LC(7) default: break; }
+    } else if (R > 8) {
+        switch (hk) { OQB_LC(8) OQB_LC(9) OQB_LC(10) OQB_LC(11) OQB_LC(12) OQB_LC(13) OQB_LC(14) OQB_LC(15) default: break; }
     }
 #undef OQB_LC
 }
 
-// R rows per thread (r = tid + k·NT), S ring stages, RV: all slot values real, ND: real diagonal terms whose
-// values are cached in registers.  A thread owns the rows that differ only in the top log2(R) index bits, so
-// XOR partners across those bits are its own registers (no shared-memory gather).
+// one chunk of CH rows (rows C0 … C0+CH-1 of this thread)
+template <int R, int NT, int CH, int C0, bool RV, int ND>
+__device__ __forceinline__ void do_chunk(const XorDesc& d, const int* s_mask, const double* s_vre, const double* s_vim,
+                                         const c128* __restrict__ x, const c128* cfs, const c128 (&xo)[R],
+                                         const double (&dreg)[R][ND > 0 ? ND : 1], const c128 (&cdiag)[ND > 0 ? ND : 1],
+                                         c128* __restrict__ out, int tid) {
+    double outr[CH], outi[CH];
+#pragma unroll
+    for (int kk = 0; kk < CH; ++kk) {  // diagonal part: (const + Σ_t c_bt d_t[r]) ψ[r]
+        const int k = C0 + kk;
+        double fr = d.fconst_re, fi = d.fconst_im;
+#pragma unroll
+        for (int t = 0; t < ND; ++t) {
+            fr = fma(cdiag[t].x, dreg[k][t], fr);
+            fi = fma(cdiag[t].y, dreg[k][t], fi);
+        }
+        outr[kk] = fr * xo[k].x - fi * xo[k].y;
+        outi[kk] = fr * xo[k].y + fi * xo[k].x;
+    }
+    for (int e = 0; e < d.n_x; ++e) {
+        double ar[CH], ai[CH];
+#pragma unroll
+        for (int kk = 0; kk < CH; ++kk) ar[kk] = ai[kk] = 0.0;
+        const int jb = d.x_begin[e], nrem = d.x_nrem[e];
+        for (int j = jb; j < jb + nrem; j += kSPR) {  // kSPR slots per round: kSPR·CH independent gathers in flight
+            c128 vv[kSPR][CH];
+#pragma unroll
+            for (int q = 0; q < kSPR; ++q) {
+                const int m = s_mask[j + q];
+#pragma unroll
+                for (int kk = 0; kk < CH; ++kk) vv[q][kk] = x[(tid + (C0 + kk) * NT) ^ m];
+            }
+#pragma unroll
+            for (int q = 0; q < kSPR; ++q) {
+                const double vr = s_vre[j + q], vi = s_vim[j + q];
+#pragma unroll
+                for (int kk = 0; kk < CH; ++kk) cacc<RV>(ar[kk], ai[kk], vr, vi, vv[q][kk]);
+            }
+        }
+        for (int j = jb + nrem; j < d.x_begin[e + 1]; ++j)  // partners in this thread's own registers
+            local_dispatch<R, CH, C0, RV>(s_mask[j] / NT, xo, ar, ai, s_vre[j], s_vim[j]);
+        const c128 cc = cfs[d.x_coef[e]];
+#pragma unroll
+        for (int kk = 0; kk < CH; ++kk) {
+            outr[kk] = fma(cc.x, ar[kk], outr[kk]); outr[kk] = fma(-cc.y, ai[kk], outr[kk]);
+            outi[kk] = fma(cc.x, ai[kk], outi[kk]); outi[kk] = fma(cc.y, ar[kk], outi[kk]);
+        }
+    }
+#pragma unroll
+    for (int kk = 0; kk < CH; ++kk) out[tid + (C0 + kk) * NT] = make_double2(outr[kk], outi[kk]);
+}
+
+// R rows per thread (r = tid + k·NT), S ring stages, RV: all slot values real, ND: real diagonal terms in registers
 template <int R, int NT, int S, bool RV, int ND>
 __global__ void __launch_bounds__(NT, 1)
-    traj_xor_kernel(int nb, XorDesc d, const c128* __restrict__ coef, long long coef_ld, const c128* __restrict__ psi,
-                    c128* __restrict__ dpsi) {
-    constexpr int n = R * NT, NW = NT / 32, CH = R < 8 ? R : 8;
+    traj_xor_kernel(int nb, const __grid_constant__ XorDesc d, const c128* __restrict__ coef, long long coef_ld,
+                    const c128* __restrict__ psi, c128* __restrict__ dpsi) {
+    constexpr int n = R * NT, NW = NT / 32, CH = R < 8 ? R : 8, STAGE = n + kCoefPad;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     c128* ring = reinterpret_cast<c128*>(smem_raw);
     __shared__ __align__(8) unsigned long long bars[2 * S];
+    __shared__ int s_mask[kXSlots + 4];
+    __shared__ double s_vre[kXSlots + 4], s_vim[kXSlots + 4];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned bar_base = s_addr(bars);
-    const unsigned bytes = n * (unsigned)sizeof(c128);
+    const unsigned psi_bytes = n * (unsigned)sizeof(c128);
+    const unsigned coef_bytes = d.coef_shared ? 0u : (unsigned)(d.ncoef * sizeof(c128));
 
     double dreg[R][ND > 0 ? ND : 1];
 #pragma unroll
     for (int k = 0; k < R; ++k)
 #pragma unroll
         for (int t = 0; t < ND; ++t) dreg[k][t] = d.diag_r[t][tid + k * NT];
-
+    if (tid < kXSlots + 4) {
+        s_mask[tid] = d.mask[tid];
+        s_vre[tid] = d.vre[tid];
+        s_vim[tid] = d.vim[tid];
+    }
     if (tid == 0) {
         for (int s = 0; s < S; ++s) {
             xb_init(bar_base + 8 * s, 1);         // full
@@ -117,16 +181,21 @@ __global__ void __launch_bounds__(NT, 1)
         }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
+    if (d.coef_shared && tid < d.ncoef)  // one coefficient row for everybody: park it in every stage
+        for (int s = 0; s < S; ++s) ring[(size_t)s * STAGE + n + tid] = coef[tid];
     __syncthreads();
     const int stride = gridDim.x;
+    auto issue = [&](int slot, long long b) {
+        const unsigned full = bar_base + 8 * slot;
+        xb_expect(full, psi_bytes + coef_bytes);
+        xb_bulk(s_addr(ring + (size_t)slot * STAGE), psi + (size_t)b * n, psi_bytes, full);
+        if (coef_bytes) xb_bulk(s_addr(ring + (size_t)slot * STAGE + n), coef + b * coef_ld, coef_bytes, full);
+    };
     if (tid == 0) {
 #pragma unroll
         for (int i = 0; i < S - 1; ++i) {
             const long long b = blockIdx.x + (long long)i * stride;
-            if (b < nb) {
-                xb_expect(bar_base + 8 * i, bytes);
-                xb_bulk(s_addr(ring + (size_t)i * n), psi + (size_t)b * n, bytes, bar_base + 8 * i);
-            }
+            if (b < nb) issue(i, b);
         }
     }
     int i = 0;
@@ -138,94 +207,24 @@ __global__ void __launch_bounds__(NT, 1)
                 if (lb < nb) {
                     const int ls = li % S;
                     xb_wait(bar_base + 8 * (S + ls), (unsigned)(((li / S) & 1) ^ 1));
-                    xb_expect(bar_base + 8 * ls, bytes);
-                    xb_bulk(s_addr(ring + (size_t)ls * n), psi + (size_t)lb * n, bytes, bar_base + 8 * ls);
+                    issue(ls, lb);
                 }
             }
             __syncwarp();
         }
         const int s = i % S;
-        const c128* __restrict__ cf = coef + b * coef_ld;
+        xb_wait(bar_base + 8 * s, (unsigned)((i / S) & 1));
+        const c128* __restrict__ x = ring + (size_t)s * STAGE;
+        const c128* cfs = x + n;
         c128 cdiag[ND > 0 ? ND : 1];
 #pragma unroll
-        for (int t = 0; t < ND; ++t) cdiag[t] = __ldg(cf + d.diag_coef[t]);
-        xb_wait(bar_base + 8 * s, (unsigned)((i / S) & 1));
-        const c128* __restrict__ x = ring + (size_t)s * n;
+        for (int t = 0; t < ND; ++t) cdiag[t] = cfs[d.diag_coef[t]];
         c128 xo[R];
 #pragma unroll
         for (int k = 0; k < R; ++k) xo[k] = x[tid + k * NT];
         c128* __restrict__ out = dpsi + (size_t)b * n;
-#pragma unroll
-        for (int c = 0; c < R / CH; ++c) {
-            double outr[CH], outi[CH];
-#pragma unroll
-            for (int kk = 0; kk < CH; ++kk) {  // diagonal part: (const + Σ_t c_bt d_t[r]) ψ[r]
-                const int k = c * CH + kk;
-                double fr = d.fconst_re, fi = d.fconst_im;
-#pragma unroll
-                for (int t = 0; t < ND; ++t) {
-                    fr = fma(cdiag[t].x, dreg[k][t], fr);
-                    fi = fma(cdiag[t].y, dreg[k][t], fi);
-                }
-                outr[kk] = fr * xo[k].x - fi * xo[k].y;
-                outi[kk] = fr * xo[k].y + fi * xo[k].x;
-            }
-            for (int e = 0; e < d.n_x; ++e) {
-                double ar[CH], ai[CH];
-#pragma unroll
-                for (int kk = 0; kk < CH; ++kk) ar[kk] = ai[kk] = 0.0;
-                const int jb = d.x_begin[e], nrem = d.x_nrem[e];
-                // remote partners: fully unrolled so that the gathers of slot j+1 are in flight while slot j is consumed
-#pragma unroll
-                for (int j = 0; j < kXSlots; ++j) {
-                    if (j < nrem) {
-                        const int m = d.mask[jb + j];
-                        const double vr = d.vre[jb + j], vi = d.vim[jb + j];
-#pragma unroll
-                        for (int kk = 0; kk < CH; ++kk) {
-                            const c128 v = x[(tid + (c * CH + kk) * NT) ^ m];
-                            if (RV) {
-                                ar[kk] = fma(vr, v.x, ar[kk]);
-                                ai[kk] = fma(vr, v.y, ai[kk]);
-                            } else {
-                                ar[kk] = fma(vr, v.x, ar[kk]); ar[kk] = fma(-vi, v.y, ar[kk]);
-                                ai[kk] = fma(vr, v.y, ai[kk]); ai[kk] = fma(vi, v.x, ai[kk]);
-                            }
-                        }
-                    }
-                }
-                // partners inside the warp (mask < 32): register shuffles instead of shared-memory gathers
-                const int nlane = d.x_nlane[e];
-                for (int j = jb + nrem; j < jb + nrem + nlane; ++j) {
-                    const int m = d.mask[j];
-                    const double vr = d.vre[j], vi = d.vim[j];
-#pragma unroll
-                    for (int kk = 0; kk < CH; ++kk) {
-                        c128 v;
-                        v.x = __shfl_xor_sync(0xffffffffu, xo[c * CH + kk].x, m);
-                        v.y = __shfl_xor_sync(0xffffffffu, xo[c * CH + kk].y, m);
-                        if (RV) {
-                            ar[kk] = fma(vr, v.x, ar[kk]);
-                            ai[kk] = fma(vr, v.y, ai[kk]);
-                        } else {
-                            ar[kk] = fma(vr, v.x, ar[kk]); ar[kk] = fma(-vi, v.y, ar[kk]);
-                            ai[kk] = fma(vr, v.y, ai[kk]); ai[kk] = fma(vi, v.x, ai[kk]);
-                        }
-                    }
-                }
-                // partners that differ only in thread-local index bits: own registers
-                for (int j = jb + nrem + nlane; j < d.x_begin[e + 1]; ++j)
-                    local_dispatch<R, CH, RV>(d.mask[j] / NT, xo, c, ar, ai, d.vre[j], d.vim[j]);
-                const c128 cc = __ldg(cf + d.x_coef[e]);
-#pragma unroll
-                for (int kk = 0; kk < CH; ++kk) {
-                    outr[kk] = fma(cc.x, ar[kk], outr[kk]); outr[kk] = fma(-cc.y, ai[kk], outr[kk]);
-                    outi[kk] = fma(cc.x, ai[kk], outi[kk]); outi[kk] = fma(cc.y, ar[kk], outi[kk]);
-                }
-            }
-#pragma unroll
-            for (int kk = 0; kk < CH; ++kk) out[tid + (c * CH + kk) * NT] = make_double2(outr[kk], outi[kk]);
-        }
+        do_chunk<R, NT, CH, 0, RV, ND>(d, s_mask, s_vre, s_vim, x, cfs, xo, dreg, cdiag, out, tid);
+        if (R > 8) do_chunk<R, NT, CH, (R > 8 ? 8 : 0), RV, ND>(d, s_mask, s_vre, s_vim, x, cfs, xo, dreg, cdiag, out, tid);
         __syncwarp();
         if (lane == 0) xb_arrive(bar_base + 8 * (S + s));
     }
@@ -234,29 +233,32 @@ __global__ void __launch_bounds__(NT, 1)
 template <int R, int NT, int S, bool RV, int ND>
 int launch(Ctx* c, int nb, const XorDesc& d_in, const c128* coef, long long coef_ld, const c128* psi, c128* dpsi) {
     XorDesc d = d_in;
-    for (int e = 0; e < d.n_x; ++e) {  // remote slots first, thread-local ones (mask % NT == 0) last
-        static const bool use_shfl = [] { const char* e = getenv("OQB_XOR_SHFL"); return e && e[0] == '1'; }();  // measured slower than LDS gathers: off by default
-        auto cls = [&](int m) { return (m & (NT - 1)) == 0 ? 2 : ((use_shfl && m > 0 && m < 32) ? 1 : 0); };
-        int w = d.x_begin[e], cnt[3] = {0, 0, 0};
-        for (int pass = 0; pass < 3; ++pass)
-            for (int j = d_in.x_begin[e]; j < d_in.x_begin[e + 1]; ++j)
-                if (cls(d_in.mask[j]) == pass) {
+    int w = 0;
+    for (int e = 0; e < d_in.n_x; ++e) {  // gathers first (padded to an even count), thread-local slots (mask % NT == 0) last
+        d.x_begin[e] = w;
+        int nrem = 0;
+        for (int pass = 0; pass < 2; ++pass) {
+            for (int j = d_in.x_begin[e]; j < d_in.x_begin[e + 1]; ++j) {
+                const bool local = (d_in.mask[j] & (NT - 1)) == 0;
+                if (local == (pass == 1)) {
+                    if (w >= kXSlots + 4) return -1;
                     d.mask[w] = d_in.mask[j]; d.vre[w] = d_in.vre[j]; d.vim[w] = d_in.vim[j];
-                    ++w; ++cnt[pass];
+                    ++w;
+                    if (!local) ++nrem;
                 }
-        d.x_nrem[e] = cnt[0];
-        d.x_nlane[e] = cnt[1];
-    }
-    {   // timing experiments only (results are wrong when set): cap the number of slots per term
-        static const int cap = [] { const char* e = getenv("OQB_XOR_DEBUG_MAXSLOTS"); return e ? atoi(e) : -1; }();
-        if (cap >= 0)
-            for (int e = 0; e < d.n_x; ++e) {
-                if (d.x_nrem[e] > cap) d.x_nrem[e] = cap;
-                if (d.x_nrem[e] + d.x_nlane[e] > cap) d.x_nlane[e] = cap - d.x_nrem[e];
-                if (d.x_begin[e + 1] - d.x_begin[e] > cap) d.x_begin[e + 1] = d.x_begin[e] + cap;
             }
+            while (pass == 0 && (nrem % kSPR)) {  // dummy gathers with zero weight keep the rounds uniform
+                if (w >= kXSlots + 4) return -1;
+                d.mask[w] = 1; d.vre[w] = 0.0; d.vim[w] = 0.0;
+                ++w; ++nrem;
+            }
+        }
+        d.x_nrem[e] = nrem;
     }
-    const size_t smem = (size_t)S * R * NT * sizeof(c128);
+    d.x_begin[d_in.n_x] = w;
+    for (int j = w; j < kXSlots + 4; ++j) { d.mask[j] = 1; d.vre[j] = d.vim[j] = 0.0; }
+    d.coef_shared = coef_ld == 0 ? 1 : 0;
+    const size_t smem = (size_t)S * (R * NT + kCoefPad) * sizeof(c128);
     static bool cfg = false;
     if (!cfg) {
         OQB_CUDA(c, cudaFuncSetAttribute(traj_xor_kernel<R, NT, S, RV, ND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -264,7 +266,7 @@ int launch(Ctx* c, int nb, const XorDesc& d_in, const c128* coef, long long coef
     }
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
-    int per_sm = (int)((224 * 1024) / (smem + 1024));
+    int per_sm = (int)((224 * 1024) / (smem + 2048));
     if (per_sm < 1) per_sm = 1;
     if (per_sm > 2048 / NT) per_sm = 2048 / NT;
     const int grid = nb < sms * per_sm ? nb : sms * per_sm;
@@ -280,19 +282,25 @@ template <bool RV, int ND>
 int by_size(Ctx* c, int n, int nb, const XorDesc& d, const c128* coef, long long coef_ld, const c128* psi, c128* dpsi,
             bool* used) {
     *used = true;
+    int st = 0;
     switch (n) {
         case 4096: {
-            static const int rsel = [] { const char* e = getenv("OQB_XOR_R"); return e ? atoi(e) : 4; }();
-            if (rsel == 16) return launch<16, 256, 3, RV, ND>(c, nb, d, coef, coef_ld, psi, dpsi);
-            if (rsel == 4) return launch<4, 1024, 3, RV, ND>(c, nb, d, coef, coef_ld, psi, dpsi);
-            return launch<8, 512, 3, RV, ND>(c, nb, d, coef, coef_ld, psi, dpsi);
+            static const int rsel = [] { const char* e = getenv("OQB_XOR_R"); return e ? atoi(e) : 16; }();
+            if (rsel == 8) st = launch<8, 512, 3, RV, ND>(c, nb, d, coef, coef_ld, psi, dpsi);
+            else st = launch<16, 256, 3, RV, ND>(c, nb, d, coef, coef_ld, psi, dpsi);
+            break;
         }
-        case 2048: return launch<8, 256, 3, RV, ND>(c, nb, d, coef, coef_ld, psi, dpsi);
-        case 1024: return launch<4, 256, 3, RV, ND>(c, nb, d, coef, coef_ld, psi, dpsi);
-        case 512: return launch<4, 128, 3, RV, ND>(c, nb, d, coef, coef_ld, psi, dpsi);
-        case 256: return launch<2, 128, 3, RV, ND>(c, nb, d, coef, coef_ld, psi, dpsi);
+        case 2048: st = launch<8, 256, 3, RV, ND>(c, nb, d, coef, coef_ld, psi, dpsi); break;
+        case 1024: st = launch<4, 256, 3, RV, ND>(c, nb, d, coef, coef_ld, psi, dpsi); break;
+        case 512: st = launch<4, 128, 3, RV, ND>(c, nb, d, coef, coef_ld, psi, dpsi); break;
+        case 256: st = launch<2, 128, 3, RV, ND>(c, nb, d, coef, coef_ld, psi, dpsi); break;
         default: *used = false; return 0;
     }
+    if (st < 0) {  // slot table overflow after padding: let the caller fall back
+        *used = false;
+        return 0;
+    }
+    return st;
 }
 
 }  // namespace
@@ -302,27 +310,28 @@ int traj_matvec_xor(Ctx* c, int n, int nb, const std::vector<const TermDev*>& ts
     *used = false;
     static const int mode = [] { const char* e = getenv("OQB_TRAJ"); return e ? (int)e[0] : 0; }();
     if (mode == 'g' || mode == 'f') return 0;  // "generic" / "fast": skip this path (A/B measurements)
+    if ((int)ts.size() > kCoefPad) return 0;
     XorDesc d;
-    d.n_x = d.n_diag = 0;
-    d.fconst_re = d.fconst_im = 0.0;
-    d.x_begin[0] = 0;
+    memset(&d, 0, sizeof(d));
+    d.ncoef = (int)ts.size();
     int slots = 0;
     bool all_real = true;
     for (size_t t = 0; t < ts.size(); ++t) {
         const TermDev* td = ts[t];
         if (td->is_diag) {
-            if (td->diag_const) {  // c_bt must be shared for a constant term to fold into a scalar
-                if (coef_ld != 0 && !td->const_coef_one) return 0;
+            if (td->diag_const) {  // c_bt must be 1 for every member for a constant term to fold into a scalar
+                if (!td->const_coef_one) return 0;
                 d.fconst_re += td->const_val.x;
                 d.fconst_im += td->const_val.y;
                 continue;
             }
-            if (!(td->is_real && td->rvals) || d.n_diag >= 2) return 0;
+            if (!(td->is_real && td->rvals) || d.n_diag >= kXDiag) return 0;
             d.diag_r[d.n_diag] = td->rvals;
             d.diag_coef[d.n_diag] = (int)t;
             d.n_diag++;
         } else {
             if (!td->xor_form || d.n_x >= kXTerms || slots + (int)td->xor_masks.size() > kXSlots) return 0;
+            d.x_begin[d.n_x] = slots;
             for (size_t j = 0; j < td->xor_masks.size(); ++j) {
                 d.mask[slots] = td->xor_masks[j];
                 d.vre[slots] = td->xor_vals[j].x;
@@ -335,8 +344,6 @@ int traj_matvec_xor(Ctx* c, int n, int nb, const std::vector<const TermDev*>& ts
             d.x_begin[d.n_x] = slots;
         }
     }
-    for (int j = slots; j < kXSlots; ++j) { d.mask[j] = 0; d.vre[j] = d.vim[j] = 0.0; }
-    for (int t = d.n_diag; t < kXDiag; ++t) { d.diag_r[t] = nullptr; d.diag_coef[t] = 0; }
     if (d.n_diag == 0) return all_real ? by_size<true, 0>(c, n, nb, d, d_coef, coef_ld, psi, dpsi, used)
                                        : by_size<false, 0>(c, n, nb, d, d_coef, coef_ld, psi, dpsi, used);
     if (d.n_diag == 1) return all_real ? by_size<true, 1>(c, n, nb, d, d_coef, coef_ld, psi, dpsi, used)
