@@ -270,10 +270,21 @@ def main():
 
     achieved = zg_fl.value / (zg_ms.value * 1e-3) / 1e12 if zg_ms.value > 0 else None
     peak = max(dgemm_tf, dmma_tf)
-    roofline = {"bound": "tensor", "kernel": "zgemm_tma_kernel (FP64 DMMA.8x8x4, TMA-staged; 4 launches of 64 products per step)",
+    mode = C.c_int()
+    ctx.check(lib.oqb_get_zgemm_mode(ctx.h, C.byref(mode)))
+    exec_ratio = 0.75 if mode.value == 1 else 1.0  # 3M executes 6·M·N·K of the 8·M·N·K algorithmic flops
+    roofline = {"bound": "tensor",
+                "kernel": "zgemm_tma_kernel (FP64 DMMA.8x8x4, TMA-staged, %s complex product; 4 launches of 64 products per step)"
+                          % ("3-multiplication" if mode.value == 1 else "4-multiplication"),
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if achieved else None,
-                "traffic": 2.163e9,
-                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one 64-product launch, ncu --set full, profiles/r1_zgemm_tma_ncu.md "
+                "executed_over_algorithmic_flops": exec_ratio,
+                "frac_executed": achieved * exec_ratio / peak if achieved else None,
+                "frac_note": "achieved counts ALGORITHMIC flops (8·M·N·K per complex product, SURVEY 8(d)); the 3-multiplication "
+                             "kernel issues only 6·M·N·K on the tensor pipe, so frac can exceed 1 — frac_executed is the pipe's "
+                             "utilisation",
+                "traffic": 2.138e9 if mode.value == 1 else 2.163e9,
+                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one 64-product launch, ncu --set full, "
+                                  + ("profiles/r1_zgemm_3m_ncu.md " if mode.value == 1 else "profiles/r1_zgemm_tma_ncu.md ") +
                                   "(algorithmic: 1 GiB read + 1 GiB written + 16 MiB V)",
                 "peak_source": "measured in this run: max(cuBLAS DGEMM 8192^3 best-of-6, DMMA issue probe); MEASURED_PEAKS.json has no FP64 figure",
                 "cublas_dgemm_tflops": dgemm_tf, "cublas_zgemm_4096_tflops": zgemm_tf,

@@ -51,6 +51,12 @@ int oqb_sync(oqb_ctx* ctx);
 int oqb_set_stream(oqb_ctx* ctx, void* cuda_stream); /* borrow an existing cudaStream_t        */
 int oqb_get_stream(oqb_ctx* ctx, void** cuda_stream);
 int oqb_launch_count(const oqb_ctx* ctx, uint64_t* n); /* kernels launched through this ctx    */
+/* Complex product used by the tensor-pipe ZGEMM behind every dense path: 1 (default) = 3-multiplication
+ * form (3 real DMMA products per complex product, ≈1.2× faster, same ≈1e-15 normwise error), 0 = the classic
+ * 4-multiplication form whose rounding matches BLAS zgemm element by element (src/opensys/lindblad.jl:99).
+ * Also settable at context creation through the environment variable OQB_ZGEMM_3M=0/1. */
+int oqb_set_zgemm_mode(oqb_ctx* ctx, int mode);
+int oqb_get_zgemm_mode(const oqb_ctx* ctx, int* mode);
 
 int oqb_malloc(oqb_ctx* ctx, size_t nbytes, void** d_ptr);
 int oqb_free(oqb_ctx* ctx, void* d_ptr);

@@ -25,6 +25,8 @@ SIGNATURES = {
     "oqb_set_stream": [c_void_p, c_void_p],
     "oqb_get_stream": [c_void_p, C.POINTER(c_void_p)],
     "oqb_launch_count": [c_void_p, C.POINTER(C.c_uint64)],
+    "oqb_set_zgemm_mode": [c_void_p, c_int],
+    "oqb_get_zgemm_mode": [c_void_p, C.POINTER(c_int)],
     "oqb_malloc": [c_void_p, c_size_t, C.POINTER(c_void_p)],
     "oqb_free": [c_void_p, c_void_p],
     "oqb_malloc_host": [c_void_p, c_size_t, C.POINTER(c_void_p)],

@@ -20,6 +20,8 @@ struct Ctx {
     cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     std::string err;
     uint64_t launches = 0;
+    // complex product of the TMA ZGEMM: 1 = 3-multiplication (default), 0 = classic 4-multiplication
+    int zgemm_3m = 1;
     // grow-only device workspace
     void* ws = nullptr;
     size_t ws_bytes = 0;

@@ -3,6 +3,8 @@
 #include <cstring>
 
 #include "../../include/oqb.h"
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace oqb {
@@ -103,6 +105,7 @@ int oqb_create(int device, oqb_ctx** out) {
     c->device = device;
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return OQB_ECUDA; }
     c->own_stream = true;
+    if (const char* e = getenv("OQB_ZGEMM_3M")) c->zgemm_3m = atoi(e) != 0;
     for (int i = 0; i < 2; ++i) cudaStreamCreateWithFlags(&c->copy_stream[i], cudaStreamNonBlocking);
     for (int i = 0; i < 8; ++i) cudaEventCreateWithFlags(&c->ev[i], cudaEventDisableTiming);
     *out = c;
@@ -140,6 +143,12 @@ int oqb_set_stream(oqb_ctx* c, void* s) {
 }
 int oqb_get_stream(oqb_ctx* c, void** s) { *s = (void*)c->stream; return 0; }
 int oqb_launch_count(const oqb_ctx* c, uint64_t* n) { *n = c->launches; return 0; }
+int oqb_set_zgemm_mode(oqb_ctx* c, int mode) {
+    if (mode != 0 && mode != 1) return set_error(c, OQB_EINVAL, "oqb_set_zgemm_mode: mode must be 0 (4M) or 1 (3M)");
+    c->zgemm_3m = mode;
+    return 0;
+}
+int oqb_get_zgemm_mode(const oqb_ctx* c, int* mode) { *mode = c->zgemm_3m; return 0; }
 
 int oqb_malloc(oqb_ctx* c, size_t nbytes, void** d) {
     cudaError_t e = cudaMalloc(d, nbytes ? nbytes : 16);

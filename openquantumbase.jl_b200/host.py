@@ -51,6 +51,10 @@ class Context:
     def sync(self):
         self.check(self.lib.oqb_sync(self.h))
 
+    def set_zgemm_mode(self, mode: int):
+        """1 = 3-multiplication complex product (default), 0 = 4-multiplication (BLAS rounding order)."""
+        self.check(self.lib.oqb_set_zgemm_mode(self.h, int(mode)))
+
     def launch_count(self) -> int:
         n = C.c_uint64()
         self.lib.oqb_launch_count(self.h, C.byref(n))

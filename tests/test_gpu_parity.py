@@ -52,10 +52,12 @@ def rand_rho(rng, B_, n):
 @pytest.mark.parametrize("M,N,K,batch", [(2, 2, 2, 1), (4, 3, 5, 3), (16, 16, 16, 2), (33, 65, 17, 2),
                                          (64, 64, 64, 3), (128, 64, 72, 2), (130, 70, 9, 2), (256, 256, 256, 2)])
 @pytest.mark.parametrize("opA,opB", [(0, 0), (2, 0), (0, 2), (2, 2), (1, 1)])
-def test_zgemm(Q, M, N, K, batch, opA, opB):
+@pytest.mark.parametrize("mode", [1, 0])  # 3-multiplication (default) and 4-multiplication complex product
+def test_zgemm(Q, M, N, K, batch, opA, opB, mode):
     import ctypes as C
     rng = np.random.default_rng(M * 1000 + N * 10 + K + opA * 7 + opB)
     ctx = Q.get_context()
+    ctx.set_zgemm_mode(mode)
     a_shape = (K, M) if opA else (M, K)
     b_shape = (N, K) if opB else (K, N)
     Ah = rand_c(rng, batch, *a_shape)
@@ -70,7 +72,33 @@ def test_zgemm(Q, M, N, K, batch, opA, opB):
     dp = lambda x: x.ctypes.data_as(C.POINTER(C.c_double))
     ctx.check(ctx.lib.oqb_zgemm_batched(ctx.h, opA, opB, M, N, K, dp(al), Ad.ptr, a_shape[0], a_shape[0] * a_shape[1],
                                         Bd.ptr, b_shape[0], 0, dp(be), Cd.ptr, M, M * N, batch))
+    ctx.set_zgemm_mode(1)
     assert relerr(Cd.to_host(), ref) < 1e-13
+
+
+def test_zgemm_3m_cancellation(Q):
+    """3M forms im = T3 − T1 − T2: purely real operands must give an exactly zero imaginary part, and a
+    product whose imaginary part cancels (A·A' is Hermitian) must stay accurate relative to ‖C‖."""
+    import ctypes as C
+    rng = np.random.default_rng(5)
+    ctx = Q.get_context()
+    n = 96
+    Ar = rng.standard_normal((1, n, n)) + 0j
+    Ac = rand_c(rng, 1, n, n)
+    al = np.array([1.0, 0.0]); be = np.array([0.0, 0.0])
+    dp = lambda x: x.ctypes.data_as(C.POINTER(C.c_double))
+    for A, opB in ((Ar, 0), (Ac, 2)):
+        Ad = Q.DeviceBatch.from_host(A)
+        Cd = Q.DeviceBatch.from_host(np.zeros_like(A))
+        ctx.check(ctx.lib.oqb_zgemm_batched(ctx.h, 0, opB, n, n, n, dp(al), Ad.ptr, n, n * n, Ad.ptr, n, n * n, dp(be),
+                                            Cd.ptr, n, n * n, 1))
+        got = Cd.to_host()[0]
+        ref = A[0] @ (A[0].conj().T if opB else A[0])
+        assert relerr(got, ref) < 1e-14
+        if opB == 0:
+            assert np.all(got.imag == 0.0)
+        else:
+            assert np.abs(np.diag(got).imag).max() < 1e-13 * np.abs(ref).max()
 
 
 # ---------------------------------------------------------------------------------------------
