@@ -38,6 +38,7 @@ typedef struct oqb_ctx oqb_ctx;       /* stream + workspace                     
 typedef struct oqb_dense oqb_dense;   /* DenseHamiltonian terms + Lindblad operators          */
 typedef struct oqb_sparse oqb_sparse; /* SparseHamiltonian terms + sparse Lindblad operators  */
 typedef struct oqb_ame oqb_ame;       /* eigenbasis (Davies / one-sided AME) Liouvillian      */
+typedef struct oqb_lambda oqb_lambda; /* batched builder of the Redfield kernel matrices Λ(t) */
 
 enum { OQB_OP_N = 0, OQB_OP_T = 1, OQB_OP_C = 2 };
 enum { OQB_OK = 0, OQB_EINVAL = 1, OQB_ECUDA = 2, OQB_ENOMEM = 3 };
@@ -115,6 +116,37 @@ int oqb_redfield_apply_acc(oqb_ctx* ctx, int n, int K, const void* d_S, int S_sh
  *   — update_vectorized_cache!(cache, R::RedfieldLiouvillian, p, t) src/opensys/redfield.jl:97-102 */
 int oqb_redfield_vectorized_acc(oqb_ctx* ctx, int n, int K, const void* d_S, int S_shared,
                                 const void* d_Lambda, int nb, void* d_cache);
+
+/* ------------------------------------------------------- Redfield Λ(t) builder */
+/* Replaces the `quadgk!` call of (R::RedfieldLiouvillian)(du,u,p,t), src/opensys/redfield.jl:46-64 (same call
+ * in update_vectorized_cache!, :76-96), for many integrals at once:
+ *     Λ_ij(t) = ∫_{max(0,t−Ta)}^{t} C_ij(t,x) U(t)U(x)† S_j(p(x)) U(x)U(t)† dx.
+ * The adaptive G7K15 control flow (QuadGK: per-integral max-heap, bisect the worst segment) and the scalar
+ * closures C_ij(t,x) stay in the host language; each refinement round is one oqb_lambda_eval call.
+ * h_S: K coupling matrices S_j (n×n, unit-scaled, src/coupling/coupling.jl:42,66); a scalar time dependence
+ * f_j(p(x)) is folded into the node weights by the host. */
+int oqb_lambda_create(oqb_ctx* ctx, int n, int K, const void* h_S, oqb_lambda** out);
+int oqb_lambda_destroy(oqb_lambda* lam);
+/* The closed-system unitaries `R.unitary` (src/opensys/redfield.jl:16, :38) of nb schedules, each sampled on G
+ * uniformly spaced points starting at 0: d_Ugrid = nb×G n×n matrices in device memory (borrowed, must stay
+ * valid); U(x) is the piecewise-linear interpolant (1−θ)U_g + θU_{g+1}. */
+int oqb_lambda_set_unitary(oqb_lambda* lam, int nb, int G, const void* d_Ugrid);
+/* storage for the integrals of the live (leaf) segments, n×n each; grows preserving content */
+int oqb_lambda_reserve_slots(oqb_lambda* lam, int64_t nslots);
+/* One Gauss–Kronrod(7,15) evaluation of nseg segments.  For segment s: h_member[s] (which schedule),
+ * h_coupling[s] (which S_j), 16 interpolation points h_gi/h_theta[s][0..14] = the 15 nodes x_i and [15] = the end
+ * time t (grid index g and fraction θ ∈ [0,1)), complex node weights h_ck[s][i] = wk_i·h·C(t,x_i) and
+ * h_cd[s][i] = (wk_i − wg_i)·h·C(t,x_i) as (re,im) pairs (h = half width; wg_i = 0 at the Kronrod-only nodes),
+ * h_slot[s] the slot that receives the segment integral.  h_E[s] returns ‖Kronrod − Gauss‖_F (QuadGK's segment
+ * error).  Synchronises. */
+int oqb_lambda_eval(oqb_lambda* lam, int nseg, const int32_t* h_member, const int32_t* h_coupling,
+                    const int32_t* h_gi, const double* h_theta, const double* h_ck, const double* h_cd,
+                    const int64_t* h_slot, double* h_E);
+/* Λ_q = Σ_k slot[h_idx[k]], k ∈ [h_ptr[q], h_ptr[q+1]) summed in that order (QuadGK's final re-summation over
+ * its heap) into d_Lambda[q] (n×n, device); h_norm[q] = ‖Λ_q‖_F for the rtol test (NULL ⇒ not returned, no
+ * synchronisation). */
+int oqb_lambda_total(oqb_lambda* lam, int nint, const int64_t* h_ptr, const int64_t* h_idx, void* d_Lambda,
+                     double* h_norm);
 
 /* ------------------------------------------ eigenbasis Liouvillian: DiffEqLiouvillian{true,·} */
 /* n: Hilbert dimension; lvl: kept levels (src/opensys/diffeq_liouvillian.jl:45-54);

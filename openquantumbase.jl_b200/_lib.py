@@ -45,6 +45,12 @@ SIGNATURES = {
     "oqb_lindblad_acc": [c_void_p, c_int, c_dp, c_int, c_void_p, c_void_p],
     "oqb_redfield_apply_acc": [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p],
     "oqb_redfield_vectorized_acc": [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p],
+    "oqb_lambda_create": [c_void_p, c_int, c_int, c_void_p, C.POINTER(c_void_p)],
+    "oqb_lambda_destroy": [c_void_p],
+    "oqb_lambda_set_unitary": [c_void_p, c_int, c_int, c_void_p],
+    "oqb_lambda_reserve_slots": [c_void_p, c_i64],
+    "oqb_lambda_eval": [c_void_p, c_int, c_i32p, c_i32p, c_i32p, c_dp, c_dp, c_dp, c_i64p, c_dp],
+    "oqb_lambda_total": [c_void_p, c_int, c_i64p, c_i64p, c_void_p, c_dp],
     "oqb_ame_create": [c_void_p, c_int, c_int, c_int, c_void_p, C.POINTER(c_void_p)],
     "oqb_ame_destroy": [c_void_p],
     "oqb_ame_set_eigen": [c_void_p, c_dp, c_void_p],

@@ -98,7 +98,7 @@ __device__ __forceinline__ double flipt(double x, unsigned mask) {
 // accumulator set — the warp tile shrinks to 32x16 complex (96 accumulator registers).
 template <int BM_, int BN_, int STAGES_, bool TA_, bool TB_, bool M3_ = false, int MINB_ = (BM_ == 64 ? 2 : 1)>
 struct TCfg {
-    static constexpr int BM = BM_, BN = BN_, BK = 8, STAGES = STAGES_;
+    static constexpr int BM = BM_, BN = BN_, STAGES = STAGES_;  // k depth of a stage: 8 complex = 128 bytes
     static constexpr bool TA = TA_, TB = TB_, M3 = M3_;
     static constexpr int WTN = M3 ? 16 : 32, NJ = WTN / 8, MINB = MINB_;
     static constexpr int WARPS_M = BM / 32, WARPS_N = BN / WTN, NCONS = WARPS_M * WARPS_N;

@@ -120,3 +120,22 @@ def test_host_quadrature_matches_oracle_mirror():
     a = quadgk_matrix(f, 0.0, 5.0, 1e-6, 1e-8)
     b, _ = O.quadgk(f, 0.0, 5.0, 1e-6, 1e-8)
     assert np.linalg.norm(a - b) < 1e-14
+
+
+def test_gk15_node_tables_and_sampled_unitary():
+    """redfield_device's 15-node tables reproduce the oracle's evalrule on a scalar integrand, and the sampled
+    unitary closure interpolates linearly (QuadGK.kronrod(7))."""
+    from oqb_b200.redfield_device import NODE_WG, NODE_WK, NODE_XI, SampledUnitary
+    assert abs(NODE_WK.sum() - 2.0) < 1e-15 and abs(NODE_WG.sum() - 2.0) < 1e-15
+    assert np.count_nonzero(NODE_WG) == 7 and np.all(np.diff(NODE_XI) > 0)
+    f = lambda x: np.exp(-x) * np.cos(3 * x)
+    a, b = 0.3, 1.7
+    h = 0.5 * (b - a)
+    x = a + (1 + NODE_XI) * h
+    Ik, Ig = (NODE_WK * f(x)).sum() * h, (NODE_WG * f(x)).sum() * h
+    I_or, E_or = O._evalrule(f, a, b)
+    assert abs(Ik - I_or) < 1e-15 and abs(abs(Ik - Ig) - E_or) < 1e-15
+    U = SampledUnitary(np.stack([np.eye(2) * g for g in range(5)]), 0.5)
+    assert np.allclose(U(0.75), 1.5 * np.eye(2)) and np.allclose(U(2.0), 4 * np.eye(2))
+    g, th = SampledUnitary.locate(np.array([0.0, 0.74, 2.0, 2.5]), 0.5, 5)
+    assert list(g) == [0, 1, 4, 4] and th[2] == 0.0 and th[3] == 0.0
