@@ -227,6 +227,26 @@ int oqb_traj_jump(oqb_sparse* sp, int nb, const double* h_gamma, int gamma_share
                   const double* d_uniform, const uint8_t* d_mask, int32_t* d_choice, double* d_prob,
                   int apply);
 
+/* --------------------------------------------- on-device trajectory stepping */
+/* One xoshiro256++ stream per trajectory (the algorithm of Julia's default RNG; Float64 = (x >>> 11)·2⁻⁵³):
+ * d_state is nb×4 uint64 in device memory, state-in/state-out.  oqb_traj_rng_init fills it from one seed
+ * (splitmix64 of seed ^ b·0xD1342543DE82EF95); a caller that wants Julia's own streams uploads the task-local
+ * RNG words with oqb_upload instead.  oqb_traj_rng_uniform draws one Float64 per stream (e.g. the initial
+ * jump thresholds). */
+int oqb_traj_rng_init(oqb_sparse* sp, int nb, uint64_t seed, uint64_t* d_state);
+int oqb_traj_rng_uniform(oqb_sparse* sp, int nb, uint64_t* d_state, double* d_out);
+/* nsteps fixed RK4 steps of dψ/dt = (−iH(s) − ½Σ_k γ_k L_k'L_k)ψ (the `cache*u` of the external solver with the
+ * cache of src/opensys/diffeq_liouvillian.jl:78-83) with the jump loop of its callback after every step:
+ * where ‖ψ_b‖² ≤ d_threshold[b], draw u (choice) and the next threshold from the member's stream, pick
+ * k = lindblad_jump/lind_jump (src/opensys/trajectory_jump.jl:2-12,71-74; prob_k = γ_k‖L_kψ‖², inverse-CDF scan with u)
+ * and set ψ ← L_kψ/‖L_kψ‖.  Coefficients: the host closures evaluated at the 2·nsteps+1 stage times t0 + j·dt/2:
+ * h_coefH[j][rows][nterms], h_gamma[j][rows][K] (rows = 1 when shared, else nb); the jump uses γ at the step's end.
+ * d_njumps[b] is incremented per jump; d_log (may be NULL) records the first max_log events of each member as
+ * (step0 + step index, k) int32 pairs.  Nothing synchronises; ψ stays in HBM throughout. */
+int oqb_traj_evolve(oqb_sparse* sp, int nb, int nsteps, double dt, const double* h_coefH, int coef_shared,
+                    const double* h_gamma, int gamma_shared, void* d_psi, uint64_t* d_rng, double* d_threshold,
+                    int32_t* d_njumps, int32_t* d_log, int max_log, int step0);
+
 /* ------------------------------------------------------------------------- observables ----- */
 /* out[b][o] = tr(O_o ρ[b]) (is_vector==0, state n×n) or ψ[b]'O_oψ[b] (is_vector!=0); complex
  * (re,im) pairs; d_obs: nobs dense n×n matrices.  Partial sums for the NCCL ensemble average. */

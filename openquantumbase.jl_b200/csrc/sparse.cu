@@ -662,6 +662,13 @@ int traj_matvec_impl(oqb_sparse* sp, int nb, const double* coefH, int coef_share
 
 }  // namespace
 
+// accessors for traj_evolve.cu (the struct layout stays private to this file)
+oqb_ctx* oqb_sparse_ctx(oqb_sparse* sp) { return sp->ctx; }
+int oqb_sparse_dims(oqb_sparse* sp, int* n, int* nterms, int* K) {
+    *n = sp->n; *nterms = sp->nterms; *K = sp->K;
+    return 0;
+}
+
 extern "C" {
 
 int oqb_sparse_destroy(oqb_sparse* sp) {

@@ -953,6 +953,49 @@ class TrajectoryEnsemble:
         return choice, prob
 
 
+class TrajectoryStepper:
+    """On-device fixed-step RK4 + jump loop for a TrajectoryEnsemble (oqb_traj_evolve): the role the
+    external solver and its jump callback play around `update_cache!` and `lindblad_jump`.  RNG: one
+    xoshiro256++ stream per trajectory, kept in device memory."""
+
+    def __init__(self, ens: TrajectoryEnsemble, B: int, seed: int = 0, max_log: int = 0, rng_state: Optional[np.ndarray] = None):
+        import torch
+        self.ens, self.ctx, self.B, self.max_log = ens, ens.ctx, B, max_log
+        dev = f"cuda:{self.ctx.device}"
+        self.rng = torch.zeros((B, 4), dtype=torch.int64, device=dev)  # uint64 words
+        if rng_state is not None:
+            self.rng.copy_(torch.from_numpy(np.ascontiguousarray(rng_state, dtype=np.uint64).view(np.int64).reshape(B, 4)))
+        else:
+            self.ctx.check(self.ctx.lib.oqb_traj_rng_init(ens.sp, B, C.c_uint64(seed), C.c_void_p(self.rng.data_ptr())))
+        self.thr = torch.zeros(B, dtype=torch.float64, device=dev)
+        self.ctx.check(self.ctx.lib.oqb_traj_rng_uniform(ens.sp, B, C.c_void_p(self.rng.data_ptr()), C.c_void_p(self.thr.data_ptr())))
+        self.njumps = torch.zeros(B, dtype=torch.int32, device=dev)
+        self.log = torch.full((B, max(max_log, 1), 2), -1, dtype=torch.int32, device=dev) if max_log > 0 else None
+        self.step = 0
+
+    def evolve(self, psi: DeviceBatch, p, t0: float, dt: float, nsteps: int):
+        """nsteps RK4 steps from physical time t0; p: ODEParams (or a list of B of them for per-member schedules)."""
+        ens, B = self.ens, self.B
+        ts = t0 + 0.5 * dt * np.arange(2 * nsteps + 1)
+        per_member = isinstance(p, (list, tuple))
+        if per_member:
+            sv = np.array([[pb(t) for pb in p] for t in ts])  # (2n+1, B)
+        else:
+            sv = np.array([[p(t)] for t in ts])  # (2n+1, 1)
+        rows = sv.shape[1]
+        cf = np.ascontiguousarray(np.stack([_coef(ens.H.f, sv[j]) for j in range(len(ts))]).reshape(len(ts), rows, -1))
+        g = None
+        if ens.lind:
+            g = np.ascontiguousarray(np.stack([ens.lind.gammas(sv[j]) for j in range(len(ts))]).reshape(len(ts), rows, -1))
+        shared = int(rows == 1)
+        vp = lambda x: None if x is None else C.c_void_p(x.data_ptr())
+        self.ctx.check(self.ctx.lib.oqb_traj_evolve(ens.sp, B, nsteps, C.c_double(dt), _lib.dptr(cf), shared, _lib.dptr(g), shared,
+                                                    psi.ptr, vp(self.rng), vp(self.thr), vp(self.njumps), vp(self.log),
+                                                    self.max_log, self.step))
+        self.step += nsteps
+        return psi
+
+
 def expect(obs: Sequence[np.ndarray], state: DeviceBatch):
     """⟨O⟩ per member: tr(Oρ_b) for matrices, ψ_b'Oψ_b for vectors → complex tensor (B, nobs) on
     the device (the per-GPU partial result that is then reduced with NCCL)."""

@@ -357,6 +357,87 @@ def lind_jump(lind: LindbladLiouvillian, u, p, s, r: float):
 
 
 # --------------------------------------------------------------------------------------
+# trajectory stepping (the external solver's role) — oracle of oqb_traj_evolve
+# --------------------------------------------------------------------------------------
+_M64 = (1 << 64) - 1
+
+
+class Xoshiro256pp:
+    """xoshiro256++ (Blackman–Vigna; the algorithm of Julia ≥1.7's default RNG [external — parity unpinned]);
+    rand(Float64) = (next() >>> 11)·2⁻⁵³.  State = 4 uint64 words."""
+
+    def __init__(self, state):
+        self.s = [int(x) & _M64 for x in state]
+
+    @staticmethod
+    def _rotl(x, k):
+        return ((x << k) | (x >> (64 - k))) & _M64
+
+    @classmethod
+    def from_seed(cls, seed: int, b: int):
+        """The seeding of oqb_traj_rng_init: splitmix64 of seed ^ b·0xD1342543DE82EF95."""
+        x = (seed ^ (b * 0xD1342543DE82EF95)) & _M64
+        st = []
+        for _ in range(4):
+            x = (x + 0x9E3779B97F4A7C15) & _M64
+            z = x
+            z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & _M64
+            z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & _M64
+            st.append(z ^ (z >> 31))
+        return cls(st)
+
+    def next_u64(self) -> int:
+        s = self.s
+        result = (self._rotl((s[0] + s[3]) & _M64, 23) + s[0]) & _M64
+        t = (s[1] << 17) & _M64
+        s[2] ^= s[0]
+        s[3] ^= s[1]
+        s[1] ^= s[2]
+        s[0] ^= s[3]
+        s[2] ^= t
+        s[3] = self._rotl(s[3], 45)
+        return result
+
+    def rand(self) -> float:
+        return float(self.next_u64() >> 11) * 2.0 ** -53
+
+
+def traj_evolve_rk4(cache_fn, jump_ops_fn, gamma_fn, psi, rng: Xoshiro256pp, thr: float, t0: float, dt: float,
+                    nsteps: int, step0: int = 0):
+    """One trajectory: nsteps classical RK4 steps of dψ/dt = cache(t)ψ (cache as update_cache! builds it,
+    src/opensys/diffeq_liouvillian.jl:78-83), after each step the callback of the external solver: if ‖ψ‖² ≤ thr →
+    u = rand() picks L_k by lind_jump's inverse-CDF scan (src/opensys/trajectory_jump.jl:2-12) with γ at the step's
+    end, ψ ← L_kψ/‖L_kψ‖, thr = rand().  Returns (ψ, thr, log[(step, k)])."""
+    psi = np.array(psi, dtype=C128)
+    log = []
+    for i in range(nsteps):
+        ta, tm, tb = t0 + (2 * i) * (dt / 2), t0 + (2 * i + 1) * (dt / 2), t0 + (2 * i + 2) * (dt / 2)
+        A0, A1, A2 = cache_fn(ta), cache_fn(tm), cache_fn(tb)
+        k = A0 @ psi
+        acc = psi + (dt / 6.0) * k
+        tmp = psi + (0.5 * dt) * k
+        k = A1 @ tmp
+        acc = acc + (dt / 3.0) * k
+        tmp = psi + (0.5 * dt) * k
+        k = A1 @ tmp
+        acc = acc + (dt / 3.0) * k
+        tmp = psi + dt * k
+        k = A2 @ tmp
+        psi = acc + (dt / 6.0) * k
+        n2 = float(np.sum(psi.real ** 2 + psi.imag ** 2))
+        if n2 <= thr:
+            u = rng.rand()
+            thr = rng.rand()
+            Ls, g = jump_ops_fn(tb), gamma_fn(tb)
+            prob = [g[j] * float(np.linalg.norm(Ls[j] @ psi) ** 2) for j in range(len(Ls))]
+            kk = sample_weights(prob, u)
+            phi = Ls[kk] @ psi
+            psi = phi / np.linalg.norm(phi)
+            log.append((step0 + i, kk))
+    return psi, thr, log
+
+
+# --------------------------------------------------------------------------------------
 # Davies / AME
 # --------------------------------------------------------------------------------------
 def _sparse_pick(c, a, b, l):
