@@ -187,6 +187,19 @@ int oqb_ame_eig_acc(oqb_ame* ame, int nb, const void* d_rho_eig, void* d_du_eig,
  *     update_cache!(cache, D::DaviesGenerator, gap_idx, v, s) src/opensys/davies.jl:76-99. */
 int oqb_ame_update_cache(oqb_ame* ame, void* d_cache);
 
+/* ame_jump for a DaviesGenerator on a batch of state vectors — lindblad_jump(Op::DiffEqLiouvillian{true,false}, u, p, t)
+ * src/opensys/trajectory_jump.jl:64-69 with ame_jump :14-51.  The probability slots are listed in the reference's
+ * order: for every unique positive gap (ascending), for every coupling i: L₊ = sparse(a, b, σ_i[a,b]) then
+ * L₋ = sparse(b, a, σ_i[b,a]); then, for every coupling, the zero-gap group.  Slot s owns the terms
+ * [h_slot_ptr[s], h_slot_ptr[s+1]) of h_term = (coupling, row, col) 0-based int32 triples sorted by (row, col),
+ * and h_rate[s] = γ(±ω) / γ(0).  prob[b][s] = rate_s·‖L_s v'ψ_b‖²; choice[b] by StatsBase's inverse-CDF scan with
+ * d_uniform[b] (−1 where d_mask[b] == 0); apply != 0 sets ψ_b ← v L_s v'ψ_b / ‖·‖ (the √γ factor of :47 cancels).
+ * d_psi: n×nb; d_prob (may be NULL): nb×nslots.  The tables depend on (w, v): set them after oqb_ame_set_eigen. */
+int oqb_ame_set_jump(oqb_ame* ame, int nslots, const int64_t* h_slot_ptr, const int32_t* h_term, const double* h_rate);
+int oqb_ame_clear_jump(oqb_ame* ame);
+int oqb_ame_jump(oqb_ame* ame, int nb, void* d_psi, const double* d_uniform, const uint8_t* d_mask, int32_t* d_choice,
+                 double* d_prob, int apply);
+
 /* ------------------------------------------- SparseHamiltonian + trajectories (ψ ensembles) */
 /* Terms and Lindblad operators as Julia SparseMatrixCSC{ComplexF64,Int64}: 1-based colptr
  * (n+1) / rowval / nzval per matrix, concatenated; *_nnz_off[i] is the offset of matrix i in the

@@ -62,6 +62,9 @@ SIGNATURES = {
     "oqb_ame_rhs_host": [c_void_p, c_int, c_void_p, c_void_p],
     "oqb_ame_eig_acc": [c_void_p, c_int, c_void_p, c_void_p, c_int],
     "oqb_ame_update_cache": [c_void_p, c_void_p],
+    "oqb_ame_set_jump": [c_void_p, c_int, c_i64p, c_i32p, c_dp],
+    "oqb_ame_clear_jump": [c_void_p],
+    "oqb_ame_jump": [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int],
     "oqb_sparse_create": [c_void_p, c_int, c_int, c_i64p, c_i64p, c_void_p, c_i64p, c_int, c_i64p, c_i64p, c_void_p,
                           c_i64p, C.POINTER(c_void_p)],
     "oqb_sparse_destroy": [c_void_p],

@@ -9,30 +9,10 @@
 
 #include "../../include/oqb.h"
 #include "common.cuh"
+#include "ame.cuh"
 
 using namespace oqb;
 
-struct oqb_ame {
-    oqb_ctx* ctx = nullptr;
-    int n = 0, lvl = 0, K = 0;
-    bool has_v = false, have_eigen = false;
-    c128* d_coup = nullptr;  // K n×n couplings as given
-    c128* d_V = nullptr;     // n × lvl
-    double* d_w = nullptr;   // lvl
-    c128* d_A = nullptr;     // K lvl×lvl rotated couplings v' A v
-    c128* d_Cm = nullptr;    // lvl×lvl Hadamard coefficients (always includes −i(w_a−w_b))
-    // Davies
-    bool davies = false;
-    double *d_gam = nullptr, *d_S = nullptr, *d_Gam = nullptr, *d_hls = nullptr, *d_Wt = nullptr;
-    long long ncross = 0, nlamb = 0;
-    int32_t* d_cross_idx = nullptr;
-    double* d_cross_rate = nullptr;
-    c128* d_Moff = nullptr;  // dense lvl×lvl off-diagonal part of −½G − iH_LS (nullptr when empty)
-    // one-sided AME
-    int npairs = 0;
-    std::vector<int32_t> h_beta;
-    c128* d_Lam = nullptr;  // npairs lvl×lvl
-};
 
 namespace {
 
@@ -232,6 +212,7 @@ int oqb_ame_destroy(oqb_ame* a) {
     a->have_eigen = false;
     oqb_ame_clear_davies(a);
     oqb_ame_clear_onesided(a);
+    oqb_ame_clear_jump(a);
     (void)he;
     dfree(a->d_coup); dfree(a->d_V); dfree(a->d_w); dfree(a->d_A); dfree(a->d_Cm);
     delete a;
@@ -248,6 +229,7 @@ int oqb_ame_set_eigen(oqb_ame* a, const double* h_w, const void* h_v) {
     a->have_eigen = false;
     OQB_TRY(oqb_ame_clear_davies(a));
     OQB_TRY(oqb_ame_clear_onesided(a));
+    OQB_TRY(oqb_ame_clear_jump(a));
     OQB_CUDA(c, cudaMemcpyAsync(a->d_w, h_w, l * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     a->has_v = h_v != nullptr;
     if (a->has_v) {

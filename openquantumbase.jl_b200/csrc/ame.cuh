@@ -1,0 +1,34 @@
+// Private layout of the eigenbasis-Liouvillian handle (shared by ame.cu and ame_jump.cu).
+#pragma once
+#include <vector>
+
+#include "common.cuh"
+
+struct oqb_ame {
+    oqb_ctx* ctx = nullptr;
+    int n = 0, lvl = 0, K = 0;
+    bool has_v = false, have_eigen = false;
+    oqb::c128* d_coup = nullptr;  // K n×n couplings as given
+    oqb::c128* d_V = nullptr;     // n × lvl
+    double* d_w = nullptr;   // lvl
+    oqb::c128* d_A = nullptr;     // K lvl×lvl rotated couplings v' A v
+    oqb::c128* d_Cm = nullptr;    // lvl×lvl Hadamard coefficients (always includes −i(w_a−w_b))
+    // Davies
+    bool davies = false;
+    double *d_gam = nullptr, *d_S = nullptr, *d_Gam = nullptr, *d_hls = nullptr, *d_Wt = nullptr;
+    long long ncross = 0, nlamb = 0;
+    int32_t* d_cross_idx = nullptr;
+    double* d_cross_rate = nullptr;
+    oqb::c128* d_Moff = nullptr;  // dense lvl×lvl off-diagonal part of −½G − iH_LS (nullptr when empty)
+    // one-sided AME
+    int npairs = 0;
+    std::vector<int32_t> h_beta;
+    oqb::c128* d_Lam = nullptr;  // npairs lvl×lvl
+    // ame_jump tables (ame_jump.cu): probability slots in the reference's order
+    int nslots = 0;
+    long long nterms = 0;
+    long long* d_slot_ptr = nullptr;  // nslots+1 offsets into the term list
+    int32_t* d_term = nullptr;        // (coupling, row, col) per term, sorted by (row, col) within a slot
+    double* d_slot_rate = nullptr;    // γ at the slot's gap
+};
+

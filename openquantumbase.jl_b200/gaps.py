@@ -116,6 +116,50 @@ class GapGroups:
         return gam, Sm, np.ascontiguousarray(cross_rate), np.ascontiguousarray(lamb_rate_S)
 
 
+def jump_slots(w, K, digits=8, sigdigits=8):
+    """Probability slots of `ame_jump` (reference src/opensys/trajectory_jump.jl:14-51) in the reference's order,
+    from the sort-based grouping: unique non-zero gap keys ascending (GapIndices keeps `uniq_w` sorted,
+    src/opensys/opensys_util.jl:41-54), pairs inside a group in the (i<j) lexicographic loop order; per group and
+    coupling the slots L₊ (rows a, cols b, rate key +ω) and L₋ (rows b, cols a, rate key −ω); then per coupling the
+    zero-gap slot (degenerate pairs in both orders + the diagonal).  Returns (slot_ptr int64, term int32 (T,3) =
+    (coupling,row,col) 0-based sorted by (row,col) inside a slot, rate_key float64 per slot, tags) where tags[s] =
+    (coupling, rows, cols) 0-based in list order (what the reference's `tag` holds, 1-based)."""
+    w = np.asarray(w, dtype=np.float64)
+    l = len(w)
+    iu, ju = np.triu_indices(l, 1)
+    gap = w[ju] - w[iu]
+    zero = np.abs(gap) <= 10.0 ** (-digits)
+    key = np.zeros_like(gap)
+    key[~zero] = round_sigdigits(gap[~zero], sigdigits)
+    nzi, nzj, nzk = iu[~zero], ju[~zero], key[~zero]
+    order = np.argsort(nzk, kind="stable")  # stable: keeps the loop order inside a group
+    ks = nzk[order]
+    starts = np.flatnonzero(np.r_[True, ks[1:] != ks[:-1]]) if ks.size else np.zeros(0, dtype=np.int64)
+    ends = np.r_[starts[1:], ks.size] if ks.size else np.zeros(0, dtype=np.int64)
+    slot_ptr, terms, rate_key, tags = [0], [], [], []
+
+    def add(i, rows, cols, kval):
+        o = np.lexsort((cols, rows))
+        for r, c in zip(rows[o], cols[o]):
+            terms.append((i, int(r), int(c)))
+        slot_ptr.append(len(terms))
+        rate_key.append(kval)
+        tags.append((i, rows, cols))
+    for g in range(len(starts)):
+        mem = order[starts[g]:ends[g]]
+        a, b, kval = nzi[mem], nzj[mem], float(ks[starts[g]])
+        for i in range(K):
+            add(i, a, b, kval)
+            add(i, b, a, -kval)
+    zi, zj = iu[zero], ju[zero]
+    a0 = np.r_[np.stack([zi, zj], axis=1).ravel(), np.arange(l)].astype(np.int64)  # push i, push j per pair (:34-37)
+    b0 = np.r_[np.stack([zj, zi], axis=1).ravel(), np.arange(l)].astype(np.int64)
+    for i in range(K):
+        add(i, a0, b0, 0.0)
+    return (np.asarray(slot_ptr, dtype=np.int64), np.asarray(terms, dtype=np.int32).reshape(-1, 3),
+            np.asarray(rate_key, dtype=np.float64), tags)
+
+
 def _eval(f, x):
     """Evaluate a scalar host closure on an array (vectorised when the object offers it)."""
     if hasattr(f, "vectorized"):

@@ -750,6 +750,49 @@ class DiffEqLiouvillian:
         self._ame, self._ame_s = h, key
         self._w, self._v = w, v
 
+    def lindblad_jump(self, psi: "DeviceBatch", p, t, uniforms, mask=None, apply=False, w=None, v=None):
+        """lindblad_jump(Op::DiffEqLiouvillian{true,false}, u, p, t) src/opensys/trajectory_jump.jl:64-69 → ame_jump
+        :14-51 on a batch of state vectors (n × B).  Returns (choice[B] = index into the reference's prob/tag list,
+        prob[B, nslots]); `jump_operator(choice)` rebuilds the matrix the reference returns.  apply=True performs the
+        ψ ← Lψ/‖Lψ‖ of the external affect! in place."""
+        import torch
+        from .gaps import _eval, jump_slots
+        if not self.diagonalization or len(self.opensys_eig) != 1 or not isinstance(self.opensys_eig[0], DaviesGenerator):
+            raise NotImplementedError("lindblad_jump{true,false}: one DaviesGenerator (resample over several is not on the device path)")
+        s = float(np.atleast_1d(p(t))[0])
+        self._prepare_ame(s, w, v)
+        if getattr(self, "_jump_key", None) != self._ame_s:
+            K = len(self.opensys_eig[0].coupling(s))
+            ptr, terms, rkey, tags = jump_slots(self._w, K, self.digits, self.sigdigits)
+            uq, inv = np.unique(rkey, return_inverse=True)
+            rate = np.ascontiguousarray(_eval(self.opensys_eig[0].gamma, uq)[inv])
+            terms = np.ascontiguousarray(terms)
+            self.ctx.check(self.ctx.lib.oqb_ame_set_jump(self._ame, len(rate), ptr.ctypes.data_as(_lib.c_i64p),
+                                                         terms.ctypes.data_as(_lib.c_i32p), _lib.dptr(rate)))
+            self._jump_key, self._jump_tags, self._jump_rate = self._ame_s, tags, rate
+        B, ns = psi.B, len(self._jump_rate)
+        dev = psi.t.device
+        u_d = torch.as_tensor(np.asarray(uniforms, dtype=np.float64), device=dev)
+        m_d = None if mask is None else torch.as_tensor(np.asarray(mask, dtype=np.uint8), device=dev)
+        choice = torch.zeros(B, dtype=torch.int32, device=dev)
+        prob = torch.zeros((B, ns), dtype=torch.float64, device=dev)
+        self.ctx.check(self.ctx.lib.oqb_ame_jump(self._ame, B, psi.ptr, C.c_void_p(u_d.data_ptr()),
+                                                 None if m_d is None else C.c_void_p(m_d.data_ptr()),
+                                                 C.c_void_p(choice.data_ptr()), C.c_void_p(prob.data_ptr()), int(apply)))
+        self.ctx.sync()
+        return choice, prob
+
+    def jump_operator(self, slot: int, A_eig: np.ndarray) -> np.ndarray:
+        """The matrix ame_jump returns for tag `slot` (:46-50): v·√γ·sparse(a, b, σ_i[a,b])·v', from the rotated
+        couplings A_eig (K, lvl, lvl) — host bookkeeping for callers that want the operator itself."""
+        i, rows, cols = self._jump_tags[slot]
+        l = len(self._w)
+        L = np.zeros((l, l), dtype=C128)
+        L[rows, cols] = A_eig[i][rows, cols]
+        L *= np.sqrt(self._jump_rate[slot])
+        v = self._v if self._v is not None else np.eye(l, dtype=C128)
+        return v @ L @ v.conj().T
+
     def _rhs_eig(self, du, u, p, t, w=None, v=None):
         """(Op::DiffEqLiouvillian{true,false})(du,u,p,t) :92-109.  All members share s (one
         eigen-system per call, like the reference's single haml_eigs)."""

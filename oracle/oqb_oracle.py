@@ -752,6 +752,46 @@ class DiffEqLiouvillian:
         return cache
 
 
+def ame_jump(D: DaviesGenerator, u, gap_idx: GapIndices, v, s, r: float):
+    """src/opensys/trajectory_jump.jl:14-51, literal: one (L₊, L₋) pair per (positive gap group, coupling), then the
+    zero-gap group per coupling; `sample(tag, Weights(prob))` with the uniform r.  Returns (choice, prob, v·√g·L·v')."""
+    l = gap_idx.get_lvl()
+    phib = v.conj().T @ u
+    sab = [v.conj().T @ op_ @ v for op_ in D.coupling(s)]
+    prob, tag = [], []
+    for (w, a, b) in gap_idx.positive_gap_indices():
+        gp, gm = D.gamma(w), D.gamma(-w)
+        for i, sg in enumerate(sab):
+            Lp = _sparse_pick(sg, a, b, l)
+            Lm = _sparse_pick(sg, b, a, l)
+            php = Lp @ phib
+            prob.append(gp * float(np.real(np.vdot(php, php))))
+            tag.append((i, a, b, np.sqrt(gp)))
+            phm = Lm @ phib
+            prob.append(gm * float(np.real(np.vdot(phm, phm))))
+            tag.append((i, b, a, np.sqrt(gm)))
+    g0 = D.gamma(0)
+    a, b = gap_idx.zero_gap_indices()
+    for i, sg in enumerate(sab):
+        L = _sparse_pick(sg, a, b, l)
+        ph = L @ phib
+        prob.append(float(np.real(g0 * np.vdot(ph, ph))))
+        tag.append((i, a, b, np.sqrt(g0)))
+    k = sample_weights(prob, r)
+    ci, ca, cb, cg = tag[k]
+    L = cg * _sparse_pick(sab[ci], ca, cb, l)
+    return k, np.array(prob), v @ L @ v.conj().T
+
+
+def lindblad_jump_ame(op: DiffEqLiouvillian, u, p, t, r: float, w=None, v=None):
+    """src/opensys/trajectory_jump.jl:64-69 ({true,false}) with one DaviesGenerator in opensys_eig."""
+    s = p(t)
+    if w is None:
+        w, v = haml_eigs(op.H, s, op.lvl)
+    gap_idx = build_gap_indices(w, op.digits, op.sigdigits)
+    return ame_jump(op.opensys_eig[0], u, gap_idx, v, s, r)
+
+
 def lindblad_jump(op: DiffEqLiouvillian, u, p, t, r: float):
     """src/opensys/trajectory_jump.jl:71-74 with a single LindbladLiouvillian in
     `opensys` (resample :81-88 returns Ls[1] when there is one)."""

@@ -532,3 +532,57 @@ def test_expect(Q):
     out = Q.expect(obs, Q.DeviceBatch.from_host(psi)).cpu().numpy()
     ref = np.array([[p.conj() @ o @ p for o in obs] for p in psi])
     assert relerr(out, ref) < 1e-13
+
+
+# ---------------------------------------------------------------------------------------------
+# ame_jump / lindblad_jump{true,false}  (reference src/opensys/trajectory_jump.jl:14-51,64-69; test/opensys/davies.jl:63-66)
+# ---------------------------------------------------------------------------------------------
+def _ame_jump_case(Q, mats, coup, lvl, s, nb, rng, gam):
+    n = mats[0].shape[0]
+    Ho = O.DenseHamiltonian([A, B], mats)
+    Hg = Q.DenseHamiltonian([A, B], mats)
+    w, v = O.haml_eigs(Ho, s, lvl)
+    opo = O.DiffEqLiouvillian(Ho, [O.DaviesGenerator(coup, gam, lamb)], [], lvl)
+    opg = Q.DiffEqLiouvillian(Hg, [Q.DaviesGenerator(Q.ConstantCouplings(coup, unit="ħ"), gam, lamb)], [], lvl)
+    psi = rand_c(rng, nb, n)
+    psi /= np.linalg.norm(psi, axis=1, keepdims=True)
+    r = rng.random(nb)
+    tf = 2.0
+    pg, po = Q.ODEParams(None, tf), O.ODEParams(None, tf)
+    pd = Q.DeviceBatch.from_host(psi)
+    choice, prob = opg.lindblad_jump(pd, pg, s * tf, r, w=w, v=v)
+    choice, prob = choice.cpu().numpy(), prob.cpu().numpy()
+    A_eig = np.stack([v.conj().T @ c @ v for c in coup])
+    for b in range(nb):
+        k, pr, L = O.lindblad_jump_ame(opo, psi[b], po, s * tf, r[b], w=w, v=v)
+        assert k == choice[b]                                   # identical index for identical uniforms
+        assert np.allclose(pr, prob[b], rtol=1e-12, atol=1e-14 * max(pr.max(), 1e-300))
+        assert L.shape == (n, n)                                # the reference's own check (davies.jl:66)
+        assert relerr(opg.jump_operator(int(k), A_eig), L) < 1e-13
+    mask = (np.arange(nb) % 3 != 1)
+    choice2, _ = opg.lindblad_jump(pd, pg, s * tf, r, mask=mask, apply=True, w=w, v=v)
+    out, choice2 = pd.to_host(), choice2.cpu().numpy()
+    for b in range(nb):
+        if mask[b]:
+            _, _, L = O.lindblad_jump_ame(opo, psi[b], po, s * tf, r[b], w=w, v=v)
+            y = L @ psi[b]
+            assert relerr(out[b], y / np.linalg.norm(y)) < TOL
+        else:
+            assert choice2[b] == -1 and np.array_equal(out[b], psi[b])
+
+
+def test_ame_jump_2qubit_fixture(Q, ame2q):
+    rng = np.random.default_rng(21)
+    _ame_jump_case(Q, ame2q["mats"], ame2q["coup"], 4, 0.5, 7, rng, gamma)
+
+
+@pytest.mark.parametrize("nq,lvl,K", [(3, 8, 3), (4, 6, 2), (5, 32, 5)])
+def test_ame_jump_vs_oracle(Q, nq, lvl, K):
+    rng = np.random.default_rng(300 + nq)
+    n = 2 ** nq
+    Hd = -F.standard_driver(nq)
+    hz = rng.standard_normal(nq)
+    Hp = sum(hz[k] * F.single_clause(["z"], [k + 1], 1.0, nq) for k in range(nq)) \
+        + F.two_local_term(list(rng.standard_normal(nq - 1)), [[i, i + 1] for i in range(1, nq)], nq)
+    coup = [F.single_clause(["z"], [k + 1], 1.0, nq) for k in range(K)]
+    _ame_jump_case(Q, [Hd, Hp], coup, lvl, 0.6, 9, rng, gamma)

@@ -139,3 +139,29 @@ def test_gk15_node_tables_and_sampled_unitary():
     assert np.allclose(U(0.75), 1.5 * np.eye(2)) and np.allclose(U(2.0), 4 * np.eye(2))
     g, th = SampledUnitary.locate(np.array([0.0, 0.74, 2.0, 2.5]), 0.5, 5)
     assert list(g) == [0, 1, 4, 4] and th[2] == 0.0 and th[3] == 0.0
+
+
+def test_jump_slots_follow_the_reference_order():
+    """gaps.jump_slots (sort-based) lists ame_jump's probability slots exactly as the literal GapIndices loop does
+    (src/opensys/opensys_util.jl:25-61, src/opensys/trajectory_jump.jl:22-44), including degenerate groups."""
+    from oqb_b200.gaps import jump_slots
+    rng = np.random.default_rng(3)
+    for w in (np.sort(rng.standard_normal(7)), np.array([0.0, 1.0, 1.0, 2.0, 3.0, 3.0 + 1e-12, 5.0]),
+              np.array([-1.0, -0.5, 0.0, 0.5, 1.0])):
+        K = 2
+        G = O.build_gap_indices(w, 8, 8)
+        ptr, terms, rkey, tags = jump_slots(w, K, 8, 8)
+        exp = []
+        for (gw, a, b) in G.positive_gap_indices():
+            for i in range(K):
+                exp.append((i, list(np.array(a) - 1), list(np.array(b) - 1), gw))
+                exp.append((i, list(np.array(b) - 1), list(np.array(a) - 1), -gw))
+        a0, b0 = G.zero_gap_indices()
+        for i in range(K):
+            exp.append((i, list(np.array(a0) - 1), list(np.array(b0) - 1), 0.0))
+        assert len(exp) == len(rkey) == len(tags) == len(ptr) - 1
+        for s, (i, rows, cols, kv) in enumerate(exp):
+            ti, tr, tc = tags[s]
+            assert ti == i and list(tr) == rows and list(tc) == cols and rkey[s] == kv
+            seg = terms[ptr[s]:ptr[s + 1]]
+            assert sorted(zip(rows, cols)) == [(int(r), int(c)) for _, r, c in seg] and all(t[0] == i for t in seg)
