@@ -589,8 +589,11 @@ int sm_count(oqb_ctx* c) {
     return sms;
 }
 
+// rk != nullptr: fuse the RK4 stage arithmetic into the store (XOR-structured operators only); *fused reports whether
+// that happened — when it did not, NOTHING was computed and the caller runs the unfused sequence.
 int traj_matvec_impl(oqb_sparse* sp, int nb, const double* coefH, int coef_shared, const double* gamma, int gamma_shared,
-                     const c128* psi, c128* dpsi) {
+                     const c128* psi, c128* dpsi, const RkEpilogue* rk = nullptr, int* fused = nullptr) {
+    if (fused) *fused = 0;
     oqb_ctx* c = sp->ctx;
     if (nb <= 0) return 0;
     if (!coefH || !psi || !dpsi) return set_error(c, OQB_EINVAL, "oqb_traj_matvec: null argument");
@@ -634,8 +637,12 @@ int traj_matvec_impl(oqb_sparse* sp, int nb, const double* coefH, int coef_share
     }
     {
         bool used = false;  // implicit-column (XOR-structured) operator, 3-deep ψ ring, no CTA barrier
-        OQB_TRY(traj_matvec_xor(c, n, nb, ts, (const c128*)d_stage, shared ? 0 : ncoef, psi, dpsi, &used));
-        if (used) return 0;
+        OQB_TRY(traj_matvec_xor(c, n, nb, ts, (const c128*)d_stage, shared ? 0 : ncoef, psi, dpsi, &used, rk));
+        if (used) {
+            if (fused) *fused = 1;
+            return 0;
+        }
+        if (rk) return 0;
     }
     {
         bool used = false;  // register-resident operator + bulk-async ψ staging when the term list allows it
@@ -661,6 +668,11 @@ int traj_matvec_impl(oqb_sparse* sp, int nb, const double* coefH, int coef_share
 }
 
 }  // namespace
+
+int oqb_traj_matvec_rk(oqb_sparse* sp, int nb, const double* h_coefH, int coef_shared, const double* h_gamma, int gamma_shared,
+                       const c128* psi_in, c128* out, const RkEpilogue* rk, int* fused) {
+    return traj_matvec_impl(sp, nb, h_coefH, coef_shared, h_gamma, gamma_shared, psi_in, out, rk, fused);
+}
 
 // accessors for traj_evolve.cu (the struct layout stays private to this file)
 oqb_ctx* oqb_sparse_ctx(oqb_sparse* sp) { return sp->ctx; }

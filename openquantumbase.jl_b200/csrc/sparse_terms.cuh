@@ -32,9 +32,21 @@ struct TermDev {
 int traj_matvec_fast(Ctx* c, int n, int nb, const std::vector<const TermDev*>& ts, const c128* d_coef,
                      long long coef_ld, const c128* psi, c128* dpsi, bool* used);
 
+// Optional RK4 stage arithmetic fused into the store of k = Aψ_in (used by oqb_traj_evolve, traj_evolve.cu):
+//   mode 1 (first stage, ψ_in = ψ0):  acc = ψ0 + wa·k,  out = ψ0 + wt·k
+//   mode 2 (middle stages):           acc += wa·k,      out = ψ0 + wt·k     (out may alias ψ_in: a trajectory is
+//                                                                            staged completely before it is computed)
+//   mode 3 (last stage):              out = acc + wa·k
+struct RkEpilogue {
+    int mode = 0;
+    double wa = 0.0, wt = 0.0;
+    const c128* psi0 = nullptr;
+    c128* acc = nullptr;
+};
+
 // Same contract for terms in XOR form + real diagonal terms (implicit columns, 3-deep bulk-async ψ ring,
 // no CTA-wide barrier): traj_xor.cu.
 int traj_matvec_xor(Ctx* c, int n, int nb, const std::vector<const TermDev*>& ts, const c128* d_coef,
-                    long long coef_ld, const c128* psi, c128* dpsi, bool* used);
+                    long long coef_ld, const c128* psi, c128* dpsi, bool* used, const RkEpilogue* rk = nullptr);
 
 }  // namespace oqb

@@ -97,11 +97,23 @@ __device__ __forceinline__ void local_dispatch(int hk, const c128 (&xo)[R], doub
 }
 
 // one chunk of CH rows (rows C0 … C0+CH-1 of this thread)
-template <int R, int NT, int CH, int C0, bool RV, int ND>
+template <int R, int NT, int CH, int C0, bool RV, int ND, int EPI>
 __device__ __forceinline__ void do_chunk(const XorDesc& d, const int* s_mask, const double* s_vre, const double* s_vim,
                                          const c128* __restrict__ x, const c128* cfs, const c128 (&xo)[R],
                                          const double (&dreg)[R][ND > 0 ? ND : 1], const c128 (&cdiag)[ND > 0 ? ND : 1],
-                                         c128* __restrict__ out, int tid) {
+                                         c128* out, int tid, double wa, double wt, const c128* __restrict__ rk_psi0,
+                                         c128* __restrict__ rk_acc) {
+    // fused RK4 stage (EPI != 0): the extra operands are requested before the gathers so that their HBM latency
+    // hides behind the shared-memory work of the chunk
+    c128 e0[EPI == 2 ? CH : 1], e1[EPI >= 2 ? CH : 1];
+    if (EPI == 2) {
+#pragma unroll
+        for (int kk = 0; kk < CH; ++kk) e0[kk] = rk_psi0[tid + (C0 + kk) * NT];
+    }
+    if (EPI >= 2) {
+#pragma unroll
+        for (int kk = 0; kk < CH; ++kk) e1[kk] = rk_acc[tid + (C0 + kk) * NT];
+    }
     double outr[CH], outi[CH];
 #pragma unroll
     for (int kk = 0; kk < CH; ++kk) {  // diagonal part: (const + Σ_t c_bt d_t[r]) ψ[r]
@@ -145,14 +157,29 @@ __device__ __forceinline__ void do_chunk(const XorDesc& d, const int* s_mask, co
         }
     }
 #pragma unroll
-    for (int kk = 0; kk < CH; ++kk) out[tid + (C0 + kk) * NT] = make_double2(outr[kk], outi[kk]);
+    for (int kk = 0; kk < CH; ++kk) {
+        const int idx = tid + (C0 + kk) * NT;
+        if (EPI == 0) {
+            out[idx] = make_double2(outr[kk], outi[kk]);
+        } else if (EPI == 1) {
+            const c128 p0 = xo[C0 + kk];
+            rk_acc[idx] = make_double2(p0.x + wa * outr[kk], p0.y + wa * outi[kk]);
+            out[idx] = make_double2(p0.x + wt * outr[kk], p0.y + wt * outi[kk]);
+        } else if (EPI == 2) {
+            rk_acc[idx] = make_double2(e1[kk].x + wa * outr[kk], e1[kk].y + wa * outi[kk]);
+            out[idx] = make_double2(e0[kk].x + wt * outr[kk], e0[kk].y + wt * outi[kk]);
+        } else {
+            out[idx] = make_double2(e1[kk].x + wa * outr[kk], e1[kk].y + wa * outi[kk]);
+        }
+    }
 }
 
 // R rows per thread (r = tid + k·NT), S ring stages, RV: all slot values real, ND: real diagonal terms in registers
-template <int R, int NT, int S, bool RV, int ND>
+template <int R, int NT, int S, bool RV, int ND, int EPI>
 __global__ void __launch_bounds__(NT, 1)
     traj_xor_kernel(int nb, const __grid_constant__ XorDesc d, const c128* __restrict__ coef, long long coef_ld,
-                    const c128* __restrict__ psi, c128* __restrict__ dpsi) {
+                    const c128* psi, c128* dpsi, double wa, double wt, const c128* __restrict__ rk_psi0,
+                    c128* __restrict__ rk_acc) {
     constexpr int n = R * NT, NW = NT / 32, CH = R < 8 ? R : 8, STAGE = n + kCoefPad;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     c128* ring = reinterpret_cast<c128*>(smem_raw);
@@ -222,16 +249,20 @@ __global__ void __launch_bounds__(NT, 1)
         c128 xo[R];
 #pragma unroll
         for (int k = 0; k < R; ++k) xo[k] = x[tid + k * NT];
-        c128* __restrict__ out = dpsi + (size_t)b * n;
-        do_chunk<R, NT, CH, 0, RV, ND>(d, s_mask, s_vre, s_vim, x, cfs, xo, dreg, cdiag, out, tid);
-        if (R > 8) do_chunk<R, NT, CH, (R > 8 ? 8 : 0), RV, ND>(d, s_mask, s_vre, s_vim, x, cfs, xo, dreg, cdiag, out, tid);
+        c128* out = dpsi + (size_t)b * n;
+        const c128* p0 = EPI == 2 ? rk_psi0 + (size_t)b * n : nullptr;
+        c128* ac = EPI != 0 ? rk_acc + (size_t)b * n : nullptr;
+        do_chunk<R, NT, CH, 0, RV, ND, EPI>(d, s_mask, s_vre, s_vim, x, cfs, xo, dreg, cdiag, out, tid, wa, wt, p0, ac);
+        if (R > 8)
+            do_chunk<R, NT, CH, (R > 8 ? 8 : 0), RV, ND, EPI>(d, s_mask, s_vre, s_vim, x, cfs, xo, dreg, cdiag, out, tid, wa, wt, p0, ac);
         __syncwarp();
         if (lane == 0) xb_arrive(bar_base + 8 * (S + s));
     }
 }
 
-template <int R, int NT, int S, bool RV, int ND>
-int launch(Ctx* c, int nb, const XorDesc& d_in, const c128* coef, long long coef_ld, const c128* psi, c128* dpsi) {
+template <int R, int NT, int S, bool RV, int ND, int EPI>
+int launch(Ctx* c, int nb, const XorDesc& d_in, const c128* coef, long long coef_ld, const c128* psi, c128* dpsi,
+           const RkEpilogue* rk) {
     XorDesc d = d_in;
     int w = 0;
     for (int e = 0; e < d_in.n_x; ++e) {  // gathers first (padded to an even count), thread-local slots (mask % NT == 0) last
@@ -261,7 +292,7 @@ int launch(Ctx* c, int nb, const XorDesc& d_in, const c128* coef, long long coef
     const size_t smem = (size_t)S * (R * NT + kCoefPad) * sizeof(c128);
     static bool cfg = false;
     if (!cfg) {
-        OQB_CUDA(c, cudaFuncSetAttribute(traj_xor_kernel<R, NT, S, RV, ND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        OQB_CUDA(c, cudaFuncSetAttribute(traj_xor_kernel<R, NT, S, RV, ND, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         cfg = true;
     }
     int sms = 148;
@@ -271,29 +302,32 @@ int launch(Ctx* c, int nb, const XorDesc& d_in, const c128* coef, long long coef
     if (per_sm > 2048 / NT) per_sm = 2048 / NT;
     const int grid = nb < sms * per_sm ? nb : sms * per_sm;
     {
-        ProfScope prof(c, 32.0 * R * NT * (double)nb);  // algorithmic bytes: read ψ + write dψ
-        traj_xor_kernel<R, NT, S, RV, ND><<<grid, NT, smem, c->stream>>>(nb, d, coef, coef_ld, psi, dpsi);
+        // algorithmic bytes: read ψ + write dψ (+ the RK operands: 1 extra vector for modes 1/3, 3 for mode 2)
+        ProfScope prof(c, (EPI == 0 ? 32.0 : (EPI == 2 ? 80.0 : 48.0)) * R * NT * (double)nb);
+        traj_xor_kernel<R, NT, S, RV, ND, EPI><<<grid, NT, smem, c->stream>>>(nb, d, coef, coef_ld, psi, dpsi, rk ? rk->wa : 0.0,
+                                                                             rk ? rk->wt : 0.0, rk ? rk->psi0 : nullptr,
+                                                                             rk ? rk->acc : nullptr);
     }
     OQB_LAUNCH_CHECK(c);
     return 0;
 }
 
-template <bool RV, int ND>
-int by_size(Ctx* c, int n, int nb, const XorDesc& d, const c128* coef, long long coef_ld, const c128* psi, c128* dpsi,
-            bool* used) {
+template <bool RV, int ND, int EPI>
+int by_size_epi(Ctx* c, int n, int nb, const XorDesc& d, const c128* coef, long long coef_ld, const c128* psi, c128* dpsi,
+                bool* used, const RkEpilogue* rk) {
     *used = true;
     int st = 0;
     switch (n) {
         case 4096: {
             static const int rsel = [] { const char* e = getenv("OQB_XOR_R"); return e ? atoi(e) : 16; }();
-            if (rsel == 8) st = launch<8, 512, 3, RV, ND>(c, nb, d, coef, coef_ld, psi, dpsi);
-            else st = launch<16, 256, 3, RV, ND>(c, nb, d, coef, coef_ld, psi, dpsi);
+            if (rsel == 8) st = launch<8, 512, 3, RV, ND, EPI>(c, nb, d, coef, coef_ld, psi, dpsi, rk);
+            else st = launch<16, 256, 3, RV, ND, EPI>(c, nb, d, coef, coef_ld, psi, dpsi, rk);
             break;
         }
-        case 2048: st = launch<8, 256, 3, RV, ND>(c, nb, d, coef, coef_ld, psi, dpsi); break;
-        case 1024: st = launch<4, 256, 3, RV, ND>(c, nb, d, coef, coef_ld, psi, dpsi); break;
-        case 512: st = launch<4, 128, 3, RV, ND>(c, nb, d, coef, coef_ld, psi, dpsi); break;
-        case 256: st = launch<2, 128, 3, RV, ND>(c, nb, d, coef, coef_ld, psi, dpsi); break;
+        case 2048: st = launch<8, 256, 3, RV, ND, EPI>(c, nb, d, coef, coef_ld, psi, dpsi, rk); break;
+        case 1024: st = launch<4, 256, 3, RV, ND, EPI>(c, nb, d, coef, coef_ld, psi, dpsi, rk); break;
+        case 512: st = launch<4, 128, 3, RV, ND, EPI>(c, nb, d, coef, coef_ld, psi, dpsi, rk); break;
+        case 256: st = launch<2, 128, 3, RV, ND, EPI>(c, nb, d, coef, coef_ld, psi, dpsi, rk); break;
         default: *used = false; return 0;
     }
     if (st < 0) {  // slot table overflow after padding: let the caller fall back
@@ -303,10 +337,21 @@ int by_size(Ctx* c, int n, int nb, const XorDesc& d, const c128* coef, long long
     return st;
 }
 
+template <bool RV, int ND>
+int by_size(Ctx* c, int n, int nb, const XorDesc& d, const c128* coef, long long coef_ld, const c128* psi, c128* dpsi,
+            bool* used, const RkEpilogue* rk) {
+    switch (rk ? rk->mode : 0) {
+        case 0: return by_size_epi<RV, ND, 0>(c, n, nb, d, coef, coef_ld, psi, dpsi, used, rk);
+        case 1: return by_size_epi<RV, ND, 1>(c, n, nb, d, coef, coef_ld, psi, dpsi, used, rk);
+        case 2: return by_size_epi<RV, ND, 2>(c, n, nb, d, coef, coef_ld, psi, dpsi, used, rk);
+        default: return by_size_epi<RV, ND, 3>(c, n, nb, d, coef, coef_ld, psi, dpsi, used, rk);
+    }
+}
+
 }  // namespace
 
 int traj_matvec_xor(Ctx* c, int n, int nb, const std::vector<const TermDev*>& ts, const c128* d_coef, long long coef_ld,
-                    const c128* psi, c128* dpsi, bool* used) {
+                    const c128* psi, c128* dpsi, bool* used, const RkEpilogue* rk) {
     *used = false;
     static const int mode = [] { const char* e = getenv("OQB_TRAJ"); return e ? (int)e[0] : 0; }();
     if (mode == 'g' || mode == 'f') return 0;  // "generic" / "fast": skip this path (A/B measurements)
@@ -344,12 +389,12 @@ int traj_matvec_xor(Ctx* c, int n, int nb, const std::vector<const TermDev*>& ts
             d.x_begin[d.n_x] = slots;
         }
     }
-    if (d.n_diag == 0) return all_real ? by_size<true, 0>(c, n, nb, d, d_coef, coef_ld, psi, dpsi, used)
-                                       : by_size<false, 0>(c, n, nb, d, d_coef, coef_ld, psi, dpsi, used);
-    if (d.n_diag == 1) return all_real ? by_size<true, 1>(c, n, nb, d, d_coef, coef_ld, psi, dpsi, used)
-                                       : by_size<false, 1>(c, n, nb, d, d_coef, coef_ld, psi, dpsi, used);
-    return all_real ? by_size<true, 2>(c, n, nb, d, d_coef, coef_ld, psi, dpsi, used)
-                    : by_size<false, 2>(c, n, nb, d, d_coef, coef_ld, psi, dpsi, used);
+    if (d.n_diag == 0) return all_real ? by_size<true, 0>(c, n, nb, d, d_coef, coef_ld, psi, dpsi, used, rk)
+                                       : by_size<false, 0>(c, n, nb, d, d_coef, coef_ld, psi, dpsi, used, rk);
+    if (d.n_diag == 1) return all_real ? by_size<true, 1>(c, n, nb, d, d_coef, coef_ld, psi, dpsi, used, rk)
+                                       : by_size<false, 1>(c, n, nb, d, d_coef, coef_ld, psi, dpsi, used, rk);
+    return all_real ? by_size<true, 2>(c, n, nb, d, d_coef, coef_ld, psi, dpsi, used, rk)
+                    : by_size<false, 2>(c, n, nb, d, d_coef, coef_ld, psi, dpsi, used, rk);
 }
 
 }  // namespace oqb
