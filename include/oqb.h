@@ -66,6 +66,11 @@ int oqb_free_host(oqb_ctx* ctx, void* h_ptr);
 int oqb_upload(oqb_ctx* ctx, void* d_dst, const void* h_src, size_t nbytes);   /* synchronous */
 int oqb_download(oqb_ctx* ctx, void* h_dst, const void* d_src, size_t nbytes); /* synchronous */
 
+/* y[b] += alpha·x[b] for nb blocks of len complex elements (stride_x = 0 shares one x): the `cache .+= D.A` /
+ * `du .+= …` accumulations of the reference's constant-operator Liouvillians (src/opensys/davies.jl:119,
+ * src/opensys/stochastic.jl:34-44) when the term was produced by an overwriting entry point. */
+int oqb_axpy_batched(oqb_ctx* ctx, int64_t len, int nb, const double* alpha, const void* d_x, int64_t stride_x, void* d_y);
+
 /* --------------------------------------------------------------- K1: batched ZGEMM -------- */
 /* C[b] = alpha*opA(A[b])*opB(B[b]) + beta*C[b] on the FP64 tensor pipe.  Replaces LinearAlgebra
  * `gemm!`/`mul!` on batches (src/hamiltonian/dense_hamiltonian.jl:87-88).  Strides in complex

@@ -33,6 +33,7 @@ SIGNATURES = {
     "oqb_free_host": [c_void_p, c_void_p],
     "oqb_upload": [c_void_p, c_void_p, c_void_p, c_size_t],
     "oqb_download": [c_void_p, c_void_p, c_void_p, c_size_t],
+    "oqb_axpy_batched": [c_void_p, c_i64, c_int, c_dp, c_void_p, c_i64, c_void_p],
     "oqb_zgemm_batched": [c_void_p, c_int, c_int, c_int, c_int, c_int, c_dp, c_void_p, c_i64, c_i64, c_void_p,
                           c_i64, c_i64, c_dp, c_void_p, c_i64, c_i64, c_int],
     "oqb_dense_create": [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, C.POINTER(c_void_p)],

@@ -165,6 +165,8 @@ namespace oqb {
 // out[b][e] (+)= Σ_j coef[b*coef_ld + j] * mats[j*len + e],  e < len, b < nb   (coef complex, device)
 int lincomb(Ctx* c, int nmat, long long len, const c128* mats, const c128* coef, long long coef_ld,
             c128* out, int nb, bool accumulate);
+// y[b][e] += alpha · x[b*stride_x + e]
+int axpy_batched(Ctx* c, long long len, int nb, c128 alpha, const c128* x, long long stride_x, c128* y);
 // X[b][a+b'*l] (+)= (Cm[a+b'*l] + (w_sub ? i(w_sub[a]-w_sub[b']) : 0)) * R[b][a+b'*l]
 int hadamard(Ctx* c, int l, const c128* Cm, const double* w_sub, const c128* R, c128* X, int nb,
              bool accumulate);

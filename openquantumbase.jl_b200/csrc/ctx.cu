@@ -143,6 +143,10 @@ int oqb_set_stream(oqb_ctx* c, void* s) {
 }
 int oqb_get_stream(oqb_ctx* c, void** s) { *s = (void*)c->stream; return 0; }
 int oqb_launch_count(const oqb_ctx* c, uint64_t* n) { *n = c->launches; return 0; }
+int oqb_axpy_batched(oqb_ctx* c, int64_t len, int nb, const double* alpha, const void* d_x, int64_t stride_x, void* d_y) {
+    if (!alpha || !d_x || !d_y) return set_error(c, OQB_EINVAL, "oqb_axpy_batched: null argument");
+    return axpy_batched(c, len, nb, make_double2(alpha[0], alpha[1]), (const c128*)d_x, stride_x, (c128*)d_y);
+}
 int oqb_set_zgemm_mode(oqb_ctx* c, int mode) {
     if (mode != 0 && mode != 1) return set_error(c, OQB_EINVAL, "oqb_set_zgemm_mode: mode must be 0 (4M) or 1 (3M)");
     c->zgemm_3m = mode;

@@ -43,6 +43,30 @@ int lincomb(Ctx* c, int nmat, long long len, const c128* mats, const c128* coef,
     return 0;
 }
 
+// y[b][e] += alpha · x[b·stride_x + e]   (stride_x = 0 shares x across the batch)
+__global__ void axpy_batched_kernel(long long len, c128 alpha, const c128* __restrict__ x, long long stride_x,
+                                    c128* __restrict__ y) {
+    const c128* xb = x + (long long)blockIdx.y * stride_x;
+    c128* yb = y + (long long)blockIdx.y * len;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < len; e += (long long)gridDim.x * blockDim.x) {
+        const c128 v = cmul(alpha, xb[e]);
+        c128 o = yb[e];
+        o.x += v.x;
+        o.y += v.y;
+        yb[e] = o;
+    }
+}
+int axpy_batched(Ctx* c, long long len, int nb, c128 alpha, const c128* x, long long stride_x, c128* y) {
+    if (nb <= 0 || len <= 0) return 0;
+    for (int b0 = 0; b0 < nb; b0 += 65535) {
+        int cnt = nb - b0 < 65535 ? nb - b0 : 65535;
+        dim3 grid(cdiv(len, 256) < 4096 ? cdiv(len, 256) : 4096, cnt);
+        axpy_batched_kernel<<<grid, 256, 0, c->stream>>>(len, alpha, x + (long long)b0 * stride_x, stride_x, y + (long long)b0 * len);
+        OQB_LAUNCH_CHECK(c);
+    }
+    return 0;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Davies closed form, per-ρ part:  X = C∘ρ̃ ;  X_aa += Σ_b W_ab ρ̃_bb   
 // ---------------------------------------------------------------------------------------------

@@ -1,0 +1,167 @@
+"""Host mirrors of the reference's remaining Liouvillian types on the RHS path, all evaluated by the
+same device entry points as the main types:
+
+  ConstDaviesGenerator   src/opensys/davies.jl:102-119   → oqb_dense_rhs (H = H_LS, L_k = Linds, γ ≡ 1) + oqb_axpy_batched
+  ConstHDaviesGenerator  src/opensys/davies.jl:121-163   → the closed-form Davies tables in a fixed basis (oqb_ame_* with v = I)
+  FluctuatorLiouvillian  src/opensys/stochastic.jl:11-44 → oqb_dense_rhs / update_cache / update_vectorized_cache with the
+                                                           noise values n_i as per-member coefficients
+
+`build_const_davies` (src/opensys/davies.jl:173-209) is construction-time host work (index bookkeeping on l×l
+matrices), like the reference's.
+"""
+import ctypes as C
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from .gaps import GapGroups, _eval, jump_slots
+from .host import C128, Context, DeviceBatch, _HostIO, _colmajor_stack, _svec, get_context
+
+_ONE = np.array([1.0, 0.0])
+
+
+def _axpy(ctx, x: DeviceBatch, y: DeviceBatch, shared_x=False):
+    n_el = y.rows * y.cols
+    ctx.check(ctx.lib.oqb_axpy_batched(ctx.h, n_el, y.B, _lib.dptr(_ONE), x.ptr, 0 if shared_x else n_el, y.ptr))
+
+
+class ConstDaviesGenerator:
+    def __init__(self, Linds: Sequence[np.ndarray], Hls: np.ndarray, A: np.ndarray, ctx: Optional[Context] = None):
+        self.Linds = [np.asarray(L, dtype=C128) for L in Linds]
+        self.Hls, self.A = np.asarray(Hls, dtype=C128), np.asarray(A, dtype=C128)
+        self.ctx = ctx or get_context()
+        self._op = None
+
+    def _dense(self):
+        if self._op is None:
+            h = C.c_void_p()
+            n = self.Hls.shape[0]
+            hb, lb = _colmajor_stack([self.Hls]), _colmajor_stack(self.Linds)
+            self.ctx.check(self.ctx.lib.oqb_dense_create(self.ctx.h, n, 1, hb.ctypes.data, len(self.Linds), lb.ctypes.data, C.byref(h)))
+            self._op = h
+        return self._op
+
+    def __call__(self, du, rho, *_):
+        """(D::ConstDaviesGenerator)(du, ρ, _, _) :111-117 — ACCUMULATES."""
+        io = _HostIO(rho, du)
+        B, K = io.u.B, len(self.Linds)
+        tmp = io.u.zeros_like()
+        one, g = np.ones((1, 1)), np.ones((1, K))
+        self.ctx.check(self.ctx.lib.oqb_dense_rhs(self._dense(), B, _lib.dptr(one), 1, _lib.dptr(g), 1, io.u.ptr, tmp.ptr))
+        _axpy(self.ctx, tmp, io.du)
+        return io.finish()
+
+    def update_cache(self, cache, *_):
+        """update_cache!(cache, D, _, _) = cache .+= D.A  (:119)."""
+        io = _HostIO(cache, cache)
+        Ad = DeviceBatch.from_host(self.A[None], self.ctx)
+        _axpy(self.ctx, Ad, io.du, shared_x=True)
+        return io.finish()
+
+
+def build_const_davies(couplings: Sequence[np.ndarray], w, gamma, S, digits=8, sigdigits=8, ctx=None) -> ConstDaviesGenerator:
+    """src/opensys/davies.jl:173-209 for constant couplings given in the eigenbasis (rotate(couplings, v))."""
+    cs = [np.asarray(c, dtype=C128) for c in couplings]
+    l = len(w)
+    _, _, rkey, tags = jump_slots(w, len(cs), digits, sigdigits)
+    uq, inv = np.unique(rkey, return_inverse=True)
+    gv, sv = _eval(gamma, uq)[inv], _eval(S, uq)[inv]
+    res = []
+    Hls = np.zeros((l, l), dtype=C128)
+    Am = np.zeros((l, l), dtype=C128)
+    for (i, rows, cols), g, sv_ in zip(tags, gv, sv):
+        L = np.zeros((l, l), dtype=C128)
+        L[rows, cols] = cs[i][rows, cols]
+        LL = L.conj().T @ L
+        res.append(np.sqrt(g) * L)
+        Hls += sv_ * LL
+        Am -= 0.5 * np.sqrt(g) ** 2 * LL
+    Am -= 1.0j * Hls
+    return ConstDaviesGenerator(res, Hls, Am, ctx)
+
+
+class ConstHDaviesGenerator:
+    """Constant Hamiltonian with eigen-energies w (GapIndices fixed at construction), couplings given in the
+    eigenbasis (possibly s-dependent).  (D)(du, ρ, _, s) ACCUMULATES the Davies terms of ρ in that basis."""
+
+    def __init__(self, w, coupling, gamma, S, digits=8, sigdigits=8, ctx: Optional[Context] = None):
+        self.w = np.ascontiguousarray(np.real(w), dtype=np.float64)
+        self.coupling = coupling if callable(coupling) else (lambda s, c=[np.asarray(m, dtype=C128) for m in coupling]: c)
+        self.gamma, self.S = gamma, S
+        self.groups = GapGroups(self.w, digits, sigdigits)
+        self.ctx = ctx or get_context()
+        self._ame, self._key = None, None
+
+    def _plan(self, s):
+        if self._ame is not None and self._key == s:
+            return self._ame
+        lib, ctx = self.ctx.lib, self.ctx
+        if self._ame is not None:
+            lib.oqb_ame_destroy(self._ame)
+        coup = [np.asarray(m, dtype=C128) for m in self.coupling(s)]
+        l = len(self.w)
+        h = C.c_void_p()
+        cbuf = _colmajor_stack(coup)  # keep the buffer alive across the call
+        ctx.check(lib.oqb_ame_create(ctx.h, l, l, len(coup), cbuf.ctypes.data, C.byref(h)))
+        ctx.check(lib.oqb_ame_set_eigen(h, _lib.dptr(self.w), None))
+        gam, Sm, crate, lrs = self.groups.tables(self.gamma, self.S)
+        gam, Sm = np.ascontiguousarray(gam.T), np.ascontiguousarray(Sm.T)
+        ci, li = np.ascontiguousarray(self.groups.cross_idx), np.ascontiguousarray(self.groups.lamb_idx)
+        ctx.check(lib.oqb_ame_set_davies(
+            h, _lib.dptr(gam), _lib.dptr(Sm), len(ci), ci.ctypes.data_as(_lib.c_i32p) if len(ci) else None,
+            _lib.dptr(crate) if len(ci) else None, len(li), li.ctypes.data_as(_lib.c_i32p) if len(li) else None,
+            _lib.dptr(lrs) if len(li) else None))
+        self._ame, self._key = h, s
+        return h
+
+    def __call__(self, du, rho, _unused, s):
+        io = _HostIO(rho, du)
+        self.ctx.check(self.ctx.lib.oqb_ame_eig_acc(self._plan(float(s)), io.u.B, io.u.ptr, io.du.ptr, 0))
+        return io.finish()
+
+
+class FluctuatorLiouvillian:
+    """coupling: K constant matrices (unit-scaled); n: noise values, (K,) shared or (B, K) one realisation per member
+    (each trajectory of a stochastic ensemble carries its own fluctuator state)."""
+
+    def __init__(self, coupling: Sequence[np.ndarray], n, ctx: Optional[Context] = None):
+        self.mats = [np.asarray(m, dtype=C128) for m in coupling]
+        self.n = np.atleast_2d(np.asarray(n, dtype=np.float64))
+        self.ctx = ctx or get_context()
+        h = C.c_void_p()
+        mbuf = _colmajor_stack(self.mats)  # keep the buffer alive across the call
+        self.ctx.check(self.ctx.lib.oqb_dense_create(self.ctx.h, self.mats[0].shape[0], len(self.mats),
+                                                     mbuf.ctypes.data, 0, None, C.byref(h)))
+        self._op = h
+
+    def _coef(self, B):
+        n = np.ascontiguousarray(self.n)
+        if n.shape[0] not in (1, B):
+            raise ValueError("noise values must be (K,) or (B, K)")
+        return n, int(n.shape[0] == 1)
+
+    def __call__(self, du, u, p, t):
+        """(F::FluctuatorLiouvillian)(du,u,p,t) :25-31 — OVERWRITES du."""
+        io = _HostIO(u, du)
+        cf, shared = self._coef(io.u.B)
+        self.ctx.check(self.ctx.lib.oqb_dense_rhs(self._op, io.u.B, _lib.dptr(cf), shared, None, 1, io.u.ptr, io.du.ptr))
+        return io.finish()
+
+    def update_cache(self, cache, p, t):
+        """update_cache!(cache, F, p, t) :34-37 — ACCUMULATES −iΣ n_i c_i."""
+        io = _HostIO(cache, cache)
+        cf, shared = self._coef(io.u.B)
+        tmp = io.u.zeros_like()
+        self.ctx.check(self.ctx.lib.oqb_dense_update_cache(self._op, io.u.B, _lib.dptr(cf), shared, None, 1, tmp.ptr))
+        _axpy(self.ctx, tmp, io.du)
+        return io.finish()
+
+    def update_vectorized_cache(self, cache, p, t):
+        """update_vectorized_cache!(cache, F, p, t) :39-44 — ACCUMULATES i(Hᵀ⊗I − I⊗H)."""
+        io = _HostIO(cache, cache)
+        cf, shared = self._coef(io.u.B)
+        tmp = io.u.zeros_like()
+        self.ctx.check(self.ctx.lib.oqb_dense_update_vectorized_cache(self._op, io.u.B, _lib.dptr(cf), shared, tmp.ptr))
+        _axpy(self.ctx, tmp, io.du)
+        return io.finish()

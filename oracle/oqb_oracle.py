@@ -752,6 +752,89 @@ class DiffEqLiouvillian:
         return cache
 
 
+class ConstDaviesGenerator:
+    """src/opensys/davies.jl:102-119: precomputed Lindblad operators, Lamb-shift Hamiltonian and DiffEq operator."""
+
+    def __init__(self, Linds, Hls, A):
+        self.Linds, self.Hls, self.A = Linds, Hls, A
+
+    def rhs_acc(self, du, rho):  # :111-117 — ACCUMULATES
+        for L in self.Linds:
+            LL = L.conj().T @ L
+            du += L @ rho @ L.conj().T - 0.5 * (LL @ rho + rho @ LL)
+        du -= 1.0j * (self.Hls @ rho - rho @ self.Hls)
+        return du
+
+    def update_cache_acc(self, cache):  # :119
+        cache += self.A
+        return cache
+
+
+def build_const_davies(cs, gap_idx: GapIndices, gamma, S) -> ConstDaviesGenerator:
+    """src/opensys/davies.jl:173-209 for constant couplings `cs` (list of matrices in the eigenbasis)."""
+    l = gap_idx.get_lvl()
+    res = []
+    Hls = np.zeros((l, l), dtype=C128)
+    Am = np.zeros((l, l), dtype=C128)
+    for (w, a, b) in gap_idx.positive_gap_indices():
+        gp, gm = np.sqrt(gamma(w)), np.sqrt(gamma(-w))
+        Sp, Sm = S(w), S(-w)
+        for c in cs:
+            Lp, Lm = _sparse_pick(c, a, b, l), _sparse_pick(c, b, a, l)
+            LLp, LLm = Lp.conj().T @ Lp, Lm.conj().T @ Lm
+            res.append(gp * Lp)
+            res.append(gm * Lm)
+            Hls += Sp * LLp + Sm * LLm
+            Am -= 0.5 * gp ** 2 * LLp + 0.5 * gm ** 2 * LLm
+    g0, S0 = np.sqrt(gamma(0)), S(0)
+    a, b = gap_idx.zero_gap_indices()
+    for c in cs:
+        L = _sparse_pick(c, a, b, l)
+        LL = L.conj().T @ L
+        res.append(g0 * L)
+        Hls += S0 * LL
+        Am -= 0.5 * g0 ** 2 * LL
+    Am -= 1.0j * Hls
+    return ConstDaviesGenerator(res, Hls, Am)
+
+
+class ConstHDaviesGenerator:
+    """src/opensys/davies.jl:121-163: constant Hamiltonian (fixed GapIndices), time-dependent couplings given in
+    the eigenbasis; the RHS is the literal gap loop on ρ in that basis."""
+
+    def __init__(self, gap_idx, coupling, gamma, S):
+        self.gap_idx = gap_idx
+        self.D = DaviesGenerator(coupling, gamma, S)
+
+    def rhs_acc(self, du, rho, s):
+        return self.D.rhs_acc(du, rho, self.gap_idx, None, s)
+
+
+class FluctuatorLiouvillian:
+    """src/opensys/stochastic.jl:11-44 (RHS and caches only; the flip process `next_state!` is host control)."""
+
+    def __init__(self, coupling, n):
+        self.coupling = coupling if callable(coupling) else (lambda s, c=list(coupling): c)
+        self.n = np.asarray(n, dtype=np.float64)
+
+    def _H(self, s):
+        return sum(x * c for x, c in zip(self.n, self.coupling(s)))
+
+    def rhs(self, u, p, t):  # :25-31 — OVERWRITES (`du .= …`)
+        H = self._H(p(t))
+        return -1.0j * (H @ u - u @ H)
+
+    def update_cache_acc(self, cache, p, t):  # :34-37
+        cache += -1.0j * self._H(p(t))
+        return cache
+
+    def update_vectorized_cache_acc(self, cache, p, t):  # :39-44
+        H = self._H(p(t))
+        iden = np.eye(H.shape[0], dtype=C128)
+        cache += 1.0j * (np.kron(H.T, iden) - np.kron(iden, H))
+        return cache
+
+
 def ame_jump(D: DaviesGenerator, u, gap_idx: GapIndices, v, s, r: float):
     """src/opensys/trajectory_jump.jl:14-51, literal: one (L₊, L₋) pair per (positive gap group, coupling), then the
     zero-gap group per coupling; `sample(tag, Weights(prob))` with the uniform r.  Returns (choice, prob, v·√g·L·v')."""

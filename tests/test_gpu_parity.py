@@ -586,3 +586,72 @@ def test_ame_jump_vs_oracle(Q, nq, lvl, K):
         + F.two_local_term(list(rng.standard_normal(nq - 1)), [[i, i + 1] for i in range(1, nq)], nq)
     coup = [F.single_clause(["z"], [k + 1], 1.0, nq) for k in range(K)]
     _ame_jump_case(Q, [Hd, Hp], coup, lvl, 0.6, 9, rng, gamma)
+
+
+# ---------------------------------------------------------------------------------------------
+# ConstDaviesGenerator / ConstHDaviesGenerator / FluctuatorLiouvillian
+#   (reference src/opensys/davies.jl:102-209, src/opensys/stochastic.jl:25-44; test/opensys/davies.jl:68-88)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("nq,K,degenerate", [(2, 1, True), (3, 2, False)])
+def test_const_davies_generators(Q, nq, K, degenerate):
+    from oqb_b200.extra_liouvillians import ConstDaviesGenerator, ConstHDaviesGenerator, build_const_davies
+    rng = np.random.default_rng(500 + nq)
+    n = 2 ** nq
+    if degenerate:  # the reference's constant test Hamiltonian: standard_driver(2) + alt_sec_chain(1, 0.5, 1, 2)
+        Hc = F.standard_driver(2) + 0.5 * np.kron(sz, sz)  # symmetric → degenerate gaps → multi-pair groups
+    else:
+        a = rand_c(rng, n, n)
+        Hc = (a + a.conj().T) / 2
+    w, v = np.linalg.eigh(Hc)
+    w = 2 * np.pi * w
+    coup = [2 * np.pi * F.single_clause(["z"], [k + 1], 1.0, nq) for k in range(K)]
+    if degenerate:
+        coup = [2 * np.pi * F.q_translate("ZI+IZ")]
+    cs = [v.conj().T @ c @ v for c in coup]
+    G = O.build_gap_indices(w, 8, 8)
+    Do = O.build_const_davies(cs, G, gamma, lamb)
+    Dg = build_const_davies(cs, w, gamma, lamb)
+    assert len(Dg.Linds) == len(Do.Linds)
+    assert relerr(Dg.A, Do.A) < 1e-14 and relerr(Dg.Hls, Do.Hls) < 1e-14
+    nb = 3
+    rho = rand_rho(rng, nb, n)
+    du0 = rand_c(rng, nb, n, n)
+    got = Dg(du0.copy(), rho, None, None)
+    ref = np.stack([Do.rhs_acc(du0[b].copy(), rho[b]) for b in range(nb)])
+    assert relerr(got, ref) < TOL
+    c0 = rand_c(rng, n, n)
+    assert relerr(Dg.update_cache(c0.copy()), Do.update_cache_acc(c0.copy())) < 1e-14
+    # constant H, couplings re-evaluated per call: closed-form tables in the fixed basis vs the literal gap loop
+    Hg = ConstHDaviesGenerator(w, lambda s: [(1 + s) * c for c in cs], gamma, lamb)
+    Ho = O.ConstHDaviesGenerator(G, lambda s: [(1 + s) * c for c in cs], gamma, lamb)
+    got = Hg(du0.copy(), rho, None, 0.3)
+    ref = np.stack([Ho.rhs_acc(du0[b].copy(), rho[b], 0.3) for b in range(nb)])
+    assert relerr(got, ref) < TOL
+    # and ConstDavies == ConstHDavies at s = 0 (same generator, two code paths in the reference)
+    assert relerr(Dg(np.zeros_like(rho), rho, None, None), Hg(np.zeros_like(rho), rho, None, 0.0)) < 1e-12
+
+
+def test_fluctuator_liouvillian(Q):
+    from oqb_b200.extra_liouvillians import FluctuatorLiouvillian
+    rng = np.random.default_rng(9)
+    nq, nb = 3, 4
+    n = 2 ** nq
+    coup = [2 * np.pi * F.single_clause(["z"], [k + 1], 1.0, nq) for k in range(nq)]
+    nvals = rng.choice([-1.0, 1.0], (nb, nq)) * rng.random((nb, nq))
+    p = O.ODEParams(None, 1.0)
+    u = rand_rho(rng, nb, n)
+    Fg = FluctuatorLiouvillian(coup, nvals)
+    got = Fg(rand_c(rng, nb, n, n), u, None, 0.5)  # overwrites du
+    ref = np.stack([O.FluctuatorLiouvillian(coup, nvals[b]).rhs(u[b], p, 0.5) for b in range(nb)])
+    assert relerr(got, ref) < TOL
+    c0 = rand_c(rng, nb, n, n)
+    got = Fg.update_cache(c0.copy(), None, 0.5)
+    ref = np.stack([O.FluctuatorLiouvillian(coup, nvals[b]).update_cache_acc(c0[b].copy(), p, 0.5) for b in range(nb)])
+    assert relerr(got, ref) < 1e-14
+    v0 = rand_c(rng, nb, n * n, n * n)
+    got = Fg.update_vectorized_cache(v0.copy(), None, 0.5)
+    ref = np.stack([O.FluctuatorLiouvillian(coup, nvals[b]).update_vectorized_cache_acc(v0[b].copy(), p, 0.5) for b in range(nb)])
+    assert relerr(got, ref) < 1e-14
+    # shared noise values
+    Fs = FluctuatorLiouvillian(coup, nvals[0])
+    assert relerr(Fs(np.zeros_like(u), u, None, 0.5)[1], O.FluctuatorLiouvillian(coup, nvals[0]).rhs(u[1], p, 0.5)) < TOL
