@@ -293,6 +293,25 @@ def main():
                 "kernel_share_of_step": zg_ms.value / ms_total if ms_total > 0 else None,
                 "algorithmic_flops_per_launch": zg_fl.value / max(zg_n.value, 1)}
 
+    # ---- cost of a NEW eigen-system per call (time-dependent H: the reference diagonalises in every RHS call,
+    #      src/opensys/diffeq_liouvillian.jl:94-96); shared by the whole batch, reported next to the resident number ----
+    prep = {}
+    for mode in ("host_lapack", "device_eigh"):
+        op.device_eigh = mode == "device_eigh"
+        best = 1e9
+        for k in range(2):
+            s_k = S_POINT + 0.01 * (k + 1) + (0.005 if op.device_eigh else 0.0)
+            t0 = time.perf_counter()
+            op._prepare_ame(s_k)
+            ctx.sync()
+            best = min(best, time.perf_counter() - t0)
+        prep[mode + "_s"] = best
+        prep["evals_per_sec_incl_" + mode] = BATCH / (ms_total / args.steps * 1e-3 + best)
+    prep["what"] = ("haml_eigs (H(s) assembly + Hermitian eigensolver) + GapIndices grouping + γ/S tables + coupling rotation for one "
+                    "new s, shared by the 64-ρ batch; host_lapack = scipy zheevd on the host cores, device_eigh = "
+                    "oqb_dense_hamiltonian + cuSOLVER (torch.linalg.eigh) + oqb_ame_set_eigen_device")
+    op.device_eigh = False
+
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         cval, cms, cores = cpu_reference_arm(2, 1)
@@ -305,7 +324,7 @@ def main():
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": BATCH * N * N * 16, "d2h_bytes_per_step": BATCH * N * N * 16,
                     "steps": e2e_steps, "max_abs_diff_vs_resident": e2e_check},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
-            "setup_s_not_timed": setup_s, "obs_allreduce_ms": obs_ms}
+            "setup_s_not_timed": setup_s, "per_call_eigensystem": prep, "obs_allreduce_ms": obs_ms}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -162,6 +162,9 @@ int oqb_ame_destroy(oqb_ame* ame);
  * h_v NULL ⇒ adiabatic frame (v = I, n == lvl).  Rotates the couplings on the device
  * (src/opensys/davies.jl:24). */
 int oqb_ame_set_eigen(oqb_ame* ame, const double* h_w, const void* h_v);
+/* same with (w, v) already in device memory — e.g. straight out of a device eigensolver (cuSOLVER Zheevd), so that
+ * the n×lvl eigenvector matrix never crosses PCIe; only w (lvl doubles) goes back for the host's gap grouping. */
+int oqb_ame_set_eigen_device(oqb_ame* ame, const double* d_w, const void* d_v);
 /* Davies generator tables (src/opensys/davies.jl:21-47, closed form of SURVEY App. A.5):
  *  h_gam[a+b*lvl] = γ(ω̃_ab), h_S[a+b*lvl] = S(ω̃_ab) at the signed ROUNDED gaps of GapIndices
  *  (src/opensys/opensys_util.jl:25-61; 0 inside the zero group), evaluated by the host closures.

@@ -55,6 +55,7 @@ SIGNATURES = {
     "oqb_ame_create": [c_void_p, c_int, c_int, c_int, c_void_p, C.POINTER(c_void_p)],
     "oqb_ame_destroy": [c_void_p],
     "oqb_ame_set_eigen": [c_void_p, c_dp, c_void_p],
+    "oqb_ame_set_eigen_device": [c_void_p, c_void_p, c_void_p],
     "oqb_ame_set_davies": [c_void_p, c_dp, c_dp, c_i64, c_i32p, c_dp, c_i64, c_i32p, c_dp],
     "oqb_ame_clear_davies": [c_void_p],
     "oqb_ame_set_onesided": [c_void_p, c_int, c_i32p, c_i32p, c_dp, c_dp, c_int],

@@ -219,21 +219,22 @@ int oqb_ame_destroy(oqb_ame* a) {
     return OQB_OK;
 }
 
-int oqb_ame_set_eigen(oqb_ame* a, const double* h_w, const void* h_v) {
+static int set_eigen_impl(oqb_ame* a, const double* w, const void* v, bool on_device, const char* who) {
     oqb_ctx* c = a->ctx;
-    if (!h_w) return set_error(c, OQB_EINVAL, "oqb_ame_set_eigen: null w");
+    if (!w) return set_error(c, OQB_EINVAL, "%s: null w", who);
     const int n = a->n, l = a->lvl, K = a->K;
     const long long nn = (long long)n * n, ll = (long long)l * l, ln = (long long)l * n;
-    if (!h_v && l != n) return set_error(c, OQB_EINVAL, "oqb_ame_set_eigen: adiabatic frame needs lvl == n");
+    if (!v && l != n) return set_error(c, OQB_EINVAL, "%s: adiabatic frame needs lvl == n", who);
+    const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
     // tables of a previous eigen-system are stale
     a->have_eigen = false;
     OQB_TRY(oqb_ame_clear_davies(a));
     OQB_TRY(oqb_ame_clear_onesided(a));
     OQB_TRY(oqb_ame_clear_jump(a));
-    OQB_CUDA(c, cudaMemcpyAsync(a->d_w, h_w, l * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-    a->has_v = h_v != nullptr;
+    OQB_CUDA(c, cudaMemcpyAsync(a->d_w, w, l * sizeof(double), kind, c->stream));
+    a->has_v = v != nullptr;
     if (a->has_v) {
-        OQB_CUDA(c, cudaMemcpyAsync(a->d_V, h_v, (size_t)ln * sizeof(c128), cudaMemcpyHostToDevice, c->stream));
+        OQB_CUDA(c, cudaMemcpyAsync(a->d_V, v, (size_t)ln * sizeof(c128), kind, c->stream));
         if (K) {  // A_α = v' c_α v   (src/opensys/davies.jl:24)
             OQB_TRY(ws_reserve(c, (size_t)K * ln * sizeof(c128)));
             c128* T = (c128*)c->ws;
@@ -254,9 +255,17 @@ int oqb_ame_set_eigen(oqb_ame* a, const double* h_w, const void* h_v) {
     } else if (K) {
         OQB_CUDA(c, cudaMemcpyAsync(a->d_A, a->d_coup, (size_t)K * nn * sizeof(c128), cudaMemcpyDeviceToDevice, c->stream));
     }
-    OQB_CUDA(c, cudaStreamSynchronize(c->stream));  // h_w / h_v may be reused by the caller
+    OQB_CUDA(c, cudaStreamSynchronize(c->stream));  // w / v may be reused by the caller
     a->have_eigen = true;
     return davies_tables(c, l, K, a->d_A, nullptr, nullptr, a->d_w, 0, nullptr, nullptr, nullptr, a->d_Cm);
+}
+
+int oqb_ame_set_eigen(oqb_ame* a, const double* h_w, const void* h_v) {
+    return set_eigen_impl(a, h_w, h_v, false, "oqb_ame_set_eigen");
+}
+
+int oqb_ame_set_eigen_device(oqb_ame* a, const double* d_w, const void* d_v) {
+    return set_eigen_impl(a, d_w, d_v, true, "oqb_ame_set_eigen_device");
 }
 
 int oqb_ame_set_davies(oqb_ame* a, const double* h_gam, const double* h_S, int64_t ncross, const int32_t* h_cross_idx,

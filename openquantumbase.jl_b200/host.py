@@ -433,6 +433,24 @@ def haml_eigs(H, s: float, lvl: Optional[int]):
     return sla.eigh(h, subset_by_index=[0, lvl - 1])
 
 
+def haml_eigs_device(H: "DenseHamiltonian", s: float, lvl: Optional[int]):
+    """haml_eigs with H(s) assembled AND diagonalised on the GPU: `oqb_dense_hamiltonian`, then the
+    library eigensolver (cuSOLVER Zheevd through torch.linalg.eigh — what CUSOLVER.jl's `heevd!` is on the Julia side).
+    Returns (w on the host — the gap grouping needs it —, w on the device, V on the device as the column-major n×lvl
+    matrix `oqb_ame_set_eigen_device` takes)."""
+    import torch
+    n = H.size[0]
+    out = DeviceBatch(1, n, n, H.ctx)
+    cf = _coef(H.f, _svec(s, 1))
+    H.ctx.check(H.ctx.lib.oqb_dense_hamiltonian(H._dense_op(), 1, _lib.dptr(cf), 1, out.ptr))
+    # out.t[0] is H column-major = Hᵀ row-major = conj(H): same eigenvalues, conjugated eigenvectors
+    w, vt = torch.linalg.eigh(out.t[0])
+    l = n if lvl is None else min(lvl, n)
+    vd = vt[:, :l].conj().T.contiguous()  # row j = eigenvector j of H  ⇔  column-major n×l
+    wd = w[:l].contiguous()
+    return wd.cpu().numpy(), wd, vd
+
+
 # --------------------------------------------------------------------------------------------
 # Lindblad
 # --------------------------------------------------------------------------------------------
@@ -683,13 +701,18 @@ class DiffEqLiouvillian:
 
     # ---- {true,false} -------------------------------------------------------------------
     def _prepare_ame(self, s: float, w=None, v=None):
-        """Everything that is shared by the batch for one value of s: eigen-system (host LAPACK, or
-        supplied), gap groups, γ/S tables, device tables."""
+        """Everything that is shared by the batch for one value of s: eigen-system (host LAPACK, the device
+        eigensolver when `self.device_eigh` is set, or supplied), gap groups, γ/S tables, device tables."""
         key = (s, None if w is None else (id(w) if v is not None else tuple(np.asarray(w).tolist())))
         if self._ame is not None and self._ame_s == key:
             return
         lib, ctx = self.ctx.lib, self.ctx
-        if w is None:
+        dev_eig = None
+        if w is None and getattr(self, "device_eigh", False) and isinstance(self.H, DenseHamiltonian):
+            w, wd, vd = haml_eigs_device(self.H, s, self.lvl)
+            dev_eig = (wd, vd)
+            v = vd  # marker: not None
+        elif w is None:
             w, v = haml_eigs(self.H, s, self.lvl)  # :94
         w = np.ascontiguousarray(np.real(w), dtype=np.float64)
         n, lvl = self.H.size[0], len(w)
@@ -704,7 +727,9 @@ class DiffEqLiouvillian:
         h = C.c_void_p()
         cbuf = _colmajor_stack(coup)
         ctx.check(lib.oqb_ame_create(ctx.h, n, lvl, len(coup), cbuf.ctypes.data, C.byref(h)))
-        if v is None:  # adiabatic frame: the state already is in the eigenbasis
+        if dev_eig is not None:
+            ctx.check(lib.oqb_ame_set_eigen_device(h, C.c_void_p(dev_eig[0].data_ptr()), C.c_void_p(dev_eig[1].data_ptr())))
+        elif v is None:  # adiabatic frame: the state already is in the eigenbasis
             ctx.check(lib.oqb_ame_set_eigen(h, _lib.dptr(w), None))
         else:
             vbuf = np.ascontiguousarray(np.asarray(v, dtype=C128).T)  # column-major n×lvl
@@ -748,7 +773,8 @@ class DiffEqLiouvillian:
             else:
                 raise NotImplementedError(f"eigenbasis term {type(lv).__name__} is not on the device path")
         self._ame, self._ame_s = h, key
-        self._w, self._v = w, v
+        self._w, self._v = w, (None if dev_eig is not None else v)
+        self._v_dev = dev_eig[1] if dev_eig is not None else None
 
     def lindblad_jump(self, psi: "DeviceBatch", p, t, uniforms, mask=None, apply=False, w=None, v=None):
         """lindblad_jump(Op::DiffEqLiouvillian{true,false}, u, p, t) src/opensys/trajectory_jump.jl:64-69 → ame_jump
@@ -790,7 +816,10 @@ class DiffEqLiouvillian:
         L = np.zeros((l, l), dtype=C128)
         L[rows, cols] = A_eig[i][rows, cols]
         L *= np.sqrt(self._jump_rate[slot])
-        v = self._v if self._v is not None else np.eye(l, dtype=C128)
+        if getattr(self, "_v_dev", None) is not None:
+            v = self._v_dev.cpu().numpy().T  # stored as rows = eigenvectors (column-major n×l)
+        else:
+            v = self._v if self._v is not None else np.eye(l, dtype=C128)
         return v @ L @ v.conj().T
 
     def _rhs_eig(self, du, u, p, t, w=None, v=None):
