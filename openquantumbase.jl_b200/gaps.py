@@ -104,11 +104,16 @@ class GapGroups:
     def tables(self, gamma, S):
         """γ and S evaluated at omega (l×l, column-major flattening is done by the caller) and at the
         cross-term keys."""
-        uniq, inv = np.unique(np.r_[self.omega.ravel(), self.cross_key, self.lamb_key], return_inverse=True)
-        gv = _eval(gamma, uniq)
-        sv = _eval(S, uniq)
         n2 = self.lvl * self.lvl
         nc = len(self.cross_key)
+        if hasattr(gamma, "vectorized") and hasattr(S, "vectorized"):
+            # array-wise closures: evaluating all l² keys directly is cheaper than sorting them for np.unique
+            allk = np.r_[self.omega.ravel(), self.cross_key, self.lamb_key]
+            gv, sv, inv = _eval(gamma, allk), _eval(S, allk), np.arange(allk.size)
+        else:
+            uniq, inv = np.unique(np.r_[self.omega.ravel(), self.cross_key, self.lamb_key], return_inverse=True)
+            gv = _eval(gamma, uniq)
+            sv = _eval(S, uniq)
         gam = gv[inv[:n2]].reshape(self.lvl, self.lvl)
         Sm = sv[inv[:n2]].reshape(self.lvl, self.lvl)
         cross_rate = gv[inv[n2:n2 + nc]]

@@ -131,4 +131,38 @@ function davies_tables(w, γ, S, digits, sigdigits)
     gam, Sm, cross, crate, lamb, lrs
 end
 
+# ------------------------------------------------------------------ Redfield Λ(t) on the device
+# One GK15 evaluation round of the quadgk! call in (R::RedfieldLiouvillian)(du,u,p,t), redfield.jl:46-64, for nseg
+# segments of many integrals at once.  The segment heap (QuadGK's `adapt`) stays in Julia: keep one
+# `DataStructures.BinaryMaxHeap` of (E, a, b, slot) per integral, bisect the worst segment of every unconverged
+# integral, call this once per round, then `oqb_lambda_total` for ‖Λ‖ — see redfield_device.py for the exact loop.
+function lambda_eval!(lam::Ptr{Cvoid}, c::Ptr{Cvoid}, member::Vector{Int32}, coupling::Vector{Int32}, gi::Matrix{Int32},
+                      θ::Matrix{Float64}, ck::Matrix{ComplexF64}, cd::Matrix{ComplexF64}, slot::Vector{Int64})
+    nseg = length(member)                       # gi, θ: 16×nseg (15 nodes + the end time t); ck, cd: 15×nseg
+    E = Vector{Float64}(undef, nseg)
+    check(c, ccall((:oqb_lambda_eval, LIB), Cint,
+                   (Ptr{Cvoid}, Cint, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ptr{Float64}, Ptr{ComplexF64}, Ptr{ComplexF64},
+                    Ptr{Int64}, Ptr{Float64}), lam, nseg, member, coupling, gi, θ, ck, cd, slot, E))
+    E
+end
+
+# ------------------------------------------------------------------ trajectories that never leave HBM
+# nsteps RK4 steps + the jump callback (lindblad_jump, trajectory_jump.jl:71-74) on the device.  coefH / γ are the
+# closures evaluated at the 2·nsteps+1 stage times (nterms × rows × (2nsteps+1) Julia arrays = the C layout).
+function traj_evolve!(sp::Ptr{Cvoid}, c::Ptr{Cvoid}, ψ::DeviceBatch, nsteps::Int, dt::Float64, coefH::Array{Float64,3},
+                      γ::Array{Float64,3}, rng::Ptr{Cvoid}, thr::Ptr{Cvoid}, njumps::Ptr{Cvoid}; step0::Int=0)
+    shared = size(coefH, 2) == 1
+    check(c, ccall((:oqb_traj_evolve, LIB), Cint,
+                   (Ptr{Cvoid}, Cint, Cint, Cdouble, Ptr{Float64}, Cint, Ptr{Float64}, Cint, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid},
+                    Ptr{Cvoid}, Ptr{Cvoid}, Cint, Cint),
+                   sp, ψ.dims[3], nsteps, dt, coefH, shared, γ, shared, ψ.ptr, rng, thr, njumps, C_NULL, 0, step0))
+end
+
+# ------------------------------------------------------------------ lindblad_jump{true,false} (ame_jump) on a ψ batch
+# After oqb_ame_set_eigen / oqb_ame_set_eigen_device: upload the probability-slot tables in the order ame_jump builds
+# its `prob`/`tag` arrays (trajectory_jump.jl:22-44; gaps.py::jump_slots is the sort-based construction), then
+#   ccall((:oqb_ame_jump, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Cvoid}, Ptr{Float64}, Ptr{UInt8}, Ptr{Int32}, Ptr{Float64}, Cint),
+#         ame, B, ψ.ptr, d_uniform, d_mask, d_choice, d_prob, apply)
+# returns the index into `tag` per member; apply = 1 performs ψ ← Lψ/‖Lψ‖ in place.
+
 end # module
