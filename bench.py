@@ -125,6 +125,15 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    # stdout must carry exactly ONE JSON line: libraries (NCCL's version banner, torch warnings) write to fd 1 at the C
+    # level, so the real stdout is kept aside and fd 1 points at stderr for the rest of the run
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+    def emit(obj):
+        real_stdout.write(json.dumps(obj) + "\n")
+        real_stdout.flush()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -146,7 +155,7 @@ def main():
                                            "10 coupling rotations, closed-form Davies, back-transform); numpy/OpenBLAS; Julia unavailable"},
                 "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "note": "steps/warmup clamped so the CPU arm finishes in minutes"}
-        print(json.dumps(line))
+        emit(line)
         return 0
 
     import torch
@@ -325,7 +334,7 @@ def main():
                     "steps": e2e_steps, "max_abs_diff_vs_resident": e2e_check},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
             "setup_s_not_timed": setup_s, "per_call_eigensystem": prep, "obs_allreduce_ms": obs_ms}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
