@@ -175,6 +175,14 @@ int oqb_ame_set_davies(oqb_ame* ame, const double* h_gam, const double* h_S, int
                        const int32_t* h_cross_idx, const double* h_cross_rate, int64_t nlamb,
                        const int32_t* h_lamb_idx, const double* h_lamb_rate_S);
 int oqb_ame_clear_davies(oqb_ame* ame);
+/* General closed-form tables, for generators whose rates are not |A_ab|²γ — CorrelatedDaviesGenerator
+ * (src/opensys/davies.jl:231-296: du += Σ_(α,β) γ_αβ(ω)(L^β ρ L^α' − ½{L^α'L^β, ρ}) − i[H_LS, ρ]) with a
+ * non-degenerate gap structure: the eigenbasis terms become  X = Cm∘ρ̃ + diag(Wᵀ-sum),  X_aa += Σ_b W[a,b]ρ̃_bb, with
+ * complex W.  h_Cm: lvl×lvl complex column-major INCLUDING the Hamiltonian part −i(w_a − w_b); h_Wt_re / h_Wt_im:
+ * Wt[b + a·lvl] = Re/Im W[a,b] (h_Wt_im may be NULL).  The host builds them from the rotated couplings
+ * (oqb_ame_get_rotated_couplings: K lvl×lvl matrices v'A_αv as the device computed them). */
+int oqb_ame_set_tables(oqb_ame* ame, const void* h_Cm, const double* h_Wt_re, const double* h_Wt_im);
+int oqb_ame_get_rotated_couplings(oqb_ame* ame, void* h_A);
 /* One-sided AME (src/opensys/davies.jl:367-379): npairs (α,β) 0-based; tables at the UNROUNDED
  * gap matrix ω_ba[i,j] = w[j]−w[i] (src/opensys/opensys_util.jl:65): h_gam/h_S are lvl×lvl per pair,
  * or one shared table when tables_shared != 0 (SingleFunctionMatrix). */

@@ -58,6 +58,8 @@ SIGNATURES = {
     "oqb_ame_set_eigen_device": [c_void_p, c_void_p, c_void_p],
     "oqb_ame_set_davies": [c_void_p, c_dp, c_dp, c_i64, c_i32p, c_dp, c_i64, c_i32p, c_dp],
     "oqb_ame_clear_davies": [c_void_p],
+    "oqb_ame_set_tables": [c_void_p, c_void_p, c_dp, c_dp],
+    "oqb_ame_get_rotated_couplings": [c_void_p, c_void_p],
     "oqb_ame_set_onesided": [c_void_p, c_int, c_i32p, c_i32p, c_dp, c_dp, c_int],
     "oqb_ame_clear_onesided": [c_void_p],
     "oqb_ame_rhs": [c_void_p, c_int, c_void_p, c_void_p],

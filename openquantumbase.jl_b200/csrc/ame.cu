@@ -45,6 +45,7 @@ int eig_apply(oqb_ame* a, int nb, const c128* R, c128* X, bool overwrite, bool w
     if (a->davies) {
         OQB_TRY(extract_diag(c, l, R, pop, nb));
         OQB_TRY(davies_diag(c, l, a->d_Wt, pop, X, nb));
+        if (a->d_Wt_im) OQB_TRY(davies_diag(c, l, a->d_Wt_im, pop, X, nb, true));
         OQB_TRY(davies_cross(c, l, a->K, a->d_A, a->ncross, a->d_cross_idx, a->d_cross_rate, R, X, nb));
         if (a->d_Moff) {
             ZgemmParams p;  // X += Moff R
@@ -141,6 +142,7 @@ int ame_rhs_impl(oqb_ame* a, int nb, const c128* u, c128* du) {
             if (a->davies) { q.diag_out = scratch; q.strideDiag = l; }
             OQB_TRY(zgemm(c, q));
             if (a->davies) OQB_TRY(davies_diag(c, l, a->d_Wt, scratch, X, cnt));
+            if (a->davies && a->d_Wt_im) OQB_TRY(davies_diag(c, l, a->d_Wt_im, scratch, X, cnt, true));
         } else {
             q.C = R;
             OQB_TRY(zgemm(c, q));
@@ -190,7 +192,7 @@ int oqb_ame_create(oqb_ctx* c, int n, int lvl, int K, const void* h_couplings, o
 
 int oqb_ame_clear_davies(oqb_ame* a) {
     cudaStreamSynchronize(a->ctx->stream);
-    dfree(a->d_gam); dfree(a->d_S); dfree(a->d_Gam); dfree(a->d_hls); dfree(a->d_Wt);
+    dfree(a->d_gam); dfree(a->d_S); dfree(a->d_Gam); dfree(a->d_hls); dfree(a->d_Wt); dfree(a->d_Wt_im);
     dfree(a->d_cross_idx); dfree(a->d_cross_rate); dfree(a->d_Moff);
     a->davies = false; a->ncross = a->nlamb = 0;
     if (a->have_eigen)  // Hamiltonian-only Hadamard coefficients
@@ -266,6 +268,33 @@ int oqb_ame_set_eigen(oqb_ame* a, const double* h_w, const void* h_v) {
 
 int oqb_ame_set_eigen_device(oqb_ame* a, const double* d_w, const void* d_v) {
     return set_eigen_impl(a, d_w, d_v, true, "oqb_ame_set_eigen_device");
+}
+
+int oqb_ame_set_tables(oqb_ame* a, const void* h_Cm, const double* h_Wt_re, const double* h_Wt_im) {
+    oqb_ctx* c = a->ctx;
+    if (!a->have_eigen) return set_error(c, OQB_EINVAL, "oqb_ame_set_tables: call oqb_ame_set_eigen first");
+    if (!h_Cm || !h_Wt_re) return set_error(c, OQB_EINVAL, "oqb_ame_set_tables: null table");
+    OQB_TRY(oqb_ame_clear_davies(a));
+    const size_t ll = (size_t)a->lvl * a->lvl;
+    OQB_TRY(dalloc(c, (void**)&a->d_Wt, ll * sizeof(double)));
+    OQB_CUDA(c, cudaMemcpyAsync(a->d_Wt, h_Wt_re, ll * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    if (h_Wt_im) {
+        OQB_TRY(dalloc(c, (void**)&a->d_Wt_im, ll * sizeof(double)));
+        OQB_CUDA(c, cudaMemcpyAsync(a->d_Wt_im, h_Wt_im, ll * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    }
+    OQB_CUDA(c, cudaMemcpyAsync(a->d_Cm, h_Cm, ll * sizeof(c128), cudaMemcpyHostToDevice, c->stream));
+    OQB_CUDA(c, cudaStreamSynchronize(c->stream));
+    a->davies = true;
+    return 0;
+}
+
+int oqb_ame_get_rotated_couplings(oqb_ame* a, void* h_A) {
+    oqb_ctx* c = a->ctx;
+    if (!a->have_eigen) return set_error(c, OQB_EINVAL, "oqb_ame_get_rotated_couplings: call oqb_ame_set_eigen first");
+    if (!h_A) return set_error(c, OQB_EINVAL, "oqb_ame_get_rotated_couplings: null output");
+    OQB_CUDA(c, cudaMemcpyAsync(h_A, a->d_A, (size_t)a->K * a->lvl * a->lvl * sizeof(c128), cudaMemcpyDeviceToHost, c->stream));
+    OQB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return 0;
 }
 
 int oqb_ame_set_davies(oqb_ame* a, const double* h_gam, const double* h_S, int64_t ncross, const int32_t* h_cross_idx,

@@ -16,6 +16,7 @@ struct oqb_ame {
     // Davies
     bool davies = false;
     double *d_gam = nullptr, *d_S = nullptr, *d_Gam = nullptr, *d_hls = nullptr, *d_Wt = nullptr;
+    double* d_Wt_im = nullptr;  // imaginary part of the rate matrix (general tables: CorrelatedDaviesGenerator)
     long long ncross = 0, nlamb = 0;
     int32_t* d_cross_idx = nullptr;
     double* d_cross_rate = nullptr;

@@ -171,7 +171,7 @@ int axpy_batched(Ctx* c, long long len, int nb, c128 alpha, const c128* x, long 
 int hadamard(Ctx* c, int l, const c128* Cm, const double* w_sub, const c128* R, c128* X, int nb,
              bool accumulate);
 // X[b][a + a*l] += Σ_b' Wt[b' + a*l] * pop[b*l + b']      (Wt real)
-int davies_diag(Ctx* c, int l, const double* Wt, const c128* pop, c128* X, int nb);
+int davies_diag(Ctx* c, int l, const double* Wt, const c128* pop, c128* X, int nb, bool times_i = false);
 // pop[b*l + a] = R[b][a + a*l]
 int extract_diag(Ctx* c, int l, const c128* R, c128* pop, int nb);
 // X[b][i+j*l] += alpha * Σ_{k<nk} (Kb[(b*nk+k)][i+j*l] + conj(Kb[(b*nk+k)][j+i*l]))

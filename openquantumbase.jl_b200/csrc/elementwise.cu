@@ -114,7 +114,7 @@ int extract_diag(Ctx* c, int l, const c128* R, c128* pop, int nb) {
 
 // one warp per (row a, member b): X_aa += Σ_b' Wt[b' + a*l] pop[b']
 __global__ void davies_diag_kernel(int l, const double* __restrict__ Wt, const c128* __restrict__ pop,
-                                   c128* __restrict__ X) {
+                                   c128* __restrict__ X, int times_i) {
     const int b = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int a = blockIdx.x * (blockDim.x >> 5) + warp;
@@ -136,15 +136,20 @@ __global__ void davies_diag_kernel(int l, const double* __restrict__ Wt, const c
     if (lane == 0) {
         c128* d = X + (long long)b * l * l + a + (long long)a * l;
         c128 v = *d;
-        v.x += sr;
-        v.y += si;
+        if (times_i) {  // the imaginary part of a complex rate matrix: i·(sr + i·si)
+            v.x -= si;
+            v.y += sr;
+        } else {
+            v.x += sr;
+            v.y += si;
+        }
         *d = v;
     }
 }
-int davies_diag(Ctx* c, int l, const double* Wt, const c128* pop, c128* X, int nb) {
+int davies_diag(Ctx* c, int l, const double* Wt, const c128* pop, c128* X, int nb, bool times_i) {
     if (nb <= 0) return 0;
     dim3 grid(cdiv(l, 8), nb);
-    davies_diag_kernel<<<grid, 256, 0, c->stream>>>(l, Wt, pop, X);
+    davies_diag_kernel<<<grid, 256, 0, c->stream>>>(l, Wt, pop, X, times_i ? 1 : 0);
     OQB_LAUNCH_CHECK(c);
     return 0;
 }

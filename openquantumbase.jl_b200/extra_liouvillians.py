@@ -121,6 +121,85 @@ class ConstHDaviesGenerator:
         return io.finish()
 
 
+class CorrelatedDaviesGenerator:
+    """src/opensys/davies.jl:220-296 (also ConstHCorrelatedDaviesGenerator :298-345).  coupling: K matrices (or
+    callables of s); gamma, S: dicts keyed by the 1-based (α,β) pairs of `inds` (array-wise closures welcome).
+    Evaluated through the general closed-form tables (`oqb_ame_set_tables`): for a gap structure whose non-zero
+    groups are single pairs,  X = Cm∘ρ̃ + diag(W·diag ρ̃)  with
+        W[a,b]   = Σ_(α,β) γ_αβ(ω_ab)·A_β[a,b]·conj(A_α[a,b])          (a ≠ b)
+        Cm[a,a'] = −i(w_a−w_a') + Σ γ_αβ(0)A_β[a,a]conj(A_α[a',a']) − ½(G_a+G_a') − i(h_a−h_a'),
+        G_b = Σ_a W[a,b] + Σ γ_αβ(0)conj(A_α[b,b])A_β[b,b],   h_b likewise with S.
+    Degenerate gap groups (several pairs per group) are not on the device path."""
+
+    def __init__(self, coupling, gamma, S, inds, digits=8, sigdigits=8, ctx: Optional[Context] = None):
+        self.coupling, self.gamma, self.S = list(coupling), gamma, S
+        self.inds = [tuple(x) for x in inds]
+        self.digits, self.sigdigits = digits, sigdigits
+        self.ctx = ctx or get_context()
+        self._ame, self._key = None, None
+
+    def _plan(self, w, v, s):
+        lib, ctx = self.ctx.lib, self.ctx
+        key = (float(s), tuple(np.asarray(w).tolist()), None if v is None else id(v))
+        if self._ame is not None and self._key == key:
+            return self._ame
+        if self._ame is not None:
+            lib.oqb_ame_destroy(self._ame)
+            self._ame = None
+        coup = [np.asarray(c(s) if callable(c) else c, dtype=C128) for c in self.coupling]
+        w = np.ascontiguousarray(np.real(w), dtype=np.float64)
+        l, n, K = len(w), coup[0].shape[0], len(coup)
+        groups = GapGroups(w, self.digits, self.sigdigits)
+        if len(groups.cross_idx):
+            raise NotImplementedError("CorrelatedDaviesGenerator with degenerate gap groups is not on the device path")
+        h = C.c_void_p()
+        cbuf = _colmajor_stack(coup)
+        ctx.check(lib.oqb_ame_create(ctx.h, n, l, K, cbuf.ctypes.data, C.byref(h)))
+        if v is None:
+            ctx.check(lib.oqb_ame_set_eigen(h, _lib.dptr(w), None))
+        else:
+            vbuf = np.ascontiguousarray(np.asarray(v, dtype=C128).T)
+            ctx.check(lib.oqb_ame_set_eigen(h, _lib.dptr(w), vbuf.ctypes.data))
+        Abuf = np.empty((K, l, l), dtype=C128)
+        ctx.check(lib.oqb_ame_get_rotated_couplings(h, Abuf.ctypes.data))
+        A = Abuf.transpose(0, 2, 1)  # (K, row, col)
+        om = groups.omega
+        off = ~np.eye(l, dtype=bool)
+        W = np.zeros((l, l), dtype=C128)
+        Hoff = np.zeros((l, l), dtype=C128)
+        Z = np.zeros((l, l), dtype=C128)
+        g0d = np.zeros(l, dtype=C128)
+        h0d = np.zeros(l, dtype=C128)
+        zero = np.zeros(1)
+        for (al, be) in self.inds:
+            Aa, Ab = A[al - 1], A[be - 1]
+            prod = Ab * Aa.conj()
+            W += np.where(off, _eval(self.gamma[(al, be)], om.ravel()).reshape(l, l), 0.0) * prod
+            Hoff += np.where(off, _eval(self.S[(al, be)], om.ravel()).reshape(l, l), 0.0) * prod
+            g0 = float(_eval(self.gamma[(al, be)], zero)[0])
+            s0 = float(_eval(self.S[(al, be)], zero)[0])
+            da, db = np.diag(Aa), np.diag(Ab)
+            Z += g0 * np.outer(db, da.conj())
+            g0d += g0 * da.conj() * db
+            h0d += s0 * da.conj() * db
+        G = W.sum(axis=0) + g0d
+        hl = Hoff.sum(axis=0) + h0d
+        Cm = -1j * (w[:, None] - w[None, :]) + Z - 0.5 * (G[:, None] + G[None, :]) - 1j * (hl[:, None] - hl[None, :])
+        cmbuf = np.ascontiguousarray(Cm.T)
+        wre, wim = np.ascontiguousarray(W.real), np.ascontiguousarray(W.imag)
+        ctx.check(lib.oqb_ame_set_tables(h, cmbuf.ctypes.data, _lib.dptr(wre), _lib.dptr(wim)))
+        self._ame, self._key = h, key
+        return h
+
+    def __call__(self, du, rho, w, *args):
+        """(D)(du, ρ, gap_idx, s) — adiabatic frame, ρ in the eigenbasis — or (D)(du, ρ̃, gap_idx, v, s); `w` stands in
+        for the GapIndices argument (its energies).  ACCUMULATES."""
+        v, s = (None, args[0]) if len(args) == 1 else args
+        io = _HostIO(rho, du)
+        self.ctx.check(self.ctx.lib.oqb_ame_eig_acc(self._plan(w, v, s), io.u.B, io.u.ptr, io.du.ptr, 0))
+        return io.finish()
+
+
 class FluctuatorLiouvillian:
     """coupling: K constant matrices (unit-scaled); n: noise values, (K,) shared or (B, K) one realisation per member
     (each trajectory of a stochastic ensemble carries its own fluctuator state)."""

@@ -810,6 +810,44 @@ class ConstHDaviesGenerator:
         return self.D.rhs_acc(du, rho, self.gap_idx, None, s)
 
 
+class CorrelatedDaviesGenerator:
+    """src/opensys/davies.jl:220-296 (and ConstHCorrelatedDaviesGenerator :298-345, same loop on a fixed GapIndices).
+    coupling: list of callables/matrices; gamma, S: dicts keyed by 1-based (α,β); inds: 1-based (α,β) pairs."""
+
+    def __init__(self, coupling, gamma, S, inds):
+        self.coupling, self.gamma, self.S, self.inds = list(coupling), gamma, S, [tuple(x) for x in inds]
+
+    def _c(self, k, s):
+        c = self.coupling[k - 1]
+        return c(s) if callable(c) else c
+
+    def rhs_acc(self, du, rho, gap_idx: GapIndices, v, s):
+        """:231-262 (v=None, adiabatic frame) / :264-296 (rotated by v; the reference writes `V'` for one factor,
+        an undefined name — the intended v' is used here)."""
+        l = du.shape[0]
+        rot = (lambda c: c) if v is None else (lambda c: v.conj().T @ c @ v)
+        Hls = np.zeros((l, l), dtype=C128)
+        for (w, a, b) in gap_idx.positive_gap_indices():
+            for (al, be) in self.inds:
+                gp, gm = self.gamma[(al, be)](w), self.gamma[(al, be)](-w)
+                Aa, Ab = rot(self._c(al, s)), rot(self._c(be, s))
+                Lp, Lpd = _sparse_pick(Ab, a, b, l), _sparse_pick(Aa, a, b, l).conj().T
+                Lm, Lmd = _sparse_pick(Ab, b, a, l), _sparse_pick(Aa, b, a, l).conj().T
+                LLp, LLm = Lpd @ Lp, Lmd @ Lm
+                du += gp * (Lp @ rho @ Lpd - 0.5 * (LLp @ rho + rho @ LLp)) + gm * (Lm @ rho @ Lmd - 0.5 * (LLm @ rho + rho @ LLm))
+                Hls += self.S[(al, be)](w) * LLp + self.S[(al, be)](-w) * LLm
+        a, b = gap_idx.zero_gap_indices()
+        for (al, be) in self.inds:
+            g0 = self.gamma[(al, be)](0)
+            Aa, Ab = rot(self._c(al, s)), rot(self._c(be, s))
+            L, Ld = _sparse_pick(Ab, a, b, l), _sparse_pick(Aa, a, b, l).conj().T
+            LL = Ld @ L
+            du += g0 * (L @ rho @ Ld - 0.5 * (LL @ rho + rho @ LL))
+            Hls += self.S[(al, be)](0) * LL
+        du -= 1.0j * (Hls @ rho - rho @ Hls)
+        return du
+
+
 class FluctuatorLiouvillian:
     """src/opensys/stochastic.jl:11-44 (RHS and caches only; the flip process `next_state!` is host control)."""
 

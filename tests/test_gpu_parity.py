@@ -682,3 +682,40 @@ def test_ame_device_eigensolver(Q):
     opo = O.DiffEqLiouvillian(Ho, [O.DaviesGenerator([2 * np.pi * c for c in coup], gamma, lamb)], [], lvl)
     ref = np.stack([opo.rhs(u[b], O.ODEParams(Ho, 2.0), 0.8) for b in range(nb)])
     assert relerr(d_dev, ref) < 1e-10
+
+
+def test_correlated_davies_generator(Q):
+    """reference test/opensys/davies.jl:173-194 (golden closed forms) + a random non-degenerate 3-qubit case vs the oracle."""
+    from oqb_b200.extra_liouvillians import CorrelatedDaviesGenerator
+    sp_, sm_ = np.array([[0, 1], [0, 0]], dtype=complex), np.array([[0, 0], [1, 0]], dtype=complex)
+    gfun = lambda w: 1.0 if w >= 0 else np.exp(-0.5)
+    zero = lambda w: 0.0
+    gam, S0 = {(1, 2): gfun, (2, 1): gfun}, {(1, 2): zero, (2, 1): zero}
+    w2 = np.array([1.0, 2.0])
+    D = CorrelatedDaviesGenerator([sp_, sm_], gam, S0, ((1, 2), (2, 1)))
+    du = D(np.zeros((2, 2), complex), np.array([[0.5, 0], [0, 0.5]], dtype=complex), w2, 0.5)
+    assert np.allclose(du, 0.0, atol=1e-15)
+    D = CorrelatedDaviesGenerator([sm_, sm_], gam, S0, ((1, 2), (2, 1)))
+    du = D(np.zeros((2, 2), complex), 0.5 * np.ones((2, 2), dtype=complex), w2, 0.5)
+    e = np.exp(-0.5)
+    assert np.allclose(du, [[-e, -0.5 * e], [-0.5 * e, e]], atol=1e-15)
+    # random case: 3 couplings, all ordered pairs, complex couplings, Lamb shift on, with and without v
+    rng = np.random.default_rng(31)
+    n, K, nb = 8, 3, 3
+    a = rand_c(rng, n, n)
+    w, v = np.linalg.eigh((a + a.conj().T) / 2)
+    coup = [rand_c(rng, n, n) for _ in range(K)]
+    inds = [(i, j) for i in range(1, K + 1) for j in range(1, K + 1) if i != j] + [(1, 1)]
+    gd = {pq: (lambda x, c=0.3 * (pq[0] + 2 * pq[1]): gamma(x) * c) for pq in inds}
+    Sd = {pq: (lambda x, c=0.1 * pq[0]: lamb(x) * c) for pq in inds}
+    Dg = CorrelatedDaviesGenerator(coup, gd, Sd, inds)
+    Do = O.CorrelatedDaviesGenerator(coup, gd, Sd, inds)
+    G = O.build_gap_indices(w, 8, 8)
+    rho = rand_c(rng, nb, n, n)
+    du0 = rand_c(rng, nb, n, n)
+    got = Dg(du0.copy(), rho, w, 0.4)
+    ref = np.stack([Do.rhs_acc(du0[b].copy(), rho[b], G, None, 0.4) for b in range(nb)])
+    assert relerr(got, ref) < TOL
+    got = Dg(du0.copy(), rho, w, v, 0.4)
+    ref = np.stack([Do.rhs_acc(du0[b].copy(), rho[b], G, v, 0.4) for b in range(nb)])
+    assert relerr(got, ref) < TOL

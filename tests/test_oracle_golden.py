@@ -328,3 +328,20 @@ def test_c1_single_qubit_ame_anchor():
     assert du[1, 1] == pytest.approx(+0.030394341407546568, rel=1e-10)
     du1 = op.rhs(rho, p, 10.0)
     assert du1[0, 1] == pytest.approx(-0.05195969170118221 - 6.2831853071795845j, rel=1e-10)
+
+
+# ---- test/opensys/davies.jl:173-194 — CorrelatedDaviesGenerator closed forms -----------------------------
+def test_correlated_davies_golden():
+    sp_, sm_ = np.array([[0, 1], [0, 0]], dtype=complex), np.array([[0, 0], [1, 0]], dtype=complex)  # σ₊, σ₋ (math_util.jl:7-8)
+    gfun = lambda w: 1.0 if w >= 0 else np.exp(-0.5)
+    zero = lambda w: 0.0
+    gam = {(1, 2): gfun, (2, 1): gfun}
+    S = {(1, 2): zero, (2, 1): zero}
+    G = O.build_gap_indices(np.array([1.0, 2.0]), 8, 8)
+    D = O.CorrelatedDaviesGenerator([sp_, sm_], gam, S, ((1, 2), (2, 1)))
+    du = D.rhs_acc(np.zeros((2, 2), complex), np.array([[0.5, 0], [0, 0.5]], dtype=complex), G, None, 0.5)
+    assert np.allclose(du, 0.0, atol=1e-15)                                                     # :184
+    D = O.CorrelatedDaviesGenerator([sm_, sm_], gam, S, ((1, 2), (2, 1)))
+    du = D.rhs_acc(np.zeros((2, 2), complex), 0.5 * np.ones((2, 2), dtype=complex), G, None, 0.5)
+    e = np.exp(-0.5)
+    assert np.allclose(du, [[-e, -0.5 * e], [-0.5 * e, e]], atol=1e-15)                         # :194
