@@ -141,19 +141,22 @@ class LambdaBuilder:
 
     # -- the adaptive loop -----------------------------------------------------------------------
     def build(self, member, coupling, t, cfun: Callable, Ta: float, atol: float, rtol: float, maxevals: int = 10 ** 7,
-              out: Optional[DeviceBatch] = None) -> DeviceBatch:
+              out: Optional[DeviceBatch] = None, t_hi=None) -> DeviceBatch:
         """Λ for integrals q = 0..nint-1: schedule member[q], coupling index coupling[q] (0-based j of S_j),
         end time t[q].  cfun(q_idx, t, x) → C(t,x)·f_j(p(x)) evaluated on arrays: q_idx (m,1) integral numbers,
-        t (m,1), x (m,15).  Returns a DeviceBatch of nint n×n matrices (written into `out` when given)."""
+        t (m,1), x (m,15).  Returns a DeviceBatch of nint n×n matrices (written into `out` when given).
+        The integration window is [max(0, t−Ta), t] (Redfield, redfield.jl:60-61) or, with t_hi given,
+        [max(0, t−Ta), t_hi] with U(t) still taken at t (ULE: t_hi = min(t+Ta, tf), lindblad.jl:60-61)."""
         member = np.asarray(member, dtype=np.int32)
         coupling = np.asarray(coupling, dtype=np.int32)
         nint = len(member)
         t = np.broadcast_to(np.asarray(t, dtype=np.float64), (nint,)).copy()
         a0 = np.maximum(0.0, t - Ta)
+        hi = t if t_hi is None else np.broadcast_to(np.asarray(t_hi, dtype=np.float64), (nint,)).copy()
         Lam = out if out is not None else DeviceBatch(nint, self.n, self.n, self.ctx)
         import torch
         scratch = DeviceBatch(nint, self.n, self.n, self.ctx)  # totals of the active integrals during refinement
-        live = np.nonzero(a0 < t)[0]  # a == b ⇒ Λ = 0 (quadgk returns zero(f(a)))
+        live = np.nonzero(a0 < hi)[0]  # a == b ⇒ Λ = 0 (quadgk returns zero(f(a)))
         if len(live) < nint:
             Lam.t.zero_()
         if len(live) == 0:
@@ -161,8 +164,8 @@ class LambdaBuilder:
         self.ctx.check(self.ctx.lib.oqb_lambda_reserve_slots(self.h, 2 * nint))
         next_slot = nint
         cv = lambda qs: (lambda x: np.asarray(cfun(qs[:, None], t[qs][:, None], x), dtype=C128))
-        E0 = self._eval(member[live], coupling[live], a0[live], t[live], t[live], cv(live), live.astype(np.int64))
-        heaps = {int(q): [(-float(e), 0, float(a0[q]), float(t[q]), int(q), float(e))] for q, e in zip(live, E0)}
+        E0 = self._eval(member[live], coupling[live], a0[live], hi[live], t[live], cv(live), live.astype(np.int64))
+        heaps = {int(q): [(-float(e), 0, float(a0[q]), float(hi[q]), int(q), float(e))] for q, e in zip(live, E0)}
         Etot = {int(q): float(e) for q, e in zip(live, E0)}
         evals = {int(q): 15 for q in live}
         tick = {int(q): 1 for q in live}
@@ -206,3 +209,44 @@ class LambdaBuilder:
         self.stats = {"rounds": rounds, "segments_evaluated": nseg_total, "integrals": nint,
                       "max_evals": max(evals.values()), "E_max": max(Etot.values())}
         return Lam
+
+
+class ULELiouvillianDevice:
+    """(L::ULELiouvillian)(du, u, p, t), reference src/opensys/lindblad.jl:41-69, for nb schedules at once:
+    LO_b = Σ_(i,j) Λ_ij (built on the device: window [max(0,t−Ta), min(t+Ta, tf)], U(t) at t), then
+    du_b += LO_b u_b LO_b† − ½(LO_b†LO_b u_b + u_b LO_b†LO_b) as five batched ZGEMMs.
+    pairs: 1-based (i,j) index pairs; cfun(q, t, x) as in LambdaBuilder.build with q numbering (member, pair)."""
+
+    def __init__(self, builder: LambdaBuilder, pairs, Ta: float, atol: float, rtol: float):
+        self.lb, self.pairs, self.Ta, self.atol, self.rtol = builder, [tuple(x) for x in pairs], Ta, atol, rtol
+
+    def LO(self, t, tf, cfun) -> DeviceBatch:
+        lb, P = self.lb, len(self.pairs)
+        member = np.repeat(np.arange(lb.nb), P)
+        coupling = np.tile(np.array([j - 1 for (_, j) in self.pairs]), lb.nb)
+        tt = np.broadcast_to(np.asarray(t, dtype=np.float64), (lb.nb,))[member]
+        tfv = np.broadcast_to(np.asarray(tf, dtype=np.float64), (lb.nb,))[member]
+        Lam = lb.build(member, coupling, tt, cfun, self.Ta, self.atol, self.rtol, t_hi=np.minimum(tt + self.Ta, tfv))
+        LO = DeviceBatch(lb.nb, lb.n, lb.n, lb.ctx)
+        nn, one = lb.n * lb.n, np.array([1.0, 0.0])
+        for k in range(P):  # axpy!(1.0, Λ, LO), lindblad.jl:65
+            lb.ctx.check(lb.ctx.lib.oqb_axpy_batched(lb.ctx.h, nn, lb.nb, _lib.dptr(one), C.c_void_p(Lam.t.data_ptr() + 16 * nn * k),
+                                                     P * nn, LO.ptr))
+        return LO
+
+    def __call__(self, du: DeviceBatch, u: DeviceBatch, t, tf, cfun):
+        """ACCUMULATES into du (device batches of nb n×n matrices)."""
+        lb = self.lb
+        ctx, n, nb = lb.ctx, lb.n, lb.nb
+        LO = self.LO(t, tf, cfun)
+        T1, M = u.zeros_like(), u.zeros_like()
+        nn = n * n
+        one, zero, mh = np.array([1.0, 0.0]), np.array([0.0, 0.0]), np.array([-0.5, 0.0])
+        g = lambda opA, opB, al, A, B_, be, C_: ctx.check(ctx.lib.oqb_zgemm_batched(
+            ctx.h, opA, opB, n, n, n, _lib.dptr(al), A.ptr, n, nn, B_.ptr, n, nn, _lib.dptr(be), C_.ptr, n, nn, nb))
+        g(0, 0, one, LO, u, zero, T1)     # T1 = LO u
+        g(0, 2, one, T1, LO, one, du)     # du += T1 LO†
+        g(2, 0, one, LO, LO, zero, M)     # M = LO† LO
+        g(0, 0, mh, M, u, one, du)        # du −= ½ M u
+        g(0, 0, mh, u, M, one, du)        # du −= ½ u M
+        return du

@@ -655,6 +655,35 @@ class RedfieldLiouvillian:
         return cache
 
 
+class ULELiouvillian:
+    """src/opensys/lindblad.jl:10-69: LO = Σ_(i,j) ∫_{max(0,t−Ta)}^{min(t+Ta,tf)} C_ij(t,x) U(t)U(x)† S_j(p(t)) U(x)U(t)† dx
+    (the coupling is evaluated at s = p(t), :50), du += LO u LO† − ½{LO†LO, u}."""
+
+    def __init__(self, kernels, unitary, Ta, atol, rtol):
+        self.kernels, self.unitary, self.Ta, self.atol, self.rtol = kernels, unitary, Ta, atol, rtol
+
+    def LO(self, p, t):
+        s = p(t)
+        LO = None
+        for (inds, coupling, cfun) in self.kernels:
+            for (i, j) in inds:
+                cf = cfun[(i, j)] if isinstance(cfun, dict) else cfun
+                Sj = RedfieldLiouvillian._coup(coupling, j, s)
+
+                def integrand(x, cf=cf, Sj=Sj):
+                    W = self.unitary(t) @ self.unitary(x).conj().T
+                    return cf(t, x) * (W @ (Sj @ W.conj().T))
+                Lam, _ = quadgk(integrand, max(0.0, t - self.Ta), min(t + self.Ta, p.tf), self.rtol, self.atol)
+                LO = Lam if LO is None else LO + Lam
+        return LO
+
+    def rhs_acc(self, du, u, p, t):
+        LO = self.LO(p, t)
+        LL = LO.conj().T @ LO
+        du += LO @ u @ LO.conj().T - 0.5 * (LL @ u + u @ LL)
+        return du
+
+
 def redfield_apply_acc(du, u, S_list, Lam_list):
     """The ρ-dependent half of redfield.jl:65-68 with Λ supplied: du −= K₂+K₂†."""
     for SS, Lam in zip(S_list, Lam_list):

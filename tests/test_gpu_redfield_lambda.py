@@ -145,3 +145,37 @@ def test_lambda_feeds_redfield_rhs(Q):
         red = O.RedfieldLiouvillian([(tuple((j + 1, j + 1) for j in range(K)), Ss, cf)], SampledUnitary(Us[b], dt), tf, 1e-9, 1e-7)
         ref = red.rhs_acc(np.zeros((n, n), complex), rho[b], p, tf)
         assert relerr(got[b], ref) < 1e-12
+
+
+def test_ule_liouvillian(Q):
+    """ULELiouvillian (src/opensys/lindblad.jl:41-69; reference test test/opensys/lindblad.jl:3-19) for a batch of
+    schedules: Λ window [max(0,t−Ta), min(t+Ta,tf)], LO = ΣΛ_ij, du += LO u LO† − ½{LO†LO, u}."""
+    from oqb_b200.redfield_device import LambdaBuilder, SampledUnitary, ULELiouvillianDevice
+    rng = np.random.default_rng(5)
+    n, nb, K, G, tf = 8, 4, 2, 129, 3.0
+    Us = []
+    for b in range(nb):
+        A = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))
+        u_, dt = sample_unitary((A + A.conj().T) / 4, tf, G)
+        Us.append(u_)
+    Us = np.stack(Us)
+    Ss = [np.diag(rng.choice([-1.0, 1.0], n)).astype(complex) for _ in range(K)]
+    cf = lambda t, x: np.exp(-0.8 * np.abs(t - x)) * np.exp(0.5j * (t - x))
+    Ta, t = 1.0, 2.4  # the window [1.4, 3.0] is clipped by tf
+    pairs = [(1, 1), (2, 2), (1, 2)]
+    lb = LambdaBuilder(Ss, Us, dt)
+    ule = ULELiouvillianDevice(lb, pairs, Ta, 1e-10, 1e-8)
+    rho = []
+    for b in range(nb):
+        g = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))
+        r = g @ g.conj().T
+        rho.append(r / np.trace(r).real)
+    rho = np.stack(rho)
+    du0 = rng.standard_normal((nb, n, n)) + 1j * rng.standard_normal((nb, n, n))
+    u, du = Q.DeviceBatch.from_host(rho), Q.DeviceBatch.from_host(du0)
+    ule(du, u, t, tf, lambda q, tt, x: cf(tt, x))
+    got = du.to_host()
+    p = O.ODEParams(None, tf, lambda tf_, t_: t_ / tf_)
+    for b in range(nb):
+        ref = O.ULELiouvillian([(tuple(pairs), Ss, cf)], SampledUnitary(Us[b], dt), Ta, 1e-10, 1e-8).rhs_acc(du0[b].copy(), rho[b], p, t)
+        assert relerr(got[b], ref) < 1e-12

@@ -345,3 +345,16 @@ def test_correlated_davies_golden():
     du = D.rhs_acc(np.zeros((2, 2), complex), 0.5 * np.ones((2, 2), dtype=complex), G, None, 0.5)
     e = np.exp(-0.5)
     assert np.allclose(du, [[-e, -0.5 * e], [-0.5 * e, e]], atol=1e-15)                         # :194
+
+
+# ---- test/opensys/lindblad.jl:3-19 — ULELiouvillian --------------------------------------------------------
+def test_ule_golden():
+    unitary = lambda t: sla.expm(-1j * t * sx)
+    rho = np.outer(F.PauliVec[0][0], F.PauliVec[0][0].conj())
+    kernels = [(((1, 1),), [sz], lambda t1, t2: 1.0)]
+    ule = O.ULELiouvillian(kernels, unitary, 5.0, 1e-8, 1e-6)
+    p = O.ODEParams(None, 5.0, lambda tf, t: t / tf)
+    L, _ = O.quadgk(lambda x: unitary(x).conj().T @ sz @ unitary(x), 0, 5, 1.5e-8, 0.0)   # :14
+    d = ule.rhs_acc(np.zeros((2, 2), complex), rho, p, 5.0)
+    exp = L @ rho @ L.conj().T - 0.5 * (L.conj().T @ L @ rho + rho @ L.conj().T @ L)
+    assert close(d, exp)                                                                  # :19
