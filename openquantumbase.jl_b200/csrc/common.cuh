@@ -131,12 +131,32 @@ int host_pipeline(Ctx* c, int nb, size_t in_bytes, size_t out_bytes, const void*
     cudaEvent_t* ev_up = &c->ev[0];
     cudaEvent_t* ev_comp = &c->ev[2];
     cudaEvent_t* ev_down = &c->ev[4];
+    // Chunk sizes ramp up at the start and down at the end (chunk/4, chunk/2, chunk, …, chunk/2, chunk/4): only the
+    // first upload and the last download are not hidden behind compute, so they are made small.
+    std::vector<int> sizes;
+    {
+        const int q = chunk / 4 > 0 ? chunk / 4 : 1, h = chunk / 2 > 0 ? chunk / 2 : 1;
+        int left = nb;
+        std::vector<int> head, tail;
+        if (nb >= 4 * chunk) {
+            head = {q, h};
+            tail = {h, q};
+            left -= 2 * (q + h);
+        }
+        sizes = head;
+        while (left > 0) {
+            const int cnt = left < chunk ? left : chunk;
+            sizes.push_back(cnt);
+            left -= cnt;
+        }
+        sizes.insert(sizes.end(), tail.begin(), tail.end());
+    }
     // order the pipeline after whatever is already queued on the compute stream
     OQB_CUDA(c, cudaEventRecord(c->ev[6], c->stream));
     OQB_CUDA(c, cudaStreamWaitEvent(up, c->ev[6], 0));
-    int i = 0;
-    for (int b0 = 0; b0 < nb; b0 += chunk, ++i) {
-        const int cnt = nb - b0 < chunk ? nb - b0 : chunk;
+    int b0 = 0;
+    for (int i = 0; i < (int)sizes.size(); ++i) {
+        const int cnt = sizes[i];
         const int s = i & 1;
         if (i >= 2) OQB_CUDA(c, cudaStreamWaitEvent(up, ev_comp[s], 0));
         OQB_CUDA(c, cudaMemcpyAsync(d_in[s], (const char*)h_in + (size_t)b0 * in_bytes, (size_t)cnt * in_bytes,
@@ -150,6 +170,7 @@ int host_pipeline(Ctx* c, int nb, size_t in_bytes, size_t out_bytes, const void*
         OQB_CUDA(c, cudaMemcpyAsync((char*)h_out + (size_t)b0 * out_bytes, d_out[s], (size_t)cnt * out_bytes,
                                     cudaMemcpyDeviceToHost, down));
         OQB_CUDA(c, cudaEventRecord(ev_down[s], down));
+        b0 += cnt;
     }
     OQB_CUDA(c, cudaStreamSynchronize(down));
     OQB_CUDA(c, cudaStreamSynchronize(c->stream));
