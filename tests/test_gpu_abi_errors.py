@@ -1,0 +1,79 @@
+"""Error behaviour and edge cases of the C ABI (include/oqb.h): every entry point returns a status and leaves a message
+in oqb_last_error — nothing throws, nothing crashes; empty batches are no-ops.  Mirrors the reference's argument
+checks (ArgumentError at src/opensys/lindblad.jl:88-90, src/coupling/interaction.jl:45-47)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def Q():
+    import oqb_b200
+    return oqb_b200
+
+
+def test_status_codes_and_messages(Q):
+    ctx = Q.get_context()
+    lib = ctx.lib
+    n = 4
+    m = np.ascontiguousarray(np.eye(n, dtype=complex)[None])
+    h = C.c_void_p()
+    assert lib.oqb_dense_create(ctx.h, n, 1, m.ctypes.data, 0, None, C.byref(h)) == 0
+    u = Q.DeviceBatch(2, n, n, ctx)
+    one = np.ones((1, 1))
+    dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    # empty batch: no-op, success
+    assert lib.oqb_dense_rhs(h, 0, dp(one), 1, None, 1, u.ptr, u.ptr) == 0
+    # null state pointer → EINVAL with a message, context stays usable
+    st = lib.oqb_dense_rhs(h, 2, dp(one), 1, None, 1, None, u.ptr)
+    assert st == 1 and b"null" in lib.oqb_last_error(ctx.h)
+    assert lib.oqb_dense_rhs(h, 2, dp(one), 1, None, 1, u.ptr, u.zeros_like().ptr) == 0
+    lib.oqb_dense_destroy(h)
+    # AME: RHS before the eigen-system was set
+    a = C.c_void_p()
+    assert lib.oqb_ame_create(ctx.h, n, n, 1, m.ctypes.data, C.byref(a)) == 0
+    assert lib.oqb_ame_rhs(a, 2, u.ptr, u.ptr) == 1 and b"set_eigen" in lib.oqb_last_error(ctx.h)
+    w = np.arange(n, dtype=float)
+    assert lib.oqb_ame_jump(a, 2, u.ptr, u.ptr, None, None, None, 0) == 1
+    assert lib.oqb_ame_set_eigen(a, dp(w), None) == 0
+    assert lib.oqb_ame_set_tables(a, None, None, None) == 1
+    lib.oqb_ame_destroy(a)
+    # zgemm mode
+    assert lib.oqb_set_zgemm_mode(ctx.h, 7) == 1
+    assert lib.oqb_set_zgemm_mode(ctx.h, 1) == 0
+    # Λ builder: evaluation before the unitary was set, node outside the sampled grid
+    lam = C.c_void_p()
+    S = np.ascontiguousarray(np.diag([1.0, -1, 1, -1]).astype(complex)[None])
+    assert lib.oqb_lambda_create(ctx.h, n, 1, S.ctypes.data, C.byref(lam)) == 0
+    i32 = lambda v: v.ctypes.data_as(C.POINTER(C.c_int32))
+    mem, cp = np.zeros(1, np.int32), np.zeros(1, np.int32)
+    gi, th = np.zeros((1, 16), np.int32), np.zeros((1, 16))
+    ck = np.zeros((1, 15, 2))
+    slot, E = np.zeros(1, np.int64), np.zeros(1)
+    call = lambda: lib.oqb_lambda_eval(lam, 1, i32(mem), i32(cp), i32(gi), dp(th), dp(ck), dp(ck),
+                                       slot.ctypes.data_as(C.POINTER(C.c_int64)), dp(E))
+    assert call() == 1 and b"set_unitary" in lib.oqb_last_error(ctx.h)
+    U = Q.DeviceBatch.from_host(np.stack([np.eye(n, dtype=complex)] * 3), ctx)
+    assert lib.oqb_lambda_set_unitary(lam, 1, 3, U.ptr) == 0
+    assert lib.oqb_lambda_reserve_slots(lam, 4) == 0
+    gi[0, 3] = 5
+    assert call() == 1 and b"outside" in lib.oqb_last_error(ctx.h)
+    gi[0, 3] = 0
+    assert call() == 0 and E[0] == 0.0
+    lib.oqb_lambda_destroy(lam)
+
+
+def test_host_mirror_argument_errors(Q):
+    sz = np.diag([1.0, -1]).astype(complex)
+    with pytest.raises(ValueError):                      # src/coupling/interaction.jl:45-47
+        Q.Lindblad(lambda s: np.eye(2), sz)
+    with pytest.raises(ValueError):                      # src/opensys/lindblad.jl:88-90
+        Q.LindbladLiouvillian([Q.Lindblad(0.1, sz), Q.Lindblad(0.1, np.eye(4, dtype=complex))])
+    H = Q.DenseHamiltonian([lambda s: 1.0], [np.kron(sz, sz)])
+    op = Q.DiffEqLiouvillian(H, [Q.DaviesGenerator([np.kron(sz, np.eye(2))], lambda w: 1.0, lambda w: 0.0)], [], 4)
+    u = np.stack([np.eye(4, dtype=complex) / 4] * 2)
+    with pytest.raises(NotImplementedError):             # one eigen-system per call: members must share s
+        op(np.zeros_like(u), u, Q.ODEParams(H, 1.0), np.array([0.1, 0.9]))
