@@ -117,6 +117,21 @@ def cpu_reference_arm(steps, warmup, evals_per_step=1):
     return steps * evals_per_step / t, t / steps * 1e3, CB.host_threads()
 
 
+def cpu_lambda_baseline(Uh, dt, couplings, cf, tf, atol, rtol, nint):
+    """CPU-baseline leg for benchmarks/lambda_bench.py (kept here: bench.py is the one measurement script allowed to
+    execute oracle/): `nint` Redfield Λ integrals of one schedule through the oracle's QuadGK restatement."""
+    from oracle import oqb_oracle as O
+    from oqb_b200.redfield_device import SampledUnitary
+    Uf = SampledUnitary(Uh, dt)
+    p_ = O.ODEParams(None, tf, lambda tf_, t: t / tf_)
+    red = O.RedfieldLiouvillian([(((1, 1),), couplings, cf)], Uf, tf, atol, rtol)
+    t0 = time.perf_counter()
+    ref = None
+    for j in range(nint):
+        ref = red.Lambda(p_, tf, couplings, cf, j % len(couplings) + 1)
+    return time.perf_counter() - t0, ref
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)

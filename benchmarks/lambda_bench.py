@@ -82,17 +82,10 @@ def main():
     st = lb.stats
     cpu = None
     if args.cpu_integrals > 0:  # the reference-structured CPU path (oracle: quadgk + 3 GEMMs per node) on the same integrals
-        from oracle import oqb_oracle as O
-        from oqb_b200.redfield_device import SampledUnitary
+        from bench import cpu_lambda_baseline  # bench.py's CPU-baseline leg is the only place that executes oracle/
         Uh = U[0].cpu().numpy().transpose(0, 2, 1)
-        Uf = SampledUnitary(Uh, dt)
-        p_ = O.ODEParams(None, tf, lambda tf_, t: t / tf_)
         cfs = lambda t, x: complex(cf(None, np.float64(t), np.float64(x)))
-        red = O.RedfieldLiouvillian([(((1, 1),), z, cfs)], Uf, tf, 1e-8, args.rtol)
-        c0 = time.perf_counter()
-        for j in range(args.cpu_integrals):
-            ref = red.Lambda(p_, tf, z, cfs, j % K + 1)
-        cs = time.perf_counter() - c0
+        cs, ref = cpu_lambda_baseline(Uh, dt, z, cfs, tf, 1e-8, args.rtol, args.cpu_integrals)
         got = out.to_host()[(args.cpu_integrals - 1) % K]
         cpu = {"value": args.cpu_integrals / cs, "unit": "lambda_matrices_per_sec", "kind": "port", "cores": os.cpu_count(),
                "sample": f"{args.cpu_integrals} integrals of schedule 0 through oracle RedfieldLiouvillian.Lambda (numpy/OpenBLAS)",
