@@ -7,7 +7,7 @@ n = 128 (7 qubits), K = 7 diagonal couplings Z_α, one unitary grid per schedule
 `grid` points, generated on the device), Gaussian-decaying complex bath correlation, atol 1e-8 / rtol 1e-6 (the
 reference test's tolerances, test/opensys/redfield.jl:12).  Prints one JSON line: wall time of the adaptive build,
 time inside the device calls, the ZGEMM share (CUDA-event bracketed) and algorithmic TFLOP/s
-(segments × 8n³ × 34: 30 for the 15-node products + 4 for the U(t) rotation).
+(segments × 8n³ × 26: 15 Kronrod + 7 Gauss node products + 4 for the U(t) rotation).
 """
 import argparse
 import ctypes as C
@@ -91,7 +91,7 @@ def main():
                "sample": f"{args.cpu_integrals} integrals of schedule 0 through oracle RedfieldLiouvillian.Lambda (numpy/OpenBLAS)",
                "relerr_device_vs_oracle": float(np.linalg.norm(got - ref) / np.linalg.norm(ref))}
     segs = st["segments_evaluated"]
-    flops = segs * 8.0 * n ** 3 * 34
+    flops = segs * 8.0 * n ** 3 * 26
     dmma, _ = ctx.probe_fp64()
     print(json.dumps({
         "config": "C5-lambda-build", "workload": f"{nb} schedules x {K} couplings, n={n}, unitary grid {G} points, atol 1e-8 rtol {args.rtol}",

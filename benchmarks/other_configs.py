@@ -61,15 +61,16 @@ def rand_states(torch, B, n, cols, seed):
     return torch.randn((B, cols, n), dtype=torch.complex128, device="cuda", generator=gen)
 
 
-def run_c2(Q, torch, steps, dense_L):
-    """C2: 8-qubit dense TFIM + 8 Lindblad operators, batch 4096 of 256×256 ρ, per-member s_b = b/B."""
-    nq, n, K, B = 8, 256, 8, 4096
+def run_c2(Q, torch, steps, dense_L, nq=8, B=4096):
+    """C2: 8-qubit dense TFIM + 8 Lindblad operators, batch 4096 of 256×256 ρ, per-member s_b = b/B.
+    C2' (SURVEY §8(d)): the same at 10 qubits — n = 1024, K = 10, B = 64."""
+    n, K = 2 ** nq, nq
     rng = np.random.default_rng(2000)
     Hd, Hp, z = tfim_dense(nq)
     Ls = [rng.standard_normal((n, n)) / np.sqrt(n) + 1j * rng.standard_normal((n, n)) / np.sqrt(n) for _ in range(K)] if dense_L \
         else [np.diag(zq).astype(complex) for zq in z]
     H = Q.DenseHamiltonian([lambda s: 1 - s, lambda s: s], [Hd, Hp], unit="ħ")
-    lind = Q.LindbladLiouvillian([Q.Lindblad(0.1 * (1 + k / 8), L) for k, L in enumerate(Ls)])
+    lind = Q.LindbladLiouvillian([Q.Lindblad(0.1 * (1 + k / nq), L) for k, L in enumerate(Ls)])
     op = Q.DiffEqLiouvillian(H, [], [lind], n)
     p = Q.ODEParams(None, 1.0)
     t = np.arange(B) / B
@@ -88,7 +89,7 @@ def run_c2(Q, torch, steps, dense_L):
     flops = 8.0 * n ** 3 * (2 + 2 * K) * B
     dmma, _ = ctx.probe_fp64()
     ach = zfl.value / (zms.value * 1e-3) / 1e12
-    return {"config": "C2" + ("-denseL" if dense_L else "-Zk"), "workload": f"8-qubit dense TFIM + {K} {'random dense' if dense_L else 'dense-stored Z_k'} Lindblad ops, batch {B} of {n}x{n} rho, per-member s",
+    return {"config": ("C2" if nq == 8 else "C2prime") + ("-denseL" if dense_L else "-Zk"), "workload": f"{nq}-qubit dense TFIM + {K} {'random dense' if dense_L else 'dense-stored Z_k'} Lindblad ops, batch {B} of {n}x{n} rho, per-member s",
             "metric": "rho_rhs_evals_per_sec", "value": B / (ms * 1e-3), "ms_per_step": ms,
             "algorithmic_tflop_per_step": flops / 1e12, "step_tflops": flops / (ms * 1e-3) / 1e12,
             "roofline": {"bound": "tensor", "kernel": "zgemm_tma_kernel", "achieved": ach, "peak": dmma, "unit": "TFLOP/s",
@@ -96,10 +97,10 @@ def run_c2(Q, torch, steps, dense_L):
                          "peak_source": "DMMA issue probe, this run"}}
 
 
-def run_c4(Q, torch, steps):
-    """C4: 12-qubit sparse TFIM trajectories, 65536 ψ of dimension 4096, per-trajectory s_b, γ_k = 0.05."""
+def tfim_sparse_c4(nq):
+    """C4 operators: X-part (nq entries per row) and ZZ-part (diagonal) as CSC terms, L_k = Z_k sparse diagonal."""
     import scipy.sparse as sps
-    nq, n, B = 12, 4096, 65536
+    n = 1 << nq
     idx = np.arange(n)
     rows = np.concatenate([idx ^ (1 << q) for q in range(nq)])
     cols = np.tile(idx, nq)
@@ -107,6 +108,13 @@ def run_c4(Q, torch, steps):
     z = [1.0 - 2.0 * ((idx >> (nq - 1 - q)) & 1) for q in range(nq)]
     Hz = sps.diags(-sum(z[i] * z[i + 1] for i in range(nq - 1))).tocsc().astype(complex)
     Ls = [sps.diags(zq).tocsc().astype(complex) for zq in z]
+    return Hx, Hz, Ls
+
+
+def run_c4(Q, torch, steps):
+    """C4: 12-qubit sparse TFIM trajectories, 65536 ψ of dimension 4096, per-trajectory s_b, γ_k = 0.05."""
+    nq, n, B = 12, 4096, 65536
+    Hx, Hz, Ls = tfim_sparse_c4(nq)
     H = Q.SparseHamiltonian([lambda s: 1 - s, lambda s: s], [Hx, Hz], unit="ħ")
     op = Q.DiffEqLiouvillian(H, [], [Q.LindbladLiouvillian([Q.Lindblad(0.05, L) for L in Ls])], n)
     ens = Q.TrajectoryEnsemble(op)
@@ -207,7 +215,7 @@ def run_c5(Q, torch, steps):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--configs", default="c2,c2dense,c4,c5")
+    ap.add_argument("--configs", default="c2,c2dense,c2prime,c4,c5")
     ap.add_argument("--steps", type=int, default=5)
     args = ap.parse_args()
     import torch
@@ -218,6 +226,8 @@ def main():
             r = run_c2(Q, torch, args.steps, False)
         elif c == "c2dense":
             r = run_c2(Q, torch, args.steps, True)
+        elif c == "c2prime":
+            r = run_c2(Q, torch, args.steps, True, nq=10, B=64)
         elif c == "c4":
             r = run_c4(Q, torch, args.steps)
         elif c == "c5":

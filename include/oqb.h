@@ -139,13 +139,13 @@ int oqb_lambda_set_unitary(oqb_lambda* lam, int nb, int G, const void* d_Ugrid);
 /* storage for the integrals of the live (leaf) segments, n×n each; grows preserving content */
 int oqb_lambda_reserve_slots(oqb_lambda* lam, int64_t nslots);
 /* One Gauss–Kronrod(7,15) evaluation of nseg segments.  For segment s: h_member[s] (which schedule),
- * h_coupling[s] (which S_j), 16 interpolation points h_gi/h_theta[s][0..14] = the 15 nodes x_i and [15] = the end
- * time t (grid index g and fraction θ ∈ [0,1)), complex node weights h_ck[s][i] = wk_i·h·C(t,x_i) and
- * h_cd[s][i] = (wk_i − wg_i)·h·C(t,x_i) as (re,im) pairs (h = half width; wg_i = 0 at the Kronrod-only nodes),
- * h_slot[s] the slot that receives the segment integral.  h_E[s] returns ‖Kronrod − Gauss‖_F (QuadGK's segment
- * error).  Synchronises. */
+ * h_coupling[s] (which S_j), 16 interpolation points h_gi/h_theta[s][0..14] = the 15 nodes x_i — the 7 GAUSS nodes
+ * first, then the 8 Kronrod-only nodes — and [15] = the end time t (grid index g and fraction θ ∈ [0,1)); complex
+ * node weights as (re,im) pairs: h_ck[s][i] = wk_i·h·C(t,x_i) for the 15 nodes and h_cg[s][i] = wg_i·h·C(t,x_i) for
+ * the first 7 (h = half width); h_slot[s] the slot that receives the segment's Kronrod integral.  h_E[s] returns
+ * ‖Kronrod − Gauss‖_F (QuadGK's segment error).  Synchronises. */
 int oqb_lambda_eval(oqb_lambda* lam, int nseg, const int32_t* h_member, const int32_t* h_coupling,
-                    const int32_t* h_gi, const double* h_theta, const double* h_ck, const double* h_cd,
+                    const int32_t* h_gi, const double* h_theta, const double* h_ck, const double* h_cg,
                     const int64_t* h_slot, double* h_E);
 /* Λ_q = Σ_k slot[h_idx[k]], k ∈ [h_ptr[q], h_ptr[q+1]) summed in that order (QuadGK's final re-summation over
  * its heap) into d_Lambda[q] (n×n, device); h_norm[q] = ‖Λ_q‖_F for the rtol test (NULL ⇒ not returned, no

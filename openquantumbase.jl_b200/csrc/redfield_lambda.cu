@@ -13,16 +13,18 @@
 //   1. lambda_stack_kernel   U(x_i) for the 15 nodes (piecewise-linear interpolant of the member's sampled unitary)
 //                            written as ONE tall matrix  A = [U(x_1); …; U(x_15)]  (15n × n), plus U(t)
 //   2. (dense S_j only)      Y_i = S_j U(x_i), a batched ZGEMM over the nodes
-//      lambda_weight_kernel  B = [ ck_i·Y_i | cd_i·Y_i ]  (15n × 2n),  ck_i = wk_i·h·C(t,x_i),
-//                            cd_i = (wk_i − wg_i)·h·C(t,x_i)   (diagonal S_j: Y_i = diag(s_j)·U(x_i) fused here)
-//   3. ZGEMM  [Ik | D] = A† B      (n × 2n, K-dimension 15n: the 15-node weighted sum rides the GEMM's k loop —
-//                                   U(x)† S U(x) is never materialised per node)
-//   4. ZGEMM  T = U(t)[Ik | D],  ZGEMM  R = T_half U(t)†   → I_seg = R[:, :n],  Kronrod − Gauss difference R[:, n:]
-//   5. lambda_finish_kernel  slot[s] = I_seg,  E_seg = ‖R[:, n:]‖_F   (fixed-order block reduction)
+//      lambda_weight_kernel  (diagonal S_j: fused into step 1, lambda_stack_weight_kernel)
+//                            Bk = [ck_i·Y_i]_{i<15} (15n × n),  Bg = [cg_i·Y_i]_{i<7} (7n × n),  ck_i = wk_i·h·C(t,x_i),
+//                            cg_i = wg_i·h·C(t,x_i); the nodes come Gauss-first, so the Gauss rule is the first
+//                            7 block rows of the same stack (diagonal S_j: Y_i = diag(s_j)·U(x_i) fused here)
+//   3. ZGEMM  Ik = A† Bk  (K-dimension 15n),  ZGEMM  Ig = A[:7n]† Bg  (K-dimension 7n): the weighted node sums ride
+//                            the GEMMs' k loops — U(x)† S U(x) is never materialised per node
+//   4. ZGEMM  T = U(t)[Ik | Ig],  ZGEMM  R = T_half U(t)†   → Kronrod integral R[:, :n],  Gauss integral R[:, n:]
+//   5. lambda_finish_kernel  slot[s] = R[:, :n],  E_seg = ‖R[:, :n] − R[:, n:]‖_F   (fixed-order block reduction)
 //
 // U(t) is pulled out of the node loop (U(t)·M·U(t)† is linear in M), which turns the reference's 3 GEMMs per node
-// (redfield.jl:49-54) into 2 per node + 4 per segment: 8n³·34 flops per segment (49 when S_j is dense) instead of
-// 8n³·45.  oqb_lambda_total then sums each integral's leaf segments in heap order (QuadGK's final re-summation)
+// (redfield.jl:49-54) into 15 + 7 node products + 4 per segment: 8n³·26 flops per segment (41 when S_j is dense)
+// instead of 8n³·45.  oqb_lambda_total then sums each integral's leaf segments in heap order (QuadGK's final re-summation)
 // and returns ‖Λ‖_F for the convergence test.
 #include <cmath>
 #include <cstring>
@@ -49,7 +51,7 @@ struct oqb_lambda {
 
 namespace {
 
-constexpr int NODES = 15;
+constexpr int NODES = 15, GNODES = 7;  // Kronrod nodes; the first GNODES of them are the Gauss nodes
 constexpr size_t kLambdaWorkspace = (size_t)3 << 30;
 
 // One block per (segment, node); node 15 is the end time t of the segment's integral.
@@ -80,16 +82,60 @@ __global__ void lambda_stack_kernel(int n, int G, const c128* __restrict__ U, co
     }
 }
 
-// B[seg] = [ck_i·Y_i | cd_i·Y_i] with Y from the Y-stack (dense couplings) or diag(s_j)·A-stack.
+// Diagonal couplings: the same interpolation, fused with the weighting — writes A, Bk = ck_i·diag(s_j)·U(x_i) and (Gauss
+// nodes) Bg = cg_i·diag(s_j)·U(x_i) in one pass, so the stack is never re-read by an elementwise kernel.
+__global__ void lambda_stack_weight_kernel(int n, int G, const c128* __restrict__ U, const int32_t* __restrict__ member,
+                                           const int32_t* __restrict__ gi, const double* __restrict__ theta,
+                                           const c128* __restrict__ sdiag, const int32_t* __restrict__ coupling,
+                                           const c128* __restrict__ ck, const c128* __restrict__ cg, c128* __restrict__ A,
+                                           c128* __restrict__ Bk, c128* __restrict__ Bg, c128* __restrict__ Ut) {
+    const int seg = blockIdx.x / (NODES + 1), node = blockIdx.x % (NODES + 1);
+    const long long nn = (long long)n * n;
+    const int g = gi[seg * (NODES + 1) + node];
+    const double th = theta[seg * (NODES + 1) + node];
+    const c128* u0 = U + ((long long)member[seg] * G + g) * nn;
+    const c128* u1 = u0 + nn;
+    const bool two = th != 0.0;
+    const double om = 1.0 - th;
+    const bool gauss = node < GNODES;
+    const c128 wk = node < NODES ? ck[seg * NODES + node] : make_double2(0.0, 0.0);
+    const c128 wg = gauss ? cg[seg * GNODES + node] : make_double2(0.0, 0.0);
+    const c128* sd = sdiag + (long long)coupling[seg] * n;
+    for (long long e = threadIdx.x; e < nn; e += blockDim.x) {
+        c128 a = u0[e];
+        if (two) {
+            const c128 b = u1[e];
+            a.x = om * a.x + th * b.x;
+            a.y = om * a.y + th * b.y;
+        }
+        if (node < NODES) {
+            const int r = (int)(e % n), col = (int)(e / n);
+            A[(long long)seg * NODES * nn + (long long)col * NODES * n + node * n + r] = a;
+            const c128 s = sd[r];
+            const c128 v = make_double2(s.x * a.x - s.y * a.y, s.x * a.y + s.y * a.x);
+            Bk[(long long)seg * NODES * nn + (long long)col * NODES * n + node * n + r] =
+                make_double2(wk.x * v.x - wk.y * v.y, wk.x * v.y + wk.y * v.x);
+            if (gauss)
+                Bg[(long long)seg * GNODES * nn + (long long)col * GNODES * n + node * n + r] =
+                    make_double2(wg.x * v.x - wg.y * v.y, wg.x * v.y + wg.y * v.x);
+        } else {
+            Ut[(long long)seg * nn + e] = a;
+        }
+    }
+}
+
+// Bk[seg] = [ck_i·Y_i]_{i<15}, Bg[seg] = [cg_i·Y_i]_{i<7} with Y from the Y-stack (dense couplings) or diag(s_j)·A-stack.
 __global__ void lambda_weight_kernel(int n, const c128* __restrict__ Y, const c128* __restrict__ sdiag,
                                      const int32_t* __restrict__ coupling, const c128* __restrict__ ck,
-                                     const c128* __restrict__ cd, c128* __restrict__ B) {
+                                     const c128* __restrict__ cg, c128* __restrict__ Bk, c128* __restrict__ Bg) {
     const int seg = blockIdx.x / NODES, node = blockIdx.x % NODES;
     const long long nn = (long long)n * n;
-    const c128 wk = ck[seg * NODES + node], wd = cd[seg * NODES + node];
+    const c128 wk = ck[seg * NODES + node];
+    const bool gauss = node < GNODES;
+    const c128 wg = gauss ? cg[seg * GNODES + node] : make_double2(0.0, 0.0);
     const c128* y = Y + (long long)seg * NODES * nn + node * n;
-    c128* bk = B + (long long)seg * 2 * NODES * nn + node * n;
-    c128* bd = bk + (long long)NODES * nn;
+    c128* bk = Bk + (long long)seg * NODES * nn + node * n;
+    c128* bg = Bg + (long long)seg * GNODES * nn + node * n;
     const c128* sd = sdiag ? sdiag + (long long)coupling[seg] * n : nullptr;
     for (long long e = threadIdx.x; e < nn; e += blockDim.x) {
         const int r = (int)(e % n), col = (int)(e / n);
@@ -99,11 +145,12 @@ __global__ void lambda_weight_kernel(int n, const c128* __restrict__ Y, const c1
             v = make_double2(s.x * v.x - s.y * v.y, s.x * v.y + s.y * v.x);
         }
         bk[(long long)col * NODES * n + r] = make_double2(wk.x * v.x - wk.y * v.y, wk.x * v.y + wk.y * v.x);
-        bd[(long long)col * NODES * n + r] = make_double2(wd.x * v.x - wd.y * v.y, wd.x * v.y + wd.y * v.x);
+        if (gauss) bg[(long long)col * GNODES * n + r] = make_double2(wg.x * v.x - wg.y * v.y, wg.x * v.y + wg.y * v.x);
     }
 }
 
-// slot[slot_id[seg]] = R[seg][:, :n];  E[seg] = ‖R[seg][:, n:]‖_F  — one block per segment, fixed reduction order.
+// slot[slot_id[seg]] = R[seg][:, :n] (Kronrod);  E[seg] = ‖R[seg][:, :n] − R[seg][:, n:]‖_F (Kronrod − Gauss)  — one block
+// per segment, fixed reduction order.
 __global__ void lambda_finish_kernel(int n, const c128* __restrict__ R, const long long* __restrict__ slot_id,
                                      c128* __restrict__ slots, double* __restrict__ E) {
     const int seg = blockIdx.x;
@@ -112,9 +159,10 @@ __global__ void lambda_finish_kernel(int n, const c128* __restrict__ R, const lo
     c128* dst = slots + slot_id[seg] * nn;
     double acc = 0.0;
     for (long long e = threadIdx.x; e < nn; e += blockDim.x) {
-        dst[e] = r[e];
-        const c128 d = r[nn + e];
-        acc += d.x * d.x + d.y * d.y;
+        const c128 k = r[e], g = r[nn + e];
+        dst[e] = k;
+        const double dx = k.x - g.x, dy = k.y - g.y;
+        acc += dx * dx + dy * dy;
     }
     __shared__ double sh[256];
     sh[threadIdx.x] = acc;
@@ -238,12 +286,12 @@ int oqb_lambda_reserve_slots(oqb_lambda* L, int64_t nslots) {
 }
 
 int oqb_lambda_eval(oqb_lambda* L, int nseg, const int32_t* h_member, const int32_t* h_coupling, const int32_t* h_gi,
-                    const double* h_theta, const double* h_ck, const double* h_cd, const int64_t* h_slot, double* h_E) {
+                    const double* h_theta, const double* h_ck, const double* h_cg, const int64_t* h_slot, double* h_E) {
     if (!L) return OQB_EINVAL;
     Ctx* c = L->c;
     if (nseg <= 0) return 0;
     if (!L->dU) return set_error(c, OQB_EINVAL, "oqb_lambda_eval: call oqb_lambda_set_unitary first");
-    if (!h_member || !h_coupling || !h_gi || !h_theta || !h_ck || !h_cd || !h_slot || !h_E)
+    if (!h_member || !h_coupling || !h_gi || !h_theta || !h_ck || !h_cg || !h_slot || !h_E)
         return set_error(c, OQB_EINVAL, "oqb_lambda_eval: null argument");
     const int n = L->n;
     const long long nn = (long long)n * n;
@@ -264,8 +312,8 @@ int oqb_lambda_eval(oqb_lambda* L, int nseg, const int32_t* h_member, const int3
     const size_t o_gi = align16(o_coupling + (size_t)nseg * 4);
     const size_t o_theta = align16(o_gi + (size_t)nseg * (NODES + 1) * 4);
     const size_t o_ck = align16(o_theta + (size_t)nseg * (NODES + 1) * 8);
-    const size_t o_cd = align16(o_ck + (size_t)nseg * NODES * 16);
-    const size_t o_slot = align16(o_cd + (size_t)nseg * NODES * 16);
+    const size_t o_cg = align16(o_ck + (size_t)nseg * NODES * 16);
+    const size_t o_slot = align16(o_cg + (size_t)nseg * GNODES * 16);
     const size_t o_E = align16(o_slot + (size_t)nseg * 8);
     const size_t total = align16(o_E + (size_t)nseg * 8);
     OQB_TRY(meta_reserve(L, total));
@@ -278,37 +326,44 @@ int oqb_lambda_eval(oqb_lambda* L, int nseg, const int32_t* h_member, const int3
     OQB_CUDA(c, up(o_gi, h_gi, (size_t)nseg * (NODES + 1) * 4));
     OQB_CUDA(c, up(o_theta, h_theta, (size_t)nseg * (NODES + 1) * 8));
     OQB_CUDA(c, up(o_ck, h_ck, (size_t)nseg * NODES * 16));
-    OQB_CUDA(c, up(o_cd, h_cd, (size_t)nseg * NODES * 16));
+    OQB_CUDA(c, up(o_cg, h_cg, (size_t)nseg * GNODES * 16));
     OQB_CUDA(c, up(o_slot, h_slot, (size_t)nseg * 8));
     const int32_t* d_member = (const int32_t*)(dm + o_member);
     const int32_t* d_coupling = (const int32_t*)(dm + o_coupling);
     const int32_t* d_gi = (const int32_t*)(dm + o_gi);
     const double* d_theta = (const double*)(dm + o_theta);
     const c128* d_ck = (const c128*)(dm + o_ck);
-    const c128* d_cd = (const c128*)(dm + o_cd);
+    const c128* d_cg = (const c128*)(dm + o_cg);
     const long long* d_slot = (const long long*)(dm + o_slot);
     double* d_E = (double*)(dm + o_E);
 
-    // ---- workspace per segment: A (15nn) [+ Y (15nn)] + B (30nn) + IkD (2nn) + T (2nn) + Ut (nn) ----
-    const size_t per = (size_t)((L->diag ? 15 : 30) + 30 + 2 + 2 + 1) * nn * sizeof(c128);
+    // ---- workspace per segment: A (15nn) [+ Y (15nn)] + Bk (15nn) + Bg (7nn) + [Ik|Ig] (2nn) + T (2nn) + Ut (nn) ----
+    const size_t per = (size_t)((L->diag ? 15 : 30) + 15 + 7 + 2 + 2 + 1) * nn * sizeof(c128);
     int chunk = (int)(kLambdaWorkspace / per);
     if (chunk < 1) chunk = 1;
     if (chunk > nseg) chunk = nseg;
     OQB_TRY(ws_reserve(c, (size_t)chunk * per));
     c128* A = (c128*)c->ws;
     c128* Y = L->diag ? A : A + (size_t)chunk * NODES * nn;
-    c128* B = Y + (size_t)chunk * NODES * nn;
-    c128* IkD = B + (size_t)chunk * 2 * NODES * nn;
+    c128* Bk = Y + (size_t)chunk * NODES * nn;
+    c128* Bg = Bk + (size_t)chunk * NODES * nn;
+    c128* IkD = Bg + (size_t)chunk * GNODES * nn;
     c128* T = IkD + (size_t)chunk * 2 * nn;
     c128* Ut = T + (size_t)chunk * 2 * nn;
     const int threads = nn >= 256 ? 256 : 64;
     for (int s0 = 0; s0 < nseg; s0 += chunk) {
         const int cnt = nseg - s0 < chunk ? nseg - s0 : chunk;
-        lambda_stack_kernel<<<cnt * (NODES + 1), threads, 0, c->stream>>>(n, L->G, L->dU, d_member + s0,
-                                                                         d_gi + (size_t)s0 * (NODES + 1),
-                                                                         d_theta + (size_t)s0 * (NODES + 1), A, Ut);
-        OQB_LAUNCH_CHECK(c);
-        if (!L->diag) {  // Y_i = S_j U(x_i): one batched product per run of equal coupling index
+        if (L->diag) {
+            lambda_stack_weight_kernel<<<cnt * (NODES + 1), threads, 0, c->stream>>>(
+                n, L->G, L->dU, d_member + s0, d_gi + (size_t)s0 * (NODES + 1), d_theta + (size_t)s0 * (NODES + 1), L->dSdiag,
+                d_coupling + s0, d_ck + (size_t)s0 * NODES, d_cg + (size_t)s0 * GNODES, A, Bk, Bg, Ut);
+            OQB_LAUNCH_CHECK(c);
+        } else {
+            lambda_stack_kernel<<<cnt * (NODES + 1), threads, 0, c->stream>>>(n, L->G, L->dU, d_member + s0,
+                                                                             d_gi + (size_t)s0 * (NODES + 1),
+                                                                             d_theta + (size_t)s0 * (NODES + 1), A, Ut);
+            OQB_LAUNCH_CHECK(c);
+            // Y_i = S_j U(x_i): one batched product per run of equal coupling index
             int r0 = 0;
             while (r0 < cnt) {
                 int r1 = r0 + 1;
@@ -321,19 +376,27 @@ int oqb_lambda_eval(oqb_lambda* L, int nseg, const int32_t* h_member, const int3
                 OQB_TRY(zgemm(c, p));
                 r0 = r1;
             }
+            lambda_weight_kernel<<<cnt * NODES, threads, 0, c->stream>>>(n, Y, nullptr, d_coupling + s0, d_ck + (size_t)s0 * NODES,
+                                                                        d_cg + (size_t)s0 * GNODES, Bk, Bg);
+            OQB_LAUNCH_CHECK(c);
         }
-        lambda_weight_kernel<<<cnt * NODES, threads, 0, c->stream>>>(n, Y, L->diag ? L->dSdiag : nullptr, d_coupling + s0,
-                                                                    d_ck + (size_t)s0 * NODES, d_cd + (size_t)s0 * NODES, B);
-        OQB_LAUNCH_CHECK(c);
-        {   // [Ik | D] = A† B
+        {   // Ik = A† Bk  (all 15 nodes)
             ZgemmParams p;
-            p.M = n; p.N = 2 * n; p.K = NODES * n; p.batch = cnt; p.opA = OP_C;
+            p.M = n; p.N = n; p.K = NODES * n; p.batch = cnt; p.opA = OP_C;
             p.A = A; p.lda = (long long)NODES * n; p.strideA = NODES * nn;
-            p.B = B; p.ldb = (long long)NODES * n; p.strideB = 2 * NODES * nn;
+            p.B = Bk; p.ldb = (long long)NODES * n; p.strideB = NODES * nn;
             p.C = IkD; p.ldc = n; p.strideC = 2 * nn;
             OQB_TRY(zgemm(c, p));
         }
-        {   // T = U(t) [Ik | D]
+        {   // Ig = A[:7n]† Bg  (the 7 Gauss nodes = the first 7 block rows of the stack)
+            ZgemmParams p;
+            p.M = n; p.N = n; p.K = GNODES * n; p.batch = cnt; p.opA = OP_C;
+            p.A = A; p.lda = (long long)NODES * n; p.strideA = NODES * nn;
+            p.B = Bg; p.ldb = (long long)GNODES * n; p.strideB = GNODES * nn;
+            p.C = IkD + nn; p.ldc = n; p.strideC = 2 * nn;
+            OQB_TRY(zgemm(c, p));
+        }
+        {   // T = U(t) [Ik | Ig]
             ZgemmParams p;
             p.M = n; p.N = 2 * n; p.K = n; p.batch = cnt;
             p.A = Ut; p.lda = n; p.strideA = nn;

@@ -137,12 +137,12 @@ end
 # `DataStructures.BinaryMaxHeap` of (E, a, b, slot) per integral, bisect the worst segment of every unconverged
 # integral, call this once per round, then `oqb_lambda_total` for ‖Λ‖ — see redfield_device.py for the exact loop.
 function lambda_eval!(lam::Ptr{Cvoid}, c::Ptr{Cvoid}, member::Vector{Int32}, coupling::Vector{Int32}, gi::Matrix{Int32},
-                      θ::Matrix{Float64}, ck::Matrix{ComplexF64}, cd::Matrix{ComplexF64}, slot::Vector{Int64})
-    nseg = length(member)                       # gi, θ: 16×nseg (15 nodes + the end time t); ck, cd: 15×nseg
+                      θ::Matrix{Float64}, ck::Matrix{ComplexF64}, cg::Matrix{ComplexF64}, slot::Vector{Int64})
+    nseg = length(member)                       # gi, θ: 16×nseg (15 nodes + the end time t); ck: 15×nseg, cg: 7×nseg (Gauss nodes first)
     E = Vector{Float64}(undef, nseg)
     check(c, ccall((:oqb_lambda_eval, LIB), Cint,
                    (Ptr{Cvoid}, Cint, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ptr{Float64}, Ptr{ComplexF64}, Ptr{ComplexF64},
-                    Ptr{Int64}, Ptr{Float64}), lam, nseg, member, coupling, gi, θ, ck, cd, slot, E))
+                    Ptr{Int64}, Ptr{Float64}), lam, nseg, member, coupling, gi, θ, ck, cg, slot, E))
     E
 end
 

@@ -30,12 +30,17 @@ _WK = np.array([0.022935322010529224963732008058970, 0.0630920926299785532907006
                 0.204432940075298892414161999234649, 0.209482141084727828012999174891714])
 _WG = np.array([0.129484966168869693270611432679082, 0.279705391489276667901467771423780,
                 0.381830050505118944950369775488975, 0.417959183673469387755102040816327])
-# the 15 nodes on [-1, 1] in ascending order with their Kronrod / Gauss weights (Gauss nodes = odd positions)
-NODE_XI = np.concatenate([-_X[:7], [0.0], _X[:7][::-1]])
-NODE_WK = np.concatenate([_WK[:7], [_WK[7]], _WK[:7][::-1]])
+# the 15 nodes on [-1, 1] with their Kronrod / Gauss weights: ascending order first (Gauss nodes = odd positions) …
+_xi = np.concatenate([-_X[:7], [0.0], _X[:7][::-1]])
+_wk = np.concatenate([_WK[:7], [_WK[7]], _WK[:7][::-1]])
 _wg_half = np.zeros(7)
 _wg_half[1::2] = _WG[:3]
-NODE_WG = np.concatenate([_wg_half, [_WG[3]], _wg_half[::-1]])
+_wg = np.concatenate([_wg_half, [_WG[3]], _wg_half[::-1]])
+# … then reordered GAUSS-FIRST (7 Gauss nodes, 8 Kronrod-only nodes): the device evaluates the Gauss rule as the first
+# 7 block rows of the node stack (oqb_lambda_eval)
+_order = np.concatenate([np.arange(1, 15, 2), np.arange(0, 15, 2)])
+NODE_XI, NODE_WK, NODE_WG = _xi[_order], _wk[_order], _wg[_order]
+N_GAUSS = 7
 
 
 class SampledUnitary:
@@ -108,21 +113,21 @@ class LambdaBuilder:
         x = a[:, None] + (1.0 + NODE_XI[None, :]) * h[:, None]  # (nseg, 15)
         cv = cvals_fn(x)  # (nseg, 15) complex
         ck = (NODE_WK[None, :] * h[:, None]) * cv
-        cd = ((NODE_WK - NODE_WG)[None, :] * h[:, None]) * cv
+        cg = (NODE_WG[None, :N_GAUSS] * h[:, None]) * cv[:, :N_GAUSS]
         pts = np.concatenate([x, t[:, None]], axis=1)
         dtm = self.dt[member][:, None]
         gi, th = SampledUnitary.locate(pts, dtm, self.G)
         gi = np.ascontiguousarray(gi, dtype=np.int32)
         th = np.ascontiguousarray(th, dtype=np.float64)
         ckf = np.ascontiguousarray(ck.astype(C128)).view(np.float64)
-        cdf = np.ascontiguousarray(cd.astype(C128)).view(np.float64)
+        cgf = np.ascontiguousarray(cg.astype(C128)).view(np.float64)
         member = np.ascontiguousarray(member, dtype=np.int32)
         coupling = np.ascontiguousarray(coupling, dtype=np.int32)
         slot = np.ascontiguousarray(slot, dtype=np.int64)
         E = np.empty(nseg, dtype=np.float64)
         i32 = lambda v: v.ctypes.data_as(_lib.c_i32p)
         self.ctx.check(self.ctx.lib.oqb_lambda_eval(self.h, nseg, i32(member), i32(coupling), i32(gi), _lib.dptr(th),
-                                                    _lib.dptr(ckf), _lib.dptr(cdf), slot.ctypes.data_as(_lib.c_i64p),
+                                                    _lib.dptr(ckf), _lib.dptr(cgf), slot.ctypes.data_as(_lib.c_i64p),
                                                     _lib.dptr(E)))
         return E
 

@@ -51,9 +51,9 @@ def test_status_codes_and_messages(Q):
     i32 = lambda v: v.ctypes.data_as(C.POINTER(C.c_int32))
     mem, cp = np.zeros(1, np.int32), np.zeros(1, np.int32)
     gi, th = np.zeros((1, 16), np.int32), np.zeros((1, 16))
-    ck = np.zeros((1, 15, 2))
+    ck, cg = np.zeros((1, 15, 2)), np.zeros((1, 7, 2))
     slot, E = np.zeros(1, np.int64), np.zeros(1)
-    call = lambda: lib.oqb_lambda_eval(lam, 1, i32(mem), i32(cp), i32(gi), dp(th), dp(ck), dp(ck),
+    call = lambda: lib.oqb_lambda_eval(lam, 1, i32(mem), i32(cp), i32(gi), dp(th), dp(ck), dp(cg),
                                        slot.ctypes.data_as(C.POINTER(C.c_int64)), dp(E))
     assert call() == 1 and b"set_unitary" in lib.oqb_last_error(ctx.h)
     U = Q.DeviceBatch.from_host(np.stack([np.eye(n, dtype=complex)] * 3), ctx)
