@@ -176,6 +176,17 @@ def main():
     import torch
     import torch.distributed as dist
     torch.cuda.set_device(local_rank)
+    # NUMA: run this rank on the CPUs next to its GPU so that the pinned host buffers of the end-to-end leg are
+    # first-touched in local memory (8 ranks move 16 GiB per step through host DRAM)
+    numa = None
+    try:
+        import pynvml as nv
+        nv.nvmlInit()
+        hnd = nv.nvmlDeviceGetHandleByIndex(local_rank)
+        nv.nvmlDeviceSetCpuAffinity(hnd)
+        numa = len(os.sched_getaffinity(0))
+    except Exception:
+        numa = None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
     import oqb_b200 as Q
@@ -348,7 +359,7 @@ def main():
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": BATCH * N * N * 16, "d2h_bytes_per_step": BATCH * N * N * 16,
                     "steps": e2e_steps, "max_abs_diff_vs_resident": e2e_check},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
-            "setup_s_not_timed": setup_s, "per_call_eigensystem": prep, "obs_allreduce_ms": obs_ms}
+            "setup_s_not_timed": setup_s, "cpus_bound_to_gpu_numa_node": numa, "per_call_eigensystem": prep, "obs_allreduce_ms": obs_ms}
     emit(line)
     if world > 1:
         dist.destroy_process_group()
