@@ -704,7 +704,12 @@ class DiffEqLiouvillian:
         """Everything that is shared by the batch for one value of s: eigen-system (host LAPACK, the device
         eigensolver when `self.device_eigh` is set, or supplied), gap groups, γ/S tables, device tables."""
         key = (s, None if w is None else (id(w) if v is not None else tuple(np.asarray(w).tolist())))
-        if self._ame is not None and self._ame_s == key:
+        plans = self.__dict__.setdefault("_plans", {})
+        if key in plans:  # a small LRU of prepared eigen-systems: schedule sweeps revisit the same s values
+            plan = plans.pop(key)
+            plans[key] = plan
+            self._ame, self._ame_s = plan["h"], key
+            self._w, self._v, self._v_dev, self._plan = plan["w"], plan["v"], plan["v_dev"], plan
             return
         lib, ctx = self.ctx.lib, self.ctx
         dev_eig = None
@@ -722,8 +727,10 @@ class DiffEqLiouvillian:
             c = [np.asarray(m, dtype=C128) for m in lv.coupling(s)]
             slices.append((len(coup), len(coup) + len(c)))
             coup += c
-        if self._ame is not None:
-            lib.oqb_ame_destroy(self._ame)
+        while len(plans) >= getattr(self, "plan_cache", 8):  # evict the least recently used plan
+            old = plans.pop(next(iter(plans)))
+            ctx.sync()
+            lib.oqb_ame_destroy(old["h"])
         h = C.c_void_p()
         cbuf = _colmajor_stack(coup)
         ctx.check(lib.oqb_ame_create(ctx.h, n, lvl, len(coup), cbuf.ctypes.data, C.byref(h)))
@@ -775,6 +782,7 @@ class DiffEqLiouvillian:
         self._ame, self._ame_s = h, key
         self._w, self._v = w, (None if dev_eig is not None else v)
         self._v_dev = dev_eig[1] if dev_eig is not None else None
+        self._plan = plans[key] = {"h": h, "w": self._w, "v": self._v, "v_dev": self._v_dev}
 
     def lindblad_jump(self, psi: "DeviceBatch", p, t, uniforms, mask=None, apply=False, w=None, v=None):
         """lindblad_jump(Op::DiffEqLiouvillian{true,false}, u, p, t) src/opensys/trajectory_jump.jl:64-69 → ame_jump
@@ -787,7 +795,7 @@ class DiffEqLiouvillian:
             raise NotImplementedError("lindblad_jump{true,false}: one DaviesGenerator (resample over several is not on the device path)")
         s = float(np.atleast_1d(p(t))[0])
         self._prepare_ame(s, w, v)
-        if getattr(self, "_jump_key", None) != self._ame_s:
+        if "jump" not in self._plan:
             K = len(self.opensys_eig[0].coupling(s))
             ptr, terms, rkey, tags = jump_slots(self._w, K, self.digits, self.sigdigits)
             uq, inv = np.unique(rkey, return_inverse=True)
@@ -795,7 +803,8 @@ class DiffEqLiouvillian:
             terms = np.ascontiguousarray(terms)
             self.ctx.check(self.ctx.lib.oqb_ame_set_jump(self._ame, len(rate), ptr.ctypes.data_as(_lib.c_i64p),
                                                          terms.ctypes.data_as(_lib.c_i32p), _lib.dptr(rate)))
-            self._jump_key, self._jump_tags, self._jump_rate = self._ame_s, tags, rate
+            self._plan["jump"] = (tags, rate)
+        self._jump_tags, self._jump_rate = self._plan["jump"]
         B, ns = psi.B, len(self._jump_rate)
         dev = psi.t.device
         u_d = torch.as_tensor(np.asarray(uniforms, dtype=np.float64), device=dev)
@@ -823,15 +832,31 @@ class DiffEqLiouvillian:
         return v @ L @ v.conj().T
 
     def _rhs_eig(self, du, u, p, t, w=None, v=None):
-        """(Op::DiffEqLiouvillian{true,false})(du,u,p,t) :92-109.  All members share s (one
-        eigen-system per call, like the reference's single haml_eigs)."""
+        """(Op::DiffEqLiouvillian{true,false})(du,u,p,t) :92-109.  Members that share s share one eigen-system (the
+        reference's single haml_eigs per call); a batch with several distinct s values (schedule sweep) is processed one
+        s-group at a time, each with its own prepared plan (LRU-cached)."""
         io = _HostIO(u, du)
         B = io.u.B
         sv = _svec(p(t), B)
         if sv.size > 1 and np.any(sv != sv[0]):
-            raise NotImplementedError("AME batches must share the annealing parameter s (one eigen-system per call)")
-        self._prepare_ame(float(sv[0]), w, v)
-        self.ctx.check(self.ctx.lib.oqb_ame_rhs(self._ame, B, io.u.ptr, io.du.ptr))
+            if w is not None:
+                raise ValueError("a supplied (w, v) applies to one s; the batch has several")
+            import torch
+            order = np.argsort(sv, kind="stable")
+            ss = sv[order]
+            starts = np.flatnonzero(np.r_[True, ss[1:] != ss[:-1]])
+            ends = np.r_[starts[1:], len(ss)]
+            dev = io.u.t.device
+            for a, b in zip(starts, ends):  # one device call per distinct s on a gathered, contiguous sub-batch
+                idx = torch.as_tensor(order[a:b], device=dev)
+                sub_u = DeviceBatch(int(b - a), io.u.rows, io.u.cols, self.ctx, io.u.t.index_select(0, idx).contiguous())
+                sub_du = sub_u.zeros_like()
+                self._prepare_ame(float(ss[a]))
+                self.ctx.check(self.ctx.lib.oqb_ame_rhs(self._ame, sub_u.B, sub_u.ptr, sub_du.ptr))
+                io.du.t.index_copy_(0, idx, sub_du.t)
+        else:
+            self._prepare_ame(float(sv[0]), w, v)
+            self.ctx.check(self.ctx.lib.oqb_ame_rhs(self._ame, B, io.u.ptr, io.du.ptr))
         for lv in self.opensys:  # :106-108
             lv(io.du, io.u, p, t)
         return io.finish()

@@ -75,5 +75,6 @@ def test_host_mirror_argument_errors(Q):
     H = Q.DenseHamiltonian([lambda s: 1.0], [np.kron(sz, sz)])
     op = Q.DiffEqLiouvillian(H, [Q.DaviesGenerator([np.kron(sz, np.eye(2))], lambda w: 1.0, lambda w: 0.0)], [], 4)
     u = np.stack([np.eye(4, dtype=complex) / 4] * 2)
-    with pytest.raises(NotImplementedError):             # one eigen-system per call: members must share s
-        op(np.zeros_like(u), u, Q.ODEParams(H, 1.0), np.array([0.1, 0.9]))
+    w4, v4 = np.linalg.eigh(np.kron(sz, sz))
+    with pytest.raises(ValueError):                      # a supplied (w, v) belongs to ONE s
+        op.rhs_with_eig(np.zeros_like(u), u, Q.ODEParams(H, 1.0), np.array([0.1, 0.9]), w4, v4)

@@ -719,3 +719,25 @@ def test_correlated_davies_generator(Q):
     got = Dg(du0.copy(), rho, w, v, 0.4)
     ref = np.stack([Do.rhs_acc(du0[b].copy(), rho[b], G, v, 0.4) for b in range(nb)])
     assert relerr(got, ref) < TOL
+
+
+def test_ame_batch_with_per_member_s(Q):
+    """A schedule sweep through the AME RHS: members with different s get their own eigen-system (grouped by s,
+    plans LRU-cached), result per member = the single-s RHS of the oracle."""
+    rng = np.random.default_rng(88)
+    nq, lvl, nb = 3, 8, 7
+    n = 2 ** nq
+    Hd = -F.standard_driver(nq)
+    Hp = F.two_local_term(list(rng.standard_normal(nq - 1)), [[i, i + 1] for i in range(1, nq)], nq) \
+        + 0.3 * F.single_clause(["z"], [1], 1.0, nq)
+    coup = [F.single_clause(["z"], [k + 1], 1.0, nq) for k in range(2)]
+    Hg, Ho = Q.DenseHamiltonian([A, B], [Hd, Hp]), O.DenseHamiltonian([A, B], [Hd, Hp])
+    opg = Q.DiffEqLiouvillian(Hg, [Q.DaviesGenerator(Q.ConstantCouplings(coup, unit="h"), gamma, lamb)], [], lvl)
+    opg.plan_cache = 2  # smaller than the number of distinct s values: exercises eviction
+    opo = O.DiffEqLiouvillian(Ho, [O.DaviesGenerator([2 * np.pi * c for c in coup], gamma, lamb)], [], lvl)
+    u = rand_rho(rng, nb, n)
+    tf = 2.0
+    t = np.array([0.2, 1.4, 0.2, 0.9, 1.4, 0.2, 1.9])  # 4 distinct s, interleaved
+    got = opg(np.zeros_like(u), u, Q.ODEParams(Hg, tf), t)
+    ref = np.stack([opo.rhs(u[b], O.ODEParams(Ho, tf), t[b]) for b in range(nb)])
+    assert relerr(got, ref) < 1e-11
