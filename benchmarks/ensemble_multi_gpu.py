@@ -1,0 +1,111 @@
+#!/usr/bin/env python
+"""C4 across GPUs: the trajectory ensemble is sharded into contiguous blocks, one per rank (one process per
+GPU, no data-path collective); every rank steps its block on the device (oqb_traj_evolve: RK4 + jump loop), reduces
+the diagonal observables ⟨Z_k⟩ and the norm of its members (oqb_expect_diag) and ONE NCCL all-reduce of
+nobs + 1 numbers forms the ensemble average.
+
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 benchmarks/ensemble_multi_gpu.py
+  python benchmarks/ensemble_multi_gpu.py --per-gpu 65536          # single GPU
+
+Weak scaling: --per-gpu trajectories (default 65536 = C4) on every rank.  Rank 0 prints one JSON line.
+"""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--per-gpu", type=int, default=65536)
+    ap.add_argument("--qubits", type=int, default=12)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--gamma", type=float, default=0.05)
+    args = ap.parse_args()
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    import oqb_b200 as Q
+    from oqb_b200.sharding import ensemble_average, shard_bounds
+    from other_configs import tfim_sparse_c4
+    nq, B = args.qubits, args.per_gpu
+    n = 1 << nq
+    lo, hi = shard_bounds(B * world, rank, world)  # this rank's block of the global ensemble
+    ctx = Q.get_context(local)
+    Hx, Hz, Ls = tfim_sparse_c4(nq)
+    H = Q.SparseHamiltonian([lambda s: 1 - s, lambda s: s], [Hx, Hz], unit="ħ", ctx=ctx)
+    op = Q.DiffEqLiouvillian(H, [], [Q.LindbladLiouvillian([Q.Lindblad(args.gamma, L) for L in Ls])], n)
+    ens = Q.TrajectoryEnsemble(op)
+    gen = torch.Generator(device=f"cuda:{local}").manual_seed(1000 + rank)
+    g = torch.randn((hi - lo, 1, n), dtype=torch.complex128, device=f"cuda:{local}", generator=gen)
+    psi = Q.DeviceBatch(hi - lo, n, 1, ctx, (g / torch.linalg.vector_norm(g, dim=2, keepdim=True)).contiguous())
+    del g
+    st = Q.TrajectoryStepper(ens, hi - lo, seed=7 + 1000003 * rank)  # distinct xoshiro streams per rank
+    p = Q.ODEParams(None, 10.0)
+    idx = np.arange(n)
+    zdiag = [1.0 - 2.0 * ((idx >> (nq - 1 - q)) & 1) for q in range(min(nq, 15))] + [np.ones(n)]
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    st.evolve(psi, p, 0.0, 0.01, 2)  # warm-up
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    st.evolve(psi, p, 0.02, 0.01, args.steps)
+    e1.record()
+    barrier()
+    tms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=f"cuda:{local}")
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    # observables: per-GPU partial sums, then the one collective of the path
+    ensemble_average(Q.expect_diag(zdiag, psi).sum(dim=0), hi - lo)  # warm-up (allocator, NCCL channel set-up)
+    torch.cuda.synchronize()
+    a0, a1, a2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    a0.record()
+    part = Q.expect_diag(zdiag, psi).sum(dim=0)
+    a1.record()
+    avg = ensemble_average(part, hi - lo)
+    a2.record()
+    torch.cuda.synchronize()
+    jumps = st.njumps.sum().to(torch.float64)
+    if world > 1:
+        dist.all_reduce(jumps)
+    if rank == 0:
+        ms = float(tms.item())
+        hbm = 6453.1
+        try:
+            hbm = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))["hbm_gbs"]
+        except Exception:
+            pass
+        gb = 17 * 16.0 * n * B / 1e9  # vector passes of one fused RK4 step, per GPU
+        real_stdout.write(json.dumps({
+            "config": "C4-multi-gpu", "workload": f"{nq}-qubit sparse TFIM trajectories, {B} psi per GPU x {world} GPUs, RK4 + jump loop on the device",
+            "metric": "trajectory_steps_per_sec", "value": world * B * args.steps / (ms * 1e-3), "n_gpus": world, "scaling": "weak",
+            "ms_per_rk4_step": ms / args.steps, "per_gpu_GBs": gb / (ms / args.steps * 1e-3),
+            "per_gpu_frac_of_measured_hbm": gb / (ms / args.steps * 1e-3) / hbm,
+            "observables": {"n": len(zdiag), "local_reduce_ms": a0.elapsed_time(a1), "allreduce_ms": a1.elapsed_time(a2),
+                            "collective": "one all_reduce(sum) of nobs+1 complex numbers (NCCL)" if world > 1 else "none (1 GPU)",
+                            "mean_norm2": float(avg[-1].real), "mean_Z1": float(avg[0].real)},
+            "jumps_total": float(jumps.item())}) + "\n")
+        real_stdout.flush()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -282,6 +282,11 @@ int oqb_traj_evolve(oqb_sparse* sp, int nb, int nsteps, double dt, const double*
 int oqb_expect(oqb_ctx* ctx, int n, int nobs, const void* d_obs, int nb, const void* d_state,
                int is_vector, double* d_out);
 
+/* Diagonal observables of a ψ ensemble (populations, ⟨Z_k⟩, energies of a diagonal problem Hamiltonian — what
+ * inst_population src/hamiltonian/hamiltonian_base.jl:216-237 reduces to in the computational basis):
+ * out[b][o] = Σ_r diag_o[r]·|ψ_b[r]|², nobs ≤ 16 real diagonals (nobs×n, device) in ONE pass over ψ. */
+int oqb_expect_diag(oqb_ctx* ctx, int n, int nobs, const double* d_diag, int nb, const void* d_psi, double* d_out);
+
 /* ------------------------------------------------------------------------------ probes ----- */
 /* Measures FP64 DMMA / DFMA issue throughput of this device (TFLOP/s) — used by bench.py to state
  * the FP64 tensor ceiling next to the cuBLAS DGEMM figure. */

@@ -300,6 +300,11 @@ int oqb_redfield_vectorized_acc(oqb_ctx* c, int n, int K, const void* d_S, int S
     return 0;
 }
 
+int oqb_expect_diag(oqb_ctx* c, int n, int nobs, const double* d_diag, int nb, const void* d_psi, double* d_out) {
+    if (!d_diag || !d_psi || !d_out) return set_error(c, OQB_EINVAL, "oqb_expect_diag: null argument");
+    return expect_diag(c, n, nobs, d_diag, nb, (const c128*)d_psi, d_out);
+}
+
 int oqb_expect(oqb_ctx* c, int n, int nobs, const void* d_obs, int nb, const void* d_state, int is_vector,
                double* d_out) {
     if (!d_obs || !d_state || !d_out) return set_error(c, OQB_EINVAL, "oqb_expect: null argument");

@@ -476,6 +476,47 @@ __global__ void expect_kernel(int n, const c128* __restrict__ obs, const c128* _
         out[(long long)b * nobs + o] = make_double2(a0, a1);
     }
 }
+// Diagonal observables of a ψ ensemble: out[b][o] = Σ_r d_o[r]·|ψ_b[r]|², all observables in ONE pass over ψ
+// (one block per member; the NOBS accumulators live in registers).
+template <int NOBS>
+__global__ void expect_diag_kernel(int n, int nobs, const double* __restrict__ diag, const c128* __restrict__ psi,
+                                   double* __restrict__ out) {
+    const int b = blockIdx.x;
+    const c128* x = psi + (long long)b * n;
+    double acc[NOBS];
+#pragma unroll
+    for (int o = 0; o < NOBS; ++o) acc[o] = 0.0;
+    for (int r = threadIdx.x; r < n; r += blockDim.x) {
+        const c128 v = x[r];
+        const double p = v.x * v.x + v.y * v.y;
+#pragma unroll
+        for (int o = 0; o < NOBS; ++o)
+            if (o < nobs) acc[o] = fma(diag[(long long)o * n + r], p, acc[o]);
+    }
+    __shared__ double red[NOBS][8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 0; o < NOBS; ++o) {
+#pragma unroll
+        for (int of = 16; of > 0; of >>= 1) acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], of);
+        if (lane == 0) red[o][warp] = acc[o];
+    }
+    __syncthreads();
+    if (threadIdx.x < nobs) {
+        double a = 0.0;
+        for (int w = 0; w < (blockDim.x >> 5); ++w) a += red[threadIdx.x][w];
+        out[(long long)b * nobs + threadIdx.x] = a;
+    }
+}
+int expect_diag(Ctx* c, int n, int nobs, const double* diag, int nb, const c128* psi, double* out) {
+    if (nb <= 0 || nobs <= 0) return 0;
+    if (nobs > 16) return set_error(c, 1, "oqb_expect_diag: at most 16 observables per call");
+    if (nobs <= 4) expect_diag_kernel<4><<<nb, 256, 0, c->stream>>>(n, nobs, diag, psi, out);
+    else expect_diag_kernel<16><<<nb, 256, 0, c->stream>>>(n, nobs, diag, psi, out);
+    OQB_LAUNCH_CHECK(c);
+    return 0;
+}
+
 int expect(Ctx* c, int n, int nobs, const c128* obs, int nb, const c128* state, int is_vector, c128* out) {
     if (nb <= 0 || nobs <= 0) return 0;
     for (int b0 = 0; b0 < nb; b0 += 65535) {

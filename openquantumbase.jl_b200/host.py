@@ -1093,6 +1093,18 @@ class TrajectoryStepper:
         return psi
 
 
+def expect_diag(diags: Sequence[np.ndarray], psi: DeviceBatch):
+    """Σ_r d_o[r]|ψ_b[r]|² for real diagonal observables (≤ 16) in one pass over the ensemble → (B, nobs) float64 tensor
+    on the device (per-GPU partials for the NCCL ensemble average)."""
+    import torch
+    ctx = psi.ctx
+    d = torch.as_tensor(np.ascontiguousarray(np.stack([np.asarray(x, dtype=np.float64) for x in diags])), device=psi.t.device)
+    out = torch.zeros((psi.B, d.shape[0]), dtype=torch.float64, device=psi.t.device)
+    ctx.check(ctx.lib.oqb_expect_diag(ctx.h, psi.rows, d.shape[0], C.c_void_p(d.data_ptr()), psi.B, psi.ptr,
+                                      C.c_void_p(out.data_ptr())))
+    return out
+
+
 def expect(obs: Sequence[np.ndarray], state: DeviceBatch):
     """⟨O⟩ per member: tr(Oρ_b) for matrices, ψ_b'Oψ_b for vectors → complex tensor (B, nobs) on
     the device (the per-GPU partial result that is then reduced with NCCL)."""

@@ -741,3 +741,14 @@ def test_ame_batch_with_per_member_s(Q):
     got = opg(np.zeros_like(u), u, Q.ODEParams(Hg, tf), t)
     ref = np.stack([opo.rhs(u[b], O.ODEParams(Ho, tf), t[b]) for b in range(nb)])
     assert relerr(got, ref) < 1e-11
+
+
+def test_expect_diag(Q):
+    rng = np.random.default_rng(3)
+    n, nb = 64, 9
+    psi = rand_c(rng, nb, n)
+    for nobs in (1, 3, 7, 16):
+        d = rng.standard_normal((nobs, n))
+        got = Q.expect_diag(list(d), Q.DeviceBatch.from_host(psi)).cpu().numpy()
+        ref = (np.abs(psi) ** 2) @ d.T
+        assert np.allclose(got, ref, rtol=1e-13, atol=1e-13)
