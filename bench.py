@@ -331,20 +331,38 @@ def main():
     # ---- cost of a NEW eigen-system per call (time-dependent H: the reference diagonalises in every RHS call,
     #      src/opensys/diffeq_liouvillian.jl:94-96); shared by the whole batch, reported next to the resident number ----
     prep = {}
-    for mode in ("host_lapack", "device_eigh"):
-        op.device_eigh = mode == "device_eigh"
+    op.plan_cache = 1  # steady state of a time-dependent solve: every call brings a new s, the plan (and its handle) is recycled
+    for mode in ("host_lapack", "device_eigh", "device_eigh_and_tables"):
+        op.device_eigh = mode != "host_lapack"
+        op.device_tables = mode == "device_eigh_and_tables"
         best = 1e9
-        for k in range(2):
-            s_k = S_POINT + 0.01 * (k + 1) + (0.005 if op.device_eigh else 0.0)
+        for k in range(3):
+            s_k = S_POINT + 0.01 * (k + 1) + {"host_lapack": 0.0, "device_eigh": 0.003, "device_eigh_and_tables": 0.006}[mode]
             t0 = time.perf_counter()
             op._prepare_ame(s_k)
             ctx.sync()
             best = min(best, time.perf_counter() - t0)
         prep[mode + "_s"] = best
         prep["evals_per_sec_incl_" + mode] = BATCH / (ms_total / args.steps * 1e-3 + best)
+    # the device-built tables give the same RHS as the host-built ones (same s, same device eigen-system is not
+    # guaranteed across two eigh calls, so compare through host LAPACK's (w, v) for both)
+    w_chk, v_chk = Q.haml_eigs(H, S_POINT, N)
+    chk = []
+    for flag in (False, True):
+        op.device_eigh, op.device_tables = False, flag
+        op.clear_plans()
+        chk.append(op.rhs_with_eig(du.zeros_like(), u, p, S_POINT * TF, w_chk, v_chk).t.clone())
+    prep["device_tables_rel_diff_vs_host_tables"] = float((chk[0] - chk[1]).norm().item() / chk[0].norm().item())
+    del chk
+    op.device_tables = False
+    op.plan_cache = 8
+    op.clear_plans()
+    op._prepare_ame(S_POINT)
     prep["what"] = ("haml_eigs (H(s) assembly + Hermitian eigensolver) + GapIndices grouping + γ/S tables + coupling rotation for one "
-                    "new s, shared by the 64-ρ batch; host_lapack = scipy zheevd on the host cores, device_eigh = "
-                    "oqb_dense_hamiltonian + cuSOLVER (torch.linalg.eigh) + oqb_ame_set_eigen_device")
+                    "new s, shared by the 64-ρ batch; host_lapack = scipy zheevd + numpy grouping/tables on the host cores; "
+                    "device_eigh = oqb_dense_hamiltonian + cuSOLVER (torch.linalg.eigh) + oqb_ame_set_eigen_device, tables on the host; "
+                    "device_eigh_and_tables = additionally the rounded-gap/Ohmic tables and the gap grouping on the device "
+                    "(oqb_ame_davies_ohmic_begin/finish), only multi-pair group members return to the host")
     op.device_eigh = False
 
     cpu = None

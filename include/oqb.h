@@ -174,6 +174,17 @@ int oqb_ame_set_eigen_device(oqb_ame* ame, const double* d_w, const void* d_v);
 int oqb_ame_set_davies(oqb_ame* ame, const double* h_gam, const double* h_S, int64_t ncross,
                        const int32_t* h_cross_idx, const double* h_cross_rate, int64_t nlamb,
                        const int32_t* h_lamb_idx, const double* h_lamb_rate_S);
+/* The same tables built ON THE DEVICE for an Ohmic bath (γ(ω) of src/bath/ohmic.jl:35-41, S ≡ 0), including the
+ * device-side part of GapIndices (src/opensys/opensys_util.jl:25-61): the l(l−1)/2 gaps are rounded (Julia's
+ * round(x, sigdigits)), sorted and scanned on the GPU; *n_multi / *n_zero return how many level pairs belong to
+ * multi-pair gap groups / to the zero group.  oqb_ame_davies_fetch_groups returns those pairs as lexicographic pair
+ * indices p(i<j) = i·l − i(i+1)/2 + (j−i−1) (multi pairs sorted by key, stable) with their keys; the host turns them into
+ * the cross-term lists (same arrays as oqb_ame_set_davies) and oqb_ame_davies_ohmic_finish installs them. */
+int oqb_ame_davies_ohmic_begin(oqb_ame* ame, double eta, double wc, double beta, int digits, int sigdigits,
+                               int64_t* n_multi, int64_t* n_zero);
+int oqb_ame_davies_fetch_groups(oqb_ame* ame, int32_t* h_multi_pair, double* h_multi_key, int32_t* h_zero_pair);
+int oqb_ame_davies_ohmic_finish(oqb_ame* ame, int64_t ncross, const int32_t* h_cross_idx, const double* h_cross_rate,
+                                int64_t nlamb, const int32_t* h_lamb_idx, const double* h_lamb_rate_S);
 int oqb_ame_clear_davies(oqb_ame* ame);
 /* General closed-form tables, for generators whose rates are not |A_ab|²γ — CorrelatedDaviesGenerator
  * (src/opensys/davies.jl:231-296: du += Σ_(α,β) γ_αβ(ω)(L^β ρ L^α' − ½{L^α'L^β, ρ}) − i[H_LS, ρ]) with a

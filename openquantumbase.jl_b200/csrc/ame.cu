@@ -215,6 +215,8 @@ int oqb_ame_destroy(oqb_ame* a) {
     oqb_ame_clear_davies(a);
     oqb_ame_clear_onesided(a);
     oqb_ame_clear_jump(a);
+    if (a->d_grp_key) cudaFree(a->d_grp_key);
+    if (a->d_grp_pair) cudaFree(a->d_grp_pair);
     (void)he;
     dfree(a->d_coup); dfree(a->d_V); dfree(a->d_w); dfree(a->d_A); dfree(a->d_Cm);
     delete a;
@@ -297,14 +299,10 @@ int oqb_ame_get_rotated_couplings(oqb_ame* a, void* h_A) {
     return 0;
 }
 
-int oqb_ame_set_davies(oqb_ame* a, const double* h_gam, const double* h_S, int64_t ncross, const int32_t* h_cross_idx,
-                       const double* h_cross_rate, int64_t nlamb, const int32_t* h_lamb_idx,
-                       const double* h_lamb_rate_S) {
+// Davies tables: γ/S at the signed rounded gaps are in a->d_gam / a->d_S (device); builds the derived tables and
+// installs the cross-term lists of multi-pair gap groups.
+int ame_davies_alloc(oqb_ame* a) {
     oqb_ctx* c = a->ctx;
-    if (!a->have_eigen) return set_error(c, OQB_EINVAL, "oqb_ame_set_davies: call oqb_ame_set_eigen first");
-    if (!h_gam || !h_S) return set_error(c, OQB_EINVAL, "oqb_ame_set_davies: null table");
-    if ((ncross > 0 && (!h_cross_idx || !h_cross_rate)) || (nlamb > 0 && (!h_lamb_idx || !h_lamb_rate_S)))
-        return set_error(c, OQB_EINVAL, "oqb_ame_set_davies: null cross-term arrays");
     OQB_TRY(oqb_ame_clear_davies(a));
     const int l = a->lvl;
     const size_t ll = (size_t)l * l;
@@ -313,8 +311,14 @@ int oqb_ame_set_davies(oqb_ame* a, const double* h_gam, const double* h_S, int64
     OQB_TRY(dalloc(c, (void**)&a->d_Gam, l * sizeof(double)));
     OQB_TRY(dalloc(c, (void**)&a->d_hls, l * sizeof(double)));
     OQB_TRY(dalloc(c, (void**)&a->d_Wt, ll * sizeof(double)));
-    OQB_CUDA(c, cudaMemcpyAsync(a->d_gam, h_gam, ll * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-    OQB_CUDA(c, cudaMemcpyAsync(a->d_S, h_S, ll * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    return 0;
+}
+
+int ame_davies_finish(oqb_ame* a, int64_t ncross, const int32_t* h_cross_idx, const double* h_cross_rate, int64_t nlamb,
+                      const int32_t* h_lamb_idx, const double* h_lamb_rate_S) {
+    oqb_ctx* c = a->ctx;
+    const int l = a->lvl;
+    const size_t ll = (size_t)l * l;
     OQB_TRY(davies_tables(c, l, a->K, a->d_A, a->d_gam, a->d_S, a->d_w, 1, a->d_Gam, a->d_hls, a->d_Wt, a->d_Cm));
     if (ncross > 0) {
         OQB_TRY(dalloc(c, (void**)&a->d_cross_idx, (size_t)ncross * 4 * sizeof(int32_t)));
@@ -342,6 +346,21 @@ int oqb_ame_set_davies(oqb_ame* a, const double* h_gam, const double* h_S, int64
     OQB_CUDA(c, cudaStreamSynchronize(c->stream));
     a->davies = true;
     return 0;
+}
+
+int oqb_ame_set_davies(oqb_ame* a, const double* h_gam, const double* h_S, int64_t ncross, const int32_t* h_cross_idx,
+                       const double* h_cross_rate, int64_t nlamb, const int32_t* h_lamb_idx,
+                       const double* h_lamb_rate_S) {
+    oqb_ctx* c = a->ctx;
+    if (!a->have_eigen) return set_error(c, OQB_EINVAL, "oqb_ame_set_davies: call oqb_ame_set_eigen first");
+    if (!h_gam || !h_S) return set_error(c, OQB_EINVAL, "oqb_ame_set_davies: null table");
+    if ((ncross > 0 && (!h_cross_idx || !h_cross_rate)) || (nlamb > 0 && (!h_lamb_idx || !h_lamb_rate_S)))
+        return set_error(c, OQB_EINVAL, "oqb_ame_set_davies: null cross-term arrays");
+    OQB_TRY(ame_davies_alloc(a));
+    const size_t ll = (size_t)a->lvl * a->lvl;
+    OQB_CUDA(c, cudaMemcpyAsync(a->d_gam, h_gam, ll * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    OQB_CUDA(c, cudaMemcpyAsync(a->d_S, h_S, ll * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    return ame_davies_finish(a, ncross, h_cross_idx, h_cross_rate, nlamb, h_lamb_idx, h_lamb_rate_S);
 }
 
 int oqb_ame_set_onesided(oqb_ame* a, int npairs, const int32_t* h_alpha, const int32_t* h_beta, const double* h_gam,

@@ -31,5 +31,14 @@ struct oqb_ame {
     long long* d_slot_ptr = nullptr;  // nslots+1 offsets into the term list
     int32_t* d_term = nullptr;        // (coupling, row, col) per term, sorted by (row, col) within a slot
     double* d_slot_rate = nullptr;    // γ at the slot's gap
+    // device-side GapIndices (ame_gaps.cu): pairs flagged as members of multi-pair groups / of the zero group
+    double* d_grp_key = nullptr;
+    int32_t* d_grp_pair = nullptr;
+    long long n_multi = 0, n_zero = 0;
 };
+
+// ame.cu internals shared with ame_gaps.cu (defined inside ame.cu's extern "C" block; not part of the public ABI)
+extern "C" int ame_davies_alloc(oqb_ame* a);
+extern "C" int ame_davies_finish(oqb_ame* a, int64_t ncross, const int32_t* h_cross_idx, const double* h_cross_rate, int64_t nlamb,
+                      const int32_t* h_lamb_idx, const double* h_lamb_rate_S);
 

@@ -121,6 +121,48 @@ class GapGroups:
         return gam, Sm, np.ascontiguousarray(cross_rate), np.ascontiguousarray(lamb_rate_S)
 
 
+_TRIU_CACHE = {}
+
+
+def pair_to_ij(l: int, pairs: np.ndarray):
+    """Lexicographic pair index p(i<j) = i·l − i(i+1)/2 + (j−i−1) → (i, j) (what oqb_ame_davies_fetch_groups returns)."""
+    if l not in _TRIU_CACHE:
+        if len(_TRIU_CACHE) > 4:
+            _TRIU_CACHE.clear()
+        _TRIU_CACHE[l] = np.triu_indices(l, 1)
+    iu, ju = _TRIU_CACHE[l]
+    pairs = np.asarray(pairs, dtype=np.int64)
+    return iu[pairs], ju[pairs]
+
+
+def cross_lists_from_groups(l: int, multi_pair, multi_key, zero_pair, max_cross=50_000_000):
+    """The cross-term / Lamb-shift lists of `GapGroups` from the device-side grouping (ame_gaps.cu): `multi_pair` are the
+    pairs that share their rounded gap with another pair, sorted by key (stable: the reference's loop order inside a
+    group), `zero_pair` the pairs of the zero group.  Returns (cross_idx, cross_key, lamb_idx, lamb_key)."""
+    cross, cross_key, lamb, lamb_key = [], [], [], []
+    multi_key = np.asarray(multi_key, dtype=np.float64)
+    if len(multi_key):
+        mi, mj = pair_to_ij(l, multi_pair)
+        starts = np.flatnonzero(np.r_[True, multi_key[1:] != multi_key[:-1]])
+        ends = np.r_[starts[1:], len(multi_key)]
+        est = int(np.sum((ends - starts).astype(np.int64) ** 2)) * 2
+        if est > max_cross:
+            raise NotImplementedError(f"gap spectrum is too degenerate for the cross-term list ({est} entries)")
+        for a, b in zip(starts, ends):
+            ii, jj, kk = mi[a:b], mj[a:b], float(multi_key[a])
+            for (aa, bb, kval) in ((ii, jj, kk), (jj, ii, -kk)):
+                GapGroups._pairs(aa, bb, kval, cross, cross_key, lamb, lamb_key)
+    if len(zero_pair):
+        zi, zj = pair_to_ij(l, np.sort(np.asarray(zero_pair)))
+        aa = np.r_[zi, zj, np.arange(l)]
+        bb = np.r_[zj, zi, np.arange(l)]
+        if len(aa) ** 2 > max_cross:
+            raise NotImplementedError("zero-gap group too large for the cross-term list")
+        GapGroups._pairs(aa, bb, 0.0, cross, cross_key, lamb, lamb_key, skip_diag_diag=True)
+    return (np.array(cross, dtype=np.int32).reshape(-1, 4), np.array(cross_key, dtype=np.float64),
+            np.array(lamb, dtype=np.int32).reshape(-1, 3), np.array(lamb_key, dtype=np.float64))
+
+
 def jump_slots(w, K, digits=8, sigdigits=8):
     """Probability slots of `ame_jump` (reference src/opensys/trajectory_jump.jl:14-51) in the reference's order,
     from the sort-based grouping: unique non-zero gap keys ascending (GapIndices keeps `uniq_w` sorted,

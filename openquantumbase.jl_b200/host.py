@@ -700,6 +700,15 @@ class DiffEqLiouvillian:
         return du
 
     # ---- {true,false} -------------------------------------------------------------------
+    def clear_plans(self):
+        """Drop every cached eigen-system plan (and its device tables)."""
+        plans = self.__dict__.get("_plans", {})
+        self.ctx.sync()
+        for plan in plans.values():
+            self.ctx.lib.oqb_ame_destroy(plan["h"])
+        plans.clear()
+        self._ame, self._ame_s = None, None
+
     def _prepare_ame(self, s: float, w=None, v=None):
         """Everything that is shared by the batch for one value of s: eigen-system (host LAPACK, the device
         eigensolver when `self.device_eigh` is set, or supplied), gap groups, γ/S tables, device tables."""
@@ -727,13 +736,20 @@ class DiffEqLiouvillian:
             c = [np.asarray(m, dtype=C128) for m in lv.coupling(s)]
             slices.append((len(coup), len(coup) + len(c)))
             coup += c
+        h = None
+        const_coup = all(isinstance(lv.coupling, ConstantCouplings) for lv in self.opensys_eig)
         while len(plans) >= getattr(self, "plan_cache", 8):  # evict the least recently used plan
             old = plans.pop(next(iter(plans)))
             ctx.sync()
-            lib.oqb_ame_destroy(old["h"])
-        h = C.c_void_p()
-        cbuf = _colmajor_stack(coup)
-        ctx.check(lib.oqb_ame_create(ctx.h, n, lvl, len(coup), cbuf.ctypes.data, C.byref(h)))
+            if h is None and const_coup and old["lvl"] == lvl:
+                h = old["h"]  # constant couplings: recycle the handle (its K n×n matrices are already on the device);
+                #               oqb_ame_set_eigen below invalidates every table of the old eigen-system
+            else:
+                lib.oqb_ame_destroy(old["h"])
+        if h is None:
+            h = C.c_void_p()
+            cbuf = _colmajor_stack(coup)
+            ctx.check(lib.oqb_ame_create(ctx.h, n, lvl, len(coup), cbuf.ctypes.data, C.byref(h)))
         if dev_eig is not None:
             ctx.check(lib.oqb_ame_set_eigen_device(h, C.c_void_p(dev_eig[0].data_ptr()), C.c_void_p(dev_eig[1].data_ptr())))
         elif v is None:  # adiabatic frame: the state already is in the eigenbasis
@@ -741,9 +757,33 @@ class DiffEqLiouvillian:
         else:
             vbuf = np.ascontiguousarray(np.asarray(v, dtype=C128).T)  # column-major n×lvl
             ctx.check(lib.oqb_ame_set_eigen(h, _lib.dptr(w), vbuf.ctypes.data))
-        groups = GapGroups(w, self.digits, self.sigdigits)  # :96
+        dev_tables = (getattr(self, "device_tables", False) and len(self.opensys_eig) == 1
+                      and isinstance(self.opensys_eig[0], DaviesGenerator)
+                      and isinstance(self.opensys_eig[0].gamma, OhmicBath) and isinstance(self.opensys_eig[0].S, _Zero))
+        groups = None if dev_tables else GapGroups(w, self.digits, self.sigdigits)  # :96
         ndav = 0
         for lv, (c0, c1) in zip(self.opensys_eig, slices):
+            if dev_tables:
+                # GapIndices grouping and the γ(ω̃_ab) table on the device (ame_gaps.cu); only the members of multi-pair
+                # groups come back for the cross-term lists
+                from .gaps import cross_lists_from_groups
+                nm, nz = C.c_int64(), C.c_int64()
+                bath = lv.gamma
+                ctx.check(lib.oqb_ame_davies_ohmic_begin(h, bath.eta, bath.wc, bath.beta, self.digits, self.sigdigits,
+                                                         C.byref(nm), C.byref(nz)))
+                mp, mk = np.empty(nm.value, dtype=np.int32), np.empty(nm.value, dtype=np.float64)
+                zp = np.empty(nz.value, dtype=np.int32)
+                if nm.value or nz.value:
+                    ctx.check(lib.oqb_ame_davies_fetch_groups(h, mp.ctypes.data_as(_lib.c_i32p), _lib.dptr(mk),
+                                                              zp.ctypes.data_as(_lib.c_i32p)))
+                ci, ck, li, lk = cross_lists_from_groups(lvl, mp, mk, zp)
+                crate = np.ascontiguousarray(bath.vectorized(ck)) if len(ck) else np.zeros(0)
+                lrs = np.ascontiguousarray(np.stack([bath.vectorized(lk), np.zeros(len(lk))], axis=1)) if len(lk) else np.zeros((0, 2))
+                ci, li = np.ascontiguousarray(ci), np.ascontiguousarray(li)
+                ctx.check(lib.oqb_ame_davies_ohmic_finish(
+                    h, len(ci), ci.ctypes.data_as(_lib.c_i32p) if len(ci) else None, _lib.dptr(crate) if len(ci) else None,
+                    len(li), li.ctypes.data_as(_lib.c_i32p) if len(li) else None, _lib.dptr(lrs) if len(li) else None))
+                continue
             if isinstance(lv, DaviesGenerator):
                 if ndav or c0 != 0 or c1 != len(coup):
                     raise NotImplementedError("one DaviesGenerator per DiffEqLiouvillian (it owns all couplings)")
@@ -782,7 +822,7 @@ class DiffEqLiouvillian:
         self._ame, self._ame_s = h, key
         self._w, self._v = w, (None if dev_eig is not None else v)
         self._v_dev = dev_eig[1] if dev_eig is not None else None
-        self._plan = plans[key] = {"h": h, "w": self._w, "v": self._v, "v_dev": self._v_dev}
+        self._plan = plans[key] = {"h": h, "w": self._w, "v": self._v, "v_dev": self._v_dev, "lvl": lvl}
 
     def lindblad_jump(self, psi: "DeviceBatch", p, t, uniforms, mask=None, apply=False, w=None, v=None):
         """lindblad_jump(Op::DiffEqLiouvillian{true,false}, u, p, t) src/opensys/trajectory_jump.jl:64-69 → ame_jump

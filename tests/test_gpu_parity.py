@@ -752,3 +752,38 @@ def test_expect_diag(Q):
         got = Q.expect_diag(list(d), Q.DeviceBatch.from_host(psi)).cpu().numpy()
         ref = (np.abs(psi) ** 2) @ d.T
         assert np.allclose(got, ref, rtol=1e-13, atol=1e-13)
+
+
+@pytest.mark.parametrize("degenerate", [False, True])
+def test_ame_device_gap_tables(Q, degenerate):
+    """Row G on the device (ame_gaps.cu): rounded-gap table, Ohmic γ table and multi-pair group detection on the GPU must
+    reproduce the host-built tables' RHS (and the oracle's literal GapIndices loop) — including degenerate spectra whose
+    gap groups hold several pairs (cross terms)."""
+    rng = np.random.default_rng(123)
+    nq, lvl, nb = 4, 16, 3
+    n = 2 ** nq
+    Hd = -F.standard_driver(nq)
+    if degenerate:  # uniform ZZ chain: highly degenerate gaps
+        Hp = -F.two_local_term([1.0] * (nq - 1), [[i, i + 1] for i in range(1, nq)], nq)
+    else:
+        Hp = F.two_local_term(list(rng.standard_normal(nq - 1)), [[i, i + 1] for i in range(1, nq)], nq) \
+            + sum(rng.standard_normal() * F.single_clause(["z"], [k + 1], 1.0, nq) for k in range(nq))
+    coup = [F.single_clause(["z"], [k + 1], 1.0, nq) for k in range(2)]
+    Hg, Ho = Q.DenseHamiltonian([A, B], [Hd, Hp]), O.DenseHamiltonian([A, B], [Hd, Hp])
+    bath_g, bath_o = Q.Ohmic(1e-2, 4, 16), O.Ohmic(1e-2, 4, 16)
+    mk = lambda: Q.DiffEqLiouvillian(Hg, [Q.DaviesGenerator(Q.ConstantCouplings(coup, unit="h"), bath_g, Q.ZERO_LAMBSHIFT)], [], lvl)
+    op_host, op_dev = mk(), mk()
+    op_dev.device_tables = True
+    u = rand_rho(rng, nb, n)
+    s = 0.35 if not degenerate else 1.0  # s = 1: H = H_p exactly (diagonal, degenerate)
+    w, v = O.haml_eigs(Ho, s, lvl)
+    p = Q.ODEParams(Hg, 2.0)
+    d_host = op_host.rhs_with_eig(np.zeros_like(u), u, p, 2.0 * s, w, v)
+    d_dev = op_dev.rhs_with_eig(np.zeros_like(u), u, p, 2.0 * s, w, v)
+    assert relerr(d_dev, d_host) < 1e-13
+    opo = O.DiffEqLiouvillian(Ho, [O.DaviesGenerator([2 * np.pi * c for c in coup], bath_o.spectrum, lambda x: 0.0)], [], lvl)
+    ref = np.stack([opo.rhs_with_eig(u[b], O.ODEParams(Ho, 2.0), 2.0 * s, w, v) for b in range(nb)])
+    assert relerr(d_dev, ref) < TOL
+    if degenerate:
+        G = O.build_gap_indices(w, 8, 8)
+        assert any(len(a) > 1 for a in G.uniq_a)  # the case really has multi-pair groups
