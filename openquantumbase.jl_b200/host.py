@@ -1133,6 +1133,37 @@ class TrajectoryStepper:
         return psi
 
 
+class DensityStepper:
+    """Fixed-step RK4 of dρ/dt = Op(ρ, p, t) for a device-resident batch: the four stage evaluations are
+    the `(du, u, p, t)` call of any operator of this module, the stage arithmetic is `oqb_axpy_batched`; ρ never leaves HBM.
+    With a time-dependent Hamiltonian the AME operator prepares one eigen-system per distinct stage time (3 per step;
+    `device_eigh` / `device_tables` keep that on the GPU)."""
+
+    def __init__(self, op):
+        self.op, self.ctx = op, op.ctx
+
+    def _axpy(self, alpha: float, x: DeviceBatch, y: DeviceBatch):
+        a = np.array([alpha, 0.0])
+        n_el = y.rows * y.cols
+        self.ctx.check(self.ctx.lib.oqb_axpy_batched(self.ctx.h, n_el, y.B, _lib.dptr(a), x.ptr, n_el, y.ptr))
+
+    def evolve(self, u: DeviceBatch, p, t0: float, dt: float, nsteps: int) -> DeviceBatch:
+        k, tmp, acc = u.zeros_like(), u.zeros_like(), u.zeros_like()
+        for i in range(nsteps):
+            t = t0 + i * dt
+            acc.t.copy_(u.t)
+            for (ts, w_acc, w_next) in ((t, dt / 6, dt / 2), (t + dt / 2, dt / 3, dt / 2), (t + dt / 2, dt / 3, dt), (t + dt, dt / 6, None)):
+                src = u if ts == t and w_next == dt / 2 and w_acc == dt / 6 else tmp
+                k.t.zero_()
+                self.op(k, src, p, ts)
+                self._axpy(w_acc, k, acc)
+                if w_next is not None:
+                    tmp.t.copy_(u.t)
+                    self._axpy(w_next, k, tmp)
+            u.t.copy_(acc.t)
+        return u
+
+
 def expect_diag(diags: Sequence[np.ndarray], psi: DeviceBatch):
     """Σ_r d_o[r]|ψ_b[r]|² for real diagonal observables (≤ 16) in one pass over the ensemble → (B, nobs) float64 tensor
     on the device (per-GPU partials for the NCCL ensemble average)."""
