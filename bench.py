@@ -97,6 +97,7 @@ class ClockSampler(threading.Thread):
 def cpu_reference_arm(steps, warmup, evals_per_step=1):
     """The reference's CPU path (restatement, see oracle/cpu_baseline.py) on a bounded sample."""
     from oracle import cpu_baseline as CB
+    cores = CB.use_all_host_threads()  # torchrun exports OMP_NUM_THREADS=1: the CPU arm must still use every host core
     Hd, Hp, coup = build_c3()
     terms = [2 * np.pi * Hd, 2 * np.pi * Hp]
     coef = [fA(S_POINT), fB(S_POINT)]
@@ -114,7 +115,7 @@ def cpu_reference_arm(steps, warmup, evals_per_step=1):
     for _ in range(steps):
         dt, _n = CB.time_ame_reference(terms, coef, cps, bath, states)
         t += dt
-    return steps * evals_per_step / t, t / steps * 1e3, CB.host_threads()
+    return steps * evals_per_step / t, t / steps * 1e3, cores
 
 
 def cpu_lambda_baseline(Uh, dt, couplings, cf, tf, atol, rtol, nint):

@@ -83,5 +83,19 @@ def time_ame_reference(h_terms, h_coef, couplings, bath, states, lvl=None):
     return time.perf_counter() - t0, len(states)
 
 
+def use_all_host_threads():
+    """Make the BLAS/LAPACK pools use every host core even when the launcher exported OMP_NUM_THREADS=1 (torchrun does);
+    returns the thread count actually in effect (what the bench line reports as `cores`)."""
+    want = os.cpu_count() or 1
+    try:
+        import threadpoolctl
+        threadpoolctl.threadpool_limits(limits=want)  # process-wide, stays in effect
+        pools = threadpoolctl.threadpool_info()
+        got = max([p.get("num_threads", 1) for p in pools if p.get("user_api") == "blas"] or [want])
+        return int(got)
+    except Exception:
+        return int(os.environ.get("OMP_NUM_THREADS", want))
+
+
 def host_threads():
-    return os.cpu_count() or 1
+    return use_all_host_threads()
