@@ -36,12 +36,14 @@ int traj_matvec_fast(Ctx* c, int n, int nb, const std::vector<const TermDev*>& t
 //   mode 1 (first stage, ψ_in = ψ0):  acc = ψ0 + wa·k,  out = ψ0 + wt·k
 //   mode 2 (middle stages):           acc += wa·k,      out = ψ0 + wt·k     (out may alias ψ_in: a trajectory is
 //                                                                            staged completely before it is computed)
-//   mode 3 (last stage):              out = acc + wa·k
+//   mode 3 (last stage):              out = acc + wa·k;  norm_part[b·16 + w] = the warps' partial sums of ‖out_b‖² (w < 16,
+//                                     unused slots zero) when norm_part != nullptr
 struct RkEpilogue {
     int mode = 0;
     double wa = 0.0, wt = 0.0;
     const c128* psi0 = nullptr;
     c128* acc = nullptr;
+    double* norm_part = nullptr;
 };
 
 // Same contract for terms in XOR form + real diagonal terms (implicit columns, 3-deep bulk-async ψ ring,

@@ -105,6 +105,16 @@ __global__ void jump_prepare_kernel(int nb, int step, const double* __restrict__
     if (log && j < max_log) log[((size_t)b * max_log + j) * 2] = step;  // the choice is filled in by jump_log_kernel
 }
 
+// ‖ψ_b‖² from the 16 per-warp partials the last fused RK stage left behind (summed in slot order: deterministic)
+__global__ void norm_from_parts_kernel(int nb, const double* __restrict__ part, double* __restrict__ norm2) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nb) return;
+    double s = 0.0;
+#pragma unroll
+    for (int w = 0; w < 16; ++w) s += part[(size_t)b * 16 + w];
+    norm2[b] = s;
+}
+
 __global__ void jump_log_kernel(int nb, const uint8_t* __restrict__ mask, const int32_t* __restrict__ choice,
                                 const int32_t* __restrict__ njumps, int32_t* __restrict__ log, int max_log) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -148,14 +158,15 @@ int oqb_traj_evolve(oqb_sparse* sp, int nb, int nsteps, double dt, const double*
     const long long len = (long long)n * nb;
     // scratch: k, tmp, acc (n×nb each) + norm2, uniform (nb doubles) + choice (nb int32) + mask (nb bytes)
     const size_t vec = (size_t)len * sizeof(c128);
-    const size_t small = ((size_t)nb * (8 + 8 + 4 + 1) + 255) / 256 * 256;
+    const size_t small = ((size_t)nb * (8 + 8 + 4 + 1 + 16 * 8) + 511) / 256 * 256;
     OQB_TRY(ws_reserve(c, 3 * vec + small));
     c128* kbuf = (c128*)c->ws;
     c128* tmp = kbuf + len;
     c128* acc = tmp + len;
     double* norm2 = (double*)(acc + len);
     double* uni = norm2 + nb;
-    int32_t* choice = (int32_t*)(uni + nb);
+    double* nparts = uni + nb;  // 16 per trajectory
+    int32_t* choice = (int32_t*)(nparts + (size_t)16 * nb);
     uint8_t* mask = (uint8_t*)(choice + nb);
     c128* psi = (c128*)d_psi;
     const size_t rowH = (size_t)(coef_shared ? 1 : nb) * nt, rowG = (size_t)(gamma_shared ? 1 : nb) * K;
@@ -186,6 +197,7 @@ int oqb_traj_evolve(oqb_sparse* sp, int nb, int nsteps, double dt, const double*
                 rk.mode = 2; rk.wa = dt / 3.0; rk.wt = dt;
                 OQB_TRY(oqb_traj_matvec_rk(sp, nb, cf1, coef_shared, g1, gamma_shared, tmp, tmp, &rk, &fused));
                 rk.mode = 3; rk.wa = dt / 6.0; rk.wt = 0.0;
+                rk.norm_part = jumps ? nparts : nullptr;
                 OQB_TRY(oqb_traj_matvec_rk(sp, nb, cf2, coef_shared, g2, gamma_shared, tmp, psi, &rk, &fused));
                 done = true;
             }
@@ -205,7 +217,12 @@ int oqb_traj_evolve(oqb_sparse* sp, int nb, int nsteps, double dt, const double*
         OQB_LAUNCH_CHECK(c);
         }
         if (jumps) {
-            OQB_TRY(oqb_traj_norm2(sp, nb, psi, norm2));
+            if (done) {
+                norm_from_parts_kernel<<<gb, 256, 0, c->stream>>>(nb, nparts, norm2);
+                OQB_LAUNCH_CHECK(c);
+            } else {
+                OQB_TRY(oqb_traj_norm2(sp, nb, psi, norm2));
+            }
             jump_prepare_kernel<<<gb, 256, 0, c->stream>>>(nb, step0 + i, norm2, d_threshold, (unsigned long long*)d_rng, mask,
                                                            uni, d_njumps, d_log, max_log);
             OQB_LAUNCH_CHECK(c);

@@ -106,7 +106,7 @@ __device__ __forceinline__ void do_chunk(const XorDesc& d, const int* s_mask, co
                                          const c128* __restrict__ x, const c128* cfs, const c128 (&xo)[R],
                                          const double (&dreg)[R][ND > 0 ? ND : 1], const c128 (&cdiag)[ND > 0 ? ND : 1],
                                          c128* out, int tid, double wa, double wt, const c128* __restrict__ rk_psi0,
-                                         c128* __restrict__ rk_acc) {
+                                         c128* __restrict__ rk_acc, double& nrm) {
     // fused RK4 stage (EPI != 0): the extra operands are requested before the gathers so that their HBM latency
     // hides behind the shared-memory work of the chunk
     c128 e0[EPI == 2 ? CH : 1], e1[EPI >= 2 ? CH : 1];
@@ -207,7 +207,10 @@ __device__ __forceinline__ void do_chunk(const XorDesc& d, const int* s_mask, co
             rk_acc[idx] = make_double2(e1[kk].x + wa * outr[kk], e1[kk].y + wa * outi[kk]);
             out[idx] = make_double2(e0[kk].x + wt * outr[kk], e0[kk].y + wt * outi[kk]);
         } else {
-            out[idx] = make_double2(e1[kk].x + wa * outr[kk], e1[kk].y + wa * outi[kk]);
+            const c128 v = make_double2(e1[kk].x + wa * outr[kk], e1[kk].y + wa * outi[kk]);
+            out[idx] = v;
+            nrm = fma(v.x, v.x, nrm);  // ‖ψ_new‖² partial of this thread (last RK stage): saves the separate norm pass
+            nrm = fma(v.y, v.y, nrm);
         }
     }
 }
@@ -217,7 +220,7 @@ template <int R, int NT, int S, bool RV, int ND, int EPI, int NG>
 __global__ void __launch_bounds__(NT, 1)
     traj_xor_kernel(int nb, const __grid_constant__ XorDesc d, const c128* __restrict__ coef, long long coef_ld,
                     const c128* psi, c128* dpsi, double wa, double wt, const c128* __restrict__ rk_psi0,
-                    c128* __restrict__ rk_acc) {
+                    c128* __restrict__ rk_acc, double* __restrict__ norm_part) {
     constexpr int n = R * NT, NW = NT / 32, CH = R < 8 ? R : 8, STAGE = n + kCoefPad;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     c128* ring = reinterpret_cast<c128*>(smem_raw);
@@ -290,9 +293,16 @@ __global__ void __launch_bounds__(NT, 1)
         c128* out = dpsi + (size_t)b * n;
         const c128* p0 = EPI == 2 ? rk_psi0 + (size_t)b * n : nullptr;
         c128* ac = EPI != 0 ? rk_acc + (size_t)b * n : nullptr;
-        do_chunk<R, NT, CH, 0, RV, ND, EPI, NG>(d, s_mask, s_vre, s_vim, x, cfs, xo, dreg, cdiag, out, tid, wa, wt, p0, ac);
+        double nrm = 0.0;
+        do_chunk<R, NT, CH, 0, RV, ND, EPI, NG>(d, s_mask, s_vre, s_vim, x, cfs, xo, dreg, cdiag, out, tid, wa, wt, p0, ac, nrm);
         if (R > 8)
-            do_chunk<R, NT, CH, (R > 8 ? 8 : 0), RV, ND, EPI, NG>(d, s_mask, s_vre, s_vim, x, cfs, xo, dreg, cdiag, out, tid, wa, wt, p0, ac);
+            do_chunk<R, NT, CH, (R > 8 ? 8 : 0), RV, ND, EPI, NG>(d, s_mask, s_vre, s_vim, x, cfs, xo, dreg, cdiag, out, tid, wa, wt, p0, ac, nrm);
+        if (EPI == 3 && norm_part) {  // per-warp partial of ‖ψ_b‖² in a fixed order: 16 slots per trajectory, unused ones zero
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) nrm += __shfl_xor_sync(0xffffffffu, nrm, o);
+            if (lane == 0) norm_part[(size_t)b * 16 + warp] = nrm;
+            if (warp == 0 && lane >= NW && lane < 16) norm_part[(size_t)b * 16 + lane] = 0.0;
+        }
         __syncwarp();
         if (lane == 0) xb_arrive(bar_base + 8 * (S + s));
     }
@@ -377,7 +387,7 @@ int launch(Ctx* c, int nb, const XorDesc& d_in, const c128* coef, long long coef
         ProfScope prof(c, (EPI == 0 ? 32.0 : (EPI == 2 ? 80.0 : 48.0)) * R * NT * (double)nb);
         traj_xor_kernel<R, NT, S, RV, ND, EPI, NG><<<grid, NT, smem, c->stream>>>(nb, d, coef, coef_ld, psi, dpsi, rk ? rk->wa : 0.0,
                                                                              rk ? rk->wt : 0.0, rk ? rk->psi0 : nullptr,
-                                                                             rk ? rk->acc : nullptr);
+                                                                             rk ? rk->acc : nullptr, rk ? rk->norm_part : nullptr);
     }
     OQB_LAUNCH_CHECK(c);
     return 0;
