@@ -86,10 +86,17 @@ def run_c2(Q, torch, steps, dense_L, nq=8, B=4096):
     ms = timed(fn, steps, 3, torch)
     zms, zn, zfl = C.c_double(), C.c_uint64(), C.c_double()
     ctx.check(ctx.lib.oqb_profile_end(ctx.h, C.byref(zms), C.byref(zn), C.byref(zfl)))
-    flops = 8.0 * n ** 3 * (2 + 2 * K) * B
+    diag_path = (not dense_L) and os.environ.get("OQB_LINDBLAD_DIAG", "1") != "0"
+    # general L_k: 2 + 2K GEMMs per rho; diagonal L_k exploited (its own row): 2 GEMMs + one Hadamard pass
+    flops = 8.0 * n ** 3 * ((2 if diag_path else 2 + 2 * K)) * B
     dmma, _ = ctx.probe_fp64()
     ach = zfl.value / (zms.value * 1e-3) / 1e12
-    return {"config": ("C2" if nq == 8 else "C2prime") + ("-denseL" if dense_L else "-Zk"), "workload": f"{nq}-qubit dense TFIM + {K} {'random dense' if dense_L else 'dense-stored Z_k'} Lindblad ops, batch {B} of {n}x{n} rho, per-member s",
+    extra = {}
+    if diag_path:
+        extra = {"note": "diagonal L_k exploited: sum_k gamma_k L_k rho L_k' is a Hadamard product with G_b[a,c] = sum_k gamma_bk d_k[a] conj(d_k[c]) "
+                         "(lindblad_diag_sandwich_kernel, 48 B per element) — 2 GEMMs per rho instead of 2+2K; OQB_LINDBLAD_DIAG=0 gives the general row",
+                 "hadamard_bytes_per_step_GB": 48.0 * n * n * B / 1e9}
+    return {**extra, "config": ("C2" if nq == 8 else "C2prime") + ("-denseL" if dense_L else ("-Zk-diagL" if diag_path else "-Zk")), "workload": f"{nq}-qubit dense TFIM + {K} {'random dense' if dense_L else 'dense-stored Z_k'} Lindblad ops, batch {B} of {n}x{n} rho, per-member s",
             "metric": "rho_rhs_evals_per_sec", "value": B / (ms * 1e-3), "ms_per_step": ms,
             "algorithmic_tflop_per_step": flops / 1e12, "step_tflops": flops / (ms * 1e-3) / 1e12,
             "roofline": {"bound": "tensor", "kernel": "zgemm_tma_kernel", "achieved": ach, "peak": dmma, "unit": "TFLOP/s",
@@ -216,13 +223,21 @@ def run_c5(Q, torch, steps):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--configs", default="c2,c2dense,c2prime,c4,c5")
+    ap.add_argument("--configs", default="c2,c2general,c2dense,c2prime,c4,c5")
     ap.add_argument("--steps", type=int, default=5)
     args = ap.parse_args()
     import torch
     import oqb_b200 as Q
     Q.get_context()
     for c in args.configs.split(","):
+        if c == "c2general":  # same operators, diagonal structure NOT exploited (the env switch is read once per process)
+            import subprocess
+            env = dict(os.environ, OQB_LINDBLAD_DIAG="0")
+            out = subprocess.run([sys.executable, os.path.abspath(__file__), "--configs", "c2", "--steps", str(args.steps)],
+                                 env=env, capture_output=True, text=True)
+            sys.stderr.write(out.stderr[-2000:])
+            print(out.stdout.strip().splitlines()[-1], flush=True)
+            continue
         if c == "c2":
             r = run_c2(Q, torch, args.steps, False)
         elif c == "c2dense":

@@ -1,6 +1,8 @@
 // DenseHamiltonian + LindbladLiouvillian + Redfield-apply entry points (include/oqb.h).
 // Everything dense is composed from the DMMA ZGEMM (zgemm.cu) and the streaming kernels of
 // elementwise.cu; this file is host orchestration only.
+#include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -14,6 +16,7 @@ struct oqb_dense {
     int n = 0, nterms = 0, K = 0;
     c128* d_mats = nullptr;  // (nterms + K) n×n : m_1..m_nterms, L_1'L_1..L_K'L_K
     c128* d_lops = nullptr;  // K n×n == the n × (K n) matrix [L_1 | … | L_K]
+    c128* d_ldiag = nullptr; // K × n diagonals when EVERY L_k is diagonal (dephasing Z_k, …), else nullptr
 };
 
 namespace {
@@ -65,6 +68,39 @@ int sandwich(oqb_dense* op, int cnt, const double* d_gamma, int gamma_mod, const
     return zgemm(c, q);
 }
 
+// Diagonal Lindblad operators L_k = diag(d_k): Σ_k γ_bk L_k u L_k' is the Hadamard product of u with
+// G_b[a,c] = Σ_k γ_bk d_k[a] conj(d_k[c]) — one elementwise pass (48 B per element) instead of 2K GEMMs.
+// grid (tiles of 256 elements, members); the K diagonals sit in shared memory.
+__global__ void lindblad_diag_sandwich_kernel(int n, int K, const c128* __restrict__ ldiag, const double* __restrict__ gamma,
+                                              int gamma_ld, const c128* __restrict__ u, c128* __restrict__ du) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    c128* sd = reinterpret_cast<c128*>(smem_raw);  // K × n
+    double* sg = reinterpret_cast<double*>(sd + (size_t)K * n);
+    const int b = blockIdx.y;
+    for (int e = threadIdx.x; e < K * n; e += blockDim.x) sd[e] = ldiag[e];
+    if (threadIdx.x < K) sg[threadIdx.x] = gamma[(size_t)b * gamma_ld + threadIdx.x];
+    __syncthreads();
+    const long long nn = (long long)n * n;
+    const c128* ub = u + (long long)b * nn;
+    c128* dub = du + (long long)b * nn;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < nn; e += (long long)gridDim.x * blockDim.x) {
+        const int a = (int)(e % n), cc = (int)(e / n);
+        double gr = 0.0, gi = 0.0;
+        for (int k = 0; k < K; ++k) {
+            const c128 da = sd[k * n + a], dc = sd[k * n + cc];
+            const double g = sg[k];
+            // g · da · conj(dc)
+            gr = fma(g, da.x * dc.x + da.y * dc.y, gr);
+            gi = fma(g, da.y * dc.x - da.x * dc.y, gi);
+        }
+        const c128 x = ub[e];
+        c128 o = dub[e];
+        o.x += gr * x.x - gi * x.y;
+        o.y += gr * x.y + gi * x.x;
+        dub[e] = o;
+    }
+}
+
 // shared implementation of oqb_dense_rhs (with_h) and oqb_lindblad_acc (!with_h)
 int dense_rhs_impl(oqb_dense* op, int nb, const double* coefH, int coef_shared, const double* gamma,
                    int gamma_shared, const c128* u, c128* du, bool with_h) {
@@ -95,13 +131,17 @@ int dense_rhs_impl(oqb_dense* op, int nb, const double* coefH, int coef_shared, 
     void* d_coef = d_stage;
     void* d_gamma = (char*)d_stage + coef_bytes;
 
-    const size_t per = (size_t)(1 + K) * nn * sizeof(c128);
+    static const bool no_diag = [] { const char* e = getenv("OQB_LINDBLAD_DIAG"); return e && e[0] == '0'; }();
+    const size_t diag_sm = (size_t)K * n * sizeof(c128) + (size_t)K * sizeof(double);
+    const bool use_diag = K > 0 && op->d_ldiag && !no_diag && diag_sm <= 160 * 1024;
+    const int Kws = use_diag ? 0 : K;  // the Hadamard form of the sandwich needs no L_k u scratch
+    const size_t per = (size_t)(1 + Kws) * nn * sizeof(c128);
     int chunk = (int)(kWorkspaceBudget / per);
     if (chunk < 1) chunk = 1;
     if (chunk > nb) chunk = nb;
     chunk = (nb + (nb + chunk - 1) / chunk - 1) / ((nb + chunk - 1) / chunk);  // balance the chunks
     const size_t he_elems = (size_t)(rows == 1 ? 1 : chunk) * nn;
-    OQB_TRY(ws_reserve(c, (he_elems + (size_t)chunk * K * nn) * sizeof(c128)));
+    OQB_TRY(ws_reserve(c, (he_elems + (size_t)chunk * Kws * nn) * sizeof(c128)));
     c128* He = (c128*)c->ws;
     c128* T = He + he_elems;
 
@@ -130,7 +170,22 @@ int dense_rhs_impl(oqb_dense* op, int nb, const double* coefH, int coef_shared, 
         OQB_TRY(zgemm(c, q));
         if (K) {
             const double* dg = (const double*)d_gamma + (gamma_shared ? 0 : (long long)b0 * K);
-            OQB_TRY(sandwich(op, cnt, dg, gamma_shared ? K : 0, ub, dub, T));
+            const size_t sm = diag_sm;
+            if (use_diag) {
+                static bool cfg = false;
+                if (!cfg) { OQB_CUDA(c, cudaFuncSetAttribute(lindblad_diag_sandwich_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); cfg = true; }
+                for (int m0 = 0; m0 < cnt; m0 += 65535) {
+                    const int mc = cnt - m0 < 65535 ? cnt - m0 : 65535;
+                    const int tiles = (int)std::min<long long>((nn + 255) / 256, 64);
+                    dim3 grid(tiles, mc);
+                    lindblad_diag_sandwich_kernel<<<grid, 256, sm, c->stream>>>(
+                        (int)n, K, op->d_ldiag, dg + (gamma_shared ? 0 : (long long)m0 * K), gamma_shared ? 0 : K,
+                        ub + (long long)m0 * nn, dub + (long long)m0 * nn);
+                    OQB_LAUNCH_CHECK(c);
+                }
+            } else {
+                OQB_TRY(sandwich(op, cnt, dg, gamma_shared ? K : 0, ub, dub, T));
+            }
         }
     }
     return 0;
@@ -162,6 +217,21 @@ int oqb_dense_create(oqb_ctx* c, int n, int nterms, const void* h_mats, int K, c
         p.C = op->d_mats + (size_t)nterms * nn; p.ldc = n; p.strideC = (long long)nn;
         int s = zgemm(c, p);
         if (s) { oqb_dense_destroy(op); return s; }
+        // every L_k diagonal (dephasing operators stored as dense matrices)? then keep the K diagonals for the
+        // Hadamard form of the sandwich term
+        const c128* L = (const c128*)h_lops;
+        bool diag = true;
+        for (long long k = 0; k < K && diag; ++k)
+            for (size_t e = 0; e < nn && diag; ++e)
+                if (e % n != e / n && (L[k * nn + e].x != 0.0 || L[k * nn + e].y != 0.0)) diag = false;
+        if (diag) {
+            std::vector<c128> d((size_t)K * n);
+            for (long long k = 0; k < K; ++k)
+                for (int r = 0; r < n; ++r) d[k * n + r] = L[k * nn + (size_t)r * n + r];
+            if (cudaMalloc((void**)&op->d_ldiag, d.size() * sizeof(c128)) != cudaSuccess) { oqb_dense_destroy(op); return set_error(c, OQB_ENOMEM, "oqb_dense_create: cudaMalloc failed"); }
+            OQB_CUDA(c, cudaMemcpyAsync(op->d_ldiag, d.data(), d.size() * sizeof(c128), cudaMemcpyHostToDevice, c->stream));
+            OQB_CUDA(c, cudaStreamSynchronize(c->stream));
+        }
     }
     OQB_CUDA(c, cudaStreamSynchronize(c->stream));
     *out = op;
@@ -173,6 +243,7 @@ int oqb_dense_destroy(oqb_dense* op) {
     cudaStreamSynchronize(op->ctx->stream);
     if (op->d_mats) cudaFree(op->d_mats);
     if (op->d_lops) cudaFree(op->d_lops);
+    if (op->d_ldiag) cudaFree(op->d_ldiag);
     delete op;
     return OQB_OK;
 }
