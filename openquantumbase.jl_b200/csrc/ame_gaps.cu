@@ -132,7 +132,7 @@ int oqb_ame_davies_ohmic_begin(oqb_ame* a, double eta, double wc, double beta, i
     cub::DeviceSelect::Flagged(nullptr, tmp_sel, (const int32_t*)nullptr, (const uint8_t*)nullptr, (int32_t*)nullptr,
                                (unsigned long long*)nullptr, (int)m, c->stream);
     const size_t tmp = tmp_sort > tmp_sel ? tmp_sort : tmp_sel;
-    const size_t bytes = (size_t)m * (8 + 8 + 4 + 4 + 1) + 256 + tmp + 1024;
+    const size_t bytes = (size_t)m * (8 + 8 + 4 + 4 + 1) + 256 + tmp + 2048;
     OQB_TRY(ws_reserve(c, bytes));
     char* base = (char*)c->ws;
     double* k_in = (double*)base;
@@ -141,7 +141,7 @@ int oqb_ame_davies_ohmic_begin(oqb_ame* a, double eta, double wc, double beta, i
     int32_t* p_out = p_in + m;
     uint8_t* flag = (uint8_t*)(p_out + m);
     unsigned long long* cnt = (unsigned long long*)(((uintptr_t)(flag + m) + 255) & ~(uintptr_t)255);
-    void* cub_tmp = (void*)(cnt + 4);
+    void* cub_tmp = (void*)(((uintptr_t)(cnt + 4) + 255) & ~(uintptr_t)255);  // cub wants a 256-byte aligned blob
     OQB_CUDA(c, cudaMemsetAsync(cnt, 0, 4 * sizeof(unsigned long long), c->stream));
     gap_table_kernel<<<(unsigned)((ll + 255) / 256), 256, 0, c->stream>>>(l, a->d_w, pow(10.0, -(double)digits), sigdigits, eta, wc,
                                                                           beta, a->d_gam, a->d_S, k_in, p_in, cnt);
