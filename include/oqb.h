@@ -20,6 +20,9 @@
  *    on the host (the *_host entry points synchronise themselves).
  *  - A context is not thread-safe; use one per (host thread, GPU) — the reference's functors are
  *    not re-entrant either (src/hamiltonian/dense_hamiltonian.jl:61 mutates an internal cache).
+ *  - Process model: ONE GPU per process (one rank per GPU under torchrun / MPI / Distributed.jl).  The library
+ *    configures its kernels (shared-memory limits) once per process and does not switch devices per call; a
+ *    process that wants a second GPU starts a second process.
  *  - There is no CPU fallback anywhere in this library.
  */
 #ifndef OQB_H
