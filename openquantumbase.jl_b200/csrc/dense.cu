@@ -101,6 +101,27 @@ __global__ void lindblad_diag_sandwich_kernel(int n, int K, const c128* __restri
     }
 }
 
+// He[b][a,a] += Σ_k coef[b][k]·|d_k[a]|²  — the L_k'L_k part of H_eff for diagonal L_k (coef already carries −(i/2)γ_bk or −½γ_bk)
+__global__ void heff_diag_add_kernel(int n, int K, const c128* __restrict__ ldiag, const c128* __restrict__ coef, long long coef_ld,
+                                     c128* __restrict__ He, long long strideHe) {
+    const int b = blockIdx.y;
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= n) return;
+    double sr = 0.0, si = 0.0;
+    for (int k = 0; k < K; ++k) {
+        const c128 d = ldiag[(size_t)k * n + a];
+        const double m2 = d.x * d.x + d.y * d.y;
+        const c128 cf = coef[(size_t)b * coef_ld + k];
+        sr = fma(cf.x, m2, sr);
+        si = fma(cf.y, m2, si);
+    }
+    c128* h = He + (long long)b * strideHe + a + (long long)a * n;
+    c128 v = *h;
+    v.x += sr;
+    v.y += si;
+    *h = v;
+}
+
 // shared implementation of oqb_dense_rhs (with_h) and oqb_lindblad_acc (!with_h)
 int dense_rhs_impl(oqb_dense* op, int nb, const double* coefH, int coef_shared, const double* gamma,
                    int gamma_shared, const c128* u, c128* du, bool with_h) {
@@ -145,13 +166,29 @@ int dense_rhs_impl(oqb_dense* op, int nb, const double* coefH, int coef_shared, 
     c128* He = (c128*)c->ws;
     c128* T = He + he_elems;
 
-    if (rows == 1) OQB_TRY(lincomb(c, nmat, nn, mats, (const c128*)d_coef, 0, He, 1, false));
+    // diagonal L_k: L_k'L_k = diag|d_k|² — assemble H_eff from the Hamiltonian terms only and add the diagonal afterwards
+    // (the per-member lincomb then reads nterms matrices instead of nterms + K)
+    const bool diag_heff = use_diag && with_h;
+    const int nlin = diag_heff ? op->nterms : nmat;
+    auto assemble = [&](const c128* cf, long long cf_ld, int cnt) -> int {
+        OQB_TRY(lincomb(c, nlin, nn, mats, cf, cf_ld, He, cnt, false));
+        if (diag_heff) {
+            for (int m0 = 0; m0 < cnt; m0 += 65535) {
+                const int mc = cnt - m0 < 65535 ? cnt - m0 : 65535;
+                dim3 grid((unsigned)((n + 255) / 256), mc);
+                heff_diag_add_kernel<<<grid, 256, 0, c->stream>>>((int)n, K, op->d_ldiag, cf + op->nterms + (long long)m0 * cf_ld, cf_ld,
+                                                                  He + (long long)m0 * nn, nn);
+                OQB_LAUNCH_CHECK(c);
+            }
+        }
+        return 0;
+    };
+    if (rows == 1) OQB_TRY(assemble((const c128*)d_coef, 0, 1));
     for (int b0 = 0; b0 < nb; b0 += chunk) {
         const int cnt = nb - b0 < chunk ? nb - b0 : chunk;
         const c128* ub = u + (long long)b0 * nn;
         c128* dub = du + (long long)b0 * nn;
-        if (rows != 1)
-            OQB_TRY(lincomb(c, nmat, nn, mats, (const c128*)d_coef + (long long)b0 * nmat, nmat, He, cnt, false));
+        if (rows != 1) OQB_TRY(assemble((const c128*)d_coef + (long long)b0 * nmat, nmat, cnt));
         ZgemmParams p;  // du = (−i) He u      [accumulate form: du += G u]
         p.M = p.N = p.K = (int)n; p.batch = cnt;
         p.A = He; p.lda = n; p.strideA = rows == 1 ? 0 : nn;
