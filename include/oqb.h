@@ -120,6 +120,11 @@ int oqb_lindblad_acc(oqb_dense* op, int nb, const double* h_gamma, int gamma_sha
  *   d_S: K n×n coupling matrices (shared, or nb×K when S_shared==0); d_Lambda: nb×K n×n. */
 int oqb_redfield_apply_acc(oqb_ctx* ctx, int n, int K, const void* d_S, int S_shared,
                            const void* d_Lambda, int nb, const void* d_u, void* d_du);
+/* The same for DIAGONAL couplings S_α = diag(s_α) (σz-type system–bath couplings stored as dense matrices): K₂ has the
+ * entries Σ_α (s_α[i] − s_α[j])·(Λ_α u)[i,j], so the 2K products with S_α become one elementwise pass — K GEMMs per
+ * member instead of 3K.  d_Sdiag: K×n complex diagonals (device).  Its own roofline row. */
+int oqb_redfield_apply_diag_acc(oqb_ctx* ctx, int n, int K, const void* d_Sdiag, const void* d_Lambda, int nb,
+                                const void* d_u, void* d_du);
 /* cache[b] (n²×n²) −= I⊗SΛ + conj(SΛ)⊗I − Sᵀ⊗Λ − conj(Λ)⊗S   (ACCUMULATES)
  *   — update_vectorized_cache!(cache, R::RedfieldLiouvillian, p, t) src/opensys/redfield.jl:97-102 */
 int oqb_redfield_vectorized_acc(oqb_ctx* ctx, int n, int K, const void* d_S, int S_shared,

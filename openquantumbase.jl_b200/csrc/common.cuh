@@ -197,6 +197,8 @@ int davies_diag(Ctx* c, int l, const double* Wt, const c128* pop, c128* X, int n
 int extract_diag(Ctx* c, int l, const c128* R, c128* pop, int nb);
 // X[b][i+j*l] += alpha * Σ_{k<nk} (Kb[(b*nk+k)][i+j*l] + conj(Kb[(b*nk+k)][j+i*l]))
 int add_adjoint(Ctx* c, int l, int nk, double alpha, const c128* Kb, c128* X, int nb);
+// X[b] −= K₂ + K₂',  K₂[i,j] = Σ_k (s_k[i] − s_k[j])·Mb[(b*nk+k)][i,j]   (Redfield apply, diagonal couplings)
+int redfield_diag_combine(Ctx* c, int l, int nk, const c128* sdiag, const c128* Mb, c128* X, int nb);
 // Davies tables from rotated couplings A (K l×l), gam/S (l×l real), w (l):
 //   Gam[b], hls[b] (column sums), Wt (l×l, transposed, zero diagonal), Cm (l×l complex)
 int davies_tables(Ctx* c, int l, int K, const c128* A, const double* gam, const double* S,

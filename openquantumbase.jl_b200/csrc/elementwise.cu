@@ -209,6 +209,67 @@ int add_adjoint(Ctx* c, int l, int nk, double alpha, const c128* Kb, c128* X, in
     return 0;
 }
 
+// Redfield apply with DIAGONAL couplings S_k = diag(s_k):  K₂ = Σ_k (S_k M_k − M_k S_k) has entries (s_k[i] − s_k[j])·M_k[i,j],
+// so  X −= K₂ + K₂'  is one pass over the K blocks M_k = Λ_k u (32x32 tiles, the adjoint read goes through shared memory).
+__global__ void redfield_diag_combine_kernel(int l, int nk, const c128* __restrict__ sdiag, const c128* __restrict__ Mb,
+                                             c128* __restrict__ X) {
+    __shared__ c128 tile[32][33];
+    const int b = blockIdx.z;
+    const int i0 = blockIdx.x * 32, j0 = blockIdx.y * 32;
+    const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
+    c128 acc[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) acc[r] = make_double2(0.0, 0.0);
+    for (int k = 0; k < nk; ++k) {
+        const c128* Km = Mb + ((long long)b * nk + k) * l * l;
+        const c128* sk = sdiag + (long long)k * l;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {  // transposed block: element (jj, ii) weighted by (s[jj] − s[ii])
+            const int jj = j0 + tx, ii = i0 + ty + r * 8;
+            c128 v = make_double2(0.0, 0.0);
+            if (jj < l && ii < l) {
+                const c128 w = make_double2(sk[jj].x - sk[ii].x, sk[jj].y - sk[ii].y);
+                v = cmul(w, Km[jj + (long long)ii * l]);
+            }
+            tile[ty + r * 8][tx] = v;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int i = i0 + tx, j = j0 + ty + r * 8;
+            if (i < l && j < l) {
+                const c128 w = make_double2(sk[i].x - sk[j].x, sk[i].y - sk[j].y);
+                const c128 d = cmul(w, Km[i + (long long)j * l]);
+                const c128 tt = tile[tx][ty + r * 8];  // = K₂_k[j, i]
+                acc[r].x += d.x + tt.x;
+                acc[r].y += d.y - tt.y;
+            }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int i = i0 + tx, j = j0 + ty + r * 8;
+        if (i < l && j < l) {
+            c128* d = X + (long long)b * l * l + i + (long long)j * l;
+            c128 v = *d;
+            v.x -= acc[r].x;
+            v.y -= acc[r].y;
+            *d = v;
+        }
+    }
+}
+int redfield_diag_combine(Ctx* c, int l, int nk, const c128* sdiag, const c128* Mb, c128* X, int nb) {
+    if (nb <= 0) return 0;
+    for (int b0 = 0; b0 < nb; b0 += 65535) {
+        const int cnt = nb - b0 < 65535 ? nb - b0 : 65535;
+        dim3 grid(cdiv(l, 32), cdiv(l, 32), cnt), block(32, 8);
+        redfield_diag_combine_kernel<<<grid, block, 0, c->stream>>>(l, nk, sdiag, Mb + (long long)b0 * nk * l * l, X + (long long)b0 * l * l);
+        OQB_LAUNCH_CHECK(c);
+    }
+    return 0;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Davies tables (per distinct s, shared by the batch).  One block per column b for the sums.
 // ---------------------------------------------------------------------------------------------

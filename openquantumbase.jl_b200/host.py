@@ -13,6 +13,7 @@ copies inside the call).  There is no CPU fallback.
 from __future__ import annotations
 
 import ctypes as C
+import os
 import math
 from typing import Callable, List, Optional, Sequence
 
@@ -995,9 +996,15 @@ class RedfieldLiouvillian:
         B, n = io.u.B, io.u.rows
         K = len(S_list)
         ctx = io.u.ctx
-        Sd = DeviceBatch.from_host(np.stack([np.asarray(x, dtype=C128) for x in S_list]), ctx)
         Ld = Lam if isinstance(Lam, DeviceBatch) else DeviceBatch.from_host(np.asarray(Lam, dtype=C128).reshape(B * K, n, n), ctx)
-        ctx.check(ctx.lib.oqb_redfield_apply_acc(ctx.h, n, K, Sd.ptr, 1, Ld.ptr, B, io.u.ptr, io.du.ptr))
+        Sh = [np.asarray(x, dtype=C128) for x in S_list]
+        if all(np.count_nonzero(x - np.diag(np.diag(x))) == 0 for x in Sh) and os.environ.get("OQB_REDFIELD_DIAG", "1") != "0":
+            # diagonal couplings: (S_αM − MS_α)[i,j] = (s_α[i] − s_α[j])·M[i,j] — K GEMMs + one elementwise pass
+            Sdiag = DeviceBatch.from_host(np.stack([np.diag(x) for x in Sh]), ctx)  # (K, n) vectors
+            ctx.check(ctx.lib.oqb_redfield_apply_diag_acc(ctx.h, n, K, Sdiag.ptr, Ld.ptr, B, io.u.ptr, io.du.ptr))
+        else:
+            Sd = DeviceBatch.from_host(np.stack(Sh), ctx)
+            ctx.check(ctx.lib.oqb_redfield_apply_acc(ctx.h, n, K, Sd.ptr, 1, Ld.ptr, B, io.u.ptr, io.du.ptr))
         ctx.sync()
         return io.finish()
 

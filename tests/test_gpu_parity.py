@@ -422,10 +422,13 @@ def test_redfield_golden_and_apply(Q):
     assert np.allclose(Ac @ rho.flatten(order="F"), ref.flatten(order="F"), atol=1e-9)
 
 
-@pytest.mark.parametrize("n,K,nb", [(4, 2, 3), (32, 3, 4), (128, 7, 3)])
-def test_redfield_apply_vs_oracle(Q, n, K, nb):
+@pytest.mark.parametrize("diagS", [False, True])
+@pytest.mark.parametrize("n,K,nb", [(4, 2, 3), (32, 3, 4), (128, 7, 3), (50, 2, 2)])
+def test_redfield_apply_vs_oracle(Q, n, K, nb, diagS):
     rng = np.random.default_rng(n + K)
     S = [(lambda x: x + x.conj().T)(rand_c(rng, n, n)) for _ in range(K)]
+    if diagS:  # diagonal couplings take the elementwise form (oqb_redfield_apply_diag_acc); complex diagonals on purpose
+        S = [np.diag(rand_c(rng, n)) for _ in range(K)]
     Lam = rand_c(rng, nb, K, n, n) / n
     u = rand_c(rng, nb, n, n)
     du0 = rand_c(rng, nb, n, n)
