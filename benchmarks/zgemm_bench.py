@@ -23,7 +23,7 @@ import oqb_b200 as Q  # noqa: E402
 def main():
     ctx = Q.get_context()
     rng = np.random.default_rng(0)
-    shapes = [("C3", 1024, 1024, 1024, 64), ("C2", 256, 256, 256, 4096), ("C5", 128, 128, 128, 7168),
+    shapes = [("C3", 1024, 1024, 1024, 64), ("C2", 256, 256, 256, 4096), ("C5", 128, 128, 128, 8192),
               ("C2-wide", 256, 256, 2048, 512)]
     ops = [(2, 0), (0, 0), (0, 2)]
     if len(sys.argv) > 1:  # e.g. `zgemm_bench.py C3 20` → one shape, one op pair (for ncu captures)
@@ -61,9 +61,26 @@ def main():
             ref = op[opA](a0) @ op[opB](b0)
             got = Cm[0].cpu().numpy().T
             err = float(np.linalg.norm(got - ref) / np.linalg.norm(ref))
+            # library bar: cublasZgemmStridedBatched on the same operands through torch.bmm
+            lib_ms = None
+            if opA == 0 and opB == 0:
+                # column-major A (M×K) stored as torch (batch, K, M); the product in torch's row-major view: C^T = B^T A^T
+                Bt = B.expand(batch, -1, -1)
+                for _ in range(2):
+                    torch.bmm(Bt, A)
+                torch.cuda.synchronize()
+                l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                l0.record()
+                for _ in range(reps):
+                    torch.bmm(Bt, A)
+                l1.record()
+                torch.cuda.synchronize()
+                lib_ms = l0.elapsed_time(l1) / reps
             print(json.dumps({"shape": name, "M": M, "N": N, "K": K, "batch": batch, "opA": opA, "opB": opB,
                               "ms": ms, "tflops_algorithmic": 8.0 * M * N * K * batch / ms / 1e9, "relerr": err,
-                              "mode3m": os.environ.get("OQB_ZGEMM_3M", "0")}), flush=True)
+                              "cublas_zgemm_strided_batched_ms": lib_ms,
+                              "cublas_tflops": None if lib_ms is None else 8.0 * M * N * K * batch / lib_ms / 1e9,
+                              "mode3m": os.environ.get("OQB_ZGEMM_3M", "1")}), flush=True)
             del A, B, Cm
 
 
