@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """C4 across GPUs: the trajectory ensemble is sharded into contiguous blocks, one per rank (one process per
 GPU, no data-path collective); every rank steps its block on the device (oqb_traj_evolve: RK4 + jump loop), reduces
-the diagonal observables ⟨Z_k⟩ and the norm of its members (oqb_expect_diag) and ONE NCCL all-reduce of
+the diagonal observables ⟨Z_k⟩ and the norm of its members (oqb_ensemble_population: one pass over ψ) and ONE NCCL all-reduce of
 nobs + 1 numbers forms the ensemble average.
 
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 benchmarks/ensemble_multi_gpu.py
@@ -73,11 +73,13 @@ def main():
     if world > 1:
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
     # observables: per-GPU partial sums, then the one collective of the path
-    ensemble_average(Q.expect_diag(zdiag, psi).sum(dim=0), hi - lo)  # warm-up (allocator, NCCL channel set-up)
+    # diagonal ensemble averages: ONE pass over ψ gives the populations P[r] = Σ_b |ψ_b[r]|², every ⟨Z_k⟩ is a dot with P
+    zd = torch.as_tensor(np.stack(zdiag), device=f"cuda:{local}")
+    ensemble_average(zd @ Q.ensemble_population(psi), hi - lo)  # warm-up (allocator, NCCL channel set-up)
     torch.cuda.synchronize()
     a0, a1, a2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
     a0.record()
-    part = Q.expect_diag(zdiag, psi).sum(dim=0)
+    part = zd @ Q.ensemble_population(psi)
     a1.record()
     avg = ensemble_average(part, hi - lo)
     a2.record()
@@ -92,7 +94,7 @@ def main():
             hbm = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))["hbm_gbs"]
         except Exception:
             pass
-        gb = 17 * 16.0 * n * B / 1e9  # vector passes of one fused RK4 step, per GPU
+        gb = 16 * 16.0 * n * B / 1e9  # 16 vector passes of one fused RK4 step, per GPU
         real_stdout.write(json.dumps({
             "config": "C4-multi-gpu", "workload": f"{nq}-qubit sparse TFIM trajectories, {B} psi per GPU x {world} GPUs, RK4 + jump loop on the device",
             "metric": "trajectory_steps_per_sec", "value": world * B * args.steps / (ms * 1e-3), "n_gpus": world, "scaling": "weak",

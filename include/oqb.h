@@ -304,6 +304,10 @@ int oqb_expect(oqb_ctx* ctx, int n, int nobs, const void* d_obs, int nb, const v
 /* Diagonal observables of a ψ ensemble (populations, ⟨Z_k⟩, energies of a diagonal problem Hamiltonian — what
  * inst_population src/hamiltonian/hamiltonian_base.jl:216-237 reduces to in the computational basis):
  * out[b][o] = Σ_r diag_o[r]·|ψ_b[r]|², nobs ≤ 16 real diagonals (nobs×n, device) in ONE pass over ψ. */
+/* Ensemble populations P[r] = Σ_b |ψ_b[r]|² in one pass over ψ (inst_population of the ensemble, src/hamiltonian/
+ * hamiltonian_base.jl:216-237, in the computational basis): every diagonal ensemble average is then d_O·P / B — the n doubles of
+ * P (or the few dot products) are what the NCCL all-reduce carries.  Fixed summation order (two-stage), d_out: n doubles. */
+int oqb_ensemble_population(oqb_ctx* ctx, int n, int nb, const void* d_psi, double* d_out);
 int oqb_expect_diag(oqb_ctx* ctx, int n, int nobs, const double* d_diag, int nb, const void* d_psi, double* d_out);
 
 /* ------------------------------------------------------------------------------ probes ----- */

@@ -89,6 +89,7 @@ SIGNATURES = {
     "oqb_traj_rng_uniform": [c_void_p, c_int, c_void_p, c_void_p],
     "oqb_traj_evolve": [c_void_p, c_int, c_int, C.c_double, c_dp, c_int, c_dp, c_int, c_void_p, c_void_p, c_void_p,
                         c_void_p, c_void_p, c_int, c_int],
+    "oqb_ensemble_population": [c_void_p, c_int, c_int, c_void_p, c_void_p],
     "oqb_expect_diag": [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p],
     "oqb_expect": [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p],
     "oqb_probe_fp64": [c_void_p, c_dp, c_dp],

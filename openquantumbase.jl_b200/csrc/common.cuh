@@ -222,6 +222,8 @@ int redfield_superop_acc(Ctx* c, int n, const c128* S, long long strideS, const 
                          long long strideLam, const c128* SL, long long strideSL, c128* cache, int nb);
 // out[(b*nobs+o)] = tr(O_o ρ_b) or ψ_b' O_o ψ_b
 int expect(Ctx* c, int n, int nobs, const c128* obs, int nb, const c128* state, int is_vector, c128* out);
+// out[r] = Σ_b |ψ_b[r]|²  (deterministic two-stage reduction)
+int ensemble_population(Ctx* c, int n, int nb, const c128* psi, double* out);
 // out[b*nobs+o] = Σ_r diag[o*n+r]·|ψ_b[r]|²  (nobs ≤ 16)
 int expect_diag(Ctx* c, int n, int nobs, const double* diag, int nb, const c128* psi, double* out);
 }  // namespace oqb

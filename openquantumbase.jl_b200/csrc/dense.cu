@@ -433,6 +433,11 @@ int oqb_redfield_vectorized_acc(oqb_ctx* c, int n, int K, const void* d_S, int S
     return 0;
 }
 
+int oqb_ensemble_population(oqb_ctx* c, int n, int nb, const void* d_psi, double* d_out) {
+    if (!d_psi || !d_out) return set_error(c, OQB_EINVAL, "oqb_ensemble_population: null argument");
+    return ensemble_population(c, n, nb, (const c128*)d_psi, d_out);
+}
+
 int oqb_expect_diag(oqb_ctx* c, int n, int nobs, const double* d_diag, int nb, const void* d_psi, double* d_out) {
     if (!d_diag || !d_psi || !d_out) return set_error(c, OQB_EINVAL, "oqb_expect_diag: null argument");
     return expect_diag(c, n, nobs, d_diag, nb, (const c128*)d_psi, d_out);

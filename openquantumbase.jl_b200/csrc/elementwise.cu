@@ -578,6 +578,46 @@ int expect_diag(Ctx* c, int n, int nobs, const double* diag, int nb, const c128*
     return 0;
 }
 
+// Ensemble populations P[r] = Σ_b |ψ_b[r]|² (what every diagonal ensemble average reduces to: ⟨O⟩ = d_O·P / B).
+// Two deterministic stages: NG groups of trajectories → partial[g][r], then the groups summed in order.
+__global__ void population_partial_kernel(int n, int nb, int per_group, const c128* __restrict__ psi, double* __restrict__ partial) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    const int g = blockIdx.y;
+    if (r >= n) return;
+    const int b0 = g * per_group, b1 = min(nb, b0 + per_group);
+    double s = 0.0;
+    for (int b = b0; b < b1; ++b) {
+        const c128 v = psi[(long long)b * n + r];
+        s = fma(v.x, v.x, s);
+        s = fma(v.y, v.y, s);
+    }
+    partial[(long long)g * n + r] = s;
+}
+__global__ void population_final_kernel(int n, int ng, const double* __restrict__ partial, double* __restrict__ out) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    double s = 0.0;
+    for (int g = 0; g < ng; ++g) s += partial[(long long)g * n + r];
+    out[r] = s;
+}
+int ensemble_population(Ctx* c, int n, int nb, const c128* psi, double* out) {
+    if (nb <= 0 || n <= 0) return 0;
+    int ng = 148 * 8 / ((n + 255) / 256);  // enough blocks to fill the machine
+    if (ng < 1) ng = 1;
+    if (ng > nb) ng = nb;
+    if (ng > 4096) ng = 4096;
+    const int per_group = (nb + ng - 1) / ng;
+    ng = (nb + per_group - 1) / per_group;
+    OQB_TRY(ws_reserve(c, (size_t)ng * n * sizeof(double)));
+    double* partial = (double*)c->ws;
+    dim3 grid((n + 255) / 256, ng);
+    population_partial_kernel<<<grid, 256, 0, c->stream>>>(n, nb, per_group, psi, partial);
+    OQB_LAUNCH_CHECK(c);
+    population_final_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(n, ng, partial, out);
+    OQB_LAUNCH_CHECK(c);
+    return 0;
+}
+
 int expect(Ctx* c, int n, int nobs, const c128* obs, int nb, const c128* state, int is_vector, c128* out) {
     if (nb <= 0 || nobs <= 0) return 0;
     for (int b0 = 0; b0 < nb; b0 += 65535) {

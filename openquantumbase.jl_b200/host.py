@@ -1171,6 +1171,16 @@ class DensityStepper:
         return u
 
 
+def ensemble_population(psi: DeviceBatch):
+    """P[r] = Σ_b |ψ_b[r]|² (float64 tensor of length n on the device): one pass over the ensemble; diagonal ensemble averages
+    are dot products with P, and P (or those dots) is what the NCCL ensemble reduction carries."""
+    import torch
+    ctx = psi.ctx
+    out = torch.zeros(psi.rows, dtype=torch.float64, device=psi.t.device)
+    ctx.check(ctx.lib.oqb_ensemble_population(ctx.h, psi.rows, psi.B, psi.ptr, C.c_void_p(out.data_ptr())))
+    return out
+
+
 def expect_diag(diags: Sequence[np.ndarray], psi: DeviceBatch):
     """Σ_r d_o[r]|ψ_b[r]|² for real diagonal observables (≤ 16) in one pass over the ensemble → (B, nobs) float64 tensor
     on the device (per-GPU partials for the NCCL ensemble average)."""

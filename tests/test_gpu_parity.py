@@ -750,6 +750,10 @@ def test_expect_diag(Q):
     rng = np.random.default_rng(3)
     n, nb = 64, 9
     psi = rand_c(rng, nb, n)
+    for nbb, nn_ in ((9, 64), (700, 300), (1, 5)):
+        ps = rand_c(rng, nbb, nn_)
+        pop = Q.ensemble_population(Q.DeviceBatch.from_host(ps)).cpu().numpy()
+        assert np.allclose(pop, (np.abs(ps) ** 2).sum(axis=0), rtol=1e-13, atol=1e-13)
     for nobs in (1, 3, 7, 16):
         d = rng.standard_normal((nobs, n))
         got = Q.expect_diag(list(d), Q.DeviceBatch.from_host(psi)).cpu().numpy()
