@@ -465,10 +465,11 @@ class Lindblad:
             self.gamma = gamma
         else:
             self.gamma = lambda s, g=gamma: g
-        if callable(L):
-            raise NotImplementedError("time-dependent Lindblad operators L(s) are not on the device path yet")
-        self.L = L
-        self.size = L.shape
+        # src/coupling/interaction.jl:42,45-53: L may be a matrix or a function of s; time-dependent operators are
+        # evaluated on the host per distinct s and uploaded per call
+        self.Lfun = L if callable(L) else None
+        self.L = None if callable(L) else L
+        self.size = (L(0.0) if callable(L) else L).shape
 
 
 class LindbladLiouvillian:
@@ -479,8 +480,11 @@ class LindbladLiouvillian:
             raise ValueError("All Lindblad operators should have the same size.")  # :88-90
         self.g = [l.gamma for l in linds]
         self.L = [l.L for l in linds]
+        self.Lfun = [l.Lfun for l in linds]
+        self.time_dependent = any(f is not None for f in self.Lfun)
         self.size = linds[0].size
         self._holder = None
+        self._holders_s = {}
 
     def __len__(self):
         return len(self.g)
@@ -488,19 +492,56 @@ class LindbladLiouvillian:
     def gammas(self, svals):
         return _coef(self.g, svals)
 
-    def _op(self, ctx):
-        if self._holder is None:  # a Hamiltonian-less dense operator that only carries the L_k
-            self._holder = _LindHolder(self, ctx)
-        return self._holder
+    def operators(self, s: float):
+        """[L_k(s)] as dense matrices (constant ones as stored)."""
+        return [(f(s) if f is not None else L) for f, L in zip(self.Lfun, self.L)]
+
+    def _op(self, ctx, s: Optional[float] = None):
+        if not self.time_dependent:
+            if self._holder is None:  # a Hamiltonian-less dense operator that only carries the L_k
+                self._holder = _LindHolder(self.L, self.size[0], ctx)
+            return self._holder
+        if s not in self._holders_s:  # L_k(s): one upload per distinct s, a few kept
+            while len(self._holders_s) >= 4:
+                old = self._holders_s.pop(next(iter(self._holders_s)))
+                ctx.sync()
+                ctx.lib.oqb_dense_destroy(old.h)
+            self._holders_s[s] = _LindHolder(self.operators(s), self.size[0], ctx)
+        return self._holders_s[s]
+
+    def _groups(self, sv, B):
+        """(s, member index array or None) per distinct s — time-dependent operators need one device operator per s."""
+        if sv.size == 1 or np.all(sv == sv[0]):
+            return [(float(sv[0]), None)]
+        order = np.argsort(sv, kind="stable")
+        ss = sv[order]
+        starts = np.flatnonzero(np.r_[True, ss[1:] != ss[:-1]])
+        ends = np.r_[starts[1:], len(ss)]
+        return [(float(ss[a]), order[a:b]) for a, b in zip(starts, ends)]
 
     def __call__(self, du, u, p, t):
         """(Lind::LindbladLiouvillian)(du,u,p,t) :94-101 — ACCUMULATES into du."""
         io = _HostIO(u, du)
         B = io.u.B
         sv = _svec(p(t), B)
-        g = self.gammas(sv)
-        hold = self._op(io.u.ctx)
-        hold.ctx.check(hold.ctx.lib.oqb_lindblad_acc(hold.h, B, _lib.dptr(g), int(sv.size == 1), io.u.ptr, io.du.ptr))
+        ctx = io.u.ctx
+        if not self.time_dependent:
+            g = self.gammas(sv)
+            hold = self._op(ctx)
+            ctx.check(ctx.lib.oqb_lindblad_acc(hold.h, B, _lib.dptr(g), int(sv.size == 1), io.u.ptr, io.du.ptr))
+            return io.finish()
+        import torch
+        for s, idx in self._groups(sv, B):
+            g = self.gammas(np.array([s]))
+            hold = self._op(ctx, s)
+            if idx is None:
+                ctx.check(ctx.lib.oqb_lindblad_acc(hold.h, B, _lib.dptr(g), 1, io.u.ptr, io.du.ptr))
+            else:  # gathered, contiguous sub-batch of the members at this s
+                ti = torch.as_tensor(idx, device=io.u.t.device)
+                su = DeviceBatch(len(idx), io.u.rows, io.u.cols, ctx, io.u.t.index_select(0, ti).contiguous())
+                sd = DeviceBatch(len(idx), io.u.rows, io.u.cols, ctx, io.du.t.index_select(0, ti).contiguous())
+                ctx.check(ctx.lib.oqb_lindblad_acc(hold.h, len(idx), _lib.dptr(g), 1, su.ptr, sd.ptr))
+                io.du.t.index_copy_(0, ti, sd.t)
         return io.finish()
 
     def update_cache(self, cache, p, t):
@@ -509,8 +550,10 @@ class LindbladLiouvillian:
         io = _HostIO(cache, cache)
         B = io.u.B
         sv = _svec(p(t), B)
+        if self.time_dependent and not (sv.size == 1 or np.all(sv == sv[0])):
+            raise NotImplementedError("update_cache! with time-dependent L_k(s): one s per call")
         g = self.gammas(sv)
-        hold = self._op(io.u.ctx)
+        hold = self._op(io.u.ctx, float(sv[0]))
         tmp = io.u.zeros_like()
         cf = np.zeros((1, 1))
         hold.ctx.check(hold.ctx.lib.oqb_dense_update_cache(hold.h, B, _lib.dptr(cf), 1, _lib.dptr(g),
@@ -521,13 +564,12 @@ class LindbladLiouvillian:
 
 
 class _LindHolder:
-    def __init__(self, lind: LindbladLiouvillian, ctx: Context):
+    def __init__(self, Ls, n: int, ctx: Context):
         self.ctx = ctx
-        n = lind.size[0]
         zero = np.zeros((1, n, n), dtype=C128)
-        lbuf = _colmajor_stack([L.toarray() if hasattr(L, "toarray") else L for L in lind.L])
+        lbuf = _colmajor_stack([L.toarray() if hasattr(L, "toarray") else L for L in Ls])
         h = C.c_void_p()
-        ctx.check(ctx.lib.oqb_dense_create(ctx.h, n, 1, zero.ctypes.data, len(lind.L), lbuf.ctypes.data, C.byref(h)))
+        ctx.check(ctx.lib.oqb_dense_create(ctx.h, n, 1, zero.ctypes.data, len(Ls), lbuf.ctypes.data, C.byref(h)))
         self.h = h
 
 
@@ -633,7 +675,7 @@ class DiffEqLiouvillian:
 
     # ---- {false,false} ------------------------------------------------------------------
     def _fused_lindblad(self):
-        return (isinstance(self.H, DenseHamiltonian) and len(self._lind) == 1)
+        return (isinstance(self.H, DenseHamiltonian) and len(self._lind) == 1 and not self._lind[0].time_dependent)
 
     def _rhs_adiabatic_frame(self, du, u, p, t):
         """(Op::DiffEqLiouvillian{true,true})(du,u,p,t) :130-140 — du = −i[H,u] then the eigenbasis terms in the
@@ -919,6 +961,8 @@ class DiffEqLiouvillian:
             return io.finish()
         if isinstance(self.H, SparseHamiltonian):
             lind = self._lind[0] if self._lind else None
+            if lind is not None and lind.time_dependent:
+                raise NotImplementedError("sparse update_cache! needs constant Lindblad operators")
             if lind is not None:
                 self.H._sparse_op(lind.L)
             g = lind.gammas(_svec(s, 1))[0] if lind else None
@@ -928,6 +972,11 @@ class DiffEqLiouvillian:
         sv = _svec(p(t), B)
         cf = _coef(self.H.f, sv)
         lind = self._lind[0] if self._lind else None
+        if lind is not None and lind.time_dependent:  # −iH(s) first, then the accumulate form with L_k(s) uploaded for this s
+            op = self.H._dense_op(None)
+            self.ctx.check(self.ctx.lib.oqb_dense_update_cache(op, B, _lib.dptr(cf), int(sv.size == 1), None, 1, io.du.ptr))
+            lind.update_cache(io.du, p, t)
+            return io.finish()
         g = lind.gammas(sv) if lind else None
         op = self.H._dense_op(lind.L if lind else None)
         self.ctx.check(self.ctx.lib.oqb_dense_update_cache(op, B, _lib.dptr(cf), int(sv.size == 1), _lib.dptr(g),
@@ -1043,6 +1092,8 @@ class TrajectoryEnsemble:
             raise TypeError("TrajectoryEnsemble needs a SparseHamiltonian")
         self.op, self.H, self.ctx = op, op.H, op.ctx
         self.lind = op._lind[0] if op._lind else None
+        if self.lind is not None and self.lind.time_dependent:
+            raise NotImplementedError("trajectory ensembles need constant Lindblad operators (L_k(s) is evaluated per call only on the ρ path)")
         self.sp = self.H._sparse_op(self.lind.L if self.lind else None)
 
     def _coefs(self, p, t, B):

@@ -835,3 +835,28 @@ def test_density_stepper_rk4(Q, ame2q, kind):
     ref = np.stack([_rk4_oracle(lambda x, t: opo.rhs(x, po, t), u0[b], 0.1, dt, nsteps) for b in range(nb)])
     assert relerr(got, ref) < 1e-11
     assert np.allclose(np.trace(got, axis1=1, axis2=2), 1.0, atol=1e-10)  # trace preserved by every RHS on the path
+
+
+def test_lindblad_time_dependent_operators(Q):
+    """Lindblad(γ, L) with L a FUNCTION of s (src/coupling/interaction.jl:42,45-53): evaluated on the host per distinct s and
+    uploaded per call; batches with several s values are processed per s-group."""
+    rng = np.random.default_rng(64)
+    n, nb = 8, 6
+    Hd, Hp = -F.standard_driver(3), F.two_local_term([1.0, -0.7], [[1, 2], [2, 3]], 3)
+    Z1, X2 = F.single_clause(["z"], [1], 1.0, 3), F.single_clause(["x"], [2], 1.0, 3)
+    Lf = [lambda s: (1 - s) * Z1 + s * X2, lambda s: np.cos(s) * X2 + 1j * s * Z1]
+    gfs = [lambda s: 0.3 + s, lambda s: 0.1]
+    Hg, Ho = Q.DenseHamiltonian([A, B], [Hd, Hp]), O.DenseHamiltonian([A, B], [Hd, Hp])
+    lg = Q.LindbladLiouvillian([Q.Lindblad(g, L) for g, L in zip(gfs, Lf)] + [Q.Lindblad(0.2, Z1)])
+    lo = O.LindbladLiouvillian([O.Lindblad(g, L) for g, L in zip(gfs, Lf)] + [O.Lindblad(0.2, Z1)])
+    opg, opo = Q.DiffEqLiouvillian(Hg, [], [lg], n), O.DiffEqLiouvillian(Ho, [], [lo], n)
+    u = rand_rho(rng, nb, n)
+    tf = 2.0
+    pg, po = Q.ODEParams(Hg, tf), O.ODEParams(Ho, tf)
+    for t in (0.8, np.array([0.2, 1.4, 0.2, 0.9, 1.4, 1.9])):
+        got = opg(np.zeros_like(u), u, pg, t)
+        tv = np.broadcast_to(t, (nb,))
+        ref = np.stack([opo.rhs(u[b], po, float(tv[b])) for b in range(nb)])
+        assert relerr(got, ref) < TOL
+    cache = opg.update_cache(np.zeros((n, n), complex), pg, 0.8)
+    assert relerr(cache, opo.update_cache(po, 0.8)) < 1e-13
