@@ -1039,6 +1039,39 @@ class RedfieldLiouvillian:
                 Ss.append(ci(s) if callable(ci) else ci)
         return Ss, out
 
+    def lambda_device(self, p, t, ctx=None):
+        """Λ_ij(t) for every kernel pair, integrated on the DEVICE (csrc/redfield_lambda.cu) — available when `unitary`
+        is a `redfield_device.SampledUnitary` (samples of the closed-system solution on a uniform grid) and the couplings
+        are constant matrices or single-term callables handled through the node weights.  Returns (S_list, DeviceBatch)."""
+        from .redfield_device import LambdaBuilder, SampledUnitary
+        if not isinstance(self.unitary, SampledUnitary):
+            raise TypeError("lambda_device needs a SampledUnitary")
+        s = p(t)
+        pairs, cfs, Ss, Sj = [], [], [], []
+        for (inds, coupling, cfun) in self.kernels:
+            if any(callable(c) for c in coupling):
+                raise NotImplementedError("device Λ builder: constant coupling matrices (time dependence goes through cfun weights)")
+            base = len(Sj)
+            Sj += [np.asarray(c, dtype=C128) for c in coupling]
+            for (i, j) in inds:
+                pairs.append(base + j - 1)
+                cfs.append(cfun[(i, j)] if isinstance(cfun, dict) else cfun)
+                Ss.append(np.asarray(coupling[i - 1], dtype=C128))
+        key = id(self.unitary)
+        if getattr(self, "_lb_key", None) != key:
+            self._lb = LambdaBuilder(Sj, self.unitary.samples[None], self.unitary.dt, ctx=ctx)
+            self._lb_key = key
+
+        def cfun_all(q, tt, x):  # q: (m,1) integral numbers → that pair's correlation function on the node array
+            out = np.empty(x.shape, dtype=C128)
+            for row in range(x.shape[0]):
+                f = cfs[int(q[row, 0])]
+                out[row] = [f(float(tt[row, 0]), float(xv)) for xv in x[row]]
+            return out
+        Lam = self._lb.build(np.zeros(len(pairs), dtype=np.int32), np.asarray(pairs, dtype=np.int32), float(t), cfun_all,
+                             self.Ta, self.atol, self.rtol)
+        return Ss, Lam
+
     def apply(self, du, u, S_list, Lam):
         """du −= K₂+K₂' with Λ given: Lam (B, K, n, n) host array or DeviceBatch of B·K matrices."""
         io = _HostIO(u, du)
@@ -1061,6 +1094,13 @@ class RedfieldLiouvillian:
         """(R::RedfieldLiouvillian)(du,u,p,t) :42-71 — ACCUMULATES.  One Λ set shared by the batch."""
         io = _HostIO(u, du)
         B, n = io.u.B, io.u.rows
+        from .redfield_device import SampledUnitary
+        if isinstance(self.unitary, SampledUnitary):  # Λ on the device, broadcast over the batch without leaving HBM
+            Ss, Ld = self.lambda_device(p, float(np.atleast_1d(t)[0]), io.u.ctx)
+            K = len(Ss)
+            Lam = DeviceBatch(B * K, n, n, io.u.ctx, Ld.t[None].expand(B, K, n, n).reshape(B * K, n, n).contiguous())
+            self.apply(io.du, io.u, Ss, Lam)
+            return io.finish()
         Ss, Ls = self.lambda_host(p, float(np.atleast_1d(t)[0]))
         Lam = np.broadcast_to(np.stack(Ls)[None], (B, len(Ls), n, n))
         self.apply(io.du, io.u, Ss, Lam)

@@ -179,3 +179,34 @@ def test_ule_liouvillian(Q):
     for b in range(nb):
         ref = O.ULELiouvillian([(tuple(pairs), Ss, cf)], SampledUnitary(Us[b], dt), Ta, 1e-10, 1e-8).rhs_acc(du0[b].copy(), rho[b], p, t)
         assert relerr(got[b], ref) < 1e-12
+
+
+def test_redfield_liouvillian_call_uses_device_lambda(Q):
+    """The mirror of (R::RedfieldLiouvillian)(du,u,p,t) (src/opensys/redfield.jl:42-71) with a SampledUnitary: Λ is integrated
+    on the device inside the call (two kernels with different coupling sets, an off-diagonal pair, dict-valued cfun)."""
+    from oqb_b200.redfield_device import SampledUnitary
+    rng = np.random.default_rng(23)
+    n, nb, G, tf = 4, 3, 129, 2.0
+    A = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))
+    Us, dt = sample_unitary((A + A.conj().T) / 4, tf, G)
+    U = SampledUnitary(Us, dt)
+    Sa = [np.diag([1.0, -1, 1, -1]).astype(complex), np.diag([1.0, 1, -1, -1]).astype(complex)]
+    B_ = rng.standard_normal((n, n))
+    Sb = [(B_ + B_.T).astype(complex)]
+    c1 = {(1, 1): lambda t, x: np.exp(-(t - x)), (1, 2): lambda t, x: 0.3j * np.exp(-2 * (t - x)), (2, 2): lambda t, x: 0.5}
+    kernels = [(((1, 1), (1, 2), (2, 2)), Sa, c1), (((1, 1),), Sb, lambda t, x: np.cos(t - x))]
+    Rg = Q.RedfieldLiouvillian(kernels, U, 1.5, 1e-9, 1e-7)
+    Ro = O.RedfieldLiouvillian(kernels, U, 1.5, 1e-9, 1e-7)
+    rho = []
+    for b in range(nb):
+        g = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))
+        r = g @ g.conj().T
+        rho.append(r / np.trace(r).real)
+    rho = np.stack(rho)
+    du0 = rng.standard_normal((nb, n, n)) + 0j
+    got = Rg(du0.copy(), rho, O.ODEParams(None, tf, lambda tf_, t: t / tf_), 1.7)
+    p = O.ODEParams(None, tf, lambda tf_, t: t / tf_)
+    ref = np.stack([Ro.rhs_acc(du0[b].copy(), rho[b], p, 1.7) for b in range(nb)])
+    # four adaptive integrals at rtol 1e-7: a near-tie between two segment error estimates (constant C(t,x) on a dyadic
+    # grid) may bisect in a different order than the oracle — both results are far inside the requested tolerance
+    assert relerr(got - du0, ref - du0) < 1e-8
