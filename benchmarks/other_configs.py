@@ -104,6 +104,40 @@ def run_c2(Q, torch, steps, dense_L, nq=8, B=4096):
                          "peak_source": "DMMA issue probe, this run"}}
 
 
+def run_c3_onesided(Q, torch, steps, K=10, B=64):
+    """C3, one-sided AME: 10-qubit OneSidedAMELiouvillian, pairs (α,α) for K couplings Z_α, Ohmic γ, S ≡ 0."""
+    import bench
+    n = bench.N
+    Hd, Hp, coup = bench.build_c3()
+    coup = coup[:K]
+    H = Q.DenseHamiltonian([bench.fA, bench.fB], [Hd, Hp], unit="h")
+    osd = Q.OneSidedAMELiouvillian(Q.ConstantCouplings(coup, unit="h"), Q.Ohmic(bench.ETA, bench.FC, bench.TMK), Q.ZERO_LAMBSHIFT,
+                                   [(a + 1, a + 1) for a in range(K)])
+    op = Q.DiffEqLiouvillian(H, [osd], [], n)
+    ctx = Q.get_context()
+    op._prepare_ame(bench.S_POINT)
+    g = rand_states(torch, B, n, 32, 3100)
+    rho = g.transpose(1, 2) @ g.conj()
+    rho = rho / torch.diagonal(rho, dim1=1, dim2=2).sum(-1).real[:, None, None]
+    u = Q.DeviceBatch(B, n, n, ctx, rho.contiguous())
+    du = u.zeros_like()
+    fn = lambda: ctx.check(ctx.lib.oqb_ame_rhs(op._ame, B, u.ptr, du.ptr))
+    fn()
+    ctx.check(ctx.lib.oqb_profile_begin(ctx.h))
+    ms = timed(fn, steps, 3, torch)
+    zms, zn, zfl = C.c_double(), C.c_uint64(), C.c_double()
+    ctx.check(ctx.lib.oqb_profile_end(ctx.h, C.byref(zms), C.byref(zn), C.byref(zfl)))
+    flops = 8.0 * n ** 3 * (5 + 2 * K) * B  # 2 forward + P ρ̃ + K·(Λρ̃, ·A) + 2 back (SURVEY §8(d))
+    dmma, _ = ctx.probe_fp64()
+    ach = zfl.value / (zms.value * 1e-3) / 1e12
+    return {"config": f"C3-onesided-K{K}", "workload": f"10-qubit OneSidedAMELiouvillian, {K} pairs, batch {B} of {n}x{n} rho",
+            "metric": "rho_rhs_evals_per_sec", "value": B / (ms * 1e-3), "ms_per_step": ms,
+            "algorithmic_tflop_per_step": flops / 1e12, "step_tflops": flops / (ms * 1e-3) / 1e12,
+            "roofline": {"bound": "tensor", "kernel": "zgemm_tma_kernel", "achieved": ach, "peak": dmma, "unit": "TFLOP/s",
+                         "frac": ach / dmma, "frac_executed": ach * _exec_ratio() / dmma, "kernel_share_of_step": zms.value / ((3 + steps) * ms),
+                         "peak_source": "DMMA issue probe, this run"}}
+
+
 def tfim_sparse_c4(nq):
     """C4 operators: X-part (nq entries per row) and ZZ-part (diagonal) as CSC terms, L_k = Z_k sparse diagonal."""
     import scipy.sparse as sps
@@ -243,7 +277,7 @@ def run_c5(Q, torch, steps):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--configs", default="c2,c2general,c2dense,c2prime,c4,c5,c5general")
+    ap.add_argument("--configs", default="c2,c2general,c2dense,c2prime,c3onesided,c4,c5,c5general")
     ap.add_argument("--steps", type=int, default=5)
     args = ap.parse_args()
     import torch
@@ -272,6 +306,8 @@ def main():
             r = run_c2(Q, torch, args.steps, True)
         elif c == "c2prime":
             r = run_c2(Q, torch, args.steps, True, nq=10, B=64)
+        elif c == "c3onesided":
+            r = run_c3_onesided(Q, torch, args.steps)
         elif c == "c4":
             r = run_c4(Q, torch, args.steps)
         elif c == "c5":

@@ -33,7 +33,7 @@ int dalloc(oqb_ctx* c, void** p, size_t bytes) {
 bool needs_general_path(const oqb_ame* a) { return a->ncross > 0 || a->d_Moff || a->npairs > 0; }
 
 // Eigenbasis terms on ρ̃ = R (lvl×lvl per member).  overwrite: X = …, else X += ….
-// with_h: include −i[diag w, ρ̃].  scratch: (1 + 2*(npairs>0)) · nb·l² + nb·l complex.
+// with_h: include −i[diag w, ρ̃].  scratch: nb·l + (npairs > 0 ? (npairs + 1)·nb·l² : 0) complex.
 int eig_apply(oqb_ame* a, int nb, const c128* R, c128* X, bool overwrite, bool with_h, c128* scratch) {
     oqb_ctx* c = a->ctx;
     const int l = a->lvl;
@@ -41,7 +41,7 @@ int eig_apply(oqb_ame* a, int nb, const c128* R, c128* X, bool overwrite, bool w
     OQB_TRY(hadamard(c, l, a->d_Cm, with_h ? nullptr : a->d_w, R, X, nb, !overwrite));
     c128* pop = scratch;
     c128* M1 = scratch + (size_t)nb * l;
-    c128* Kb = M1 + (size_t)nb * ll;
+    c128* Kb = M1 + (size_t)nb * ll * (a->npairs > 0 ? a->npairs : 1);
     if (a->davies) {
         OQB_TRY(extract_diag(c, l, R, pop, nb));
         OQB_TRY(davies_diag(c, l, a->d_Wt, pop, X, nb));
@@ -64,22 +64,27 @@ int eig_apply(oqb_ame* a, int nb, const c128* R, c128* X, bool overwrite, bool w
             OQB_TRY(zgemm(c, q));
         }
     }
-    for (int pidx = 0; pidx < a->npairs; ++pidx) {  // src/opensys/davies.jl:369-378
-        const c128* Lam = a->d_Lam + (long long)pidx * ll;
-        const c128* Ab = a->d_A + (long long)a->h_beta[pidx] * ll;
-        ZgemmParams p;  // M1 = Λ ρ̃
-        p.M = p.N = p.K = l; p.batch = nb;
-        p.A = Lam; p.lda = l; p.strideA = 0;
-        p.B = R; p.ldb = l; p.strideB = ll;
-        p.C = M1; p.ldc = l; p.strideC = ll;
+    if (a->npairs > 0) {
+        // src/opensys/davies.jl:369-378:  K₂ = Σ_p (A_βΛ_p ρ̃ − Λ_p ρ̃ A_β) = P ρ̃ − [Λ_1ρ̃ | … | Λ_Pρ̃]·[A_β1; …; A_βP]
+        // with P = Σ_p A_βΛ_p precomputed per eigen-system: npairs + 1 products of depth l and ONE of depth npairs·l per
+        // member instead of 3·npairs products of depth l.
+        const int P = a->npairs;
+        ZgemmParams p;  // M1[b,p] = Λ_p ρ̃_b, the blocks of member b side by side (l × P·l)
+        p.M = p.N = p.K = l; p.batch = nb; p.batch2 = P;
+        p.A = a->d_Lam; p.lda = l; p.strideA = 0; p.strideA2 = ll;
+        p.B = R; p.ldb = l; p.strideB = ll; p.strideB2 = 0;
+        p.C = M1; p.ldc = l; p.strideC = (long long)P * ll; p.strideC2 = ll;
         OQB_TRY(zgemm(c, p));
-        ZgemmParams q = p;  // Kb = A_β M1
-        q.A = Ab; q.B = M1; q.C = Kb;
+        ZgemmParams q;  // Kb = P ρ̃
+        q.M = q.N = q.K = l; q.batch = nb;
+        q.A = a->d_Psum; q.lda = l; q.strideA = 0;
+        q.B = R; q.ldb = l; q.strideB = ll;
+        q.C = Kb; q.ldc = l; q.strideC = ll;
         OQB_TRY(zgemm(c, q));
-        ZgemmParams r;  // Kb −= M1 A_β
-        r.M = r.N = r.K = l; r.batch = nb;
-        r.A = M1; r.lda = l; r.strideA = ll;
-        r.B = Ab; r.ldb = l; r.strideB = 0;
+        ZgemmParams r;  // Kb −= M1stack · Abstack   (depth P·l)
+        r.M = r.N = l; r.K = P * l; r.batch = nb;
+        r.A = M1; r.lda = l; r.strideA = (long long)P * ll;
+        r.B = a->d_Abstack; r.ldb = (long long)P * l; r.strideB = 0;
         r.C = Kb; r.ldc = l; r.strideC = ll;
         r.alpha = make_double2(-1.0, 0.0);
         r.beta = make_double2(1.0, 0.0);
@@ -91,7 +96,7 @@ int eig_apply(oqb_ame* a, int nb, const c128* R, c128* X, bool overwrite, bool w
 
 size_t eig_scratch_elems(const oqb_ame* a, int nb) {
     const size_t ll = (size_t)a->lvl * a->lvl;
-    return (size_t)nb * a->lvl + (a->npairs > 0 ? 2 * (size_t)nb * ll : 0);
+    return (size_t)nb * a->lvl + (a->npairs > 0 ? ((size_t)a->npairs + 1) * nb * ll : 0);
 }
 
 int ame_rhs_impl(oqb_ame* a, int nb, const c128* u, c128* du) {
@@ -203,6 +208,8 @@ int oqb_ame_clear_davies(oqb_ame* a) {
 int oqb_ame_clear_onesided(oqb_ame* a) {
     cudaStreamSynchronize(a->ctx->stream);
     dfree(a->d_Lam);
+    dfree(a->d_Psum);
+    dfree(a->d_Abstack);
     a->npairs = 0;
     a->h_beta.clear();
     return 0;
@@ -390,6 +397,22 @@ int oqb_ame_set_onesided(oqb_ame* a, int npairs, const int32_t* h_alpha, const i
     if (s) return s;
     a->npairs = npairs;
     a->h_beta.assign(h_beta, h_beta + npairs);
+    // per eigen-system: P = Σ_p A_βp Λ_p and the vertical stack [A_β1; …; A_βP] (npairs·l × l)
+    OQB_TRY(dalloc(c, (void**)&a->d_Psum, ll * sizeof(c128)));
+    OQB_TRY(dalloc(c, (void**)&a->d_Abstack, (size_t)npairs * ll * sizeof(c128)));
+    for (int p = 0; p < npairs; ++p) {
+        const c128* Ab = a->d_A + (long long)h_beta[p] * ll;
+        ZgemmParams g;
+        g.M = g.N = g.K = l; g.batch = 1;
+        g.A = Ab; g.lda = l;
+        g.B = a->d_Lam + (long long)p * ll; g.ldb = l;
+        g.C = a->d_Psum; g.ldc = l;
+        g.beta = p == 0 ? make_double2(0.0, 0.0) : make_double2(1.0, 0.0);
+        OQB_TRY(zgemm(c, g));
+        OQB_CUDA(c, cudaMemcpy2DAsync(a->d_Abstack + (long long)p * l, (size_t)npairs * l * sizeof(c128), Ab, (size_t)l * sizeof(c128),
+                                      (size_t)l * sizeof(c128), l, cudaMemcpyDeviceToDevice, c->stream));
+    }
+    OQB_CUDA(c, cudaStreamSynchronize(c->stream));
     return 0;
 }
 

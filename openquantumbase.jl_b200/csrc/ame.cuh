@@ -25,6 +25,8 @@ struct oqb_ame {
     int npairs = 0;
     std::vector<int32_t> h_beta;
     oqb::c128* d_Lam = nullptr;  // npairs lvl×lvl
+    oqb::c128* d_Psum = nullptr;     // Σ_p A_βp Λ_p (lvl×lvl)
+    oqb::c128* d_Abstack = nullptr;  // [A_β1; …; A_βP]  (npairs·lvl × lvl)
     // ame_jump tables (ame_jump.cu): probability slots in the reference's order
     int nslots = 0;
     long long nterms = 0;
