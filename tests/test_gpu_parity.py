@@ -860,3 +860,40 @@ def test_lindblad_time_dependent_operators(Q):
         assert relerr(got, ref) < TOL
     cache = opg.update_cache(np.zeros((n, n), complex), pg, 0.8)
     assert relerr(cache, opo.update_cache(po, 0.8)) < 1e-13
+
+
+def test_device_against_committed_golden_file(Q):
+    """The CUDA path against tests/golden/reference_known_answers.json (the reference's own known answers, transcribed by
+    tests/golden/make_golden.py): Lindblad RHS and cache, DenseHamiltonian values, CorrelatedDavies closed forms, Redfield Λ."""
+    import json
+    import os
+    import scipy.linalg as sla
+    from oqb_b200.extra_liouvillians import CorrelatedDaviesGenerator
+    from oqb_b200.redfield_device import LambdaBuilder
+    G = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_known_answers.json")))
+    cm = lambda x: np.asarray(x, dtype=float)[..., 0] + 1j * np.asarray(x, dtype=float)[..., 1]
+    ops = {"sx": sx, "sz": sz, "sigma_plus": np.array([[0, 1], [0, 0]], dtype=complex),
+           "sigma_minus": np.array([[0, 0], [1, 0]], dtype=complex)}
+    states = {"|+x><+x|": np.outer(F.PauliVec[0][0], F.PauliVec[0][0].conj()),
+              "|+y><+y|": np.outer(F.PauliVec[1][0], F.PauliVec[1][0].conj())}
+    p = Q.ODEParams(None, 5.0)
+    for key, ckey in (("lindblad_rhs_Lz_on_plus_x", "lindblad_cache_Lz"), ("lindblad_rhs_Lz_Lx_on_plus_y", "lindblad_cache_Lz_Lx")):
+        g = G[key]
+        L = Q.LindbladLiouvillian([Q.Lindblad(gm, ops[o]) for gm, o in zip(g["gamma"], g["ops"])])
+        assert np.allclose(L(np.zeros((2, 2), complex), states[g["state"]], p, 5.0), cm(g["drho"]), atol=1e-15)
+        assert np.allclose(L.update_cache(np.zeros((2, 2), complex), p, 5.0), cm(G[ckey]["cache"]), atol=1e-15)
+    g = G["dense_hamiltonian_half"]
+    H = Q.DenseHamiltonian([A, B], [sx, sz])
+    assert np.allclose(H(g["s"]), cm(g["H"]), atol=1e-15)
+    assert np.allclose(H.update_cache(np.zeros((2, 2), complex), g["s"]), cm(g["cache"]), atol=1e-15)
+    for key in ("correlated_davies_zero", "correlated_davies_closed_form"):
+        g = G[key]
+        gfun = lambda w: 1.0 if w >= 0 else np.exp(-0.5)
+        inds = [tuple(x) for x in g["inds"]]
+        D = CorrelatedDaviesGenerator([ops[c] for c in g["couplings"]], {i: gfun for i in inds}, {i: (lambda w: 0.0) for i in inds}, inds)
+        assert np.allclose(D(np.zeros((2, 2), complex), cm(g["rho"]), np.array(g["w"]), g["s"]), cm(g["du"]), atol=1e-15)
+    g = G["redfield_lambda_code_form"]  # analytic unitary sampled finely: the grid error stays below the fixture tolerance × 100
+    Gn = 4097
+    Us = np.stack([sla.expm(-1j * (5.0 * k / (Gn - 1)) * sx) for k in range(Gn)])
+    Lam = LambdaBuilder([sz], Us[None], 5.0 / (Gn - 1)).build([0], [0], 5.0, lambda q, t, x: np.ones_like(x), 5.0, 1e-8, 1e-6).to_host()[0]
+    assert np.allclose(Lam, cm(g["Lambda"]), atol=1e-5)

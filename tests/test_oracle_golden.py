@@ -358,3 +358,47 @@ def test_ule_golden():
     d = ule.rhs_acc(np.zeros((2, 2), complex), rho, p, 5.0)
     exp = L @ rho @ L.conj().T - 0.5 * (L.conj().T @ L @ rho + rho @ L.conj().T @ L)
     assert close(d, exp)                                                                  # :19
+
+
+# ---- tests/golden/reference_known_answers.json (transcribed from the reference's tests by tests/golden/make_golden.py) ----
+def _gold():
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_known_answers.json")) as f:
+        return json.load(f)
+
+
+def _cm(x):
+    a = np.asarray(x, dtype=float)
+    return a[..., 0] + 1j * a[..., 1]
+
+
+def test_oracle_against_committed_golden_file():
+    G = _gold()
+    ops = {"sx": sx, "sz": sz, "sigma_plus": np.array([[0, 1], [0, 0]], dtype=complex),
+           "sigma_minus": np.array([[0, 0], [1, 0]], dtype=complex)}
+    states = {"|+x><+x|": np.outer(F.PauliVec[0][0], F.PauliVec[0][0].conj()),
+              "|+y><+y|": np.outer(F.PauliVec[1][0], F.PauliVec[1][0].conj())}
+    p = O.ODEParams(None, 5.0, lambda tf, t: t / tf)
+    for key in ("lindblad_rhs_Lz_on_plus_x", "lindblad_rhs_Lz_Lx_on_plus_y"):
+        g = G[key]
+        L = O.LindbladLiouvillian([O.Lindblad(gm, ops[o]) for gm, o in zip(g["gamma"], g["ops"])])
+        assert np.allclose(L.rhs_acc(np.zeros((2, 2), complex), states[g["state"]], p, 5.0), _cm(g["drho"]), atol=1e-15)
+    g = G["dense_hamiltonian_half"]
+    H = O.DenseHamiltonian([A, B], [sx, sz])
+    assert np.array_equal(H(g["s"]), _cm(g["H"])) and np.array_equal(H.update_cache(g["s"]), _cm(g["cache"]))
+    for key in ("correlated_davies_zero", "correlated_davies_closed_form"):
+        g = G[key]
+        gfun = lambda w: 1.0 if w >= 0 else np.exp(-0.5)
+        inds = [tuple(x) for x in g["inds"]]
+        D = O.CorrelatedDaviesGenerator([ops[c] for c in g["couplings"]], {i: gfun for i in inds}, {i: (lambda w: 0.0) for i in inds}, inds)
+        du = D.rhs_acc(np.zeros((2, 2), complex), _cm(g["rho"]), O.build_gap_indices(np.array(g["w"]), 8, 8), None, g["s"])
+        assert np.allclose(du, _cm(g["du"]), atol=1e-15)
+    g = G["redfield_lambda_code_form"]
+    red = O.RedfieldLiouvillian([(((1, 1),), [sz], lambda t1, t2: 1.0)], lambda t: sla.expm(-1j * t * sx), 5.0, 1e-8, 1e-6)
+    assert np.allclose(red.Lambda(p, 5.0, [sz], lambda t1, t2: 1.0, 1), _cm(g["Lambda"]), atol=g["tolerance"])
+    g = G["odeparams"]
+    assert O.ODEParams(None, g["tf"], lambda tf, t: t / tf)(g["t"]) == g["s"]
+    g = G["ohmic_gamma0"]
+    bath = O.Ohmic(g["eta"], g["fc"], g["T"])
+    assert bath.spectrum(0.0) == 2 * np.pi * g["eta"] / bath.beta
