@@ -78,3 +78,12 @@ def test_host_mirror_argument_errors(Q):
     w4, v4 = np.linalg.eigh(np.kron(sz, sz))
     with pytest.raises(ValueError):                      # a supplied (w, v) belongs to ONE s
         op.rhs_with_eig(np.zeros_like(u), u, Q.ODEParams(H, 1.0), np.array([0.1, 0.9]), w4, v4)
+
+
+def test_plain_c_host_program(c_demo_exe):
+    """examples/c_abi_demo.c — a host program in C calling the ABI directly — reproduces the reference's Lindblad and
+    commutator known answers (test/opensys/lindblad.jl:25-31, test/hamiltonian/dense_hamiltonian.jl:35-38)."""
+    import subprocess
+    out = subprocess.run([c_demo_exe], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "kernels launched" in out.stdout

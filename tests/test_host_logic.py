@@ -190,3 +190,14 @@ def test_cross_lists_from_device_grouping_match_gapgroups():
         assert np.array_equal(li, G.lamb_idx) and np.array_equal(lk, G.lamb_key)
         i2, j2 = pair_to_ij(l, np.arange(len(iu)))
         assert np.array_equal(i2, iu) and np.array_equal(j2, ju)
+
+
+def test_c_abi_header_is_plain_c_and_links(c_demo_exe):
+    """include/oqb.h is a C header (no C++/torch types) and every symbol the demo uses resolves at link time; without a GPU
+    the program stops at oqb_create with a clear message and a non-zero exit code (no CPU fallback)."""
+    import subprocess
+    import torch
+    exe = c_demo_exe
+    if not torch.cuda.is_available():
+        out = subprocess.run([exe], capture_output=True, text=True)
+        assert out.returncode == 3 and "no CPU fallback" in out.stderr
