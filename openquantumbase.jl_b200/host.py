@@ -692,9 +692,9 @@ class DiffEqLiouvillian:
         ctx.check(lib.oqb_dense_rhs(h, B, _lib.dptr(one), 1, None, 1, io.u.ptr, io.du.ptr))  # :136 (OVERWRITES)
         ctx.sync()
         lib.oqb_dense_destroy(h)
-        if not self.diagonalization:
-            if self.opensys:
-                raise NotImplementedError("adiabatic-frame `opensys` terms (ConstDaviesGenerator) are not on the device path")
+        if not self.diagonalization:  # {false,true} :142-149 — lv(du, u, nothing, s) for ConstDavies / ConstHDavies terms
+            for lv in self.opensys:
+                lv(io.du, io.u, None, s)
             return io.finish()
         self._prepare_ame(s, np.real(np.diag(Hm)).copy(), None)
         ctx.check(lib.oqb_ame_eig_acc(self._ame, B, io.u.ptr, io.du.ptr, 0))
@@ -952,6 +952,13 @@ class DiffEqLiouvillian:
     def update_cache(self, cache, p, t, w=None, v=None):
         """update_cache!(cache, Op, p, t): :78-83 ({false,false}) or :111-128 ({true,false}) — OVERWRITES."""
         s = float(np.atleast_1d(p(t))[0])
+        if self.adiabatic_frame and not self.diagonalization:  # {false,true} :151-158 — cache = −iH(tf, s), then the terms
+            io = _HostIO(cache, cache)
+            Hm = np.asarray(self.H(p.tf, s), dtype=C128)
+            io.du.t.copy_(DeviceBatch.from_host(np.broadcast_to(-1j * Hm, (io.u.B,) + Hm.shape).copy(), self.ctx).t)
+            for lv in self.opensys:
+                lv.update_cache(io.du, p, t)
+            return io.finish()
         if self.diagonalization:
             io = _HostIO(cache, cache)
             self._prepare_ame(s, w, v)

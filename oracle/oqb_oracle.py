@@ -787,14 +787,14 @@ class ConstDaviesGenerator:
     def __init__(self, Linds, Hls, A):
         self.Linds, self.Hls, self.A = Linds, Hls, A
 
-    def rhs_acc(self, du, rho):  # :111-117 — ACCUMULATES
+    def rhs_acc(self, du, rho, *_):  # :111-117 — ACCUMULATES; (D)(du, ρ, ::Any, ::Any)
         for L in self.Linds:
             LL = L.conj().T @ L
             du += L @ rho @ L.conj().T - 0.5 * (LL @ rho + rho @ LL)
         du -= 1.0j * (self.Hls @ rho - rho @ self.Hls)
         return du
 
-    def update_cache_acc(self, cache):  # :119
+    def update_cache_acc(self, cache, *_):  # :119
         cache += self.A
         return cache
 
@@ -835,8 +835,8 @@ class ConstHDaviesGenerator:
         self.gap_idx = gap_idx
         self.D = DaviesGenerator(coupling, gamma, S)
 
-    def rhs_acc(self, du, rho, s):
-        return self.D.rhs_acc(du, rho, self.gap_idx, None, s)
+    def rhs_acc(self, du, rho, *args):  # (D)(du, ρ, ::Any, s)
+        return self.D.rhs_acc(du, rho, self.gap_idx, None, args[-1])
 
 
 class CorrelatedDaviesGenerator:

@@ -897,3 +897,34 @@ def test_device_against_committed_golden_file(Q):
     Us = np.stack([sla.expm(-1j * (5.0 * k / (Gn - 1)) * sx) for k in range(Gn)])
     Lam = LambdaBuilder([sz], Us[None], 5.0 / (Gn - 1)).build([0], [0], 5.0, lambda q, t, x: np.ones_like(x), 5.0, 1e-8, 1e-6).to_host()[0]
     assert np.allclose(Lam, cm(g["Lambda"]), atol=1e-5)
+
+
+def test_adiabatic_frame_with_const_davies(Q):
+    """DiffEqLiouvillian{false,true} (src/opensys/diffeq_liouvillian.jl:142-158): adiabatic-frame Hamiltonian + a
+    ConstDaviesGenerator in `opensys` — RHS and update_cache! against the oracle."""
+    from oqb_b200.extra_liouvillians import build_const_davies
+    rng = np.random.default_rng(606)
+    n, nb = 4, 3
+    wfun = lambda s: np.array([-1.0, -0.2 + 0.1 * s, 0.4, 1.3 - 0.2 * s])
+    geo = lambda s: 0.05 * np.array([[0, 1j, 0, 0], [-1j, 0, 1j, 0], [0, -1j, 0, 1j], [0, 0, -1j, 0]])
+    cs = [(lambda x: x + x.conj().T)(rand_c(rng, n, n)) * 0.2]
+    w0 = 2 * np.pi * wfun(0.0)
+    Dg = build_const_davies(cs, w0, gamma, lamb)
+    Do = O.build_const_davies(cs, O.build_gap_indices(w0, 8, 8), gamma, lamb)
+    Hg = Q.AdiabaticFrameHamiltonian(wfun, geo)
+    opg = Q.DiffEqLiouvillian(Hg, [], [Dg], n)
+
+    class HoFrame:  # H(tf, s) of the adiabatic frame for the oracle: 2π diag(ω(s)) + G(s)/tf
+        size = (n, n)
+
+        def __call__(self, tf, s):
+            return np.diag(2 * np.pi * wfun(s)).astype(complex) + geo(s) / tf
+    opo = O.DiffEqLiouvillian(HoFrame(), [], [Do], n, adiabatic_frame=True)
+    u = rand_rho(rng, nb, n)
+    tf = 3.0
+    pg, po = Q.ODEParams(None, tf), O.ODEParams(None, tf)
+    got = opg(rand_c(rng, nb, n, n), u, pg, 1.2)  # overwrites du
+    ref = np.stack([opo.rhs(u[b], po, 1.2) for b in range(nb)])
+    assert relerr(got, ref) < TOL
+    cache = opg.update_cache(np.zeros((n, n), complex), pg, 1.2)
+    assert relerr(cache, opo.update_cache(po, 1.2)) < 1e-13
