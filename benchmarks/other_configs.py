@@ -138,6 +138,73 @@ def run_c3_onesided(Q, torch, steps, K=10, B=64):
                          "peak_source": "DMMA issue probe, this run"}}
 
 
+def run_c3_lambshift(Q, torch, steps, B=64):
+    """C3 with the Lamb shift switched on ("S from a 1001-point table on [−50,50]"):
+    (1) build_lambshift's tabulation — 1001 adaptive quadratures — on the device vs the CPU port on a sample,
+    (2) the per-call eigen-system cost with the S(ω̃_ab) table evaluated from the spline on the device vs on the host,
+    (3) the resident RHS rate (the tables are precomputed, so it must equal the S ≡ 0 number)."""
+    import time
+    import bench
+    from oracle import oqb_oracle as O
+    n = bench.N
+    Hd, Hp, coup = bench.build_c3()
+    H = Q.DenseHamiltonian([bench.fA, bench.fB], [Hd, Hp], unit="h")
+    bath = Q.Ohmic(bench.ETA, bench.FC, bench.TMK)
+    ctx = Q.get_context()
+    w_range = np.linspace(-50, 50, 1001)
+    bath.S(w_range[:8])  # warm-up (workspace growth, module load)
+    t0 = time.perf_counter()
+    S_tab, err, nseg = bath.S(w_range, info=True)
+    t_dev = time.perf_counter() - t0
+    bo = O.Ohmic(bench.ETA, bench.FC, bench.TMK)
+    sample = np.arange(0, 1001, 25)
+    t0 = time.perf_counter()
+    S_cpu = np.array([O.lambshift(w_range[i], bo.spectrum) for i in sample])
+    t_cpu = (time.perf_counter() - t0) / len(sample) * len(w_range)
+    S_fn = Q.build_lambshift(w_range, True, bath)
+    op = Q.DiffEqLiouvillian(H, [Q.DaviesGenerator(Q.ConstantCouplings(coup, unit="h"), bath, S_fn)], [], n)
+    op.plan_cache = 1
+    prep = {}
+    for mode in ("host_tables", "device_tables"):
+        op.device_eigh, op.device_tables = True, mode == "device_tables"
+        best = 1e9
+        for k in range(3):
+            t0 = time.perf_counter()
+            op._prepare_ame(bench.S_POINT + 0.01 * (k + 1) + (0.004 if mode == "device_tables" else 0.0))
+            ctx.sync()
+            best = min(best, time.perf_counter() - t0)
+        prep[mode + "_s"] = best
+    g = rand_states(torch, B, n, 32, 3300)
+    rho = g.transpose(1, 2) @ g.conj()
+    rho = rho / torch.diagonal(rho, dim1=1, dim2=2).sum(-1).real[:, None, None]
+    u = Q.DeviceBatch(B, n, n, ctx, rho.contiguous())
+    du = u.zeros_like()
+    w_chk, v_chk = Q.haml_eigs(H, bench.S_POINT, n)
+    p = Q.ODEParams(H, bench.TF)
+    chk = []
+    for flag in (False, True):
+        op.device_eigh, op.device_tables = False, flag
+        op.clear_plans()
+        chk.append(op.rhs_with_eig(du.zeros_like(), u, p, bench.S_POINT * bench.TF, w_chk, v_chk).t.clone())
+    rel = float((chk[0] - chk[1]).norm().item() / chk[0].norm().item())
+    op0 = Q.DiffEqLiouvillian(H, [Q.DaviesGenerator(Q.ConstantCouplings(coup, unit="h"), bath, Q.ZERO_LAMBSHIFT)], [], n)
+    d0 = op0.rhs_with_eig(du.zeros_like(), u, p, bench.S_POINT * bench.TF, w_chk, v_chk).t
+    lamb_effect = float((chk[1] - d0).norm().item() / chk[1].norm().item())
+    del chk, d0
+    fn = lambda: ctx.check(ctx.lib.oqb_ame_rhs(op._ame, B, u.ptr, du.ptr))
+    fn()
+    ms = timed(fn, steps, 3, torch)
+    return {"config": "C3-lambshift", "workload": f"10-qubit DaviesGenerator with tabulated Lamb shift (1001-point spline on [-50,50]), batch {B}",
+            "metric": "rho_rhs_evals_per_sec", "value": B / (ms * 1e-3), "ms_per_step": ms,
+            "lambshift_table": {"points": 1001, "device_s": t_dev, "cpu_port_s_extrapolated": t_cpu, "cpu_sample_points": len(sample),
+                                "speedup": t_cpu / t_dev, "segments_median": float(np.median(nseg)), "segments_max": int(nseg.max()),
+                                "max_rel_diff_vs_cpu_port_on_sample": float(np.max(np.abs(S_tab[sample] - S_cpu) / np.abs(S_cpu))),
+                                "rtol": 1.4901161193847656e-08},
+            "per_call_eigensystem_with_lambshift": dict(prep, evals_per_sec_incl_host_tables=B / (ms * 1e-3 + prep["host_tables_s"]),
+                                                        evals_per_sec_incl_device_tables=B / (ms * 1e-3 + prep["device_tables_s"])),
+            "device_tables_rel_diff_vs_host_tables": rel, "rhs_rel_change_due_to_lambshift": lamb_effect}
+
+
 def tfim_sparse_c4(nq):
     """C4 operators: X-part (nq entries per row) and ZZ-part (diagonal) as CSC terms, L_k = Z_k sparse diagonal."""
     import scipy.sparse as sps
@@ -308,6 +375,8 @@ def main():
             r = run_c2(Q, torch, args.steps, True, nq=10, B=64)
         elif c == "c3onesided":
             r = run_c3_onesided(Q, torch, args.steps)
+        elif c == "c3lamb":
+            r = run_c3_lambshift(Q, torch, args.steps)
         elif c == "c4":
             r = run_c4(Q, torch, args.steps)
         elif c == "c5":

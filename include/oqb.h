@@ -188,6 +188,11 @@ int oqb_ame_set_davies(oqb_ame* ame, const double* h_gam, const double* h_S, int
  * multi-pair gap groups / to the zero group.  oqb_ame_davies_fetch_groups returns those pairs as lexicographic pair
  * indices p(i<j) = i·l − i(i+1)/2 + (j−i−1) (multi pairs sorted by key, stable) with their keys; the host turns them into
  * the cross-term lists (same arrays as oqb_ame_set_davies) and oqb_ame_davies_ohmic_finish installs them. */
+/* Tabulated Lamb shift for the device-built tables: the n+2 prefiltered coefficients of the quadratic B-spline that
+ * build_lambshift / construct_interpolations return for a range grid x0 + k·dx, k = 0…n−1 (src/bath/bath_util.jl:26-38,
+ * src/interpolation.jl:22-34; Interpolations.jl BSpline(Quadratic(Line(OnGrid()))), value 0 outside the grid).
+ * oqb_ame_davies_ohmic_begin then fills S(ω̃_ab) from it on the device; n = 0 restores S ≡ 0. */
+int oqb_ame_set_lambshift_spline(oqb_ame* ame, int n, double x0, double dx, const double* h_coef);
 int oqb_ame_davies_ohmic_begin(oqb_ame* ame, double eta, double wc, double beta, int digits, int sigdigits,
                                int64_t* n_multi, int64_t* n_zero);
 int oqb_ame_davies_fetch_groups(oqb_ame* ame, int32_t* h_multi_pair, double* h_multi_key, int32_t* h_zero_pair);
@@ -294,6 +299,17 @@ int oqb_traj_rng_uniform(oqb_sparse* sp, int nb, uint64_t* d_state, double* d_ou
 int oqb_traj_evolve(oqb_sparse* sp, int nb, int nsteps, double dt, const double* h_coefH, int coef_shared,
                     const double* h_gamma, int gamma_shared, void* d_psi, uint64_t* d_rng, double* d_threshold,
                     int32_t* d_njumps, int32_t* d_log, int max_log, int step0);
+
+/* ---------------------------------------------------------------------------------- bath ----- */
+/* S(ω) of an Ohmic bath for n frequencies (src/bath/bath_util.jl:17 → lambshift, src/integration/ext_util.jl:23-28:
+ * S = −(1/2π)∫₀^∞ (γ(ω+x) − γ(ω−x))/x dx by adaptive G7K15 on QuadGK's t/(1−t) map, stop at E ≤ atol or E ≤ rtol|I|;
+ * QuadGK's defaults are rtol = √eps, atol = 0): one device thread per frequency with its own segment heap
+ * (at most max_segments segments).  h_err (error estimates) and h_nseg (segments used) may be NULL. */
+int oqb_ohmic_lambshift(oqb_ctx* ctx, double eta, double wc, double beta, int n, const double* h_w, double rtol,
+                        double atol, int max_segments, double* h_S, double* h_err, int32_t* h_nseg);
+/* y[k] = spline(x[k]) for the quadratic B-spline of oqb_ame_set_lambshift_spline (host arrays; m points). */
+int oqb_bspline_eval(oqb_ctx* ctx, int n, double x0, double dx, const double* h_coef, int m, const double* h_x,
+                     double* h_y);
 
 /* ------------------------------------------------------------------------- observables ----- */
 /* out[b][o] = tr(O_o ρ[b]) (is_vector==0, state n×n) or ψ[b]'O_oψ[b] (is_vector!=0); complex

@@ -223,6 +223,7 @@ int oqb_ame_destroy(oqb_ame* a) {
     oqb_ame_clear_onesided(a);
     oqb_ame_clear_jump(a);
     if (a->d_grp_key) cudaFree(a->d_grp_key);
+    if (a->d_Scoef) cudaFree(a->d_Scoef);
     if (a->d_grp_pair) cudaFree(a->d_grp_pair);
     (void)he;
     dfree(a->d_coup); dfree(a->d_V); dfree(a->d_w); dfree(a->d_A); dfree(a->d_Cm);

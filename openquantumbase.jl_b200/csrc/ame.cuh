@@ -37,6 +37,10 @@ struct oqb_ame {
     double* d_grp_key = nullptr;
     int32_t* d_grp_pair = nullptr;
     long long n_multi = 0, n_zero = 0;
+    // tabulated Lamb shift for the device-built tables: quadratic B-spline coefficients (n_Stab+2) on x0 + k·dx
+    int n_Stab = 0;
+    double S_x0 = 0.0, S_dx = 1.0;
+    double* d_Scoef = nullptr;
 };
 
 // ame.cu internals shared with ame_gaps.cu (defined inside ame.cu's extern "C" block; not part of the public ABI)

@@ -20,6 +20,7 @@
 
 #include "../../include/oqb.h"
 #include "ame.cuh"
+#include "bath.cuh"
 #include "common.cuh"
 
 using namespace oqb;
@@ -56,14 +57,8 @@ __device__ __forceinline__ double round_sigdigits(double x, int sig) {
     return isfinite(r) ? r : x;
 }
 
-__device__ __forceinline__ double ohmic(double w, double eta, double wc, double beta) {
-    const double two_pi = 6.283185307179586;
-    if (fabs(w) <= 1e-9) return __ddiv_rn(__dmul_rn(two_pi, eta), beta);  // γ(0) = 2πη/β  (ohmic.jl:37)
-    const double num = __dmul_rn(__dmul_rn(__dmul_rn(two_pi, eta), w), exp(-fabs(w) / wc));
-    return __ddiv_rn(num, 1.0 - exp(-beta * w));
-}
-
 __global__ void gap_table_kernel(int l, const double* __restrict__ w, double thr, int sig, double eta, double wc, double beta,
+                                 int nS, double S_x0, double S_dx, const double* __restrict__ S_coef,
                                  double* __restrict__ gam, double* __restrict__ S, double* __restrict__ keys,
                                  int32_t* __restrict__ pairs, unsigned long long* __restrict__ nzero) {
     const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -83,8 +78,8 @@ __global__ void gap_table_kernel(int l, const double* __restrict__ w, double thr
             if (zero) atomicAdd(nzero, 1ull);
         }
     }
-    gam[e] = ohmic(key, eta, wc, beta);
-    S[e] = 0.0;
+    gam[e] = ohmic_spectrum(key, eta, wc, beta);
+    S[e] = nS ? bspline2_eval(key, nS, S_x0, S_dx, S_coef) : 0.0;  // tabulated Lamb shift (build_lambshift) or S ≡ 0
 }
 
 __global__ void flag_multi_kernel(long long m, const double* __restrict__ keys, uint8_t* __restrict__ flag) {
@@ -99,6 +94,22 @@ __global__ void flag_multi_kernel(long long m, const double* __restrict__ keys, 
 }  // namespace
 
 extern "C" {
+
+int oqb_ame_set_lambshift_spline(oqb_ame* a, int n, double x0, double dx, const double* h_coef) {
+    if (!a) return OQB_EINVAL;
+    oqb_ctx* c = a->ctx;
+    if (n < 0 || (n > 0 && (!h_coef || !(dx > 0.0)))) return set_error(c, OQB_EINVAL, "oqb_ame_set_lambshift_spline: bad argument");
+    OQB_CUDA(c, cudaStreamSynchronize(c->stream));
+    dfree(a->d_Scoef);
+    a->n_Stab = 0;
+    if (n == 0) return 0;
+    OQB_CUDA(c, cudaMalloc((void**)&a->d_Scoef, (size_t)(n + 2) * 8));
+    OQB_CUDA(c, cudaMemcpy(a->d_Scoef, h_coef, (size_t)(n + 2) * 8, cudaMemcpyHostToDevice));
+    a->n_Stab = n;
+    a->S_x0 = x0;
+    a->S_dx = dx;
+    return 0;
+}
 
 int oqb_ame_davies_ohmic_begin(oqb_ame* a, double eta, double wc, double beta, int digits, int sigdigits, int64_t* n_multi,
                                int64_t* n_zero) {
@@ -144,7 +155,8 @@ int oqb_ame_davies_ohmic_begin(oqb_ame* a, double eta, double wc, double beta, i
     void* cub_tmp = (void*)(((uintptr_t)(cnt + 4) + 255) & ~(uintptr_t)255);  // cub wants a 256-byte aligned blob
     OQB_CUDA(c, cudaMemsetAsync(cnt, 0, 4 * sizeof(unsigned long long), c->stream));
     gap_table_kernel<<<(unsigned)((ll + 255) / 256), 256, 0, c->stream>>>(l, a->d_w, pow(10.0, -(double)digits), sigdigits, eta, wc,
-                                                                          beta, a->d_gam, a->d_S, k_in, p_in, cnt);
+                                                                          beta, a->n_Stab, a->S_x0, a->S_dx, a->d_Scoef, a->d_gam, a->d_S,
+                                                                          k_in, p_in, cnt);
     OQB_LAUNCH_CHECK(c);
     size_t t1 = tmp;
     OQB_CUDA(c, cub::DeviceRadixSort::SortPairs(cub_tmp, t1, k_in, k_out, p_in, p_out, (int)m, 0, 64, c->stream));

@@ -22,6 +22,8 @@ import numpy as np
 from . import _lib
 from .gaps import GapGroups, ohmic_spectrum_vec
 
+_SQRT_EPS = math.sqrt(np.finfo(np.float64).eps)  # quadgk's default rtol
+
 C128 = np.complex128
 
 
@@ -605,6 +607,19 @@ class OhmicBath:
     def vectorized(self, w):
         return ohmic_spectrum_vec(self.eta, self.wc, self.beta, w)
 
+    def S(self, w, rtol=_SQRT_EPS, atol=0.0, max_segments=1024, ctx: Optional[Context] = None, info=False):
+        """S(w, bath) of src/bath/bath_util.jl:17 — lambshift(w, ω -> spectrum(ω, bath)) with quadgk's keyword
+        defaults — for a scalar or an array of frequencies: one device thread per frequency runs the adaptive G7K15
+        (csrc/bath.cu).  `info=True` also returns the error estimates and segment counts."""
+        ctx = ctx or get_context()
+        wv = np.ascontiguousarray(np.atleast_1d(np.asarray(w, dtype=np.float64)).ravel())
+        out, err = np.empty_like(wv), np.empty_like(wv)
+        nseg = np.empty(wv.size, dtype=np.int32)
+        ctx.check(ctx.lib.oqb_ohmic_lambshift(ctx.h, self.eta, self.wc, self.beta, wv.size, wv.ctypes.data, rtol, atol,
+                                              max_segments, out.ctypes.data, err.ctypes.data, nseg.ctypes.data))
+        res = float(out[0]) if np.ndim(w) == 0 else out.reshape(np.shape(w))
+        return (res, err, nseg) if info else res
+
 
 def Ohmic(eta, fc, T) -> OhmicBath:
     """src/bath/ohmic.jl:24-28 with temperature_2_β of src/unit_util.jl:13-15."""
@@ -620,6 +635,77 @@ class _Zero:
 
 
 ZERO_LAMBSHIFT = _Zero()  # build_lambshift(..., turn_on=false) → (ω)->0.0, src/bath/bath_util.jl:36-38
+
+
+class QuadraticBSpline:
+    """What construct_interpolations(x::AbstractRange, y) returns with its defaults (src/interpolation.jl:22-34):
+    Interpolations.jl's BSpline(Quadratic(Line(OnGrid()))) scaled to the range, 0 outside it.  The n+2 prefiltered
+    coefficients (⅛, ¾, ⅛ rows closed by c₀ − 2c₁ + c₂ = 0 at both ends) are computed once here; evaluation at the l²
+    gaps of an eigen-system happens on the device (oqb_ame_set_lambshift_spline)."""
+
+    def __init__(self, x0: float, dx: float, y):
+        y = np.asarray(y, dtype=np.float64)
+        n = y.shape[0]
+        if n < 3 or not dx > 0:
+            raise ValueError("QuadraticBSpline needs at least 3 points on an increasing range")
+        self.x0, self.dx, self.n = float(x0), float(dx), n
+        M = np.zeros((n + 2, n + 2))
+        M[0, :3] = (1.0, -2.0, 1.0)
+        M[n + 1, n - 1:] = (1.0, -2.0, 1.0)
+        idx = np.arange(1, n + 1)
+        M[idx, idx - 1], M[idx, idx], M[idx, idx + 1] = 0.125, 0.75, 0.125
+        rhs = np.zeros(n + 2)
+        rhs[1:n + 1] = y
+        self.coef = self._banded(M, rhs)
+
+    @staticmethod
+    def _banded(M, rhs):
+        import scipy.linalg as _sla
+        m = M.shape[0]
+        ab = np.zeros((5, m))  # bandwidth 2 each side covers the closure rows
+        for d in range(-2, 3):
+            diag = np.diagonal(M, d)
+            if d >= 0:
+                ab[2 - d, d:] = diag
+            else:
+                ab[2 - d, :m + d] = diag
+        return np.ascontiguousarray(_sla.solve_banded((2, 2), ab, rhs))
+
+    def vectorized(self, x):
+        x = np.asarray(x, dtype=np.float64)
+        u = (x - self.x0) / self.dx
+        inside = (u >= 0) & (u <= self.n - 1)
+        i = np.clip(np.floor(np.where(inside, u, 0.0) + 0.5).astype(np.int64), 0, self.n - 1)
+        d = np.where(inside, u, 0.0) - i
+        c = self.coef
+        val = c[i] * (0.5 * (d - 0.5) ** 2) + c[i + 1] * (0.75 - d * d) + c[i + 2] * (0.5 * (d + 0.5) ** 2)
+        return np.where(inside, val, 0.0)
+
+    def __call__(self, x):
+        return float(self.vectorized(x))
+
+    def on_device(self, x, ctx: Optional[Context] = None):
+        """The same evaluation by the device routine the gap tables use (oqb_bspline_eval)."""
+        ctx = ctx or get_context()
+        xv = np.ascontiguousarray(np.asarray(x, dtype=np.float64).ravel())
+        out = np.empty_like(xv)
+        ctx.check(ctx.lib.oqb_bspline_eval(ctx.h, self.n, self.x0, self.dx, self.coef.ctypes.data, xv.size,
+                                           xv.ctypes.data, out.ctypes.data))
+        return out.reshape(np.shape(x))
+
+
+def build_lambshift(w_range, turn_on: bool, bath, rtol=_SQRT_EPS, atol=0.0):
+    """src/bath/bath_util.jl:26-38 for an OhmicBath: S ≡ 0 when off; `bath.S` (device quadrature per call) when
+    `w_range` is empty; else the quadratic B-spline through [S(ω) for ω in ω_range], tabulated in one launch."""
+    if not turn_on:
+        return ZERO_LAMBSHIFT
+    if len(w_range) == 0:
+        return lambda w: bath.S(w, rtol=rtol, atol=atol)
+    w_range = np.asarray(w_range, dtype=np.float64)
+    step = np.diff(w_range)
+    if not np.allclose(step, step[0], rtol=1e-12, atol=0.0):
+        raise NotImplementedError("build_lambshift: non-uniform grids (Gridded(Linear())) are not on the device path")
+    return QuadraticBSpline(w_range[0], (w_range[-1] - w_range[0]) / (len(w_range) - 1), bath.S(w_range, rtol=rtol, atol=atol))
 
 
 # --------------------------------------------------------------------------------------------
@@ -802,7 +888,8 @@ class DiffEqLiouvillian:
             ctx.check(lib.oqb_ame_set_eigen(h, _lib.dptr(w), vbuf.ctypes.data))
         dev_tables = (getattr(self, "device_tables", False) and len(self.opensys_eig) == 1
                       and isinstance(self.opensys_eig[0], DaviesGenerator)
-                      and isinstance(self.opensys_eig[0].gamma, OhmicBath) and isinstance(self.opensys_eig[0].S, _Zero))
+                      and isinstance(self.opensys_eig[0].gamma, OhmicBath)
+                      and isinstance(self.opensys_eig[0].S, (_Zero, QuadraticBSpline)))
         groups = None if dev_tables else GapGroups(w, self.digits, self.sigdigits)  # :96
         ndav = 0
         for lv, (c0, c1) in zip(self.opensys_eig, slices):
@@ -812,6 +899,10 @@ class DiffEqLiouvillian:
                 from .gaps import cross_lists_from_groups
                 nm, nz = C.c_int64(), C.c_int64()
                 bath = lv.gamma
+                if isinstance(lv.S, QuadraticBSpline):  # tabulated Lamb shift: S(ω̃_ab) from the spline on the device
+                    ctx.check(lib.oqb_ame_set_lambshift_spline(h, lv.S.n, lv.S.x0, lv.S.dx, lv.S.coef.ctypes.data))
+                else:
+                    ctx.check(lib.oqb_ame_set_lambshift_spline(h, 0, 0.0, 1.0, None))
                 ctx.check(lib.oqb_ame_davies_ohmic_begin(h, bath.eta, bath.wc, bath.beta, self.digits, self.sigdigits,
                                                          C.byref(nm), C.byref(nz)))
                 mp, mk = np.empty(nm.value, dtype=np.int32), np.empty(nm.value, dtype=np.float64)
@@ -821,7 +912,8 @@ class DiffEqLiouvillian:
                                                               zp.ctypes.data_as(_lib.c_i32p)))
                 ci, ck, li, lk = cross_lists_from_groups(lvl, mp, mk, zp)
                 crate = np.ascontiguousarray(bath.vectorized(ck)) if len(ck) else np.zeros(0)
-                lrs = np.ascontiguousarray(np.stack([bath.vectorized(lk), np.zeros(len(lk))], axis=1)) if len(lk) else np.zeros((0, 2))
+                lrs = (np.ascontiguousarray(np.stack([bath.vectorized(lk), lv.S.vectorized(lk)], axis=1)) if len(lk)
+                       else np.zeros((0, 2)))
                 ci, li = np.ascontiguousarray(ci), np.ascontiguousarray(li)
                 ctx.check(lib.oqb_ame_davies_ohmic_finish(
                     h, len(ci), ci.ctypes.data_as(_lib.c_i32p) if len(ci) else None, _lib.dptr(crate) if len(ci) else None,

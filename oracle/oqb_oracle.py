@@ -15,6 +15,10 @@ tests only pin loosely are marked "parity unpinned" below:
   * StatsBase.jl (compat 0.30-0.34) `sample(Weights)` inverse-CDF scan — restated in
     `sample_weights`; reference test checks membership only (test/opensys/lindblad.jl:48-50).
   * Base.round(x, sigdigits=n) — restated in `round_sigdigits` from Julia Base floatfuncs.jl.
+  * Interpolations.jl (compat 0.12-0.14) BSpline(Quadratic(Line(OnGrid()))) — restated in
+    `QuadraticBSpline` from its published prefilter system and basis; pinned by the reference's
+    own known answers (test/interpolations.jl:3-22: linear data reproduced, 0 outside the grid,
+    gradient) and test/coupling_bath_interaction/bath.jl:76 (tabulated Lamb shift).
 
 All file:line citations are relative to /root/reference.  Arrays are numpy complex128;
 indices are 0-based here (the reference is 1-based) unless a function says otherwise.
@@ -50,6 +54,14 @@ def temperature_2_beta(T: float) -> float:
     return 5 * 6.62607004 / 1.38064852 / np.pi / T
 
 
+def _exp(x: float) -> float:
+    """IEEE exp as Julia's: overflows to Inf instead of raising."""
+    try:
+        return math.exp(x)
+    except OverflowError:
+        return math.inf
+
+
 @dataclass
 class OhmicBath:
     """src/bath/ohmic.jl:13-17."""
@@ -61,7 +73,7 @@ class OhmicBath:
         """src/bath/ohmic.jl:35-41 (isapprox(ω,0,atol=1e-9) ⇔ |ω| ≤ 1e-9)."""
         if abs(w) <= 1e-9:
             return 2 * np.pi * self.eta / self.beta
-        return 2 * np.pi * self.eta * w * math.exp(-abs(w) / self.wc) / (1 - math.exp(-self.beta * w))
+        return 2 * np.pi * self.eta * w * _exp(-abs(w) / self.wc) / (1 - _exp(-self.beta * w))
 
     __call__ = spectrum
 
@@ -601,6 +613,83 @@ def quadgk(f, a, b, rtol, atol, maxevals=10 ** 7):
         I = I + sgm[4]
         E = E + sgm[5]
     return I, E
+
+
+def quadgk_semi_infinite(f, a, rtol, atol, maxevals=10 ** 7):
+    """quadgk(f, a, Inf): QuadGK.jl maps [a,∞) onto t∈[0,1) with x = a + t/(1−t) and integrates
+    f(a + t·den)·den·den, den = 1/(1−t), with the same adaptive rule [external QuadGK 2.x]."""
+    def g(t):
+        den = 1.0 / (1.0 - t)
+        return f(a + t * den) * den * den
+    return quadgk(g, 0.0, 1.0, rtol, atol, maxevals)
+
+
+def lambshift(w, gamma, rtol=math.sqrt(np.finfo(float).eps), atol=0.0):
+    """src/integration/ext_util.jl:23-28: S(ω) = −(1/2π)∫₀^∞ (γ(ω+x) − γ(ω−x))/x dx (quadgk defaults
+    rtol = √eps, atol = 0)."""
+    integral, _ = quadgk_semi_infinite(lambda x: (gamma(w + x) - gamma(w - x)) / x, 0.0, rtol, atol)
+    return -integral / 2 / np.pi
+
+
+class QuadraticBSpline:
+    """construct_interpolations(x::AbstractRange, y) with the defaults of src/interpolation.jl:22-34:
+    scale(extrapolate(interpolate(y, BSpline(Quadratic(Line(OnGrid())))), 0), x).
+
+    Interpolations.jl's quadratic B-spline [external, 0.12-0.14]: n+2 coefficients c₀…c_{n+1} solve
+    c_{i−1}/8 + ¾c_i + c_{i+1}/8 = y_i (i = 1…n) with the `Line(OnGrid())` closure c₀ − 2c₁ + c₂ = 0,
+    c_{n−1} − 2c_n + c_{n+1} = 0; at index coordinate u, i = round(u), δ = u − i:
+    value = c_{i−1}·½(δ−½)² + c_i·(¾−δ²) + c_{i+1}·½(δ+½)²; outside [1,n] the fill value 0."""
+
+    def __init__(self, x0: float, dx: float, y):
+        y = np.asarray(y)
+        n = y.shape[0]
+        self.x0, self.dx, self.n = float(x0), float(dx), n
+        M = np.zeros((n + 2, n + 2))
+        rhs = np.zeros(n + 2, dtype=y.dtype)
+        M[0, :3] = (1.0, -2.0, 1.0)
+        M[n + 1, n - 1:] = (1.0, -2.0, 1.0)
+        for i in range(1, n + 1):
+            M[i, i - 1:i + 2] = (0.125, 0.75, 0.125)
+            rhs[i] = y[i - 1]
+        self.c = np.linalg.solve(M, rhs)
+
+    def _locate(self, x):
+        u = (x - self.x0) / self.dx  # 0-based index coordinate
+        if u < 0 or u > self.n - 1:
+            return None
+        i = int(np.floor(u + 0.5))
+        i = min(max(i, 0), self.n - 1)
+        return i, u - i
+
+    def __call__(self, x):
+        loc = self._locate(x)
+        if loc is None:
+            return self.c.dtype.type(0)
+        i, d = loc
+        c = self.c
+        return c[i] * (0.5 * (d - 0.5) ** 2) + c[i + 1] * (0.75 - d * d) + c[i + 2] * (0.5 * (d + 0.5) ** 2)
+
+    def gradient(self, x):
+        """src/interpolation.jl gradient(itp, x) (Interpolations.gradient1, chain rule 1/dx)."""
+        loc = self._locate(x)
+        if loc is None:
+            return self.c.dtype.type(0)
+        i, d = loc
+        c = self.c
+        return (c[i] * (d - 0.5) + c[i + 1] * (-2 * d) + c[i + 2] * (d + 0.5)) / self.dx
+
+
+def build_lambshift(w_range, turn_on: bool, bath, **quad_kwargs):
+    """src/bath/bath_util.jl:26-38: S ≡ 0 when off; per-call quadgk when `w_range` is empty; else a
+    quadratic B-spline through [S(ω) for ω in ω_range] (0 outside the range)."""
+    if not turn_on:
+        return lambda w: 0.0
+    gam = bath.spectrum if hasattr(bath, "spectrum") else bath
+    if len(w_range) == 0:
+        return lambda w: lambshift(w, gam, **quad_kwargs)
+    w_range = np.asarray(w_range, dtype=float)
+    s_list = np.array([lambshift(w, gam, **quad_kwargs) for w in w_range])
+    return QuadraticBSpline(w_range[0], (w_range[-1] - w_range[0]) / (len(w_range) - 1), s_list)
 
 
 class RedfieldLiouvillian:

@@ -928,3 +928,84 @@ def test_adiabatic_frame_with_const_davies(Q):
     assert relerr(got, ref) < TOL
     cache = opg.update_cache(np.zeros((n, n), complex), pg, 1.2)
     assert relerr(cache, opo.update_cache(po, 1.2)) < 1e-13
+
+
+@pytest.mark.gpu
+def test_ohmic_lambshift_device(Q):
+    """Row B: S(ω, bath) = lambshift(ω, γ) (bath_util.jl:17, ext_util.jl:23-28) by the per-thread adaptive G7K15 of
+    csrc/bath.cu against the oracle's quadgk restatement.  Both stop at QuadGK's default rtol = √eps ≈ 1.5e-8, and the
+    device exp() may differ from libm's in the last bit, so the two adaptive runs are only REQUIRED to agree to the
+    quadrature tolerance (asserted: 1e-7 relative); in practice they bisect identically and agree to ~1e-13, which is
+    asserted for the median.  Known answer: test/coupling_bath_interaction/bath.jl:14-16."""
+    bath_g, bath_o = Q.OhmicBath(1e-4, 8 * np.pi, 1 / 2.23), O.OhmicBath(1e-4, 8 * np.pi, 1 / 2.23)
+    assert np.isclose(bath_g.S(0.0), -0.0025132734115775254, rtol=1e-4, atol=1e-4)
+    bath_g, bath_o = Q.Ohmic(1e-4, 4, 16), O.Ohmic(1e-4, 4, 16)
+    ws = np.concatenate([np.linspace(-50, 50, 41), [1e-10, -1e-3, 0.37]])
+    S_dev, err, nseg = bath_g.S(ws, info=True)
+    S_ref = np.array([O.lambshift(w, bath_o.spectrum) for w in ws])
+    rel = np.abs(S_dev - S_ref) / np.abs(S_ref)
+    assert rel.max() < 1e-7 and np.median(rel) < 1e-12
+    assert np.all(err <= 1.5e-8 * np.abs(S_dev) * 1.0001) and nseg.max() < 1024  # every integral converged
+    # tighter request → more segments (ω = 1e-10 sits on the isapprox(ω, 0) switch of ohmic.jl:36 and runs into the
+    # segment cap); the result moves by no more than a few times the first request's tolerance
+    S_tight, _, nseg2 = bath_g.S(ws, rtol=1e-12, info=True)
+    assert np.all(nseg2 >= nseg) and np.max(np.abs(S_tight - S_dev) / np.abs(S_dev)) < 1e-6
+
+
+@pytest.mark.gpu
+def test_bspline_device_eval(Q):
+    """construct_interpolations' quadratic B-spline (interpolation.jl:22-34) evaluated by the device routine the gap
+    tables use, against the oracle's restatement: grid points, midpoints, random points, both ends, outside (fill 0)."""
+    rng = np.random.default_rng(77)
+    x0, dx, n = -5.0, 10 / 200, 201
+    y = np.sin(np.linspace(-5, 5, n)) * np.exp(-0.1 * np.linspace(-5, 5, n) ** 2)
+    sp_g, sp_o = Q.QuadraticBSpline(x0, dx, y), O.QuadraticBSpline(x0, dx, y)
+    assert np.allclose(sp_g.coef, sp_o.c, rtol=0, atol=1e-14)
+    xs = np.concatenate([x0 + dx * np.arange(n), x0 + dx * (np.arange(n - 1) + 0.5), rng.uniform(-5, 5, 500),
+                         [-5.0, 5.0, -5.0000001, 5.0000001, -7.0, 9.0]])
+    ref = np.array([sp_o(v) for v in xs]).real
+    assert np.max(np.abs(sp_g.on_device(xs) - ref)) < 1e-14
+    assert np.max(np.abs(sp_g.vectorized(xs) - ref)) < 1e-14
+    assert np.max(np.abs(sp_g.vectorized(x0 + dx * np.arange(n)) - y)) < 1e-13  # interpolates the data
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("degenerate", [False, True])
+def test_ame_device_tables_tabulated_lambshift(Q, degenerate):
+    """DaviesGenerator with the Lamb shift build_lambshift tabulates over ω_range (bath_util.jl:26-38): the S(ω̃_ab)
+    table is evaluated from the spline ON THE DEVICE (device_tables) and must reproduce both the host-table path and
+    the oracle's literal loop with its own spline through the same samples."""
+    rng = np.random.default_rng(321)
+    nq, lvl, nb = 4, 16, 3
+    n = 2 ** nq
+    Hd = -F.standard_driver(nq)
+    if degenerate:
+        Hp = -F.two_local_term([1.0] * (nq - 1), [[i, i + 1] for i in range(1, nq)], nq)
+    else:
+        Hp = F.two_local_term(list(rng.standard_normal(nq - 1)), [[i, i + 1] for i in range(1, nq)], nq) \
+            + sum(rng.standard_normal() * F.single_clause(["z"], [k + 1], 1.0, nq) for k in range(nq))
+    coup = [F.single_clause(["z"], [k + 1], 1.0, nq) for k in range(2)]
+    Hg, Ho = Q.DenseHamiltonian([A, B], [Hd, Hp]), O.DenseHamiltonian([A, B], [Hd, Hp])
+    bath_g, bath_o = Q.Ohmic(1e-2, 4, 16), O.Ohmic(1e-2, 4, 16)
+    w_range = np.linspace(-30, 30, 601)  # narrower than the spectrum for s = 0.35: some gaps fall outside → S = 0 there
+    S_g = Q.build_lambshift(w_range, True, bath_g)
+    assert isinstance(S_g, Q.QuadraticBSpline)
+    samples = S_g.vectorized(w_range)
+    S_o = O.QuadraticBSpline(w_range[0], (w_range[-1] - w_range[0]) / 600, samples)
+    mk = lambda: Q.DiffEqLiouvillian(Hg, [Q.DaviesGenerator(Q.ConstantCouplings(coup, unit="h"), bath_g, S_g)], [], lvl)
+    op_host, op_dev = mk(), mk()
+    op_dev.device_tables = True
+    u = rand_rho(rng, nb, n)
+    s = 0.35 if not degenerate else 1.0
+    w, v = O.haml_eigs(Ho, s, lvl)
+    p = Q.ODEParams(Hg, 2.0)
+    d_host = op_host.rhs_with_eig(np.zeros_like(u), u, p, 2.0 * s, w, v)
+    d_dev = op_dev.rhs_with_eig(np.zeros_like(u), u, p, 2.0 * s, w, v)
+    assert relerr(d_dev, d_host) < 1e-13
+    opo = O.DiffEqLiouvillian(Ho, [O.DaviesGenerator([2 * np.pi * c for c in coup], bath_o.spectrum, lambda x: S_o(x).real)], [], lvl)
+    ref = np.stack([opo.rhs_with_eig(u[b], O.ODEParams(Ho, 2.0), 2.0 * s, w, v) for b in range(nb)])
+    assert relerr(d_dev, ref) < TOL
+    # the Lamb shift matters in this case (the test would not notice a dropped table otherwise)
+    op0 = Q.DiffEqLiouvillian(Hg, [Q.DaviesGenerator(Q.ConstantCouplings(coup, unit="h"), bath_g, Q.ZERO_LAMBSHIFT)], [], lvl)
+    d0 = op0.rhs_with_eig(np.zeros_like(u), u, p, 2.0 * s, w, v)
+    assert relerr(d0, ref) > 1e-6 or degenerate

@@ -201,3 +201,19 @@ def test_c_abi_header_is_plain_c_and_links(c_demo_exe):
     if not torch.cuda.is_available():
         out = subprocess.run([exe], capture_output=True, text=True)
         assert out.returncode == 3 and "no CPU fallback" in out.stderr
+
+
+def test_quadratic_bspline_host_coefficients():
+    """Host mirror of construct_interpolations (interpolation.jl:22-34): banded prefilter solve and the vectorised
+    evaluation agree with the oracle's dense restatement; linear data is reproduced (test/interpolations.jl:3-17)."""
+    from oqb_b200 import host as H
+    x = np.linspace(0, 10, 100)
+    sp, so = H.QuadraticBSpline(0.0, 10 / 99, 10 - x), O.QuadraticBSpline(0.0, 10 / 99, 10 - x)
+    assert np.allclose(sp.coef, so.c, rtol=0, atol=1e-13)
+    tx = np.linspace(0, 10, 50)
+    assert np.allclose(sp.vectorized(tx), 10 - tx) and sp(-1) == 0 and sp(11) == 0
+    rng = np.random.default_rng(5)
+    y = rng.standard_normal(37)
+    sp, so = H.QuadraticBSpline(-2.0, 0.25, y), O.QuadraticBSpline(-2.0, 0.25, y)
+    xs = rng.uniform(-3, 8, 200)
+    assert np.max(np.abs(sp.vectorized(xs) - np.array([so(v) for v in xs]))) < 1e-13

@@ -402,3 +402,28 @@ def test_oracle_against_committed_golden_file():
     g = G["ohmic_gamma0"]
     bath = O.Ohmic(g["eta"], g["fc"], g["T"])
     assert bath.spectrum(0.0) == 2 * np.pi * g["eta"] / bath.beta
+
+
+def test_lambshift_known_answers():
+    """test/coupling_bath_interaction/bath.jl:14-16 (S(0) of the Ohmic bath against the cpvagk value, rtol 1e-4) and
+    :72-80 (correlated-bath spectrum: quadgk per call and the 1000-point spline both give 0.03551, atol 1e-4)."""
+    bath = O.OhmicBath(1e-4, 8 * np.pi, 1 / 2.23)
+    assert np.isclose(O.lambshift(0.0, bath.spectrum), -0.0025132734115775254, rtol=1e-4, atol=1e-4)
+    gfun = lambda w: np.exp(-w) if w >= 0 else np.exp(0.8 * w)
+    assert abs(O.lambshift(0.0, gfun) - 0.03551) < 1e-4
+    assert O.build_lambshift([0.0], False, gfun)(0.5) == 0
+    S_tab = O.build_lambshift(np.linspace(-5, 5, 1000), True, gfun)
+    assert abs(S_tab(0.0) - 0.03551) < 1e-4
+
+
+def test_quadratic_bspline_known_answers():
+    """test/interpolations.jl:3-22: linear data on a 100-point range is reproduced on a 50-point range, the value
+    outside the grid is the fill value 0, the gradient of 10 − x is −1."""
+    x = np.linspace(0, 10, 100)
+    itp = O.QuadraticBSpline(0.0, 10 / 99, 10 - x)
+    itc = O.QuadraticBSpline(0.0, 10 / 99, x + 1j * x)
+    tx = np.linspace(0, 10, 50)
+    assert np.allclose([itp(v) for v in tx], 10 - tx) and np.allclose([itc(v) for v in tx], tx + 1j * tx)
+    assert itc(-1) == 0 and isinstance(itc(-1), complex) or np.iscomplexobj(itc(-1))
+    assert itp(11) == 0
+    assert np.isclose(itp.gradient(2.3), -1) and np.allclose([itp.gradient(v) for v in (0.13, 0.21)], [-1, -1])
