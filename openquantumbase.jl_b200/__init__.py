@@ -9,6 +9,6 @@ from .host import (  # noqa: F401
     ZERO_LAMBSHIFT, AdiabaticFrameHamiltonian, ConstantCouplings, Context, DaviesGenerator, DenseHamiltonian, DensityStepper, DeviceBatch,
     DiffEqLiouvillian, GapIndices, Lindblad, LindbladLiouvillian, ODEParams, Ohmic, OhmicBath,
     OneSidedAMELiouvillian, QuadraticBSpline, RedfieldLiouvillian, SparseHamiltonian, TrajectoryEnsemble, TrajectoryStepper, ensemble_population, expect, expect_diag,
-    build_lambshift, get_context, haml_eigs, unit_scale, update_cache_, update_vectorized_cache_,
+    build_lambshift, get_context, haml_eigs, lambshift, unit_scale, update_cache_, update_vectorized_cache_,
 )
 from .build import build  # noqa: F401

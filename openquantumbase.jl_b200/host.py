@@ -694,11 +694,38 @@ class QuadraticBSpline:
         return out.reshape(np.shape(x))
 
 
+def lambshift(w, gamma, rtol=_SQRT_EPS, atol=0.0):
+    """src/integration/ext_util.jl:23-28 for a spectrum given as an arbitrary HOST closure (CustomBath, the entries of
+    a CorrelatedBath spectrum matrix, src/bath/custom.jl:61-80): the closure can only be evaluated where it lives, so
+    this is the host quadrature of quadrature.py on QuadGK's t/(1−t) map.  OhmicBath.S is the device version."""
+    from .quadrature import quadgk_matrix
+
+    def g(t):
+        den = 1.0 / (1.0 - t)
+        x = t * den
+        return (gamma(w + x) - gamma(w - x)) / x * den * den
+    integral = quadgk_matrix(g, 0.0, 1.0, rtol, atol)
+    return -float(integral) / 2 / math.pi
+
+
+class _ClosureBath:
+    def __init__(self, gamma):
+        self.gamma = gamma
+
+    def S(self, w, rtol=_SQRT_EPS, atol=0.0):
+        if np.ndim(w) == 0:
+            return lambshift(float(w), self.gamma, rtol, atol)
+        return np.array([lambshift(float(x), self.gamma, rtol, atol) for x in np.ravel(w)]).reshape(np.shape(w))
+
+
 def build_lambshift(w_range, turn_on: bool, bath, rtol=_SQRT_EPS, atol=0.0):
-    """src/bath/bath_util.jl:26-38 for an OhmicBath: S ≡ 0 when off; `bath.S` (device quadrature per call) when
-    `w_range` is empty; else the quadratic B-spline through [S(ω) for ω in ω_range], tabulated in one launch."""
+    """src/bath/bath_util.jl:26-38: S ≡ 0 when off; `bath.S` per call when `w_range` is empty; else the quadratic
+    B-spline through [S(ω) for ω in ω_range].  For an OhmicBath the quadratures run on the device (one launch for the
+    whole table); a bare spectrum closure is integrated on the host (`lambshift`)."""
     if not turn_on:
         return ZERO_LAMBSHIFT
+    if not hasattr(bath, "S"):
+        bath = _ClosureBath(bath.spectrum if hasattr(bath, "spectrum") else bath)
     if len(w_range) == 0:
         return lambda w: bath.S(w, rtol=rtol, atol=atol)
     w_range = np.asarray(w_range, dtype=np.float64)

@@ -46,6 +46,14 @@ GOLD = {
     "ohmic_gamma0": {"source": "test/coupling_bath_interaction/bath.jl:3-14", "eta": 1e-4, "fc": 4, "T": 16,
                       "rule": "gamma(0) == 2*pi*eta/beta"},
     "odeparams": {"source": "test/annealing.jl:19-22", "tf": 10.0, "t": 5.0, "s": 0.5},
+    "ohmic_lambshift_at_zero": {"source": "test/coupling_bath_interaction/bath.jl:3-16", "eta": 1e-4, "wc": 8 * math.pi,
+                                "beta": 1 / 2.23, "w": 0.0, "S": -0.0025132734115775254, "rtol": 1e-4, "atol": 1e-4},
+    "lambshift_piecewise_exponential_spectrum": {"source": "test/coupling_bath_interaction/bath.jl:58-80",
+                                                 "spectrum": "w >= 0 ? exp(-w) : exp(0.8w)", "w": 0.0, "S": 0.03551,
+                                                 "atol": 1e-4, "table": {"lo": -5, "hi": 5, "length": 1000}},
+    "bspline_linear_data": {"source": "test/interpolations.jl:3-22", "grid": {"lo": 0, "hi": 10, "length": 100},
+                            "y": "10 - x", "test_grid": {"lo": 0, "hi": 10, "length": 50}, "outside": [[-1, 0.0], [11, 0.0]],
+                            "gradient": -1.0},
 }
 
 if __name__ == "__main__":

@@ -897,6 +897,14 @@ def test_device_against_committed_golden_file(Q):
     Us = np.stack([sla.expm(-1j * (5.0 * k / (Gn - 1)) * sx) for k in range(Gn)])
     Lam = LambdaBuilder([sz], Us[None], 5.0 / (Gn - 1)).build([0], [0], 5.0, lambda q, t, x: np.ones_like(x), 5.0, 1e-8, 1e-6).to_host()[0]
     assert np.allclose(Lam, cm(g["Lambda"]), atol=1e-5)
+    g = G["ohmic_lambshift_at_zero"]  # device quadrature against the reference's cpvagk value
+    assert np.isclose(Q.OhmicBath(g["eta"], g["wc"], g["beta"]).S(g["w"]), g["S"], rtol=g["rtol"], atol=g["atol"])
+    g = G["bspline_linear_data"]  # device spline evaluation reproduces linear data and fills 0 outside
+    x = np.linspace(g["grid"]["lo"], g["grid"]["hi"], g["grid"]["length"])
+    itp = Q.QuadraticBSpline(x[0], x[1] - x[0], 10 - x)
+    tx = np.linspace(g["test_grid"]["lo"], g["test_grid"]["hi"], g["test_grid"]["length"])
+    assert np.allclose(itp.on_device(tx), 10 - tx)
+    assert np.array_equal(itp.on_device(np.array([xo for xo, _ in g["outside"]], dtype=float)), [yo for _, yo in g["outside"]])
 
 
 def test_adiabatic_frame_with_const_davies(Q):

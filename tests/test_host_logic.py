@@ -217,3 +217,16 @@ def test_quadratic_bspline_host_coefficients():
     sp, so = H.QuadraticBSpline(-2.0, 0.25, y), O.QuadraticBSpline(-2.0, 0.25, y)
     xs = rng.uniform(-3, 8, 200)
     assert np.max(np.abs(sp.vectorized(xs) - np.array([so(v) for v in xs]))) < 1e-13
+
+
+def test_lambshift_host_closure_known_answer():
+    """lambshift of a spectrum given as a host closure (ext_util.jl:23-28) and its tabulated spline
+    (bath_util.jl:26-38): test/coupling_bath_interaction/bath.jl:58-80 expects 0.03551 (atol 1e-4) from both."""
+    from oqb_b200 import host as H
+    gfun = lambda w: np.exp(-w) if w >= 0 else np.exp(0.8 * w)
+    assert abs(H.lambshift(0.0, gfun) - 0.03551) < 1e-4
+    assert abs(H.lambshift(0.3, gfun) - O.lambshift(0.3, gfun)) < 1e-12
+    assert H.build_lambshift([0.0], False, gfun)(0.5) == 0
+    S_tab = H.build_lambshift(np.linspace(-5, 5, 200), True, gfun)
+    assert isinstance(S_tab, H.QuadraticBSpline) and abs(S_tab(0.0) - 0.03551) < 2e-3  # coarser table than the reference's
+    assert abs(H.build_lambshift([], True, gfun)(0.0) - 0.03551) < 1e-4

@@ -402,6 +402,19 @@ def test_oracle_against_committed_golden_file():
     g = G["ohmic_gamma0"]
     bath = O.Ohmic(g["eta"], g["fc"], g["T"])
     assert bath.spectrum(0.0) == 2 * np.pi * g["eta"] / bath.beta
+    g = G["ohmic_lambshift_at_zero"]
+    assert np.isclose(O.lambshift(g["w"], O.OhmicBath(g["eta"], g["wc"], g["beta"]).spectrum), g["S"], rtol=g["rtol"], atol=g["atol"])
+    g = G["lambshift_piecewise_exponential_spectrum"]
+    gfun = lambda w: np.exp(-w) if w >= 0 else np.exp(0.8 * w)
+    assert abs(O.lambshift(g["w"], gfun) - g["S"]) < g["atol"]
+    tb = g["table"]
+    assert abs(O.build_lambshift(np.linspace(tb["lo"], tb["hi"], tb["length"]), True, gfun)(g["w"]) - g["S"]) < g["atol"]
+    g = G["bspline_linear_data"]
+    x = np.linspace(g["grid"]["lo"], g["grid"]["hi"], g["grid"]["length"])
+    itp = O.QuadraticBSpline(x[0], x[1] - x[0], 10 - x)
+    tx = np.linspace(g["test_grid"]["lo"], g["test_grid"]["hi"], g["test_grid"]["length"])
+    assert np.allclose([itp(v) for v in tx], 10 - tx) and all(itp(xo) == yo for xo, yo in g["outside"])
+    assert np.isclose(itp.gradient(2.3), g["gradient"])
 
 
 def test_lambshift_known_answers():
