@@ -212,6 +212,10 @@ int oqb_ame_get_rotated_couplings(oqb_ame* ame, void* h_A);
  * or one shared table when tables_shared != 0 (SingleFunctionMatrix). */
 int oqb_ame_set_onesided(oqb_ame* ame, int npairs, const int32_t* h_alpha, const int32_t* h_beta,
                          const double* h_gam, const double* h_S, int tables_shared);
+/* The same with the shared tables built ON THE DEVICE for an Ohmic bath: γ(w[b] − w[a]) in closed form and S from the
+ * spline of oqb_ame_set_lambshift_spline (S ≡ 0 when none is set). */
+int oqb_ame_set_onesided_ohmic(oqb_ame* ame, int npairs, const int32_t* h_alpha, const int32_t* h_beta, double eta,
+                               double wc, double beta);
 int oqb_ame_clear_onesided(oqb_ame* ame);
 /* du[b] = v·( −i[diag w, ρ̃] + Σ eigenbasis terms(ρ̃) )·v',  ρ̃ = v' u[b] v   (OVERWRITES du)
  *   — (Op::DiffEqLiouvillian{true,false})(du,u,p,t) src/opensys/diffeq_liouvillian.jl:92-105.

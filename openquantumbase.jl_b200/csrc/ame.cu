@@ -371,30 +371,23 @@ int oqb_ame_set_davies(oqb_ame* a, const double* h_gam, const double* h_S, int64
     return ame_davies_finish(a, ncross, h_cross_idx, h_cross_rate, nlamb, h_lamb_idx, h_lamb_rate_S);
 }
 
-int oqb_ame_set_onesided(oqb_ame* a, int npairs, const int32_t* h_alpha, const int32_t* h_beta, const double* h_gam,
-                         const double* h_S, int tables_shared) {
+// Λ_p = (½γ + iS)∘A_αp from DEVICE tables, then the per-eigen-system products of the one-sided generator
+int ame_onesided_install(oqb_ame* a, int npairs, const int32_t* h_alpha, const int32_t* h_beta, const double* d_g,
+                         const double* d_s, int tables_shared) {
     oqb_ctx* c = a->ctx;
-    if (!a->have_eigen) return set_error(c, OQB_EINVAL, "oqb_ame_set_onesided: call oqb_ame_set_eigen first");
-    if (npairs <= 0 || !h_alpha || !h_beta || !h_gam || !h_S) return set_error(c, OQB_EINVAL, "oqb_ame_set_onesided: bad arguments");
     for (int p = 0; p < npairs; ++p)
         if (h_alpha[p] < 0 || h_alpha[p] >= a->K || h_beta[p] < 0 || h_beta[p] >= a->K)
             return set_error(c, OQB_EINVAL, "oqb_ame_set_onesided: coupling index out of range");
     OQB_TRY(oqb_ame_clear_onesided(a));
     const int l = a->lvl;
     const size_t ll = (size_t)l * l;
-    const size_t nt = tables_shared ? 1 : (size_t)npairs;
-    double *d_g = nullptr, *d_s = nullptr;
     int32_t* d_alpha = nullptr;
     OQB_TRY(dalloc(c, (void**)&a->d_Lam, (size_t)npairs * ll * sizeof(c128)));
-    OQB_TRY(dalloc(c, (void**)&d_g, nt * ll * sizeof(double)));
-    OQB_TRY(dalloc(c, (void**)&d_s, nt * ll * sizeof(double)));
     OQB_TRY(dalloc(c, (void**)&d_alpha, npairs * sizeof(int32_t)));
-    OQB_CUDA(c, cudaMemcpyAsync(d_g, h_gam, nt * ll * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-    OQB_CUDA(c, cudaMemcpyAsync(d_s, h_S, nt * ll * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     OQB_CUDA(c, cudaMemcpyAsync(d_alpha, h_alpha, npairs * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
     int s = onesided_lambda(c, l, npairs, d_alpha, a->d_A, d_g, d_s, tables_shared ? 0 : (long long)ll, a->d_Lam);
     cudaStreamSynchronize(c->stream);
-    cudaFree(d_g); cudaFree(d_s); cudaFree(d_alpha);
+    cudaFree(d_alpha);
     if (s) return s;
     a->npairs = npairs;
     a->h_beta.assign(h_beta, h_beta + npairs);
@@ -415,6 +408,24 @@ int oqb_ame_set_onesided(oqb_ame* a, int npairs, const int32_t* h_alpha, const i
     }
     OQB_CUDA(c, cudaStreamSynchronize(c->stream));
     return 0;
+}
+
+int oqb_ame_set_onesided(oqb_ame* a, int npairs, const int32_t* h_alpha, const int32_t* h_beta, const double* h_gam,
+                         const double* h_S, int tables_shared) {
+    oqb_ctx* c = a->ctx;
+    if (!a->have_eigen) return set_error(c, OQB_EINVAL, "oqb_ame_set_onesided: call oqb_ame_set_eigen first");
+    if (npairs <= 0 || !h_alpha || !h_beta || !h_gam || !h_S) return set_error(c, OQB_EINVAL, "oqb_ame_set_onesided: bad arguments");
+    const size_t ll = (size_t)a->lvl * a->lvl;
+    const size_t nt = tables_shared ? 1 : (size_t)npairs;
+    double *d_g = nullptr, *d_s = nullptr;
+    OQB_TRY(dalloc(c, (void**)&d_g, nt * ll * sizeof(double)));
+    OQB_TRY(dalloc(c, (void**)&d_s, nt * ll * sizeof(double)));
+    OQB_CUDA(c, cudaMemcpyAsync(d_g, h_gam, nt * ll * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    OQB_CUDA(c, cudaMemcpyAsync(d_s, h_S, nt * ll * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    const int s = ame_onesided_install(a, npairs, h_alpha, h_beta, d_g, d_s, tables_shared);
+    cudaStreamSynchronize(c->stream);
+    cudaFree(d_g); cudaFree(d_s);
+    return s;
 }
 
 int oqb_ame_rhs(oqb_ame* a, int nb, const void* d_u, void* d_du) {

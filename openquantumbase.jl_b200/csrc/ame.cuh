@@ -48,3 +48,5 @@ extern "C" int ame_davies_alloc(oqb_ame* a);
 extern "C" int ame_davies_finish(oqb_ame* a, int64_t ncross, const int32_t* h_cross_idx, const double* h_cross_rate, int64_t nlamb,
                       const int32_t* h_lamb_idx, const double* h_lamb_rate_S);
 
+extern "C" int ame_onesided_install(oqb_ame* a, int npairs, const int32_t* h_alpha, const int32_t* h_beta, const double* d_g,
+                                    const double* d_s, int tables_shared);

@@ -82,6 +82,18 @@ __global__ void gap_table_kernel(int l, const double* __restrict__ w, double thr
     S[e] = nS ? bspline2_eval(key, nS, S_x0, S_dx, S_coef) : 0.0;  // tabulated Lamb shift (build_lambshift) or S ≡ 0
 }
 
+// one-sided AME tables at the UNROUNDED gap matrix ω_ba[a,b] = w[b] − w[a] (src/opensys/opensys_util.jl:65, davies.jl:368)
+__global__ void onesided_table_kernel(int l, const double* __restrict__ w, double eta, double wc, double beta, int nS, double S_x0,
+                                      double S_dx, const double* __restrict__ S_coef, double* __restrict__ gam,
+                                      double* __restrict__ S) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (long long)l * l) return;
+    const int a = (int)(e % l), b = (int)(e / l);
+    const double g = w[b] - w[a];
+    gam[e] = ohmic_spectrum(g, eta, wc, beta);
+    S[e] = nS ? bspline2_eval(g, nS, S_x0, S_dx, S_coef) : 0.0;
+}
+
 __global__ void flag_multi_kernel(long long m, const double* __restrict__ keys, uint8_t* __restrict__ flag) {
     const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= m) return;
@@ -109,6 +121,27 @@ int oqb_ame_set_lambshift_spline(oqb_ame* a, int n, double x0, double dx, const 
     a->S_x0 = x0;
     a->S_dx = dx;
     return 0;
+}
+
+int oqb_ame_set_onesided_ohmic(oqb_ame* a, int npairs, const int32_t* h_alpha, const int32_t* h_beta, double eta, double wc,
+                               double beta) {
+    if (!a) return OQB_EINVAL;
+    oqb_ctx* c = a->ctx;
+    if (!a->have_eigen) return set_error(c, OQB_EINVAL, "oqb_ame_set_onesided_ohmic: call oqb_ame_set_eigen first");
+    if (npairs <= 0 || !h_alpha || !h_beta) return set_error(c, OQB_EINVAL, "oqb_ame_set_onesided_ohmic: bad arguments");
+    const long long ll = (long long)a->lvl * a->lvl;
+    double* d_g = nullptr;
+    OQB_CUDA(c, cudaMalloc((void**)&d_g, (size_t)ll * 2 * sizeof(double)));
+    double* d_s = d_g + ll;
+    onesided_table_kernel<<<(unsigned)((ll + 255) / 256), 256, 0, c->stream>>>(a->lvl, a->d_w, eta, wc, beta, a->n_Stab, a->S_x0,
+                                                                               a->S_dx, a->d_Scoef, d_g, d_s);
+    int s = 0;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) s = set_error(c, OQB_ECUDA, "onesided_table_kernel launch failed: %s", cudaGetErrorString(e));
+    if (!s) s = ame_onesided_install(a, npairs, h_alpha, h_beta, d_g, d_s, 1);
+    cudaStreamSynchronize(c->stream);
+    cudaFree(d_g);
+    return s;
 }
 
 int oqb_ame_davies_ohmic_begin(oqb_ame* a, double eta, double wc, double beta, int digits, int sigdigits, int64_t* n_multi,

@@ -917,7 +917,11 @@ class DiffEqLiouvillian:
                       and isinstance(self.opensys_eig[0], DaviesGenerator)
                       and isinstance(self.opensys_eig[0].gamma, OhmicBath)
                       and isinstance(self.opensys_eig[0].S, (_Zero, QuadraticBSpline)))
-        groups = None if dev_tables else GapGroups(w, self.digits, self.sigdigits)  # :96
+        dev_onesided = (getattr(self, "device_tables", False) and len(self.opensys_eig) == 1
+                        and isinstance(self.opensys_eig[0], OneSidedAMELiouvillian)
+                        and isinstance(self.opensys_eig[0].gamma, OhmicBath)
+                        and isinstance(self.opensys_eig[0].S, (_Zero, QuadraticBSpline)))
+        groups = None if (dev_tables or dev_onesided) else GapGroups(w, self.digits, self.sigdigits)  # :96
         ndav = 0
         for lv, (c0, c1) in zip(self.opensys_eig, slices):
             if dev_tables:
@@ -959,6 +963,15 @@ class DiffEqLiouvillian:
                     h, _lib.dptr(gam), _lib.dptr(Sm), len(ci), ci.ctypes.data_as(_lib.c_i32p) if len(ci) else None,
                     _lib.dptr(crate) if len(ci) else None, len(li),
                     li.ctypes.data_as(_lib.c_i32p) if len(li) else None, _lib.dptr(lrs) if len(li) else None))
+            elif isinstance(lv, OneSidedAMELiouvillian) and dev_onesided:
+                # γ(w_b − w_a) and the spline S at the l² unrounded gaps on the device (one shared table, davies.jl:368)
+                Ssp = lv.S if isinstance(lv.S, QuadraticBSpline) else None
+                ctx.check(lib.oqb_ame_set_lambshift_spline(h, Ssp.n if Ssp else 0, Ssp.x0 if Ssp else 0.0, Ssp.dx if Ssp else 1.0,
+                                                           Ssp.coef.ctypes.data if Ssp else None))
+                al = np.ascontiguousarray([c0 + a - 1 for a, _ in lv.inds], dtype=np.int32)
+                be = np.ascontiguousarray([c0 + b - 1 for _, b in lv.inds], dtype=np.int32)
+                ctx.check(lib.oqb_ame_set_onesided_ohmic(h, len(lv.inds), al.ctypes.data_as(_lib.c_i32p),
+                                                         be.ctypes.data_as(_lib.c_i32p), lv.gamma.eta, lv.gamma.wc, lv.gamma.beta))
             elif isinstance(lv, OneSidedAMELiouvillian):
                 from .gaps import _eval
                 gm = groups.gap_matrix  # UNROUNDED, davies.jl:368

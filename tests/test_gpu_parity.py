@@ -1017,3 +1017,39 @@ def test_ame_device_tables_tabulated_lambshift(Q, degenerate):
     op0 = Q.DiffEqLiouvillian(Hg, [Q.DaviesGenerator(Q.ConstantCouplings(coup, unit="h"), bath_g, Q.ZERO_LAMBSHIFT)], [], lvl)
     d0 = op0.rhs_with_eig(np.zeros_like(u), u, p, 2.0 * s, w, v)
     assert relerr(d0, ref) > 1e-6 or degenerate
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("with_lambshift", [False, True])
+def test_onesided_ame_device_tables(Q, with_lambshift):
+    """OneSidedAMELiouvillian (davies.jl:367-379) with γ(w_b − w_a) and the spline Lamb shift evaluated at the l² UNROUNDED
+    gaps on the device (oqb_ame_set_onesided_ohmic) against host-evaluated tables and the oracle."""
+    rng = np.random.default_rng(654 + with_lambshift)
+    nq, lvl, nb = 4, 16, 3
+    n = 2 ** nq
+    Hd = -F.standard_driver(nq)
+    Hp = F.two_local_term(list(rng.standard_normal(nq - 1)), [[i, i + 1] for i in range(1, nq)], nq) \
+        + sum(rng.standard_normal() * F.single_clause(["z"], [k + 1], 1.0, nq) for k in range(nq))
+    coup = [F.single_clause(["z"], [k + 1], 1.0, nq) for k in range(3)]
+    inds = [(1, 1), (2, 2), (3, 3), (1, 2)]
+    Hg, Ho = Q.DenseHamiltonian([A, B], [Hd, Hp]), O.DenseHamiltonian([A, B], [Hd, Hp])
+    bath_g, bath_o = Q.Ohmic(1e-2, 4, 16), O.Ohmic(1e-2, 4, 16)
+    if with_lambshift:
+        w_range = np.linspace(-30, 30, 301)
+        S_g = Q.build_lambshift(w_range, True, bath_g)
+        S_o_sp = O.QuadraticBSpline(w_range[0], 0.2, S_g.vectorized(w_range))
+        S_o = lambda x: S_o_sp(x).real
+    else:
+        S_g, S_o = Q.ZERO_LAMBSHIFT, (lambda x: 0.0)
+    mk = lambda: Q.DiffEqLiouvillian(Hg, [Q.OneSidedAMELiouvillian(Q.ConstantCouplings(coup, unit="h"), bath_g, S_g, inds)], [], lvl)
+    op_host, op_dev = mk(), mk()
+    op_dev.device_tables = True
+    u = rand_rho(rng, nb, n)
+    w, v = O.haml_eigs(Ho, 0.4, lvl)
+    p = Q.ODEParams(Hg, 2.0)
+    d_host = op_host.rhs_with_eig(np.zeros_like(u), u, p, 0.8, w, v)
+    d_dev = op_dev.rhs_with_eig(np.zeros_like(u), u, p, 0.8, w, v)
+    assert relerr(d_dev, d_host) < 1e-13
+    opo = O.DiffEqLiouvillian(Ho, [O.OneSidedAMELiouvillian([2 * np.pi * c for c in coup], bath_o.spectrum, S_o, inds)], [], lvl)
+    ref = np.stack([opo.rhs_with_eig(u[b], O.ODEParams(Ho, 2.0), 0.8, w, v) for b in range(nb)])
+    assert relerr(d_dev, ref) < TOL
