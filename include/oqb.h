@@ -311,6 +311,13 @@ int oqb_traj_evolve(oqb_sparse* sp, int nb, int nsteps, double dt, const double*
  * (at most max_segments segments).  h_err (error estimates) and h_nseg (segments used) may be NULL. */
 int oqb_ohmic_lambshift(oqb_ctx* ctx, double eta, double wc, double beta, int n, const double* h_w, double rtol,
                         double atol, int max_segments, double* h_S, double* h_err, int32_t* h_nseg);
+/* C(τ) of the Ohmic bath (src/bath/ohmic.jl:48-52: η(ψ₁(1 + x₂ − x₁) + ψ₁(x₁ + x₂))/β², x₁ = iτ/β, x₂ = 1/(βωc)) for n lags;
+ * h_C: n interleaved complex128.  This is the cfun of the Redfield / ULE kernels (src/coupling/interaction.jl:178-186). */
+int oqb_ohmic_correlation(oqb_ctx* ctx, double eta, double wc, double beta, int n, const double* h_tau, void* h_C);
+/* Bath time scales (src/bath/bath_util.jl:55-89): 1/τ_SB = ∫₀^∞|C(τ)|dτ, τ_B = τ_SB·∫₀^lim τ|C(τ)|dτ with the error
+ * estimates the reference returns (err/res², err·τ_SB; may be NULL); coarse_grain_timescale is √(τ_SB τ_B/5). */
+int oqb_ohmic_timescales(oqb_ctx* ctx, double eta, double wc, double beta, double lim, double rtol, double atol,
+                         int max_segments, double* tau_sb, double* err_sb, double* tau_b, double* err_b);
 /* y[k] = spline(x[k]) for the quadratic B-spline of oqb_ame_set_lambshift_spline (host arrays; m points). */
 int oqb_bspline_eval(oqb_ctx* ctx, int n, double x0, double dx, const double* h_coef, int m, const double* h_x,
                      double* h_y);

@@ -77,6 +77,60 @@ class OhmicBath:
 
     __call__ = spectrum
 
+    def correlation(self, tau: float) -> complex:
+        """src/bath/ohmic.jl:48-52: C(τ) = η(ψ₁(1 + x₂ − x₁) + ψ₁(x₁ + x₂))/β², x₂ = 1/(βωc), x₁ = iτ/β."""
+        x2 = 1 / self.beta / self.wc
+        x1 = 1.0j * tau / self.beta
+        return self.eta * (trigamma(-x1 + 1 + x2) + trigamma(x1 + x2)) / self.beta ** 2
+
+
+def trigamma(z: complex) -> complex:
+    """ψ₁(z) as SpecialFunctions.jl (compat 0.8-2.0) computes it for Complex{Float64} [external — restated from its
+    published algorithm]: reflection for Re z ≤ 0, upward recurrence ψ₁(z) = ψ₁(z+1) + 1/z² to Re z ≥ 10, then the
+    asymptotic series 1/z + 1/(2z²) + Σ_{k=1..8} B_{2k}/z^{2k+1}.  Pinned by τ_SB / τ_B of
+    test/coupling_bath_interaction/bath.jl:19-24 and against mpmath in tests/test_oracle_golden.py."""
+    z = complex(z)
+    x = z.real
+    if x <= 0:
+        return (np.pi / np.sin(np.pi * z)) ** 2 - trigamma(1 - z)
+    psi = 0.0j
+    N = 10
+    if x < N:
+        n = N - int(math.floor(x))
+        psi += (1 / z) ** 2
+        for nu in range(1, n):
+            psi += (1 / (z + nu)) ** 2
+        z += n
+    t = 1 / z
+    w = t * t
+    psi += t + 0.5 * w
+    coef = (0.16666666666666666, -0.03333333333333333, 0.023809523809523808, -0.03333333333333333, 0.07575757575757576,
+            -0.2531135531135531, 1.1666666666666667, -7.092156862745098)
+    poly = 0.0j
+    for c in reversed(coef):
+        poly = poly * w + c
+    return psi + t * w * poly
+
+
+def tau_SB(cfun, lim=math.inf, rtol=math.sqrt(np.finfo(float).eps), atol=0.0):
+    """src/bath/bath_util.jl:55-58: 1/τ_SB = ∫₀^lim |C(τ)|dτ; returns (τ_SB, err/res²)."""
+    f = lambda x: abs(cfun(x))
+    res, err = quadgk_semi_infinite(f, 0.0, rtol, atol) if math.isinf(lim) else quadgk(f, 0.0, lim, rtol, atol)
+    return 1 / res, err / abs(res) ** 2
+
+
+def tau_B(cfun, lim, tausb, rtol=math.sqrt(np.finfo(float).eps), atol=0.0):
+    """src/bath/bath_util.jl:72-75: τ_B/τ_SB = ∫₀^lim τ|C(τ)|dτ."""
+    res, err = quadgk(lambda x: x * abs(cfun(x)), 0.0, lim, rtol, atol)
+    return res * tausb, err * tausb
+
+
+def coarse_grain_timescale(cfun, lim, rtol=math.sqrt(np.finfo(float).eps), atol=0.0):
+    """src/bath/bath_util.jl:85-89: T_a = √(τ_SB τ_B / 5)."""
+    tsb, esb = tau_SB(cfun, rtol=rtol, atol=atol)
+    tb, eb = tau_B(cfun, lim, tsb, rtol=rtol, atol=atol)
+    return math.sqrt(tsb * tb / 5), (esb * tb + tsb * eb) / 10 / math.sqrt(tsb * tb / 5)
+
 
 def Ohmic(eta, fc, T) -> OhmicBath:
     """src/bath/ohmic.jl:24-28."""

@@ -1053,3 +1053,23 @@ def test_onesided_ame_device_tables(Q, with_lambshift):
     opo = O.DiffEqLiouvillian(Ho, [O.OneSidedAMELiouvillian([2 * np.pi * c for c in coup], bath_o.spectrum, S_o, inds)], [], lvl)
     ref = np.stack([opo.rhs_with_eig(u[b], O.ODEParams(Ho, 2.0), 0.8, w, v) for b in range(nb)])
     assert relerr(d_dev, ref) < TOL
+
+
+@pytest.mark.gpu
+def test_ohmic_correlation_and_timescales_device(Q):
+    """correlation(τ, ::OhmicBath) (ohmic.jl:48-52: complex trigamma) and τ_SB / τ_B / coarse_grain_timescale
+    (bath_util.jl:55-105) on the device against the oracle and the reference's known answers
+    (test/coupling_bath_interaction/bath.jl:18-26)."""
+    bath_g, bath_o = Q.Ohmic(1e-4, 4, 16), O.Ohmic(1e-4, 4, 16)
+    taus = np.concatenate([[0.0, 1e-6, 1e-3], np.linspace(0.01, 5, 60), [20.0, 100.0, 1e3, -0.7]])
+    Cd = bath_g.correlation(taus)
+    Co = np.array([bath_o.correlation(t) for t in taus])
+    assert np.max(np.abs(Cd - Co) / np.abs(Co)) < 1e-13
+    assert abs(bath_g.correlation(0.3) - bath_o.correlation(0.3)) < 1e-13 * abs(bath_o.correlation(0.3))
+    (tsb, esb), (tb, eb) = bath_g.timescales(100)
+    assert np.isclose(tsb, 284.61181493, rtol=1e-6, atol=1e-6) and np.isclose(tb, 0.07638653, rtol=1e-6, atol=1e-6)
+    tsb_o, esb_o = O.tau_SB(bath_o.correlation)
+    tb_o, eb_o = O.tau_B(bath_o.correlation, 100, tsb_o)
+    assert abs(tsb - tsb_o) < 1e-7 * tsb_o and abs(tb - tb_o) < 1e-7 * tb_o  # quadrature tolerance √eps; typically ~1e-13
+    ta, ta_err = bath_g.coarse_grain_timescale(100)
+    assert np.isclose(ta, np.sqrt(tsb * tb / 5), rtol=1e-12) and ta_err < 1e-6

@@ -210,3 +210,30 @@ def test_redfield_liouvillian_call_uses_device_lambda(Q):
     # four adaptive integrals at rtol 1e-7: a near-tie between two segment error estimates (constant C(t,x) on a dyadic
     # grid) may bisect in a different order than the oracle — both results are far inside the requested tolerance
     assert relerr(got - du0, ref - du0) < 1e-8
+
+
+def test_lambda_with_ohmic_correlation(Q):
+    """The Redfield kernel of a real Ohmic bath: cfun(t, x) = correlation(t − x, bath) (coupling/interaction.jl:178-186
+    with bath_util.jl:9-10 and ohmic.jl:48-52).  The device evaluates C at every round's quadrature nodes (complex
+    trigamma, one launch per round); the oracle uses its own trigamma restatement.  Ta from coarse_grain_timescale."""
+    from oqb_b200.redfield_device import LambdaBuilder, SampledUnitary
+    rng = np.random.default_rng(4242)
+    n, nb, G, tf = 8, 3, 257, 4.0
+    bath_g, bath_o = Q.Ohmic(1e-2, 4, 16), O.Ohmic(1e-2, 4, 16)
+    Ta, _ = bath_g.coarse_grain_timescale(tf)
+    Ta_o, _ = O.coarse_grain_timescale(bath_o.correlation, tf)
+    assert abs(Ta - Ta_o) < 1e-7 * Ta_o
+    Us = []
+    for b in range(nb):
+        A = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))
+        u, dt = sample_unitary((A + A.conj().T) / (2 * np.sqrt(n)), tf, G)
+        Us.append(u)
+    Us = np.stack(Us)
+    S = np.diag(rng.choice([-1.0, 1.0], n)).astype(complex)
+    atol, rtol = 1e-10, 1e-8
+    tend = np.array([tf, 0.7 * tf, 0.35 * tf])
+    lb = LambdaBuilder([S], Us, dt)
+    Lam = lb.build(np.arange(nb), np.zeros(nb, dtype=int), tend, lambda q, t, x: bath_g.correlation(t - x), Ta, atol, rtol).to_host()
+    cf_o = lambda t, x: bath_o.correlation(t - x)
+    worst = max(relerr(Lam[b], oracle_lambda(SampledUnitary(Us[b], dt), S, cf_o, float(tend[b]), Ta, atol, rtol)) for b in range(nb))
+    assert worst < 1e-12

@@ -440,3 +440,21 @@ def test_quadratic_bspline_known_answers():
     assert itc(-1) == 0 and isinstance(itc(-1), complex) or np.iscomplexobj(itc(-1))
     assert itp(11) == 0
     assert np.isclose(itp.gradient(2.3), -1) and np.allclose([itp.gradient(v) for v in (0.13, 0.21)], [-1, -1])
+
+
+def test_ohmic_correlation_and_timescales_known_answers():
+    """test/coupling_bath_interaction/bath.jl:10,18-26: correlation(t1, t2) = correlation(t1 − t2); for Ohmic(1e-4, 4, 16)
+    τ_SB ≈ 284.61181493, τ_B(bath, 100, τ_SB) ≈ 0.07638653 (atol = rtol = 1e-6), T_c = √(τ_SB τ_B/5).  These pin the complex
+    trigamma restatement; it is also checked against mpmath where that is importable."""
+    bath = O.Ohmic(1e-4, 4, 16)
+    tsb, _ = O.tau_SB(bath.correlation)
+    tb, _ = O.tau_B(bath.correlation, 100, tsb)
+    assert np.isclose(tsb, 284.61181493, rtol=1e-6, atol=1e-6) and np.isclose(tb, 0.07638653, rtol=1e-6, atol=1e-6)
+    tc, _ = O.coarse_grain_timescale(bath.correlation, 100)
+    assert np.isclose(tc, np.sqrt(tsb * tb / 5), rtol=1e-6, atol=1e-6)
+    b2 = O.OhmicBath(1e-4, 8 * np.pi, 1 / 2.23)
+    assert b2.correlation(0.02 - 0.01) == b2.correlation(0.01)
+    mpmath = pytest.importorskip("mpmath")
+    for z in (0.084 + 0.3j, 1.084 - 2j, 0.5, 3 + 40j, 0.084 + 1e-3j, 12.5 + 0.1j, -0.3 + 0.2j):
+        ref = complex(mpmath.psi(1, z))
+        assert abs(O.trigamma(z) - ref) <= 1e-15 * abs(ref) * 4
