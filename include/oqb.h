@@ -166,6 +166,10 @@ int oqb_lambda_total(oqb_lambda* lam, int nint, const int64_t* h_ptr, const int6
  * h_couplings: K coupling matrices A_α (n×n, unit-scaled, src/coupling/coupling.jl:42,66). */
 int oqb_ame_create(oqb_ctx* ctx, int n, int lvl, int K, const void* h_couplings, oqb_ame** out);
 int oqb_ame_destroy(oqb_ame* ame);
+/* Moves a handle to another context of the same device: later calls launch on that context's stream and use its
+ * workspace.  The caller orders the two streams (all work issued through the old context must have completed).  Lets
+ * a side stream prepare the next eigen-system while the current one is in use. */
+int oqb_ame_rebind(oqb_ame* ame, oqb_ctx* ctx);
 /* (w, v) exactly as haml_eigs returned them on the host (src/hamiltonian/hamiltonian_base.jl:155);
  * h_v NULL ⇒ adiabatic frame (v = I, n == lvl).  Rotates the couplings on the device
  * (src/opensys/davies.jl:24). */

@@ -18,18 +18,6 @@ namespace {
 
 const size_t kAmeBudget = (size_t)8 << 30;  // bytes of scratch per batch chunk (180 GB HBM per GPU)
 
-template <class T>
-void dfree(T*& p) {
-    if (p) cudaFree(p);
-    p = nullptr;
-}
-
-int dalloc(oqb_ctx* c, void** p, size_t bytes) {
-    cudaError_t e = cudaMalloc(p, bytes ? bytes : 16);
-    if (e != cudaSuccess) return set_error(c, OQB_ENOMEM, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
-    return 0;
-}
-
 bool needs_general_path(const oqb_ame* a) { return a->ncross > 0 || a->d_Moff || a->npairs > 0; }
 
 // Eigenbasis terms on ρ̃ = R (lvl×lvl per member).  overwrite: X = …, else X += ….
@@ -181,11 +169,11 @@ int oqb_ame_create(oqb_ctx* c, int n, int lvl, int K, const void* h_couplings, o
     oqb_ame* a = new oqb_ame();
     a->ctx = c; a->n = n; a->lvl = lvl; a->K = K;
     const size_t nn = (size_t)n * n, ll = (size_t)lvl * lvl;
-    int s = dalloc(c, (void**)&a->d_coup, (K + 1) * nn * sizeof(c128));
-    if (!s) s = dalloc(c, (void**)&a->d_V, (size_t)n * lvl * sizeof(c128));
-    if (!s) s = dalloc(c, (void**)&a->d_w, lvl * sizeof(double));
-    if (!s) s = dalloc(c, (void**)&a->d_A, (K + 1) * ll * sizeof(c128));
-    if (!s) s = dalloc(c, (void**)&a->d_Cm, ll * sizeof(c128));
+    int s = ame_alloc(c, (void**)&a->d_coup, (K + 1) * nn * sizeof(c128));
+    if (!s) s = ame_alloc(c, (void**)&a->d_V, (size_t)n * lvl * sizeof(c128));
+    if (!s) s = ame_alloc(c, (void**)&a->d_w, lvl * sizeof(double));
+    if (!s) s = ame_alloc(c, (void**)&a->d_A, (K + 1) * ll * sizeof(c128));
+    if (!s) s = ame_alloc(c, (void**)&a->d_Cm, ll * sizeof(c128));
     if (s) { oqb_ame_destroy(a); return s; }
     if (K) {
         OQB_CUDA(c, cudaMemcpyAsync(a->d_coup, h_couplings, K * nn * sizeof(c128), cudaMemcpyHostToDevice, c->stream));
@@ -197,19 +185,26 @@ int oqb_ame_create(oqb_ctx* c, int n, int lvl, int K, const void* h_couplings, o
 
 int oqb_ame_clear_davies(oqb_ame* a) {
     cudaStreamSynchronize(a->ctx->stream);
-    dfree(a->d_gam); dfree(a->d_S); dfree(a->d_Gam); dfree(a->d_hls); dfree(a->d_Wt); dfree(a->d_Wt_im);
-    dfree(a->d_cross_idx); dfree(a->d_cross_rate); dfree(a->d_Moff);
+    ame_free(a->ctx, a->d_gam); ame_free(a->ctx, a->d_S); ame_free(a->ctx, a->d_Gam); ame_free(a->ctx, a->d_hls); ame_free(a->ctx, a->d_Wt); ame_free(a->ctx, a->d_Wt_im);
+    ame_free(a->ctx, a->d_cross_idx); ame_free(a->ctx, a->d_cross_rate); ame_free(a->ctx, a->d_Moff);
     a->davies = false; a->ncross = a->nlamb = 0;
     if (a->have_eigen)  // Hamiltonian-only Hadamard coefficients
         return davies_tables(a->ctx, a->lvl, a->K, a->d_A, nullptr, nullptr, a->d_w, 0, nullptr, nullptr, nullptr, a->d_Cm);
     return 0;
 }
 
+int oqb_ame_rebind(oqb_ame* a, oqb_ctx* ctx) {
+    if (!a || !ctx) return OQB_EINVAL;
+    if (ctx->device != a->ctx->device) return set_error(ctx, OQB_EINVAL, "oqb_ame_rebind: contexts live on different devices");
+    a->ctx = ctx;
+    return 0;
+}
+
 int oqb_ame_clear_onesided(oqb_ame* a) {
     cudaStreamSynchronize(a->ctx->stream);
-    dfree(a->d_Lam);
-    dfree(a->d_Psum);
-    dfree(a->d_Abstack);
+    ame_free(a->ctx, a->d_Lam);
+    ame_free(a->ctx, a->d_Psum);
+    ame_free(a->ctx, a->d_Abstack);
     a->npairs = 0;
     a->h_beta.clear();
     return 0;
@@ -222,11 +217,11 @@ int oqb_ame_destroy(oqb_ame* a) {
     oqb_ame_clear_davies(a);
     oqb_ame_clear_onesided(a);
     oqb_ame_clear_jump(a);
-    if (a->d_grp_key) cudaFree(a->d_grp_key);
-    if (a->d_Scoef) cudaFree(a->d_Scoef);
-    if (a->d_grp_pair) cudaFree(a->d_grp_pair);
+    ame_free(a->ctx, a->d_grp_key);
+    ame_free(a->ctx, a->d_Scoef);
+    ame_free(a->ctx, a->d_grp_pair);
     (void)he;
-    dfree(a->d_coup); dfree(a->d_V); dfree(a->d_w); dfree(a->d_A); dfree(a->d_Cm);
+    ame_free(a->ctx, a->d_coup); ame_free(a->ctx, a->d_V); ame_free(a->ctx, a->d_w); ame_free(a->ctx, a->d_A); ame_free(a->ctx, a->d_Cm);
     delete a;
     return OQB_OK;
 }
@@ -286,10 +281,10 @@ int oqb_ame_set_tables(oqb_ame* a, const void* h_Cm, const double* h_Wt_re, cons
     if (!h_Cm || !h_Wt_re) return set_error(c, OQB_EINVAL, "oqb_ame_set_tables: null table");
     OQB_TRY(oqb_ame_clear_davies(a));
     const size_t ll = (size_t)a->lvl * a->lvl;
-    OQB_TRY(dalloc(c, (void**)&a->d_Wt, ll * sizeof(double)));
+    OQB_TRY(ame_alloc(c, (void**)&a->d_Wt, ll * sizeof(double)));
     OQB_CUDA(c, cudaMemcpyAsync(a->d_Wt, h_Wt_re, ll * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     if (h_Wt_im) {
-        OQB_TRY(dalloc(c, (void**)&a->d_Wt_im, ll * sizeof(double)));
+        OQB_TRY(ame_alloc(c, (void**)&a->d_Wt_im, ll * sizeof(double)));
         OQB_CUDA(c, cudaMemcpyAsync(a->d_Wt_im, h_Wt_im, ll * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     }
     OQB_CUDA(c, cudaMemcpyAsync(a->d_Cm, h_Cm, ll * sizeof(c128), cudaMemcpyHostToDevice, c->stream));
@@ -314,11 +309,11 @@ int ame_davies_alloc(oqb_ame* a) {
     OQB_TRY(oqb_ame_clear_davies(a));
     const int l = a->lvl;
     const size_t ll = (size_t)l * l;
-    OQB_TRY(dalloc(c, (void**)&a->d_gam, ll * sizeof(double)));
-    OQB_TRY(dalloc(c, (void**)&a->d_S, ll * sizeof(double)));
-    OQB_TRY(dalloc(c, (void**)&a->d_Gam, l * sizeof(double)));
-    OQB_TRY(dalloc(c, (void**)&a->d_hls, l * sizeof(double)));
-    OQB_TRY(dalloc(c, (void**)&a->d_Wt, ll * sizeof(double)));
+    OQB_TRY(ame_alloc(c, (void**)&a->d_gam, ll * sizeof(double)));
+    OQB_TRY(ame_alloc(c, (void**)&a->d_S, ll * sizeof(double)));
+    OQB_TRY(ame_alloc(c, (void**)&a->d_Gam, l * sizeof(double)));
+    OQB_TRY(ame_alloc(c, (void**)&a->d_hls, l * sizeof(double)));
+    OQB_TRY(ame_alloc(c, (void**)&a->d_Wt, ll * sizeof(double)));
     return 0;
 }
 
@@ -329,25 +324,25 @@ int ame_davies_finish(oqb_ame* a, int64_t ncross, const int32_t* h_cross_idx, co
     const size_t ll = (size_t)l * l;
     OQB_TRY(davies_tables(c, l, a->K, a->d_A, a->d_gam, a->d_S, a->d_w, 1, a->d_Gam, a->d_hls, a->d_Wt, a->d_Cm));
     if (ncross > 0) {
-        OQB_TRY(dalloc(c, (void**)&a->d_cross_idx, (size_t)ncross * 4 * sizeof(int32_t)));
-        OQB_TRY(dalloc(c, (void**)&a->d_cross_rate, (size_t)ncross * sizeof(double)));
+        OQB_TRY(ame_alloc(c, (void**)&a->d_cross_idx, (size_t)ncross * 4 * sizeof(int32_t)));
+        OQB_TRY(ame_alloc(c, (void**)&a->d_cross_rate, (size_t)ncross * sizeof(double)));
         OQB_CUDA(c, cudaMemcpyAsync(a->d_cross_idx, h_cross_idx, (size_t)ncross * 4 * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
         OQB_CUDA(c, cudaMemcpyAsync(a->d_cross_rate, h_cross_rate, (size_t)ncross * sizeof(double), cudaMemcpyHostToDevice, c->stream));
         a->ncross = ncross;
     }
     if (nlamb > 0) {
-        OQB_TRY(dalloc(c, (void**)&a->d_Moff, ll * sizeof(c128)));
+        OQB_TRY(ame_alloc(c, (void**)&a->d_Moff, ll * sizeof(c128)));
         OQB_CUDA(c, cudaMemsetAsync(a->d_Moff, 0, ll * sizeof(c128), c->stream));
         int32_t* d_idx = nullptr;
         double* d_rs = nullptr;
-        OQB_TRY(dalloc(c, (void**)&d_idx, (size_t)nlamb * 3 * sizeof(int32_t)));
-        OQB_TRY(dalloc(c, (void**)&d_rs, (size_t)nlamb * 2 * sizeof(double)));
+        OQB_TRY(ame_alloc(c, (void**)&d_idx, (size_t)nlamb * 3 * sizeof(int32_t)));
+        OQB_TRY(ame_alloc(c, (void**)&d_rs, (size_t)nlamb * 2 * sizeof(double)));
         OQB_CUDA(c, cudaMemcpyAsync(d_idx, h_lamb_idx, (size_t)nlamb * 3 * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
         OQB_CUDA(c, cudaMemcpyAsync(d_rs, h_lamb_rate_S, (size_t)nlamb * 2 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
         int s = davies_lamb_build(c, l, a->K, a->d_A, nlamb, d_idx, d_rs, a->d_Moff);
         cudaStreamSynchronize(c->stream);
-        cudaFree(d_idx);
-        cudaFree(d_rs);
+        cudaFreeAsync(d_idx, c->stream);
+        cudaFreeAsync(d_rs, c->stream);
         if (s) return s;
         a->nlamb = nlamb;
     }
@@ -382,18 +377,18 @@ int ame_onesided_install(oqb_ame* a, int npairs, const int32_t* h_alpha, const i
     const int l = a->lvl;
     const size_t ll = (size_t)l * l;
     int32_t* d_alpha = nullptr;
-    OQB_TRY(dalloc(c, (void**)&a->d_Lam, (size_t)npairs * ll * sizeof(c128)));
-    OQB_TRY(dalloc(c, (void**)&d_alpha, npairs * sizeof(int32_t)));
+    OQB_TRY(ame_alloc(c, (void**)&a->d_Lam, (size_t)npairs * ll * sizeof(c128)));
+    OQB_TRY(ame_alloc(c, (void**)&d_alpha, npairs * sizeof(int32_t)));
     OQB_CUDA(c, cudaMemcpyAsync(d_alpha, h_alpha, npairs * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
     int s = onesided_lambda(c, l, npairs, d_alpha, a->d_A, d_g, d_s, tables_shared ? 0 : (long long)ll, a->d_Lam);
     cudaStreamSynchronize(c->stream);
-    cudaFree(d_alpha);
+    cudaFreeAsync(d_alpha, c->stream);
     if (s) return s;
     a->npairs = npairs;
     a->h_beta.assign(h_beta, h_beta + npairs);
     // per eigen-system: P = Σ_p A_βp Λ_p and the vertical stack [A_β1; …; A_βP] (npairs·l × l)
-    OQB_TRY(dalloc(c, (void**)&a->d_Psum, ll * sizeof(c128)));
-    OQB_TRY(dalloc(c, (void**)&a->d_Abstack, (size_t)npairs * ll * sizeof(c128)));
+    OQB_TRY(ame_alloc(c, (void**)&a->d_Psum, ll * sizeof(c128)));
+    OQB_TRY(ame_alloc(c, (void**)&a->d_Abstack, (size_t)npairs * ll * sizeof(c128)));
     for (int p = 0; p < npairs; ++p) {
         const c128* Ab = a->d_A + (long long)h_beta[p] * ll;
         ZgemmParams g;
@@ -418,13 +413,13 @@ int oqb_ame_set_onesided(oqb_ame* a, int npairs, const int32_t* h_alpha, const i
     const size_t ll = (size_t)a->lvl * a->lvl;
     const size_t nt = tables_shared ? 1 : (size_t)npairs;
     double *d_g = nullptr, *d_s = nullptr;
-    OQB_TRY(dalloc(c, (void**)&d_g, nt * ll * sizeof(double)));
-    OQB_TRY(dalloc(c, (void**)&d_s, nt * ll * sizeof(double)));
+    OQB_TRY(ame_alloc(c, (void**)&d_g, nt * ll * sizeof(double)));
+    OQB_TRY(ame_alloc(c, (void**)&d_s, nt * ll * sizeof(double)));
     OQB_CUDA(c, cudaMemcpyAsync(d_g, h_gam, nt * ll * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     OQB_CUDA(c, cudaMemcpyAsync(d_s, h_S, nt * ll * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     const int s = ame_onesided_install(a, npairs, h_alpha, h_beta, d_g, d_s, tables_shared);
     cudaStreamSynchronize(c->stream);
-    cudaFree(d_g); cudaFree(d_s);
+    cudaFreeAsync(d_g, c->stream); cudaFreeAsync(d_s, c->stream);
     return s;
 }
 

@@ -43,6 +43,21 @@ struct oqb_ame {
     double* d_Scoef = nullptr;
 };
 
+// Per-handle device buffers come from the stream-ordered allocator: cudaMalloc/cudaFree would synchronise the whole
+// device, which stalls a side stream that prepares the next eigen-system while the current one is in use.
+namespace oqb {
+template <class T>
+inline void ame_free(Ctx* c, T*& p) {
+    if (p) cudaFreeAsync((void*)p, c->stream);
+    p = nullptr;
+}
+inline int ame_alloc(Ctx* c, void** p, size_t bytes) {
+    cudaError_t e = cudaMallocAsync(p, bytes ? bytes : 16, c->stream);
+    if (e != cudaSuccess) return set_error(c, OQB_ENOMEM, "cudaMallocAsync(%zu) failed: %s", bytes, cudaGetErrorString(e));
+    return 0;
+}
+}  // namespace oqb
+
 // ame.cu internals shared with ame_gaps.cu (defined inside ame.cu's extern "C" block; not part of the public ABI)
 extern "C" int ame_davies_alloc(oqb_ame* a);
 extern "C" int ame_davies_finish(oqb_ame* a, int64_t ncross, const int32_t* h_cross_idx, const double* h_cross_rate, int64_t nlamb,

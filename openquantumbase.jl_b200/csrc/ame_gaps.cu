@@ -29,12 +29,6 @@ namespace {
 
 __constant__ double c_pow10[31];
 
-template <class T>
-void dfree(T*& p) {
-    if (p) cudaFree(p);
-    p = nullptr;
-}
-
 // Julia Base.round(x, sigdigits=n) for Float64 (floatfuncs.jl: hidigit + _round_digits); x != 0, finite.
 __device__ __forceinline__ double round_sigdigits(double x, int sig) {
     const double ax = fabs(x);
@@ -112,11 +106,12 @@ int oqb_ame_set_lambshift_spline(oqb_ame* a, int n, double x0, double dx, const 
     oqb_ctx* c = a->ctx;
     if (n < 0 || (n > 0 && (!h_coef || !(dx > 0.0)))) return set_error(c, OQB_EINVAL, "oqb_ame_set_lambshift_spline: bad argument");
     OQB_CUDA(c, cudaStreamSynchronize(c->stream));
-    dfree(a->d_Scoef);
+    ame_free(c, a->d_Scoef);
     a->n_Stab = 0;
     if (n == 0) return 0;
-    OQB_CUDA(c, cudaMalloc((void**)&a->d_Scoef, (size_t)(n + 2) * 8));
-    OQB_CUDA(c, cudaMemcpy(a->d_Scoef, h_coef, (size_t)(n + 2) * 8, cudaMemcpyHostToDevice));
+    OQB_TRY(ame_alloc(c, (void**)&a->d_Scoef, (size_t)(n + 2) * 8));
+    OQB_CUDA(c, cudaMemcpyAsync(a->d_Scoef, h_coef, (size_t)(n + 2) * 8, cudaMemcpyHostToDevice, c->stream));
+    OQB_CUDA(c, cudaStreamSynchronize(c->stream));
     a->n_Stab = n;
     a->S_x0 = x0;
     a->S_dx = dx;
@@ -131,7 +126,7 @@ int oqb_ame_set_onesided_ohmic(oqb_ame* a, int npairs, const int32_t* h_alpha, c
     if (npairs <= 0 || !h_alpha || !h_beta) return set_error(c, OQB_EINVAL, "oqb_ame_set_onesided_ohmic: bad arguments");
     const long long ll = (long long)a->lvl * a->lvl;
     double* d_g = nullptr;
-    OQB_CUDA(c, cudaMalloc((void**)&d_g, (size_t)ll * 2 * sizeof(double)));
+    OQB_TRY(ame_alloc(c, (void**)&d_g, (size_t)ll * 2 * sizeof(double)));
     double* d_s = d_g + ll;
     onesided_table_kernel<<<(unsigned)((ll + 255) / 256), 256, 0, c->stream>>>(a->lvl, a->d_w, eta, wc, beta, a->n_Stab, a->S_x0,
                                                                                a->S_dx, a->d_Scoef, d_g, d_s);
@@ -140,7 +135,7 @@ int oqb_ame_set_onesided_ohmic(oqb_ame* a, int npairs, const int32_t* h_alpha, c
     if (e != cudaSuccess) s = set_error(c, OQB_ECUDA, "onesided_table_kernel launch failed: %s", cudaGetErrorString(e));
     if (!s) s = ame_onesided_install(a, npairs, h_alpha, h_beta, d_g, d_s, 1);
     cudaStreamSynchronize(c->stream);
-    cudaFree(d_g);
+    cudaFreeAsync(d_g, c->stream);
     return s;
 }
 
@@ -164,8 +159,8 @@ int oqb_ame_davies_ohmic_begin(oqb_ame* a, double eta, double wc, double beta, i
     OQB_TRY(ame_davies_alloc(a));
     const int l = a->lvl;
     const long long ll = (long long)l * l, m = (long long)l * (l - 1) / 2;
-    dfree(a->d_grp_key);
-    dfree(a->d_grp_pair);
+    ame_free(c, a->d_grp_key);
+    ame_free(c, a->d_grp_pair);
     a->n_multi = a->n_zero = 0;
     *n_multi = *n_zero = 0;
     if (m == 0) return 0;
@@ -207,8 +202,8 @@ int oqb_ame_davies_ohmic_begin(oqb_ame* a, double eta, double wc, double beta, i
     // keep: [multi pairs (nm) | zero pairs (nz)] and the multi keys; zero-group pairs are the +inf tail of the sorted list
     const long long keep = nm + nz;
     if (keep > 0) {
-        OQB_CUDA(c, cudaMalloc((void**)&a->d_grp_pair, (size_t)keep * sizeof(int32_t)));
-        OQB_CUDA(c, cudaMalloc((void**)&a->d_grp_key, (size_t)(nm ? nm : 1) * sizeof(double)));
+        OQB_TRY(ame_alloc(c, (void**)&a->d_grp_pair, (size_t)keep * sizeof(int32_t)));
+        OQB_TRY(ame_alloc(c, (void**)&a->d_grp_key, (size_t)(nm ? nm : 1) * sizeof(double)));
         if (nm) {
             OQB_CUDA(c, cudaMemcpyAsync(a->d_grp_pair, p_in, (size_t)nm * 4, cudaMemcpyDeviceToDevice, c->stream));
             OQB_CUDA(c, cudaMemcpyAsync(a->d_grp_key, k_in, (size_t)nm * 8, cudaMemcpyDeviceToDevice, c->stream));
@@ -246,8 +241,8 @@ int oqb_ame_davies_ohmic_finish(oqb_ame* a, int64_t ncross, const int32_t* h_cro
     if (!a->d_gam) return set_error(c, OQB_EINVAL, "oqb_ame_davies_ohmic_finish: call oqb_ame_davies_ohmic_begin first");
     if ((ncross > 0 && (!h_cross_idx || !h_cross_rate)) || (nlamb > 0 && (!h_lamb_idx || !h_lamb_rate_S)))
         return set_error(c, OQB_EINVAL, "oqb_ame_davies_ohmic_finish: null cross-term arrays");
-    dfree(a->d_grp_key);
-    dfree(a->d_grp_pair);
+    ame_free(c, a->d_grp_key);
+    ame_free(c, a->d_grp_pair);
     return ame_davies_finish(a, ncross, h_cross_idx, h_cross_rate, nlamb, h_lamb_idx, h_lamb_rate_S);
 }
 

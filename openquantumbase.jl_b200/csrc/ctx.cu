@@ -101,6 +101,14 @@ int oqb_create(int device, oqb_ctx** out) {
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return OQB_ECUDA;
     if (prop.major != 10) return OQB_ECUDA;  // sm_100a code only
+    {  // the stream-ordered allocator keeps freed blocks instead of returning them to the driver at every synchronisation
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        cudaGetLastError();
+    }
     oqb_ctx* c = new oqb_ctx();
     c->device = device;
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return OQB_ECUDA; }

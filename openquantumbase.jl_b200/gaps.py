@@ -39,6 +39,49 @@ def round_sigdigits(x: np.ndarray, sigdigits: int) -> np.ndarray:
     return out
 
 
+def _group_cross_lists(mi, mj, starts, ends, keys):
+    """Cross-term and Lamb-shift lists of all multi-pair gap groups at once (the vectorised form of
+    `GapGroups._pairs`): groups are slices [starts[g], ends[g]) of the pair arrays (mi, mj) with key keys[g]; per group
+    the L₊ entries (rows mi, cols mj, +key) come first, then the L₋ entries (rows mj, cols mi, −key); inside each the
+    ordered pairs (p, q), p ≠ q, with p outermost — the order the loop produces."""
+    sizes = (ends - starts).astype(np.int64)
+    cr, ck, cg, lm, lk, lg = [], [], [], [], [], []
+    for m in np.unique(sizes):
+        if m < 2:
+            continue
+        gsel = np.flatnonzero(sizes == m)
+        idx = starts[gsel][:, None] + np.arange(m)[None, :]
+        I, J, kv = mi[idx], mj[idx], keys[gsel]
+        P, Q = np.nonzero(~np.eye(int(m), dtype=bool))
+        for sign, (aa, bb) in enumerate(((I, J), (J, I))):
+            ent = np.stack([aa[:, P], bb[:, P], aa[:, Q], bb[:, Q]], axis=-1)  # (G, m(m−1), 4)
+            kk = np.repeat((kv if sign == 0 else -kv)[:, None], len(P), axis=1)
+            gid = np.repeat((2 * gsel + sign)[:, None], len(P), axis=1)
+            cr.append(ent.reshape(-1, 4)); ck.append(kk.ravel()); cg.append(gid.ravel())
+            same = (aa[:, P] == aa[:, Q])
+            lm.append(ent[same][:, [0, 1, 3]]); lk.append(kk[same]); lg.append(gid[same])
+    if not cr:
+        return (np.zeros((0, 4), dtype=np.int32), np.zeros(0), np.zeros((0, 3), dtype=np.int32), np.zeros(0))
+    cr, ck, cg = np.concatenate(cr), np.concatenate(ck), np.concatenate(cg)
+    lm, lk, lg = np.concatenate(lm), np.concatenate(lk), np.concatenate(lg)
+    oc, ol = np.argsort(cg, kind="stable"), np.argsort(lg, kind="stable")
+    return cr[oc].astype(np.int32), ck[oc], lm[ol].astype(np.int32).reshape(-1, 3), lk[ol]
+
+
+def _zero_group_lists(aa, bb):
+    """The same for the zero-gap group (degenerate pairs in both orders + the diagonal): ordered pairs p ≠ q, minus the
+    (k,k)×(k',k') combinations, which are the γ(0)·A_kk·conj(A_k'k') Hadamard term."""
+    aa, bb = np.asarray(aa, dtype=np.int64), np.asarray(bb, dtype=np.int64)
+    m = len(aa)
+    diag = aa == bb
+    keep = ~np.eye(m, dtype=bool) & ~(diag[:, None] & diag[None, :])
+    P, Q = np.nonzero(keep)
+    ent = np.stack([aa[P], bb[P], aa[Q], bb[Q]], axis=-1)
+    same = aa[P] == aa[Q]
+    return (ent.astype(np.int32).reshape(-1, 4), np.zeros(len(P)), ent[same][:, [0, 1, 3]].astype(np.int32).reshape(-1, 3),
+            np.zeros(int(same.sum())))
+
+
 class GapGroups:
     def __init__(self, w, digits=8, sigdigits=8, max_cross=50_000_000):
         w = np.asarray(w, dtype=np.float64)
@@ -55,7 +98,7 @@ class GapGroups:
         self.omega = omega
         self.gap_matrix = w[None, :] - w[:, None]  # UNROUNDED (opensys_util.jl:65), one-sided AME only
         # ---- groups with more than one pair --------------------------------------------------
-        cross, cross_key, lamb, lamb_key = [], [], [], []
+        parts = []
         nzi, nzj, nzk = iu[~zero], ju[~zero], key[~zero]
         if nzk.size:
             order = np.argsort(nzk, kind="stable")
@@ -68,11 +111,7 @@ class GapGroups:
                 raise NotImplementedError(
                     f"gap spectrum is too degenerate for the cross-term list ({est} entries); "
                     "the dense per-group path is not implemented")
-            for g in multi:
-                mem = order[starts[g]:ends[g]]
-                ii, jj, kk = nzi[mem], nzj[mem], float(ks[starts[g]])
-                for (aa, bb, kval) in ((ii, jj, kk), (jj, ii, -kk)):  # L₊ then L₋ (davies.jl:30-31)
-                    self._pairs(aa, bb, kval, cross, cross_key, lamb, lamb_key)
+            parts.append(_group_cross_lists(nzi[order], nzj[order], starts[multi], ends[multi], ks[starts[multi]]))
         # ---- zero group: degenerate pairs (both orders) + the diagonal ---------------------------
         zi, zj = iu[zero], ju[zero]
         if zi.size:
@@ -80,11 +119,11 @@ class GapGroups:
             bb = np.r_[zj, zi, np.arange(l)]
             if (len(aa)) ** 2 > max_cross:
                 raise NotImplementedError("zero-gap group too large for the cross-term list")
-            self._pairs(aa, bb, 0.0, cross, cross_key, lamb, lamb_key, skip_diag_diag=True)
-        self.cross_idx = np.array(cross, dtype=np.int32).reshape(-1, 4)
-        self.cross_key = np.array(cross_key, dtype=np.float64)
-        self.lamb_idx = np.array(lamb, dtype=np.int32).reshape(-1, 3)
-        self.lamb_key = np.array(lamb_key, dtype=np.float64)
+            parts.append(_zero_group_lists(aa, bb))
+        self.cross_idx = np.concatenate([q[0] for q in parts]) if parts else np.zeros((0, 4), dtype=np.int32)
+        self.cross_key = np.concatenate([q[1] for q in parts]) if parts else np.zeros(0)
+        self.lamb_idx = np.concatenate([q[2] for q in parts]) if parts else np.zeros((0, 3), dtype=np.int32)
+        self.lamb_key = np.concatenate([q[3] for q in parts]) if parts else np.zeros(0)
 
     @staticmethod
     def _pairs(aa, bb, kval, cross, cross_key, lamb, lamb_key, skip_diag_diag=False):
@@ -139,7 +178,7 @@ def cross_lists_from_groups(l: int, multi_pair, multi_key, zero_pair, max_cross=
     """The cross-term / Lamb-shift lists of `GapGroups` from the device-side grouping (ame_gaps.cu): `multi_pair` are the
     pairs that share their rounded gap with another pair, sorted by key (stable: the reference's loop order inside a
     group), `zero_pair` the pairs of the zero group.  Returns (cross_idx, cross_key, lamb_idx, lamb_key)."""
-    cross, cross_key, lamb, lamb_key = [], [], [], []
+    parts = []
     multi_key = np.asarray(multi_key, dtype=np.float64)
     if len(multi_key):
         mi, mj = pair_to_ij(l, multi_pair)
@@ -148,19 +187,18 @@ def cross_lists_from_groups(l: int, multi_pair, multi_key, zero_pair, max_cross=
         est = int(np.sum((ends - starts).astype(np.int64) ** 2)) * 2
         if est > max_cross:
             raise NotImplementedError(f"gap spectrum is too degenerate for the cross-term list ({est} entries)")
-        for a, b in zip(starts, ends):
-            ii, jj, kk = mi[a:b], mj[a:b], float(multi_key[a])
-            for (aa, bb, kval) in ((ii, jj, kk), (jj, ii, -kk)):
-                GapGroups._pairs(aa, bb, kval, cross, cross_key, lamb, lamb_key)
+        parts.append(_group_cross_lists(mi, mj, starts, ends, multi_key[starts]))
     if len(zero_pair):
         zi, zj = pair_to_ij(l, np.sort(np.asarray(zero_pair)))
         aa = np.r_[zi, zj, np.arange(l)]
         bb = np.r_[zj, zi, np.arange(l)]
         if len(aa) ** 2 > max_cross:
             raise NotImplementedError("zero-gap group too large for the cross-term list")
-        GapGroups._pairs(aa, bb, 0.0, cross, cross_key, lamb, lamb_key, skip_diag_diag=True)
-    return (np.array(cross, dtype=np.int32).reshape(-1, 4), np.array(cross_key, dtype=np.float64),
-            np.array(lamb, dtype=np.int32).reshape(-1, 3), np.array(lamb_key, dtype=np.float64))
+        parts.append(_zero_group_lists(aa, bb))
+    if not parts:
+        return np.zeros((0, 4), dtype=np.int32), np.zeros(0), np.zeros((0, 3), dtype=np.int32), np.zeros(0)
+    return (np.concatenate([q[0] for q in parts]), np.concatenate([q[1] for q in parts]),
+            np.concatenate([q[2] for q in parts]), np.concatenate([q[3] for q in parts]))
 
 
 def jump_slots(w, K, digits=8, sigdigits=8):

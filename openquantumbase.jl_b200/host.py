@@ -15,6 +15,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 import math
+import threading
 from typing import Callable, List, Optional, Sequence
 
 import numpy as np
@@ -57,6 +58,11 @@ class Context:
     def set_zgemm_mode(self, mode: int):
         """1 = 3-multiplication complex product (default), 0 = 4-multiplication (BLAS rounding order)."""
         self.check(self.lib.oqb_set_zgemm_mode(self.h, int(mode)))
+
+    def zgemm_mode(self) -> int:
+        m = C.c_int()
+        self.check(self.lib.oqb_get_zgemm_mode(self.h, C.byref(m)))
+        return m.value
 
     def launch_count(self) -> int:
         n = C.c_uint64()
@@ -794,6 +800,83 @@ class GapIndices:
         self.w = self.groups.w
 
 
+class _PlanPrefetcher:
+    """Worker thread + high-priority CUDA stream + its own oqb_ctx that builds AME plans (H(s) assembly, eigensolver,
+    coupling rotation, gap tables) ahead of the RHS calls that will use them."""
+
+    def __init__(self, op):
+        import queue
+        import torch
+        self.op = op
+        self.device = op.ctx.device
+        with torch.cuda.device(self.device):
+            self.stream = torch.cuda.Stream(priority=-1)
+            with torch.cuda.stream(self.stream):
+                self.ctx = Context(self.device)
+        self.ctx.set_zgemm_mode(op.ctx.zgemm_mode() if hasattr(op.ctx, "zgemm_mode") else 1)
+        H = op.H
+        self.H = DenseHamiltonian.__new__(DenseHamiltonian)
+        self.H.__dict__.update(f=H.f, m=H.m, size=H.size, dimensionless_time=H.dimensionless_time, ctx=self.ctx, _op=None,
+                               _lind_key=None)
+        self.q = queue.Queue()
+        self.lock = threading.Lock()
+        self.pending, self.ready, self.errors = {}, {}, {}
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
+
+    def request(self, s: float):
+        key = (s, None)
+        with self.lock:
+            if key in self.pending or key in self.ready:
+                return
+            self.pending[key] = threading.Event()
+        self.q.put(s)
+
+    def take(self, key):
+        with self.lock:
+            ev = self.pending.get(key)
+        if ev is None:
+            return None
+        ev.wait()
+        with self.lock:
+            self.pending.pop(key, None)
+            err = self.errors.pop(key, None)
+            plan = self.ready.pop(key, None)
+        if err is not None:
+            raise err
+        return plan
+
+    def _run(self):
+        import torch
+        with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
+            while True:
+                s = self.q.get()
+                if s is None:
+                    return
+                key = (s, None)
+                try:
+                    plan = self.op._build_plan(s, None, None, self.ctx, self.H)
+                    self.ctx.sync()  # blocks this thread only: the plan is complete before anyone can adopt it
+                    with self.lock:
+                        self.ready[key] = plan
+                except BaseException as e:  # surfaced by take() in the caller's thread
+                    with self.lock:
+                        self.errors[key] = e
+                finally:
+                    self.pending[key].set()
+
+    def shutdown(self):
+        """Stops the worker; returns the plans nobody adopted (the caller destroys their handles)."""
+        self.q.put(None)
+        self.thread.join()
+        left = list(self.ready.values())
+        self.ready.clear()
+        self.pending.clear()
+        if self.H._op is not None:
+            self.ctx.lib.oqb_dense_destroy(self.H._op)
+        return left
+
+
 class DiffEqLiouvillian:
     """src/opensys/diffeq_liouvillian.jl:11-128.
 
@@ -890,11 +973,33 @@ class DiffEqLiouvillian:
     def clear_plans(self):
         """Drop every cached eigen-system plan (and its device tables)."""
         plans = self.__dict__.get("_plans", {})
+        pf = self.__dict__.pop("_prefetcher", None)
+        if pf is not None:
+            for plan in pf.shutdown():
+                self.ctx.lib.oqb_ame_destroy(plan["h"])
         self.ctx.sync()
         for plan in plans.values():
             self.ctx.lib.oqb_ame_destroy(plan["h"])
         plans.clear()
+        for _, h in self.__dict__.pop("_handle_pool", []):
+            self.ctx.lib.oqb_ame_destroy(h)
         self._ame, self._ame_s = None, None
+
+    def prefetch(self, p, ts: Sequence[float]):
+        """Start preparing the eigen-systems of the upcoming stage times on a high-priority side stream (its own
+        oqb_ctx, a worker thread) while the current stages' GEMMs run: s = p(t) of an RK stage is known before its ρ is.
+        `_prepare_ame` adopts a prefetched plan instead of building it.  Needs `device_eigh` (the side stream runs the
+        device eigensolver); a no-op otherwise."""
+        if not (getattr(self, "device_eigh", False) and isinstance(self.H, DenseHamiltonian) and self.opensys_eig):
+            return
+        pf = self.__dict__.get("_prefetcher")
+        if pf is None:
+            pf = self._prefetcher = _PlanPrefetcher(self)
+        plans = self.__dict__.setdefault("_plans", {})
+        for t in ts:
+            s = p(t)
+            if (s, None) not in plans:
+                pf.request(s)
 
     def _prepare_ame(self, s: float, w=None, v=None):
         """Everything that is shared by the batch for one value of s: eigen-system (host LAPACK, the device
@@ -904,19 +1009,48 @@ class DiffEqLiouvillian:
         if key in plans:  # a small LRU of prepared eigen-systems: schedule sweeps revisit the same s values
             plan = plans.pop(key)
             plans[key] = plan
-            self._ame, self._ame_s = plan["h"], key
-            self._w, self._v, self._v_dev, self._plan = plan["w"], plan["v"], plan["v_dev"], plan
-            return
-        lib, ctx = self.ctx.lib, self.ctx
+        else:
+            pf = self.__dict__.get("_prefetcher")
+            plan = pf.take(key) if (pf is not None and w is None) else None
+            if plan is not None:  # prepared on the side stream while earlier stages ran: adopt it on this context
+                self.ctx.check(self.ctx.lib.oqb_ame_rebind(plan["h"], self.ctx.h))
+                if plan["v_dev"] is not None:
+                    import torch
+                    plan["v_dev"].record_stream(torch.cuda.current_stream())
+            self._evict_plans(plans)
+            if plan is None:
+                plan = self._build_plan(s, w, v, self.ctx, self.H)
+            plans[key] = plan
+        self._ame, self._ame_s = plan["h"], key
+        self._w, self._v, self._v_dev, self._plan = plan["w"], plan["v"], plan["v_dev"], plan
+
+    def _evict_plans(self, plans):
+        """Drop least-recently-used plans down to `plan_cache` − 1; with constant couplings the handle (its K n×n
+        coupling matrices already on the device) goes to a small pool for the next eigen-system."""
+        const_coup = all(isinstance(lv.coupling, ConstantCouplings) for lv in self.opensys_eig)
+        pool = self.__dict__.setdefault("_handle_pool", [])
+        while len(plans) >= getattr(self, "plan_cache", 8):
+            old = plans.pop(next(iter(plans)))
+            self.ctx.sync()
+            if const_coup and len(pool) < 4:
+                with self.__dict__.setdefault("_pool_lock", threading.Lock()):
+                    pool.append((old["lvl"], old["h"]))
+            else:
+                self.ctx.lib.oqb_ame_destroy(old["h"])
+
+    def _build_plan(self, s: float, w, v, ctx: Context, H):
+        """One eigen-system and its tables on context `ctx` (the main one, or the prefetcher's side stream)."""
+        lib = ctx.lib
+        self.plans_built = getattr(self, "plans_built", 0) + 1
         dev_eig = None
-        if w is None and getattr(self, "device_eigh", False) and isinstance(self.H, DenseHamiltonian):
-            w, wd, vd = haml_eigs_device(self.H, s, self.lvl)
+        if w is None and getattr(self, "device_eigh", False) and isinstance(H, DenseHamiltonian):
+            w, wd, vd = haml_eigs_device(H, s, self.lvl)
             dev_eig = (wd, vd)
             v = vd  # marker: not None
         elif w is None:
-            w, v = haml_eigs(self.H, s, self.lvl)  # :94
+            w, v = haml_eigs(H, s, self.lvl)  # :94
         w = np.ascontiguousarray(np.real(w), dtype=np.float64)
-        n, lvl = self.H.size[0], len(w)
+        n, lvl = H.size[0], len(w)
         # couplings of all eigenbasis terms, concatenated; remember each term's slice
         coup, slices = [], []
         for lv in self.opensys_eig:
@@ -924,15 +1058,15 @@ class DiffEqLiouvillian:
             slices.append((len(coup), len(coup) + len(c)))
             coup += c
         h = None
-        const_coup = all(isinstance(lv.coupling, ConstantCouplings) for lv in self.opensys_eig)
-        while len(plans) >= getattr(self, "plan_cache", 8):  # evict the least recently used plan
-            old = plans.pop(next(iter(plans)))
-            ctx.sync()
-            if h is None and const_coup and old["lvl"] == lvl:
-                h = old["h"]  # constant couplings: recycle the handle (its K n×n matrices are already on the device);
-                #               oqb_ame_set_eigen below invalidates every table of the old eigen-system
-            else:
-                lib.oqb_ame_destroy(old["h"])
+        pool = self.__dict__.setdefault("_handle_pool", [])
+        with self.__dict__.setdefault("_pool_lock", threading.Lock()):  # the prefetch thread shares this pool
+            for ent in pool:
+                if ent[0] == lvl:
+                    pool.remove(ent)
+                    h = ent[1]  # recycled handle: oqb_ame_set_eigen below invalidates every table of the old eigen-system
+                    break
+        if h is not None:
+            ctx.check(lib.oqb_ame_rebind(h, ctx.h))
         if h is None:
             h = C.c_void_p()
             cbuf = _colmajor_stack(coup)
@@ -1025,10 +1159,8 @@ class DiffEqLiouvillian:
                                                    int(shared)))
             else:
                 raise NotImplementedError(f"eigenbasis term {type(lv).__name__} is not on the device path")
-        self._ame, self._ame_s = h, key
-        self._w, self._v = w, (None if dev_eig is not None else v)
-        self._v_dev = dev_eig[1] if dev_eig is not None else None
-        self._plan = plans[key] = {"h": h, "w": self._w, "v": self._v, "v_dev": self._v_dev, "lvl": lvl}
+        return {"h": h, "w": w, "v": (None if dev_eig is not None else v),
+                "v_dev": dev_eig[1] if dev_eig is not None else None, "lvl": lvl}
 
     def lindblad_jump(self, psi: "DeviceBatch", p, t, uniforms, mask=None, apply=False, w=None, v=None):
         """lindblad_jump(Op::DiffEqLiouvillian{true,false}, u, p, t) src/opensys/trajectory_jump.jl:64-69 → ame_jump
@@ -1419,8 +1551,11 @@ class DensityStepper:
         k, tmp, acc = u.zeros_like(), u.zeros_like(), u.zeros_like()
         for i in range(nsteps):
             t = t0 + i * dt
+            if getattr(self.op, "prefetch_stages", False):  # eigen-systems of this and the next step's stage times
+                self.op.prefetch(p, [t + dt / 2, t0 + (i + 1) * dt] + ([t0 + (i + 1) * dt + dt / 2, t0 + (i + 2) * dt] if i + 1 < nsteps else []))
             acc.t.copy_(u.t)
-            for (ts, w_acc, w_next) in ((t, dt / 6, dt / 2), (t + dt / 2, dt / 3, dt / 2), (t + dt / 2, dt / 3, dt), (t + dt, dt / 6, None)):
+            t_end = t0 + (i + 1) * dt  # bit-identical to the next step's first stage time: its eigen-system plan is reused
+            for (ts, w_acc, w_next) in ((t, dt / 6, dt / 2), (t + dt / 2, dt / 3, dt / 2), (t + dt / 2, dt / 3, dt), (t_end, dt / 6, None)):
                 src = u if ts == t and w_next == dt / 2 and w_acc == dt / 6 else tmp
                 k.t.zero_()
                 self.op(k, src, p, ts)

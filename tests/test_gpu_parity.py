@@ -1073,3 +1073,36 @@ def test_ohmic_correlation_and_timescales_device(Q):
     assert abs(tsb - tsb_o) < 1e-7 * tsb_o and abs(tb - tb_o) < 1e-7 * tb_o  # quadrature tolerance √eps; typically ~1e-13
     ta, ta_err = bath_g.coarse_grain_timescale(100)
     assert np.isclose(ta, np.sqrt(tsb * tb / 5), rtol=1e-12) and ta_err < 1e-6
+
+
+@pytest.mark.gpu
+def test_density_stepper_prefetched_eigensystems(Q):
+    """DensityStepper with the eigen-systems of the coming stage times prepared on a side stream (own context, worker
+    thread, oqb_ame_rebind on adoption) gives the same trajectory as preparing them in line; handles are recycled
+    through the shared pool (plan_cache smaller than the number of stage times)."""
+    rng = np.random.default_rng(808)
+    nq, nb = 4, 3
+    n = 2 ** nq
+    Hd = -F.standard_driver(nq)
+    Hp = F.two_local_term(list(rng.standard_normal(nq - 1)), [[i, i + 1] for i in range(1, nq)], nq) \
+        + sum(rng.standard_normal() * F.single_clause(["z"], [k + 1], 1.0, nq) for k in range(nq))
+    coup = [0.05 * F.single_clause(["z"], [k + 1], 1.0, nq) for k in range(2)]
+    Hg = Q.DenseHamiltonian([A, B], [Hd, Hp])
+    bath = Q.Ohmic(1e-2, 4, 16)
+    p = Q.ODEParams(Hg, 2.0)
+    u0 = rand_rho(rng, nb, n)
+    res = {}
+    for mode in ("inline", "prefetch"):
+        op = Q.DiffEqLiouvillian(Hg, [Q.DaviesGenerator(Q.ConstantCouplings(coup, unit="h"), bath, Q.ZERO_LAMBSHIFT)], [], n)
+        op.device_eigh, op.device_tables, op.plan_cache = True, True, 3
+        op.prefetch_stages = mode == "prefetch"
+        u = Q.DeviceBatch.from_host(u0.copy(), Q.get_context())
+        Q.DensityStepper(op).evolve(u, p, 0.2, 0.01, 6)
+        res[mode] = u.to_host()
+        if mode == "prefetch":
+            assert op.__dict__.get("_prefetcher") is not None  # the side stream really was used
+        op.clear_plans()
+        assert op.__dict__.get("_prefetcher") is None
+    assert relerr(res["prefetch"], res["inline"]) < 1e-10
+    tr = np.trace(res["prefetch"], axis1=1, axis2=2)
+    assert np.max(np.abs(tr - 1)) < 1e-12

@@ -230,3 +230,43 @@ def test_lambshift_host_closure_known_answer():
     S_tab = H.build_lambshift(np.linspace(-5, 5, 200), True, gfun)
     assert isinstance(S_tab, H.QuadraticBSpline) and abs(S_tab(0.0) - 0.03551) < 2e-3  # coarser table than the reference's
     assert abs(H.build_lambshift([], True, gfun)(0.0) - 0.03551) < 1e-4
+
+
+def test_vectorised_cross_lists_equal_the_loop():
+    """gaps._group_cross_lists / _zero_group_lists (numpy) produce exactly the lists — entries AND order — of the plain
+    double loop GapGroups._pairs that states the semantics (davies.jl:25-44 restricted to multi-pair groups)."""
+    from oqb_b200 import gaps as G
+    rng = np.random.default_rng(11)
+    for trial in range(6):
+        l = [5, 8, 12, 16, 9, 7][trial]
+        if trial % 2 == 0:
+            w = np.sort(rng.integers(-3, 4, l) * 0.5 + (rng.integers(0, 2, l) * 0.25))  # many equal gaps and equal levels
+        else:
+            w = np.arange(l) * 0.75 + (rng.random(l) < 0.3) * 0.75
+        gg = G.GapGroups(w, 8, 8)
+        # the loop, group by group
+        iu, ju = np.triu_indices(l, 1)
+        gap = w[ju] - w[iu]
+        zero = np.abs(gap) <= 1e-8
+        key = np.zeros_like(gap)
+        key[~zero] = G.round_sigdigits(gap[~zero], 8)
+        cross, ck, lamb, lk = [], [], [], []
+        nzi, nzj, nzk = iu[~zero], ju[~zero], key[~zero]
+        order = np.argsort(nzk, kind="stable")
+        ks = nzk[order]
+        starts = np.flatnonzero(np.r_[True, ks[1:] != ks[:-1]]) if ks.size else np.zeros(0, dtype=int)
+        ends = np.r_[starts[1:], ks.size] if ks.size else np.zeros(0, dtype=int)
+        for a, b in zip(starts, ends):
+            if b - a < 2:
+                continue
+            mem = order[a:b]
+            for (aa, bb, kv) in ((nzi[mem], nzj[mem], float(ks[a])), (nzj[mem], nzi[mem], -float(ks[a]))):
+                G.GapGroups._pairs(aa, bb, kv, cross, ck, lamb, lk)
+        zi, zj = iu[zero], ju[zero]
+        if zi.size:
+            G.GapGroups._pairs(np.r_[zi, zj, np.arange(l)], np.r_[zj, zi, np.arange(l)], 0.0, cross, ck, lamb, lk, skip_diag_diag=True)
+        assert np.array_equal(gg.cross_idx, np.array(cross, dtype=np.int32).reshape(-1, 4))
+        assert np.array_equal(gg.cross_key, np.array(ck, dtype=float))
+        assert np.array_equal(gg.lamb_idx, np.array(lamb, dtype=np.int32).reshape(-1, 3))
+        assert np.array_equal(gg.lamb_key, np.array(lk, dtype=float))
+        assert len(cross) > 0
