@@ -61,6 +61,12 @@ int oqb_launch_count(const oqb_ctx* ctx, uint64_t* n); /* kernels launched throu
  * Also settable at context creation through the environment variable OQB_ZGEMM_3M=0/1. */
 int oqb_set_zgemm_mode(oqb_ctx* ctx, int mode);
 int oqb_get_zgemm_mode(const oqb_ctx* ctx, int* mode);
+/* Real eigenvectors: when the eigenvector matrix handed to oqb_ame_set_eigen(_device) has no imaginary part (H(s) real
+ * symmetric — every X/Z/ZZ annealing Hamiltonian), the rotations v'ρv and vXv' need 2 real products per complex product
+ * instead of 3 (the other factor's imaginary part times zero is skipped).  1 (default) = detect and exploit, 0 = always
+ * run the general complex product.  Results agree to rounding.  Environment: OQB_REAL_OPERAND=0/1. */
+int oqb_set_real_operand_mode(oqb_ctx* ctx, int on);
+int oqb_get_real_operand_mode(const oqb_ctx* ctx, int* on);
 
 int oqb_malloc(oqb_ctx* ctx, size_t nbytes, void** d_ptr);
 int oqb_free(oqb_ctx* ctx, void* d_ptr);
@@ -177,6 +183,8 @@ int oqb_ame_set_eigen(oqb_ame* ame, const double* h_w, const void* h_v);
 /* same with (w, v) already in device memory — e.g. straight out of a device eigensolver (cuSOLVER Zheevd), so that
  * the n×lvl eigenvector matrix never crosses PCIe; only w (lvl doubles) goes back for the host's gap grouping. */
 int oqb_ame_set_eigen_device(oqb_ame* ame, const double* d_w, const void* d_v);
+/* *out = 1 when the current eigenvector matrix is exactly real (the real-operand products are then used). */
+int oqb_ame_eigenvectors_real(const oqb_ame* ame, int* out);
 /* Davies generator tables (src/opensys/davies.jl:21-47, closed form of SURVEY App. A.5):
  *  h_gam[a+b*lvl] = γ(ω̃_ab), h_S[a+b*lvl] = S(ω̃_ab) at the signed ROUNDED gaps of GapIndices
  *  (src/opensys/opensys_util.jl:25-61; 0 inside the zero group), evaluated by the host closures.

@@ -58,6 +58,9 @@ SIGNATURES = {
     "oqb_ame_set_eigen": [c_void_p, c_dp, c_void_p],
     "oqb_ame_set_eigen_device": [c_void_p, c_void_p, c_void_p],
     "oqb_ame_set_davies": [c_void_p, c_dp, c_dp, c_i64, c_i32p, c_dp, c_i64, c_i32p, c_dp],
+    "oqb_set_real_operand_mode": [c_void_p, c_int],
+    "oqb_get_real_operand_mode": [c_void_p, C.POINTER(c_int)],
+    "oqb_ame_eigenvectors_real": [c_void_p, C.POINTER(c_int)],
     "oqb_ame_rebind": [c_void_p, c_void_p],
     "oqb_ame_set_onesided_ohmic": [c_void_p, c_int, c_i32p, c_i32p, C.c_double, C.c_double, C.c_double],
     "oqb_ame_set_lambshift_spline": [c_void_p, c_int, C.c_double, C.c_double, c_void_p],

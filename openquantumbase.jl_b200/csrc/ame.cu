@@ -18,6 +18,14 @@ namespace {
 
 const size_t kAmeBudget = (size_t)8 << 30;  // bytes of scratch per batch chunk (180 GB HBM per GPU)
 
+// counts entries of V with a non-zero imaginary part (any NaN counts too)
+__global__ void imag_nonzero_kernel(long long n, const c128* __restrict__ v, unsigned int* __restrict__ cnt) {
+    bool nz = false;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x)
+        nz |= !(v[e].y == 0.0);
+    if (__syncthreads_or(nz) && threadIdx.x == 0) atomicAdd(cnt, 1u);
+}
+
 bool needs_general_path(const oqb_ame* a) { return a->ncross > 0 || a->d_Moff || a->npairs > 0; }
 
 // Eigenbasis terms on ρ̃ = R (lvl×lvl per member).  overwrite: X = …, else X += ….
@@ -120,6 +128,7 @@ int ame_rhs_impl(oqb_ame* a, int nb, const c128* u, c128* du) {
         p.M = l; p.N = n; p.K = n; p.batch = cnt;
         p.opA = OP_C;
         p.A = a->d_V; p.lda = n; p.strideA = 0;
+        p.real_operand = a->v_real ? 1 : 0;
         p.B = ub; p.ldb = n; p.strideB = nn;
         p.C = T; p.ldc = l; p.strideC = ln;
         OQB_TRY(zgemm(c, p));
@@ -127,6 +136,7 @@ int ame_rhs_impl(oqb_ame* a, int nb, const c128* u, c128* du) {
         q.M = l; q.N = l; q.K = n; q.batch = cnt;
         q.A = T; q.lda = l; q.strideA = ln;
         q.B = a->d_V; q.ldb = n; q.strideB = 0;
+        q.real_operand = a->v_real ? 2 : 0;
         q.ldc = l; q.strideC = ll;
         if (!general) {
             // fused: X = C∘ρ̃ in the GEMM epilogue, diagonal of ρ̃ captured for the W·pop term
@@ -145,11 +155,13 @@ int ame_rhs_impl(oqb_ame* a, int nb, const c128* u, c128* du) {
         r.M = l; r.N = n; r.K = l; r.batch = cnt;
         r.A = X; r.lda = l; r.strideA = ll;
         r.B = a->d_V; r.ldb = n; r.strideB = 0; r.opB = OP_C;
+        r.real_operand = a->v_real ? 2 : 0;
         r.C = T; r.ldc = l; r.strideC = ln;
         OQB_TRY(zgemm(c, r));
         ZgemmParams s;  // du = v T           (n × n), OVERWRITES  (diffeq_liouvillian.jl:105)
         s.M = n; s.N = n; s.K = l; s.batch = cnt;
         s.A = a->d_V; s.lda = n; s.strideA = 0;
+        s.real_operand = a->v_real ? 1 : 0;
         s.B = T; s.ldb = l; s.strideB = ln;
         s.C = dub; s.ldc = n; s.strideC = nn;
         OQB_TRY(zgemm(c, s));
@@ -240,8 +252,20 @@ static int set_eigen_impl(oqb_ame* a, const double* w, const void* v, bool on_de
     OQB_TRY(oqb_ame_clear_jump(a));
     OQB_CUDA(c, cudaMemcpyAsync(a->d_w, w, l * sizeof(double), kind, c->stream));
     a->has_v = v != nullptr;
+    a->v_real = false;
     if (a->has_v) {
         OQB_CUDA(c, cudaMemcpyAsync(a->d_V, v, (size_t)ln * sizeof(c128), kind, c->stream));
+        {   // real eigenvectors (real-symmetric H): the rotations below and in every RHS use the real-operand product
+            OQB_TRY(ws_reserve(c, 256));
+            unsigned int* cnt = (unsigned int*)c->ws;
+            unsigned int h_cnt = 1;
+            OQB_CUDA(c, cudaMemsetAsync(cnt, 0, sizeof(unsigned int), c->stream));
+            imag_nonzero_kernel<<<296, 256, 0, c->stream>>>(ln, a->d_V, cnt);
+            OQB_LAUNCH_CHECK(c);
+            OQB_CUDA(c, cudaMemcpyAsync(&h_cnt, cnt, sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
+            OQB_CUDA(c, cudaStreamSynchronize(c->stream));
+            a->v_real = h_cnt == 0;
+        }
         if (K) {  // A_α = v' c_α v   (src/opensys/davies.jl:24)
             OQB_TRY(ws_reserve(c, (size_t)K * ln * sizeof(c128)));
             c128* T = (c128*)c->ws;
@@ -249,12 +273,14 @@ static int set_eigen_impl(oqb_ame* a, const double* w, const void* v, bool on_de
             p.M = n; p.N = l; p.K = n; p.batch = K;
             p.A = a->d_coup; p.lda = n; p.strideA = nn;
             p.B = a->d_V; p.ldb = n; p.strideB = 0;
+            p.real_operand = a->v_real ? 2 : 0;
             p.C = T; p.ldc = n; p.strideC = ln;
             OQB_TRY(zgemm(c, p));
             ZgemmParams q;  // A_α = v' T_α  (l × l)
             q.M = l; q.N = l; q.K = n; q.batch = K;
             q.opA = OP_C;
             q.A = a->d_V; q.lda = n; q.strideA = 0;
+            q.real_operand = a->v_real ? 1 : 0;
             q.B = T; q.ldb = n; q.strideB = ln;
             q.C = a->d_A; q.ldc = l; q.strideC = ll;
             OQB_TRY(zgemm(c, q));
@@ -265,6 +291,12 @@ static int set_eigen_impl(oqb_ame* a, const double* w, const void* v, bool on_de
     OQB_CUDA(c, cudaStreamSynchronize(c->stream));  // w / v may be reused by the caller
     a->have_eigen = true;
     return davies_tables(c, l, K, a->d_A, nullptr, nullptr, a->d_w, 0, nullptr, nullptr, nullptr, a->d_Cm);
+}
+
+int oqb_ame_eigenvectors_real(const oqb_ame* a, int* out) {
+    if (!a || !out) return OQB_EINVAL;
+    *out = (a->have_eigen && a->has_v && a->v_real) ? 1 : 0;
+    return 0;
 }
 
 int oqb_ame_set_eigen(oqb_ame* a, const double* h_w, const void* h_v) {
@@ -473,11 +505,13 @@ int oqb_ame_update_cache(oqb_ame* a, void* d_cache) {
     p.M = l; p.N = n; p.K = l;
     p.A = D; p.lda = l;
     p.B = a->d_V; p.ldb = n; p.opB = OP_C;
+    p.real_operand = a->v_real ? 2 : 0;
     p.C = T; p.ldc = l;
     OQB_TRY(zgemm(c, p));
     ZgemmParams q;  // cache = v T   (src/opensys/diffeq_liouvillian.jl:124)
     q.M = n; q.N = n; q.K = l;
     q.A = a->d_V; q.lda = n;
+    q.real_operand = a->v_real ? 1 : 0;
     q.B = T; q.ldb = l;
     q.C = (c128*)d_cache; q.ldc = n;
     return zgemm(c, q);

@@ -8,6 +8,7 @@ struct oqb_ame {
     oqb_ctx* ctx = nullptr;
     int n = 0, lvl = 0, K = 0;
     bool has_v = false, have_eigen = false;
+    bool v_real = false;  // every entry of V has zero imaginary part: rotations use the real-operand product
     oqb::c128* d_coup = nullptr;  // K n×n couplings as given
     oqb::c128* d_V = nullptr;     // n × lvl
     double* d_w = nullptr;   // lvl

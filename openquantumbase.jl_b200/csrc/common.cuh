@@ -22,6 +22,8 @@ struct Ctx {
     uint64_t launches = 0;
     // complex product of the TMA ZGEMM: 1 = 3-multiplication (default), 0 = classic 4-multiplication
     int zgemm_3m = 1;
+    // exploit ZgemmParams::real_operand hints (oqb_set_real_operand_mode; OQB_REAL_OPERAND=0 disables)
+    int real_operand = 1;
     // grow-only device workspace
     void* ws = nullptr;
     size_t ws_bytes = 0;
@@ -111,6 +113,10 @@ struct ZgemmParams {
     //   (index z % alpha_scale_mod when alpha_scale_mod > 0)
     const double* alpha_scale = nullptr;
     int alpha_scale_mod = 0;
+    // hint: 1 = every entry of A has zero imaginary part, 2 = same for B (e.g. the eigenvectors of a real-symmetric
+    // Hamiltonian).  The TMA kernel then issues 2 real products per complex one (re += Ar·Br, im += Ar·Bi) instead of
+    // 3 or 4; kernels that ignore the hint still give the right answer.  Only honoured when Ctx::real_operand is on.
+    int real_operand = 0;
 };
 int zgemm(Ctx* c, const ZgemmParams& p);
 int zgemm_tma(Ctx* c, const ZgemmParams& p, bool* used);  // zgemm_tma.cu

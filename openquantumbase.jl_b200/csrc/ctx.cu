@@ -114,6 +114,7 @@ int oqb_create(int device, oqb_ctx** out) {
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return OQB_ECUDA; }
     c->own_stream = true;
     if (const char* e = getenv("OQB_ZGEMM_3M")) c->zgemm_3m = atoi(e) != 0;
+    if (const char* e = getenv("OQB_REAL_OPERAND")) c->real_operand = atoi(e) != 0;
     for (int i = 0; i < 2; ++i) cudaStreamCreateWithFlags(&c->copy_stream[i], cudaStreamNonBlocking);
     for (int i = 0; i < 8; ++i) cudaEventCreateWithFlags(&c->ev[i], cudaEventDisableTiming);
     *out = c;
@@ -161,6 +162,11 @@ int oqb_set_zgemm_mode(oqb_ctx* c, int mode) {
     return 0;
 }
 int oqb_get_zgemm_mode(const oqb_ctx* c, int* mode) { *mode = c->zgemm_3m; return 0; }
+int oqb_set_real_operand_mode(oqb_ctx* c, int on) {
+    c->real_operand = on != 0;
+    return 0;
+}
+int oqb_get_real_operand_mode(const oqb_ctx* c, int* on) { *on = c->real_operand; return 0; }
 
 int oqb_malloc(oqb_ctx* c, size_t nbytes, void** d) {
     cudaError_t e = cudaMalloc(d, nbytes ? nbytes : 16);

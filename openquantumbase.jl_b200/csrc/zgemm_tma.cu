@@ -96,10 +96,14 @@ __device__ __forceinline__ double flipt(double x, unsigned mask) {
 // M3_ selects the 3-multiplication complex product (T1 = ArBr, T2 = AiBi, T3 = (Ar+Ai)(Br+Bi);
 // re = T1 − T2, im = T3 − T1 − T2): 3 DMMAs per complex 8x8x4 instead of 4, at the price of a third
 // accumulator set — the warp tile shrinks to 32x16 complex (96 accumulator registers).
-template <int BM_, int BN_, int STAGES_, bool TA_, bool TB_, bool M3_ = false, int MINB_ = (BM_ == 64 ? 2 : 1)>
+// RM_ (4-multiplication layout only): 1 = A is real, 2 = B is real — two DMMAs per complex 8x8x4
+// (re += Ar·Br and im += Ar·Bi, resp. im += Ai·Br); the unused imaginary fragments are never touched.
+template <int BM_, int BN_, int STAGES_, bool TA_, bool TB_, bool M3_ = false, int MINB_ = (BM_ == 64 ? 2 : 1), int RM_ = 0>
 struct TCfg {
     static constexpr int BM = BM_, BN = BN_, STAGES = STAGES_;  // k depth of a stage: 8 complex = 128 bytes
     static constexpr bool TA = TA_, TB = TB_, M3 = M3_;
+    static constexpr int RM = RM_;
+    static_assert(!(M3_ && RM_ != 0), "the real-operand product uses the two-accumulator layout");
     static constexpr int WTN = M3 ? 16 : 32, NJ = WTN / 8, MINB = MINB_;
     static constexpr int WARPS_M = BM / 32, WARPS_N = BN / WTN, NCONS = WARPS_M * WARPS_N;
     static constexpr int NTHREADS = NCONS * 32;
@@ -300,15 +304,20 @@ __global__ void __launch_bounds__(CF::NTHREADS, CF::MINB)
 #pragma unroll
                     for (int j = 0; j < NJ; ++j) {
                         dmma884t(acc_re[i][j][0], acc_re[i][j][1], ar[i], br[j]);
-                        dmma884t(acc_im[i][j][0], acc_im[i][j][1], ar[i], bi[j]);
+                        if constexpr (CF::RM == 2)
+                            dmma884t(acc_im[i][j][0], acc_im[i][j][1], ai[i], br[j]);
+                        else
+                            dmma884t(acc_im[i][j][0], acc_im[i][j][1], ar[i], bi[j]);
                     }
+                if constexpr (CF::RM == 0) {
 #pragma unroll
-                for (int i = 0; i < 4; ++i)
+                    for (int i = 0; i < 4; ++i)
 #pragma unroll
-                    for (int j = 0; j < NJ; ++j) {
-                        dmma884t(acc_re[i][j][0], acc_re[i][j][1], nai[i], bi[j]);
-                        dmma884t(acc_im[i][j][0], acc_im[i][j][1], ai[i], br[j]);
-                    }
+                        for (int j = 0; j < NJ; ++j) {
+                            dmma884t(acc_re[i][j][0], acc_re[i][j][1], nai[i], bi[j]);
+                            dmma884t(acc_im[i][j][0], acc_im[i][j][1], ai[i], br[j]);
+                        }
+                }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(bars + (STAGES + s) * 8);
@@ -483,6 +492,9 @@ int dispatch(Ctx* c, const ZgemmParams& p, bool* used) {
     const bool big = bm_force ? bm_force == 128 : p.K > 512;
     // 3M product (Ctx::zgemm_3m, default on; oqb_set_zgemm_mode / OQB_ZGEMM_3M=0 select the 4-multiplication kernel):
     // 64x64 CTA of 8 warps (32x16 warp tiles), 8 stages, one CTA per SM.
+    // real operand (eigenvectors of a real-symmetric Hamiltonian): half the DMMAs of the 4-multiplication product
+    if (c->real_operand && p.real_operand == 1 && p.M > 64) return launch_tma<TCfg<128, 64, 6, TA, TB, false, 1, 1>>(c, p, used);
+    if (c->real_operand && p.real_operand == 2 && p.M > 64) return launch_tma<TCfg<128, 64, 6, TA, TB, false, 1, 2>>(c, p, used);
     if (c->zgemm_3m) return launch_tma<TCfg<64, 64, 8, TA, TB, true, 1>>(c, p, used);
     if (p.M > 64 && big) return launch_tma<TCfg<128, 64, 6, TA, TB>>(c, p, used);
     return launch_tma<TCfg<64, 64, 6, TA, TB>>(c, p, used);

@@ -59,6 +59,15 @@ class Context:
         """1 = 3-multiplication complex product (default), 0 = 4-multiplication (BLAS rounding order)."""
         self.check(self.lib.oqb_set_zgemm_mode(self.h, int(mode)))
 
+    def set_real_operand_mode(self, on: bool):
+        """Exploit exactly-real eigenvector matrices in the AME rotations (default on); off = general complex product."""
+        self.check(self.lib.oqb_set_real_operand_mode(self.h, int(bool(on))))
+
+    def real_operand_mode(self) -> bool:
+        m = C.c_int()
+        self.check(self.lib.oqb_get_real_operand_mode(self.h, C.byref(m)))
+        return bool(m.value)
+
     def zgemm_mode(self) -> int:
         m = C.c_int()
         self.check(self.lib.oqb_get_zgemm_mode(self.h, C.byref(m)))
@@ -453,7 +462,15 @@ def haml_eigs_device(H: "DenseHamiltonian", s: float, lvl: Optional[int]):
     cf = _coef(H.f, _svec(s, 1))
     H.ctx.check(H.ctx.lib.oqb_dense_hamiltonian(H._dense_op(), 1, _lib.dptr(cf), 1, out.ptr))
     # out.t[0] is H column-major = Hᵀ row-major = conj(H): same eigenvalues, conjugated eigenvectors
-    w, vt = torch.linalg.eigh(out.t[0])
+    if getattr(H, "_is_real", None) is None:  # real-symmetric H(s) for every s: real term matrices (real coefficients)
+        H._is_real = all(not np.any(np.imag(m)) for m in H.m)
+    if H._is_real and not np.any(np.imag(cf)):
+        # the real symmetric eigensolver (Dsyevd) is cheaper than Zheevd and returns exactly real eigenvectors, which
+        # the rotations exploit (oqb_set_real_operand_mode)
+        w, vr = torch.linalg.eigh(out.t[0].real)
+        vt = vr.to(torch.complex128)
+    else:
+        w, vt = torch.linalg.eigh(out.t[0])
     l = n if lvl is None else min(lvl, n)
     vd = vt[:, :l].conj().T.contiguous()  # row j = eigenvector j of H  ⇔  column-major n×l
     wd = w[:l].contiguous()

@@ -1106,3 +1106,62 @@ def test_density_stepper_prefetched_eigensystems(Q):
     assert relerr(res["prefetch"], res["inline"]) < 1e-10
     tr = np.trace(res["prefetch"], axis1=1, axis2=2)
     assert np.max(np.abs(tr - 1)) < 1e-12
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("lvl", [128, 16])
+def test_ame_real_eigenvector_products(Q, lvl):
+    """Real-symmetric H(s) ⇒ exactly real eigenvectors ⇒ the rotations v'ρv, vXv' run the real-operand product
+    (2 DMMAs per complex product, zgemm_tma.cu RM modes).  Same RHS as the general complex product (1e-13) and as the
+    oracle (1e-12); a Hamiltonian with a σy term keeps the general path."""
+    import ctypes
+    rng = np.random.default_rng(99 + lvl)
+    nq, nb = 7, 2
+    n = 2 ** nq
+    Hd = -F.standard_driver(nq)
+    Hp = F.two_local_term(list(rng.standard_normal(nq - 1)), [[i, i + 1] for i in range(1, nq)], nq) \
+        + sum(rng.standard_normal() * F.single_clause(["z"], [k + 1], 1.0, nq) for k in range(nq))
+    coup = [F.single_clause(["z"], [k + 1], 1.0, nq) for k in range(2)]
+    ctx = Q.get_context()
+    Hg, Ho = Q.DenseHamiltonian([A, B], [Hd, Hp]), O.DenseHamiltonian([A, B], [Hd, Hp])
+    bath_g, bath_o = Q.Ohmic(1e-2, 4, 16), O.Ohmic(1e-2, 4, 16)
+    mk = lambda H: Q.DiffEqLiouvillian(H, [Q.DaviesGenerator(Q.ConstantCouplings(coup, unit="h"), bath_g, Q.ZERO_LAMBSHIFT)], [], lvl)
+    u = rand_rho(rng, nb, n)
+    p = Q.ODEParams(Hg, 2.0)
+    w, v = O.haml_eigs(Ho, 0.45, lvl)
+    assert not np.any(v.imag)  # LAPACK keeps real data real
+    res = {}
+    try:
+        for on in (True, False):
+            ctx.set_real_operand_mode(on)
+            op = mk(Hg)
+            res[on] = op.rhs_with_eig(np.zeros_like(u), u, p, 0.9, w, v)
+            flag = ctypes.c_int()
+            ctx.check(ctx.lib.oqb_ame_eigenvectors_real(op._ame, ctypes.byref(flag)))
+            assert flag.value == 1
+            cache = op.update_cache(np.zeros((n, n), complex), p, 0.9, w, v)
+            res[("cache", on)] = cache
+            op.clear_plans()
+    finally:
+        ctx.set_real_operand_mode(True)
+    assert relerr(res[True], res[False]) < 1e-13 and relerr(res[("cache", True)], res[("cache", False)]) < 1e-13
+    if lvl == 16:
+        opo = O.DiffEqLiouvillian(Ho, [O.DaviesGenerator([2 * np.pi * c for c in coup], bath_o.spectrum, lambda x: 0.0)], [], lvl)
+        ref = np.stack([opo.rhs_with_eig(u[b], O.ODEParams(Ho, 2.0), 0.9, w, v) for b in range(nb)])
+        assert relerr(res[True], ref) < TOL
+    # device eigensolver on a real Hamiltonian: real symmetric solver, same RHS (gauge-invariant)
+    op = mk(Hg)
+    op.device_eigh = True
+    d_dev = op(np.zeros_like(u), u, p, 0.9)
+    flag = ctypes.c_int()
+    ctx.check(ctx.lib.oqb_ame_eigenvectors_real(op._ame, ctypes.byref(flag)))
+    assert flag.value == 1 and relerr(d_dev, res[True]) < 1e-9
+    op.clear_plans()
+    # complex Hamiltonian: not real, general product
+    sy_term = F.single_clause(["y"], [1], 0.3, nq)
+    Hc = Q.DenseHamiltonian([A, B, lambda s: 1.0], [Hd, Hp, sy_term])
+    opc = mk(Hc)
+    opc(np.zeros_like(u), u, Q.ODEParams(Hc, 2.0), 0.9)
+    ctx.check(ctx.lib.oqb_ame_eigenvectors_real(opc._ame, ctypes.byref(flag)))
+    assert flag.value == 0
+    opc.clear_plans()
