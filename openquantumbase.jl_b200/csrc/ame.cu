@@ -26,6 +26,21 @@ __global__ void imag_nonzero_kernel(long long n, const c128* __restrict__ v, uns
     if (__syncthreads_or(nz) && threadIdx.x == 0) atomicAdd(cnt, 1u);
 }
 
+// *out = true when no entry of v[0..n) has a non-zero imaginary part (synchronises the stream)
+int detect_real(oqb_ame* a, const c128* v, long long n, bool* out) {
+    oqb_ctx* c = a->ctx;
+    *out = false;
+    if (!a->d_flag) OQB_TRY(ame_alloc(c, (void**)&a->d_flag, 256));
+    unsigned int h_cnt = 1;
+    OQB_CUDA(c, cudaMemsetAsync(a->d_flag, 0, sizeof(unsigned int), c->stream));
+    imag_nonzero_kernel<<<296, 256, 0, c->stream>>>(n, v, a->d_flag);
+    OQB_LAUNCH_CHECK(c);
+    OQB_CUDA(c, cudaMemcpyAsync(&h_cnt, a->d_flag, sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
+    OQB_CUDA(c, cudaStreamSynchronize(c->stream));
+    *out = h_cnt == 0;
+    return 0;
+}
+
 bool needs_general_path(const oqb_ame* a) { return a->ncross > 0 || a->d_Moff || a->npairs > 0; }
 
 // Eigenbasis terms on ρ̃ = R (lvl×lvl per member).  overwrite: X = …, else X += ….
@@ -68,12 +83,14 @@ int eig_apply(oqb_ame* a, int nb, const c128* R, c128* X, bool overwrite, bool w
         ZgemmParams p;  // M1[b,p] = Λ_p ρ̃_b, the blocks of member b side by side (l × P·l)
         p.M = p.N = p.K = l; p.batch = nb; p.batch2 = P;
         p.A = a->d_Lam; p.lda = l; p.strideA = 0; p.strideA2 = ll;
+        p.real_operand = a->lam_real ? 1 : 0;
         p.B = R; p.ldb = l; p.strideB = ll; p.strideB2 = 0;
         p.C = M1; p.ldc = l; p.strideC = (long long)P * ll; p.strideC2 = ll;
         OQB_TRY(zgemm(c, p));
         ZgemmParams q;  // Kb = P ρ̃
         q.M = q.N = q.K = l; q.batch = nb;
         q.A = a->d_Psum; q.lda = l; q.strideA = 0;
+        q.real_operand = a->psum_real ? 1 : 0;
         q.B = R; q.ldb = l; q.strideB = ll;
         q.C = Kb; q.ldc = l; q.strideC = ll;
         OQB_TRY(zgemm(c, q));
@@ -81,6 +98,7 @@ int eig_apply(oqb_ame* a, int nb, const c128* R, c128* X, bool overwrite, bool w
         r.M = r.N = l; r.K = P * l; r.batch = nb;
         r.A = M1; r.lda = l; r.strideA = (long long)P * ll;
         r.B = a->d_Abstack; r.ldb = (long long)P * l; r.strideB = 0;
+        r.real_operand = a->ab_real ? 2 : 0;
         r.C = Kb; r.ldc = l; r.strideC = ll;
         r.alpha = make_double2(-1.0, 0.0);
         r.beta = make_double2(1.0, 0.0);
@@ -218,6 +236,7 @@ int oqb_ame_clear_onesided(oqb_ame* a) {
     ame_free(a->ctx, a->d_Psum);
     ame_free(a->ctx, a->d_Abstack);
     a->npairs = 0;
+    a->lam_real = a->psum_real = a->ab_real = false;
     a->h_beta.clear();
     return 0;
 }
@@ -230,6 +249,7 @@ int oqb_ame_destroy(oqb_ame* a) {
     oqb_ame_clear_onesided(a);
     oqb_ame_clear_jump(a);
     ame_free(a->ctx, a->d_grp_key);
+    ame_free(a->ctx, a->d_flag);
     ame_free(a->ctx, a->d_Scoef);
     ame_free(a->ctx, a->d_grp_pair);
     (void)he;
@@ -255,17 +275,8 @@ static int set_eigen_impl(oqb_ame* a, const double* w, const void* v, bool on_de
     a->v_real = false;
     if (a->has_v) {
         OQB_CUDA(c, cudaMemcpyAsync(a->d_V, v, (size_t)ln * sizeof(c128), kind, c->stream));
-        {   // real eigenvectors (real-symmetric H): the rotations below and in every RHS use the real-operand product
-            OQB_TRY(ws_reserve(c, 256));
-            unsigned int* cnt = (unsigned int*)c->ws;
-            unsigned int h_cnt = 1;
-            OQB_CUDA(c, cudaMemsetAsync(cnt, 0, sizeof(unsigned int), c->stream));
-            imag_nonzero_kernel<<<296, 256, 0, c->stream>>>(ln, a->d_V, cnt);
-            OQB_LAUNCH_CHECK(c);
-            OQB_CUDA(c, cudaMemcpyAsync(&h_cnt, cnt, sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
-            OQB_CUDA(c, cudaStreamSynchronize(c->stream));
-            a->v_real = h_cnt == 0;
-        }
+        // real eigenvectors (real-symmetric H): the rotations below and in every RHS use the real-operand product
+        OQB_TRY(detect_real(a, a->d_V, ln, &a->v_real));
         if (K) {  // A_α = v' c_α v   (src/opensys/davies.jl:24)
             OQB_TRY(ws_reserve(c, (size_t)K * ln * sizeof(c128)));
             c128* T = (c128*)c->ws;
@@ -434,6 +445,10 @@ int ame_onesided_install(oqb_ame* a, int npairs, const int32_t* h_alpha, const i
                                       (size_t)l * sizeof(c128), l, cudaMemcpyDeviceToDevice, c->stream));
     }
     OQB_CUDA(c, cudaStreamSynchronize(c->stream));
+    // real couplings in a real eigenbasis with S ≡ 0 make Λ_p, ΣA_βΛ_p and the A_β stack real: real-operand products
+    OQB_TRY(detect_real(a, a->d_Lam, (long long)npairs * ll, &a->lam_real));
+    OQB_TRY(detect_real(a, a->d_Psum, (long long)ll, &a->psum_real));
+    OQB_TRY(detect_real(a, a->d_Abstack, (long long)npairs * ll, &a->ab_real));
     return 0;
 }
 

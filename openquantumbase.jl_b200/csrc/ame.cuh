@@ -9,6 +9,8 @@ struct oqb_ame {
     int n = 0, lvl = 0, K = 0;
     bool has_v = false, have_eigen = false;
     bool v_real = false;  // every entry of V has zero imaginary part: rotations use the real-operand product
+    bool lam_real = false, psum_real = false, ab_real = false;  // same for Λ_p, Σ A_βΛ_p and the A_β stack (one-sided AME)
+    unsigned int* d_flag = nullptr;  // counter for the exact-realness checks
     oqb::c128* d_coup = nullptr;  // K n×n couplings as given
     oqb::c128* d_V = nullptr;     // n × lvl
     double* d_w = nullptr;   // lvl

@@ -164,6 +164,7 @@ int oqb_ame_jump(oqb_ame* a, int nb, void* d_psi, const double* d_uniform, const
         ZgemmParams p;
         p.M = l; p.N = nb; p.K = n; p.opA = OP_C;
         p.A = a->d_V; p.lda = n;
+        p.real_operand = a->v_real ? 1 : 0;
         p.B = Psi; p.ldb = n;
         p.C = Phi; p.ldc = l;
         OQB_TRY(zgemm(c, p));
@@ -183,6 +184,7 @@ int oqb_ame_jump(oqb_ame* a, int nb, void* d_psi, const double* d_uniform, const
             ZgemmParams p;
             p.M = n; p.N = nb; p.K = l;
             p.A = a->d_V; p.lda = n;
+            p.real_operand = a->v_real ? 1 : 0;
             p.B = PhiNew; p.ldb = l;
             p.C = PsiNew; p.ldc = n;
             OQB_TRY(zgemm(c, p));

@@ -1165,3 +1165,39 @@ def test_ame_real_eigenvector_products(Q, lvl):
     ctx.check(ctx.lib.oqb_ame_eigenvectors_real(opc._ame, ctypes.byref(flag)))
     assert flag.value == 0
     opc.clear_plans()
+
+
+@pytest.mark.gpu
+def test_onesided_and_jump_real_operand_products(Q):
+    """One-sided AME with real couplings in a real eigenbasis and S ≡ 0: Λ_p, ΣA_βΛ_p and the A_β stack are exactly real
+    and their products run the real-operand kernel (l = 128 > 64); ame_jump's v'ψ / vφ' too.  Against the general
+    complex product (1e-13) and the oracle (1e-12)."""
+    rng = np.random.default_rng(2024)
+    nq, nb, lvl = 7, 2, 128
+    n = 2 ** nq
+    Hd = -F.standard_driver(nq)
+    Hp = F.two_local_term(list(rng.standard_normal(nq - 1)), [[i, i + 1] for i in range(1, nq)], nq) \
+        + sum(rng.standard_normal() * F.single_clause(["z"], [k + 1], 1.0, nq) for k in range(nq))
+    coup = [F.single_clause(["z"], [k + 1], 1.0, nq) for k in range(3)]
+    inds = [(1, 1), (2, 2), (3, 1)]
+    ctx = Q.get_context()
+    Hg, Ho = Q.DenseHamiltonian([A, B], [Hd, Hp]), O.DenseHamiltonian([A, B], [Hd, Hp])
+    bath_g, bath_o = Q.Ohmic(1e-2, 4, 16), O.Ohmic(1e-2, 4, 16)
+    u = rand_rho(rng, nb, n)
+    p = Q.ODEParams(Hg, 2.0)
+    w, v = O.haml_eigs(Ho, 0.45, lvl)
+    res = {}
+    try:
+        for on in (True, False):
+            ctx.set_real_operand_mode(on)
+            op = Q.DiffEqLiouvillian(Hg, [Q.OneSidedAMELiouvillian(Q.ConstantCouplings(coup, unit="h"), bath_g, Q.ZERO_LAMBSHIFT, inds)], [], lvl)
+            res[on] = op.rhs_with_eig(np.zeros_like(u), u, p, 0.9, w, v)
+            op.clear_plans()
+    finally:
+        ctx.set_real_operand_mode(True)
+    assert relerr(res[True], res[False]) < 1e-13
+    opo = O.DiffEqLiouvillian(Ho, [O.OneSidedAMELiouvillian([2 * np.pi * c for c in coup], bath_o.spectrum, lambda x: 0.0, inds)], [], lvl)
+    ref = np.stack([opo.rhs_with_eig(u[b], O.ODEParams(Ho, 2.0), 0.9, w, v) for b in range(nb)])
+    assert relerr(res[True], ref) < TOL
+    # ame_jump with l = 80 levels of the same real Hamiltonian
+    _ame_jump_case(Q, [Hd, Hp], coup[:2], 80, 0.6, 3, rng, gamma)
