@@ -17,6 +17,7 @@ struct oqb_dense {
     c128* d_mats = nullptr;  // (nterms + K) n×n : m_1..m_nterms, L_1'L_1..L_K'L_K
     c128* d_lops = nullptr;  // K n×n == the n × (K n) matrix [L_1 | … | L_K]
     c128* d_ldiag = nullptr; // K × n diagonals when EVERY L_k is diagonal (dephasing Z_k, …), else nullptr
+    bool terms_real = false;  // every Hamiltonian term matrix has zero imaginary part: H(s)ρ and ρH(s) take the real-operand product
 };
 
 namespace {
@@ -71,8 +72,10 @@ int sandwich(oqb_dense* op, int cnt, const double* d_gamma, int gamma_mod, const
 // Diagonal Lindblad operators L_k = diag(d_k): Σ_k γ_bk L_k u L_k' is the Hadamard product of u with
 // G_b[a,c] = Σ_k γ_bk d_k[a] conj(d_k[c]) — one elementwise pass (48 B per element) instead of 2K GEMMs.
 // grid (tiles of 256 elements, members); the K diagonals sit in shared memory.
+// with_anti: also the anticommutator part −½(D_a + D_c)·u[a,c], D_a = Σ_k γ_bk |d_k[a]|² — used when H_eff's diagonal
+// imaginary part is kept out of the GEMM operand so that the operand stays real.
 __global__ void lindblad_diag_sandwich_kernel(int n, int K, const c128* __restrict__ ldiag, const double* __restrict__ gamma,
-                                              int gamma_ld, const c128* __restrict__ u, c128* __restrict__ du) {
+                                              int gamma_ld, const c128* __restrict__ u, c128* __restrict__ du, int with_anti) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     c128* sd = reinterpret_cast<c128*>(smem_raw);  // K × n
     double* sg = reinterpret_cast<double*>(sd + (size_t)K * n);
@@ -92,6 +95,7 @@ __global__ void lindblad_diag_sandwich_kernel(int n, int K, const c128* __restri
             // g · da · conj(dc)
             gr = fma(g, da.x * dc.x + da.y * dc.y, gr);
             gi = fma(g, da.y * dc.x - da.x * dc.y, gi);
+            if (with_anti) gr = fma(-0.5 * g, (da.x * da.x + da.y * da.y) + (dc.x * dc.x + dc.y * dc.y), gr);
         }
         const c128 x = ub[e];
         c128 o = dub[e];
@@ -170,9 +174,12 @@ int dense_rhs_impl(oqb_dense* op, int nb, const double* coefH, int coef_shared, 
     // (the per-member lincomb then reads nterms matrices instead of nterms + K)
     const bool diag_heff = use_diag && with_h;
     const int nlin = diag_heff ? op->nterms : nmat;
+    // real Hamiltonian terms: keep the (imaginary) L'L diagonal out of the operand — it moves into the Hadamard pass —
+    // and run both products with the real-operand kernel; without Lindblad operators the operand is H(s) itself
+    const bool real_h = with_h && op->terms_real && c->real_operand && (diag_heff || K == 0);
     auto assemble = [&](const c128* cf, long long cf_ld, int cnt) -> int {
         OQB_TRY(lincomb(c, nlin, nn, mats, cf, cf_ld, He, cnt, false));
-        if (diag_heff) {
+        if (diag_heff && !real_h) {
             for (int m0 = 0; m0 < cnt; m0 += 65535) {
                 const int mc = cnt - m0 < 65535 ? cnt - m0 : 65535;
                 dim3 grid((unsigned)((n + 255) / 256), mc);
@@ -192,6 +199,7 @@ int dense_rhs_impl(oqb_dense* op, int nb, const double* coefH, int coef_shared, 
         ZgemmParams p;  // du = (−i) He u      [accumulate form: du += G u]
         p.M = p.N = p.K = (int)n; p.batch = cnt;
         p.A = He; p.lda = n; p.strideA = rows == 1 ? 0 : nn;
+        p.real_operand = real_h ? 1 : 0;
         p.B = ub; p.ldb = n; p.strideB = nn;
         p.C = dub; p.ldc = n; p.strideC = nn;
         p.alpha = with_h ? make_double2(0.0, -1.0) : make_double2(1.0, 0.0);
@@ -201,6 +209,7 @@ int dense_rhs_impl(oqb_dense* op, int nb, const double* coefH, int coef_shared, 
         q.M = q.N = q.K = (int)n; q.batch = cnt;
         q.A = ub; q.lda = n; q.strideA = nn;
         q.B = He; q.ldb = n; q.strideB = rows == 1 ? 0 : nn; q.opB = with_h ? OP_C : OP_N;
+        q.real_operand = real_h ? 2 : 0;
         q.C = dub; q.ldc = n; q.strideC = nn;
         q.alpha = with_h ? make_double2(0.0, 1.0) : make_double2(1.0, 0.0);
         q.beta = make_double2(1.0, 0.0);
@@ -217,7 +226,7 @@ int dense_rhs_impl(oqb_dense* op, int nb, const double* coefH, int coef_shared, 
                     dim3 grid(tiles, mc);
                     lindblad_diag_sandwich_kernel<<<grid, 256, sm, c->stream>>>(
                         (int)n, K, op->d_ldiag, dg + (gamma_shared ? 0 : (long long)m0 * K), gamma_shared ? 0 : K,
-                        ub + (long long)m0 * nn, dub + (long long)m0 * nn);
+                        ub + (long long)m0 * nn, dub + (long long)m0 * nn, real_h ? 1 : 0);
                     OQB_LAUNCH_CHECK(c);
                 }
             } else {
@@ -244,6 +253,12 @@ int oqb_dense_create(oqb_ctx* c, int n, int nterms, const void* h_mats, int K, c
     if (e == cudaSuccess) e = cudaMalloc((void**)&op->d_lops, (K + 1) * nn * sizeof(c128));
     if (e != cudaSuccess) { oqb_dense_destroy(op); return set_error(c, OQB_ENOMEM, "oqb_dense_create: %s", cudaGetErrorString(e)); }
     if (nterms) OQB_CUDA(c, cudaMemcpyAsync(op->d_mats, h_mats, nterms * nn * sizeof(c128), cudaMemcpyHostToDevice, c->stream));
+    {
+        const c128* Hm = (const c128*)h_mats;
+        bool re = nterms > 0;
+        for (size_t e = 0; re && e < (size_t)nterms * nn; ++e) re = Hm[e].y == 0.0;
+        op->terms_real = re;
+    }
     if (K) {
         OQB_CUDA(c, cudaMemcpyAsync(op->d_lops, h_lops, K * nn * sizeof(c128), cudaMemcpyHostToDevice, c->stream));
         ZgemmParams p;  // L_k' L_k   (src/opensys/lindblad.jl:99,107)

@@ -493,8 +493,10 @@ int dispatch(Ctx* c, const ZgemmParams& p, bool* used) {
     // 3M product (Ctx::zgemm_3m, default on; oqb_set_zgemm_mode / OQB_ZGEMM_3M=0 select the 4-multiplication kernel):
     // 64x64 CTA of 8 warps (32x16 warp tiles), 8 stages, one CTA per SM.
     // real operand (eigenvectors of a real-symmetric Hamiltonian): half the DMMAs of the 4-multiplication product
-    if (c->real_operand && p.real_operand == 1 && p.M > 64) return launch_tma<TCfg<128, 64, 6, TA, TB, false, 1, 1>>(c, p, used);
-    if (c->real_operand && p.real_operand == 2 && p.M > 64) return launch_tma<TCfg<128, 64, 6, TA, TB, false, 1, 2>>(c, p, used);
+    if (c->real_operand && p.real_operand == 1 && p.M > 64)
+        return big ? launch_tma<TCfg<128, 64, 6, TA, TB, false, 1, 1>>(c, p, used) : launch_tma<TCfg<64, 64, 6, TA, TB, false, 2, 1>>(c, p, used);
+    if (c->real_operand && p.real_operand == 2 && p.M > 64)
+        return big ? launch_tma<TCfg<128, 64, 6, TA, TB, false, 1, 2>>(c, p, used) : launch_tma<TCfg<64, 64, 6, TA, TB, false, 2, 2>>(c, p, used);
     if (c->zgemm_3m) return launch_tma<TCfg<64, 64, 8, TA, TB, true, 1>>(c, p, used);
     if (p.M > 64 && big) return launch_tma<TCfg<128, 64, 6, TA, TB>>(c, p, used);
     return launch_tma<TCfg<64, 64, 6, TA, TB>>(c, p, used);

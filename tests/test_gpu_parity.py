@@ -1201,3 +1201,37 @@ def test_onesided_and_jump_real_operand_products(Q):
     assert relerr(res[True], ref) < TOL
     # ame_jump with l = 80 levels of the same real Hamiltonian
     _ame_jump_case(Q, [Hd, Hp], coup[:2], 80, 0.6, 3, rng, gamma)
+
+
+@pytest.mark.gpu
+def test_lindblad_real_hamiltonian_products(Q):
+    """Real Hamiltonian terms + diagonal L_k: H_eff's imaginary diagonal moves into the Hadamard pass (−½(D_a + D_c)ρ_ac)
+    and H(s)ρ, ρH(s) run the real-operand product.  Diagonals with complex phases, per-member s; against the general
+    product (1e-13), the oracle (1e-12), and the commutator-only call."""
+    rng = np.random.default_rng(31337)
+    nq, K, nb = 7, 3, 4
+    n = 2 ** nq
+    Hd = -F.standard_driver(nq)
+    Hp = F.two_local_term(list(rng.standard_normal(nq - 1)), [[i, i + 1] for i in range(1, nq)], nq)
+    Ls = [np.diag(np.exp(1j * rng.uniform(0, 2 * np.pi, n)) * rng.uniform(0.5, 1.5, n)) for _ in range(K)]
+    gfs = [lambda s, k=k: 0.2 * (1 + k) * (1 + s) for k in range(K)]
+    fs = [A, B]
+    ctx = Q.get_context()
+    Hg, Ho = Q.DenseHamiltonian(fs, [Hd, Hp], unit="ħ"), O.DenseHamiltonian(fs, [Hd, Hp], unit="ħ")
+    u = rand_rho(rng, nb, n)
+    t = np.linspace(0.5, 9.0, nb)
+    res = {}
+    try:
+        for on in (True, False):
+            ctx.set_real_operand_mode(on)
+            opg = Q.DiffEqLiouvillian(Hg, [], [Q.LindbladLiouvillian([Q.Lindblad(g, L) for g, L in zip(gfs, Ls)])], n)
+            res[on] = opg(np.zeros_like(u), u, Q.ODEParams(None, 10.0), t)
+            res[("comm", on)] = Hg(np.zeros_like(u), u, None, 0.3)
+    finally:
+        ctx.set_real_operand_mode(True)
+    assert relerr(res[True], res[False]) < 1e-13 and relerr(res[("comm", True)], res[("comm", False)]) < 1e-13
+    opo = O.DiffEqLiouvillian(Ho, [], [O.LindbladLiouvillian([O.Lindblad(g, L) for g, L in zip(gfs, Ls)])], n)
+    for b in range(nb):
+        assert relerr(res[True][b], opo.rhs(u[b], O.ODEParams(None, 10.0), t[b])) < TOL
+    h = Ho(0.3)
+    assert relerr(res[("comm", True)][1], -1j * (h @ u[1] - u[1] @ h)) < TOL
