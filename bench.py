@@ -339,6 +339,9 @@ def main():
     mode = C.c_int()
     ctx.check(lib.oqb_get_zgemm_mode(ctx.h, C.byref(mode)))
     exec_ratio = 0.75 if mode.value == 1 else 1.0  # 3M executes 6·M·N·K of the 8·M·N·K algorithmic flops
+    config["eigenvectors"] = ("exactly real (H(s) of this config is real symmetric): the four rotation products skip the zero "
+                              "imaginary part of V; the same step with the general complex product is in "
+                              "roofline.general_complex_eigenvectors" if real_path else "complex (general product)")
     if real_path:
         exec_ratio = 0.5  # real eigenvectors: 4·M·N·K executed (re += Vr·Br, im += Vr·Bi)
     roofline = {"bound": "tensor",
