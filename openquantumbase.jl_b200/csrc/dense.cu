@@ -17,6 +17,7 @@ struct oqb_dense {
     c128* d_mats = nullptr;  // (nterms + K) n×n : m_1..m_nterms, L_1'L_1..L_K'L_K
     c128* d_lops = nullptr;  // K n×n == the n × (K n) matrix [L_1 | … | L_K]
     c128* d_ldiag = nullptr; // K × n diagonals when EVERY L_k is diagonal (dephasing Z_k, …), else nullptr
+    bool lops_real = false;   // every L_k has zero imaginary part (σx, σ±, σz, …): both sandwich products are real-operand products
     bool terms_real = false;  // every Hamiltonian term matrix has zero imaginary part: H(s)ρ and ρH(s) take the real-operand product
 };
 
@@ -55,6 +56,7 @@ int sandwich(oqb_dense* op, int cnt, const double* d_gamma, int gamma_mod, const
     p.M = p.N = p.K = (int)n;
     p.batch = cnt; p.batch2 = K;
     p.A = op->d_lops; p.lda = n; p.strideA = 0; p.strideA2 = nn;
+    p.real_operand = op->lops_real ? 1 : 0;
     p.B = u; p.ldb = n; p.strideB = nn; p.strideB2 = 0;
     p.C = T; p.ldc = n; p.strideC = K * nn; p.strideC2 = nn;
     p.alpha_scale = d_gamma; p.alpha_scale_mod = gamma_mod;
@@ -64,6 +66,7 @@ int sandwich(oqb_dense* op, int cnt, const double* d_gamma, int gamma_mod, const
     q.batch = cnt;
     q.A = T; q.lda = n; q.strideA = K * nn;
     q.B = op->d_lops; q.ldb = n; q.strideB = 0; q.opB = OP_C;
+    q.real_operand = op->lops_real ? 2 : 0;
     q.C = du; q.ldc = n; q.strideC = nn;
     q.beta = make_double2(1.0, 0.0);
     return zgemm(c, q);
@@ -272,6 +275,11 @@ int oqb_dense_create(oqb_ctx* c, int n, int nterms, const void* h_mats, int K, c
         // every L_k diagonal (dephasing operators stored as dense matrices)? then keep the K diagonals for the
         // Hadamard form of the sandwich term
         const c128* L = (const c128*)h_lops;
+        {
+            bool re = true;
+            for (size_t e = 0; re && e < (size_t)K * nn; ++e) re = L[e].y == 0.0;
+            op->lops_real = re;
+        }
         bool diag = true;
         for (long long k = 0; k < K && diag; ++k)
             for (size_t e = 0; e < nn && diag; ++e)

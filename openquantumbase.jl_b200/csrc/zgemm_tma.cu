@@ -169,7 +169,7 @@ __global__ void __launch_bounds__(CF::NTHREADS, CF::MINB)
     };
     // tiles kept in flight: STAGES-1, or STAGES-2 for the 3M loop (one slot of slack, so that the warp on
     // producer duty does not stall on a slot whose last reader is only a few DMMAs behind)
-    constexpr int AHEAD = CF::M3 ? STAGES - 2 : STAGES - 1;
+    constexpr int AHEAD = (CF::M3 || CF::RM != 0) ? STAGES - 2 : STAGES - 1;
     if (warp == 0 && lane == 0) {
         const int pre = KT < AHEAD ? KT : AHEAD;
         for (int lt = 0; lt < pre; ++lt) produce(lt);
@@ -267,6 +267,62 @@ __global__ void __launch_bounds__(CF::NTHREADS, CF::MINB)
             }
             mma(f1);
             // the DMMAs above consumed every fragment register of stage kt, so its shared-memory reads are complete
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bars + (STAGES + kt % STAGES) * 8);
+        }
+    } else if constexpr (CF::RM != 0) {
+        // real-operand main loop, software-pipelined like the 3M loop: 32 DMMAs per half-stage leave less time to hide
+        // the fragment loads than the 64 of the 4-multiplication product, so the next half-stage's fragments are
+        // fetched while the current one's DMMAs issue.
+        struct Frag { double ar[4], ax[4], br[NJ], bx[NJ]; };  // ax = Ai (RM 2 only), bx = Bi (RM 1 only)
+        auto fetch = [&](Frag& f, int q) {
+            const int kt = q >> 1, h = q & 1;
+            const int s_ = kt % STAGES;
+            if (h == 0) mbar_wait(bars + s_ * 8, (kt / STAGES) & 1);
+            const unsigned st = base + s_ * CF::STAGE_BYTES;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                c128 a = lds128(st + aoff[h] + i * 1024);
+                f.ar[i] = a.x;
+                f.ax[i] = flipt(a.y, sgnA);
+            }
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) {
+                c128 b = lds128(st + boff[h] + j * 1024);
+                f.br[j] = b.x;
+                f.bx[j] = flipt(b.y, sgnB);
+            }
+        };
+        auto mma = [&](const Frag& f) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) {
+                    dmma884t(acc_re[i][j][0], acc_re[i][j][1], f.ar[i], f.br[j]);
+                    if constexpr (CF::RM == 2)
+                        dmma884t(acc_im[i][j][0], acc_im[i][j][1], f.ax[i], f.br[j]);
+                    else
+                        dmma884t(acc_im[i][j][0], acc_im[i][j][1], f.ar[i], f.bx[j]);
+                }
+        };
+        auto duty = [&](int kt) {
+            const int lt = kt + AHEAD;
+            if (lt < KT && warp == lt % CF::NCONS) {
+                if (lane == 0) produce(lt);
+                __syncwarp();
+            }
+        };
+        Frag f0, f1;
+        duty(0);
+        fetch(f0, 0);
+        for (int kt = 0; kt < KT; ++kt) {
+            fetch(f1, 2 * kt + 1);
+            mma(f0);
+            if (kt + 1 < KT) {
+                duty(kt + 1);
+                fetch(f0, 2 * kt + 2);
+            }
+            mma(f1);
             __syncwarp();
             if (lane == 0) mbar_arrive(bars + (STAGES + kt % STAGES) * 8);
         }
@@ -494,9 +550,9 @@ int dispatch(Ctx* c, const ZgemmParams& p, bool* used) {
     // 64x64 CTA of 8 warps (32x16 warp tiles), 8 stages, one CTA per SM.
     // real operand (eigenvectors of a real-symmetric Hamiltonian): half the DMMAs of the 4-multiplication product
     if (c->real_operand && p.real_operand == 1 && p.M > 64)
-        return big ? launch_tma<TCfg<128, 64, 6, TA, TB, false, 1, 1>>(c, p, used) : launch_tma<TCfg<64, 64, 6, TA, TB, false, 2, 1>>(c, p, used);
+        return big ? launch_tma<TCfg<128, 64, 8, TA, TB, false, 1, 1>>(c, p, used) : launch_tma<TCfg<64, 64, 6, TA, TB, false, 2, 1>>(c, p, used);
     if (c->real_operand && p.real_operand == 2 && p.M > 64)
-        return big ? launch_tma<TCfg<128, 64, 6, TA, TB, false, 1, 2>>(c, p, used) : launch_tma<TCfg<64, 64, 6, TA, TB, false, 2, 2>>(c, p, used);
+        return big ? launch_tma<TCfg<128, 64, 8, TA, TB, false, 1, 2>>(c, p, used) : launch_tma<TCfg<64, 64, 6, TA, TB, false, 2, 2>>(c, p, used);
     if (c->zgemm_3m) return launch_tma<TCfg<64, 64, 8, TA, TB, true, 1>>(c, p, used);
     if (p.M > 64 && big) return launch_tma<TCfg<128, 64, 6, TA, TB>>(c, p, used);
     return launch_tma<TCfg<64, 64, 6, TA, TB>>(c, p, used);

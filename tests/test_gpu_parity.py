@@ -1235,3 +1235,34 @@ def test_lindblad_real_hamiltonian_products(Q):
         assert relerr(res[True][b], opo.rhs(u[b], O.ODEParams(None, 10.0), t[b])) < TOL
     h = Ho(0.3)
     assert relerr(res[("comm", True)][1], -1j * (h @ u[1] - u[1] @ h)) < TOL
+
+
+@pytest.mark.gpu
+def test_lindblad_real_jump_operators(Q):
+    """General (non-diagonal) but REAL Lindblad operators (σ∓-type ladders, σx): both sandwich products L_kρ and (L_kρ)L_k'
+    run the real-operand kernel (n = 128 > 64); against the general complex product and the oracle."""
+    rng = np.random.default_rng(777)
+    nq, K, nb = 7, 3, 3
+    n = 2 ** nq
+    Hd = -F.standard_driver(nq)
+    Hp = F.two_local_term(list(rng.standard_normal(nq - 1)), [[i, i + 1] for i in range(1, nq)], nq)
+    sm = np.array([[0, 0], [1, 0]], dtype=complex)
+    Ls = [F.single_clause(["x"], [1], 1.0, nq).astype(complex), np.kron(np.eye(2 ** 3), np.kron(sm, np.eye(2 ** 3))),
+          rng.standard_normal((n, n)).astype(complex) / np.sqrt(n)]
+    gfs = [lambda s, k=k: 0.3 * (1 + k) for k in range(K)]
+    ctx = Q.get_context()
+    Hg, Ho = Q.DenseHamiltonian([A, B], [Hd, Hp], unit="ħ"), O.DenseHamiltonian([A, B], [Hd, Hp], unit="ħ")
+    u = rand_rho(rng, nb, n)
+    t = np.linspace(1.0, 8.0, nb)
+    res = {}
+    try:
+        for on in (True, False):
+            ctx.set_real_operand_mode(on)
+            opg = Q.DiffEqLiouvillian(Hg, [], [Q.LindbladLiouvillian([Q.Lindblad(g, L) for g, L in zip(gfs, Ls)])], n)
+            res[on] = opg(np.zeros_like(u), u, Q.ODEParams(None, 10.0), t)
+    finally:
+        ctx.set_real_operand_mode(True)
+    assert relerr(res[True], res[False]) < 1e-13
+    opo = O.DiffEqLiouvillian(Ho, [], [O.LindbladLiouvillian([O.Lindblad(g, L) for g, L in zip(gfs, Ls)])], n)
+    for b in range(nb):
+        assert relerr(res[True][b], opo.rhs(u[b], O.ODEParams(None, 10.0), t[b])) < TOL
