@@ -477,7 +477,8 @@ int oqb_ame_rhs(oqb_ame* a, int nb, const void* d_u, void* d_du) {
 int oqb_ame_rhs_host(oqb_ame* a, int nb, const void* h_u, void* h_du) {
     oqb_ctx* c = a->ctx;
     const size_t bytes = (size_t)a->n * a->n * sizeof(c128);
-    int chunk = (int)(((size_t)128 << 20) / bytes);
+    static const int chunk_mib = [] { const char* e = getenv("OQB_AME_HOST_CHUNK_MIB"); return e ? atoi(e) : 128; }();
+    int chunk = (int)(((size_t)chunk_mib << 20) / bytes);
     if (chunk < 1) chunk = 1;
     return host_pipeline(c, nb, bytes, bytes, h_u, h_du, chunk, [&](int, int cnt, const void* din, void* dout) {
         return ame_rhs_impl(a, cnt, (const c128*)din, (c128*)dout);

@@ -141,13 +141,15 @@ int host_pipeline(Ctx* c, int nb, size_t in_bytes, size_t out_bytes, const void*
     // first upload and the last download are not hidden behind compute, so they are made small.
     std::vector<int> sizes;
     {
-        const int q = chunk / 4 > 0 ? chunk / 4 : 1, h = chunk / 2 > 0 ? chunk / 2 : 1;
         int left = nb;
         std::vector<int> head, tail;
         if (nb >= 4 * chunk) {
-            head = {q, h};
-            tail = {h, q};
-            left -= 2 * (q + h);
+            // ramp chunk/4, chunk/2 — then the mirror image at the end (measured on C3, e2e evals/s: chunks of 8 ρ with
+            // this ramp 1 775; a finer ramp starting at 1 ρ 1 738; chunks of 4 / 16 / 32 ρ 1 630 / 1 605 / 1 235)
+            const int first = chunk / 4 > 0 ? chunk / 4 : 1;
+            for (int sz = first; sz < chunk; sz *= 2) head.push_back(sz);
+            tail.assign(head.rbegin(), head.rend());
+            for (int sz : head) left -= 2 * sz;
         }
         sizes = head;
         while (left > 0) {
