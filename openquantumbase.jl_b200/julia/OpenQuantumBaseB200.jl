@@ -16,7 +16,7 @@ module OpenQuantumBaseB200
 
 using OpenQuantumBase
 import OpenQuantumBase: update_cache!, DenseHamiltonian, DiffEqLiouvillian, LindbladLiouvillian,
-    DaviesGenerator, GapIndices, haml_eigs
+    DaviesGenerator, GapIndices, haml_eigs, OhmicBath, S, correlation
 using LinearAlgebra
 
 const LIB = get(ENV, "OQB_B200_LIB", "liboqb_b200.so")
@@ -164,5 +164,37 @@ end
 #   ccall((:oqb_ame_jump, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Cvoid}, Ptr{Float64}, Ptr{UInt8}, Ptr{Int32}, Ptr{Float64}, Cint),
 #         ame, B, ψ.ptr, d_uniform, d_mask, d_choice, d_prob, apply)
 # returns the index into `tag` per member; apply = 1 performs ψ ← Lψ/‖Lψ‖ in place.
+
+# ------------------------------------------------------------------ bath functions on the device (row B)
+# S(ω, bath) for an Ohmic bath (bath_util.jl:17 → ext_util.jl:23-28): one device thread per frequency runs QuadGK's
+# adaptive G7K15.  `build_lambshift(ω_range, true, bath, kw)` (bath_util.jl:26-38) becomes
+#     s_list = S(collect(ω_range), bath); construct_interpolations(ω_range, s_list)
+# with the tabulation below in place of the scalar loop.
+function S(ω::AbstractVector{Float64}, bath::OhmicBath; rtol=sqrt(eps()), atol=0.0, max_segments=1024, device=0)
+    c = ctx(device)
+    out = Vector{Float64}(undef, length(ω))
+    check(c, ccall((:oqb_ohmic_lambshift, LIB), Cint,
+                   (Ptr{Cvoid}, Cdouble, Cdouble, Cdouble, Cint, Ptr{Float64}, Cdouble, Cdouble, Cint, Ptr{Float64}, Ptr{Float64},
+                    Ptr{Int32}), c, bath.η, bath.ωc, bath.β, length(ω), ω, rtol, atol, max_segments, out, C_NULL, C_NULL))
+    out
+end
+
+# correlation(τ, bath) on an array of lags (ohmic.jl:48-52) — the cfun of the Redfield / ULE kernels
+function correlation(τ::AbstractVector{Float64}, bath::OhmicBath; device=0)
+    c = ctx(device)
+    out = Vector{ComplexF64}(undef, length(τ))
+    check(c, ccall((:oqb_ohmic_correlation, LIB), Cint, (Ptr{Cvoid}, Cdouble, Cdouble, Cdouble, Cint, Ptr{Float64}, Ptr{ComplexF64}),
+                   c, bath.η, bath.ωc, bath.β, length(τ), τ, out))
+    out
+end
+
+# Tabulated Lamb shift evaluated on the device at the rounded gaps: hand the prefiltered coefficients of the
+# BSpline(Quadratic(Line(OnGrid()))) interpolant (`itp.itp.itp.coefs` of what construct_interpolations returns, n+2
+# numbers) to the handle before oqb_ame_davies_ohmic_begin / oqb_ame_set_onesided_ohmic:
+#   ccall((:oqb_ame_set_lambshift_spline, LIB), Cint, (Ptr{Cvoid}, Cint, Cdouble, Cdouble, Ptr{Float64}),
+#         ame, length(ω_range), first(ω_range), step(ω_range), coefs)
+#
+# Options: ccall((:oqb_set_real_operand_mode, LIB), Cint, (Ptr{Cvoid}, Cint), ctx(), 0) switches the real-eigenvector /
+# real-Hamiltonian products off (general complex product everywhere); oqb_set_zgemm_mode selects 3M / 4M.
 
 end # module

@@ -87,3 +87,65 @@ def test_plain_c_host_program(c_demo_exe):
     out = subprocess.run([c_demo_exe], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "kernels launched" in out.stdout
+
+
+def test_bath_and_option_entry_points_reject_bad_arguments(Q):
+    """Argument checks of the bath routines, the spline table and the handle/option calls added for rows B and (f)-3."""
+    ctx = Q.get_context()
+    lib = ctx.lib
+    dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    w = np.array([0.0, 1.0])
+    S = np.zeros(2)
+    # empty request: no-op
+    assert lib.oqb_ohmic_lambshift(ctx.h, 1e-4, 25.0, 0.5, 0, w.ctypes.data, 1e-8, 0.0, 64, S.ctypes.data, None, None) == 0
+    # null output / non-positive cutoff / one-segment heap
+    assert lib.oqb_ohmic_lambshift(ctx.h, 1e-4, 25.0, 0.5, 2, w.ctypes.data, 1e-8, 0.0, 64, None, None, None) == 1
+    assert b"null" in lib.oqb_last_error(ctx.h)
+    assert lib.oqb_ohmic_lambshift(ctx.h, 1e-4, -1.0, 0.5, 2, w.ctypes.data, 1e-8, 0.0, 64, S.ctypes.data, None, None) == 1
+    assert lib.oqb_ohmic_lambshift(ctx.h, 1e-4, 25.0, 0.5, 2, w.ctypes.data, 1e-8, 0.0, 1, S.ctypes.data, None, None) == 1
+    # a segment cap that is too small for the tolerance still returns (the error estimate says it did not converge)
+    err = np.zeros(2)
+    nseg = np.zeros(2, dtype=np.int32)
+    assert lib.oqb_ohmic_lambshift(ctx.h, 1e-4, 25.0, 0.5, 2, w.ctypes.data, 1e-14, 0.0, 4, S.ctypes.data, err.ctypes.data,
+                                   nseg.ctypes.data) == 0
+    assert np.all(nseg <= 4) and np.all(np.isfinite(S)) and np.all(err > 1e-14 * np.abs(S))
+    Cc = np.zeros(2, dtype=complex)
+    assert lib.oqb_ohmic_correlation(ctx.h, 1e-4, 25.0, 0.5, 2, None, Cc.ctypes.data) == 1
+    assert lib.oqb_ohmic_correlation(ctx.h, 1e-4, 25.0, 0.5, 0, None, None) == 0
+    out = [C.c_double() for _ in range(4)]
+    assert lib.oqb_ohmic_timescales(ctx.h, 1e-4, 25.0, 0.5, float("inf"), 1e-8, 0.0, 256, *[C.byref(x) for x in out]) == 1
+    assert lib.oqb_ohmic_timescales(ctx.h, 1e-4, 25.0, 0.5, 10.0, 1e-8, 0.0, 256, None, None, None, None) == 1
+    coef = np.zeros(5)
+    x = np.zeros(3)
+    assert lib.oqb_bspline_eval(ctx.h, 3, 0.0, -1.0, coef.ctypes.data, 3, x.ctypes.data, x.ctypes.data) == 1
+    assert lib.oqb_bspline_eval(ctx.h, 3, 0.0, 1.0, coef.ctypes.data, 0, None, None) == 0
+    # handle-level calls
+    n = 4
+    m = np.ascontiguousarray(np.eye(n, dtype=complex)[None])
+    a = C.c_void_p()
+    assert lib.oqb_ame_create(ctx.h, n, n, 1, m.ctypes.data, C.byref(a)) == 0
+    assert lib.oqb_ame_rebind(a, None) == 1 and lib.oqb_ame_rebind(None, ctx.h) == 1
+    assert lib.oqb_ame_rebind(a, ctx.h) == 0
+    assert lib.oqb_ame_set_lambshift_spline(a, 3, 0.0, 0.0, coef.ctypes.data) == 1
+    assert lib.oqb_ame_set_lambshift_spline(a, 3, 0.0, 1.0, None) == 1
+    assert lib.oqb_ame_set_lambshift_spline(a, 0, 0.0, 1.0, None) == 0
+    i32 = np.zeros(1, dtype=np.int32)
+    ip = i32.ctypes.data_as(C.POINTER(C.c_int32))
+    assert lib.oqb_ame_set_onesided_ohmic(a, 1, ip, ip, 1e-4, 25.0, 0.5) == 1  # no eigen-system yet
+    assert b"set_eigen" in lib.oqb_last_error(ctx.h)
+    flag = C.c_int(7)
+    assert lib.oqb_ame_eigenvectors_real(a, C.byref(flag)) == 0 and flag.value == 0
+    assert lib.oqb_ame_eigenvectors_real(a, None) == 1
+    wv = np.arange(n, dtype=float)
+    V = np.ascontiguousarray(np.eye(n, dtype=complex))
+    assert lib.oqb_ame_set_eigen(a, dp(wv), V.ctypes.data) == 0
+    assert lib.oqb_ame_eigenvectors_real(a, C.byref(flag)) == 0 and flag.value == 1
+    V[0, 0] = 1j
+    assert lib.oqb_ame_set_eigen(a, dp(wv), V.ctypes.data) == 0
+    assert lib.oqb_ame_eigenvectors_real(a, C.byref(flag)) == 0 and flag.value == 0
+    bad = np.array([5], dtype=np.int32)
+    assert lib.oqb_ame_set_onesided_ohmic(a, 1, bad.ctypes.data_as(C.POINTER(C.c_int32)), ip, 1e-4, 25.0, 0.5) == 1
+    lib.oqb_ame_destroy(a)
+    on = C.c_int()
+    assert lib.oqb_set_real_operand_mode(ctx.h, 0) == 0 and lib.oqb_get_real_operand_mode(ctx.h, C.byref(on)) == 0 and on.value == 0
+    assert lib.oqb_set_real_operand_mode(ctx.h, 1) == 0

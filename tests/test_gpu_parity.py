@@ -1266,3 +1266,38 @@ def test_lindblad_real_jump_operators(Q):
     opo = O.DiffEqLiouvillian(Ho, [], [O.LindbladLiouvillian([O.Lindblad(g, L) for g, L in zip(gfs, Ls)])], n)
     for b in range(nb):
         assert relerr(res[True][b], opo.rhs(u[b], O.ODEParams(None, 10.0), t[b])) < TOL
+
+
+@pytest.mark.gpu
+def test_real_operand_products_ragged_sizes(Q):
+    """Real-operand kernels on sizes that are no multiple of the 128×64 / 64×64 tiles or of the 8-deep k stage
+    (n = 100, lvl = 77): out-of-bounds tile parts come from TMA zero fill and the guarded epilogue."""
+    rng = np.random.default_rng(5150)
+    n, lvl, nb = 100, 77, 3
+    Asym = rng.standard_normal((n, n))
+    H0 = (Asym + Asym.T) / 2
+    Bsym = rng.standard_normal((n, n))
+    H1 = (Bsym + Bsym.T) / 2
+    coup = []
+    for _ in range(2):
+        Cs = rng.standard_normal((n, n))
+        coup.append((Cs + Cs.T) / 2)
+    ctx = Q.get_context()
+    Hg, Ho = Q.DenseHamiltonian([A, B], [H0, H1], unit="ħ"), O.DenseHamiltonian([A, B], [H0, H1], unit="ħ")
+    w, v = O.haml_eigs(Ho, 0.3, lvl)
+    u = rand_rho(rng, nb, n)
+    p = Q.ODEParams(Hg, 1.0)
+    res = {}
+    try:
+        for on in (True, False):
+            ctx.set_real_operand_mode(on)
+            op = Q.DiffEqLiouvillian(Hg, [Q.DaviesGenerator(Q.ConstantCouplings(coup, unit="ħ"), gamma, lamb)], [], lvl)
+            res[on] = op.rhs_with_eig(np.zeros_like(u), u, p, 0.3, w, v)
+            res[("c", on)] = Hg(np.zeros_like(u), u, None, 0.3)
+            op.clear_plans()
+    finally:
+        ctx.set_real_operand_mode(True)
+    assert relerr(res[True], res[False]) < 1e-13 and relerr(res[("c", True)], res[("c", False)]) < 1e-13
+    opo = O.DiffEqLiouvillian(Ho, [O.DaviesGenerator(coup, gamma, lamb)], [], lvl)
+    ref = np.stack([opo.rhs_with_eig(u[b], O.ODEParams(Ho, 1.0), 0.3, w, v) for b in range(nb)])
+    assert relerr(res[True], ref) < TOL
