@@ -891,7 +891,14 @@ class _PlanPrefetcher:
         self.pending.clear()
         if self.H._op is not None:
             self.ctx.lib.oqb_dense_destroy(self.H._op)
+            self.H._op = None
         return left
+
+    def close(self):
+        """Destroys the side context (stream borrowed from torch, workspace owned) once its last handle is gone."""
+        if self.ctx is not None:
+            self.ctx.lib.oqb_destroy(self.ctx.h)
+            self.ctx = None
 
 
 class DiffEqLiouvillian:
@@ -994,6 +1001,7 @@ class DiffEqLiouvillian:
         if pf is not None:
             for plan in pf.shutdown():
                 self.ctx.lib.oqb_ame_destroy(plan["h"])
+            pf.close()  # nothing references the side context any more (adopted plans were rebound, pooled handles too)
         self.ctx.sync()
         for plan in plans.values():
             self.ctx.lib.oqb_ame_destroy(plan["h"])
