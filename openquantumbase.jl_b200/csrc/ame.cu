@@ -26,6 +26,17 @@ __global__ void imag_nonzero_kernel(long long n, const c128* __restrict__ v, uns
     if (__syncthreads_or(nz) && threadIdx.x == 0) atomicAdd(cnt, 1u);
 }
 
+// T[α][i + j·n] = d_α[i] · V[i + j·n]  — c_α·V for diagonal couplings (grid.y = α)
+__global__ void rowscale_kernel(int n, int l, const c128* __restrict__ diag, const c128* __restrict__ V, c128* __restrict__ T) {
+    const long long ln = (long long)n * l;
+    const c128* d = diag + (size_t)blockIdx.y * n;
+    c128* t = T + (long long)blockIdx.y * ln;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < ln; e += (long long)gridDim.x * blockDim.x) {
+        const c128 s = d[e % n], v = V[e];
+        t[e] = make_double2(s.x * v.x - s.y * v.y, s.x * v.y + s.y * v.x);
+    }
+}
+
 // *out = true when no entry of v[0..n) has a non-zero imaginary part (synchronises the stream)
 int detect_real(oqb_ame* a, const c128* v, long long n, bool* out) {
     oqb_ctx* c = a->ctx;
@@ -207,6 +218,26 @@ int oqb_ame_create(oqb_ctx* c, int n, int lvl, int K, const void* h_couplings, o
     if (s) { oqb_ame_destroy(a); return s; }
     if (K) {
         OQB_CUDA(c, cudaMemcpyAsync(a->d_coup, h_couplings, K * nn * sizeof(c128), cudaMemcpyHostToDevice, c->stream));
+        // every coupling diagonal (σz-type system operators stored as dense matrices)?  Then c_α·v is a row scaling and
+        // the rotation v'c_αv of every new eigen-system needs one GEMM per coupling instead of two.
+        const c128* Cm = (const c128*)h_couplings;
+        bool diag = true;
+        for (int k = 0; diag && k < K; ++k)
+            for (size_t col = 0; diag && col < (size_t)n; ++col)
+                for (size_t row = 0; row < (size_t)n; ++row) {
+                    if (row == col) continue;
+                    const c128 x = Cm[(size_t)k * nn + row + col * n];
+                    if (x.x != 0.0 || x.y != 0.0) { diag = false; break; }
+                }
+        std::vector<c128> dg;
+        if (diag) {
+            dg.resize((size_t)K * n);
+            for (int k = 0; k < K; ++k)
+                for (int i = 0; i < n; ++i) dg[(size_t)k * n + i] = Cm[(size_t)k * nn + i + (size_t)i * n];
+            s = ame_alloc(c, (void**)&a->d_cdiag, dg.size() * sizeof(c128));
+            if (s) { oqb_ame_destroy(a); return s; }
+            OQB_CUDA(c, cudaMemcpyAsync(a->d_cdiag, dg.data(), dg.size() * sizeof(c128), cudaMemcpyHostToDevice, c->stream));
+        }
         OQB_CUDA(c, cudaStreamSynchronize(c->stream));
     }
     *out = a;
@@ -250,6 +281,7 @@ int oqb_ame_destroy(oqb_ame* a) {
     oqb_ame_clear_jump(a);
     ame_free(a->ctx, a->d_grp_key);
     ame_free(a->ctx, a->d_flag);
+    ame_free(a->ctx, a->d_cdiag);
     ame_free(a->ctx, a->d_Scoef);
     ame_free(a->ctx, a->d_grp_pair);
     (void)he;
@@ -280,13 +312,20 @@ static int set_eigen_impl(oqb_ame* a, const double* w, const void* v, bool on_de
         if (K) {  // A_α = v' c_α v   (src/opensys/davies.jl:24)
             OQB_TRY(ws_reserve(c, (size_t)K * ln * sizeof(c128)));
             c128* T = (c128*)c->ws;
-            ZgemmParams p;  // T_α = c_α v   (n × l)
-            p.M = n; p.N = l; p.K = n; p.batch = K;
-            p.A = a->d_coup; p.lda = n; p.strideA = nn;
-            p.B = a->d_V; p.ldb = n; p.strideB = 0;
-            p.real_operand = a->v_real ? 2 : 0;
-            p.C = T; p.ldc = n; p.strideC = ln;
-            OQB_TRY(zgemm(c, p));
+            static const bool no_cdiag = [] { const char* e = getenv("OQB_COUPLING_DIAG"); return e && e[0] == '0'; }();
+            if (a->d_cdiag && !no_cdiag) {  // T_α = d_α ∘ v (rows scaled)
+                dim3 grid((unsigned)std::min<long long>((ln + 255) / 256, 592), (unsigned)K);
+                rowscale_kernel<<<grid, 256, 0, c->stream>>>(n, l, a->d_cdiag, a->d_V, T);
+                OQB_LAUNCH_CHECK(c);
+            } else {
+                ZgemmParams p;  // T_α = c_α v   (n × l)
+                p.M = n; p.N = l; p.K = n; p.batch = K;
+                p.A = a->d_coup; p.lda = n; p.strideA = nn;
+                p.B = a->d_V; p.ldb = n; p.strideB = 0;
+                p.real_operand = a->v_real ? 2 : 0;
+                p.C = T; p.ldc = n; p.strideC = ln;
+                OQB_TRY(zgemm(c, p));
+            }
             ZgemmParams q;  // A_α = v' T_α  (l × l)
             q.M = l; q.N = l; q.K = n; q.batch = K;
             q.opA = OP_C;

@@ -12,6 +12,7 @@ struct oqb_ame {
     bool lam_real = false, psum_real = false, ab_real = false;  // same for Λ_p, Σ A_βΛ_p and the A_β stack (one-sided AME)
     unsigned int* d_flag = nullptr;  // counter for the exact-realness checks
     oqb::c128* d_coup = nullptr;  // K n×n couplings as given
+    oqb::c128* d_cdiag = nullptr; // K × n diagonals when EVERY coupling is a diagonal matrix (σz-type), else nullptr
     oqb::c128* d_V = nullptr;     // n × lvl
     double* d_w = nullptr;   // lvl
     oqb::c128* d_A = nullptr;     // K lvl×lvl rotated couplings v' A v
