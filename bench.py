@@ -357,12 +357,11 @@ def main():
                              "1 — frac_executed is the pipe's utilisation; general_complex_eigenvectors holds the same step "
                              "without the real-eigenvector shortcut",
                 "general_complex_eigenvectors": general,
-                "traffic": 2.573e9 if real_path else (2.138e9 if mode.value == 1 else 2.163e9),
+                "traffic": 2.157e9 if real_path else (2.138e9 if mode.value == 1 else 2.163e9),
                 "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one 64-product launch, ncu --set full, "
                                   + ("profiles/r1_zgemm_real_ncu.md " if real_path else
                                      ("profiles/r1_zgemm_3m_ncu.md " if mode.value == 1 else "profiles/r1_zgemm_tma_ncu.md ")) +
-                                  "(algorithmic: 1 GiB read + 1 GiB written + 16 MiB V; the 128x64-tile real-operand launch re-reads part of its "
-                                  "streamed operand: 1.52 GB read)",
+                                  "(algorithmic: 1 GiB read + 1 GiB written + 16 MiB V)",
                 "peak_source": "measured in this run: max(cuBLAS DGEMM 8192^3 best-of-6, DMMA issue probe); MEASURED_PEAKS.json has no FP64 figure",
                 "cublas_dgemm_tflops": dgemm_tf, "cublas_zgemm_4096_tflops": zgemm_tf,
                 "dmma_probe_tflops": dmma_tf, "dfma_probe_tflops": dfma_tf,
