@@ -123,7 +123,9 @@ int oqb_lindblad_acc(oqb_dense* op, int nb, const double* h_gamma, int gamma_sha
                      const void* d_u, void* d_du);
 /* du[b] −= K₂+K₂', K₂ = S_α Λ_α u − Λ_α u S_α summed over α<K  (ACCUMULATES)
  *   — the ρ-dependent half of (R::RedfieldLiouvillian)(du,u,p,t) src/opensys/redfield.jl:65-68.
- *   d_S: K n×n coupling matrices (shared, or nb×K when S_shared==0); d_Lambda: nb×K n×n. */
+ *   d_S: K n×n coupling matrices (shared, or nb×K when bit 0 of S_shared is clear); d_Lambda: nb×K n×n.
+ *   S_shared bit 1 (value 2): the caller asserts that no entry of d_S has an imaginary part (σx, σ±, σz … couplings) —
+ *   the two products with S_α then run as real-operand products (see oqb_set_real_operand_mode). */
 int oqb_redfield_apply_acc(oqb_ctx* ctx, int n, int K, const void* d_S, int S_shared,
                            const void* d_Lambda, int nb, const void* d_u, void* d_du);
 /* The same for DIAGONAL couplings S_α = diag(s_α) (σz-type system–bath couplings stored as dense matrices): K₂ has the

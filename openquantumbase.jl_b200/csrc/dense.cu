@@ -375,6 +375,8 @@ int oqb_redfield_apply_acc(oqb_ctx* c, int n, int K, const void* d_S, int S_shar
     if (nb <= 0 || K <= 0) return 0;
     if (!d_S || !d_Lambda || !d_u || !d_du) return set_error(c, OQB_EINVAL, "oqb_redfield_apply_acc: null argument");
     const long long nn = (long long)n * n;
+    const bool s_real = (S_shared & 2) != 0;  // caller asserts: no coupling entry has an imaginary part
+    S_shared &= 1;
     const size_t per = (size_t)2 * K * nn * sizeof(c128);
     int chunk = (int)(kWorkspaceBudget / per);
     if (chunk < 1) chunk = 1;
@@ -396,12 +398,14 @@ int oqb_redfield_apply_acc(oqb_ctx* c, int n, int K, const void* d_S, int S_shar
         OQB_TRY(zgemm(c, p));
         ZgemmParams q = p;  // Kb[b,α] = S_α M1[b,α]
         q.A = S; q.strideA = S_shared ? 0 : K * nn; q.strideA2 = nn;
+        q.real_operand = s_real ? 1 : 0;
         q.B = M1; q.strideB = K * nn; q.strideB2 = nn;
         q.C = Kb;
         OQB_TRY(zgemm(c, q));
         ZgemmParams r = p;  // Kb[b,α] −= M1[b,α] S_α
         r.A = M1; r.strideA = K * nn; r.strideA2 = nn;
         r.B = S; r.strideB = S_shared ? 0 : K * nn; r.strideB2 = nn;
+        r.real_operand = s_real ? 2 : 0;
         r.C = Kb;
         r.alpha = make_double2(-1.0, 0.0);
         r.beta = make_double2(1.0, 0.0);

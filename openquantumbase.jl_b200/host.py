@@ -1413,7 +1413,8 @@ class RedfieldLiouvillian:
             ctx.check(ctx.lib.oqb_redfield_apply_diag_acc(ctx.h, n, K, Sdiag.ptr, Ld.ptr, B, io.u.ptr, io.du.ptr))
         else:
             Sd = DeviceBatch.from_host(np.stack(Sh), ctx)
-            ctx.check(ctx.lib.oqb_redfield_apply_acc(ctx.h, n, K, Sd.ptr, 1, Ld.ptr, B, io.u.ptr, io.du.ptr))
+            s_real = 2 if not any(np.any(np.imag(x)) for x in Sh) else 0  # real couplings: real-operand products
+            ctx.check(ctx.lib.oqb_redfield_apply_acc(ctx.h, n, K, Sd.ptr, 1 | s_real, Ld.ptr, B, io.u.ptr, io.du.ptr))
         ctx.sync()
         return io.finish()
 

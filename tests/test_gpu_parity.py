@@ -1301,3 +1301,36 @@ def test_real_operand_products_ragged_sizes(Q):
     opo = O.DiffEqLiouvillian(Ho, [O.DaviesGenerator(coup, gamma, lamb)], [], lvl)
     ref = np.stack([opo.rhs_with_eig(u[b], O.ODEParams(Ho, 1.0), 0.3, w, v) for b in range(nb)])
     assert relerr(res[True], ref) < TOL
+
+
+@pytest.mark.gpu
+def test_redfield_apply_real_dense_couplings(Q):
+    """General Redfield apply (redfield.jl:65-68) with REAL dense couplings (σx-type): the caller's realness flag (bit 1 of
+    S_shared) sends S_α(Λ_αu) and (Λ_αu)S_α through the real-operand product; n = 128 so that the kernel is taken.
+    Against the general product (1e-13) and the oracle (1e-12); complex couplings keep the general path."""
+    rng = np.random.default_rng(4096)
+    n, K, nb = 128, 3, 3
+    S = []
+    for _ in range(K):
+        x = rng.standard_normal((n, n))
+        S.append(((x + x.T) / 2).astype(complex))
+    Lam = rand_c(rng, nb, K, n, n) / n
+    u = rand_c(rng, nb, n, n)
+    du0 = rand_c(rng, nb, n, n)
+    ctx = Q.get_context()
+    rg = Q.RedfieldLiouvillian(None, None, 0, 0, 0)
+    res = {}
+    try:
+        for on in (True, False):
+            ctx.set_real_operand_mode(on)
+            res[on] = rg.apply(du0.copy(), u, S, Lam)
+    finally:
+        ctx.set_real_operand_mode(True)
+    assert relerr(res[True], res[False]) < 1e-13
+    ref = np.stack([O.redfield_apply_acc(du0[b].copy(), u[b], S, list(Lam[b])) for b in range(nb)])
+    assert relerr(res[True], ref) < TOL
+    Sc = [s + 1j * np.diag(rng.standard_normal(n)) @ np.eye(n) * 0 + 0.1j * (s - s.T + np.triu(s, 1) - np.triu(s, 1).T) for s in S]
+    Sc = [s + 0.1j * (np.triu(np.real(s), 1) - np.triu(np.real(s), 1).T) for s in S]  # Hermitian with imaginary parts
+    du_c = rg.apply(du0.copy(), u, Sc, Lam)
+    ref_c = np.stack([O.redfield_apply_acc(du0[b].copy(), u[b], Sc, list(Lam[b])) for b in range(nb)])
+    assert relerr(du_c, ref_c) < TOL
