@@ -355,7 +355,7 @@ def run_c5(Q, torch, steps):
         if diag_path:
             ctx.check(ctx.lib.oqb_redfield_apply_diag_acc(ctx.h, n, K, Sdiag.ptr, Lam.ptr, B, u.ptr, du.ptr))
         else:
-            ctx.check(ctx.lib.oqb_redfield_apply_acc(ctx.h, n, K, Sd.ptr, 1 | 2, Lam.ptr, B, u.ptr, du.ptr)  # bit 1: the Z_α couplings are real)
+            ctx.check(ctx.lib.oqb_redfield_apply_acc(ctx.h, n, K, Sd.ptr, 1 | 2, Lam.ptr, B, u.ptr, du.ptr))  # bit 1: the Z_α couplings are real
     fn()
     ctx.check(ctx.lib.oqb_profile_begin(ctx.h))
     ms = timed(fn, steps, 3, torch)

@@ -65,7 +65,7 @@ def main():
         if diag_path:
             ctx.check(ctx.lib.oqb_redfield_apply_diag_acc(ctx.h, n, K, Sdiag.ptr, Lam.ptr, B, u.ptr, du.ptr))
         else:
-            ctx.check(ctx.lib.oqb_redfield_apply_acc(ctx.h, n, K, Sd.ptr, 1 | 2, Lam.ptr, B, u.ptr, du.ptr)  # bit 1: the Z_α couplings are real)
+            ctx.check(ctx.lib.oqb_redfield_apply_acc(ctx.h, n, K, Sd.ptr, 1 | 2, Lam.ptr, B, u.ptr, du.ptr))  # bit 1: the Z_α couplings are real
 
     def barrier():
         torch.cuda.synchronize()
