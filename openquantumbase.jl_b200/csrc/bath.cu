@@ -298,7 +298,7 @@ int oqb_ohmic_timescales(oqb_ctx* c, double eta, double wc, double beta, double 
     double h[4];
     OQB_CUDA(c, cudaMemcpyAsync(h, d_out, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
     OQB_CUDA(c, cudaStreamSynchronize(c->stream));
-    // τ_SB = 1/res, err/res² (bath_util.jl:55-58);  τ_B = res·τ_SB, err·τ_SB (:72-75)
+    // τ_SB = 1/res, err/res² (bath_util.jl:55-58);  τ_B = res·τ_SB, err·τ_SB (:73-76)
     *tau_sb = 1.0 / h[0];
     if (err_sb) *err_sb = h[2] / (h[0] * h[0]);
     *tau_b = h[1] * *tau_sb;

@@ -660,7 +660,7 @@ def _ohmic_correlation(self, tau, ctx: Optional[Context] = None):
 
 
 def _ohmic_timescales(self, lim, rtol=_SQRT_EPS, atol=0.0, max_segments=4096, ctx: Optional[Context] = None):
-    """(τ_SB, err), (τ_B, err) of src/bath/bath_util.jl:55-83 with the integration limit `lim` of τ_B."""
+    """(τ_SB, err), (τ_B, err) of src/bath/bath_util.jl:55-84 with the integration limit `lim` of τ_B."""
     ctx = ctx or get_context()
     v = [C.c_double() for _ in range(4)]
     ctx.check(ctx.lib.oqb_ohmic_timescales(ctx.h, self.eta, self.wc, self.beta, float(lim), rtol, atol, max_segments,
@@ -669,7 +669,7 @@ def _ohmic_timescales(self, lim, rtol=_SQRT_EPS, atol=0.0, max_segments=4096, ct
 
 
 def _ohmic_coarse_grain(self, lim, rtol=_SQRT_EPS, atol=0.0, ctx: Optional[Context] = None):
-    """coarse_grain_timescale(bath, lim) of src/bath/bath_util.jl:96-105: T_a = √(τ_SB τ_B/5) and its error."""
+    """coarse_grain_timescale(bath, lim) of src/bath/bath_util.jl:97-108: T_a = √(τ_SB τ_B/5) and its error."""
     (tsb, esb), (tb, eb) = self.timescales(lim, rtol, atol, ctx=ctx)
     ta = math.sqrt(tsb * tb / 5)
     return ta, (esb * tb + tsb * eb) / 10 / ta

@@ -120,13 +120,13 @@ def tau_SB(cfun, lim=math.inf, rtol=math.sqrt(np.finfo(float).eps), atol=0.0):
 
 
 def tau_B(cfun, lim, tausb, rtol=math.sqrt(np.finfo(float).eps), atol=0.0):
-    """src/bath/bath_util.jl:72-75: τ_B/τ_SB = ∫₀^lim τ|C(τ)|dτ."""
+    """src/bath/bath_util.jl:73-76: τ_B/τ_SB = ∫₀^lim τ|C(τ)|dτ."""
     res, err = quadgk(lambda x: x * abs(cfun(x)), 0.0, lim, rtol, atol)
     return res * tausb, err * tausb
 
 
 def coarse_grain_timescale(cfun, lim, rtol=math.sqrt(np.finfo(float).eps), atol=0.0):
-    """src/bath/bath_util.jl:85-89: T_a = √(τ_SB τ_B / 5)."""
+    """src/bath/bath_util.jl:86-90: T_a = √(τ_SB τ_B / 5)."""
     tsb, esb = tau_SB(cfun, rtol=rtol, atol=atol)
     tb, eb = tau_B(cfun, lim, tsb, rtol=rtol, atol=atol)
     return math.sqrt(tsb * tb / 5), (esb * tb + tsb * eb) / 10 / math.sqrt(tsb * tb / 5)
