@@ -156,6 +156,11 @@ def main():
     config = {"workload": "C3: 10-qubit (1024x1024) DaviesGenerator/AME RHS, Ohmic bath, 64 rho per GPU, K=10 Z_k couplings, s=0.5, lvl=1024",
               "batch_per_gpu": BATCH, "n": N, "inputs_exceed_l2": True,
               "l2_note": "u and du are 1 GiB each per GPU (> 126 MB L2); no flush needed"}
+    try:  # the metric key is a slug of BASELINE.json's wording; carry the wording itself too
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "BASELINE.json")) as f:
+            config["baseline_metric"] = json.load(f)["metric"]
+    except Exception:
+        pass
 
     if args.impl == "reference":
         if rank != 0:
