@@ -643,41 +643,33 @@ class OhmicBath:
         res = float(out[0]) if np.ndim(w) == 0 else out.reshape(np.shape(w))
         return (res, err, nseg) if info else res
 
+    def correlation(self, tau, ctx: Optional[Context] = None):
+        """correlation(τ, bath) of src/bath/ohmic.jl:48-52 for a scalar or an array of lags (device evaluation of the
+        complex trigamma; arrays of quadrature nodes from the Λ builder go through in one launch)."""
+        ctx = ctx or get_context()
+        tv = np.ascontiguousarray(np.atleast_1d(np.asarray(tau, dtype=np.float64)).ravel())
+        out = np.empty(tv.size, dtype=C128)
+        ctx.check(ctx.lib.oqb_ohmic_correlation(ctx.h, self.eta, self.wc, self.beta, tv.size, tv.ctypes.data, out.ctypes.data))
+        return complex(out[0]) if np.ndim(tau) == 0 else out.reshape(np.shape(tau))
+
+    def timescales(self, lim, rtol=_SQRT_EPS, atol=0.0, max_segments=4096, ctx: Optional[Context] = None):
+        """(τ_SB, err), (τ_B, err) of src/bath/bath_util.jl:55-84 with the integration limit `lim` of τ_B."""
+        ctx = ctx or get_context()
+        v = [C.c_double() for _ in range(4)]
+        ctx.check(ctx.lib.oqb_ohmic_timescales(ctx.h, self.eta, self.wc, self.beta, float(lim), rtol, atol, max_segments,
+                                               *[C.byref(x) for x in v]))
+        return (v[0].value, v[1].value), (v[2].value, v[3].value)
+
+    def coarse_grain_timescale(self, lim, rtol=_SQRT_EPS, atol=0.0, ctx: Optional[Context] = None):
+        """coarse_grain_timescale(bath, lim) of src/bath/bath_util.jl:97-108: T_a = √(τ_SB τ_B/5) and its error."""
+        (tsb, esb), (tb, eb) = self.timescales(lim, rtol, atol, ctx=ctx)
+        ta = math.sqrt(tsb * tb / 5)
+        return ta, (esb * tb + tsb * eb) / 10 / ta
+
 
 def Ohmic(eta, fc, T) -> OhmicBath:
     """src/bath/ohmic.jl:24-28 with temperature_2_β of src/unit_util.jl:13-15."""
     return OhmicBath(eta, 2 * math.pi * fc, 5 * 6.62607004 / 1.38064852 / math.pi / T)
-
-
-def _ohmic_correlation(self, tau, ctx: Optional[Context] = None):
-    """correlation(τ, bath) of src/bath/ohmic.jl:48-52 for a scalar or an array of lags (device evaluation of the
-    complex trigamma; arrays of quadrature nodes from the Λ builder go through in one launch)."""
-    ctx = ctx or get_context()
-    tv = np.ascontiguousarray(np.atleast_1d(np.asarray(tau, dtype=np.float64)).ravel())
-    out = np.empty(tv.size, dtype=C128)
-    ctx.check(ctx.lib.oqb_ohmic_correlation(ctx.h, self.eta, self.wc, self.beta, tv.size, tv.ctypes.data, out.ctypes.data))
-    return complex(out[0]) if np.ndim(tau) == 0 else out.reshape(np.shape(tau))
-
-
-def _ohmic_timescales(self, lim, rtol=_SQRT_EPS, atol=0.0, max_segments=4096, ctx: Optional[Context] = None):
-    """(τ_SB, err), (τ_B, err) of src/bath/bath_util.jl:55-84 with the integration limit `lim` of τ_B."""
-    ctx = ctx or get_context()
-    v = [C.c_double() for _ in range(4)]
-    ctx.check(ctx.lib.oqb_ohmic_timescales(ctx.h, self.eta, self.wc, self.beta, float(lim), rtol, atol, max_segments,
-                                           *[C.byref(x) for x in v]))
-    return (v[0].value, v[1].value), (v[2].value, v[3].value)
-
-
-def _ohmic_coarse_grain(self, lim, rtol=_SQRT_EPS, atol=0.0, ctx: Optional[Context] = None):
-    """coarse_grain_timescale(bath, lim) of src/bath/bath_util.jl:97-108: T_a = √(τ_SB τ_B/5) and its error."""
-    (tsb, esb), (tb, eb) = self.timescales(lim, rtol, atol, ctx=ctx)
-    ta = math.sqrt(tsb * tb / 5)
-    return ta, (esb * tb + tsb * eb) / 10 / ta
-
-
-OhmicBath.correlation = _ohmic_correlation
-OhmicBath.timescales = _ohmic_timescales
-OhmicBath.coarse_grain_timescale = _ohmic_coarse_grain
 
 
 class _Zero:
