@@ -20,9 +20,10 @@
  *    on the host (the *_host entry points synchronise themselves).
  *  - A context is not thread-safe; use one per (host thread, GPU) — the reference's functors are
  *    not re-entrant either (src/hamiltonian/dense_hamiltonian.jl:61 mutates an internal cache).
- *  - Process model: ONE GPU per process (one rank per GPU under torchrun / MPI / Distributed.jl).  The library
- *    configures its kernels (shared-memory limits) once per process and does not switch devices per call; a
- *    process that wants a second GPU starts a second process.
+ *  - Process model: one context per (host thread, GPU).  A process may hold contexts on several GPUs (one host
+ *    thread per GPU) or run one rank per GPU under torchrun / MPI / Distributed.jl: every entry
+ *    point selects the device of the context it was handed and per-device kernel configuration is tracked per
+ *    device.  The library reads no environment variables; switches are per context (oqb_set_option).
  *  - There is no CPU fallback anywhere in this library.
  */
 #ifndef OQB_H
@@ -55,16 +56,26 @@ int oqb_sync(oqb_ctx* ctx);
 int oqb_set_stream(oqb_ctx* ctx, void* cuda_stream); /* borrow an existing cudaStream_t        */
 int oqb_get_stream(oqb_ctx* ctx, void** cuda_stream);
 int oqb_launch_count(const oqb_ctx* ctx, uint64_t* n); /* kernels launched through this ctx    */
+/* Per-context switches by name (A/B measurements and structure exploitation; defaults in parentheses):
+ *   "zgemm_3m" (1), "real_operand" (1)        — as oqb_set_zgemm_mode / oqb_set_real_operand_mode below
+ *   "zgemm_tma" (1)  0 = cp.async ZGEMM only;  "zgemm_bm" (0) 64/128 force the CTA tile height;  "tma_oneshot" (1)
+ *   "lindblad_diag" (1), "coupling_diag" (1)   — treat diagonal L_k / couplings as general dense matrices when 0
+ *   "traj_kernel" (0)  0 = pick by operator structure, 1 = generic kernels only, 2 = no XOR specialisation
+ *   "traj_ell" (1)     width-specialised ELL kernel for unstructured sparse operators;  "rk_fuse" (1), "xor_fixed" (1), "xor_rows" (16)
+ *   "ame_host_chunk_mib" (128)                  — chunk size of oqb_ame_rhs_host's H2D/D2H pipeline
+ *   "davies_dense_min_pairs" (0 = cost model)   — gap groups with at least this many level pairs use the dense per-group
+ *                                                  products instead of the cross-term list;  "davies_max_cross" (5e7) caps the list. */
+int oqb_set_option(oqb_ctx* ctx, const char* name, int64_t value);
+int oqb_get_option(const oqb_ctx* ctx, const char* name, int64_t* value);
 /* Complex product used by the tensor-pipe ZGEMM behind every dense path: 1 (default) = 3-multiplication
  * form (3 real DMMA products per complex product, ≈1.2× faster, same ≈1e-15 normwise error), 0 = the classic
- * 4-multiplication form whose rounding matches BLAS zgemm element by element (src/opensys/lindblad.jl:99).
- * Also settable at context creation through the environment variable OQB_ZGEMM_3M=0/1. */
+ * 4-multiplication form whose rounding matches BLAS zgemm element by element (src/opensys/lindblad.jl:99). */
 int oqb_set_zgemm_mode(oqb_ctx* ctx, int mode);
 int oqb_get_zgemm_mode(const oqb_ctx* ctx, int* mode);
 /* Real eigenvectors: when the eigenvector matrix handed to oqb_ame_set_eigen(_device) has no imaginary part (H(s) real
  * symmetric — every X/Z/ZZ annealing Hamiltonian), the rotations v'ρv and vXv' need 2 real products per complex product
  * instead of 3 (the other factor's imaginary part times zero is skipped).  1 (default) = detect and exploit, 0 = always
- * run the general complex product.  Results agree to rounding.  Environment: OQB_REAL_OPERAND=0/1. */
+ * run the general complex product.  Results agree to rounding. */
 int oqb_set_real_operand_mode(oqb_ctx* ctx, int on);
 int oqb_get_real_operand_mode(const oqb_ctx* ctx, int* on);
 
@@ -213,6 +224,36 @@ int oqb_ame_davies_fetch_groups(oqb_ame* ame, int32_t* h_multi_pair, double* h_m
 int oqb_ame_davies_ohmic_finish(oqb_ame* ame, int64_t ncross, const int32_t* h_cross_idx, const double* h_cross_rate,
                                 int64_t nlamb, const int32_t* h_lamb_idx, const double* h_lamb_rate_S);
 int oqb_ame_clear_davies(oqb_ame* ame);
+
+/* ---- GapIndices and the Davies term list, built inside the library ------------------------------------------------
+ * GapIndices(w, digits, sigdigits) of the current eigen-system (src/opensys/opensys_util.jl:25-61), on the device:
+ * |w_j − w_i| ≤ 10^-digits → zero group, else round(gap, sigdigits) (Julia's rule), grouped by exact equality.
+ * *n_keys = number of distinct non-zero keys (= length(uniq_w)), *n_zero_pairs = level pairs i<j of the zero group.
+ * Invalidates Davies tables built for another grouping. */
+int oqb_ame_gaps_build(oqb_ame* ame, int digits, int sigdigits, int64_t* n_keys, int64_t* n_zero_pairs);
+/* h_keys[n_keys] = uniq_w, ascending — the arguments the reference's loop hands to γ(w), γ(−w), S(w), S(−w)
+ * (src/opensys/davies.jl:26-28): the host language evaluates its closures at these and passes the values back. */
+int oqb_ame_gaps_keys(oqb_ame* ame, double* h_keys);
+/* The index lists in the reference's own form, 1-based: group g owns h_a/h_b[h_group_ptr[g] .. h_group_ptr[g+1]) (= uniq_a[g],
+ * uniq_b[g] in the (i<j) loop order); h_a0/h_b0 (2·n_zero_pairs + lvl entries) = a0, b0 (:34-37, :58-59).  Any pointer may be
+ * NULL.  For callers that want the GapIndices object itself; the RHS does not need it. */
+int oqb_ame_gaps_fetch(oqb_ame* ame, int64_t* h_group_ptr, int32_t* h_a, int32_t* h_b, int32_t* h_a0, int32_t* h_b0);
+/* Adds one DaviesGenerator (src/opensys/davies.jl:21-47) over the couplings [k0, k0+nk) of the handle:
+ * h_gamma_plus[g] = γ(uniq_w[g]), h_gamma_minus[g] = γ(−uniq_w[g]), likewise S (NULL ⇒ S ≡ 0), gamma0 = γ(0), S0 = S(0).
+ * Calls accumulate: one per generator of `opensys_eig` (src/opensys/diffeq_liouvillian.jl:101-103; davies_from_interactions
+ * builds one per interaction, src/coupling/interaction.jl:101-117).  Single-pair groups go into the closed-form
+ * tables, small groups onto the cross-term list, large groups (degenerate spectra) are applied as dense products
+ * L_x ρ̃ L_x' with L_x = A∘[ω̃ == x], group by group like the reference's loop. */
+int oqb_ame_add_davies(oqb_ame* ame, int k0, int nk, const double* h_gamma_plus, const double* h_gamma_minus,
+                       const double* h_S_plus, const double* h_S_minus, double gamma0, double S0);
+/* The same with γ of an Ohmic bath (src/bath/ohmic.jl:35-41) and S from a quadratic B-spline table (nS = 0 ⇒ S ≡ 0;
+ * arguments as oqb_ame_set_lambshift_spline) evaluated at the keys on the device. */
+int oqb_ame_add_davies_ohmic(oqb_ame* ame, int k0, int nk, double eta, double wc, double beta, int nS, double S_x0,
+                             double S_dx, const double* h_S_coef);
+/* What the gap structure turned into: generators added, cross-term and L'L list entries, gap groups on the dense path,
+ * dense blocks kept (blocks whose masked coupling vanishes to rounding are dropped).  Any pointer may be NULL. */
+int oqb_ame_davies_stats(const oqb_ame* ame, int64_t* n_terms, int64_t* n_cross, int64_t* n_lamb, int64_t* n_dense_groups,
+                         int64_t* n_dense_blocks);
 /* General closed-form tables, for generators whose rates are not |A_ab|²γ — CorrelatedDaviesGenerator
  * (src/opensys/davies.jl:231-296: du += Σ_(α,β) γ_αβ(ω)(L^β ρ L^α' − ½{L^α'L^β, ρ}) − i[H_LS, ρ]) with a
  * non-degenerate gap structure: the eigenbasis terms become  X = Cm∘ρ̃ + diag(Wᵀ-sum),  X_aa += Σ_b W[a,b]ρ̃_bb, with

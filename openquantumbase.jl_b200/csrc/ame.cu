@@ -37,8 +37,10 @@ __global__ void rowscale_kernel(int n, int l, const c128* __restrict__ diag, con
     }
 }
 
+}  // namespace
+
 // *out = true when no entry of v[0..n) has a non-zero imaginary part (synchronises the stream)
-int detect_real(oqb_ame* a, const c128* v, long long n, bool* out) {
+int ame_detect_real(oqb_ame* a, const c128* v, long long n, bool* out) {
     oqb_ctx* c = a->ctx;
     *out = false;
     if (!a->d_flag) OQB_TRY(ame_alloc(c, (void**)&a->d_flag, 256));
@@ -52,7 +54,13 @@ int detect_real(oqb_ame* a, const c128* v, long long n, bool* out) {
     return 0;
 }
 
-bool needs_general_path(const oqb_ame* a) { return a->ncross > 0 || a->d_Moff || a->npairs > 0; }
+namespace {
+
+int detect_real(oqb_ame* a, const c128* v, long long n, bool* out) { return ame_detect_real(a, v, n, out); }
+
+bool needs_general_path(const oqb_ame* a) { return a->ncross > 0 || a->d_Moff || a->npairs > 0 || a->nd > 0; }
+
+const int kDenseSlab = 16;  // dense per-group blocks processed per pair of products (scratch: slab·l² per member)
 
 // Eigenbasis terms on ρ̃ = R (lvl×lvl per member).  overwrite: X = …, else X += ….
 // with_h: include −i[diag w, ρ̃].  scratch: nb·l + (npairs > 0 ? (npairs + 1)·nb·l² : 0) complex.
@@ -63,12 +71,14 @@ int eig_apply(oqb_ame* a, int nb, const c128* R, c128* X, bool overwrite, bool w
     OQB_TRY(hadamard(c, l, a->d_Cm, with_h ? nullptr : a->d_w, R, X, nb, !overwrite));
     c128* pop = scratch;
     c128* M1 = scratch + (size_t)nb * l;
-    c128* Kb = M1 + (size_t)nb * ll * (a->npairs > 0 ? a->npairs : 1);
+    c128* Kb = M1 + (size_t)nb * ll * (a->npairs > 0 ? a->npairs : 0);
+    c128* Md = Kb + (a->npairs > 0 ? (size_t)nb * ll : 0);  // dense per-group scratch: nb × slab l×l blocks
     if (a->davies) {
         OQB_TRY(extract_diag(c, l, R, pop, nb));
         OQB_TRY(davies_diag(c, l, a->d_Wt, pop, X, nb));
         if (a->d_Wt_im) OQB_TRY(davies_diag(c, l, a->d_Wt_im, pop, X, nb, true));
-        OQB_TRY(davies_cross(c, l, a->K, a->d_A, a->ncross, a->d_cross_idx, a->d_cross_rate, R, X, nb));
+        for (const DaviesTerm& t : a->terms)  // every DaviesGenerator of opensys_eig: its couplings, its γ
+            OQB_TRY(davies_cross(c, l, t.nk, a->d_A + (long long)t.k0 * ll, a->ncross, a->d_cross_idx, t.d_rate, R, X, nb));
         if (a->d_Moff) {
             ZgemmParams p;  // X += Moff R
             p.M = p.N = p.K = l; p.batch = nb;
@@ -81,6 +91,28 @@ int eig_apply(oqb_ame* a, int nb, const c128* R, c128* X, bool overwrite, bool w
             q.M = q.N = q.K = l; q.batch = nb;
             q.A = R; q.lda = l; q.strideA = ll;
             q.B = a->d_Moff; q.ldb = l; q.strideB = 0; q.opB = OP_C;
+            q.C = X; q.ldc = l; q.strideC = ll;
+            q.beta = make_double2(1.0, 0.0);
+            OQB_TRY(zgemm(c, q));
+        }
+        // Large gap groups (degenerate spectra: the start of every anneal) as dense products, group by group like the
+        // reference's loop (src/opensys/davies.jl:26-45):  X += Σ_j γ_j L_j ρ̃ L_j',  L_j = A_k∘[ω̃ == x] — the blocks of a slab
+        // side by side, so the sum over j rides the second product's k loop.
+        for (int j0 = 0; j0 < a->nd; j0 += kDenseSlab) {
+            const int jc = a->nd - j0 < kDenseSlab ? a->nd - j0 : kDenseSlab;
+            ZgemmParams p;  // Md[b, j] = γ_j L_j ρ̃_b
+            p.M = p.N = p.K = l; p.batch = nb; p.batch2 = jc;
+            p.A = a->d_Lstack + (long long)j0 * ll; p.lda = l; p.strideA = 0; p.strideA2 = ll;
+            p.real_operand = a->dense_real ? 1 : 0;
+            p.B = R; p.ldb = l; p.strideB = ll; p.strideB2 = 0;
+            p.C = Md; p.ldc = l; p.strideC = (long long)jc * ll; p.strideC2 = ll;
+            p.alpha_scale = a->d_drate + j0; p.alpha_scale_mod = jc;
+            OQB_TRY(zgemm(c, p));
+            ZgemmParams q;  // X_b += [Md_b1 | … | Md_bJ]·[L_1 | … | L_J]'   (depth J·l)
+            q.M = q.N = l; q.K = jc * l; q.batch = nb;
+            q.A = Md; q.lda = l; q.strideA = (long long)jc * ll;
+            q.B = a->d_Lstack + (long long)j0 * ll; q.ldb = l; q.strideB = 0; q.opB = OP_C;
+            q.real_operand = a->dense_real ? 2 : 0;
             q.C = X; q.ldc = l; q.strideC = ll;
             q.beta = make_double2(1.0, 0.0);
             OQB_TRY(zgemm(c, q));
@@ -121,7 +153,8 @@ int eig_apply(oqb_ame* a, int nb, const c128* R, c128* X, bool overwrite, bool w
 
 size_t eig_scratch_elems(const oqb_ame* a, int nb) {
     const size_t ll = (size_t)a->lvl * a->lvl;
-    return (size_t)nb * a->lvl + (a->npairs > 0 ? ((size_t)a->npairs + 1) * nb * ll : 0);
+    const size_t slab = (size_t)(a->nd < kDenseSlab ? a->nd : kDenseSlab);
+    return (size_t)nb * a->lvl + (a->npairs > 0 ? ((size_t)a->npairs + 1) * nb * ll : 0) + slab * nb * ll;
 }
 
 int ame_rhs_impl(oqb_ame* a, int nb, const c128* u, c128* du) {
@@ -203,6 +236,7 @@ int ame_rhs_impl(oqb_ame* a, int nb, const c128* u, c128* du) {
 extern "C" {
 
 int oqb_ame_create(oqb_ctx* c, int n, int lvl, int K, const void* h_couplings, oqb_ame** out) {
+    OQB_DEVICE(c, c);
     if (!c || !out) return OQB_EINVAL;
     *out = nullptr;
     if (n <= 0 || lvl <= 0 || lvl > n || K < 0 || (K > 0 && !h_couplings))
@@ -245,16 +279,19 @@ int oqb_ame_create(oqb_ctx* c, int n, int lvl, int K, const void* h_couplings, o
 }
 
 int oqb_ame_clear_davies(oqb_ame* a) {
+    OQB_DEVICE(a, a->ctx);
     cudaStreamSynchronize(a->ctx->stream);
     ame_free(a->ctx, a->d_gam); ame_free(a->ctx, a->d_S); ame_free(a->ctx, a->d_Gam); ame_free(a->ctx, a->d_hls); ame_free(a->ctx, a->d_Wt); ame_free(a->ctx, a->d_Wt_im);
-    ame_free(a->ctx, a->d_cross_idx); ame_free(a->ctx, a->d_cross_rate); ame_free(a->ctx, a->d_Moff);
-    a->davies = false; a->ncross = a->nlamb = 0;
+    ame_free(a->ctx, a->d_Moff);
+    ame_clear_terms(a);
+    a->davies = false;
     if (a->have_eigen)  // Hamiltonian-only Hadamard coefficients
         return davies_tables(a->ctx, a->lvl, a->K, a->d_A, nullptr, nullptr, a->d_w, 0, nullptr, nullptr, nullptr, a->d_Cm);
     return 0;
 }
 
 int oqb_ame_rebind(oqb_ame* a, oqb_ctx* ctx) {
+    OQB_DEVICE(a, a->ctx);
     if (!a || !ctx) return OQB_EINVAL;
     if (ctx->device != a->ctx->device) return set_error(ctx, OQB_EINVAL, "oqb_ame_rebind: contexts live on different devices");
     a->ctx = ctx;
@@ -262,6 +299,7 @@ int oqb_ame_rebind(oqb_ame* a, oqb_ctx* ctx) {
 }
 
 int oqb_ame_clear_onesided(oqb_ame* a) {
+    OQB_DEVICE(a, a->ctx);
     cudaStreamSynchronize(a->ctx->stream);
     ame_free(a->ctx, a->d_Lam);
     ame_free(a->ctx, a->d_Psum);
@@ -273,12 +311,14 @@ int oqb_ame_clear_onesided(oqb_ame* a) {
 }
 
 int oqb_ame_destroy(oqb_ame* a) {
+    OQB_DEVICE(a, a->ctx);
     if (!a) return OQB_OK;
     bool he = a->have_eigen;
     a->have_eigen = false;
     oqb_ame_clear_davies(a);
     oqb_ame_clear_onesided(a);
     oqb_ame_clear_jump(a);
+    ame_clear_gaps(a);
     ame_free(a->ctx, a->d_grp_key);
     ame_free(a->ctx, a->d_flag);
     ame_free(a->ctx, a->d_cdiag);
@@ -302,6 +342,7 @@ static int set_eigen_impl(oqb_ame* a, const double* w, const void* v, bool on_de
     OQB_TRY(oqb_ame_clear_davies(a));
     OQB_TRY(oqb_ame_clear_onesided(a));
     OQB_TRY(oqb_ame_clear_jump(a));
+    OQB_TRY(ame_clear_gaps(a));
     OQB_CUDA(c, cudaMemcpyAsync(a->d_w, w, l * sizeof(double), kind, c->stream));
     a->has_v = v != nullptr;
     a->v_real = false;
@@ -312,8 +353,7 @@ static int set_eigen_impl(oqb_ame* a, const double* w, const void* v, bool on_de
         if (K) {  // A_α = v' c_α v   (src/opensys/davies.jl:24)
             OQB_TRY(ws_reserve(c, (size_t)K * ln * sizeof(c128)));
             c128* T = (c128*)c->ws;
-            static const bool no_cdiag = [] { const char* e = getenv("OQB_COUPLING_DIAG"); return e && e[0] == '0'; }();
-            if (a->d_cdiag && !no_cdiag) {  // T_α = d_α ∘ v (rows scaled)
+            if (a->d_cdiag && c->opt.coupling_diag) {  // T_α = d_α ∘ v (rows scaled)
                 dim3 grid((unsigned)std::min<long long>((ln + 255) / 256, 592), (unsigned)K);
                 rowscale_kernel<<<grid, 256, 0, c->stream>>>(n, l, a->d_cdiag, a->d_V, T);
                 OQB_LAUNCH_CHECK(c);
@@ -344,20 +384,24 @@ static int set_eigen_impl(oqb_ame* a, const double* w, const void* v, bool on_de
 }
 
 int oqb_ame_eigenvectors_real(const oqb_ame* a, int* out) {
+    OQB_DEVICE(a, a->ctx);
     if (!a || !out) return OQB_EINVAL;
     *out = (a->have_eigen && a->has_v && a->v_real) ? 1 : 0;
     return 0;
 }
 
 int oqb_ame_set_eigen(oqb_ame* a, const double* h_w, const void* h_v) {
+    OQB_DEVICE(a, a->ctx);
     return set_eigen_impl(a, h_w, h_v, false, "oqb_ame_set_eigen");
 }
 
 int oqb_ame_set_eigen_device(oqb_ame* a, const double* d_w, const void* d_v) {
+    OQB_DEVICE(a, a->ctx);
     return set_eigen_impl(a, d_w, d_v, true, "oqb_ame_set_eigen_device");
 }
 
 int oqb_ame_set_tables(oqb_ame* a, const void* h_Cm, const double* h_Wt_re, const double* h_Wt_im) {
+    OQB_DEVICE(a, a->ctx);
     oqb_ctx* c = a->ctx;
     if (!a->have_eigen) return set_error(c, OQB_EINVAL, "oqb_ame_set_tables: call oqb_ame_set_eigen first");
     if (!h_Cm || !h_Wt_re) return set_error(c, OQB_EINVAL, "oqb_ame_set_tables: null table");
@@ -376,6 +420,7 @@ int oqb_ame_set_tables(oqb_ame* a, const void* h_Cm, const double* h_Wt_re, cons
 }
 
 int oqb_ame_get_rotated_couplings(oqb_ame* a, void* h_A) {
+    OQB_DEVICE(a, a->ctx);
     oqb_ctx* c = a->ctx;
     if (!a->have_eigen) return set_error(c, OQB_EINVAL, "oqb_ame_get_rotated_couplings: call oqb_ame_set_eigen first");
     if (!h_A) return set_error(c, OQB_EINVAL, "oqb_ame_get_rotated_couplings: null output");
@@ -406,10 +451,13 @@ int ame_davies_finish(oqb_ame* a, int64_t ncross, const int32_t* h_cross_idx, co
     const size_t ll = (size_t)l * l;
     OQB_TRY(davies_tables(c, l, a->K, a->d_A, a->d_gam, a->d_S, a->d_w, 1, a->d_Gam, a->d_hls, a->d_Wt, a->d_Cm));
     if (ncross > 0) {
+        DaviesTerm t;  // host-supplied lists: one generator over all K couplings
+        t.k0 = 0; t.nk = a->K;
         OQB_TRY(ame_alloc(c, (void**)&a->d_cross_idx, (size_t)ncross * 4 * sizeof(int32_t)));
-        OQB_TRY(ame_alloc(c, (void**)&a->d_cross_rate, (size_t)ncross * sizeof(double)));
+        OQB_TRY(ame_alloc(c, (void**)&t.d_rate, (size_t)ncross * sizeof(double)));
         OQB_CUDA(c, cudaMemcpyAsync(a->d_cross_idx, h_cross_idx, (size_t)ncross * 4 * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
-        OQB_CUDA(c, cudaMemcpyAsync(a->d_cross_rate, h_cross_rate, (size_t)ncross * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        OQB_CUDA(c, cudaMemcpyAsync(t.d_rate, h_cross_rate, (size_t)ncross * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        a->terms.push_back(t);
         a->ncross = ncross;
     }
     if (nlamb > 0) {
@@ -436,6 +484,7 @@ int ame_davies_finish(oqb_ame* a, int64_t ncross, const int32_t* h_cross_idx, co
 int oqb_ame_set_davies(oqb_ame* a, const double* h_gam, const double* h_S, int64_t ncross, const int32_t* h_cross_idx,
                        const double* h_cross_rate, int64_t nlamb, const int32_t* h_lamb_idx,
                        const double* h_lamb_rate_S) {
+    OQB_DEVICE(a, a->ctx);
     oqb_ctx* c = a->ctx;
     if (!a->have_eigen) return set_error(c, OQB_EINVAL, "oqb_ame_set_davies: call oqb_ame_set_eigen first");
     if (!h_gam || !h_S) return set_error(c, OQB_EINVAL, "oqb_ame_set_davies: null table");
@@ -493,6 +542,7 @@ int ame_onesided_install(oqb_ame* a, int npairs, const int32_t* h_alpha, const i
 
 int oqb_ame_set_onesided(oqb_ame* a, int npairs, const int32_t* h_alpha, const int32_t* h_beta, const double* h_gam,
                          const double* h_S, int tables_shared) {
+    OQB_DEVICE(a, a->ctx);
     oqb_ctx* c = a->ctx;
     if (!a->have_eigen) return set_error(c, OQB_EINVAL, "oqb_ame_set_onesided: call oqb_ame_set_eigen first");
     if (npairs <= 0 || !h_alpha || !h_beta || !h_gam || !h_S) return set_error(c, OQB_EINVAL, "oqb_ame_set_onesided: bad arguments");
@@ -510,13 +560,15 @@ int oqb_ame_set_onesided(oqb_ame* a, int npairs, const int32_t* h_alpha, const i
 }
 
 int oqb_ame_rhs(oqb_ame* a, int nb, const void* d_u, void* d_du) {
+    OQB_DEVICE(a, a->ctx);
     return ame_rhs_impl(a, nb, (const c128*)d_u, (c128*)d_du);
 }
 
 int oqb_ame_rhs_host(oqb_ame* a, int nb, const void* h_u, void* h_du) {
+    OQB_DEVICE(a, a->ctx);
     oqb_ctx* c = a->ctx;
     const size_t bytes = (size_t)a->n * a->n * sizeof(c128);
-    static const int chunk_mib = [] { const char* e = getenv("OQB_AME_HOST_CHUNK_MIB"); return e ? atoi(e) : 128; }();
+    const int chunk_mib = c->opt.ame_host_chunk_mib > 0 ? c->opt.ame_host_chunk_mib : 128;
     int chunk = (int)(((size_t)chunk_mib << 20) / bytes);
     if (chunk < 1) chunk = 1;
     return host_pipeline(c, nb, bytes, bytes, h_u, h_du, chunk, [&](int, int cnt, const void* din, void* dout) {
@@ -525,6 +577,7 @@ int oqb_ame_rhs_host(oqb_ame* a, int nb, const void* h_u, void* h_du) {
 }
 
 int oqb_ame_eig_acc(oqb_ame* a, int nb, const void* d_rho_eig, void* d_du_eig, int with_hamiltonian) {
+    OQB_DEVICE(a, a->ctx);
     oqb_ctx* c = a->ctx;
     if (nb <= 0) return 0;
     if (!a->have_eigen) return set_error(c, OQB_EINVAL, "oqb_ame_eig_acc: call oqb_ame_set_eigen first");
@@ -544,6 +597,7 @@ int oqb_ame_eig_acc(oqb_ame* a, int nb, const void* d_rho_eig, void* d_du_eig, i
 }
 
 int oqb_ame_update_cache(oqb_ame* a, void* d_cache) {
+    OQB_DEVICE(a, a->ctx);
     oqb_ctx* c = a->ctx;
     if (!a->have_eigen) return set_error(c, OQB_EINVAL, "oqb_ame_update_cache: call oqb_ame_set_eigen first");
     if (!d_cache) return set_error(c, OQB_EINVAL, "oqb_ame_update_cache: null cache");

@@ -4,6 +4,13 @@
 
 #include "common.cuh"
 
+// One DaviesGenerator of the term list `opensys_eig` (src/opensys/diffeq_liouvillian.jl:101-103): its coupling slice
+// [k0, k0+nk) of the handle's K couplings and γ at the keys of the shared cross-term list.
+struct DaviesTerm {
+    int k0 = 0, nk = 0;
+    double* d_rate = nullptr;  // ncross rates (owned)
+};
+
 struct oqb_ame {
     oqb_ctx* ctx = nullptr;
     int n = 0, lvl = 0, K = 0;
@@ -22,9 +29,30 @@ struct oqb_ame {
     double *d_gam = nullptr, *d_S = nullptr, *d_Gam = nullptr, *d_hls = nullptr, *d_Wt = nullptr;
     double* d_Wt_im = nullptr;  // imaginary part of the rate matrix (general tables: CorrelatedDaviesGenerator)
     long long ncross = 0, nlamb = 0;
-    int32_t* d_cross_idx = nullptr;
-    double* d_cross_rate = nullptr;
+    int32_t* d_cross_idx = nullptr;  // (a,b,a2,b2) per cross entry — shared by all Davies terms (it depends on the gaps only)
+    std::vector<DaviesTerm> terms;
     oqb::c128* d_Moff = nullptr;  // dense lvl×lvl off-diagonal part of −½G − iH_LS (nullptr when empty)
+    // gap structure of the current eigen-system (ame_terms.cu, GapIndices of src/opensys/opensys_util.jl:25-61)
+    bool have_gaps = false, lists_built = false;
+    int gap_digits = 8, gap_sigdigits = 8;
+    long long ng = 0;              // distinct non-zero gap keys (= GapIndices.uniq_w, ascending)
+    long long nzp = 0;             // level pairs (i<j) of the zero group
+    int32_t* d_gid = nullptr;      // lvl×lvl signed group number: +(g+1) at (i,j), −(g+1) at (j,i), i<j; 0 inside the zero group
+    double* d_ukeys = nullptr;     // ng keys
+    int32_t* d_spair = nullptr;    // the l(l−1)/2 pair numbers sorted by key (stable); the zero-group pairs are the tail
+    std::vector<long long> h_gptr; // ng+1 offsets of the groups in d_spair
+    std::vector<double> h_ukeys;
+    int32_t* d_gslot = nullptr;    // per group: number of its dense slot, −1 when it is on the cross-term list
+    std::vector<long long> h_dense_groups;  // groups that take the dense per-group products
+    bool zero_dense = false;
+    int32_t* d_cross_g = nullptr;  // signed group number per cross entry (0: zero group)
+    int32_t* d_lamb_idx = nullptr; // (a,b,b2) per entry that also contributes to L'L
+    int32_t* d_lamb_g = nullptr;
+    // dense per-group blocks L = A_k∘[ω̃ == x] of all terms (src/opensys/davies.jl:26-45 applied group by group)
+    int nd = 0;
+    oqb::c128* d_Lstack = nullptr;  // nd lvl×lvl blocks side by side (an lvl × nd·lvl matrix)
+    double* d_drate = nullptr;      // γ(x) per block
+    bool dense_real = false;
     // one-sided AME
     int npairs = 0;
     std::vector<int32_t> h_beta;
@@ -64,6 +92,9 @@ inline int ame_alloc(Ctx* c, void** p, size_t bytes) {
 
 // ame.cu internals shared with ame_gaps.cu (defined inside ame.cu's extern "C" block; not part of the public ABI)
 extern "C" int ame_davies_alloc(oqb_ame* a);
+extern "C" int ame_clear_gaps(oqb_ame* a);      // ame_terms.cu
+extern "C" int ame_clear_terms(oqb_ame* a);     // ame_terms.cu: cross lists, dense blocks, per-term rates
+int ame_detect_real(oqb_ame* a, const oqb::c128* v, long long n, bool* out);  // ame.cu
 extern "C" int ame_davies_finish(oqb_ame* a, int64_t ncross, const int32_t* h_cross_idx, const double* h_cross_rate, int64_t nlamb,
                       const int32_t* h_lamb_idx, const double* h_lamb_rate_S);
 

@@ -102,6 +102,7 @@ __global__ void flag_multi_kernel(long long m, const double* __restrict__ keys, 
 extern "C" {
 
 int oqb_ame_set_lambshift_spline(oqb_ame* a, int n, double x0, double dx, const double* h_coef) {
+    OQB_DEVICE(a, a->ctx);
     if (!a) return OQB_EINVAL;
     oqb_ctx* c = a->ctx;
     if (n < 0 || (n > 0 && (!h_coef || !(dx > 0.0)))) return set_error(c, OQB_EINVAL, "oqb_ame_set_lambshift_spline: bad argument");
@@ -120,6 +121,7 @@ int oqb_ame_set_lambshift_spline(oqb_ame* a, int n, double x0, double dx, const 
 
 int oqb_ame_set_onesided_ohmic(oqb_ame* a, int npairs, const int32_t* h_alpha, const int32_t* h_beta, double eta, double wc,
                                double beta) {
+    OQB_DEVICE(a, a->ctx);
     if (!a) return OQB_EINVAL;
     oqb_ctx* c = a->ctx;
     if (!a->have_eigen) return set_error(c, OQB_EINVAL, "oqb_ame_set_onesided_ohmic: call oqb_ame_set_eigen first");
@@ -141,12 +143,13 @@ int oqb_ame_set_onesided_ohmic(oqb_ame* a, int npairs, const int32_t* h_alpha, c
 
 int oqb_ame_davies_ohmic_begin(oqb_ame* a, double eta, double wc, double beta, int digits, int sigdigits, int64_t* n_multi,
                                int64_t* n_zero) {
+    OQB_DEVICE(a, a->ctx);
     if (!a) return OQB_EINVAL;
     oqb_ctx* c = a->ctx;
     if (!a->have_eigen) return set_error(c, OQB_EINVAL, "oqb_ame_davies_ohmic_begin: call oqb_ame_set_eigen first");
     if (!n_multi || !n_zero) return set_error(c, OQB_EINVAL, "oqb_ame_davies_ohmic_begin: null output");
-    static bool table_set = false;
-    if (!table_set) {
+    static DevOnce table_set;
+    if (!table_set.done(c->device)) {
         double p10[31];
         for (int k = 0; k <= 30; ++k) {  // exactly the decimal literals "1e<k>" (correctly rounded), like gaps._POW10_TABLE
             char buf[8];
@@ -154,7 +157,7 @@ int oqb_ame_davies_ohmic_begin(oqb_ame* a, double eta, double wc, double beta, i
             p10[k] = strtod(buf, nullptr);
         }
         OQB_CUDA(c, cudaMemcpyToSymbol(c_pow10, p10, sizeof(p10)));
-        table_set = true;
+        table_set.set(c->device);
     }
     OQB_TRY(ame_davies_alloc(a));
     const int l = a->lvl;
@@ -219,6 +222,7 @@ int oqb_ame_davies_ohmic_begin(oqb_ame* a, double eta, double wc, double beta, i
 }
 
 int oqb_ame_davies_fetch_groups(oqb_ame* a, int32_t* h_multi_pair, double* h_multi_key, int32_t* h_zero_pair) {
+    OQB_DEVICE(a, a->ctx);
     if (!a) return OQB_EINVAL;
     oqb_ctx* c = a->ctx;
     if (a->n_multi > 0) {
@@ -236,6 +240,7 @@ int oqb_ame_davies_fetch_groups(oqb_ame* a, int32_t* h_multi_pair, double* h_mul
 
 int oqb_ame_davies_ohmic_finish(oqb_ame* a, int64_t ncross, const int32_t* h_cross_idx, const double* h_cross_rate, int64_t nlamb,
                                 const int32_t* h_lamb_idx, const double* h_lamb_rate_S) {
+    OQB_DEVICE(a, a->ctx);
     if (!a) return OQB_EINVAL;
     oqb_ctx* c = a->ctx;
     if (!a->d_gam) return set_error(c, OQB_EINVAL, "oqb_ame_davies_ohmic_finish: call oqb_ame_davies_ohmic_begin first");

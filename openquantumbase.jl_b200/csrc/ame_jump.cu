@@ -32,9 +32,9 @@ __device__ __forceinline__ c128 cmul(c128 a, c128 b) { return make_double2(a.x *
 // grid (nb, ceil(nslots/128)): one thread per (member, slot)
 __global__ void ame_jump_prob_kernel(int l, int nslots, const long long* __restrict__ slot_ptr, const int32_t* __restrict__ term,
                                      const double* __restrict__ rate, const c128* __restrict__ A, const c128* __restrict__ Phi,
-                                     const uint8_t* __restrict__ mask, double* __restrict__ prob) {
+                                     const uint8_t* __restrict__ mask, double* __restrict__ prob, int s0) {
     const int b = blockIdx.x;
-    const int s = blockIdx.y * blockDim.x + threadIdx.x;
+    const int s = s0 + blockIdx.y * blockDim.x + threadIdx.x;
     if (s >= nslots || (mask && !mask[b])) return;
     const c128* phi = Phi + (size_t)b * l;
     const long long ll = (long long)l * l;
@@ -115,6 +115,7 @@ __global__ void ame_jump_apply_kernel(int n, const c128* __restrict__ PsiNew, co
 extern "C" {
 
 int oqb_ame_clear_jump(oqb_ame* a) {
+    OQB_DEVICE(a, a->ctx);
     if (!a) return 0;
     cudaStreamSynchronize(a->ctx->stream);
     dfree(a->d_slot_ptr); dfree(a->d_term); dfree(a->d_slot_rate);
@@ -123,6 +124,7 @@ int oqb_ame_clear_jump(oqb_ame* a) {
 }
 
 int oqb_ame_set_jump(oqb_ame* a, int nslots, const int64_t* h_slot_ptr, const int32_t* h_term, const double* h_rate) {
+    OQB_DEVICE(a, a->ctx);
     if (!a) return OQB_EINVAL;
     oqb_ctx* c = a->ctx;
     if (nslots < 1 || !h_slot_ptr || !h_term || !h_rate) return set_error(c, OQB_EINVAL, "oqb_ame_set_jump: bad argument");
@@ -145,6 +147,7 @@ int oqb_ame_set_jump(oqb_ame* a, int nslots, const int64_t* h_slot_ptr, const in
 
 int oqb_ame_jump(oqb_ame* a, int nb, void* d_psi, const double* d_uniform, const uint8_t* d_mask, int32_t* d_choice,
                  double* d_prob, int apply) {
+    OQB_DEVICE(a, a->ctx);
     if (!a) return OQB_EINVAL;
     oqb_ctx* c = a->ctx;
     if (nb <= 0) return 0;
@@ -172,9 +175,12 @@ int oqb_ame_jump(oqb_ame* a, int nb, void* d_psi, const double* d_uniform, const
         OQB_CUDA(c, cudaMemcpyAsync(Phi, Psi, e_phi * sizeof(c128), cudaMemcpyDeviceToDevice, c->stream));
     }
     if (apply) OQB_CUDA(c, cudaMemsetAsync(PhiNew, 0, e_phi * sizeof(c128), c->stream));
-    dim3 grid(nb, (ns + 127) / 128);
-    ame_jump_prob_kernel<<<grid, 128, 0, c->stream>>>(l, ns, a->d_slot_ptr, a->d_term, a->d_slot_rate, a->d_A, Phi, d_mask, prob);
-    OQB_LAUNCH_CHECK(c);
+    for (int s0 = 0; s0 < ns; s0 += 65535 * 128) {  // gridDim.y ≤ 65535
+        const int cnt = ns - s0 < 65535 * 128 ? ns - s0 : 65535 * 128;
+        dim3 grid(nb, (cnt + 127) / 128);
+        ame_jump_prob_kernel<<<grid, 128, 0, c->stream>>>(l, ns, a->d_slot_ptr, a->d_term, a->d_slot_rate, a->d_A, Phi, d_mask, prob, s0);
+        OQB_LAUNCH_CHECK(c);
+    }
     ame_jump_choose_kernel<<<(nb + 63) / 64, 64, 0, c->stream>>>(l, nb, ns, a->d_slot_ptr, a->d_term, a->d_A, Phi, prob, d_uniform,
                                                               d_mask, d_choice, apply ? PhiNew : nullptr);
     OQB_LAUNCH_CHECK(c);

@@ -242,6 +242,7 @@ extern "C" {
 
 int oqb_ohmic_lambshift(oqb_ctx* c, double eta, double wc, double beta, int n, const double* h_w, double rtol, double atol,
                         int max_segments, double* h_S, double* h_err, int32_t* h_nseg) {
+    OQB_DEVICE(c, c);
     if (!c) return OQB_EINVAL;
     if (n <= 0) return 0;
     if (!h_w || !h_S) return set_error(c, OQB_EINVAL, "oqb_ohmic_lambshift: null argument");
@@ -268,6 +269,7 @@ int oqb_ohmic_lambshift(oqb_ctx* c, double eta, double wc, double beta, int n, c
 }
 
 int oqb_ohmic_correlation(oqb_ctx* c, double eta, double wc, double beta, int n, const double* h_tau, void* h_C) {
+    OQB_DEVICE(c, c);
     if (!c) return OQB_EINVAL;
     if (n <= 0) return 0;
     if (!h_tau || !h_C || !(wc > 0.0) || !(beta > 0.0)) return set_error(c, OQB_EINVAL, "oqb_ohmic_correlation: bad argument");
@@ -284,6 +286,7 @@ int oqb_ohmic_correlation(oqb_ctx* c, double eta, double wc, double beta, int n,
 
 int oqb_ohmic_timescales(oqb_ctx* c, double eta, double wc, double beta, double lim, double rtol, double atol, int max_segments,
                          double* tau_sb, double* err_sb, double* tau_b, double* err_b) {
+    OQB_DEVICE(c, c);
     if (!c) return OQB_EINVAL;
     if (!tau_sb || !tau_b || max_segments < 2 || !(wc > 0.0) || !(beta > 0.0) || !(lim > 0.0) || !isfinite(lim) || !(rtol >= 0.0) ||
         !(atol >= 0.0))
@@ -307,6 +310,7 @@ int oqb_ohmic_timescales(oqb_ctx* c, double eta, double wc, double beta, double 
 }
 
 int oqb_bspline_eval(oqb_ctx* c, int n, double x0, double dx, const double* h_coef, int m, const double* h_x, double* h_y) {
+    OQB_DEVICE(c, c);
     if (!c) return OQB_EINVAL;
     if (m <= 0) return 0;
     if (n < 1 || !(dx > 0.0) || !h_coef || !h_x || !h_y) return set_error(c, OQB_EINVAL, "oqb_bspline_eval: bad argument");

@@ -1,6 +1,7 @@
 // Shared declarations for the B200-native OpenQuantumBase RHS library (sm_100a only).
 #pragma once
 #include <cuda_runtime.h>
+#include <atomic>
 #include <cstdint>
 #include <cstdio>
 #include <string>
@@ -12,8 +13,35 @@ typedef double2 c128;  // interleaved (re, im) == Julia ComplexF64 == numpy comp
 
 enum Op : int { OP_N = 0, OP_T = 1, OP_C = 2 };
 
+// Per-context switches (oqb_set_option / oqb_get_option).  The library reads no environment variables.
+struct Options {
+    int zgemm_tma = 1;        // 0: cp.async fallback ZGEMM only
+    int zgemm_bm = 0;         // 0 = by K, 64 / 128 force the CTA tile height of the TMA ZGEMM
+    int tma_oneshot = 1;      // one-instruction 5-D operand tiles
+    int lindblad_diag = 1;    // exploit diagonal L_k
+    int coupling_diag = 1;    // exploit diagonal couplings in the rotation v'c_αv
+    int traj_kernel = 0;      // 0 = pick by operator structure, 1 = generic kernels only, 2 = no XOR specialisation
+    int traj_ell = 1;         // width-specialised ELL trajectory kernel for unstructured sparse operators
+    int rk_fuse = 1;          // RK4 stage arithmetic fused into the trajectory matvec
+    int xor_fixed = 1;        // fully unrolled transverse-field variant of the XOR kernel
+    int xor_rows = 16;        // rows per thread of the XOR kernel at n = 4096
+    int ame_host_chunk_mib = 128;
+    int davies_dense_min_pairs = 0;        // gap groups with at least this many level pairs take the dense per-group path (0 = cost model)
+    long long davies_max_cross = 50000000; // cap on the cross-term list; larger groups go dense first
+};
+
+// "configured once per DEVICE" flag for cudaFuncSetAttribute and constant-memory uploads (several contexts / devices per
+// process; setting an attribute twice is harmless, so the benign race between two contexts of one device is fine).
+struct DevOnce {
+    std::atomic<unsigned char> f[64];
+    DevOnce() { for (auto& x : f) x.store(0); }
+    bool done(int dev) const { return f[dev & 63].load(std::memory_order_acquire) != 0; }
+    void set(int dev) { f[dev & 63].store(1, std::memory_order_release); }
+};
+
 struct Ctx {
     int device = 0;
+    Options opt;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     cudaStream_t copy_stream[2] = {nullptr, nullptr};
@@ -82,6 +110,12 @@ int coef_upload(Ctx* c, const void* host, size_t bytes, void** dptr);  // async 
         if (_e != cudaSuccess)                                                                 \
             return oqb::set_error((c), 2, "kernel launch failed: %s (%s:%d)",                  \
                                   cudaGetErrorString(_e), __FILE__, __LINE__);                 \
+    } while (0)
+
+// Several devices per process: every extern "C" entry point selects the GPU of the context it was handed.
+#define OQB_DEVICE(handle, ctxexpr)                     \
+    do {                                                \
+        if (handle) cudaSetDevice((ctxexpr)->device);   \
     } while (0)
 
 #define OQB_TRY(expr)            \

@@ -113,8 +113,6 @@ int oqb_create(int device, oqb_ctx** out) {
     c->device = device;
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return OQB_ECUDA; }
     c->own_stream = true;
-    if (const char* e = getenv("OQB_ZGEMM_3M")) c->zgemm_3m = atoi(e) != 0;
-    if (const char* e = getenv("OQB_REAL_OPERAND")) c->real_operand = atoi(e) != 0;
     for (int i = 0; i < 2; ++i) cudaStreamCreateWithFlags(&c->copy_stream[i], cudaStreamNonBlocking);
     for (int i = 0; i < 8; ++i) cudaEventCreateWithFlags(&c->ev[i], cudaEventDisableTiming);
     *out = c;
@@ -139,11 +137,13 @@ int oqb_destroy(oqb_ctx* c) {
 const char* oqb_last_error(const oqb_ctx* c) { return c ? c->err.c_str() : "null context"; }
 
 int oqb_sync(oqb_ctx* c) {
+    OQB_DEVICE(c, c);
     OQB_CUDA(c, cudaStreamSynchronize(c->stream));
     return 0;
 }
 
 int oqb_set_stream(oqb_ctx* c, void* s) {
+    OQB_DEVICE(c, c);
     OQB_CUDA(c, cudaStreamSynchronize(c->stream));
     if (c->own_stream) cudaStreamDestroy(c->stream);
     c->stream = (cudaStream_t)s;
@@ -153,43 +153,81 @@ int oqb_set_stream(oqb_ctx* c, void* s) {
 int oqb_get_stream(oqb_ctx* c, void** s) { *s = (void*)c->stream; return 0; }
 int oqb_launch_count(const oqb_ctx* c, uint64_t* n) { *n = c->launches; return 0; }
 int oqb_axpy_batched(oqb_ctx* c, int64_t len, int nb, const double* alpha, const void* d_x, int64_t stride_x, void* d_y) {
+    OQB_DEVICE(c, c);
     if (!alpha || !d_x || !d_y) return set_error(c, OQB_EINVAL, "oqb_axpy_batched: null argument");
     return axpy_batched(c, len, nb, make_double2(alpha[0], alpha[1]), (const c128*)d_x, stride_x, (c128*)d_y);
 }
+namespace {
+struct OptEntry { const char* name; int Options::* field; };
+const OptEntry kOpts[] = {
+    {"zgemm_tma", &Options::zgemm_tma}, {"zgemm_bm", &Options::zgemm_bm}, {"tma_oneshot", &Options::tma_oneshot},
+    {"lindblad_diag", &Options::lindblad_diag}, {"coupling_diag", &Options::coupling_diag}, {"traj_kernel", &Options::traj_kernel},
+    {"traj_ell", &Options::traj_ell}, {"rk_fuse", &Options::rk_fuse}, {"xor_fixed", &Options::xor_fixed}, {"xor_rows", &Options::xor_rows},
+    {"ame_host_chunk_mib", &Options::ame_host_chunk_mib}, {"davies_dense_min_pairs", &Options::davies_dense_min_pairs},
+};
+}  // namespace
+
+int oqb_set_option(oqb_ctx* c, const char* name, int64_t value) {
+    if (!c || !name) return OQB_EINVAL;
+    if (!strcmp(name, "zgemm_3m")) return oqb_set_zgemm_mode(c, (int)value);
+    if (!strcmp(name, "real_operand")) return oqb_set_real_operand_mode(c, (int)value);
+    if (!strcmp(name, "davies_max_cross")) { c->opt.davies_max_cross = value; return 0; }
+    for (const OptEntry& e : kOpts)
+        if (!strcmp(name, e.name)) { c->opt.*(e.field) = (int)value; return 0; }
+    return set_error(c, OQB_EINVAL, "oqb_set_option: unknown option '%s'", name);
+}
+
+int oqb_get_option(const oqb_ctx* c, const char* name, int64_t* value) {
+    if (!c || !name || !value) return OQB_EINVAL;
+    if (!strcmp(name, "zgemm_3m")) { *value = c->zgemm_3m; return 0; }
+    if (!strcmp(name, "real_operand")) { *value = c->real_operand; return 0; }
+    if (!strcmp(name, "davies_max_cross")) { *value = c->opt.davies_max_cross; return 0; }
+    for (const OptEntry& e : kOpts)
+        if (!strcmp(name, e.name)) { *value = c->opt.*(e.field); return 0; }
+    return OQB_EINVAL;
+}
+
 int oqb_set_zgemm_mode(oqb_ctx* c, int mode) {
+    OQB_DEVICE(c, c);
     if (mode != 0 && mode != 1) return set_error(c, OQB_EINVAL, "oqb_set_zgemm_mode: mode must be 0 (4M) or 1 (3M)");
     c->zgemm_3m = mode;
     return 0;
 }
 int oqb_get_zgemm_mode(const oqb_ctx* c, int* mode) { *mode = c->zgemm_3m; return 0; }
 int oqb_set_real_operand_mode(oqb_ctx* c, int on) {
+    OQB_DEVICE(c, c);
     c->real_operand = on != 0;
     return 0;
 }
 int oqb_get_real_operand_mode(const oqb_ctx* c, int* on) { *on = c->real_operand; return 0; }
 
 int oqb_malloc(oqb_ctx* c, size_t nbytes, void** d) {
+    OQB_DEVICE(c, c);
     cudaError_t e = cudaMalloc(d, nbytes ? nbytes : 16);
     if (e != cudaSuccess) return set_error(c, OQB_ENOMEM, "cudaMalloc(%zu) failed: %s", nbytes, cudaGetErrorString(e));
     return 0;
 }
 int oqb_free(oqb_ctx* c, void* d) {
+    OQB_DEVICE(c, c);
     OQB_CUDA(c, cudaStreamSynchronize(c->stream));
     OQB_CUDA(c, cudaFree(d));
     return 0;
 }
 int oqb_malloc_host(oqb_ctx* c, size_t nbytes, void** h) {
+    OQB_DEVICE(c, c);
     cudaError_t e = cudaMallocHost(h, nbytes ? nbytes : 16);
     if (e != cudaSuccess) return set_error(c, OQB_ENOMEM, "cudaMallocHost(%zu) failed: %s", nbytes, cudaGetErrorString(e));
     return 0;
 }
 int oqb_free_host(oqb_ctx* c, void* h) { OQB_CUDA(c, cudaFreeHost(h)); return 0; }
 int oqb_upload(oqb_ctx* c, void* d, const void* h, size_t n) {
+    OQB_DEVICE(c, c);
     OQB_CUDA(c, cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, c->stream));
     OQB_CUDA(c, cudaStreamSynchronize(c->stream));
     return 0;
 }
 int oqb_download(oqb_ctx* c, void* h, const void* d, size_t n) {
+    OQB_DEVICE(c, c);
     OQB_CUDA(c, cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, c->stream));
     OQB_CUDA(c, cudaStreamSynchronize(c->stream));
     return 0;
@@ -198,6 +236,7 @@ int oqb_download(oqb_ctx* c, void* h, const void* d, size_t n) {
 int oqb_zgemm_batched(oqb_ctx* c, int opA, int opB, int M, int N, int K, const double* alpha, const void* dA,
                       int64_t lda, int64_t strideA, const void* dB, int64_t ldb, int64_t strideB,
                       const double* beta, void* dC, int64_t ldc, int64_t strideC, int batch) {
+    OQB_DEVICE(c, c);
     if (opA < 0 || opA > 2 || opB < 0 || opB > 2) return set_error(c, OQB_EINVAL, "zgemm: bad op");
     ZgemmParams p;
     p.M = M; p.N = N; p.K = K; p.batch = batch;
@@ -211,6 +250,7 @@ int oqb_zgemm_batched(oqb_ctx* c, int opA, int opB, int M, int N, int K, const d
 }
 
 int oqb_profile_begin(oqb_ctx* c) {
+    OQB_DEVICE(c, c);
     for (cudaEvent_t e : c->prof_events) cudaEventDestroy(e);
     c->prof_events.clear();
     c->prof_flops = 0.0;
@@ -219,6 +259,7 @@ int oqb_profile_begin(oqb_ctx* c) {
 }
 
 int oqb_profile_end(oqb_ctx* c, double* zgemm_ms, uint64_t* zgemm_launches, double* zgemm_flops) {
+    OQB_DEVICE(c, c);
     c->profiling = false;
     OQB_CUDA(c, cudaStreamSynchronize(c->stream));
     double total = 0.0;

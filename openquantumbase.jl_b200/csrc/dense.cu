@@ -159,7 +159,7 @@ int dense_rhs_impl(oqb_dense* op, int nb, const double* coefH, int coef_shared, 
     void* d_coef = d_stage;
     void* d_gamma = (char*)d_stage + coef_bytes;
 
-    static const bool no_diag = [] { const char* e = getenv("OQB_LINDBLAD_DIAG"); return e && e[0] == '0'; }();
+    const bool no_diag = !c->opt.lindblad_diag;
     const size_t diag_sm = (size_t)K * n * sizeof(c128) + (size_t)K * sizeof(double);
     const bool use_diag = K > 0 && op->d_ldiag && !no_diag && diag_sm <= 160 * 1024;
     const int Kws = use_diag ? 0 : K;  // the Hadamard form of the sandwich needs no L_k u scratch
@@ -221,8 +221,8 @@ int dense_rhs_impl(oqb_dense* op, int nb, const double* coefH, int coef_shared, 
             const double* dg = (const double*)d_gamma + (gamma_shared ? 0 : (long long)b0 * K);
             const size_t sm = diag_sm;
             if (use_diag) {
-                static bool cfg = false;
-                if (!cfg) { OQB_CUDA(c, cudaFuncSetAttribute(lindblad_diag_sandwich_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); cfg = true; }
+                static DevOnce cfg;
+                if (!cfg.done(c->device)) { OQB_CUDA(c, cudaFuncSetAttribute(lindblad_diag_sandwich_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); cfg.set(c->device); }
                 for (int m0 = 0; m0 < cnt; m0 += 65535) {
                     const int mc = cnt - m0 < 65535 ? cnt - m0 : 65535;
                     const int tiles = (int)std::min<long long>((nn + 255) / 256, 64);
@@ -245,6 +245,7 @@ int dense_rhs_impl(oqb_dense* op, int nb, const double* coefH, int coef_shared, 
 extern "C" {
 
 int oqb_dense_create(oqb_ctx* c, int n, int nterms, const void* h_mats, int K, const void* h_lops, oqb_dense** out) {
+    OQB_DEVICE(c, c);
     if (!c || !out) return OQB_EINVAL;
     *out = nullptr;
     if (n <= 0 || nterms < 0 || K < 0 || (nterms > 0 && !h_mats) || (K > 0 && !h_lops))
@@ -299,6 +300,7 @@ int oqb_dense_create(oqb_ctx* c, int n, int nterms, const void* h_mats, int K, c
 }
 
 int oqb_dense_destroy(oqb_dense* op) {
+    OQB_DEVICE(op, op->ctx);
     if (!op) return OQB_OK;
     cudaStreamSynchronize(op->ctx->stream);
     if (op->d_mats) cudaFree(op->d_mats);
@@ -309,6 +311,7 @@ int oqb_dense_destroy(oqb_dense* op) {
 }
 
 int oqb_dense_hamiltonian(oqb_dense* op, int nb, const double* h_coefH, int coef_shared, void* d_out) {
+    OQB_DEVICE(op, op->ctx);
     oqb_ctx* c = op->ctx;
     if (nb <= 0) return 0;
     if (!h_coefH || !d_out) return set_error(c, OQB_EINVAL, "oqb_dense_hamiltonian: null argument");
@@ -323,6 +326,7 @@ int oqb_dense_hamiltonian(oqb_dense* op, int nb, const double* h_coefH, int coef
 
 int oqb_dense_update_cache(oqb_dense* op, int nb, const double* h_coefH, int coef_shared, const double* h_gamma,
                            int gamma_shared, void* d_cache) {
+    OQB_DEVICE(op, op->ctx);
     oqb_ctx* c = op->ctx;
     if (nb <= 0) return 0;
     if (!h_coefH || !d_cache) return set_error(c, OQB_EINVAL, "oqb_dense_update_cache: null argument");
@@ -338,6 +342,7 @@ int oqb_dense_update_cache(oqb_dense* op, int nb, const double* h_coefH, int coe
 }
 
 int oqb_dense_update_vectorized_cache(oqb_dense* op, int nb, const double* h_coefH, int coef_shared, void* d_cache) {
+    OQB_DEVICE(op, op->ctx);
     oqb_ctx* c = op->ctx;
     if (nb <= 0) return 0;
     const long long nn = (long long)op->n * op->n;
@@ -349,15 +354,18 @@ int oqb_dense_update_vectorized_cache(oqb_dense* op, int nb, const double* h_coe
 
 int oqb_dense_rhs(oqb_dense* op, int nb, const double* h_coefH, int coef_shared, const double* h_gamma,
                   int gamma_shared, const void* d_u, void* d_du) {
+    OQB_DEVICE(op, op->ctx);
     return dense_rhs_impl(op, nb, h_coefH, coef_shared, h_gamma, gamma_shared, (const c128*)d_u, (c128*)d_du, true);
 }
 
 int oqb_lindblad_acc(oqb_dense* op, int nb, const double* h_gamma, int gamma_shared, const void* d_u, void* d_du) {
+    OQB_DEVICE(op, op->ctx);
     return dense_rhs_impl(op, nb, nullptr, 1, h_gamma, gamma_shared, (const c128*)d_u, (c128*)d_du, false);
 }
 
 int oqb_dense_rhs_host(oqb_dense* op, int nb, const double* h_coefH, int coef_shared, const double* h_gamma,
                        int gamma_shared, const void* h_u, void* h_du) {
+    OQB_DEVICE(op, op->ctx);
     oqb_ctx* c = op->ctx;
     const size_t bytes = (size_t)op->n * op->n * sizeof(c128);
     int chunk = (int)(((size_t)256 << 20) / bytes);
@@ -372,6 +380,7 @@ int oqb_dense_rhs_host(oqb_dense* op, int nb, const double* h_coefH, int coef_sh
 
 int oqb_redfield_apply_acc(oqb_ctx* c, int n, int K, const void* d_S, int S_shared, const void* d_Lambda, int nb,
                            const void* d_u, void* d_du) {
+    OQB_DEVICE(c, c);
     if (nb <= 0 || K <= 0) return 0;
     if (!d_S || !d_Lambda || !d_u || !d_du) return set_error(c, OQB_EINVAL, "oqb_redfield_apply_acc: null argument");
     const long long nn = (long long)n * n;
@@ -417,6 +426,7 @@ int oqb_redfield_apply_acc(oqb_ctx* c, int n, int K, const void* d_S, int S_shar
 
 int oqb_redfield_apply_diag_acc(oqb_ctx* c, int n, int K, const void* d_Sdiag, const void* d_Lambda, int nb, const void* d_u,
                                 void* d_du) {
+    OQB_DEVICE(c, c);
     if (nb <= 0 || K <= 0) return 0;
     if (!d_Sdiag || !d_Lambda || !d_u || !d_du) return set_error(c, OQB_EINVAL, "oqb_redfield_apply_diag_acc: null argument");
     const long long nn = (long long)n * n;
@@ -442,6 +452,7 @@ int oqb_redfield_apply_diag_acc(oqb_ctx* c, int n, int K, const void* d_Sdiag, c
 
 int oqb_redfield_vectorized_acc(oqb_ctx* c, int n, int K, const void* d_S, int S_shared, const void* d_Lambda,
                                 int nb, void* d_cache) {
+    OQB_DEVICE(c, c);
     if (nb <= 0 || K <= 0) return 0;
     const long long nn = (long long)n * n;
     OQB_TRY(ws_reserve(c, (size_t)nb * nn * sizeof(c128)));
@@ -461,17 +472,20 @@ int oqb_redfield_vectorized_acc(oqb_ctx* c, int n, int K, const void* d_S, int S
 }
 
 int oqb_ensemble_population(oqb_ctx* c, int n, int nb, const void* d_psi, double* d_out) {
+    OQB_DEVICE(c, c);
     if (!d_psi || !d_out) return set_error(c, OQB_EINVAL, "oqb_ensemble_population: null argument");
     return ensemble_population(c, n, nb, (const c128*)d_psi, d_out);
 }
 
 int oqb_expect_diag(oqb_ctx* c, int n, int nobs, const double* d_diag, int nb, const void* d_psi, double* d_out) {
+    OQB_DEVICE(c, c);
     if (!d_diag || !d_psi || !d_out) return set_error(c, OQB_EINVAL, "oqb_expect_diag: null argument");
     return expect_diag(c, n, nobs, d_diag, nb, (const c128*)d_psi, d_out);
 }
 
 int oqb_expect(oqb_ctx* c, int n, int nobs, const void* d_obs, int nb, const void* d_state, int is_vector,
                double* d_out) {
+    OQB_DEVICE(c, c);
     if (!d_obs || !d_state || !d_out) return set_error(c, OQB_EINVAL, "oqb_expect: null argument");
     return expect(c, n, nobs, (const c128*)d_obs, nb, (const c128*)d_state, is_vector, (c128*)d_out);
 }

@@ -105,10 +105,12 @@ __global__ void extract_diag_kernel(int l, const c128* __restrict__ R, c128* __r
     if (a < l) pop[(long long)b * l + a] = R[(long long)b * l * l + a + (long long)a * l];
 }
 int extract_diag(Ctx* c, int l, const c128* R, c128* pop, int nb) {
-    if (nb <= 0) return 0;
-    dim3 grid(cdiv(l, 256), nb);
-    extract_diag_kernel<<<grid, 256, 0, c->stream>>>(l, R, pop);
-    OQB_LAUNCH_CHECK(c);
+    for (int b0 = 0; b0 < nb; b0 += 65535) {  // gridDim.y ≤ 65535
+        const int cnt = nb - b0 < 65535 ? nb - b0 : 65535;
+        dim3 grid(cdiv(l, 256), cnt);
+        extract_diag_kernel<<<grid, 256, 0, c->stream>>>(l, R + (long long)b0 * l * l, pop + (long long)b0 * l);
+        OQB_LAUNCH_CHECK(c);
+    }
     return 0;
 }
 
@@ -147,10 +149,12 @@ __global__ void davies_diag_kernel(int l, const double* __restrict__ Wt, const c
     }
 }
 int davies_diag(Ctx* c, int l, const double* Wt, const c128* pop, c128* X, int nb, bool times_i) {
-    if (nb <= 0) return 0;
-    dim3 grid(cdiv(l, 8), nb);
-    davies_diag_kernel<<<grid, 256, 0, c->stream>>>(l, Wt, pop, X, times_i ? 1 : 0);
-    OQB_LAUNCH_CHECK(c);
+    for (int b0 = 0; b0 < nb; b0 += 65535) {
+        const int cnt = nb - b0 < 65535 ? nb - b0 : 65535;
+        dim3 grid(cdiv(l, 8), cnt);
+        davies_diag_kernel<<<grid, 256, 0, c->stream>>>(l, Wt, pop + (long long)b0 * l, X + (long long)b0 * l * l, times_i ? 1 : 0);
+        OQB_LAUNCH_CHECK(c);
+    }
     return 0;
 }
 
@@ -364,9 +368,12 @@ __global__ void davies_cross_kernel(int l, int K, const c128* __restrict__ A, lo
 int davies_cross(Ctx* c, int l, int K, const c128* A, long long ncross, const int32_t* idx, const double* rate,
                  const c128* R, c128* X, int nb) {
     if (ncross <= 0 || nb <= 0) return 0;
-    dim3 grid(cdiv(ncross, 256), nb);
-    davies_cross_kernel<<<grid, 256, 0, c->stream>>>(l, K, A, ncross, idx, rate, R, X);
-    OQB_LAUNCH_CHECK(c);
+    for (int b0 = 0; b0 < nb; b0 += 65535) {
+        const int cnt = nb - b0 < 65535 ? nb - b0 : 65535;
+        dim3 grid(cdiv(ncross, 256), cnt);
+        davies_cross_kernel<<<grid, 256, 0, c->stream>>>(l, K, A, ncross, idx, rate, R + (long long)b0 * l * l, X + (long long)b0 * l * l);
+        OQB_LAUNCH_CHECK(c);
+    }
     return 0;
 }
 

@@ -47,6 +47,7 @@ __global__ void __launch_bounds__(256) probe_dfma_kernel(double* out, int iters)
 }  // namespace
 
 extern "C" int oqb_probe_fp64(oqb_ctx* c, double* dmma_tflops, double* dfma_tflops) {
+    OQB_DEVICE(c, c);
     int sms = 0;
     OQB_CUDA(c, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
     double* d_out = nullptr;

@@ -221,6 +221,7 @@ size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
 extern "C" {
 
 int oqb_lambda_create(oqb_ctx* c, int n, int K, const void* h_S, oqb_lambda** out) {
+    OQB_DEVICE(c, c);
     if (!c || !out || !h_S || n < 1 || K < 1) return c ? set_error(c, OQB_EINVAL, "oqb_lambda_create: bad argument") : OQB_EINVAL;
     oqb_lambda* L = new oqb_lambda();
     L->c = c; L->n = n; L->K = K;
@@ -245,6 +246,7 @@ int oqb_lambda_create(oqb_ctx* c, int n, int K, const void* h_S, oqb_lambda** ou
 }
 
 int oqb_lambda_destroy(oqb_lambda* L) {
+    OQB_DEVICE(L, L->c);
     if (!L) return 0;
     cudaStreamSynchronize(L->c->stream);
     if (L->dS) cudaFree(L->dS);
@@ -256,6 +258,7 @@ int oqb_lambda_destroy(oqb_lambda* L) {
 }
 
 int oqb_lambda_set_unitary(oqb_lambda* L, int nb, int G, const void* d_Ugrid) {
+    OQB_DEVICE(L, L->c);
     if (!L) return OQB_EINVAL;
     if (nb < 1 || G < 1 || !d_Ugrid) return set_error(L->c, OQB_EINVAL, "oqb_lambda_set_unitary: bad argument");
     L->nb = nb; L->G = G; L->dU = (const c128*)d_Ugrid;
@@ -263,6 +266,7 @@ int oqb_lambda_set_unitary(oqb_lambda* L, int nb, int G, const void* d_Ugrid) {
 }
 
 int oqb_lambda_reserve_slots(oqb_lambda* L, int64_t nslots) {
+    OQB_DEVICE(L, L->c);
     if (!L) return OQB_EINVAL;
     Ctx* c = L->c;
     if (nslots <= L->nslots) return 0;
@@ -287,6 +291,7 @@ int oqb_lambda_reserve_slots(oqb_lambda* L, int64_t nslots) {
 
 int oqb_lambda_eval(oqb_lambda* L, int nseg, const int32_t* h_member, const int32_t* h_coupling, const int32_t* h_gi,
                     const double* h_theta, const double* h_ck, const double* h_cg, const int64_t* h_slot, double* h_E) {
+    OQB_DEVICE(L, L->c);
     if (!L) return OQB_EINVAL;
     Ctx* c = L->c;
     if (nseg <= 0) return 0;
@@ -421,6 +426,7 @@ int oqb_lambda_eval(oqb_lambda* L, int nseg, const int32_t* h_member, const int3
 }
 
 int oqb_lambda_total(oqb_lambda* L, int nint, const int64_t* h_ptr, const int64_t* h_idx, void* d_Lambda, double* h_norm) {
+    OQB_DEVICE(L, L->c);
     if (!L) return OQB_EINVAL;
     Ctx* c = L->c;
     if (nint <= 0) return 0;

@@ -653,8 +653,8 @@ int traj_matvec_impl(oqb_sparse* sp, int nb, const double* coefH, int coef_share
     const int threads = n >= 2048 ? 512 : (n >= 256 ? 256 : 64);
     const int sms = sm_count(c);
     if (smem <= 200 * 1024) {
-        static bool cfg = false;
-        if (!cfg) { OQB_CUDA(c, cudaFuncSetAttribute(traj_matvec_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); cfg = true; }
+        static DevOnce cfg;
+        if (!cfg.done(c->device)) { OQB_CUDA(c, cudaFuncSetAttribute(traj_matvec_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); cfg.set(c->device); }
         int per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (220 * 1024) / (smem + 1024)));
         int grid = std::min(nb, sms * per_sm);
         ProfScope prof(c, 32.0 * n * (double)nb);
@@ -671,12 +671,14 @@ int traj_matvec_impl(oqb_sparse* sp, int nb, const double* coefH, int coef_share
 
 int oqb_traj_matvec_rk(oqb_sparse* sp, int nb, const double* h_coefH, int coef_shared, const double* h_gamma, int gamma_shared,
                        const c128* psi_in, c128* out, const RkEpilogue* rk, int* fused) {
+    OQB_DEVICE(sp, sp->ctx);
     return traj_matvec_impl(sp, nb, h_coefH, coef_shared, h_gamma, gamma_shared, psi_in, out, rk, fused);
 }
 
 // accessors for traj_evolve.cu (the struct layout stays private to this file)
 oqb_ctx* oqb_sparse_ctx(oqb_sparse* sp) { return sp->ctx; }
 int oqb_sparse_dims(oqb_sparse* sp, int* n, int* nterms, int* K) {
+    OQB_DEVICE(sp, sp->ctx);
     *n = sp->n; *nterms = sp->nterms; *K = sp->K;
     return 0;
 }
@@ -684,6 +686,7 @@ int oqb_sparse_dims(oqb_sparse* sp, int* n, int* nterms, int* K) {
 extern "C" {
 
 int oqb_sparse_destroy(oqb_sparse* sp) {
+    OQB_DEVICE(sp, sp->ctx);
     if (!sp) return OQB_OK;
     cudaStreamSynchronize(sp->ctx->stream);
     for (auto& t : sp->h_terms) free_term(t);
@@ -704,6 +707,7 @@ int oqb_sparse_destroy(oqb_sparse* sp) {
 int oqb_sparse_create(oqb_ctx* c, int n, int nterms, const int64_t* h_colptr, const int64_t* h_rowval, const void* h_nzval,
                       const int64_t* h_nnz_off, int K, const int64_t* h_l_colptr, const int64_t* h_l_rowval,
                       const void* h_l_nzval, const int64_t* h_l_nnz_off, oqb_sparse** out) {
+    OQB_DEVICE(c, c);
     if (!c || !out) return OQB_EINVAL;
     *out = nullptr;
     if (n <= 0 || nterms < 0 || K < 0 || nterms + K > kMaxTerms - 1 || (nterms > 0 && (!h_colptr || !h_rowval || !h_nzval || !h_nnz_off)) ||
@@ -815,6 +819,7 @@ int oqb_sparse_create(oqb_ctx* c, int n, int nterms, const int64_t* h_colptr, co
 
 int oqb_sparse_pattern_nnz(oqb_sparse* sp, int64_t* nnz) { *nnz = sp->nnzU; return 0; }
 int oqb_sparse_pattern(oqb_sparse* sp, int64_t* h_colptr, int64_t* h_rowval) {
+    OQB_DEVICE(sp, sp->ctx);
     for (int j = 0; j <= sp->n; ++j) h_colptr[j] = sp->u_colptr[j] + 1;
     for (int64_t p = 0; p < sp->nnzU; ++p) h_rowval[p] = sp->u_row[p] + 1;
     return 0;
@@ -822,6 +827,7 @@ int oqb_sparse_pattern(oqb_sparse* sp, int64_t* h_colptr, int64_t* h_rowval) {
 
 int oqb_sparse_update_cache(oqb_sparse* sp, int nb, const double* h_coefH, int coef_shared, const double* h_gamma,
                             int gamma_shared, void* d_nzval) {
+    OQB_DEVICE(sp, sp->ctx);
     oqb_ctx* c = sp->ctx;
     if (nb <= 0 || sp->nnzU == 0) return 0;
     if (!h_coefH || !d_nzval) return set_error(c, OQB_EINVAL, "oqb_sparse_update_cache: null argument");
@@ -839,6 +845,7 @@ int oqb_sparse_update_cache(oqb_sparse* sp, int nb, const double* h_coefH, int c
 }
 
 int oqb_sparse_update_vectorized_cache(oqb_sparse* sp, int nb, const double* h_coefH, int coef_shared, void* d_cache) {
+    OQB_DEVICE(sp, sp->ctx);
     oqb_ctx* c = sp->ctx;
     if (nb <= 0) return 0;
     if (!h_coefH || !d_cache) return set_error(c, OQB_EINVAL, "oqb_sparse_update_vectorized_cache: null argument");
@@ -864,6 +871,7 @@ int oqb_sparse_update_vectorized_cache(oqb_sparse* sp, int nb, const double* h_c
 }
 
 int oqb_sparse_commutator(oqb_sparse* sp, int nb, const double* h_coefH, int coef_shared, const void* d_u, void* d_du) {
+    OQB_DEVICE(sp, sp->ctx);
     oqb_ctx* c = sp->ctx;
     if (nb <= 0) return 0;
     if (!h_coefH || !d_u || !d_du) return set_error(c, OQB_EINVAL, "oqb_sparse_commutator: null argument");
@@ -889,11 +897,13 @@ int oqb_sparse_commutator(oqb_sparse* sp, int nb, const double* h_coefH, int coe
 
 int oqb_traj_matvec(oqb_sparse* sp, int nb, const double* h_coefH, int coef_shared, const double* h_gamma, int gamma_shared,
                     const void* d_psi, void* d_dpsi) {
+    OQB_DEVICE(sp, sp->ctx);
     return traj_matvec_impl(sp, nb, h_coefH, coef_shared, h_gamma, gamma_shared, (const c128*)d_psi, (c128*)d_dpsi);
 }
 
 int oqb_traj_matvec_host(oqb_sparse* sp, int nb, const double* h_coefH, int coef_shared, const double* h_gamma,
                          int gamma_shared, const void* h_psi, void* h_dpsi) {
+    OQB_DEVICE(sp, sp->ctx);
     oqb_ctx* c = sp->ctx;
     const size_t bytes = (size_t)sp->n * sizeof(c128);
     int chunk = (int)(((size_t)256 << 20) / bytes);
@@ -907,6 +917,7 @@ int oqb_traj_matvec_host(oqb_sparse* sp, int nb, const double* h_coefH, int coef
 }
 
 int oqb_traj_norm2(oqb_sparse* sp, int nb, const void* d_psi, double* d_out) {
+    OQB_DEVICE(sp, sp->ctx);
     oqb_ctx* c = sp->ctx;
     if (nb <= 0) return 0;
     norm2_kernel<<<nb, 256, 0, c->stream>>>(sp->n, (const c128*)d_psi, d_out);
@@ -916,6 +927,7 @@ int oqb_traj_norm2(oqb_sparse* sp, int nb, const void* d_psi, double* d_out) {
 
 int oqb_traj_jump(oqb_sparse* sp, int nb, const double* h_gamma, int gamma_shared, void* d_psi, const double* d_uniform,
                   const uint8_t* d_mask, int32_t* d_choice, double* d_prob, int apply) {
+    OQB_DEVICE(sp, sp->ctx);
     oqb_ctx* c = sp->ctx;
     if (nb <= 0) return 0;
     if (sp->K <= 0) return set_error(c, OQB_EINVAL, "oqb_traj_jump: no Lindblad operators");
@@ -933,7 +945,7 @@ int oqb_traj_jump(oqb_sparse* sp, int nb, const double* h_gamma, int gamma_share
             all_diag = all_diag && sp->l_terms[k].is_diag && sp->l_terms[k].absq;
             all_const = all_const && sp->l_terms[k].absq_const;
         }
-        static const bool no_fast = [] { const char* e = getenv("OQB_TRAJ"); return e && e[0] == 'g'; }();
+        const bool no_fast = c->opt.traj_kernel == 1;
         if (all_diag && !no_fast && n <= 512 * 16) {
             DiagJumpDesc dj;
             dj.K = K;
@@ -964,8 +976,8 @@ int oqb_traj_jump(oqb_sparse* sp, int nb, const double* h_gamma, int gamma_share
     const int threads = n >= 2048 ? 512 : (n >= 256 ? 256 : 64);
     const int sms = sm_count(c);
     if (smem <= 200 * 1024) {
-        static bool cfg = false;
-        if (!cfg) { OQB_CUDA(c, cudaFuncSetAttribute(traj_jump_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); cfg = true; }
+        static DevOnce cfg;
+        if (!cfg.done(c->device)) { OQB_CUDA(c, cudaFuncSetAttribute(traj_jump_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); cfg.set(c->device); }
         int per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (200 * 1024) / (smem + 8 * 1024)));
         int grid = std::min(nb, sms * per_sm);
         ProfScope prof(c, (apply ? 32.0 : 16.0) * n * (double)nb);

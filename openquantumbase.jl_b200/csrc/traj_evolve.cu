@@ -128,6 +128,7 @@ __global__ void jump_log_kernel(int nb, const uint8_t* __restrict__ mask, const 
 extern "C" {
 
 int oqb_traj_rng_init(oqb_sparse* sp, int nb, uint64_t seed, uint64_t* d_state) {
+    OQB_DEVICE(sp, oqb_sparse_ctx(sp));
     oqb_ctx* c = oqb_sparse_ctx(sp);
     if (nb <= 0) return 0;
     if (!d_state) return set_error(c, OQB_EINVAL, "oqb_traj_rng_init: null state");
@@ -137,6 +138,7 @@ int oqb_traj_rng_init(oqb_sparse* sp, int nb, uint64_t seed, uint64_t* d_state) 
 }
 
 int oqb_traj_rng_uniform(oqb_sparse* sp, int nb, uint64_t* d_state, double* d_out) {
+    OQB_DEVICE(sp, oqb_sparse_ctx(sp));
     oqb_ctx* c = oqb_sparse_ctx(sp);
     if (nb <= 0) return 0;
     if (!d_state || !d_out) return set_error(c, OQB_EINVAL, "oqb_traj_rng_uniform: null argument");
@@ -148,6 +150,7 @@ int oqb_traj_rng_uniform(oqb_sparse* sp, int nb, uint64_t* d_state, double* d_ou
 int oqb_traj_evolve(oqb_sparse* sp, int nb, int nsteps, double dt, const double* h_coefH, int coef_shared,
                     const double* h_gamma, int gamma_shared, void* d_psi, uint64_t* d_rng, double* d_threshold,
                     int32_t* d_njumps, int32_t* d_log, int max_log, int step0) {
+    OQB_DEVICE(sp, oqb_sparse_ctx(sp));
     oqb_ctx* c = oqb_sparse_ctx(sp);
     if (nb <= 0 || nsteps <= 0) return 0;
     int n = 0, nt = 0, K = 0;
@@ -172,7 +175,7 @@ int oqb_traj_evolve(oqb_sparse* sp, int nb, int nsteps, double dt, const double*
     const size_t rowH = (size_t)(coef_shared ? 1 : nb) * nt, rowG = (size_t)(gamma_shared ? 1 : nb) * K;
     const int grid = 148 * 8, thr = 256;
     const int gb = (nb + 255) / 256;
-    static const bool no_fuse = [] { const char* e = getenv("OQB_RK_FUSE"); return e && e[0] == '0'; }();
+    const bool no_fuse = !c->opt.rk_fuse;
     bool try_fused = !no_fuse;
     for (int i = 0; i < nsteps; ++i) {
         const double* cf0 = h_coefH + (size_t)(2 * i) * rowH;

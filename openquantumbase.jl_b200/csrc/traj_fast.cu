@@ -159,10 +159,10 @@ __global__ void __launch_bounds__(NT, 1)
 template <int R, int NT, int WT>
 int launch(Ctx* c, int nb, const FastDesc& fd, const c128* coef, long long coef_ld, const c128* psi, c128* dpsi) {
     const size_t smem = 2 * (size_t)R * NT * sizeof(c128);
-    static bool cfg = false;
-    if (!cfg) {
+    static DevOnce cfg;
+    if (!cfg.done(c->device)) {
         OQB_CUDA(c, cudaFuncSetAttribute(traj_fast_kernel<R, NT, WT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        cfg = true;
+        cfg.set(c->device);
     }
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
@@ -195,7 +195,7 @@ int dispatch_n(Ctx* c, int n, int nb, const FastDesc& fd, const c128* coef, long
 int traj_matvec_fast(Ctx* c, int n, int nb, const std::vector<const TermDev*>& ts, const c128* d_coef, long long coef_ld,
                      const c128* psi, c128* dpsi, bool* used) {
     *used = false;
-    static const bool disabled = [] { const char* e = getenv("OQB_TRAJ"); return e && e[0] == 'g'; }();  // "generic"
+    const bool disabled = c->opt.traj_kernel == 1;  // generic kernels only
     if (disabled) return 0;
     FastDesc fd;
     fd.n_ell = fd.n_diag = fd.wtot = 0;

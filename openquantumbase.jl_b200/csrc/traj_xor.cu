@@ -340,7 +340,7 @@ int launch(Ctx* c, int nb, const XorDesc& d_in, const c128* coef, long long coef
         // One X-type term whose thread-local slots are exactly the single-bit flips NT·{1,2,4,…} (transverse-field
         // drivers): run the fully unrolled variant.  The local slots are put in ascending mask order first.
         constexpr int LOG2R = R == 16 ? 4 : (R == 8 ? 3 : (R == 4 ? 2 : 1));
-        static const bool no_fixed = [] { const char* e = getenv("OQB_XOR_FIXED"); return e && e[0] == '0'; }();
+        const bool no_fixed = !c->opt.xor_fixed;
         if (!no_fixed && d.n_x == 1) {
             const int ng = d.x_nrem[0], nl = d.x_begin[1] - ng;
             bool ok = nl == LOG2R && (ng == 8 || (R == 16 && (ng == 4 || ng == 12)));
@@ -371,10 +371,10 @@ int launch(Ctx* c, int nb, const XorDesc& d_in, const c128* coef, long long coef
     }
     d.coef_shared = coef_ld == 0 ? 1 : 0;
     const size_t smem = (size_t)S * (R * NT + kCoefPad) * sizeof(c128);
-    static bool cfg = false;
-    if (!cfg) {
+    static DevOnce cfg;
+    if (!cfg.done(c->device)) {
         OQB_CUDA(c, cudaFuncSetAttribute(traj_xor_kernel<R, NT, S, RV, ND, EPI, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        cfg = true;
+        cfg.set(c->device);
     }
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
@@ -400,7 +400,7 @@ int by_size_epi(Ctx* c, int n, int nb, const XorDesc& d, const c128* coef, long 
     int st = 0;
     switch (n) {
         case 4096: {
-            static const int rsel = [] { const char* e = getenv("OQB_XOR_R"); return e ? atoi(e) : 16; }();
+            const int rsel = c->opt.xor_rows;
             if (rsel == 8) st = launch<8, 512, 3, RV, ND, EPI>(c, nb, d, coef, coef_ld, psi, dpsi, rk);
             else st = launch<16, 256, 3, RV, ND, EPI>(c, nb, d, coef, coef_ld, psi, dpsi, rk);
             break;
@@ -434,8 +434,7 @@ int by_size(Ctx* c, int n, int nb, const XorDesc& d, const c128* coef, long long
 int traj_matvec_xor(Ctx* c, int n, int nb, const std::vector<const TermDev*>& ts, const c128* d_coef, long long coef_ld,
                     const c128* psi, c128* dpsi, bool* used, const RkEpilogue* rk) {
     *used = false;
-    static const int mode = [] { const char* e = getenv("OQB_TRAJ"); return e ? (int)e[0] : 0; }();
-    if (mode == 'g' || mode == 'f') return 0;  // "generic" / "fast": skip this path (A/B measurements)
+    if (c->opt.traj_kernel != 0) return 0;  // generic / no-XOR modes skip this path (A/B measurements)
     if ((int)ts.size() > kCoefPad) return 0;
     XorDesc d;
     memset(&d, 0, sizeof(d));

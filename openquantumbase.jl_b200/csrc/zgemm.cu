@@ -227,11 +227,11 @@ __global__ void __launch_bounds__(CF::NTHREADS) zgemm_kernel(ZgemmParams p, int 
 
 template <class CF>
 static int launch_cfg(Ctx* c, const ZgemmParams& p) {
-    static bool configured = false;
-    if (!configured) {
+    static DevOnce configured;
+    if (!configured.done(c->device)) {
         OQB_CUDA(c, cudaFuncSetAttribute(zgemm_kernel<CF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)CF::SMEM));
-        configured = true;
+        configured.set(c->device);
     }
     const long long nz = (long long)p.batch * p.batch2;
     dim3 block(CF::NTHREADS);

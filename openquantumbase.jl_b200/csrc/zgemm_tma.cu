@@ -492,7 +492,7 @@ int launch_tma(Ctx* c, const ZgemmParams& p, bool* used) {
     alignas(64) CUtensorMap mapA, mapB;
     int zA2, zA, zB2, zB;
     // A: k-major when op != N (A stored K×M, k contiguous), else m-major
-    static const bool no_one_shot = [] { const char* e = getenv("OQB_TMA_ONESHOT"); return e && e[0] == '0'; }();
+    const bool no_one_shot = !c->opt.tma_oneshot;
     int oneA = 0, oneB = 0;
     bool okA, okB;
     if (CF::TA) {
@@ -512,10 +512,10 @@ int launch_tma(Ctx* c, const ZgemmParams& p, bool* used) {
         else okB = make_map(&mapB, p.B, p.N, p.K, p.ldb, p.batch2, p.strideB2, p.batch, p.strideB, 8, false, 0, &zB2, &zB);
     }
     if (!okA || !okB) return 0;
-    static bool configured = false;
-    if (!configured) {
+    static DevOnce configured;
+    if (!configured.done(c->device)) {
         OQB_CUDA(c, cudaFuncSetAttribute(zgemm_tma_kernel<CF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CF::SMEM));
-        configured = true;
+        configured.set(c->device);
     }
     const long long nz = (long long)p.batch * p.batch2;
     for (long long z0 = 0; z0 < nz; z0 += 65535) {
@@ -544,7 +544,7 @@ template <bool TA, bool TB>
 int dispatch(Ctx* c, const ZgemmParams& p, bool* used) {
     // Long-K products amortise the prologue/epilogue of a 128x64 CTA (1 per SM); for short K two co-resident
     // 64x64 CTAs per SM overlap one CTA's epilogue with the other's main loop (measured: C2 +1.3 %, C5 +3.7 %).
-    static const int bm_force = [] { const char* e = getenv("OQB_ZGEMM_BM"); return e ? atoi(e) : 0; }();
+    const int bm_force = c->opt.zgemm_bm;
     const bool big = bm_force ? bm_force == 128 : p.K > 512;
     // 3M product (Ctx::zgemm_3m, default on; oqb_set_zgemm_mode / OQB_ZGEMM_3M=0 select the 4-multiplication kernel):
     // 64x64 CTA of 8 warps (32x16 warp tiles), 8 stages, one CTA per SM.
@@ -563,7 +563,7 @@ int dispatch(Ctx* c, const ZgemmParams& p, bool* used) {
 // Returns 0 and sets *used when the TMA kernel handled the product; *used == false ⇒ caller falls back.
 int zgemm_tma(Ctx* c, const ZgemmParams& p, bool* used) {
     *used = false;
-    static const bool disabled = [] { const char* e = getenv("OQB_ZGEMM"); return e && e[0] == 'c'; }();  // "cpasync"
+    const bool disabled = !c->opt.zgemm_tma;
     if (disabled || p.K < 1 || p.M < 1 || p.N < 1) return 0;
     if (((uintptr_t)p.A & 15) || ((uintptr_t)p.B & 15)) return 0;
     const bool ta = p.opA != OP_N, tb = p.opB != OP_N;

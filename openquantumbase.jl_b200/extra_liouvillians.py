@@ -16,7 +16,7 @@ import numpy as np
 
 from . import _lib
 from .gaps import GapGroups, _eval, jump_slots
-from .host import C128, Context, DeviceBatch, _HostIO, _colmajor_stack, _svec, get_context
+from .host import C128, Context, DeviceBatch, _HostIO, _colmajor_stack, _svec, add_davies_terms, get_context
 
 _ONE = np.array([1.0, 0.0])
 
@@ -89,7 +89,7 @@ class ConstHDaviesGenerator:
         self.w = np.ascontiguousarray(np.real(w), dtype=np.float64)
         self.coupling = coupling if callable(coupling) else (lambda s, c=[np.asarray(m, dtype=C128) for m in coupling]: c)
         self.gamma, self.S = gamma, S
-        self.groups = GapGroups(self.w, digits, sigdigits)
+        self.digits, self.sigdigits = digits, sigdigits
         self.ctx = ctx or get_context()
         self._ame, self._key = None, None
 
@@ -105,13 +105,7 @@ class ConstHDaviesGenerator:
         cbuf = _colmajor_stack(coup)  # keep the buffer alive across the call
         ctx.check(lib.oqb_ame_create(ctx.h, l, l, len(coup), cbuf.ctypes.data, C.byref(h)))
         ctx.check(lib.oqb_ame_set_eigen(h, _lib.dptr(self.w), None))
-        gam, Sm, crate, lrs = self.groups.tables(self.gamma, self.S)
-        gam, Sm = np.ascontiguousarray(gam.T), np.ascontiguousarray(Sm.T)
-        ci, li = np.ascontiguousarray(self.groups.cross_idx), np.ascontiguousarray(self.groups.lamb_idx)
-        ctx.check(lib.oqb_ame_set_davies(
-            h, _lib.dptr(gam), _lib.dptr(Sm), len(ci), ci.ctypes.data_as(_lib.c_i32p) if len(ci) else None,
-            _lib.dptr(crate) if len(ci) else None, len(li), li.ctypes.data_as(_lib.c_i32p) if len(li) else None,
-            _lib.dptr(lrs) if len(li) else None))
+        add_davies_terms(ctx, h, [(self.gamma, self.S, 0, len(coup))], self.digits, self.sigdigits)
         self._ame, self._key = h, s
         return h
 

@@ -83,7 +83,7 @@ def _zero_group_lists(aa, bb):
 
 
 class GapGroups:
-    def __init__(self, w, digits=8, sigdigits=8, max_cross=50_000_000):
+    def __init__(self, w, digits=8, sigdigits=8):
         w = np.asarray(w, dtype=np.float64)
         l = len(w)
         self.w, self.lvl = w, l
@@ -97,7 +97,13 @@ class GapGroups:
         omega[ju, iu] = -key
         self.omega = omega
         self.gap_matrix = w[None, :] - w[:, None]  # UNROUNDED (opensys_util.jl:65), one-sided AME only
-        # ---- groups with more than one pair --------------------------------------------------
+        self._iu, self._ju, self._zero, self._key = iu, ju, zero, key
+        self._lists = None
+
+    def _build_lists(self):
+        """Cross-term / L'L lists of the multi-pair groups — host-side statement of what csrc/ame_terms.cu builds on the
+        device (used by the CPU tests; O(Σ m²) entries, so only meant for spectra whose groups are small)."""
+        iu, ju, zero, key, l = self._iu, self._ju, self._zero, self._key, self.lvl
         parts = []
         nzi, nzj, nzk = iu[~zero], ju[~zero], key[~zero]
         if nzk.size:
@@ -106,24 +112,28 @@ class GapGroups:
             starts = np.flatnonzero(np.r_[True, ks[1:] != ks[:-1]])
             ends = np.r_[starts[1:], ks.size]
             multi = np.flatnonzero(ends - starts > 1)
-            est = int(np.sum((ends[multi] - starts[multi]).astype(np.int64) ** 2)) * 2
-            if est > max_cross:
-                raise NotImplementedError(
-                    f"gap spectrum is too degenerate for the cross-term list ({est} entries); "
-                    "the dense per-group path is not implemented")
             parts.append(_group_cross_lists(nzi[order], nzj[order], starts[multi], ends[multi], ks[starts[multi]]))
         # ---- zero group: degenerate pairs (both orders) + the diagonal ---------------------------
         zi, zj = iu[zero], ju[zero]
         if zi.size:
             aa = np.r_[zi, zj, np.arange(l)]
             bb = np.r_[zj, zi, np.arange(l)]
-            if (len(aa)) ** 2 > max_cross:
-                raise NotImplementedError("zero-gap group too large for the cross-term list")
             parts.append(_zero_group_lists(aa, bb))
-        self.cross_idx = np.concatenate([q[0] for q in parts]) if parts else np.zeros((0, 4), dtype=np.int32)
-        self.cross_key = np.concatenate([q[1] for q in parts]) if parts else np.zeros(0)
-        self.lamb_idx = np.concatenate([q[2] for q in parts]) if parts else np.zeros((0, 3), dtype=np.int32)
-        self.lamb_key = np.concatenate([q[3] for q in parts]) if parts else np.zeros(0)
+        self._lists = (
+            np.concatenate([q[0] for q in parts]) if parts else np.zeros((0, 4), dtype=np.int32),
+            np.concatenate([q[1] for q in parts]) if parts else np.zeros(0),
+            np.concatenate([q[2] for q in parts]) if parts else np.zeros((0, 3), dtype=np.int32),
+            np.concatenate([q[3] for q in parts]) if parts else np.zeros(0))
+
+    def _list(self, k):
+        if self._lists is None:
+            self._build_lists()
+        return self._lists[k]
+
+    cross_idx = property(lambda self: self._list(0))
+    cross_key = property(lambda self: self._list(1))
+    lamb_idx = property(lambda self: self._list(2))
+    lamb_key = property(lambda self: self._list(3))
 
     @staticmethod
     def _pairs(aa, bb, kval, cross, cross_key, lamb, lamb_key, skip_diag_diag=False):
@@ -174,7 +184,7 @@ def pair_to_ij(l: int, pairs: np.ndarray):
     return iu[pairs], ju[pairs]
 
 
-def cross_lists_from_groups(l: int, multi_pair, multi_key, zero_pair, max_cross=50_000_000):
+def cross_lists_from_groups(l: int, multi_pair, multi_key, zero_pair):
     """The cross-term / Lamb-shift lists of `GapGroups` from the device-side grouping (ame_gaps.cu): `multi_pair` are the
     pairs that share their rounded gap with another pair, sorted by key (stable: the reference's loop order inside a
     group), `zero_pair` the pairs of the zero group.  Returns (cross_idx, cross_key, lamb_idx, lamb_key)."""
@@ -184,16 +194,11 @@ def cross_lists_from_groups(l: int, multi_pair, multi_key, zero_pair, max_cross=
         mi, mj = pair_to_ij(l, multi_pair)
         starts = np.flatnonzero(np.r_[True, multi_key[1:] != multi_key[:-1]])
         ends = np.r_[starts[1:], len(multi_key)]
-        est = int(np.sum((ends - starts).astype(np.int64) ** 2)) * 2
-        if est > max_cross:
-            raise NotImplementedError(f"gap spectrum is too degenerate for the cross-term list ({est} entries)")
         parts.append(_group_cross_lists(mi, mj, starts, ends, multi_key[starts]))
     if len(zero_pair):
         zi, zj = pair_to_ij(l, np.sort(np.asarray(zero_pair)))
         aa = np.r_[zi, zj, np.arange(l)]
         bb = np.r_[zj, zi, np.arange(l)]
-        if len(aa) ** 2 > max_cross:
-            raise NotImplementedError("zero-gap group too large for the cross-term list")
         parts.append(_zero_group_lists(aa, bb))
     if not parts:
         return np.zeros((0, 4), dtype=np.int32), np.zeros(0), np.zeros((0, 3), dtype=np.int32), np.zeros(0)

@@ -12,6 +12,7 @@ copies inside the call).  There is no CPU fallback.
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
 import os
 import math
@@ -31,6 +32,16 @@ C128 = np.complex128
 # --------------------------------------------------------------------------------------------
 # context / device batches
 # --------------------------------------------------------------------------------------------
+_ENV_OPTIONS = {
+    "OQB_ZGEMM_3M": ("zgemm_3m", int), "OQB_REAL_OPERAND": ("real_operand", int),
+    "OQB_LINDBLAD_DIAG": ("lindblad_diag", int), "OQB_COUPLING_DIAG": ("coupling_diag", int),
+    "OQB_RK_FUSE": ("rk_fuse", int), "OQB_TMA_ONESHOT": ("tma_oneshot", int), "OQB_ZGEMM_BM": ("zgemm_bm", int),
+    "OQB_AME_HOST_CHUNK_MIB": ("ame_host_chunk_mib", int), "OQB_XOR_FIXED": ("xor_fixed", int), "OQB_XOR_R": ("xor_rows", int),
+    "OQB_TRAJ": ("traj_kernel", lambda v: {"g": 1, "f": 2}.get(v[:1], 0)),
+    "OQB_ZGEMM": ("zgemm_tma", lambda v: 0 if v[:1] == "c" else 1),
+}
+
+
 class Context:
     """One CUDA stream + workspace (oqb_ctx).  Not thread-safe, like the reference's functors."""
 
@@ -47,6 +58,30 @@ class Context:
         import torch
         with torch.cuda.device(device):
             self.check(self.lib.oqb_set_stream(self.h, C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        # A/B switches for the benchmark scripts: the LIBRARY reads no environment variables (switches are per context,
+        # oqb_set_option); this host mirror forwards the ones the round-1 scripts used.
+        for env, (name, conv) in _ENV_OPTIONS.items():
+            if env in os.environ:
+                self.set_option(name, conv(os.environ[env]))
+
+    def set_option(self, name: str, value: int):
+        """Per-context switch by name (include/oqb.h: oqb_set_option)."""
+        self.check(self.lib.oqb_set_option(self.h, name.encode(), int(value)))
+
+    def get_option(self, name: str) -> int:
+        v = C.c_int64()
+        self.check(self.lib.oqb_get_option(self.h, name.encode(), C.byref(v)))
+        return v.value
+
+    @contextlib.contextmanager
+    def option(self, name: str, value: int):
+        """`with ctx.option("davies_dense_min_pairs", 2): …` — set for the block, restore afterwards."""
+        old = self.get_option(name)
+        self.set_option(name, value)
+        try:
+            yield
+        finally:
+            self.set_option(name, old)
 
     def check(self, st):
         if st != 0:
@@ -784,6 +819,40 @@ def build_lambshift(w_range, turn_on: bool, bath, rtol=_SQRT_EPS, atol=0.0):
 # --------------------------------------------------------------------------------------------
 # eigenbasis Liouvillians
 # --------------------------------------------------------------------------------------------
+def add_davies_terms(ctx, h, terms, digits=8, sigdigits=8):
+    """GapIndices + the Davies term list of one eigen-system, built by the library (csrc/ame_terms.cu).
+    terms: (γ, S, k0, nk) per DaviesGenerator — its coupling slice of the handle `h`.  Ohmic baths (with S ≡ 0 or a
+    tabulated Lamb shift) are evaluated on the device; any other closure is evaluated HERE, but only at the distinct gap
+    keys the library reports — the calls the reference's loop makes (src/opensys/davies.jl:26-28, :38)."""
+    from .gaps import _eval
+    lib = ctx.lib
+    nk_, nz_ = C.c_int64(), C.c_int64()
+    ctx.check(lib.oqb_ame_gaps_build(h, digits, sigdigits, C.byref(nk_), C.byref(nz_)))
+    keys = None
+    for gamma, S, k0, nk in terms:
+        if isinstance(gamma, OhmicBath) and isinstance(S, (_Zero, QuadraticBSpline)):
+            Ssp = S if isinstance(S, QuadraticBSpline) else None
+            ctx.check(lib.oqb_ame_add_davies_ohmic(h, k0, nk, gamma.eta, gamma.wc, gamma.beta, Ssp.n if Ssp else 0,
+                                                   Ssp.x0 if Ssp else 0.0, Ssp.dx if Ssp else 1.0,
+                                                   Ssp.coef.ctypes.data if Ssp else None))
+            continue
+        if keys is None:
+            keys = np.empty(nk_.value, dtype=np.float64)
+            ctx.check(lib.oqb_ame_gaps_keys(h, _lib.dptr(keys)))
+        gp, gm = np.ascontiguousarray(_eval(gamma, keys)), np.ascontiguousarray(_eval(gamma, -keys))
+        sp_, sm_ = np.ascontiguousarray(_eval(S, keys)), np.ascontiguousarray(_eval(S, -keys))
+        g0, S0 = float(_eval(gamma, np.zeros(1))[0]), float(_eval(S, np.zeros(1))[0])
+        ctx.check(lib.oqb_ame_add_davies(h, k0, nk, _lib.dptr(gp), _lib.dptr(gm), _lib.dptr(sp_), _lib.dptr(sm_), g0, S0))
+    return nk_.value, nz_.value
+
+
+def davies_stats(ctx, h):
+    """(generators, cross-list entries, L'L list entries, gap groups on the dense path, dense blocks kept) of a plan."""
+    v = [C.c_int64() for _ in range(5)]
+    ctx.check(ctx.lib.oqb_ame_davies_stats(h, *[C.byref(x) for x in v]))
+    return tuple(x.value for x in v)
+
+
 class DaviesGenerator:
     """src/opensys/davies.jl:12-19.  coupling: ConstantCouplings (or a list of matrices, already
     unit-scaled); γ, S: host closures (objects with `.vectorized` are evaluated array-wise)."""
@@ -971,7 +1040,24 @@ class DiffEqLiouvillian:
         the H2D/D2H copies are inside the call and pipelined against the kernels."""
         B = u.shape[0]
         sv = _svec(p(t), B)
+        if self.adiabatic_frame:
+            raise NotImplementedError("rhs_host: the adiabatic-frame forms take the call operator (device or numpy states)")
         if self.diagonalization:
+            if self.opensys:  # :106-108 — the non-eigenbasis terms need the state on the device: use the call operator
+                raise NotImplementedError("rhs_host with extra `opensys` terms: use the call operator (it accepts numpy states)")
+            if sv.size > 1 and np.any(sv != sv[0]):  # schedule sweep: one pipelined call per group of members sharing s
+                order = np.argsort(sv, kind="stable")
+                ss = sv[order]
+                starts = np.flatnonzero(np.r_[True, ss[1:] != ss[:-1]])
+                ends = np.r_[starts[1:], len(ss)]
+                for a, b in zip(starts, ends):
+                    idx = order[a:b]
+                    sub_u = np.ascontiguousarray(u[idx])
+                    sub_du = np.empty_like(sub_u)
+                    self._prepare_ame(float(ss[a]))
+                    self.ctx.check(self.ctx.lib.oqb_ame_rhs_host(self._ame, len(idx), sub_u.ctypes.data, sub_du.ctypes.data))
+                    du[idx] = sub_du
+                return du
             self._prepare_ame(float(sv[0]))
             self.ctx.check(self.ctx.lib.oqb_ame_rhs_host(self._ame, B, u.ctypes.data, du.ctypes.data))
             return du
@@ -1021,7 +1107,14 @@ class DiffEqLiouvillian:
     def _prepare_ame(self, s: float, w=None, v=None):
         """Everything that is shared by the batch for one value of s: eigen-system (host LAPACK, the device
         eigensolver when `self.device_eigh` is set, or supplied), gap groups, γ/S tables, device tables."""
-        key = (s, None if w is None else (id(w) if v is not None else tuple(np.asarray(w).tolist())))
+        if w is None:
+            key = (s, None)
+        else:  # a supplied eigen-system is keyed by CONTENT (an id() can be recycled by a later array)
+            import hashlib
+            hh = hashlib.blake2b(np.ascontiguousarray(w, dtype=np.float64).tobytes(), digest_size=16)
+            if v is not None:
+                hh.update(np.ascontiguousarray(v).tobytes())
+            key = (s, hh.hexdigest())
         plans = self.__dict__.setdefault("_plans", {})
         if key in plans:  # a small LRU of prepared eigen-systems: schedule sweeps revisit the same s values
             plan = plans.pop(key)
@@ -1095,58 +1188,24 @@ class DiffEqLiouvillian:
         else:
             vbuf = np.ascontiguousarray(np.asarray(v, dtype=C128).T)  # column-major n×lvl
             ctx.check(lib.oqb_ame_set_eigen(h, _lib.dptr(w), vbuf.ctypes.data))
-        dev_tables = (getattr(self, "device_tables", False) and len(self.opensys_eig) == 1
-                      and isinstance(self.opensys_eig[0], DaviesGenerator)
-                      and isinstance(self.opensys_eig[0].gamma, OhmicBath)
-                      and isinstance(self.opensys_eig[0].S, (_Zero, QuadraticBSpline)))
-        dev_onesided = (getattr(self, "device_tables", False) and len(self.opensys_eig) == 1
-                        and isinstance(self.opensys_eig[0], OneSidedAMELiouvillian)
-                        and isinstance(self.opensys_eig[0].gamma, OhmicBath)
-                        and isinstance(self.opensys_eig[0].S, (_Zero, QuadraticBSpline)))
-        groups = None if (dev_tables or dev_onesided) else GapGroups(w, self.digits, self.sigdigits)  # :96
-        ndav = 0
-        for lv, (c0, c1) in zip(self.opensys_eig, slices):
-            if dev_tables:
-                # GapIndices grouping and the γ(ω̃_ab) table on the device (ame_gaps.cu); only the members of multi-pair
-                # groups come back for the cross-term lists
-                from .gaps import cross_lists_from_groups
-                nm, nz = C.c_int64(), C.c_int64()
-                bath = lv.gamma
-                if isinstance(lv.S, QuadraticBSpline):  # tabulated Lamb shift: S(ω̃_ab) from the spline on the device
-                    ctx.check(lib.oqb_ame_set_lambshift_spline(h, lv.S.n, lv.S.x0, lv.S.dx, lv.S.coef.ctypes.data))
-                else:
-                    ctx.check(lib.oqb_ame_set_lambshift_spline(h, 0, 0.0, 1.0, None))
-                ctx.check(lib.oqb_ame_davies_ohmic_begin(h, bath.eta, bath.wc, bath.beta, self.digits, self.sigdigits,
-                                                         C.byref(nm), C.byref(nz)))
-                mp, mk = np.empty(nm.value, dtype=np.int32), np.empty(nm.value, dtype=np.float64)
-                zp = np.empty(nz.value, dtype=np.int32)
-                if nm.value or nz.value:
-                    ctx.check(lib.oqb_ame_davies_fetch_groups(h, mp.ctypes.data_as(_lib.c_i32p), _lib.dptr(mk),
-                                                              zp.ctypes.data_as(_lib.c_i32p)))
-                ci, ck, li, lk = cross_lists_from_groups(lvl, mp, mk, zp)
-                crate = np.ascontiguousarray(bath.vectorized(ck)) if len(ck) else np.zeros(0)
-                lrs = (np.ascontiguousarray(np.stack([bath.vectorized(lk), lv.S.vectorized(lk)], axis=1)) if len(lk)
-                       else np.zeros((0, 2)))
-                ci, li = np.ascontiguousarray(ci), np.ascontiguousarray(li)
-                ctx.check(lib.oqb_ame_davies_ohmic_finish(
-                    h, len(ci), ci.ctypes.data_as(_lib.c_i32p) if len(ci) else None, _lib.dptr(crate) if len(ci) else None,
-                    len(li), li.ctypes.data_as(_lib.c_i32p) if len(li) else None, _lib.dptr(lrs) if len(li) else None))
-                continue
-            if isinstance(lv, DaviesGenerator):
-                if ndav or c0 != 0 or c1 != len(coup):
-                    raise NotImplementedError("one DaviesGenerator per DiffEqLiouvillian (it owns all couplings)")
-                ndav += 1
-                gam, Sm, crate, lrs = groups.tables(lv.gamma, lv.S)
-                gam = np.ascontiguousarray(gam.T)  # column-major [a + b*l]
-                Sm = np.ascontiguousarray(Sm.T)
-                ci = np.ascontiguousarray(groups.cross_idx)
-                li = np.ascontiguousarray(groups.lamb_idx)
-                ctx.check(lib.oqb_ame_set_davies(
-                    h, _lib.dptr(gam), _lib.dptr(Sm), len(ci), ci.ctypes.data_as(_lib.c_i32p) if len(ci) else None,
-                    _lib.dptr(crate) if len(ci) else None, len(li),
-                    li.ctypes.data_as(_lib.c_i32p) if len(li) else None, _lib.dptr(lrs) if len(li) else None))
-            elif isinstance(lv, OneSidedAMELiouvillian) and dev_onesided:
+        # ---- eigenbasis terms (src/opensys/diffeq_liouvillian.jl:101-103: every term of opensys_eig accumulates) ----
+        # GapIndices (:96) is built by the library on the device; γ and S are needed only at its distinct keys — the
+        # same closure calls the reference's loop makes (src/opensys/davies.jl:26-28).
+        from .gaps import _eval
+        davies = [(lv, sl) for lv, sl in zip(self.opensys_eig, slices) if isinstance(lv, DaviesGenerator)]
+        onesided = [(lv, sl) for lv, sl in zip(self.opensys_eig, slices) if isinstance(lv, OneSidedAMELiouvillian)]
+        for lv in self.opensys_eig:
+            if not isinstance(lv, (DaviesGenerator, OneSidedAMELiouvillian)):
+                raise NotImplementedError(f"eigenbasis term {type(lv).__name__} is not on the device path")
+        if davies:
+            add_davies_terms(ctx, h, [(lv.gamma, lv.S, c0, c1 - c0) for lv, (c0, c1) in davies], self.digits, self.sigdigits)
+        if onesided:
+            dev_onesided = (getattr(self, "device_tables", False) and len(onesided) == 1
+                            and isinstance(onesided[0][0].gamma, OhmicBath)
+                            and isinstance(onesided[0][0].S, (_Zero, QuadraticBSpline)))
+            if dev_onesided:
                 # γ(w_b − w_a) and the spline S at the l² unrounded gaps on the device (one shared table, davies.jl:368)
+                lv, (c0, c1) = onesided[0]
                 Ssp = lv.S if isinstance(lv.S, QuadraticBSpline) else None
                 ctx.check(lib.oqb_ame_set_lambshift_spline(h, Ssp.n if Ssp else 0, Ssp.x0 if Ssp else 0.0, Ssp.dx if Ssp else 1.0,
                                                            Ssp.coef.ctypes.data if Ssp else None))
@@ -1154,28 +1213,25 @@ class DiffEqLiouvillian:
                 be = np.ascontiguousarray([c0 + b - 1 for _, b in lv.inds], dtype=np.int32)
                 ctx.check(lib.oqb_ame_set_onesided_ohmic(h, len(lv.inds), al.ctypes.data_as(_lib.c_i32p),
                                                          be.ctypes.data_as(_lib.c_i32p), lv.gamma.eta, lv.gamma.wc, lv.gamma.beta))
-            elif isinstance(lv, OneSidedAMELiouvillian):
-                from .gaps import _eval
-                gm = groups.gap_matrix  # UNROUNDED, davies.jl:368
-                uniq, inv = np.unique(gm.ravel(), return_inverse=True)
-                shared = not isinstance(lv.gamma, dict)
-                pairs = lv.inds
-                if shared:
-                    g1 = _eval(lv.gamma, uniq)[inv].reshape(lvl, lvl)
-                    s1 = _eval(lv.S, uniq)[inv].reshape(lvl, lvl)
-                    gt = np.ascontiguousarray(g1.T)[None]
-                    st_ = np.ascontiguousarray(s1.T)[None]
-                else:
-                    gt = np.stack([np.ascontiguousarray(_eval(lv.gamma[pq], uniq)[inv].reshape(lvl, lvl).T) for pq in pairs])
-                    st_ = np.stack([np.ascontiguousarray(_eval(lv.S[pq], uniq)[inv].reshape(lvl, lvl).T) for pq in pairs])
-                al = np.ascontiguousarray([c0 + a - 1 for a, _ in pairs], dtype=np.int32)
-                be = np.ascontiguousarray([c0 + b - 1 for _, b in pairs], dtype=np.int32)
-                gt, st_ = np.ascontiguousarray(gt), np.ascontiguousarray(st_)
-                ctx.check(lib.oqb_ame_set_onesided(h, len(pairs), al.ctypes.data_as(_lib.c_i32p),
-                                                   be.ctypes.data_as(_lib.c_i32p), _lib.dptr(gt), _lib.dptr(st_),
-                                                   int(shared)))
             else:
-                raise NotImplementedError(f"eigenbasis term {type(lv).__name__} is not on the device path")
+                gm_ = w[None, :] - w[:, None]  # UNROUNDED gap matrix ω_ba[i,j] = w[j] − w[i] (opensys_util.jl:65, davies.jl:368)
+                uniq, inv = np.unique(gm_.ravel(), return_inverse=True)
+                al, be, gts, sts = [], [], [], []
+                shared = len(onesided) == 1 and not isinstance(onesided[0][0].gamma, dict)
+                for lv, (c0, c1) in onesided:  # the (α,β) pairs of every one-sided term, concatenated
+                    for pq in lv.inds:
+                        al.append(c0 + pq[0] - 1)
+                        be.append(c0 + pq[1] - 1)
+                        if shared and gts:
+                            continue
+                        gf = lv.gamma[pq] if isinstance(lv.gamma, dict) else lv.gamma
+                        sf = lv.S[pq] if isinstance(lv.S, dict) else lv.S
+                        gts.append(np.ascontiguousarray(_eval(gf, uniq)[inv].reshape(lvl, lvl).T))
+                        sts.append(np.ascontiguousarray(_eval(sf, uniq)[inv].reshape(lvl, lvl).T))
+                al, be = np.ascontiguousarray(al, dtype=np.int32), np.ascontiguousarray(be, dtype=np.int32)
+                gt, st_ = np.ascontiguousarray(np.stack(gts)), np.ascontiguousarray(np.stack(sts))
+                ctx.check(lib.oqb_ame_set_onesided(h, len(al), al.ctypes.data_as(_lib.c_i32p), be.ctypes.data_as(_lib.c_i32p),
+                                                   _lib.dptr(gt), _lib.dptr(st_), int(shared)))
         return {"h": h, "w": w, "v": (None if dev_eig is not None else v),
                 "v_dev": dev_eig[1] if dev_eig is not None else None, "lvl": lvl}
 

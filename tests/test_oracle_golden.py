@@ -458,3 +458,62 @@ def test_ohmic_correlation_and_timescales_known_answers():
     for z in (0.084 + 0.3j, 1.084 - 2j, 0.5, 3 + 40j, 0.084 + 1e-3j, 12.5 + 0.1j, -0.3 + 0.2j):
         ref = complex(mpmath.psi(1, z))
         assert abs(O.trigamma(z) - ref) <= 1e-15 * abs(ref) * 4
+
+
+# ---- oracle/davies_groups.py: the scalable Davies statement against the literal loop --------------------------------
+def _spectra(l, rng):
+    """generic / equally spaced / degenerate / 8-digit coincidences forced / several of those mixed"""
+    w_gen = np.sort(rng.standard_normal(l) * 3.0)
+    w_eq = np.arange(l, dtype=float) * 0.5
+    w_deg = np.sort(np.repeat(np.arange(l // 4 + 1, dtype=float), 4)[:l] * 1.25)
+    w_coin = w_gen.copy()
+    w_coin[l // 2] = w_coin[l // 2 - 1] + (w_coin[3] - w_coin[1])            # an exact coincidence of two gaps
+    w_coin[l - 1] = w_coin[l - 2] + (w_coin[2] - w_coin[0]) * (1 + 3e-10)    # a coincidence after rounding to 8 digits
+    w_coin = np.sort(w_coin)
+    w_tiny = w_gen.copy()
+    w_tiny[1] = w_tiny[0] + 3e-9                                              # inside the 10^-8 zero-gap threshold
+    w_tiny[5] = w_tiny[4] + 1.2e-8                                            # just outside it
+    return {"generic": w_gen, "equal": w_eq, "degenerate": w_deg, "coincidence": w_coin, "tiny": np.sort(w_tiny)}
+
+
+@pytest.mark.parametrize("l", [6, 16, 40])
+@pytest.mark.parametrize("kind", ["generic", "equal", "degenerate", "coincidence", "tiny"])
+def test_davies_groups_oracle_matches_literal_loop(l, kind):
+    from oracle import davies_groups as DG
+    rng = np.random.default_rng(l * 31 + len(kind))
+    w = _spectra(l, rng)[kind]
+    As = [(lambda m: m + m.conj().T)(rng.standard_normal((l, l)) + 1j * rng.standard_normal((l, l))) for _ in range(2)]
+    rho = rng.standard_normal((l, l)) + 1j * rng.standard_normal((l, l))  # no Hermiticity assumed (App. A.3)
+    gi = O.build_gap_indices(w, 8, 8)
+    D = O.DaviesGenerator(As, gamma, lamb)
+    ref = D.rhs_acc(np.zeros((l, l), dtype=complex), rho, gi, None, 0.0)   # literal loop, couplings already in the eigenbasis
+    got = DG.davies_eig_acc(np.zeros((l, l), dtype=complex), rho, As, w, gamma, lamb, 8, 8)
+    assert np.linalg.norm(got - ref) <= 2e-14 * np.linalg.norm(ref)
+    # the grouping itself: same keys, same member lists in loop order, same zero group
+    grp, zero = DG.gap_groups(w, 8, 8)
+    assert sorted(grp) == list(gi.uniq_w)
+    for key, a, b in gi.positive_gap_indices():
+        assert [(i + 1, j + 1) for i, j in grp[key]] == list(zip(a, b))
+    assert [(i + 1, j + 1) for i, j in zero] == list(zip(gi.a0[0:2 * len(zero):2], gi.b0[0:2 * len(zero):2]))
+
+
+def test_davies_groups_oracle_two_generators_full_rhs():
+    """ame_rhs with two DaviesGenerators (davies_from_interactions: one per interaction, src/coupling/interaction.jl:101-117)
+    against the literal DiffEqLiouvillian{true,false} restatement."""
+    from oracle import davies_groups as DG
+    rng = np.random.default_rng(5)
+    n = 16
+    H = F.random_hermitian(n, rng) if hasattr(F, "random_hermitian") else (lambda m: (m + m.conj().T) / 2)(rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n)))
+    w, v = np.linalg.eigh(H)
+    cs = [(lambda m: m + m.conj().T)(rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))) for _ in range(3)]
+    g2 = lambda x: 0.3 * gamma(x)
+    s2 = lambda x: 0.5 * x
+    u = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))
+    got = DG.ame_rhs(u, w, v, cs, [(gamma, lamb, [0, 1]), (g2, s2, [2])], 8, 8)
+    gi = O.build_gap_indices(w, 8, 8)
+    rho = v.conj().T @ u @ v
+    X = -1j * (np.diag(w) @ rho - rho @ np.diag(w))
+    O.DaviesGenerator(cs[:2], gamma, lamb).rhs_acc(X, rho, gi, v, 0.0)
+    O.DaviesGenerator(cs[2:], g2, s2).rhs_acc(X, rho, gi, v, 0.0)
+    ref = v @ X @ v.conj().T
+    assert np.linalg.norm(got - ref) <= 1e-13 * np.linalg.norm(ref)
