@@ -43,6 +43,8 @@ typedef struct oqb_dense oqb_dense;   /* DenseHamiltonian terms + Lindblad opera
 typedef struct oqb_sparse oqb_sparse; /* SparseHamiltonian terms + sparse Lindblad operators  */
 typedef struct oqb_ame oqb_ame;       /* eigenbasis (Davies / one-sided AME) Liouvillian      */
 typedef struct oqb_lambda oqb_lambda; /* batched builder of the Redfield kernel matrices Λ(t) */
+typedef struct oqb_liouv oqb_liouv;   /* DiffEqLiouvillian{true,false}: H terms + eigenbasis terms + cached eigen-systems */
+typedef struct oqb_comm oqb_comm;     /* NCCL communicator for the ensemble-average reduce      */
 
 enum { OQB_OP_N = 0, OQB_OP_T = 1, OQB_OP_C = 2 };
 enum { OQB_OK = 0, OQB_EINVAL = 1, OQB_ECUDA = 2, OQB_ENOMEM = 3 };
@@ -262,6 +264,7 @@ int oqb_ame_davies_stats(const oqb_ame* ame, int64_t* n_terms, int64_t* n_cross,
  * (oqb_ame_get_rotated_couplings: K lvl×lvl matrices v'A_αv as the device computed them). */
 int oqb_ame_set_tables(oqb_ame* ame, const void* h_Cm, const double* h_Wt_re, const double* h_Wt_im);
 int oqb_ame_get_rotated_couplings(oqb_ame* ame, void* h_A);
+int oqb_ame_get_levels(oqb_ame* ame, double* h_w); /* the lvl eigen-energies of the current eigen-system */
 /* One-sided AME (src/opensys/davies.jl:367-379): npairs (α,β) 0-based; tables at the UNROUNDED
  * gap matrix ω_ba[i,j] = w[j]−w[i] (src/opensys/opensys_util.jl:65): h_gam/h_S are lvl×lvl per pair,
  * or one shared table when tables_shared != 0 (SingleFunctionMatrix). */
@@ -298,6 +301,50 @@ int oqb_ame_set_jump(oqb_ame* ame, int nslots, const int64_t* h_slot_ptr, const 
 int oqb_ame_clear_jump(oqb_ame* ame);
 int oqb_ame_jump(oqb_ame* ame, int nb, void* d_psi, const double* d_uniform, const uint8_t* d_mask, int32_t* d_choice,
                  double* d_prob, int apply);
+
+/* ---------------------------------------------- DiffEqLiouvillian{true,false} as one library object ---------- */
+/* Everything (Op::DiffEqLiouvillian{true,false})(du,u,p,t) does, src/opensys/diffeq_liouvillian.jl:92-105, behind one call:
+ * H(s) = Σ f_i(s) m_i from the DenseHamiltonian terms of `H` (borrowed; must outlive the object), haml_eigs on the device
+ * (cuSOLVER Zheevd, or Dsyevd when every term matrix is real — bound with dlopen at first use), GapIndices(w, digits,
+ * sigdigits), the tables of every eigenbasis term, the rotations.  Prepared eigen-systems are cached (LRU) by the
+ * coefficient row f_i(s), so RK stages and schedule sweeps that revisit an s pay the O(n³) setup once.
+ * lvl: kept levels (≤ 0 or > n ⇒ n).  h_couplings: the K coupling matrices of ALL eigenbasis terms, concatenated
+ * (n×n each, unit-scaled); terms refer to them by index.  Constant couplings only. */
+int oqb_liouv_create(oqb_ctx* ctx, oqb_dense* H, int lvl, int digits, int sigdigits, int K, const void* h_couplings,
+                     oqb_liouv** out);
+int oqb_liouv_destroy(oqb_liouv* L);
+/* A spectrum γ(ω) or S(ω) as a C callback, evaluated on the CALLING thread during plan preparation at the distinct gap
+ * keys (vectorised: out[i] = f(w[i]), i < n) — Julia passes an @cfunction pointer wrapping the user's closure. */
+typedef void (*oqb_spectrum_fn)(void* user, int64_t n, const double* w, double* out);
+/* push!(opensys_eig, DaviesGenerator(couplings[k0:k0+nk), γ, S)) — src/opensys/davies.jl:12-19; one call per interaction
+ * (src/coupling/interaction.jl:101-117).  Ohmic: γ in closed form, S ≡ 0 (nS = 0) or the quadratic B-spline of
+ * build_lambshift (arguments as oqb_ame_set_lambshift_spline), all evaluated on the device. */
+int oqb_liouv_add_davies_ohmic(oqb_liouv* L, int k0, int nk, double eta, double wc, double beta, int nS, double S_x0,
+                               double S_dx, const double* h_S_coef);
+int oqb_liouv_add_davies_fn(oqb_liouv* L, int k0, int nk, oqb_spectrum_fn gamma, void* gamma_user, oqb_spectrum_fn S,
+                            void* S_user); /* S may be NULL (≡ 0) */
+/* push!(opensys_eig, OneSidedAMELiouvillian(…, inds)) — src/opensys/davies.jl:356-365; (α,β) 0-based into the couplings. */
+int oqb_liouv_add_onesided_ohmic(oqb_liouv* L, int npairs, const int32_t* h_alpha, const int32_t* h_beta, double eta,
+                                 double wc, double beta, int nS, double S_x0, double S_dx, const double* h_S_coef);
+int oqb_liouv_add_onesided_fn(oqb_liouv* L, int npairs, const int32_t* h_alpha, const int32_t* h_beta,
+                              oqb_spectrum_fn gamma, void* gamma_user, oqb_spectrum_fn S, void* S_user);
+int oqb_liouv_set_plan_cache(oqb_liouv* L, int capacity); /* default 8 eigen-systems */
+/* du[b] = full eigenbasis RHS (OVERWRITES).  h_coefH: the closure values f_i(s_b), [nb][nterms] (one row when
+ * coef_shared): members are grouped by row, one eigen-system per distinct row. */
+int oqb_liouv_rhs(oqb_liouv* L, int nb, const double* h_coefH, int coef_shared, const void* d_u, void* d_du);
+int oqb_liouv_rhs_host(oqb_liouv* L, int nb, const double* h_coefH, int coef_shared, const void* h_u, void* h_du);
+/* update_cache!(cache, Op::DiffEqLiouvillian{true,false}, p, t) :111-125 for one s (h_coefH: one row)  (OVERWRITES) */
+int oqb_liouv_update_cache(oqb_liouv* L, const double* h_coefH, void* d_cache);
+/* The prepared eigen-system for one coefficient row (built if not cached), e.g. for oqb_ame_jump / oqb_ame_gaps_fetch.
+ * Owned by the object; valid until evicted. */
+int oqb_liouv_prepare(oqb_liouv* L, const double* h_coefH, oqb_ame** plan);
+int oqb_liouv_stats(const oqb_liouv* L, uint64_t* plans_built, uint64_t* cache_hits, double* last_prepare_ms,
+                    double* last_eig_ms);
+/* haml_eigs(H, s, lvl) on the device (src/hamiltonian/hamiltonian_base.jl:155-160): H(s) from one coefficient row,
+ * ascending eigenvalues into d_w (n doubles) and eigenvectors into d_V (n×n column-major; the first lvl columns are the
+ * truncated basis).  Real term matrices take the real symmetric solver and return exactly real eigenvectors. */
+int oqb_dense_eigen(oqb_dense* op, const double* h_coefH, double* d_w, void* d_V);
+int oqb_dense_info(const oqb_dense* op, int* n, int* nterms, int* K, int* terms_real);
 
 /* ------------------------------------------- SparseHamiltonian + trajectories (ψ ensembles) */
 /* Terms and Lindblad operators as Julia SparseMatrixCSC{ComplexF64,Int64}: 1-based colptr
@@ -382,6 +429,32 @@ int oqb_bspline_eval(oqb_ctx* ctx, int n, double x0, double dx, const double* h_
  * (re,im) pairs; d_obs: nobs dense n×n matrices.  Partial sums for the NCCL ensemble average. */
 int oqb_expect(oqb_ctx* ctx, int n, int nobs, const void* d_obs, int nb, const void* d_state,
                int is_vector, double* d_out);
+
+/* Per-GPU partial sums for an ensemble average: out[o] = Σ_b tr(O_o ρ[b]) (or Σ_b ψ[b]'O_oψ[b]), nobs complex (re,im) pairs in
+ * device memory, summed in a fixed order (deterministic) on the context stream — the input of oqb_allreduce_obs. */
+int oqb_expect_sum(oqb_ctx* ctx, int n, int nobs, const void* d_obs, int nb, const void* d_state, int is_vector,
+                   double* d_out);
+
+/* ------------------------------------------------------------- multi-GPU: the ensemble reduce ----- */
+/* The only collective of the path: every ρ / ψ / schedule is independent inside an RHS call; ensemble
+ * averages (C4) are one ncclAllReduce(sum, double) and per-schedule observables (C5) one ncclAllGather per output point.
+ * NCCL is bound with dlopen("libnccl.so.2") when the first communicator is created.
+ *  - one process or thread per GPU: rank 0 calls oqb_comm_unique_id (128 bytes), the host ships them to the other ranks
+ *    (MPI, torch.distributed, Distributed.jl, a file …), every rank calls oqb_comm_init_rank with its own context;
+ *  - one process driving all GPUs (a Julia process with Threads.@threads over devices): oqb_comm_init_all over one
+ *    context per GPU (ncclCommInitAll); collectives issued from ONE thread for several communicators go between
+ *    oqb_comm_group_start / oqb_comm_group_end.
+ * Collectives are enqueued on the communicator's context stream (no host synchronisation) and work in place. */
+int oqb_nccl_version(int* version);
+int oqb_comm_unique_id(void* id128);
+int oqb_comm_init_rank(oqb_ctx* ctx, int nranks, int rank, const void* id128, oqb_comm** out);
+int oqb_comm_init_all(int ndev, oqb_ctx* const* ctxs, oqb_comm** out /* ndev handles */);
+int oqb_comm_destroy(oqb_comm* comm);
+int oqb_comm_rank(const oqb_comm* comm, int* rank, int* nranks);
+int oqb_comm_group_start(void);
+int oqb_comm_group_end(void);
+int oqb_allreduce_obs(oqb_comm* comm, double* d_buf, int64_t count);                                   /* sum, in place */
+int oqb_allgather_obs(oqb_comm* comm, const double* d_send, double* d_recv, int64_t count_per_rank);  /* rank-major */
 
 /* Diagonal observables of a ψ ensemble (populations, ⟨Z_k⟩, energies of a diagonal problem Hamiltonian — what
  * inst_population src/hamiltonian/hamiltonian_base.jl:216-237 reduces to in the computational basis):

@@ -113,6 +113,33 @@ SIGNATURES = {
     "oqb_ensemble_population": [c_void_p, c_int, c_int, c_void_p, c_void_p],
     "oqb_expect_diag": [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p],
     "oqb_expect": [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p],
+    "oqb_ame_get_levels": [c_void_p, c_dp],
+    "oqb_liouv_create": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, C.POINTER(c_void_p)],
+    "oqb_liouv_destroy": [c_void_p],
+    "oqb_liouv_add_davies_ohmic": [c_void_p, c_int, c_int, C.c_double, C.c_double, C.c_double, c_int, C.c_double, C.c_double, c_void_p],
+    "oqb_liouv_add_davies_fn": [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p],
+    "oqb_liouv_add_onesided_ohmic": [c_void_p, c_int, c_i32p, c_i32p, C.c_double, C.c_double, C.c_double, c_int, C.c_double,
+                                     C.c_double, c_void_p],
+    "oqb_liouv_add_onesided_fn": [c_void_p, c_int, c_i32p, c_i32p, c_void_p, c_void_p, c_void_p, c_void_p],
+    "oqb_liouv_set_plan_cache": [c_void_p, c_int],
+    "oqb_liouv_rhs": [c_void_p, c_int, c_dp, c_int, c_void_p, c_void_p],
+    "oqb_liouv_rhs_host": [c_void_p, c_int, c_dp, c_int, c_void_p, c_void_p],
+    "oqb_liouv_update_cache": [c_void_p, c_dp, c_void_p],
+    "oqb_liouv_prepare": [c_void_p, c_dp, C.POINTER(c_void_p)],
+    "oqb_liouv_stats": [c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), c_dp, c_dp],
+    "oqb_dense_eigen": [c_void_p, c_dp, c_void_p, c_void_p],
+    "oqb_dense_info": [c_void_p, C.POINTER(c_int), C.POINTER(c_int), C.POINTER(c_int), C.POINTER(c_int)],
+    "oqb_expect_sum": [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p],
+    "oqb_nccl_version": [C.POINTER(c_int)],
+    "oqb_comm_unique_id": [c_void_p],
+    "oqb_comm_init_rank": [c_void_p, c_int, c_int, c_void_p, C.POINTER(c_void_p)],
+    "oqb_comm_init_all": [c_int, C.POINTER(c_void_p), C.POINTER(c_void_p)],
+    "oqb_comm_destroy": [c_void_p],
+    "oqb_comm_rank": [c_void_p, C.POINTER(c_int), C.POINTER(c_int)],
+    "oqb_comm_group_start": [],
+    "oqb_comm_group_end": [],
+    "oqb_allreduce_obs": [c_void_p, c_void_p, c_i64],
+    "oqb_allgather_obs": [c_void_p, c_void_p, c_void_p, c_i64],
     "oqb_probe_fp64": [c_void_p, c_dp, c_dp],
     "oqb_profile_begin": [c_void_p],
     "oqb_profile_end": [c_void_p, c_dp, C.POINTER(C.c_uint64), c_dp],

@@ -419,6 +419,16 @@ int oqb_ame_set_tables(oqb_ame* a, const void* h_Cm, const double* h_Wt_re, cons
     return 0;
 }
 
+int oqb_ame_get_levels(oqb_ame* a, double* h_w) {
+    OQB_DEVICE(a, a->ctx);
+    oqb_ctx* c = a->ctx;
+    if (!a->have_eigen) return set_error(c, OQB_EINVAL, "oqb_ame_get_levels: call oqb_ame_set_eigen first");
+    if (!h_w) return set_error(c, OQB_EINVAL, "oqb_ame_get_levels: null output");
+    OQB_CUDA(c, cudaMemcpyAsync(h_w, a->d_w, (size_t)a->lvl * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    OQB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
 int oqb_ame_get_rotated_couplings(oqb_ame* a, void* h_A) {
     OQB_DEVICE(a, a->ctx);
     oqb_ctx* c = a->ctx;

@@ -1,6 +1,7 @@
 // Shared declarations for the B200-native OpenQuantumBase RHS library (sm_100a only).
 #pragma once
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 #include <atomic>
 #include <cstdint>
 #include <cstdio>
@@ -68,9 +69,20 @@ struct Ctx {
     // grow-only device staging for the *_host entry points (double-buffered u / du chunks)
     void* io = nullptr;
     size_t io_bytes = 0;
+    // cuSOLVER handle of the device eigensolver (liouvillian.cu; the library is bound with dlopen on first use)
+    void* cusolver = nullptr;
+    void (*cusolver_destroy)(void*) = nullptr;
 };
 
 int set_error(Ctx* c, int code, const char* fmt, ...);
+
+struct EntryScope {
+    EntryScope(const Ctx* c, const char* name) {
+        if (c) cudaSetDevice(c->device);
+        nvtxRangePushA(name);
+    }
+    ~EntryScope() { nvtxRangePop(); }
+};
 
 // Brackets one launch of a path's dominant kernel with a CUDA-event pair while profiling is on
 // (oqb_profile_begin/end); `work` is the launch's algorithmic flops or bytes.
@@ -112,11 +124,9 @@ int coef_upload(Ctx* c, const void* host, size_t bytes, void** dptr);  // async 
                                   cudaGetErrorString(_e), __FILE__, __LINE__);                 \
     } while (0)
 
-// Several devices per process: every extern "C" entry point selects the GPU of the context it was handed.
-#define OQB_DEVICE(handle, ctxexpr)                     \
-    do {                                                \
-        if (handle) cudaSetDevice((ctxexpr)->device);   \
-    } while (0)
+// First statement of every extern "C" entry point: selects the GPU of the context it was handed (several devices per
+// process) and brackets the call with an NVTX range named after the entry point (visible in Nsight Systems / ncu --nvtx).
+#define OQB_DEVICE(handle, ctxexpr) oqb::EntryScope _oqb_entry((handle) ? (const oqb::Ctx*)(ctxexpr) : nullptr, __func__)
 
 #define OQB_TRY(expr)            \
     do {                         \

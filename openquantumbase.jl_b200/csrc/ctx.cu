@@ -123,6 +123,7 @@ int oqb_destroy(oqb_ctx* c) {
     if (!c) return OQB_OK;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    if (c->cusolver && c->cusolver_destroy) c->cusolver_destroy(c->cusolver);
     if (c->ws) cudaFree(c->ws);
     if (c->io) cudaFree(c->io);
     if (c->pin) cudaFreeHost(c->pin);

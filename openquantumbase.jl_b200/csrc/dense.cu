@@ -310,6 +310,17 @@ int oqb_dense_destroy(oqb_dense* op) {
     return OQB_OK;
 }
 
+oqb_ctx* oqb_dense_ctx(const oqb_dense* op) { return op ? op->ctx : nullptr; }
+
+int oqb_dense_info(const oqb_dense* op, int* n, int* nterms, int* K, int* terms_real) {
+    if (!op) return OQB_EINVAL;
+    if (n) *n = op->n;
+    if (nterms) *nterms = op->nterms;
+    if (K) *K = op->K;
+    if (terms_real) *terms_real = op->terms_real ? 1 : 0;
+    return 0;
+}
+
 int oqb_dense_hamiltonian(oqb_dense* op, int nb, const double* h_coefH, int coef_shared, void* d_out) {
     OQB_DEVICE(op, op->ctx);
     oqb_ctx* c = op->ctx;

@@ -42,6 +42,9 @@ _ENV_OPTIONS = {
 }
 
 
+_SPECTRUM_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int64, C.POINTER(C.c_double), C.POINTER(C.c_double))  # oqb_spectrum_fn
+
+
 class Context:
     """One CUDA stream + workspace (oqb_ctx).  Not thread-safe, like the reference's functors."""
 
@@ -1072,6 +1075,69 @@ class DiffEqLiouvillian:
         return du
 
     # ---- {true,false} -------------------------------------------------------------------
+    def _library_eligible(self):
+        """The whole call can run inside the library (oqb_liouv, csrc/liouvillian.cu): dense Hamiltonian terms, constant
+        couplings, Davies / one-sided terms.  Opt in with `op.library = True` (the C-only path a ccall user gets)."""
+        return (getattr(self, "library", False) and isinstance(self.H, DenseHamiltonian) and not self.adiabatic_frame
+                and all(isinstance(lv, (DaviesGenerator, OneSidedAMELiouvillian)) and isinstance(lv.coupling, ConstantCouplings)
+                        for lv in self.opensys_eig)
+                and sum(isinstance(lv, OneSidedAMELiouvillian) for lv in self.opensys_eig) <= 1)
+
+    def _liouv(self):
+        """The oqb_liouv handle: terms registered once, eigen-systems prepared and cached by the library."""
+        L = self.__dict__.get("_liouv_h")
+        if L is not None:
+            return L
+        from .gaps import _eval
+        lib, ctx = self.ctx.lib, self.ctx
+        coup, slices = [], []
+        for lv in self.opensys_eig:
+            c = [np.asarray(m, dtype=C128) for m in lv.coupling(0.0)]
+            slices.append((len(coup), len(coup) + len(c)))
+            coup += c
+        cbuf = _colmajor_stack(coup)
+        L = C.c_void_p()
+        ctx.check(lib.oqb_liouv_create(ctx.h, self.H._dense_op(), self.lvl, self.digits, self.sigdigits, len(coup),
+                                       cbuf.ctypes.data, C.byref(L)))
+        ctx.check(lib.oqb_liouv_set_plan_cache(L, int(getattr(self, "plan_cache", 8))))
+        keep = self.__dict__.setdefault("_liouv_keep", [])  # callback thunks must outlive the handle
+
+        def thunk(f):  # oqb_spectrum_fn: vectorised evaluation of a host closure at the keys the library asks for
+            def cb(_user, n, w_ptr, out_ptr):
+                w = np.ctypeslib.as_array(w_ptr, shape=(n,))
+                np.ctypeslib.as_array(out_ptr, shape=(n,))[:] = _eval(f, w)
+            fn = _SPECTRUM_FN(cb)
+            keep.append(fn)
+            return C.cast(fn, C.c_void_p)
+        for lv, (c0, c1) in zip(self.opensys_eig, slices):
+            ohmic = isinstance(lv.gamma, OhmicBath) and isinstance(lv.S, (_Zero, QuadraticBSpline))
+            Ssp = lv.S if isinstance(lv.S, QuadraticBSpline) else None
+            sargs = (Ssp.n if Ssp else 0, Ssp.x0 if Ssp else 0.0, Ssp.dx if Ssp else 1.0, Ssp.coef.ctypes.data if Ssp else None)
+            if isinstance(lv, DaviesGenerator):
+                if ohmic:
+                    ctx.check(lib.oqb_liouv_add_davies_ohmic(L, c0, c1 - c0, lv.gamma.eta, lv.gamma.wc, lv.gamma.beta, *sargs))
+                else:
+                    ctx.check(lib.oqb_liouv_add_davies_fn(L, c0, c1 - c0, thunk(lv.gamma), None, thunk(lv.S), None))
+            else:
+                al = np.ascontiguousarray([c0 + a - 1 for a, _ in lv.inds], dtype=np.int32)
+                be = np.ascontiguousarray([c0 + b - 1 for _, b in lv.inds], dtype=np.int32)
+                if isinstance(lv.gamma, dict):
+                    raise NotImplementedError("library mode: per-pair spectra of a one-sided term take the host-orchestrated path")
+                if ohmic:
+                    ctx.check(lib.oqb_liouv_add_onesided_ohmic(L, len(al), al.ctypes.data_as(_lib.c_i32p), be.ctypes.data_as(_lib.c_i32p),
+                                                               lv.gamma.eta, lv.gamma.wc, lv.gamma.beta, *sargs))
+                else:
+                    ctx.check(lib.oqb_liouv_add_onesided_fn(L, len(al), al.ctypes.data_as(_lib.c_i32p), be.ctypes.data_as(_lib.c_i32p),
+                                                            thunk(lv.gamma), None, thunk(lv.S), None))
+        self._liouv_h = L
+        return L
+
+    def liouv_stats(self):
+        """(plans built, cache hits, ms of the last plan preparation, ms of its eigensolver) of the library object."""
+        pb, ch, ms, es = C.c_uint64(), C.c_uint64(), C.c_double(), C.c_double()
+        self.ctx.check(self.ctx.lib.oqb_liouv_stats(self._liouv(), C.byref(pb), C.byref(ch), C.byref(ms), C.byref(es)))
+        return pb.value, ch.value, ms.value, es.value
+
     def clear_plans(self):
         """Drop every cached eigen-system plan (and its device tables)."""
         plans = self.__dict__.get("_plans", {})
@@ -1086,6 +1152,10 @@ class DiffEqLiouvillian:
         plans.clear()
         for _, h in self.__dict__.pop("_handle_pool", []):
             self.ctx.lib.oqb_ame_destroy(h)
+        L = self.__dict__.pop("_liouv_h", None)
+        if L is not None:
+            self.ctx.lib.oqb_liouv_destroy(L)
+            self.__dict__.pop("_liouv_keep", None)
         self._ame, self._ame_s = None, None
 
     def prefetch(self, p, ts: Sequence[float]):
@@ -1107,6 +1177,16 @@ class DiffEqLiouvillian:
     def _prepare_ame(self, s: float, w=None, v=None):
         """Everything that is shared by the batch for one value of s: eigen-system (host LAPACK, the device
         eigensolver when `self.device_eigh` is set, or supplied), gap groups, γ/S tables, device tables."""
+        if w is None and self._library_eligible():
+            # the library assembles H(s), diagonalises it on the device, builds GapIndices and every term table, and caches it
+            row = _coef(self.H.f, _svec(s, 1))
+            plan = C.c_void_p()
+            self.ctx.check(self.ctx.lib.oqb_liouv_prepare(self._liouv(), _lib.dptr(row), C.byref(plan)))
+            wbuf = np.empty(self.lvl, dtype=np.float64)
+            self.ctx.check(self.ctx.lib.oqb_ame_get_levels(plan, _lib.dptr(wbuf)))
+            self._ame, self._ame_s = plan, (s, None)
+            self._w, self._v, self._v_dev, self._plan = wbuf, None, None, {"h": plan, "w": wbuf, "v": None, "v_dev": None, "lvl": self.lvl}
+            return
         if w is None:
             key = (s, None)
         else:  # a supplied eigen-system is keyed by CONTENT (an id() can be recycled by a later array)
@@ -1289,6 +1369,12 @@ class DiffEqLiouvillian:
         io = _HostIO(u, du)
         B = io.u.B
         sv = _svec(p(t), B)
+        if w is None and self._library_eligible():  # one C call: grouping by s, eigen-systems, tables, rotations
+            cf = _coef(self.H.f, sv)
+            self.ctx.check(self.ctx.lib.oqb_liouv_rhs(self._liouv(), B, _lib.dptr(cf), int(sv.size == 1), io.u.ptr, io.du.ptr))
+            for lv in self.opensys:  # :106-108
+                lv(io.du, io.u, p, t)
+            return io.finish()
         if sv.size > 1 and np.any(sv != sv[0]):
             if w is not None:
                 raise ValueError("a supplied (w, v) applies to one s; the batch has several")

@@ -89,6 +89,27 @@ def test_plain_c_host_program(c_demo_exe):
     assert "kernels launched" in out.stdout
 
 
+def test_plain_c_ame_end_to_end(c_liouv_exe):
+    """examples/c_liouv_demo.c — a 6-qubit C3-shaped AME (gap coincidences, degenerate start) through C only: H(s) assembly,
+    device eigensolver, GapIndices, Davies tables and rotations behind oqb_liouv_rhs_host, against a golden file written
+    from the oracle's literal gap loop (tests/golden/make_liouv_golden.py)."""
+    import os
+    import subprocess
+    golden = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "liouv_c_demo.bin")
+    out = subprocess.run([c_liouv_exe, golden], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "c_liouv_demo OK" in out.stdout
+
+
+def test_plain_c_nccl_reduce(c_comm_exe):
+    """examples/c_comm_demo.c — oqb_comm_init_all + oqb_expect_sum + oqb_allreduce_obs from one C process with one context
+    (and one host thread) per visible GPU; with a single GPU the communicator has one rank and the reduce is the identity."""
+    import subprocess
+    out = subprocess.run([c_comm_exe], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "c_comm_demo OK" in out.stdout
+
+
 def test_bath_and_option_entry_points_reject_bad_arguments(Q):
     """Argument checks of the bath routines, the spline table and the handle/option calls added for rows B and (f)-3."""
     ctx = Q.get_context()

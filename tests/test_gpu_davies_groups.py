@@ -223,3 +223,76 @@ def test_small_batches_beyond_grid_limit(Q):
     pick = [0, 1, 65534, 65535, 65536, B - 1]
     ref = np.stack([opo.rhs_with_eig(u[i], O.ODEParams(None, 1.0), 0.5, w, v) for i in pick])
     assert relerr(du[pick], ref) < TOL
+
+
+# ---- the whole call inside the library: oqb_liouv (csrc/liouvillian.cu) ---------------------------------------------
+def _lib_case(Q, q, rng, closures=False, onesided=False):
+    n = 2 ** q
+    Hd = -np.asarray(F.standard_driver(q), dtype=complex)
+    Hp = np.asarray(F.random_ising(q, rng), dtype=complex)
+    coup = z_couplings(q)
+    fs = [lambda s: 1 - s, lambda s: s]
+    bath, ob = Q.Ohmic(1e-4, 4, 16), O.Ohmic(1e-4, 4, 16)
+    g_g, S_g = (ob.spectrum, lambda x: 0.05 * x) if closures else (bath, Q.ZERO_LAMBSHIFT)
+    g_o, S_o = (ob.spectrum, (lambda x: 0.05 * x) if closures else (lambda x: 0.0))
+    Hg, Ho = Q.DenseHamiltonian(fs, [Hd, Hp]), O.DenseHamiltonian(fs, [Hd, Hp])
+    cg = Q.ConstantCouplings(coup, unit="h")
+    co = [2 * np.pi * c for c in coup]
+    if onesided:
+        tg = [Q.DaviesGenerator(Q.ConstantCouplings(coup[:2], unit="h"), g_g, S_g),
+              Q.OneSidedAMELiouvillian(Q.ConstantCouplings(coup[2:4], unit="h"), g_g, S_g, [(1, 1), (2, 2)])]
+        to = [O.DaviesGenerator(co[:2], g_o, S_o), O.OneSidedAMELiouvillian(co[2:4], g_o, S_o, [(1, 1), (2, 2)])]
+    else:
+        tg = [Q.DaviesGenerator(cg, g_g, S_g)]
+        to = [O.DaviesGenerator(co, g_o, S_o)]
+    opg = Q.DiffEqLiouvillian(Hg, tg, [], n)
+    opg.library = True
+    opo = O.DiffEqLiouvillian(Ho, to, [], n)
+    return opg, opo, n
+
+
+@pytest.mark.parametrize("closures", [False, True])
+@pytest.mark.parametrize("onesided", [False, True])
+def test_library_liouvillian_one_call(Q, closures, onesided):
+    """(Op::DiffEqLiouvillian{true,false})(du,u,p,t) entirely behind oqb_liouv_rhs: H(s) assembly, device eigensolver,
+    GapIndices, term tables (device-evaluated Ohmic or C callbacks into host closures), rotations.  The eigen-system comes
+    from another solver than the oracle's LAPACK, so the bound is the gauge-invariant 1e-10 (as test_ame_device_eigensolver)."""
+    rng = np.random.default_rng(41)
+    opg, opo, n = _lib_case(Q, 5, rng, closures, onesided)
+    pg, po = Q.ODEParams(None, 10.0), O.ODEParams(None, 10.0)
+    u = np.stack([F.random_density_matrix(n, rng) for _ in range(5)])
+    # per-member s, interleaved: members 0,2,4 share s = 0.3; 1,3 share s = 0.7 (gather/scatter inside the library)
+    t = np.array([3.0, 7.0, 3.0, 7.0, 3.0])
+    du = opg(np.zeros_like(u), u, pg, t)
+    ref = np.stack([opo.rhs(x, po, tt) for x, tt in zip(u, t)])
+    assert relerr(du, ref) < 1e-10
+    built, hits, ms, eig_ms = opg.liouv_stats()
+    assert built == 2 and hits == 0
+    du2 = opg(np.zeros_like(u), u, pg, t)          # both eigen-systems come from the cache now
+    assert np.array_equal(du2, du)
+    assert opg.liouv_stats()[:2] == (2, 2)
+    # shared s, host buffers, update_cache!
+    du3 = opg(np.zeros_like(u), u, pg, 3.0)
+    assert relerr(du3, np.stack([opo.rhs(x, po, 3.0) for x in u])) < 1e-10
+    uh = np.ascontiguousarray(u.transpose(0, 2, 1)); duh = np.zeros_like(uh)
+    cf = np.ascontiguousarray([[0.7, 0.3]] * 5)
+    import oqb_b200._lib as _l
+    ctx = Q.get_context()
+    ctx.check(ctx.lib.oqb_liouv_rhs_host(opg._liouv(), 5, _l.dptr(cf), 0, uh.ctypes.data, duh.ctypes.data))
+    assert relerr(duh.transpose(0, 2, 1), du3) < 1e-14
+    if not onesided:
+        cache = opg.update_cache(np.zeros((n, n), complex), pg, 3.0)
+        assert relerr(cache, opo.update_cache(po, 3.0)) < 1e-10
+
+
+def test_library_liouvillian_degenerate_start(Q):
+    """The anneal's starting point through the one-call path: s = 0 (H = −ΣX, binomially degenerate, dense gap groups) and
+    the first stage times after it."""
+    rng = np.random.default_rng(43)
+    opg, opo, n = _lib_case(Q, 6, rng)
+    u = np.stack([F.random_density_matrix(n, rng) for _ in range(2)])
+    pg, po = Q.ODEParams(None, 10.0), O.ODEParams(None, 10.0)
+    for t in (0.0, 1e-8, 0.05):
+        du = opg(np.zeros_like(u), u, pg, t)
+        ref = np.stack([opo.rhs(x, po, t) for x in u])
+        assert relerr(du, ref) < 1e-10, t

@@ -203,6 +203,16 @@ def test_c_abi_header_is_plain_c_and_links(c_demo_exe):
         assert out.returncode == 3 and "no CPU fallback" in out.stderr
 
 
+def test_c_only_examples_compile(c_liouv_exe, c_comm_exe):
+    """The C-only AME and NCCL demos build against include/oqb.h with -Wall -Werror; without a GPU they stop at oqb_create."""
+    import subprocess
+    import torch
+    if not torch.cuda.is_available():
+        for exe in (c_liouv_exe, c_comm_exe):
+            out = subprocess.run([exe], capture_output=True, text=True)
+            assert out.returncode == 3 and "no CPU fallback" in out.stderr
+
+
 def test_quadratic_bspline_host_coefficients():
     """Host mirror of construct_interpolations (interpolation.jl:22-34): banded prefilter solve and the vectorised
     evaluation agree with the oracle's dense restatement; linear data is reproduced (test/interpolations.jl:3-17)."""
