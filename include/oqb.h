@@ -386,6 +386,17 @@ int oqb_traj_jump(oqb_sparse* sp, int nb, const double* h_gamma, int gamma_share
                   const double* d_uniform, const uint8_t* d_mask, int32_t* d_choice, double* d_prob,
                   int apply);
 
+/* resample (src/opensys/trajectory_jump.jl:81-88): when `opensys` / `opensys_eig` holds several Liouvillians, each proposes
+ * one jump operator (its own oqb_traj_jump / oqb_ame_jump with its own uniform) and the winner is drawn with the weights
+ * ‖L_m ψ‖ (first power).  oqb_traj_apply_choice: norm[b] = ‖L_{choice[b]} ψ_b‖ for the operators of `sp` (d_norm may be
+ * NULL) and, when apply != 0, ψ_b ← L_kψ_b/‖L_kψ_b‖ where d_mask[b] != 0.  oqb_resample: pick[b] = sample(1:M,
+ * Weights(weight[:, b])) with the supplied uniform (StatsBase's inverse-CDF scan); d_weight is M×nb, row m = the
+ * candidates of Liouvillian m; pick = −1 where d_mask[b] == 0. */
+int oqb_traj_apply_choice(oqb_sparse* sp, int nb, void* d_psi, const int32_t* d_choice, const uint8_t* d_mask,
+                          double* d_norm, int apply);
+int oqb_resample(oqb_ctx* ctx, int nb, int M, const double* d_weight, const double* d_uniform, const uint8_t* d_mask,
+                 int32_t* d_pick);
+
 /* --------------------------------------------- on-device trajectory stepping */
 /* One xoshiro256++ stream per trajectory (the algorithm of Julia's default RNG; Float64 = (x >>> 11)·2⁻⁵³):
  * d_state is nb×4 uint64 in device memory, state-in/state-out.  oqb_traj_rng_init fills it from one seed

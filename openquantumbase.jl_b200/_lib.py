@@ -106,6 +106,8 @@ SIGNATURES = {
     "oqb_traj_matvec_host": [c_void_p, c_int, c_dp, c_int, c_dp, c_int, c_void_p, c_void_p],
     "oqb_traj_norm2": [c_void_p, c_int, c_void_p, c_void_p],
     "oqb_traj_jump": [c_void_p, c_int, c_dp, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int],
+    "oqb_traj_apply_choice": [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int],
+    "oqb_resample": [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p],
     "oqb_traj_rng_init": [c_void_p, c_int, C.c_uint64, c_void_p],
     "oqb_traj_rng_uniform": [c_void_p, c_int, c_void_p, c_void_p],
     "oqb_traj_evolve": [c_void_p, c_int, c_int, C.c_double, c_dp, c_int, c_dp, c_int, c_void_p, c_void_p, c_void_p,

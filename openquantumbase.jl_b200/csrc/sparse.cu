@@ -430,6 +430,67 @@ __global__ void __launch_bounds__(512) traj_jump_kernel(int n, int nb, TermList 
     }
 }
 
+// resample (src/opensys/trajectory_jump.jl:81-88) needs ‖L_k ψ‖ of the operator each Liouvillian proposed, and the winner is
+// applied afterwards: norm[b] = ‖L_{choice[b]} ψ_b‖ and, when apply != 0, ψ_b ← L_kψ_b/‖L_kψ_b‖ (members with mask 0 or a
+// negative choice are skipped).  ψ staged in shared memory, fixed-order reduction.
+__global__ void __launch_bounds__(512) traj_apply_choice_kernel(int n, int nb, TermList tl, c128* __restrict__ psi,
+                                                                const int32_t* __restrict__ choice,
+                                                                const unsigned char* __restrict__ mask, double* __restrict__ norm,
+                                                                int apply) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    c128* sp = reinterpret_cast<c128*>(smem_raw);
+    __shared__ double red[32];
+    __shared__ double s_n2;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    for (int b = blockIdx.x; b < nb; b += gridDim.x) {
+        const int k = choice[b];
+        if ((mask && !mask[b]) || k < 0 || k >= tl.count) continue;
+        c128* pb = psi + (size_t)b * n;
+        __syncthreads();
+        for (int r = threadIdx.x; r < n; r += blockDim.x) sp[r] = pb[r];
+        __syncthreads();
+        double s = 0.0;
+        for (int r = threadIdx.x; r < n; r += blockDim.x) {
+            const c128 y = term_row(tl.t[k], sp, r, n);
+            s = fma(y.x, y.x, s);
+            s = fma(y.y, y.y, s);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) red[warp] = s;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double a = 0.0;
+            for (int i = 0; i < nwarp; ++i) a += red[i];
+            s_n2 = a;
+            if (norm) norm[b] = sqrt(a);
+        }
+        __syncthreads();
+        if (apply) {
+            const double nrm = s_n2 > 0.0 ? 1.0 / sqrt(s_n2) : 0.0;
+            for (int r = threadIdx.x; r < n; r += blockDim.x) {
+                const c128 y = term_row(tl.t[k], sp, r, n);
+                pb[r] = make_double2(y.x * nrm, y.y * nrm);
+            }
+        }
+    }
+}
+
+// pick[b] = StatsBase.sample(1:M, Weights(w[:, b])) with the supplied uniform: t = u·Σw; scan left to right
+__global__ void resample_kernel(int nb, int M, const double* __restrict__ w, const double* __restrict__ uniform,
+                                const unsigned char* __restrict__ mask, int32_t* __restrict__ pick) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nb) return;
+    if (mask && !mask[b]) { pick[b] = -1; return; }
+    double total = 0.0;
+    for (int m = 0; m < M; ++m) total += w[(size_t)m * nb + b];
+    const double t = uniform[b] * total;
+    int i = 0;
+    double cw = w[b];
+    while (cw < t && i < M - 1) { ++i; cw += w[(size_t)i * nb + b]; }
+    pick[b] = i;
+}
+
 // K8 for diagonal jump operators (e.g. Z_k dephasing): no gathers, so ψ never touches shared memory — every
 // thread keeps its R rows in registers, the K norms are reduced by a fixed-order shuffle tree, and the
 // selected operator is applied from registers.  DRAM traffic: 16n read (+16n written when applied).
@@ -992,6 +1053,40 @@ int oqb_traj_jump(oqb_sparse* sp, int nb, const double* h_gamma, int gamma_share
         traj_jump_kernel<false><<<grid, threads, 0, c->stream>>>(n, nb, tl, (const double*)d_gamma, gamma_shared ? 0 : K,
                                                                  (c128*)d_psi, d_uniform, d_mask, d_choice, d_prob, apply);
     }
+    OQB_LAUNCH_CHECK(c);
+    return 0;
+}
+
+int oqb_traj_apply_choice(oqb_sparse* sp, int nb, void* d_psi, const int32_t* d_choice, const uint8_t* d_mask, double* d_norm,
+                          int apply) {
+    OQB_DEVICE(sp, sp->ctx);
+    oqb_ctx* c = sp->ctx;
+    if (nb <= 0) return 0;
+    if (sp->K <= 0) return set_error(c, OQB_EINVAL, "oqb_traj_apply_choice: no Lindblad operators");
+    if (!d_psi || !d_choice) return set_error(c, OQB_EINVAL, "oqb_traj_apply_choice: null argument");
+    const int n = sp->n, K = sp->K;
+    std::vector<const TermDev*> ts;
+    for (int k = 0; k < K; ++k) ts.push_back(&sp->l_terms[k]);
+    TermList tl;
+    OQB_TRY(term_list(ts, tl, c));
+    const size_t smem = (size_t)n * sizeof(c128);
+    if (smem > 200 * 1024) return set_error(c, OQB_EINVAL, "oqb_traj_apply_choice: n = %d exceeds the shared-memory staging (12 800 levels)", n);
+    static DevOnce cfg;
+    if (!cfg.done(c->device)) { OQB_CUDA(c, cudaFuncSetAttribute(traj_apply_choice_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); cfg.set(c->device); }
+    const int threads = n >= 2048 ? 512 : (n >= 256 ? 256 : 64);
+    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (200 * 1024) / (smem + 8 * 1024)));
+    const int grid = std::min(nb, sm_count(c) * per_sm);
+    traj_apply_choice_kernel<<<grid, threads, smem, c->stream>>>(n, nb, tl, (c128*)d_psi, d_choice, d_mask, d_norm, apply);
+    OQB_LAUNCH_CHECK(c);
+    return 0;
+}
+
+int oqb_resample(oqb_ctx* c, int nb, int M, const double* d_weight, const double* d_uniform, const uint8_t* d_mask, int32_t* d_pick) {
+    if (!c) return OQB_EINVAL;
+    OQB_DEVICE(c, c);
+    if (nb <= 0) return 0;
+    if (M <= 0 || !d_weight || !d_uniform || !d_pick) return set_error(c, OQB_EINVAL, "oqb_resample: bad arguments");
+    resample_kernel<<<(nb + 255) / 256, 256, 0, c->stream>>>(nb, M, d_weight, d_uniform, d_mask, d_pick);
     OQB_LAUNCH_CHECK(c);
     return 0;
 }

@@ -52,6 +52,17 @@ class ConstDaviesGenerator:
         _axpy(self.ctx, tmp, io.du)
         return io.finish()
 
+    def ame_jump(self, psi: DeviceBatch, uniforms, mask=None, apply=False):
+        """ame_jump(D::ConstDaviesGenerator, u, _, _), src/opensys/trajectory_jump.jl:53-56: prob_k = real(u'L_k'L_ku) for the
+        precomputed operators (√γ already inside), sample(D.Linds, Weights(prob)) with the supplied uniforms; returns
+        (choice[B], prob[B, K]) device tensors.  apply=True performs ψ ← L_kψ/‖L_kψ‖."""
+        from .host import JumpOperators
+        if getattr(self, "_jump", None) is None:
+            self._jump = JumpOperators(self.Linds, self.ctx)
+        out = self._jump.jump(psi, np.ones((1, len(self.Linds))), uniforms, mask, apply)
+        self.ctx.sync()
+        return out
+
     def update_cache(self, cache, *_):
         """update_cache!(cache, D, _, _) = cache .+= D.A  (:119)."""
         io = _HostIO(cache, cache)

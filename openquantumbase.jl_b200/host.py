@@ -1315,27 +1315,33 @@ class DiffEqLiouvillian:
         return {"h": h, "w": w, "v": (None if dev_eig is not None else v),
                 "v_dev": dev_eig[1] if dev_eig is not None else None, "lvl": lvl}
 
-    def lindblad_jump(self, psi: "DeviceBatch", p, t, uniforms, mask=None, apply=False, w=None, v=None):
+    def lindblad_jump(self, psi: "DeviceBatch", p, t, uniforms, mask=None, apply=False, w=None, v=None, term=0):
         """lindblad_jump(Op::DiffEqLiouvillian{true,false}, u, p, t) src/opensys/trajectory_jump.jl:64-69 → ame_jump
         :14-51 on a batch of state vectors (n × B).  Returns (choice[B] = index into the reference's prob/tag list,
         prob[B, nslots]); `jump_operator(choice)` rebuilds the matrix the reference returns.  apply=True performs the
         ψ ← Lψ/‖Lψ‖ of the external affect! in place."""
         import torch
         from .gaps import _eval, jump_slots
-        if not self.diagonalization or len(self.opensys_eig) != 1 or not isinstance(self.opensys_eig[0], DaviesGenerator):
-            raise NotImplementedError("lindblad_jump{true,false}: one DaviesGenerator (resample over several is not on the device path)")
+        if not self.diagonalization or not isinstance(self.opensys_eig[term], DaviesGenerator):
+            raise NotImplementedError("lindblad_jump{true,false}: ame_jump is defined for DaviesGenerator terms (src/opensys/trajectory_jump.jl:14)")
         s = float(np.atleast_1d(p(t))[0])
         self._prepare_ame(s, w, v)
-        if "jump" not in self._plan:
-            K = len(self.opensys_eig[0].coupling(s))
+        jumps = self._plan.setdefault("jump", {})
+        if term not in jumps:  # probability slots of THIS generator: its couplings sit at [c0, c1) of the handle
+            c0 = sum(len(lv.coupling(s)) for lv in self.opensys_eig[:term])
+            K = len(self.opensys_eig[term].coupling(s))
             ptr, terms, rkey, tags = jump_slots(self._w, K, self.digits, self.sigdigits)
             uq, inv = np.unique(rkey, return_inverse=True)
-            rate = np.ascontiguousarray(_eval(self.opensys_eig[0].gamma, uq)[inv])
+            rate = np.ascontiguousarray(_eval(self.opensys_eig[term].gamma, uq)[inv])
             terms = np.ascontiguousarray(terms)
+            terms[:, 0] += c0
+            jumps[term] = (ptr, terms, rate, [(c0 + i, r_, c_) for i, r_, c_ in tags])
+        ptr, terms, rate, tags = jumps[term]
+        if self._plan.get("jump_installed") != term:
             self.ctx.check(self.ctx.lib.oqb_ame_set_jump(self._ame, len(rate), ptr.ctypes.data_as(_lib.c_i64p),
                                                          terms.ctypes.data_as(_lib.c_i32p), _lib.dptr(rate)))
-            self._plan["jump"] = (tags, rate)
-        self._jump_tags, self._jump_rate = self._plan["jump"]
+            self._plan["jump_installed"] = term
+        self._jump_tags, self._jump_rate = tags, rate
         B, ns = psi.B, len(self._jump_rate)
         dev = psi.t.device
         u_d = torch.as_tensor(np.asarray(uniforms, dtype=np.float64), device=dev)
@@ -1648,6 +1654,126 @@ class TrajectoryEnsemble:
             C.c_void_p(prob.data_ptr()), int(apply)))
         self.ctx.sync()
         return choice, prob
+
+
+class JumpOperators:
+    """A set of (sparse) jump operators on the device without a Hamiltonian: the candidates of one Liouvillian for
+    lind_jump / ame_jump(::ConstDaviesGenerator) and `resample` (src/opensys/trajectory_jump.jl:2-12, :53-56, :81-88)."""
+
+    def __init__(self, Ls, ctx: Optional[Context] = None):
+        import scipy.sparse as sps
+        self.ctx = ctx or get_context()
+        lm = [sps.csc_matrix(sps.csc_matrix(L).astype(C128)) for L in Ls]
+        for m in lm:
+            m.sort_indices()
+        n = lm[0].shape[0]
+        self.n, self.K = n, len(lm)
+        empty = sps.csc_matrix((n, n), dtype=C128)
+        cp, rv, nz, off = SparseHamiltonian._pack([empty])
+        lcp, lrv, lnz, loff = SparseHamiltonian._pack(lm)
+        i64 = lambda a: a.ctypes.data_as(_lib.c_i64p)
+        h = C.c_void_p()
+        self.ctx.check(self.ctx.lib.oqb_sparse_create(self.ctx.h, n, 1, i64(cp), i64(rv), nz.ctypes.data, i64(off), self.K,
+                                                      i64(lcp), i64(lrv), lnz.ctypes.data, i64(loff), C.byref(h)))
+        self.h = h
+
+    def jump(self, psi: "DeviceBatch", gamma, uniforms, mask=None, apply=False):
+        """prob[b,k] = γ_k‖L_kψ_b‖², choice by the inverse-CDF scan with `uniforms`; returns (choice, prob) device tensors."""
+        import torch
+        B, dev = psi.B, psi.t.device
+        g = np.ascontiguousarray(np.atleast_2d(np.asarray(gamma, dtype=np.float64)))
+        u_d = torch.as_tensor(np.asarray(uniforms, dtype=np.float64), device=dev)
+        m_d = None if mask is None else torch.as_tensor(np.asarray(mask, dtype=np.uint8), device=dev)
+        choice = torch.zeros(B, dtype=torch.int32, device=dev)
+        prob = torch.zeros((B, self.K), dtype=torch.float64, device=dev)
+        self.ctx.check(self.ctx.lib.oqb_traj_jump(self.h, B, _lib.dptr(g), int(g.shape[0] == 1), psi.ptr, C.c_void_p(u_d.data_ptr()),
+                                                  None if m_d is None else C.c_void_p(m_d.data_ptr()), C.c_void_p(choice.data_ptr()),
+                                                  C.c_void_p(prob.data_ptr()), int(apply)))
+        return choice, prob
+
+    def apply_choice(self, psi: "DeviceBatch", choice, mask=None, apply=False):
+        """‖L_{choice[b]}ψ_b‖ (device tensor) and, with apply=True, ψ_b ← L_kψ_b/‖L_kψ_b‖ where mask[b]."""
+        import torch
+        out = torch.zeros(psi.B, dtype=torch.float64, device=psi.t.device)
+        self.ctx.check(self.ctx.lib.oqb_traj_apply_choice(self.h, psi.B, psi.ptr, C.c_void_p(choice.data_ptr()),
+                                                          None if mask is None else C.c_void_p(mask.data_ptr()),
+                                                          C.c_void_p(out.data_ptr()), int(apply)))
+        return out
+
+
+def resample(ctx: Context, weights, uniforms, mask=None):
+    """resample (src/opensys/trajectory_jump.jl:81-88) on the device: weights (M, B) = ‖L_m ψ_b‖ of the operator each
+    Liouvillian proposed; returns pick[B] (int32 device tensor, −1 where masked out)."""
+    import torch
+    M, B = weights.shape
+    dev = weights.device
+    u_d = torch.as_tensor(np.asarray(uniforms, dtype=np.float64), device=dev)
+    pick = torch.zeros(B, dtype=torch.int32, device=dev)
+    w = weights.contiguous()
+    ctx.check(ctx.lib.oqb_resample(ctx.h, B, M, C.c_void_p(w.data_ptr()), C.c_void_p(u_d.data_ptr()),
+                                   None if mask is None else C.c_void_p(mask.data_ptr()), C.c_void_p(pick.data_ptr())))
+    return pick
+
+
+def lindblad_jump(op: "DiffEqLiouvillian", psi: "DeviceBatch", p, t, uniforms, mask=None, apply=False, w=None, v=None):
+    """lindblad_jump(Op, u, p, t), src/opensys/trajectory_jump.jl:64-79, for ANY number of Liouvillians in `opensys`
+    ({false,false}: LindbladLiouvillians) or `opensys_eig` ({true,false}: DaviesGenerators): each proposes one operator with
+    its own uniform — uniforms[m] (shape (M+1, B), or (B,) when M = 1) — and `resample` (:81-88) draws the winner with
+    uniforms[M] and the weights ‖L_mψ‖.  Returns (pick[B], choices (M, B)) as numpy arrays; apply=True performs
+    ψ ← Lψ/‖Lψ‖ with the winning operator in place."""
+    import torch
+    ctx = op.ctx
+    B, dev = psi.B, psi.t.device
+    uni = np.atleast_2d(np.asarray(uniforms, dtype=np.float64))
+    m_d = None if mask is None else torch.as_tensor(np.asarray(mask, dtype=np.uint8), device=dev)
+    s = float(np.atleast_1d(p(t))[0])
+    if op.diagonalization:
+        terms = [lv for lv in op.opensys_eig if isinstance(lv, DaviesGenerator)]
+        if len(terms) != len(op.opensys_eig):
+            raise NotImplementedError("lindblad_jump{true,false}: DaviesGenerator terms (ame_jump is not defined for the others either)")
+        M = len(terms)
+        if M == 1:
+            choice, _ = op.lindblad_jump(psi, p, t, uni[0], mask, apply, w, v)
+            return np.zeros(B, dtype=np.int32), choice.cpu().numpy()[None]
+        choices, weights = [], []
+        for m in range(M):
+            c_m, p_m = op.lindblad_jump(psi, p, t, uni[m], mask, False, w, v, term=m)
+            choices.append(c_m)
+            weights.append(torch.sqrt(torch.gather(p_m, 1, c_m.clamp(min=0).long()[:, None])[:, 0]))  # ‖√γ·L ϕ‖ = ‖v√γLv'ψ‖
+        pick = resample(ctx, torch.stack(weights), uni[M], m_d)
+        if apply:
+            for m in range(M):
+                mm = (pick == m).to(torch.uint8).cpu().numpy()
+                if mm.any():
+                    op.lindblad_jump(psi, p, t, uni[m], mm, True, w, v, term=m)
+        ctx.sync()
+        return pick.cpu().numpy(), torch.stack(choices).cpu().numpy()
+    linds = op._lind
+    if len(linds) != len(op.opensys):
+        raise NotImplementedError("lindblad_jump{false,false}: LindbladLiouvillian terms only (lind_jump, :2-12)")
+    M = len(linds)
+    sets = op.__dict__.setdefault("_jump_sets", {})
+    choices, weights, ops = [], [], []
+    for m, lind in enumerate(linds):
+        if lind.time_dependent:
+            js = JumpOperators(lind.operators(s), ctx)
+        else:
+            js = sets.get(m) or sets.setdefault(m, JumpOperators(lind.L, ctx))
+        g = lind.gammas(_svec(s, 1))
+        c_m, _ = js.jump(psi, g, uni[m], mask, apply and M == 1)
+        choices.append(c_m)
+        ops.append(js)
+        if M > 1:
+            weights.append(js.apply_choice(psi, c_m, m_d, False))
+    if M == 1:
+        ctx.sync()
+        return np.zeros(B, dtype=np.int32), choices[0].cpu().numpy()[None]
+    pick = resample(ctx, torch.stack(weights), uni[M], m_d)
+    if apply:
+        for m in range(M):
+            ops[m].apply_choice(psi, choices[m], (pick == m).to(torch.uint8), True)
+    ctx.sync()
+    return pick.cpu().numpy(), torch.stack(choices).cpu().numpy()
 
 
 class TrajectoryStepper:

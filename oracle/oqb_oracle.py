@@ -1092,6 +1092,42 @@ def lindblad_jump(op: DiffEqLiouvillian, u, p, t, r: float):
     return lind_jump(op.opensys[0], u, p, s, r)
 
 
+def resample(Ls, u, r: float) -> int:
+    """src/opensys/trajectory_jump.jl:81-88: one candidate → index 0 (no random number drawn); otherwise
+    sample(Ls, Weights([norm(L*u) for L in Ls])) — FIRST power of the norm.  Returns the 0-based index."""
+    if len(Ls) == 1:
+        return 0
+    return sample_weights([float(np.linalg.norm(L @ u)) for L in Ls], r)
+
+
+def lindblad_jump_multi(op: "DiffEqLiouvillian", u, p, t, rs: Sequence[float], w=None, v=None):
+    """lindblad_jump for several Liouvillians (src/opensys/trajectory_jump.jl:64-79): every Liouvillian proposes one jump
+    operator with its own random number rs[m] (lind_jump / ame_jump, in list order), `resample` draws the winner with
+    rs[M].  Returns (winner index m, per-Liouvillian choices, the winning operator matrix)."""
+    s = p(t)
+    cands, choices = [], []
+    if op.opensys_eig:  # {true,false} :64-69
+        if w is None:
+            w, v = haml_eigs(op.H, s, op.lvl)
+        gap_idx = build_gap_indices(w, op.digits, op.sigdigits)
+        for m, lv in enumerate(op.opensys_eig):
+            k, _, Lm = ame_jump(lv, u, gap_idx, v, s, rs[m])
+            choices.append(k); cands.append(Lm)
+    else:  # {false,false} :71-74
+        for m, lv in enumerate(op.opensys):
+            k, _ = lind_jump(lv, u, p, s, rs[m])
+            choices.append(k); cands.append(np.asarray(lv.Ls[k](s), dtype=C128))
+    win = resample(cands, u, rs[len(cands)] if len(cands) > 1 else 0.0)
+    return win, choices, cands[win]
+
+
+def ame_jump_const(D: ConstDaviesGenerator, u, r: float):
+    """ame_jump(D::ConstDaviesGenerator, u, ::Any, ::Any), src/opensys/trajectory_jump.jl:53-56:
+    prob = real(u' L' L u) per precomputed operator; sample(D.Linds, Weights(prob))."""
+    prob = [float(np.real(np.vdot(L @ u, L @ u))) for L in D.Linds]
+    return sample_weights(prob, r), np.array(prob)
+
+
 # --------------------------------------------------------------------------------------
 # the reference's own independent restatements (src/dev_tools.jl) — used to reproduce its tests
 # --------------------------------------------------------------------------------------
