@@ -133,6 +133,45 @@ def cpu_lambda_baseline(Uh, dt, couplings, cf, tf, atol, rtol, nint):
     return time.perf_counter() - t0, ref
 
 
+def run_secondary(Q, torch, ctx):
+    """C2 (8-qubit Lindblad, batch 4096), C4 (12-qubit trajectory ensemble: the XOR-specialised kernel AND the generic kernel
+    on the same operators, plus an unstructured random-pattern Hamiltonian) and C5 (7-qubit Redfield apply, 1024 schedules)
+    in a few steps each — so that these numbers are driver-run, not builder-run.  Details: benchmarks/other_configs.py."""
+    sys.path.insert(0, os.path.join(ROOT, "benchmarks"))
+    import other_configs as OC
+    out = {}
+
+    def short(r, keys):
+        return {k: r[k] for k in keys if k in r}
+    try:
+        r = OC.run_c2(Q, torch, 3, False)
+        out["C2_dephasing_diagL"] = short(r, ("config", "workload", "value", "ms_per_step", "roofline"))
+        torch.cuda.empty_cache()
+        with ctx.option("lindblad_diag", 0):
+            r = OC.run_c2(Q, torch, 2, False)
+        out["C2_general_2plus2K_gemms"] = short(r, ("config", "value", "ms_per_step", "roofline"))
+        torch.cuda.empty_cache()
+    except Exception as e:  # noqa: BLE001
+        out["C2_error"] = f"{type(e).__name__}: {e}"
+    try:
+        r = OC.run_c4(Q, torch, 5)
+        out["C4_traj_xor"] = short(r, ("config", "workload", "value", "ms_per_step", "roofline", "jump_kernel", "evolve"))
+        torch.cuda.empty_cache()
+        out["C4_generic_kernel_same_operators"] = OC.run_c4_matvec_only(Q, torch, 3, generic=True)
+        torch.cuda.empty_cache()
+        out["C4_random_pattern"] = OC.run_c4_matvec_only(Q, torch, 3, random_pattern=True)
+        torch.cuda.empty_cache()
+    except Exception as e:  # noqa: BLE001
+        out["C4_error"] = f"{type(e).__name__}: {e}"
+    try:
+        r = OC.run_c5(Q, torch, 5)
+        out["C5_per_gpu"] = short(r, ("config", "workload", "value", "ms_per_step", "roofline"))
+        torch.cuda.empty_cache()
+    except Exception as e:  # noqa: BLE001
+        out["C5_error"] = f"{type(e).__name__}: {e}"
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -140,6 +179,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the C2/C4/C5 block (N = 1 only)")
     args = ap.parse_args()
     # stdout must carry exactly ONE JSON line: libraries (NCCL's version banner, torch warnings) write to fd 1 at the C
     # level, so the real stdout is kept aside and fd 1 points at stderr for the rest of the run
@@ -301,18 +341,121 @@ def main():
         torch.cuda.synchronize()
         del du_real
 
-    # ---- ensemble-average observable reduce (the only collective of the path), timed separately ----
-    obs_ms = None
+    # ---- ensemble-average observable reduce (the only collective of the path), timed separately: per-GPU partial sums
+    #      (oqb_expect_sum) and ncclAllReduce through the library's own communicator (oqb_comm_*, NCCL bound with dlopen), both on
+    #      the context stream; median of 30 calls after 10 warm-up calls.  torch.distributed's all_reduce on the same
+    #      buffer is timed beside it. ----
+    obs = None
     if world > 1:
-        zs = [np.diag(np.diag(c)) for c in coup[:3]] + [np.eye(N)]
-        ev = Q.expect(zs, u).sum(dim=0)
+        idbuf = [None]
+        if rank == 0:
+            raw = (C.c_char * 128)()
+            ctx.check(lib.oqb_comm_unique_id(raw))
+            idbuf = [bytes(raw)]
+        dist.broadcast_object_list(idbuf, src=0)
+        comm = C.c_void_p()
+        ctx.check(lib.oqb_comm_init_rank(ctx.h, world, rank, idbuf[0], C.byref(comm)))
+        zs = np.stack([np.diag(np.diag(c)) for c in coup[:3]] + [np.eye(N)]).astype(np.complex128)
+        d_obs = torch.as_tensor(zs, device=f"cuda:{local_rank}")  # diagonal: row- and column-major coincide
+        d_out = torch.zeros(8, dtype=torch.float64, device=f"cuda:{local_rank}")
+
+        def reduce_once(with_sum):
+            if with_sum:
+                ctx.check(lib.oqb_expect_sum(ctx.h, N, 4, C.c_void_p(d_obs.data_ptr()), BATCH, u.ptr, 0, C.c_void_p(d_out.data_ptr())))
+            ctx.check(lib.oqb_allreduce_obs(comm, C.c_void_p(d_out.data_ptr()), 8))
+
+        def med_ms(fn, reps=30, warm=10):
+            for _ in range(warm):
+                fn()
+            torch.cuda.synchronize()
+            ts = []
+            for _ in range(reps):
+                a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                dist.barrier()
+                a0.record(); fn(); a1.record()
+                torch.cuda.synchronize()
+                ts.append(a0.elapsed_time(a1))
+            return float(np.median(ts)), float(np.min(ts)), float(np.max(ts))
+        m_all = med_ms(lambda: reduce_once(False))
+        m_sum = med_ms(lambda: reduce_once(True))
+        m_torch = med_ms(lambda: dist.all_reduce(d_out))
+        reduce_once(True)
         torch.cuda.synchronize()
-        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a0.record()
-        dist.all_reduce(ev)
-        a1.record()
+        ref = Q.expect(list(zs), u).sum(dim=0)  # per-rank partial sums by the per-member kernel
+        dist.all_reduce(ref)
+        got = torch.view_as_complex(d_out.reshape(4, 2))
+        obs = {"what": "8 doubles (tr(Z_1 rho), tr(Z_2 rho), tr(Z_3 rho), tr rho summed over the ensemble)",
+               "allreduce_ms_median": m_all[0], "allreduce_ms_min_max": m_all[1:],
+               "expect_sum_plus_allreduce_ms_median": m_sum[0],
+               "torch_distributed_allreduce_ms_median": m_torch[0], "calls": 30, "warmup_calls": 10,
+               "rel_diff_vs_torch_path": float((got - ref).abs().max().item() / ref.abs().max().item())}
+        ctx.check(lib.oqb_comm_destroy(comm))
+
+    # ---- what the host can feed: every rank copies 1 GiB pinned host <-> device in both directions AT THE SAME TIME (the
+    #      end-to-end leg moves 1 GiB each way per rank per step); e2e is then readable as a fraction of this link ----
+    link = None
+    try:
+        nbytes = 1 << 30
+        hb_in = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+        hb_out = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+        db_in = torch.empty(nbytes, dtype=torch.uint8, device=f"cuda:{local_rank}")
+        db_out = torch.empty(nbytes, dtype=torch.uint8, device=f"cuda:{local_rank}")
+        s_up, s_dn = torch.cuda.Stream(), torch.cuda.Stream()
+        reps = 3
+        for it in range(2):  # first pass warms up
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                with torch.cuda.stream(s_up):
+                    db_in.copy_(hb_in, non_blocking=True)
+                with torch.cuda.stream(s_dn):
+                    hb_out.copy_(db_out, non_blocking=True)
+            torch.cuda.synchronize()
+            dt_link = time.perf_counter() - t0
+        per_dir = reps * nbytes / dt_link / 1e9
+        agg = torch.tensor([per_dir, dt_link], dtype=torch.float64, device=f"cuda:{local_rank}")
+        if world > 1:
+            dist.all_reduce(agg, op=dist.ReduceOp.SUM)
+        link = {"what": "concurrent pinned H2D + D2H of 1 GiB per direction on every rank at once (torch copy_ on two streams), GB/s per direction",
+                "this_rank_gbs_per_direction": per_dir, "all_ranks_sum_gbs_per_direction": float(agg[0].item()),
+                "e2e_bytes_per_direction_per_s_GB": e2e_val * N * N * 16 / 1e9,
+                "e2e_fraction_of_link": e2e_val * N * N * 16 / 1e9 / float(agg[0].item())}
+        del hb_in, hb_out, db_in, db_out
+    except Exception as e:  # noqa: BLE001
+        link = {"error": f"{type(e).__name__}: {e}"}
+
+    # ---- like for like with the CPU arm: ONE C call per step does what the reference does per call — H(s) assembly, device
+    #      eigensolver, GapIndices, Davies tables, rotations — for a NEW s every step, with HOST buffers (oqb_liouv_rhs_host) ----
+    lfl = None
+    try:
+        opL = Q.DiffEqLiouvillian(H, [dav], [], N)
+        opL.library = True
+        opL.plan_cache = 2
+        Lh = opL._liouv()
+        cf0 = np.ascontiguousarray([[fA(S_POINT), fB(S_POINT)]])
+        ctx.check(lib.oqb_liouv_rhs_host(Lh, BATCH, cf0.ctypes.data_as(C.POINTER(C.c_double)), 1, C.c_void_p(uh.data_ptr()), C.c_void_p(duh.data_ptr())))
+        lfl_diff = float((duh.to(f"cuda:{local_rank}") - du.t).norm().item() / du.t.norm().item())
+        lsteps = max(2, min(args.steps, 5))
+        barrier()
+        t0 = time.perf_counter()
+        for k in range(lsteps):
+            sk = S_POINT + 0.013 * (k + 1)
+            cfk = np.ascontiguousarray([[fA(sk), fB(sk)]])
+            ctx.check(lib.oqb_liouv_rhs_host(Lh, BATCH, cfk.ctypes.data_as(C.POINTER(C.c_double)), 1, C.c_void_p(uh.data_ptr()), C.c_void_p(duh.data_ptr())))
         torch.cuda.synchronize()
-        obs_ms = a0.elapsed_time(a1)
+        tl = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=f"cuda:{local_rank}")
+        if world > 1:
+            dist.all_reduce(tl, op=dist.ReduceOp.MAX)
+        built, hits, prep_ms, eig_ms = opL.liouv_stats()
+        lfl = {"what": "e2e with a NEW eigen-system every step, everything inside one C call (oqb_liouv_rhs_host): H(s) assembly, device "
+                       "eigensolver (cuSOLVER Dsyevd via dlopen), GapIndices + Ohmic tables on the device, rotations, host buffers — "
+                       "the work the reference's CPU path does per call",
+               "value": world * BATCH * lsteps / float(tl.item()), "unit": UNIT, "steps": lsteps,
+               "plan_prepare_ms_last": prep_ms, "eigensolver_ms_last": eig_ms, "plans_built": built,
+               "rel_diff_vs_host_lapack_plan_at_s0": lfl_diff}
+        opL.clear_plans()
+    except Exception as e:  # noqa: BLE001
+        lfl = {"error": f"{type(e).__name__}: {e}"}
 
     if rank != 0:
         if world > 1:
@@ -339,51 +482,68 @@ def main():
     del za
     dmma_tf, dfma_tf = ctx.probe_fp64()
 
-    achieved = zg_fl.value / (zg_ms.value * 1e-3) / 1e12 if zg_ms.value > 0 else None
+    alg_tflops = zg_fl.value / (zg_ms.value * 1e-3) / 1e12 if zg_ms.value > 0 else None  # 8·M·N·K per complex product
     peak = max(dgemm_tf, dmma_tf)
     mode = C.c_int()
     ctx.check(lib.oqb_get_zgemm_mode(ctx.h, C.byref(mode)))
-    exec_ratio = 0.75 if mode.value == 1 else 1.0  # 3M executes 6·M·N·K of the 8·M·N·K algorithmic flops
     config["eigenvectors"] = ("exactly real (H(s) of this config is real symmetric): the four rotation products skip the zero "
-                              "imaginary part of V; the same step with the general complex product is in "
-                              "roofline.general_complex_eigenvectors" if real_path else "complex (general product)")
+                              "imaginary part of V — the structure row; the contract row (general complex product) is "
+                              "roofline.contract_row" if real_path else "complex (general product)")
+    common = {"bound": "tensor", "peak": peak, "unit": "TFLOP/s",
+              "peak_source": "measured in this run: max(cuBLAS DGEMM 8192^3 best-of-6, DMMA issue probe); MEASURED_PEAKS.json has no FP64 figure",
+              "cublas_dgemm_tflops": dgemm_tf, "cublas_zgemm_4096_tflops": zgemm_tf, "dmma_probe_tflops": dmma_tf,
+              "dfma_probe_tflops": dfma_tf}
+    traffic_profile = {"value_bytes_per_launch": 2.157e9 if real_path else (2.138e9 if mode.value == 1 else 2.163e9),
+                       "from_profile_not_this_run": ("profiles/r1_zgemm_real_ncu.md" if real_path else
+                                                     ("profiles/r1_zgemm_3m_ncu.md" if mode.value == 1 else "profiles/r1_zgemm_tma_ncu.md")),
+                       "algorithmic_bytes_per_launch": 2 * BATCH * N * N * 16 + N * N * 16}
+    kern = {"kernel_ms_per_launch": zg_ms.value / max(zg_n.value, 1), "kernel_launches_timed": zg_n.value,
+            "kernel_share_of_step": zg_ms.value / ms_total if ms_total > 0 else None}
     if real_path:
-        exec_ratio = 0.5  # real eigenvectors: 4·M·N·K executed (re += Vr·Br, im += Vr·Bi)
-    roofline = {"bound": "tensor",
-                "kernel": "zgemm_tma_kernel (FP64 DMMA.8x8x4, TMA-staged, %s; 4 launches of 64 products per step)"
-                          % ("real-operand product: the eigenvector factor of every rotation is exactly real, 2 DMMAs per complex 8x8x4"
-                             if real_path else
-                             ("3-multiplication complex product" if mode.value == 1 else "4-multiplication complex product")),
-                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if achieved else None,
-                "executed_over_algorithmic_flops": exec_ratio,
-                "frac_executed": achieved * exec_ratio / peak if achieved else None,
-                "frac_note": "achieved counts ALGORITHMIC flops (8·M·N·K per complex product, SURVEY 8(d)); the kernel issues "
-                             "only 4·M·N·K (real eigenvectors) or 6·M·N·K (3-multiplication) on the tensor pipe, so frac can exceed "
-                             "1 — frac_executed is the pipe's utilisation; general_complex_eigenvectors holds the same step "
-                             "without the real-eigenvector shortcut",
-                "general_complex_eigenvectors": general,
-                "traffic": 2.157e9 if real_path else (2.138e9 if mode.value == 1 else 2.163e9),
-                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one 64-product launch, ncu --set full, "
-                                  + ("profiles/r1_zgemm_real_ncu.md " if real_path else
-                                     ("profiles/r1_zgemm_3m_ncu.md " if mode.value == 1 else "profiles/r1_zgemm_tma_ncu.md ")) +
-                                  "(algorithmic: 1 GiB read + 1 GiB written + 16 MiB V)",
-                "peak_source": "measured in this run: max(cuBLAS DGEMM 8192^3 best-of-6, DMMA issue probe); MEASURED_PEAKS.json has no FP64 figure",
-                "cublas_dgemm_tflops": dgemm_tf, "cublas_zgemm_4096_tflops": zgemm_tf,
-                "dmma_probe_tflops": dmma_tf, "dfma_probe_tflops": dfma_tf,
-                "kernel_ms_per_launch": zg_ms.value / max(zg_n.value, 1), "kernel_launches_timed": zg_n.value,
-                "kernel_share_of_step": zg_ms.value / ms_total if ms_total > 0 else None,
-                "algorithmic_flops_per_launch": zg_fl.value / max(zg_n.value, 1)}
+        # STRUCTURE ROW (an exploited structure is its own row, never divided into the dense flop count): with an
+        # exactly real eigenvector factor a complex product is 2 real products, so this row's algorithmic work is 4·M·N·K
+        # flops per product (16 n³ per ρ) and frac is the FP64 tensor pipe's utilisation.
+        work = 0.5 * zg_fl.value
+        ach = work / (zg_ms.value * 1e-3) / 1e12 if zg_ms.value > 0 else None
+        roofline = {**common, "row": "structure: real eigenvectors (real-symmetric H), 16 n^3 flops per rho",
+                    "kernel": "zgemm_tma_kernel real-operand variant (FP64 DMMA.8x8x4, TMA-staged, 128x64 CTA, 2 DMMAs per complex 8x8x4; "
+                              "4 launches of 64 products per step)",
+                    "achieved": ach, "frac": ach / peak if ach else None,
+                    "algorithmic_flops_per_launch": work / max(zg_n.value, 1),
+                    "speedup_vs_contract_row": (general["ms_per_step"] / (ms_total / args.steps)) if general else None,
+                    "tflops_if_counted_as_8MNK": alg_tflops, "traffic": None, "traffic_profile": traffic_profile, **kern,
+                    "contract_row": None if general is None else {
+                        "row": "contract: general complex product (any complex H), 32 n^3 algorithmic flops per rho",
+                        "kernel": "zgemm_tma_kernel, 3-multiplication complex product" if mode.value == 1 else "zgemm_tma_kernel, 4-multiplication complex product",
+                        "value_per_gpu": general["value_per_gpu"], "ms_per_step": general["ms_per_step"],
+                        "achieved": general["algorithmic_tflops"], "peak": peak, "unit": "TFLOP/s",
+                        "frac": general["algorithmic_tflops"] / peak,
+                        "executed_over_algorithmic_flops": 0.75 if mode.value == 1 else 1.0,
+                        "frac_executed": general["algorithmic_tflops"] * (0.75 if mode.value == 1 else 1.0) / peak,
+                        "frac_note": "achieved counts the ALGORITHMIC 8·M·N·K flops per complex product; the 3-multiplication kernel issues "
+                                     "6·M·N·K on the tensor pipe, so frac may exceed 1 — frac_executed is the pipe utilisation",
+                        "rel_diff_vs_structure_row_result": general["rel_diff_real_vs_general_product"]}}
+    else:
+        exec_ratio = 0.75 if mode.value == 1 else 1.0
+        roofline = {**common, "row": "contract: general complex product, 32 n^3 algorithmic flops per rho",
+                    "kernel": "zgemm_tma_kernel (FP64 DMMA.8x8x4, TMA-staged, %s; 4 launches of 64 products per step)"
+                              % ("3-multiplication complex product" if mode.value == 1 else "4-multiplication complex product"),
+                    "achieved": alg_tflops, "frac": alg_tflops / peak if alg_tflops else None,
+                    "executed_over_algorithmic_flops": exec_ratio, "frac_executed": alg_tflops * exec_ratio / peak if alg_tflops else None,
+                    "algorithmic_flops_per_launch": zg_fl.value / max(zg_n.value, 1), "traffic": None, "traffic_profile": traffic_profile, **kern}
 
     # ---- cost of a NEW eigen-system per call (time-dependent H: the reference diagonalises in every RHS call,
     #      src/opensys/diffeq_liouvillian.jl:94-96); shared by the whole batch, reported next to the resident number ----
     prep = {}
     op.plan_cache = 1  # steady state of a time-dependent solve: every call brings a new s, the plan (and its handle) is recycled
-    for mode in ("host_lapack", "device_eigh", "device_eigh_and_tables"):
+    for mode in ("host_lapack", "device_eigh", "device_eigh_and_tables", "library_one_call"):
         op.device_eigh = mode != "host_lapack"
         op.device_tables = mode == "device_eigh_and_tables"
+        op.library = mode == "library_one_call"
+        op.clear_plans()
         best = 1e9
         for k in range(3):
-            s_k = S_POINT + 0.01 * (k + 1) + {"host_lapack": 0.0, "device_eigh": 0.003, "device_eigh_and_tables": 0.006}[mode]
+            s_k = S_POINT + 0.01 * (k + 1) + {"host_lapack": 0.0, "device_eigh": 0.003, "device_eigh_and_tables": 0.006, "library_one_call": 0.008}[mode]
             t0 = time.perf_counter()
             op._prepare_ame(s_k)
             ctx.sync()
@@ -394,10 +554,12 @@ def main():
     # guaranteed across two eigh calls, so compare through host LAPACK's (w, v) for both)
     w_chk, v_chk = Q.haml_eigs(H, S_POINT, N)
     chk = []
+    op.library = False
     for flag in (False, True):
         op.device_eigh, op.device_tables = False, flag
         op.clear_plans()
         chk.append(op.rhs_with_eig(du.zeros_like(), u, p, S_POINT * TF, w_chk, v_chk).t.clone())
+    op.library = False
     prep["device_tables_rel_diff_vs_host_tables"] = float((chk[0] - chk[1]).norm().item() / chk[0].norm().item())
     del chk
     op.device_tables = False
@@ -408,7 +570,9 @@ def main():
                     "new s, shared by the 64-ρ batch; host_lapack = scipy zheevd + numpy grouping/tables on the host cores; "
                     "device_eigh = oqb_dense_hamiltonian + cuSOLVER (torch.linalg.eigh) + oqb_ame_set_eigen_device, tables on the host; "
                     "device_eigh_and_tables = additionally the rounded-gap/Ohmic tables and the gap grouping on the device "
-                    "(oqb_ame_davies_ohmic_begin/finish), only multi-pair group members return to the host")
+                    "(oqb_ame_gaps_build + oqb_ame_add_davies_ohmic: grouping, cross-term lists and tables all on the device); "
+                    "library_one_call = oqb_liouv_prepare: the same with the eigensolver bound inside the library (dlopen cuSOLVER) and "
+                    "no host-language step at all")
     op.device_eigh = False
 
     cpu = None
@@ -417,13 +581,19 @@ def main():
         cpu = {"value": cval, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": "2 rho through the reference-structured per-call AME RHS (eigh + rotations + closed-form Davies), numpy/OpenBLAS; see oracle/cpu_baseline.py"}
 
+    # ---- the other BASELINE.json configurations, measured in the same driver run (N = 1 only; short) ----
+    secondary = None
+    if world == 1 and not args.no_secondary:
+        secondary = run_secondary(Q, torch, ctx)
+
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_total_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64 (complex128)", "data": "synthetic", "config": config,
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": BATCH * N * N * 16, "d2h_bytes_per_step": BATCH * N * N * 16,
                     "steps": e2e_steps, "max_abs_diff_vs_resident": e2e_check},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
-            "setup_s_not_timed": setup_s, "cpus_bound_to_gpu_numa_node": numa, "per_call_eigensystem": prep, "obs_allreduce_ms": obs_ms}
+            "setup_s_not_timed": setup_s, "cpus_bound_to_gpu_numa_node": numa, "per_call_eigensystem": prep, "like_for_like_e2e": lfl, "host_link": link,
+            "obs_allreduce": obs, "secondary": secondary}
     emit(line)
     if world > 1:
         dist.destroy_process_group()

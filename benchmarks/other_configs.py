@@ -19,7 +19,8 @@ sys.path.insert(0, ROOT)
 
 def _exec_ratio():
     """Executed / algorithmic flops of the ZGEMM: 0.75 for the default 3-multiplication complex product (6·M·N·K of 8·M·N·K)."""
-    return 1.0 if os.environ.get("OQB_ZGEMM_3M", "1") == "0" else 0.75
+    import oqb_b200 as Q
+    return 1.0 if Q.get_context().zgemm_mode() == 0 else 0.75
 
 
 def _ame_real(ctx, op):
@@ -94,7 +95,7 @@ def run_c2(Q, torch, steps, dense_L, nq=8, B=4096):
     ms = timed(fn, steps, 3, torch)
     zms, zn, zfl = C.c_double(), C.c_uint64(), C.c_double()
     ctx.check(ctx.lib.oqb_profile_end(ctx.h, C.byref(zms), C.byref(zn), C.byref(zfl)))
-    diag_path = (not dense_L) and os.environ.get("OQB_LINDBLAD_DIAG", "1") != "0"
+    diag_path = (not dense_L) and ctx.get_option("lindblad_diag") != 0
     # general L_k: 2 + 2K GEMMs per rho; diagonal L_k exploited (its own row): 2 GEMMs + one Hadamard pass
     flops = 8.0 * n ** 3 * ((2 if diag_path else 2 + 2 * K)) * B
     dmma, _ = ctx.probe_fp64()
@@ -109,7 +110,7 @@ def run_c2(Q, torch, steps, dense_L, nq=8, B=4096):
             "algorithmic_tflop_per_step": flops / 1e12, "step_tflops": flops / (ms * 1e-3) / 1e12,
             "roofline": {"bound": "tensor", "kernel": "zgemm_tma_kernel", "achieved": ach, "peak": dmma, "unit": "TFLOP/s",
                          "frac": ach / dmma,
-                         "frac_executed": ach * (0.5 if (not dense_L and ctx.real_operand_mode() and os.environ.get("OQB_LINDBLAD_DIAG", "1") != "0")
+                         "frac_executed": ach * (0.5 if (diag_path and ctx.real_operand_mode())
                                                  else _exec_ratio()) / dmma,
                          "kernel_share_of_step": zms.value / ((max(3, 3) + steps) * ms),
                          "peak_source": "DMMA issue probe, this run"}}
@@ -306,7 +307,7 @@ def run_c4(Q, torch, steps):
     st.evolve(psi, pO, 0.0, 0.01, 2)
     ms_ev = timed(lambda: st.evolve(psi, pO, 0.0, 0.01, nst), max(2, steps // 5), 1, torch) / nst
     njump = int(st.njumps.sum().item())
-    fusedrk = os.environ.get("OQB_RK_FUSE", "1") != "0"
+    fusedrk = ctx.get_option("rk_fuse") != 0
     # vector passes per RK4 step: fused stage arithmetic 3+5+5+3 (the norm rides the last stage); unfused 4 matvecs (2 each)
     # + stage kernels 4+5+5+3 + 1 norm pass
     passes = 16 if fusedrk else 26
@@ -328,6 +329,62 @@ def run_c4(Q, torch, steps):
                        "ms_per_rk4_step": ms_ev, "trajectory_steps_per_sec": B / (ms_ev * 1e-3), "jumps_so_far": njump,
                        "vector_passes_per_step": passes, "bytes_moved_model_GB_per_step": moved, "GBs_of_moved_bytes": moved / (ms_ev * 1e-3),
                        "frac_of_measured_hbm": moved / (ms_ev * 1e-3) / hbm}}
+
+
+def random_sparse_c4(nq, per_row=6, seed=4100):
+    """An UNSTRUCTURED 12-qubit SparseHamiltonian: `per_row` random off-diagonal entries per row with random complex values,
+    symmetrised (≈ 2·per_row + 1 = 13 entries per row like the TFIM, but no Pauli/XOR structure), plus a random real diagonal term."""
+    import scipy.sparse as sps
+    n = 1 << nq
+    rng = np.random.default_rng(seed)
+    rows = np.repeat(np.arange(n), per_row)
+    cols = rng.integers(0, n, size=n * per_row)
+    keep = rows != cols
+    vals = rng.standard_normal(n * per_row) + 1j * rng.standard_normal(n * per_row)
+    A = sps.csc_matrix((vals[keep], (rows[keep], cols[keep])), shape=(n, n))
+    Hoff = (A + A.conj().T).tocsc()
+    Hdiag = sps.diags(rng.standard_normal(n)).tocsc().astype(complex)
+    return Hoff, Hdiag
+
+
+def run_c4_matvec_only(Q, torch, steps, generic=False, random_pattern=False):
+    """The C4 ensemble matvec alone: `generic=True` forces the generic kernels on the TFIM operators (option "traj_kernel" = 1),
+    `random_pattern=True` swaps in an unstructured Hamiltonian (no kernel specialisation applies).  HBM roofline fraction of the kernel."""
+    nq, n, B = 12, 4096, 65536
+    ctx = Q.get_context()
+    if random_pattern:
+        Ha, Hb = random_sparse_c4(nq)
+        _, _, Ls = tfim_sparse_c4(nq)
+    else:
+        Ha, Hb, Ls = tfim_sparse_c4(nq)
+    H = Q.SparseHamiltonian([lambda s: 1 - s, lambda s: s], [Ha, Hb], unit="ħ")
+    op = Q.DiffEqLiouvillian(H, [], [Q.LindbladLiouvillian([Q.Lindblad(0.05, L) for L in Ls])], n)
+    ens = Q.TrajectoryEnsemble(op)
+    psi_t = rand_states(torch, B, n, 1, 4000)
+    psi_t = psi_t / torch.linalg.vector_norm(psi_t, dim=2, keepdim=True)
+    psi = Q.DeviceBatch(B, n, 1, ctx, psi_t.contiguous())
+    dpsi = psi.zeros_like()
+    rng = np.random.default_rng(4000)
+    s = rng.random(B)
+    cf = np.ascontiguousarray(np.stack([1 - s, s], axis=1))
+    gam = np.full((1, nq), 0.05)
+    dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    mv = lambda: ctx.check(ctx.lib.oqb_traj_matvec(ens.sp, B, dp(cf), 0, dp(gam), 1, psi.ptr, dpsi.ptr))
+    with ctx.option("traj_kernel", 1 if generic else 0):
+        ms = timed(mv, steps, 3, torch)
+        ctx.check(ctx.lib.oqb_profile_begin(ctx.h))
+        for _ in range(steps):
+            mv()
+        a, b_, w = C.c_double(), C.c_uint64(), C.c_double()
+        ctx.check(ctx.lib.oqb_profile_end(ctx.h, C.byref(a), C.byref(b_), C.byref(w)))
+    kms, kb = a.value / max(b_.value, 1), w.value / max(b_.value, 1)
+    hbm, src = peaks()
+    nnz_row = (Ha.nnz + Hb.nnz) / n
+    return {"workload": f"12-qubit {'UNSTRUCTURED random-pattern' if random_pattern else 'TFIM'} SparseHamiltonian, {B} psi of dim {n}, "
+                        f"{nnz_row:.1f} entries per row, per-trajectory s" + (", generic kernels forced" if generic else ""),
+            "value": B / (ms * 1e-3), "ms_per_step": ms,
+            "roofline": {"bound": "hbm", "achieved": kb / 1e9 / (kms * 1e-3), "peak": hbm, "unit": "GB/s",
+                         "frac": kb / 1e9 / (kms * 1e-3) / hbm, "kernel_ms": kms, "algorithmic_bytes_per_launch": kb, "peak_source": src}}
 
 
 def run_c5(Q, torch, steps):
@@ -389,13 +446,16 @@ def main():
             sys.stderr.write(out.stderr[-2000:])
             print(out.stdout.strip().splitlines()[-1], flush=True)
             continue
-        if c == "c2general":  # same operators, diagonal structure NOT exploited (the env switch is read once per process)
-            import subprocess
-            env = dict(os.environ, OQB_LINDBLAD_DIAG="0")
-            out = subprocess.run([sys.executable, os.path.abspath(__file__), "--configs", "c2", "--steps", str(args.steps)],
-                                 env=env, capture_output=True, text=True)
-            sys.stderr.write(out.stderr[-2000:])
-            print(out.stdout.strip().splitlines()[-1], flush=True)
+        if c == "c2general":  # same operators, diagonal structure NOT exploited
+            with Q.get_context().option("lindblad_diag", 0):
+                r = run_c2(Q, torch, args.steps, False)
+            print(json.dumps(r), flush=True)
+            torch.cuda.empty_cache()
+            continue
+        if c in ("c4generic", "c4random"):
+            r = run_c4_matvec_only(Q, torch, args.steps, generic=c == "c4generic", random_pattern=c == "c4random")
+            print(json.dumps(r), flush=True)
+            torch.cuda.empty_cache()
             continue
         if c == "c2":
             r = run_c2(Q, torch, args.steps, False)

@@ -149,9 +149,9 @@ def test_long_k_real_operand_kernel_vs_numpy(Q):
     op = Q.DiffEqLiouvillian(H, [Q.DaviesGenerator([np.eye(n, dtype=complex)], lambda x: 0.0, lambda x: 0.0)], [], n)
     u = np.stack([rand_c(rng, n, n), lowrank_rho(rng, n)])
     ctx = Q.get_context()
-    rho = np.einsum("ia,bij,jc->bac", v, u, v)  # v' u v (v real)
+    rho = v.T @ u @ v  # v' u v (v real), broadcast over the batch
     X = -1j * (w[None, :, None] - w[None, None, :]) * rho
-    ref = np.einsum("ia,bac,jc->bij", v, X, v)
+    ref = v @ X @ v.T
     for real_op in (1, 0):
         with ctx.option("real_operand", real_op):
             op.clear_plans()
