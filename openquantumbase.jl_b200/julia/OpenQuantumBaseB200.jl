@@ -1,27 +1,33 @@
 # OpenQuantumBaseB200.jl — Julia-side glue for liboqb_b200.so (the C ABI of include/oqb.h).
 #
-# STATUS: Julia is not installed in the build container or on the GPU box, so this file has never
-# been executed.  It is the binding a maintainer adds next to OpenQuantumBase.jl; the equivalent
-# Python `ctypes` binding (openquantumbase.jl_b200/_lib.py + host.py) is what the test-suite runs.
+# STATUS: Julia is not installed in the build container or on the GPU box, so this file has NEVER BEEN EXECUTED.
+# Everything it calls is exercised through the same C entry points by the plain-C programs examples/c_abi_demo.c,
+# examples/c_liouv_demo.c, examples/c_comm_demo.c (compiled and run by the test-suite) and by the ctypes host mirror.
+# The file is deliberately thin: all orchestration the reference does inside an RHS call — H(s) assembly, haml_eigs,
+# GapIndices, cross-term lists, γ/S tables, plan caching, grouping a batch by s, the NCCL reduce — lives in the library
+# (csrc/liouvillian.cu, csrc/ame_terms.cu, csrc/comm.cu); Julia only evaluates the user's closures and passes pointers.
 #
-# It only ADDS METHODS for a new argument type, `DeviceBatch` (an opaque, device-resident
-# n×n×B Array{ComplexF64,3}); no struct of OpenQuantumBase.jl changes:
-#   (H::DenseHamiltonian)(du::DeviceBatch, u::DeviceBatch, p, s)        dense_hamiltonian.jl:84
-#   update_cache!(cache::DeviceBatch, H::DenseHamiltonian, p, s)        dense_hamiltonian.jl:71
-#   (Op::DiffEqLiouvillian{false,false})(du, u, p, t)                   diffeq_liouvillian.jl:70
-#   (Op::DiffEqLiouvillian{true,false})(du, u, p, t)                    diffeq_liouvillian.jl:92
-#   update_cache!(cache, Op::DiffEqLiouvillian, p, t)                   diffeq_liouvillian.jl:78,111
-#   lindblad_jump(Op::DiffEqLiouvillian{false,false}, ψ::DeviceBatch, p, t; uniforms)
+# It only ADDS METHODS for new argument types (no struct of OpenQuantumBase.jl changes):
+#   DeviceBatch  — an opaque device-resident n×n×B (ρ batch) or n×1×B (ψ ensemble) Array{ComplexF64,3}
+#   (H::DenseHamiltonian)(du::DeviceBatch, u::DeviceBatch, p, s)              dense_hamiltonian.jl:84
+#   (H::SparseHamiltonian)(du::DeviceBatch, u::DeviceBatch, p, s)             sparse_hamiltonian.jl:83
+#   update_cache!(cache::DeviceBatch, H, p, s), update_vectorized_cache!       dense_hamiltonian.jl:71,78
+#   (Op::DiffEqLiouvillian{false,false})(du, u, p, t), update_cache!           diffeq_liouvillian.jl:70,78
+#   (Op::DiffEqLiouvillian{true,false})(du, u, p, t), update_cache!            diffeq_liouvillian.jl:92,111
+#   (R::RedfieldLiouvillian)(du, u, p, t) with Λ supplied on the device        redfield.jl:65-68
+#   traj_matvec!(dψ, Op, ψ, p, t), lindblad_jump(Op{false,false}, ψ, p, t; uniforms)   trajectory_jump.jl:71-74
+#   ensemble_expect_allreduce!(comm, out, obs, ψ)                               the ensemble-average reduce (SURVEY §8(e))
 module OpenQuantumBaseB200
 
 using OpenQuantumBase
-import OpenQuantumBase: update_cache!, DenseHamiltonian, DiffEqLiouvillian, LindbladLiouvillian,
-    DaviesGenerator, GapIndices, haml_eigs, OhmicBath, S, correlation
-using LinearAlgebra
+import OpenQuantumBase: update_cache!, update_vectorized_cache!, lindblad_jump, DenseHamiltonian, SparseHamiltonian,
+    DiffEqLiouvillian, LindbladLiouvillian, DaviesGenerator, OneSidedAMELiouvillian, RedfieldLiouvillian,
+    ConstantCouplings, OhmicBath
+using LinearAlgebra, SparseArrays
 
-const LIB = get(ENV, "OQB_B200_LIB", "liboqb_b200.so")
+const LIB = "liboqb_b200.so"   # resolved through the loader path (LD_LIBRARY_PATH / rpath); no environment switches
 
-# ---------------------------------------------------------------- context (one per thread × GPU)
+# ---------------------------------------------------------------- context: one per (thread, GPU)
 const CTX = Dict{Tuple{Int,Int},Ptr{Cvoid}}()
 function ctx(device::Int=0)
     get!(CTX, (Threads.threadid(), device)) do
@@ -31,7 +37,11 @@ function ctx(device::Int=0)
         h[]
     end
 end
-check(c, st) = st == 0 || error(unsafe_string(ccall((:oqb_last_error, LIB), Cstring, (Ptr{Cvoid},), c)))
+lasterr(c) = unsafe_string(ccall((:oqb_last_error, LIB), Cstring, (Ptr{Cvoid},), c))
+check(c, st) = st == 0 ? nothing : error(lasterr(c))
+sync(c=ctx()) = check(c, ccall((:oqb_sync, LIB), Cint, (Ptr{Cvoid},), c))
+set_option(name::String, v::Integer; c=ctx()) =
+    check(c, ccall((:oqb_set_option, LIB), Cint, (Ptr{Cvoid}, Cstring, Int64), c, name, v))
 
 # ---------------------------------------------------------------- device-resident batches
 mutable struct DeviceBatch <: AbstractArray{ComplexF64,3}
@@ -46,20 +56,36 @@ mutable struct DeviceBatch <: AbstractArray{ComplexF64,3}
     end
 end
 Base.size(b::DeviceBatch) = b.dims
+# element access goes through the host (display, tests); bulk transfers use upload!/download!
+function Base.getindex(b::DeviceBatch, i::Int, j::Int, k::Int)
+    v = Ref{ComplexF64}()
+    off = 16 * ((i - 1) + b.dims[1] * ((j - 1) + b.dims[2] * (k - 1)))
+    check(b.c, ccall((:oqb_download, LIB), Cint, (Ptr{Cvoid}, Ref{ComplexF64}, Ptr{Cvoid}, Csize_t), b.c, v, b.ptr + off, 16))
+    v[]
+end
+Base.IndexStyle(::Type{DeviceBatch}) = IndexCartesian()
 upload!(b::DeviceBatch, a::Array{ComplexF64,3}) =
     check(b.c, ccall((:oqb_upload, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{ComplexF64}, Csize_t), b.c, b.ptr, a, sizeof(a)))
 download!(a::Array{ComplexF64,3}, b::DeviceBatch) =
     check(b.c, ccall((:oqb_download, LIB), Cint, (Ptr{Cvoid}, Ptr{ComplexF64}, Ptr{Cvoid}, Csize_t), b.c, a, b.ptr, sizeof(a)))
+DeviceBatch(a::Array{ComplexF64,3}; device=0) = (b = DeviceBatch(size(a); device=device); upload!(b, a); b)
 
-# ---------------------------------------------------------------- operator upload (once per object)
-const DENSE = IdDict{Any,Ptr{Cvoid}}()
-function dev(H::DenseHamiltonian, lind::Union{Nothing,LindbladLiouvillian}=nothing; device=0)
-    get!(DENSE, (H, lind)) do
+# closure values per batch member: coefficient rows are row-major [member][term] in C = column-major term×member here
+batch_s(p, t::Real) = Float64[p(t)]                                  # one annealing parameter for the whole batch
+batch_s(p, t::AbstractVector) = Float64[p(x) for x in t]             # one time per member (schedule sweeps)
+coef_rows(fs, s) = Float64[real(f(sb)) for f in fs, sb in s]
+shared(s) = Cint(length(s) == 1)
+
+# ---------------------------------------------------------------- operators: uploaded once per object, immutable afterwards
+const HANDLES = IdDict{Any,Ptr{Cvoid}}()
+
+function dev(H::DenseHamiltonian, lind::Union{Nothing,LindbladLiouvillian}=nothing; c=ctx())
+    get!(HANDLES, (H, lind)) do
         n = size(H, 1)
-        mats = cat(H.m...; dims=3)                                     # n×n×nterms, already unit-scaled (:38)
-        K = lind === nothing ? 0 : length(lind)
-        lops = K == 0 ? ComplexF64[] : cat([ComplexF64.(L(0.0)) for L in lind.L]...; dims=3)
-        h = Ref{Ptr{Cvoid}}(C_NULL); c = ctx(device)
+        mats = cat([ComplexF64.(m) for m in H.m]...; dims=3)          # already unit-scaled (dense_hamiltonian.jl:38)
+        K = lind === nothing ? 0 : length(lind.L)
+        lops = K == 0 ? ComplexF64[] : cat([ComplexF64.(Matrix(L(0.0))) for L in lind.L]...; dims=3)  # constant L_k
+        h = Ref{Ptr{Cvoid}}(C_NULL)
         check(c, ccall((:oqb_dense_create, LIB), Cint,
                        (Ptr{Cvoid}, Cint, Cint, Ptr{ComplexF64}, Cint, Ptr{ComplexF64}, Ref{Ptr{Cvoid}}),
                        c, n, length(H.m), mats, K, lops, h))
@@ -67,134 +93,264 @@ function dev(H::DenseHamiltonian, lind::Union{Nothing,LindbladLiouvillian}=nothi
     end
 end
 
-batch_s(p, t::Real, B) = fill(Float64(p(t)), 1)                     # shared annealing parameter
-batch_s(p, t::AbstractVector, B) = Float64[p(x) for x in t]         # one time per member (schedule sweeps)
+"concatenated CSC arrays of a list of SparseMatrixCSC{ComplexF64,Int} exactly as Julia stores them (1-based)"
+function pack(ms)
+    colptr = vcat([Int64.(m.colptr) for m in ms]...)
+    rowval = vcat([Int64.(m.rowval) for m in ms]...)
+    nzval = vcat([ComplexF64.(m.nzval) for m in ms]...)
+    off = Int64[0; cumsum([nnz(m) for m in ms])]
+    isempty(rowval) && (rowval = Int64[1]; nzval = ComplexF64[0])
+    colptr, rowval, nzval, off
+end
 
-# ---------------------------------------------------------------- DiffEqLiouvillian{false,false}
+function dev(H::SparseHamiltonian, lind::Union{Nothing,LindbladLiouvillian}=nothing; c=ctx())
+    get!(HANDLES, (H, lind)) do
+        n = size(H, 1)
+        cp, rv, nz, off = pack(H.m)
+        K = lind === nothing ? 0 : length(lind.L)
+        h = Ref{Ptr{Cvoid}}(C_NULL)
+        if K == 0
+            check(c, ccall((:oqb_sparse_create, LIB), Cint,
+                           (Ptr{Cvoid}, Cint, Cint, Ptr{Int64}, Ptr{Int64}, Ptr{ComplexF64}, Ptr{Int64}, Cint, Ptr{Int64}, Ptr{Int64},
+                            Ptr{ComplexF64}, Ptr{Int64}, Ref{Ptr{Cvoid}}),
+                           c, n, length(H.m), cp, rv, nz, off, 0, C_NULL, C_NULL, C_NULL, C_NULL, h))
+        else
+            lcp, lrv, lnz, loff = pack([sparse(ComplexF64.(L(0.0))) for L in lind.L])
+            check(c, ccall((:oqb_sparse_create, LIB), Cint,
+                           (Ptr{Cvoid}, Cint, Cint, Ptr{Int64}, Ptr{Int64}, Ptr{ComplexF64}, Ptr{Int64}, Cint, Ptr{Int64}, Ptr{Int64},
+                            Ptr{ComplexF64}, Ptr{Int64}, Ref{Ptr{Cvoid}}),
+                           c, n, length(H.m), cp, rv, nz, off, K, lcp, lrv, lnz, loff, h))
+        end
+        h[]
+    end
+end
+
+# ---------------------------------------------------------------- Hamiltonians
+function (H::DenseHamiltonian)(du::DeviceBatch, u::DeviceBatch, p, s)                  # du = −i[H(s),u]  (OVERWRITES)
+    sv = s isa Real ? Float64[s] : Float64.(s)
+    check(u.c, ccall((:oqb_dense_rhs, LIB), Cint,
+                     (Ptr{Cvoid}, Cint, Ptr{Float64}, Cint, Ptr{Float64}, Cint, Ptr{Cvoid}, Ptr{Cvoid}),
+                     dev(H), size(u, 3), coef_rows(H.f, sv), shared(sv), C_NULL, 1, u.ptr, du.ptr))
+end
+function update_cache!(cache::DeviceBatch, H::DenseHamiltonian, p, s)                   # cache = −iH(s)
+    sv = s isa Real ? Float64[s] : Float64.(s)
+    check(cache.c, ccall((:oqb_dense_update_cache, LIB), Cint,
+                         (Ptr{Cvoid}, Cint, Ptr{Float64}, Cint, Ptr{Float64}, Cint, Ptr{Cvoid}),
+                         dev(H), size(cache, 3), coef_rows(H.f, sv), shared(sv), C_NULL, 1, cache.ptr))
+end
+function update_vectorized_cache!(cache::DeviceBatch, H::DenseHamiltonian, p, s)        # cache = i(Hᵀ⊗I − I⊗H)
+    sv = s isa Real ? Float64[s] : Float64.(s)
+    check(cache.c, ccall((:oqb_dense_update_vectorized_cache, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}, Cint, Ptr{Cvoid}),
+                         dev(H), size(cache, 3), coef_rows(H.f, sv), shared(sv), cache.ptr))
+end
+function (H::SparseHamiltonian)(du::DeviceBatch, u::DeviceBatch, p, s)
+    sv = s isa Real ? Float64[s] : Float64.(s)
+    check(u.c, ccall((:oqb_sparse_commutator, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}, Cint, Ptr{Cvoid}, Ptr{Cvoid}),
+                     dev(H), size(u, 3), coef_rows(H.f, sv), shared(sv), u.ptr, du.ptr))
+end
+"update_cache!(cache, H::SparseHamiltonian, p, s): the values on the union pattern, as a SparseMatrixCSC (one member)"
+function update_cache!(cache::SparseMatrixCSC{ComplexF64,Int}, H::SparseHamiltonian, p, s::Real; c=ctx())
+    h = dev(H)
+    nnzU = Ref{Int64}(0)
+    check(c, ccall((:oqb_sparse_pattern_nnz, LIB), Cint, (Ptr{Cvoid}, Ref{Int64}), h, nnzU))
+    d = Ref{Ptr{Cvoid}}(C_NULL)
+    check(c, ccall((:oqb_malloc, LIB), Cint, (Ptr{Cvoid}, Csize_t, Ref{Ptr{Cvoid}}), c, 16nnzU[], d))
+    check(c, ccall((:oqb_sparse_update_cache, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}, Cint, Ptr{Float64}, Cint, Ptr{Cvoid}),
+                   h, 1, coef_rows(H.f, Float64[s]), 1, C_NULL, 1, d[]))
+    length(cache.nzval) == nnzU[] || error("cache must have the union sparsity pattern of the terms (sparse_hamiltonian.jl:33-34)")
+    check(c, ccall((:oqb_download, LIB), Cint, (Ptr{Cvoid}, Ptr{ComplexF64}, Ptr{Cvoid}, Csize_t), c, cache.nzval, d[], 16nnzU[]))
+    ccall((:oqb_free, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), c, d[])
+    cache
+end
+
+# ---------------------------------------------------------------- DiffEqLiouvillian{false,false}: H + Lindblad (+ others)
+lindblad_of(Op) = (i = findfirst(x -> x isa LindbladLiouvillian, Op.opensys); i === nothing ? nothing : Op.opensys[i])
+
 function (Op::DiffEqLiouvillian{false,false})(du::DeviceBatch, u::DeviceBatch, p, t)
-    B = size(u, 3); s = batch_s(p, t, B); shared = Cint(length(s) == 1)
-    lind = isempty(Op.opensys) ? nothing : Op.opensys[1]::LindbladLiouvillian
-    coefH = Float64[real(f(sb)) for f in Op.H.f, sb in s]              # nterms × rows (row-major [b][i] in C)
-    gam = lind === nothing ? C_NULL : Float64[g(sb) for g in lind.γ, sb in s]
-    c = u.c
-    check(c, ccall((:oqb_dense_rhs, LIB), Cint,
-                   (Ptr{Cvoid}, Cint, Ptr{Float64}, Cint, Ptr{Float64}, Cint, Ptr{Cvoid}, Ptr{Cvoid}),
-                   dev(Op.H, lind), B, coefH, shared, gam, shared, u.ptr, du.ptr))
+    s = batch_s(p, t)
+    lind = Op.H isa DenseHamiltonian ? lindblad_of(Op) : nothing
+    if Op.H isa DenseHamiltonian
+        gam = lind === nothing ? C_NULL : Float64[g(sb) for g in lind.γ, sb in s]
+        check(u.c, ccall((:oqb_dense_rhs, LIB), Cint,
+                         (Ptr{Cvoid}, Cint, Ptr{Float64}, Cint, Ptr{Float64}, Cint, Ptr{Cvoid}, Ptr{Cvoid}),
+                         dev(Op.H, lind), size(u, 3), coef_rows(Op.H.f, s), shared(s), gam, shared(s), u.ptr, du.ptr))
+    else
+        Op.H(du, u, p, s)                                                # diffeq_liouvillian.jl:72 (s to H …)
+    end
+    for lv in Op.opensys                                                  # :73-75 (… t to the Liouvillians), each ACCUMULATES
+        lv === lind && continue
+        lv(du, u, p, t)
+    end
+    du
 end
 
 function update_cache!(cache::DeviceBatch, Op::DiffEqLiouvillian{false,false}, p, t)
-    B = size(cache, 3); s = batch_s(p, t, B); shared = Cint(length(s) == 1)
-    lind = isempty(Op.opensys) ? nothing : Op.opensys[1]::LindbladLiouvillian
-    coefH = Float64[real(f(sb)) for f in Op.H.f, sb in s]
+    s = batch_s(p, t)
+    lind = lindblad_of(Op)
     gam = lind === nothing ? C_NULL : Float64[g(sb) for g in lind.γ, sb in s]
     check(cache.c, ccall((:oqb_dense_update_cache, LIB), Cint,
                          (Ptr{Cvoid}, Cint, Ptr{Float64}, Cint, Ptr{Float64}, Cint, Ptr{Cvoid}),
-                         dev(Op.H, lind), B, coefH, shared, gam, shared, cache.ptr))
+                         dev(Op.H, lind), size(cache, 3), coef_rows(Op.H.f, s), shared(s), gam, shared(s), cache.ptr))
 end
 
-# ---------------------------------------------------------------- DiffEqLiouvillian{true,false} (Davies)
-# One eigen-system per call, shared by the batch, exactly like the single haml_eigs of :94.
-function (Op::DiffEqLiouvillian{true,false})(du::DeviceBatch, u::DeviceBatch, p, t::Real)
-    s = p(t); c = u.c; n = size(u, 1)
-    w, v = haml_eigs(Op.H, s, Op.lvl)                                   # host LAPACK (:94)
-    D = Op.opensys_eig[1]::DaviesGenerator
-    coup = cat([ComplexF64.(m) for m in D.coupling(s)]...; dims=3)
-    h = Ref{Ptr{Cvoid}}(C_NULL)
-    check(c, ccall((:oqb_ame_create, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Cint, Ptr{ComplexF64}, Ref{Ptr{Cvoid}}),
-                   c, n, length(w), size(coup, 3), coup, h))
-    check(c, ccall((:oqb_ame_set_eigen, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{ComplexF64}), h[], Float64.(w), ComplexF64.(v)))
-    # γ, S at the signed rounded gaps of GapIndices (opensys_util.jl:25-61); cross-term lists for
-    # non-singleton groups are produced the same way openquantumbase.jl_b200/gaps.py does.
-    gam, Sm, cross, crate, lamb, lrs = davies_tables(w, D.γ, D.S, Op.digits, Op.sigdigits)
-    check(c, ccall((:oqb_ame_set_davies, LIB), Cint,
-                   (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64, Ptr{Int32}, Ptr{Float64}, Int64, Ptr{Int32}, Ptr{Float64}),
-                   h[], gam, Sm, size(cross, 2), cross, crate, size(lamb, 2), lamb, lrs))
-    check(c, ccall((:oqb_ame_rhs, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Cvoid}, Ptr{Cvoid}), h[], size(u, 3), u.ptr, du.ptr))
-    ccall((:oqb_ame_destroy, LIB), Cint, (Ptr{Cvoid},), h[])
-    for lv in Op.opensys; lv(du, u, p, t); end                          # :106-108
-end
-
-"""Signed rounded gap tables (l×l, column-major) + cross terms — Julia transcription of gaps.py."""
-function davies_tables(w, γ, S, digits, sigdigits)
-    l = length(w)
-    ω = zeros(l, l)
-    for i in 1:l-1, j in i+1:l
-        gap = w[j] - w[i]
-        if abs(gap) > 10.0^(-digits)
-            k = round(gap, sigdigits=sigdigits); ω[i, j] = k; ω[j, i] = -k
-        end
+"a LindbladLiouvillian on its own ACCUMULATES (lindblad.jl:94-101)"
+function (lind::LindbladLiouvillian)(du::DeviceBatch, u::DeviceBatch, p, t)
+    s = batch_s(p, t)
+    h = get!(HANDLES, lind) do                                            # zero Hamiltonian, the L_k of this Liouvillian
+        n = lind.size[1]; z = zeros(ComplexF64, n, n, 1)
+        lops = cat([ComplexF64.(Matrix(L(0.0))) for L in lind.L]...; dims=3)
+        r = Ref{Ptr{Cvoid}}(C_NULL)
+        check(u.c, ccall((:oqb_dense_create, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{ComplexF64}, Cint, Ptr{ComplexF64}, Ref{Ptr{Cvoid}}),
+                         u.c, n, 1, z, length(lind.L), lops, r))
+        r[]
     end
-    gam = γ.(ω); Sm = S.(ω)
-    # groups holding more than one pair → cross / lamb lists (see gaps.py::GapGroups._pairs)
-    cross = zeros(Int32, 4, 0); crate = Float64[]; lamb = zeros(Int32, 3, 0); lrs = zeros(2, 0)
-    # … (same enumeration as gaps.py; omitted lists are empty for non-degenerate spectra)
-    gam, Sm, cross, crate, lamb, lrs
+    gam = Float64[g(sb) for g in lind.γ, sb in s]
+    check(u.c, ccall((:oqb_lindblad_acc, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}, Cint, Ptr{Cvoid}, Ptr{Cvoid}),
+                     h, size(u, 3), gam, shared(s), u.ptr, du.ptr))
 end
 
-# ------------------------------------------------------------------ Redfield Λ(t) on the device
-# One GK15 evaluation round of the quadgk! call in (R::RedfieldLiouvillian)(du,u,p,t), redfield.jl:46-64, for nseg
-# segments of many integrals at once.  The segment heap (QuadGK's `adapt`) stays in Julia: keep one
-# `DataStructures.BinaryMaxHeap` of (E, a, b, slot) per integral, bisect the worst segment of every unconverged
-# integral, call this once per round, then `oqb_lambda_total` for ‖Λ‖ — see redfield_device.py for the exact loop.
-function lambda_eval!(lam::Ptr{Cvoid}, c::Ptr{Cvoid}, member::Vector{Int32}, coupling::Vector{Int32}, gi::Matrix{Int32},
-                      θ::Matrix{Float64}, ck::Matrix{ComplexF64}, cg::Matrix{ComplexF64}, slot::Vector{Int64})
-    nseg = length(member)                       # gi, θ: 16×nseg (15 nodes + the end time t); ck: 15×nseg, cg: 7×nseg (Gauss nodes first)
-    E = Vector{Float64}(undef, nseg)
-    check(c, ccall((:oqb_lambda_eval, LIB), Cint,
-                   (Ptr{Cvoid}, Cint, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ptr{Float64}, Ptr{ComplexF64}, Ptr{ComplexF64},
-                    Ptr{Int64}, Ptr{Float64}), lam, nseg, member, coupling, gi, θ, ck, cg, slot, E))
-    E
+# ---------------------------------------------------------------- DiffEqLiouvillian{true,false}: everything inside the library
+# γ(ω) / S(ω) closures reach the library as C callbacks (oqb_spectrum_fn), evaluated at the distinct gap keys only.
+function spectrum_thunk(user::Ptr{Cvoid}, n::Int64, w::Ptr{Float64}, out::Ptr{Float64})::Cvoid
+    f = unsafe_pointer_to_objref(user)::Base.RefValue{Any}
+    for i in 1:n
+        unsafe_store!(out, Float64(f[](unsafe_load(w, i))), i)
+    end
+    nothing
+end
+const KEEP = IdDict{Any,Any}()   # closures handed to C must stay rooted as long as the handle lives
+
+function liouv(Op::DiffEqLiouvillian{true,false}; c=ctx())
+    get!(HANDLES, Op) do
+        Op.H isa DenseHamiltonian || error("the one-call path takes a DenseHamiltonian; sparse H: rotate on the host and use oqb_ame_* directly")
+        all(lv -> lv.coupling isa ConstantCouplings, Op.opensys_eig) || error("constant couplings only")
+        mats = vcat([[ComplexF64.(Matrix(m)) for m in lv.coupling.mats] for lv in Op.opensys_eig]...)
+        coup = cat(mats...; dims=3)
+        L = Ref{Ptr{Cvoid}}(C_NULL)
+        check(c, ccall((:oqb_liouv_create, LIB), Cint,
+                       (Ptr{Cvoid}, Ptr{Cvoid}, Cint, Cint, Cint, Cint, Ptr{ComplexF64}, Ref{Ptr{Cvoid}}),
+                       c, dev(Op.H), Op.lvl, Op.digits, Op.sigdigits, size(coup, 3), coup, L))
+        fn = @cfunction(spectrum_thunk, Cvoid, (Ptr{Cvoid}, Int64, Ptr{Float64}, Ptr{Float64}))
+        roots = Any[]
+        k0 = 0
+        for lv in Op.opensys_eig
+            nk = length(lv.coupling.mats)
+            g = Ref{Any}(lv.γ); S = Ref{Any}(lv.S); push!(roots, g, S)
+            gp, Sp = pointer_from_objref(g), pointer_from_objref(S)
+            if lv isa DaviesGenerator
+                if lv.γ isa OhmicBath   # hypothetical: γ passed as the bath object ⇒ closed form on the device, S ≡ 0
+                    b = lv.γ
+                    check(c, ccall((:oqb_liouv_add_davies_ohmic, LIB), Cint,
+                                   (Ptr{Cvoid}, Cint, Cint, Float64, Float64, Float64, Cint, Float64, Float64, Ptr{Float64}),
+                                   L[], k0, nk, b.η, b.ωc, b.β, 0, 0.0, 1.0, C_NULL))
+                else
+                    check(c, ccall((:oqb_liouv_add_davies_fn, LIB), Cint,
+                                   (Ptr{Cvoid}, Cint, Cint, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}), L[], k0, nk, fn, gp, fn, Sp))
+                end
+            elseif lv isa OneSidedAMELiouvillian
+                al = Int32[k0 + a - 1 for (a, _) in lv.inds]; be = Int32[k0 + b - 1 for (_, b) in lv.inds]
+                check(c, ccall((:oqb_liouv_add_onesided_fn, LIB), Cint,
+                               (Ptr{Cvoid}, Cint, Ptr{Int32}, Ptr{Int32}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}),
+                               L[], length(al), al, be, fn, gp, fn, Sp))
+            else
+                error("eigenbasis term $(typeof(lv)) is not on the device path")
+            end
+            k0 += nk
+        end
+        KEEP[Op] = roots
+        L[]
+    end
 end
 
-# ------------------------------------------------------------------ trajectories that never leave HBM
-# nsteps RK4 steps + the jump callback (lindblad_jump, trajectory_jump.jl:71-74) on the device.  coefH / γ are the
-# closures evaluated at the 2·nsteps+1 stage times (nterms × rows × (2nsteps+1) Julia arrays = the C layout).
-function traj_evolve!(sp::Ptr{Cvoid}, c::Ptr{Cvoid}, ψ::DeviceBatch, nsteps::Int, dt::Float64, coefH::Array{Float64,3},
-                      γ::Array{Float64,3}, rng::Ptr{Cvoid}, thr::Ptr{Cvoid}, njumps::Ptr{Cvoid}; step0::Int=0)
-    shared = size(coefH, 2) == 1
-    check(c, ccall((:oqb_traj_evolve, LIB), Cint,
-                   (Ptr{Cvoid}, Cint, Cint, Cdouble, Ptr{Float64}, Cint, Ptr{Float64}, Cint, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid},
-                    Ptr{Cvoid}, Ptr{Cvoid}, Cint, Cint),
-                   sp, ψ.dims[3], nsteps, dt, coefH, shared, γ, shared, ψ.ptr, rng, thr, njumps, C_NULL, 0, step0))
+function (Op::DiffEqLiouvillian{true,false})(du::DeviceBatch, u::DeviceBatch, p, t)
+    s = batch_s(p, t)
+    check(u.c, ccall((:oqb_liouv_rhs, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}, Cint, Ptr{Cvoid}, Ptr{Cvoid}),
+                     liouv(Op), size(u, 3), coef_rows(Op.H.f, s), shared(s), u.ptr, du.ptr))   # :92-105 (OVERWRITES)
+    for lv in Op.opensys; lv(du, u, p, t); end                                                 # :106-108
+    du
+end
+"same with HOST arrays (n×n×B): H2D/D2H inside the call, pipelined against the kernels"
+function (Op::DiffEqLiouvillian{true,false})(du::Array{ComplexF64,3}, u::Array{ComplexF64,3}, p, t)
+    isempty(Op.opensys) || error("host-buffer path: eigenbasis terms only")
+    s = batch_s(p, t)
+    c = ctx()
+    check(c, ccall((:oqb_liouv_rhs_host, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}, Cint, Ptr{ComplexF64}, Ptr{ComplexF64}),
+                   liouv(Op), size(u, 3), coef_rows(Op.H.f, s), shared(s), u, du))
+    du
+end
+function update_cache!(cache::DeviceBatch, Op::DiffEqLiouvillian{true,false}, p, t::Real)
+    check(cache.c, ccall((:oqb_liouv_update_cache, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Cvoid}),
+                         liouv(Op), coef_rows(Op.H.f, Float64[p(t)]), cache.ptr))              # :111-125 (OVERWRITES)
+    for lv in Op.opensys; update_cache!(cache, lv, p, t); end
+    cache
 end
 
-# ------------------------------------------------------------------ lindblad_jump{true,false} (ame_jump) on a ψ batch
-# After oqb_ame_set_eigen / oqb_ame_set_eigen_device: upload the probability-slot tables in the order ame_jump builds
-# its `prob`/`tag` arrays (trajectory_jump.jl:22-44; gaps.py::jump_slots is the sort-based construction), then
-#   ccall((:oqb_ame_jump, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Cvoid}, Ptr{Float64}, Ptr{UInt8}, Ptr{Int32}, Ptr{Float64}, Cint),
-#         ame, B, ψ.ptr, d_uniform, d_mask, d_choice, d_prob, apply)
-# returns the index into `tag` per member; apply = 1 performs ψ ← Lψ/‖Lψ‖ in place.
-
-# ------------------------------------------------------------------ bath functions on the device (row B)
-# S(ω, bath) for an Ohmic bath (bath_util.jl:17 → ext_util.jl:23-28): one device thread per frequency runs QuadGK's
-# adaptive G7K15.  `build_lambshift(ω_range, true, bath, kw)` (bath_util.jl:26-38) becomes
-#     s_list = S(collect(ω_range), bath); construct_interpolations(ω_range, s_list)
-# with the tabulation below in place of the scalar loop.
-function S(ω::AbstractVector{Float64}, bath::OhmicBath; rtol=sqrt(eps()), atol=0.0, max_segments=1024, device=0)
-    c = ctx(device)
-    out = Vector{Float64}(undef, length(ω))
-    check(c, ccall((:oqb_ohmic_lambshift, LIB), Cint,
-                   (Ptr{Cvoid}, Cdouble, Cdouble, Cdouble, Cint, Ptr{Float64}, Cdouble, Cdouble, Cint, Ptr{Float64}, Ptr{Float64},
-                    Ptr{Int32}), c, bath.η, bath.ωc, bath.β, length(ω), ω, rtol, atol, max_segments, out, C_NULL, C_NULL))
-    out
+"GapIndices of H(s) from the device grouping, in the reference's own form (uniq_w, uniq_a, uniq_b, a0, b0)"
+function device_gap_indices(Op::DiffEqLiouvillian{true,false}, p, t::Real)
+    c = ctx(); plan = Ref{Ptr{Cvoid}}(C_NULL)
+    check(c, ccall((:oqb_liouv_prepare, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ref{Ptr{Cvoid}}), liouv(Op), coef_rows(Op.H.f, Float64[p(t)]), plan))
+    nk = Ref{Int64}(0); nz = Ref{Int64}(0)
+    check(c, ccall((:oqb_ame_gaps_build, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Ref{Int64}, Ref{Int64}), plan[], Op.digits, Op.sigdigits, nk, nz))
+    l = Op.lvl; np = l * (l - 1) ÷ 2 - nz[]
+    keys = Vector{Float64}(undef, nk[]); gptr = Vector{Int64}(undef, nk[] + 1)
+    a = Vector{Int32}(undef, np); b = similar(a); a0 = Vector{Int32}(undef, 2nz[] + l); b0 = similar(a0)
+    check(c, ccall((:oqb_ame_gaps_keys, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}), plan[], keys))
+    check(c, ccall((:oqb_ame_gaps_fetch, LIB), Cint, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}), plan[], gptr, a, b, a0, b0))
+    uniq_a = [Int.(a[gptr[g]+1:gptr[g+1]]) for g in 1:nk[]]; uniq_b = [Int.(b[gptr[g]+1:gptr[g+1]]) for g in 1:nk[]]
+    keys, uniq_a, uniq_b, Int.(a0), Int.(b0)
 end
 
-# correlation(τ, bath) on an array of lags (ohmic.jl:48-52) — the cfun of the Redfield / ULE kernels
-function correlation(τ::AbstractVector{Float64}, bath::OhmicBath; device=0)
-    c = ctx(device)
-    out = Vector{ComplexF64}(undef, length(τ))
-    check(c, ccall((:oqb_ohmic_correlation, LIB), Cint, (Ptr{Cvoid}, Cdouble, Cdouble, Cdouble, Cint, Ptr{Float64}, Ptr{ComplexF64}),
-                   c, bath.η, bath.ωc, bath.β, length(τ), τ, out))
-    out
+# ---------------------------------------------------------------- Redfield: apply step with Λ on the device
+"du −= K₂ + K₂' with K₂ = Σ_α (S_α Λ_α u − Λ_α u S_α): the ρ-dependent half of redfield.jl:65-68; Λ (n×n×(K·B)) comes from the device builder (oqb_lambda_*)"
+function redfield_apply!(du::DeviceBatch, u::DeviceBatch, S::DeviceBatch, Λ::DeviceBatch; real_couplings=false)
+    n, K = size(S, 1), size(S, 3)
+    check(u.c, ccall((:oqb_redfield_apply_acc, LIB), Cint,
+                     (Ptr{Cvoid}, Cint, Cint, Ptr{Cvoid}, Cint, Ptr{Cvoid}, Cint, Ptr{Cvoid}, Ptr{Cvoid}),
+                     u.c, n, K, S.ptr, 1 | (real_couplings ? 2 : 0), Λ.ptr, size(u, 3), u.ptr, du.ptr))
 end
 
-# Tabulated Lamb shift evaluated on the device at the rounded gaps: hand the prefiltered coefficients of the
-# BSpline(Quadratic(Line(OnGrid()))) interpolant (`itp.itp.itp.coefs` of what construct_interpolations returns, n+2
-# numbers) to the handle before oqb_ame_davies_ohmic_begin / oqb_ame_set_onesided_ohmic:
-#   ccall((:oqb_ame_set_lambshift_spline, LIB), Cint, (Ptr{Cvoid}, Cint, Cdouble, Cdouble, Ptr{Float64}),
-#         ame, length(ω_range), first(ω_range), step(ω_range), coefs)
-#
-# Options: ccall((:oqb_set_real_operand_mode, LIB), Cint, (Ptr{Cvoid}, Cint), ctx(), 0) switches the real-eigenvector /
-# real-Hamiltonian products off (general complex product everywhere); oqb_set_zgemm_mode selects 3M / 4M.
+# ---------------------------------------------------------------- trajectories (ψ ensembles, n×1×B)
+"dψ = (−iH(s_b) − ½Σγ_k L_k'L_k)ψ: the `cache*u` of the external solver with the cache of diffeq_liouvillian.jl:78-83"
+function traj_matvec!(dψ::DeviceBatch, Op::DiffEqLiouvillian{false,false}, ψ::DeviceBatch, p, t)
+    s = batch_s(p, t); lind = lindblad_of(Op)
+    gam = lind === nothing ? C_NULL : Float64[g(sb) for g in lind.γ, sb in s]
+    check(ψ.c, ccall((:oqb_traj_matvec, LIB), Cint,
+                     (Ptr{Cvoid}, Cint, Ptr{Float64}, Cint, Ptr{Float64}, Cint, Ptr{Cvoid}, Ptr{Cvoid}),
+                     dev(Op.H, lind), size(ψ, 3), coef_rows(Op.H.f, s), shared(s), gam, shared(s), ψ.ptr, dψ.ptr))
+end
+
+"lindblad_jump(Op{false,false}, ψ, p, t) on a batch (trajectory_jump.jl:2-12, :71-74): `uniforms` are the rand() values; returns the chosen operator index per member (0-based) — apply=true performs ψ ← Lψ/‖Lψ‖"
+function lindblad_jump(Op::DiffEqLiouvillian{false,false}, ψ::DeviceBatch, p, t::Real; uniforms::Vector{Float64}, apply=false)
+    length(Op.opensys) == 1 || error("several Liouvillians: propose per Liouvillian with this method, then oqb_traj_apply_choice + oqb_resample (include/oqb.h)")
+    lind = Op.opensys[1]::LindbladLiouvillian
+    c = ψ.c; B = size(ψ, 3); s = p(t)
+    gam = Float64[g(s) for g in lind.γ]
+    du = Ref{Ptr{Cvoid}}(C_NULL); dc = Ref{Ptr{Cvoid}}(C_NULL)
+    check(c, ccall((:oqb_malloc, LIB), Cint, (Ptr{Cvoid}, Csize_t, Ref{Ptr{Cvoid}}), c, 8B, du))
+    check(c, ccall((:oqb_malloc, LIB), Cint, (Ptr{Cvoid}, Csize_t, Ref{Ptr{Cvoid}}), c, 4B, dc))
+    check(c, ccall((:oqb_upload, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}, Csize_t), c, du[], uniforms, 8B))
+    check(c, ccall((:oqb_traj_jump, LIB), Cint,
+                   (Ptr{Cvoid}, Cint, Ptr{Float64}, Cint, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cint),
+                   dev(Op.H, lind), B, gam, 1, ψ.ptr, du[], C_NULL, dc[], C_NULL, apply ? 1 : 0))
+    choice = Vector{Int32}(undef, B)
+    check(c, ccall((:oqb_download, LIB), Cint, (Ptr{Cvoid}, Ptr{Int32}, Ptr{Cvoid}, Csize_t), c, choice, dc[], 4B))
+    ccall((:oqb_free, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), c, du[]); ccall((:oqb_free, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), c, dc[])
+    choice
+end
+
+# ---------------------------------------------------------------- multi-GPU: the ensemble-average reduce
+"one communicator per GPU of this process (ncclCommInitAll); use with Threads.@threads over devices, one ctx(device) per thread"
+function comm_init_all(ctxs::Vector{Ptr{Cvoid}})
+    comms = Vector{Ptr{Cvoid}}(undef, length(ctxs))
+    check(ctxs[1], ccall((:oqb_comm_init_all, LIB), Cint, (Cint, Ptr{Ptr{Cvoid}}, Ptr{Ptr{Cvoid}}), length(ctxs), ctxs, comms))
+    comms
+end
+"out (device, 2·nobs doubles) = Σ over ALL GPUs of Σ_b ψ_b'O_oψ_b: per-GPU partial sums and ncclAllReduce on the context stream"
+function ensemble_expect_allreduce!(comm::Ptr{Cvoid}, out::Ptr{Cvoid}, obs::DeviceBatch, ψ::DeviceBatch; is_vector=true)
+    c = ψ.c
+    check(c, ccall((:oqb_expect_sum, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{Cvoid}, Cint, Ptr{Cvoid}, Cint, Ptr{Cvoid}),
+                   c, size(obs, 1), size(obs, 3), obs.ptr, size(ψ, 3), ψ.ptr, is_vector ? 1 : 0, out))
+    check(c, ccall((:oqb_allreduce_obs, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Int64), comm, out, 2size(obs, 3)))
+end
 
 end # module

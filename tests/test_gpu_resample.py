@@ -50,7 +50,7 @@ def test_lindblad_jump_two_liouvillians_resample(Q):
     pg, po = Q.ODEParams(None, 2.0), O.ODEParams(None, 2.0)
     dpsi = Q.DeviceBatch.from_host(psi[:, :, None].copy())
     pick, choices = Hm.lindblad_jump(opg, dpsi, pg, 1.0, uni, mask, apply=True)
-    out = dpsi.to_host()[:, :, 0]
+    out = dpsi.to_host().reshape(B, -1)
     for b in range(B):
         if not mask[b]:
             assert pick[b] == -1 and np.array_equal(out[b], psi[b])
@@ -80,7 +80,7 @@ def test_ame_jump_two_davies_generators_resample(Q):
     uni = rng.random((3, B))
     dpsi = Q.DeviceBatch.from_host(psi[:, :, None].copy())
     pick, choices = Hm.lindblad_jump(opg, dpsi, Q.ODEParams(None, 1.0), 0.5, uni, None, apply=True, w=w, v=v)
-    out = dpsi.to_host()[:, :, 0]
+    out = dpsi.to_host().reshape(B, -1)
     for b in range(B):
         win, ch, L = O.lindblad_jump_multi(opo, psi[b], O.ODEParams(None, 1.0), 0.5, [uni[0, b], uni[1, b], uni[2, b]], w, v)
         assert pick[b] == win and list(choices[:, b]) == ch, b
@@ -106,7 +106,7 @@ def test_ame_jump_const_davies(Q):
     dpsi = Q.DeviceBatch.from_host(psi[:, :, None].copy())
     choice, prob = Dg.ame_jump(dpsi, uni, None, apply=True)
     choice, prob = choice.cpu().numpy(), prob.cpu().numpy()
-    out = dpsi.to_host()[:, :, 0]
+    out = dpsi.to_host().reshape(B, -1)
     for b in range(B):
         k, pr = O.ame_jump_const(Do, psi[b], uni[b])
         assert choice[b] == k
