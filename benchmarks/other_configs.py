@@ -110,7 +110,7 @@ def run_c2(Q, torch, steps, dense_L, nq=8, B=4096):
             "algorithmic_tflop_per_step": flops / 1e12, "step_tflops": flops / (ms * 1e-3) / 1e12,
             "roofline": {"bound": "tensor", "kernel": "zgemm_tma_kernel", "achieved": ach, "peak": dmma, "unit": "TFLOP/s",
                          "frac": ach / dmma,
-                         "frac_executed": ach * (0.5 if (diag_path and ctx.real_operand_mode())
+                         "frac_executed": ach * (0.5 if ((not dense_L) and ctx.real_operand_mode())  # real H terms and real Z_k: every product is a real-operand product
                                                  else _exec_ratio()) / dmma,
                          "kernel_share_of_step": zms.value / ((max(3, 3) + steps) * ms),
                          "peak_source": "DMMA issue probe, this run"}}

@@ -182,6 +182,26 @@ int oqb_lambda_eval(oqb_lambda* lam, int nseg, const int32_t* h_member, const in
 int oqb_lambda_total(oqb_lambda* lam, int nint, const int64_t* h_ptr, const int64_t* h_idx, void* d_Lambda,
                      double* h_norm);
 
+/* The whole adaptive quadrature inside the library: quadgk!(…, max(0, t−Ta), t; rtol, atol) of src/opensys/redfield.jl:57-64
+ * (window [lo, hi] per integral: ULE passes hi = min(t+Ta, tf), src/opensys/lindblad.jl:60-61) for nint integrals in lock
+ * step — per-integral max-heap, bisect the worst segment until E ≤ atol or E ≤ rtol·‖I‖_F, final re-summation over the heap.
+ * Integral q: schedule h_member[q], coupling h_coupling[q], end time h_t[q] (where U(t) is taken), window h_lo/h_hi[q];
+ * h_dt[m]: grid spacing of schedule m's sampled unitary (G points, oqb_lambda_set_unitary).  The correlation function is a C
+ * callback evaluated on the calling thread once per refinement round for all new nodes:
+ *   cfun(user, nseg, integral[nseg], t[nseg], x[nseg×15], out[nseg×15 (re,im)]) with out = C(t, x)·f_j(p(x)).
+ * d_Lambda: nint n×n matrices (device).  rounds / segments report the work done (may be NULL). */
+typedef void (*oqb_kernel_fn)(void* user, int64_t nseg, const int32_t* integral, const double* t, const double* x, double* out);
+int oqb_lambda_integrate(oqb_lambda* lam, oqb_ctx* ctx, int nint, const int32_t* h_member, const int32_t* h_coupling,
+                         const double* h_t, const double* h_lo, const double* h_hi, const double* h_dt, int G,
+                         oqb_kernel_fn cfun, void* user, double atol, double rtol, int64_t maxevals, void* d_Lambda,
+                         int64_t* rounds, int64_t* segments, int64_t* h_evals /* integrand evaluations per integral, may be NULL */);
+/* The same with the Ohmic bath's C(t − x) (src/bath/ohmic.jl:48-52) evaluated by the library — no callback at all. */
+int oqb_lambda_integrate_ohmic(oqb_lambda* lam, oqb_ctx* ctx, int nint, const int32_t* h_member, const int32_t* h_coupling,
+                               const double* h_t, const double* h_lo, const double* h_hi, const double* h_dt, int G, double eta,
+                               double wc, double beta, double atol, double rtol, int64_t maxevals, void* d_Lambda,
+                               int64_t* rounds, int64_t* segments, int64_t* h_evals);
+int oqb_lambda_dims(const oqb_lambda* lam, int* n, int* K);
+
 /* ------------------------------------------ eigenbasis Liouvillian: DiffEqLiouvillian{true,·} */
 /* n: Hilbert dimension; lvl: kept levels (src/opensys/diffeq_liouvillian.jl:45-54);
  * h_couplings: K coupling matrices A_α (n×n, unit-scaled, src/coupling/coupling.jl:42,66). */

@@ -52,6 +52,11 @@ SIGNATURES = {
     "oqb_lambda_set_unitary": [c_void_p, c_int, c_int, c_void_p],
     "oqb_lambda_reserve_slots": [c_void_p, c_i64],
     "oqb_lambda_eval": [c_void_p, c_int, c_i32p, c_i32p, c_i32p, c_dp, c_dp, c_dp, c_i64p, c_dp],
+    "oqb_lambda_integrate": [c_void_p, c_void_p, c_int, c_i32p, c_i32p, c_dp, c_dp, c_dp, c_dp, c_int, c_void_p, c_void_p,
+                             C.c_double, C.c_double, c_i64, c_void_p, c_i64p, c_i64p, c_i64p],
+    "oqb_lambda_integrate_ohmic": [c_void_p, c_void_p, c_int, c_i32p, c_i32p, c_dp, c_dp, c_dp, c_dp, c_int, C.c_double, C.c_double,
+                                   C.c_double, C.c_double, C.c_double, c_i64, c_void_p, c_i64p, c_i64p, c_i64p],
+    "oqb_lambda_dims": [c_void_p, C.POINTER(c_int), C.POINTER(c_int)],
     "oqb_lambda_total": [c_void_p, c_int, c_i64p, c_i64p, c_void_p, c_dp],
     "oqb_ame_create": [c_void_p, c_int, c_int, c_int, c_void_p, C.POINTER(c_void_p)],
     "oqb_ame_destroy": [c_void_p],

@@ -245,6 +245,13 @@ int oqb_lambda_create(oqb_ctx* c, int n, int K, const void* h_S, oqb_lambda** ou
     return 0;
 }
 
+int oqb_lambda_dims(const oqb_lambda* L, int* n, int* K) {
+    if (!L) return OQB_EINVAL;
+    if (n) *n = L->n;
+    if (K) *K = L->K;
+    return 0;
+}
+
 int oqb_lambda_destroy(oqb_lambda* L) {
     OQB_DEVICE(L, L->c);
     if (!L) return 0;

@@ -55,13 +55,37 @@ class ConstDaviesGenerator:
     def ame_jump(self, psi: DeviceBatch, uniforms, mask=None, apply=False):
         """ame_jump(D::ConstDaviesGenerator, u, _, _), src/opensys/trajectory_jump.jl:53-56: prob_k = real(u'L_k'L_ku) for the
         precomputed operators (√γ already inside), sample(D.Linds, Weights(prob)) with the supplied uniforms; returns
-        (choice[B], prob[B, K]) device tensors.  apply=True performs ψ ← L_kψ/‖L_kψ‖."""
-        from .host import JumpOperators
+        (choice[B], prob[B, K]) device tensors.  apply=True performs ψ ← L_kψ/‖L_kψ‖.  The operators are sparse in one fixed
+        basis, so they go to the AME jump kernel as probability slots (one per operator: its non-zero entries, rate 1) of a
+        handle in the adiabatic frame (v = I) — any number of operators."""
+        import torch
+        lib, ctx = self.ctx.lib, self.ctx
+        l, K = self.Hls.shape[0], len(self.Linds)
         if getattr(self, "_jump", None) is None:
-            self._jump = JumpOperators(self.Linds, self.ctx)
-        out = self._jump.jump(psi, np.ones((1, len(self.Linds))), uniforms, mask, apply)
-        self.ctx.sync()
-        return out
+            h = C.c_void_p()
+            cbuf = _colmajor_stack(self.Linds)
+            ctx.check(lib.oqb_ame_create(ctx.h, l, l, K, cbuf.ctypes.data, C.byref(h)))
+            ctx.check(lib.oqb_ame_set_eigen(h, _lib.dptr(np.zeros(l)), None))
+            ptr, terms = [0], []
+            for k, L in enumerate(self.Linds):
+                r, c_ = np.nonzero(L)
+                o = np.lexsort((c_, r))
+                terms += [(k, int(a), int(b)) for a, b in zip(r[o], c_[o])]
+                ptr.append(len(terms))
+            ptr = np.asarray(ptr, dtype=np.int64)
+            terms = np.ascontiguousarray(np.asarray(terms, dtype=np.int32).reshape(-1, 3))
+            rate = np.ones(K)
+            ctx.check(lib.oqb_ame_set_jump(h, K, ptr.ctypes.data_as(_lib.c_i64p), terms.ctypes.data_as(_lib.c_i32p), _lib.dptr(rate)))
+            self._jump = h
+        B, dev = psi.B, psi.t.device
+        u_d = torch.as_tensor(np.asarray(uniforms, dtype=np.float64), device=dev)
+        m_d = None if mask is None else torch.as_tensor(np.asarray(mask, dtype=np.uint8), device=dev)
+        choice = torch.zeros(B, dtype=torch.int32, device=dev)
+        prob = torch.zeros((B, K), dtype=torch.float64, device=dev)
+        ctx.check(lib.oqb_ame_jump(self._jump, B, psi.ptr, C.c_void_p(u_d.data_ptr()), None if m_d is None else C.c_void_p(m_d.data_ptr()),
+                                   C.c_void_p(choice.data_ptr()), C.c_void_p(prob.data_ptr()), int(apply)))
+        ctx.sync()
+        return choice, prob
 
     def update_cache(self, cache, *_):
         """update_cache!(cache, D, _, _) = cache .+= D.A  (:119)."""

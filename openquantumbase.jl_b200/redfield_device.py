@@ -41,6 +41,8 @@ _wg = np.concatenate([_wg_half, [_WG[3]], _wg_half[::-1]])
 _order = np.concatenate([np.arange(1, 15, 2), np.arange(0, 15, 2)])
 NODE_XI, NODE_WK, NODE_WG = _xi[_order], _wk[_order], _wg[_order]
 N_GAUSS = 7
+_KERNEL_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int64, C.POINTER(C.c_int32), C.POINTER(C.c_double), C.POINTER(C.c_double),
+                         C.POINTER(C.c_double))  # oqb_kernel_fn
 
 
 class SampledUnitary:
@@ -145,8 +147,56 @@ class LambdaBuilder:
         return nrm
 
     # -- the adaptive loop -----------------------------------------------------------------------
-    def build(self, member, coupling, t, cfun: Callable, Ta: float, atol: float, rtol: float, maxevals: int = 10 ** 7,
-              out: Optional[DeviceBatch] = None, t_hi=None) -> DeviceBatch:
+    def build(self, member, coupling, t, cfun, Ta: float, atol: float, rtol: float, maxevals: int = 10 ** 7,
+              out: Optional[DeviceBatch] = None, t_hi=None, host_heap: bool = False) -> DeviceBatch:
+        """Λ for integrals q = 0..nint-1 (see `build_host_heap` for the arguments).  By default the adaptive control flow —
+        QuadGK's per-integral segment heap — runs INSIDE the library (oqb_lambda_integrate, csrc/lambda_integrate.cu); `cfun`
+        is handed over as a C callback, or, when it is an OhmicBath, evaluated by the library itself (C(t − x)).
+        host_heap=True runs the same loop in Python (the round-1 path, kept for A/B checks: identical segment sequence)."""
+        from .host import OhmicBath
+        if host_heap and not isinstance(cfun, OhmicBath):
+            return self.build_host_heap(member, coupling, t, cfun, Ta, atol, rtol, maxevals, out, t_hi)
+        member = np.ascontiguousarray(member, dtype=np.int32)
+        coupling = np.ascontiguousarray(coupling, dtype=np.int32)
+        nint = len(member)
+        t = np.ascontiguousarray(np.broadcast_to(np.asarray(t, dtype=np.float64), (nint,)))
+        lo = np.ascontiguousarray(np.maximum(0.0, t - Ta))
+        hi = t if t_hi is None else np.ascontiguousarray(np.broadcast_to(np.asarray(t_hi, dtype=np.float64), (nint,)))
+        Lam = out if out is not None else DeviceBatch(nint, self.n, self.n, self.ctx)
+        rounds, segs = C.c_int64(), C.c_int64()
+        evals = np.zeros(nint, dtype=np.int64)
+        ev_p = evals.ctypes.data_as(_lib.c_i64p)
+        i32 = lambda v: v.ctypes.data_as(_lib.c_i32p)
+        lib, ctx = self.ctx.lib, self.ctx
+        dt = np.ascontiguousarray(self.dt)
+        if isinstance(cfun, OhmicBath):
+            ctx.check(lib.oqb_lambda_integrate_ohmic(self.h, ctx.h, nint, i32(member), i32(coupling), _lib.dptr(t), _lib.dptr(lo),
+                                                     _lib.dptr(hi), _lib.dptr(dt), self.G, cfun.eta, cfun.wc, cfun.beta, atol, rtol,
+                                                     maxevals, Lam.ptr, C.byref(rounds), C.byref(segs), ev_p))
+        else:
+            err = []
+
+            def cb(_user, nseg, q_ptr, t_ptr, x_ptr, out_ptr):
+                try:
+                    q = np.ctypeslib.as_array(q_ptr, shape=(nseg,)).astype(np.int64)
+                    tt = np.ctypeslib.as_array(t_ptr, shape=(nseg,))
+                    x = np.ctypeslib.as_array(x_ptr, shape=(nseg, 15))
+                    cv = np.asarray(cfun(q[:, None], tt[:, None], x), dtype=C128)
+                    np.ctypeslib.as_array(out_ptr, shape=(nseg, 30))[:] = np.ascontiguousarray(np.broadcast_to(cv, (nseg, 15))).view(np.float64)
+                except BaseException as e:  # an exception must not cross the C frame
+                    err.append(e)
+                    np.ctypeslib.as_array(out_ptr, shape=(nseg, 30))[:] = np.nan
+            fn = _KERNEL_FN(cb)
+            ctx.check(lib.oqb_lambda_integrate(self.h, ctx.h, nint, i32(member), i32(coupling), _lib.dptr(t), _lib.dptr(lo), _lib.dptr(hi),
+                                               _lib.dptr(dt), self.G, C.cast(fn, C.c_void_p), None, atol, rtol, maxevals, Lam.ptr,
+                                               C.byref(rounds), C.byref(segs), ev_p))
+            if err:
+                raise err[0]
+        self.stats = {"rounds": rounds.value, "segments_evaluated": segs.value, "integrals": nint, "max_evals": int(evals.max())}
+        return Lam
+
+    def build_host_heap(self, member, coupling, t, cfun: Callable, Ta: float, atol: float, rtol: float, maxevals: int = 10 ** 7,
+                        out: Optional[DeviceBatch] = None, t_hi=None) -> DeviceBatch:
         """Λ for integrals q = 0..nint-1: schedule member[q], coupling index coupling[q] (0-based j of S_j),
         end time t[q].  cfun(q_idx, t, x) → C(t,x)·f_j(p(x)) evaluated on arrays: q_idx (m,1) integral numbers,
         t (m,1), x (m,15).  Returns a DeviceBatch of nint n×n matrices (written into `out` when given).

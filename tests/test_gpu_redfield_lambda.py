@@ -237,3 +237,33 @@ def test_lambda_with_ohmic_correlation(Q):
     cf_o = lambda t, x: bath_o.correlation(t - x)
     worst = max(relerr(Lam[b], oracle_lambda(SampledUnitary(Us[b], dt), S, cf_o, float(tend[b]), Ta, atol, rtol)) for b in range(nb))
     assert worst < 1e-12
+    # the bath object itself as cfun: C(t − x) evaluated by the library, no host callback at all (oqb_lambda_integrate_ohmic)
+    Lam2 = lb.build(np.arange(nb), np.zeros(nb, dtype=int), tend, bath_g, Ta, atol, rtol).to_host()
+    assert relerr(Lam2, Lam) < 1e-13
+
+
+def test_library_heap_equals_host_heap(Q):
+    """oqb_lambda_integrate (QuadGK's segment heap in C++) against the Python host loop it replaces: same segment sequence,
+    same evaluation counts, same re-summation order — identical results."""
+    from oqb_b200.redfield_device import LambdaBuilder
+    rng = np.random.default_rng(7)
+    n, nb, K, G, tf = 8, 5, 2, 129, 3.0
+    Us = []
+    for b in range(nb):
+        A = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))
+        u, dt = sample_unitary((A + A.conj().T) / (2 * np.sqrt(n)), tf, G)
+        Us.append(u)
+    Ss = [np.diag(rng.choice([-1.0, 1.0], n)).astype(complex), (lambda m: (m + m.conj().T) / 2)(rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n)))]
+    cf = lambda q, t, x: np.exp(-0.7 * (t - x) ** 2) * np.exp(-1.3j * (t - x)) / (1.0 + 0.2 * x)
+    member = np.repeat(np.arange(nb), K)
+    coupling = np.tile(np.arange(K), nb)
+    tend = np.array([tf * (0.3 + 0.7 * b / (nb - 1)) for b in range(nb)])[member]
+    tend[3] = 0.0  # an empty window in the middle of the batch
+    lb = LambdaBuilder(Ss, np.stack(Us), dt)
+    A1 = lb.build(member, coupling, tend, cf, 2.0, 1e-10, 1e-8).to_host()
+    s1 = dict(lb.stats)
+    A2 = lb.build(member, coupling, tend, cf, 2.0, 1e-10, 1e-8, host_heap=True).to_host()
+    s2 = dict(lb.stats)
+    assert np.array_equal(A1, A2)
+    assert s1["rounds"] == s2["rounds"] and s1["segments_evaluated"] == s2["segments_evaluated"] and s1["max_evals"] == s2["max_evals"]
+    assert np.all(A1[3] == 0)
