@@ -578,8 +578,11 @@ def main():
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         cval, cms, cores = cpu_reference_arm(2, 1)
+        from oracle import cpu_baseline as CB
         cpu = {"value": cval, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": "2 rho through the reference-structured per-call AME RHS (eigh + rotations + closed-form Davies), numpy/OpenBLAS; see oracle/cpu_baseline.py"}
+               "sample": "2 rho through the reference-structured per-call AME RHS (eigh + rotations + closed-form Davies), numpy/OpenBLAS; see oracle/cpu_baseline.py",
+               "literal_davies_loop": CB.time_literal_davies_loop(),
+               "julia_script": "baseline/julia_ref.jl runs the real package for anyone with Julia >= 1.9 (not installed here)"}
 
     # ---- the other BASELINE.json configurations, measured in the same driver run (N = 1 only; short) ----
     secondary = None

@@ -66,7 +66,9 @@ int oqb_launch_count(const oqb_ctx* ctx, uint64_t* n); /* kernels launched throu
  *   "traj_ell" (1)     width-specialised ELL kernel for unstructured sparse operators;  "rk_fuse" (1), "xor_fixed" (1), "xor_rows" (16)
  *   "ame_host_chunk_mib" (128)                  — chunk size of oqb_ame_rhs_host's H2D/D2H pipeline
  *   "davies_dense_min_pairs" (0 = cost model)   — gap groups with at least this many level pairs use the dense per-group
- *                                                  products instead of the cross-term list;  "davies_max_cross" (5e7) caps the list. */
+ *                                                  products instead of the cross-term list;  "davies_max_cross" (5e7) caps the list.
+ *   "debug_checks" (0)                          — 1: every index list the Davies term builder produces is range- and
+ *                                                  consistency-checked on the device before use (an error is returned) */
 int oqb_set_option(oqb_ctx* ctx, const char* name, int64_t value);
 int oqb_get_option(const oqb_ctx* ctx, const char* name, int64_t* value);
 /* Complex product used by the tensor-pipe ZGEMM behind every dense path: 1 (default) = 3-multiplication

@@ -349,6 +349,38 @@ __global__ void dense_mask_kernel(int l, const c128* __restrict__ A, const int32
         o[e] = entry_slot(gid[e], gslot, zero_slot) == want ? Ak[e] : make_double2(0.0, 0.0);
 }
 
+// "debug_checks": every index the term builder produced is range-checked on the device before it is used (the pool this
+// library is developed on does not allow compute-sanitizer, so the builder carries its own bounds checks)
+__global__ void validate_lists_kernel(int l, long long ng, long long ncross, const int32_t* __restrict__ cidx, const int32_t* __restrict__ cg,
+                                      long long nlamb, const int32_t* __restrict__ lidx, const int32_t* __restrict__ lg,
+                                      const int32_t* __restrict__ gid, const int32_t* __restrict__ gslot, int ndense, unsigned long long* __restrict__ bad) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long b = 0;
+    if (e < ncross) {
+        for (int k = 0; k < 4; ++k) b += (cidx[4 * e + k] < 0 || cidx[4 * e + k] >= l) ? 1 : 0;
+        const int g = cg[e];
+        b += ((g > 0 ? g : -g) > ng) ? 1 : 0;
+        if (!b) {  // the two entries of a cross term belong to the group the term claims
+            b += gid[cidx[4 * e] + (long long)cidx[4 * e + 1] * l] != g ? 1 : 0;
+            b += gid[cidx[4 * e + 2] + (long long)cidx[4 * e + 3] * l] != g ? 1 : 0;
+        }
+    }
+    if (e < nlamb) {
+        for (int k = 0; k < 3; ++k) b += (lidx[3 * e + k] < 0 || lidx[3 * e + k] >= l) ? 1 : 0;
+        b += ((lg[e] > 0 ? lg[e] : -lg[e]) > ng) ? 1 : 0;
+    }
+    if (e < (long long)l * l) {
+        const int g = gid[e];
+        const long long ag = g > 0 ? g : -g;
+        b += ag > ng ? 1 : 0;
+        if (ag >= 1 && ag <= ng) b += (gslot[ag - 1] < -1 || gslot[ag - 1] >= ndense) ? 1 : 0;
+        const int a = (int)(e % l), c = (int)(e / l);
+        b += (a == c && g != 0) ? 1 : 0;                                   // the diagonal is in the zero group
+        b += (a != c && gid[c + (long long)a * l] != -g) ? 1 : 0;          // (j,i) carries −key of (i,j)
+    }
+    if (b) atomicAdd(bad, b);
+}
+
 inline unsigned cdivu(long long a, long long b) { return (unsigned)((a + b - 1) / b); }
 
 // grow a device array preserving its content (stream-ordered)
@@ -467,6 +499,20 @@ int build_lists(oqb_ame* a) {
             OQB_CUDA(c, cudaStreamSynchronize(c->stream));  // d_src lives in the workspace
         }
         a->nlamb = (long long)h_n;
+    }
+    if (c->opt.debug_checks) {
+        unsigned long long* d_bad = nullptr;
+        OQB_TRY(ame_alloc(c, (void**)&d_bad, sizeof(unsigned long long)));
+        OQB_CUDA(c, cudaMemsetAsync(d_bad, 0, sizeof(unsigned long long), c->stream));
+        const long long work = std::max<long long>(std::max<long long>(a->ncross, a->nlamb), (long long)l * l);
+        validate_lists_kernel<<<cdivu(work, 256), 256, 0, c->stream>>>(l, ng, a->ncross, a->d_cross_idx, a->d_cross_g, a->nlamb, a->d_lamb_idx,
+                                                                        a->d_lamb_g, a->d_gid, a->d_gslot, (int)a->h_dense_groups.size(), d_bad);
+        c->launches++;
+        unsigned long long h_bad = 1;
+        OQB_CUDA(c, cudaMemcpyAsync(&h_bad, d_bad, sizeof(h_bad), cudaMemcpyDeviceToHost, c->stream));
+        OQB_CUDA(c, cudaStreamSynchronize(c->stream));
+        cudaFreeAsync(d_bad, c->stream);
+        if (h_bad) return set_error(c, OQB_ECUDA, "davies term builder: %llu index/group consistency violations (debug_checks)", h_bad);
     }
     a->lists_built = true;
     return 0;

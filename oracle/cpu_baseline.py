@@ -99,3 +99,33 @@ def use_all_host_threads():
 
 def host_threads():
     return use_all_host_threads()
+
+
+def time_literal_davies_loop(levels=(16, 32, 64), K=1, seed=7):
+    """BASELINE.md §4 / SURVEY §8(d): the reference's LITERAL DaviesGenerator loop (GapIndices with sorted insertion,
+    src/opensys/opensys_util.jl:25-61, then one pair of l×l operators per gap group, src/opensys/davies.jl:26-45) timed at
+    lvl ∈ {16, 32, 64} on a generic spectrum — it cannot finish at lvl = 1024 — with the measured scaling exponent and its
+    extrapolation to lvl = 1024.  The restatement (oracle/oqb_oracle.py) uses dense l×l temporaries where the reference
+    uses SparseArrays, so the constant differs; the O(#groups·l²) ~ l⁴ growth is the point."""
+    from . import oqb_oracle as O
+    rng = np.random.default_rng(seed)
+    gamma = lambda x: x + 1 if x >= 0 else (1 - x) * np.exp(x)
+    zero = lambda x: 0.0
+    out = {}
+    for l in levels:
+        w = np.sort(rng.standard_normal(l) * 3.0)
+        cs = [(lambda m: m + m.conj().T)(rng.standard_normal((l, l)) + 1j * rng.standard_normal((l, l))) for _ in range(K)]
+        rho = rng.standard_normal((l, l)) + 1j * rng.standard_normal((l, l))
+        t0 = time.perf_counter()
+        gi = O.build_gap_indices(w, 8, 8)
+        t1 = time.perf_counter()
+        O.DaviesGenerator(cs, gamma, zero).rhs_acc(np.zeros((l, l), dtype=complex), rho, gi, None, 0.0)
+        t2 = time.perf_counter()
+        out[int(l)] = {"gap_indices_ms": (t1 - t0) * 1e3, "davies_loop_ms": (t2 - t1) * 1e3, "groups": len(gi.uniq_w)}
+    ls = np.array(sorted(out), dtype=float)
+    ts = np.array([out[int(l)]["davies_loop_ms"] + out[int(l)]["gap_indices_ms"] for l in ls])
+    expo = float(np.polyfit(np.log(ls), np.log(ts), 1)[0])
+    ext = float(ts[-1] * (1024.0 / ls[-1]) ** expo)
+    return {"what": "literal per-gap-group DaviesGenerator loop + GapIndices builder, K = %d coupling, one rho, CPU restatement" % K,
+            "per_level": out, "fitted_exponent": expo, "extrapolated_ms_per_rho_at_lvl_1024": ext,
+            "note": "the timed CPU arm replaces this loop by the closed form (in the reference's favour); this row shows why"}

@@ -89,7 +89,8 @@ def test_davies_transverse_field_start(Q, host_mod, q, mode):
     opg = Q.DiffEqLiouvillian(Hg, [Q.DaviesGenerator(coup, gamma, lamb)], [], n)
     u = np.stack([F.random_density_matrix(n, rng) for _ in range(2)] + [rand_c(rng, n, n)])
     thr = {"auto": 0, "all_dense": 2, "all_list": 10 ** 9}[mode]
-    with ctx.option("davies_dense_min_pairs", thr), ctx.option("davies_max_cross", 10 ** 12 if mode == "all_list" else 50_000_000):
+    with ctx.option("davies_dense_min_pairs", thr), ctx.option("davies_max_cross", 10 ** 12 if mode == "all_list" else 50_000_000), \
+            ctx.option("debug_checks", 1):  # the term builder's own device-side bounds / consistency checks are on
         opg.clear_plans()
         du = opg.rhs_with_eig(np.zeros_like(u), u, Q.ODEParams(None, 1.0), 0.0, w, v)
         stats = host_mod.davies_stats(ctx, opg._ame)
