@@ -274,6 +274,12 @@ int oqb_ame_add_davies(oqb_ame* ame, int k0, int nk, const double* h_gamma_plus,
  * arguments as oqb_ame_set_lambshift_spline) evaluated at the keys on the device. */
 int oqb_ame_add_davies_ohmic(oqb_ame* ame, int k0, int nk, double eta, double wc, double beta, int nS, double S_x0,
                              double S_dx, const double* h_S_coef);
+/* One pair (α,β) of a CorrelatedDaviesGenerator / ConstHCorrelatedDaviesGenerator (src/opensys/davies.jl:231-345):
+ *   du += Σ_x γ_αβ(x)(L^β_x ρ L^α_x' − ½{L^α_x'L^β_x, ρ}) − i[S_αβ(x) L^α_x'L^β_x, ρ],  L^k_x = A_k∘[ω̃ == x]
+ * with γ_αβ(±uniq_w[g]), S_αβ(±uniq_w[g]) per gap key and at 0 (real-valued spectra); one call per pair of `inds`, on top of
+ * oqb_ame_gaps_build; accumulates with any other term.  Degenerate gap groups are handled like for oqb_ame_add_davies. */
+int oqb_ame_add_correlated(oqb_ame* ame, int alpha, int beta, const double* h_gamma_plus, const double* h_gamma_minus,
+                           const double* h_S_plus, const double* h_S_minus, double gamma0, double S0);
 /* What the gap structure turned into: generators added, cross-term and L'L list entries, gap groups on the dense path,
  * dense blocks kept (blocks whose masked coupling vanishes to rounding are dropped).  Any pointer may be NULL. */
 int oqb_ame_davies_stats(const oqb_ame* ame, int64_t* n_terms, int64_t* n_cross, int64_t* n_lamb, int64_t* n_dense_groups,

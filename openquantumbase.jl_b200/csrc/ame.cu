@@ -79,6 +79,7 @@ int eig_apply(oqb_ame* a, int nb, const c128* R, c128* X, bool overwrite, bool w
         if (a->d_Wt_im) OQB_TRY(davies_diag(c, l, a->d_Wt_im, pop, X, nb, true));
         for (const DaviesTerm& t : a->terms)  // every DaviesGenerator of opensys_eig: its couplings, its γ
             OQB_TRY(davies_cross(c, l, t.nk, a->d_A + (long long)t.k0 * ll, a->ncross, a->d_cross_idx, t.d_rate, R, X, nb));
+        if (!a->corr_terms.empty()) OQB_TRY(ame_corr_cross(a, nb, R, X));  // pairs (α,β) of a CorrelatedDaviesGenerator
         if (a->d_Moff) {
             ZgemmParams p;  // X += Moff R
             p.M = p.N = p.K = l; p.batch = nb;
@@ -90,7 +91,8 @@ int eig_apply(oqb_ame* a, int nb, const c128* R, c128* X, bool overwrite, bool w
             ZgemmParams q;  // X += R Moff'
             q.M = q.N = q.K = l; q.batch = nb;
             q.A = R; q.lda = l; q.strideA = ll;
-            q.B = a->d_Moff; q.ldb = l; q.strideB = 0; q.opB = OP_C;
+            if (a->d_Moff2) { q.B = a->d_Moff2; q.ldb = l; q.strideB = 0; }  // correlated pairs: the right-hand matrix is not Moff'
+            else { q.B = a->d_Moff; q.ldb = l; q.strideB = 0; q.opB = OP_C; }
             q.C = X; q.ldc = l; q.strideC = ll;
             q.beta = make_double2(1.0, 0.0);
             OQB_TRY(zgemm(c, q));
@@ -111,7 +113,7 @@ int eig_apply(oqb_ame* a, int nb, const c128* R, c128* X, bool overwrite, bool w
             ZgemmParams q;  // X_b += [Md_b1 | … | Md_bJ]·[L_1 | … | L_J]'   (depth J·l)
             q.M = q.N = l; q.K = jc * l; q.batch = nb;
             q.A = Md; q.lda = l; q.strideA = (long long)jc * ll;
-            q.B = a->d_Lstack + (long long)j0 * ll; q.ldb = l; q.strideB = 0; q.opB = OP_C;
+            q.B = (a->d_Rstack ? a->d_Rstack : a->d_Lstack) + (long long)j0 * ll; q.ldb = l; q.strideB = 0; q.opB = OP_C;
             q.real_operand = a->dense_real ? 2 : 0;
             q.C = X; q.ldc = l; q.strideC = ll;
             q.beta = make_double2(1.0, 0.0);
@@ -611,6 +613,7 @@ int oqb_ame_update_cache(oqb_ame* a, void* d_cache) {
     oqb_ctx* c = a->ctx;
     if (!a->have_eigen) return set_error(c, OQB_EINVAL, "oqb_ame_update_cache: call oqb_ame_set_eigen first");
     if (!d_cache) return set_error(c, OQB_EINVAL, "oqb_ame_update_cache: null cache");
+    if (a->has_corr) return set_error(c, OQB_EINVAL, "oqb_ame_update_cache: the reference defines no update_cache! for CorrelatedDaviesGenerator");
     const int n = a->n, l = a->lvl;
     const long long ll = (long long)l * l, ln = (long long)l * n;
     if (!a->has_v)

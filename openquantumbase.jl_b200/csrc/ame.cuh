@@ -11,6 +11,12 @@ struct DaviesTerm {
     double* d_rate = nullptr;  // ncross rates (owned)
 };
 
+// One (α,β) pair of a CorrelatedDaviesGenerator (src/opensys/davies.jl:231-296): A_β on the left, A_α' on the right.
+struct CorrTerm {
+    int ka = 0, kb = 0;
+    double* d_rate = nullptr;  // ncross rates (owned)
+};
+
 struct oqb_ame {
     oqb_ctx* ctx = nullptr;
     int n = 0, lvl = 0, K = 0;
@@ -53,6 +59,12 @@ struct oqb_ame {
     oqb::c128* d_Lstack = nullptr;  // nd lvl×lvl blocks side by side (an lvl × nd·lvl matrix)
     double* d_drate = nullptr;      // γ(x) per block
     bool dense_real = false;
+    // correlated pairs: right-hand operators differ from the left-hand ones
+    std::vector<CorrTerm> corr_terms;
+    bool has_corr = false;
+    oqb::c128* d_Rstack = nullptr;   // right-hand blocks (nullptr: same as d_Lstack)
+    oqb::c128* d_Moff2 = nullptr;    // −½G + iH_LS off-diagonal part applied on the RIGHT of ρ (nullptr: d_Moff')
+    oqb::c128* d_Mscratch = nullptr; // l×l scratch
     // one-sided AME
     int npairs = 0;
     std::vector<int32_t> h_beta;
@@ -95,6 +107,7 @@ extern "C" int ame_davies_alloc(oqb_ame* a);
 extern "C" int ame_clear_gaps(oqb_ame* a);      // ame_terms.cu
 extern "C" int ame_clear_terms(oqb_ame* a);     // ame_terms.cu: cross lists, dense blocks, per-term rates
 int ame_detect_real(oqb_ame* a, const oqb::c128* v, long long n, bool* out);  // ame.cu
+extern "C" int ame_corr_cross(oqb_ame* a, int nb, const oqb::c128* R, oqb::c128* X);  // ame_terms.cu
 extern "C" int ame_davies_finish(oqb_ame* a, int64_t ncross, const int32_t* h_cross_idx, const double* h_cross_rate, int64_t nlamb,
                       const int32_t* h_lamb_idx, const double* h_lamb_rate_S);
 

@@ -304,6 +304,101 @@ __global__ void term_cmat_acc_kernel(int l, int K, const c128* __restrict__ A, c
     Cm[e] = v;
 }
 
+// ---- correlated pair terms (CorrelatedDaviesGenerator, src/opensys/davies.jl:231-296): for one pair (α,β) the operators are
+// L = A_β∘[ω̃ == x] on the left and L_d' = (A_α∘[ω̃ == x])' on the right: γ(L ρ L_d' − ½{L_d'L, ρ}) − i[S·L_d'L, ρ].  The rank-one
+// products A_β[a,b]·conj(A_α[a,b]) are complex, so Γ, h and the rate matrix W are complex, and −½G ∓ iH_LS are two
+// different matrices (M1 on the left of ρ, M2 on the right) unless the pair set is symmetric.
+// one block per column b:  Γ_t[b] = Σ_a γ_ab conj(A_α[a,b])A_β[a,b],  h_t[b] with S;  Wt(+i·Wt_im)[b + a·l] += γ_ab A_β[a,b]conj(A_α[a,b])
+__global__ void corr_colsum_kernel(int l, const c128* __restrict__ Aa, const c128* __restrict__ Ab, const double* __restrict__ gam,
+                                   const double* __restrict__ S, c128* __restrict__ Gam_t, c128* __restrict__ hls_t, double* __restrict__ Wt,
+                                   double* __restrict__ Wt_im) {
+    const int b = blockIdx.x;
+    double gr = 0.0, gi = 0.0, hr = 0.0, hi = 0.0;
+    for (int a = threadIdx.x; a < l; a += blockDim.x) {
+        const c128 x = Aa[a + (long long)b * l], y = Ab[a + (long long)b * l];
+        const double pr = x.x * y.x + x.y * y.y, pi = x.x * y.y - x.y * y.x;  // conj(A_α)·A_β
+        const double g = gam[a + (long long)b * l], sv = S[a + (long long)b * l];
+        gr += g * pr; gi += g * pi;
+        hr += sv * pr; hi += sv * pi;
+        if (a != b) {  // W[a,b] = γ·A_β·conj(A_α) = the same product (conj(x)·y)
+            Wt[b + (long long)a * l] += g * pr;
+            Wt_im[b + (long long)a * l] += g * pi;
+        }
+    }
+    __shared__ double red[4][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        gr += __shfl_xor_sync(0xffffffffu, gr, o); gi += __shfl_xor_sync(0xffffffffu, gi, o);
+        hr += __shfl_xor_sync(0xffffffffu, hr, o); hi += __shfl_xor_sync(0xffffffffu, hi, o);
+    }
+    if (lane == 0) { red[0][warp] = gr; red[1][warp] = gi; red[2][warp] = hr; red[3][warp] = hi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int i = 0; i < (blockDim.x >> 5); ++i)
+            for (int k = 0; k < 4; ++k) t[k] += red[k][i];
+        Gam_t[b] = make_double2(t[0], t[1]);
+        hls_t[b] = make_double2(t[2], t[3]);
+    }
+}
+// Cm[a,b] += (−½Γ_a − i h_a) + (−½Γ_b + i h_b) + γ(0)·A_β[a,a]·conj(A_α[b,b])   (complex Γ, h; last term while the zero group is on the list)
+__global__ void corr_cmat_acc_kernel(int l, const c128* __restrict__ Aa, const c128* __restrict__ Ab, const c128* __restrict__ Gam_t,
+                                     const c128* __restrict__ hls_t, const double* __restrict__ g0p, int zero_dense, c128* __restrict__ Cm) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (long long)l * l) return;
+    const int a = (int)(e % l), b = (int)(e / l);
+    c128 v = Cm[e];
+    const c128 Ga = Gam_t[a], Gb = Gam_t[b], ha = hls_t[a], hb = hls_t[b];
+    v.x += -0.5 * Ga.x + ha.y - 0.5 * Gb.x - hb.y;   // −i·h = (h.y, −h.x);  +i·h = (−h.y, h.x)
+    v.y += -0.5 * Ga.y - ha.x - 0.5 * Gb.y + hb.x;
+    if (!zero_dense) {
+        const double g0 = *g0p;
+        const c128 p = Ab[a + (long long)a * l], q = Aa[b + (long long)b * l];
+        v.x += g0 * (p.x * q.x + p.y * q.y);
+        v.y += g0 * (p.y * q.x - p.x * q.y);
+    }
+    Cm[e] = v;
+}
+// X[b][a + a2·l] += rate·A_β[a,b]·conj(A_α[a2,b2])·R[b][b + b2·l]
+__global__ void corr_cross_kernel(int l, const c128* __restrict__ Aa, const c128* __restrict__ Ab, long long ncross, const int32_t* __restrict__ idx,
+                                  const double* __restrict__ rate, const c128* __restrict__ R, c128* __restrict__ X) {
+    const int bb = blockIdx.y;
+    const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (e >= ncross) return;
+    const int a = idx[4 * e], b = idx[4 * e + 1], a2 = idx[4 * e + 2], b2 = idx[4 * e + 3];
+    const c128 y = Ab[a + (long long)b * l], x = Aa[a2 + (long long)b2 * l];
+    const double r = rate[e];
+    const double sr = r * (y.x * x.x + y.y * x.y), si = r * (y.y * x.x - y.x * x.y);  // r·y·conj(x)
+    const c128 q = R[(long long)bb * l * l + b + (long long)b2 * l];
+    c128* d = X + (long long)bb * l * l + a + (long long)a2 * l;
+    atomicAdd(&d->x, sr * q.x - si * q.y);
+    atomicAdd(&d->y, sr * q.y + si * q.x);
+}
+// M1[b + b2·l] += (−½γ − iS)·conj(A_α[a,b])·A_β[a,b2],  M2[…] += (−½γ + iS)·(same)
+__global__ void corr_lamb_kernel(int l, const c128* __restrict__ Aa, const c128* __restrict__ Ab, long long nlamb, const int32_t* __restrict__ idx,
+                                 const double* __restrict__ rs, c128* __restrict__ M1, c128* __restrict__ M2) {
+    const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (e >= nlamb) return;
+    const int a = idx[3 * e], b = idx[3 * e + 1], b2 = idx[3 * e + 2];
+    const c128 x = Aa[a + (long long)b * l], y = Ab[a + (long long)b2 * l];
+    const double pr = x.x * y.x + x.y * y.y, pi = x.x * y.y - x.y * y.x;  // conj(x)·y
+    const double g = -0.5 * rs[2 * e], sv = rs[2 * e + 1];
+    atomicAdd(&M1[b + (long long)b2 * l].x, g * pr + sv * pi);   // (g − i·sv)(pr + i·pi)
+    atomicAdd(&M1[b + (long long)b2 * l].y, g * pi - sv * pr);
+    atomicAdd(&M2[b + (long long)b2 * l].x, g * pr - sv * pi);   // (g + i·sv)(pr + i·pi)
+    atomicAdd(&M2[b + (long long)b2 * l].y, g * pi + sv * pr);
+}
+
+// out = in' (l×l)
+__global__ void adjoint_kernel(int l, const c128* __restrict__ in, c128* __restrict__ out) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (long long)l * l) return;
+    const int a = (int)(e % l), b = (int)(e / l);
+    const c128 v = in[b + (long long)a * l];
+    out[e] = make_double2(v.x, -v.y);
+}
+
 __global__ void vec_add_kernel(int n, const double* __restrict__ x, double* __restrict__ y) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) y[i] += x[i];
@@ -518,6 +613,113 @@ int build_lists(oqb_ame* a) {
     return 0;
 }
 
+// Dense per-group blocks of one term: left operators A_left[k]∘[ω̃ == x], right operators A_right[k]∘[…] (nullptr: the same —
+// a DaviesGenerator; a correlated pair has A_β on the left and A_α on the right).  Appends to the handle's stacks and adds
+// (−½γ ∓ iS)·L_d'L to the off-diagonal matrices.
+int add_dense_blocks(oqb_ame* a, const c128* A, const c128* Ar, int nk, const double* d_vals) {
+    oqb_ctx* c = a->ctx;
+    const int l = a->lvl;
+    const long long ll = (long long)l * l, ng = a->ng;
+    const int ndg = (int)a->h_dense_groups.size();
+    const int nslots = 2 * ndg + (a->zero_dense ? 1 : 0);
+    if (nslots == 0) return 0;
+    const bool pair = Ar != nullptr;
+    const int zero_slot = a->zero_dense ? 2 * ndg : -1;
+    // squared norms of every candidate block and of the couplings themselves; γ, S of the slots
+    const size_t nnorm = (size_t)nslots * nk + nk;
+    double* d_norm = nullptr;
+    OQB_TRY(ame_alloc(c, (void**)&d_norm, 2 * nnorm * sizeof(double)));
+    OQB_CUDA(c, cudaMemsetAsync(d_norm, 0, 2 * nnorm * sizeof(double), c->stream));
+    dim3 gridn(std::min<unsigned>(cdivu(ll, 256), 1184u), (unsigned)nk);
+    dense_norm_kernel<<<gridn, 256, 0, c->stream>>>(l, nk, A, a->d_gid, a->d_gslot, zero_slot, d_norm, d_norm + (size_t)nslots * nk);
+    if (pair) dense_norm_kernel<<<gridn, 256, 0, c->stream>>>(l, nk, Ar, a->d_gid, a->d_gslot, zero_slot, d_norm + nnorm, d_norm + nnorm + (size_t)nslots * nk);
+    c->launches += pair ? 2 : 1;
+    std::vector<double> h_norm(2 * nnorm);
+    cudaError_t e = cudaMemcpyAsync(h_norm.data(), d_norm, h_norm.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+    std::vector<double> h_g(nslots), h_S(nslots);
+    auto fetch = [&](double* dst, long long index) {
+        if (e == cudaSuccess) e = cudaMemcpyAsync(dst, d_vals + index, sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+    };
+    for (int d = 0; d < ndg; ++d) {
+        const long long g = a->h_dense_groups[d];
+        fetch(&h_g[2 * d], g); fetch(&h_g[2 * d + 1], ng + g);
+        fetch(&h_S[2 * d], 2 * ng + g); fetch(&h_S[2 * d + 1], 3 * ng + g);
+    }
+    if (a->zero_dense) { fetch(&h_g[2 * ndg], 4 * ng); fetch(&h_S[2 * ndg], 4 * ng + 1); }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFreeAsync(d_norm, c->stream);
+    if (e != cudaSuccess) return set_error(c, OQB_ECUDA, "oqb_ame_add_davies: %s", cudaGetErrorString(e));
+    // keep the blocks that matter: ‖L‖² ≤ 1e-26·‖A_k‖² contributes ≤ 1e-26 relative (eigenvectors of a degenerate level
+    // leave "forbidden" blocks at rounding level, ≈1e-32)
+    std::vector<int32_t> bslot, bk;
+    std::vector<double> brate;
+    std::vector<c128> bcoef;
+    for (int sl = 0; sl < nslots; ++sl)
+        for (int k = 0; k < nk; ++k) {
+            if (!(h_norm[(size_t)sl * nk + k] > 1e-26 * h_norm[(size_t)nslots * nk + k])) continue;
+            if (pair && !(h_norm[nnorm + (size_t)sl * nk + k] > 1e-26 * h_norm[nnorm + (size_t)nslots * nk + k])) continue;
+            if (h_g[sl] == 0.0 && h_S[sl] == 0.0) continue;
+            bslot.push_back(sl);
+            bk.push_back(k);
+            brate.push_back(h_g[sl]);
+            bcoef.push_back(make_double2(-0.5 * h_g[sl], -h_S[sl]));  // −½γ − iS
+        }
+    const int nb_new = (int)bslot.size();
+    if (nb_new == 0) return 0;
+    const size_t blk_bytes = (size_t)ll * sizeof(c128);
+    const bool need_right = pair || a->d_Rstack != nullptr;
+    if (((size_t)a->nd + nb_new) * blk_bytes * (need_right ? 2 : 1) > ((size_t)24 << 30))
+        return set_error(c, OQB_ENOMEM, "oqb_ame_add_davies: %d dense gap-group blocks of %d×%d exceed the 24 GiB budget", a->nd + nb_new, l, l);
+    if (pair && !a->d_Rstack && a->nd > 0) {  // earlier DaviesGenerator blocks: right = left
+        OQB_TRY(ame_alloc(c, (void**)&a->d_Rstack, (size_t)a->nd * blk_bytes));
+        OQB_CUDA(c, cudaMemcpyAsync(a->d_Rstack, a->d_Lstack, (size_t)a->nd * blk_bytes, cudaMemcpyDeviceToDevice, c->stream));
+    }
+    OQB_TRY(grow(c, a->d_Lstack, (size_t)a->nd * ll, ((size_t)a->nd + nb_new) * ll));
+    if (need_right) OQB_TRY(grow(c, a->d_Rstack, (size_t)a->nd * ll, ((size_t)a->nd + nb_new) * ll));
+    OQB_TRY(grow(c, a->d_drate, (size_t)a->nd, (size_t)a->nd + nb_new));
+    int32_t* d_b = nullptr;
+    OQB_TRY(ame_alloc(c, (void**)&d_b, (size_t)2 * nb_new * sizeof(int32_t)));
+    OQB_CUDA(c, cudaMemcpyAsync(d_b, bslot.data(), nb_new * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+    OQB_CUDA(c, cudaMemcpyAsync(d_b + nb_new, bk.data(), nb_new * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+    OQB_CUDA(c, cudaMemcpyAsync(a->d_drate + a->nd, brate.data(), nb_new * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    c128* Lnew = a->d_Lstack + (long long)a->nd * ll;
+    c128* Rnew = need_right ? a->d_Rstack + (long long)a->nd * ll : Lnew;
+    for (int j0 = 0; j0 < nb_new; j0 += 65535) {
+        const int cnt = nb_new - j0 < 65535 ? nb_new - j0 : 65535;
+        dim3 gridm(std::min<unsigned>(cdivu(ll, 256), 1184u), (unsigned)cnt);
+        dense_mask_kernel<<<gridm, 256, 0, c->stream>>>(l, A, a->d_gid, a->d_gslot, zero_slot, d_b + j0, d_b + nb_new + j0, Lnew + (long long)j0 * ll);
+        OQB_LAUNCH_CHECK(c);
+        if (need_right) {
+            dense_mask_kernel<<<gridm, 256, 0, c->stream>>>(l, pair ? Ar : A, a->d_gid, a->d_gslot, zero_slot, d_b + j0, d_b + nb_new + j0,
+                                                            Rnew + (long long)j0 * ll);
+            OQB_LAUNCH_CHECK(c);
+        }
+    }
+    OQB_CUDA(c, cudaStreamSynchronize(c->stream));  // host vectors were the copy sources
+    cudaFreeAsync(d_b, c->stream);
+    // M1 += (−½γ − iS) L_d'L per block (and M2 += (−½γ + iS) L_d'L when the two differ)
+    for (int j = 0; j < nb_new; ++j) {
+        ZgemmParams p;
+        p.M = p.N = p.K = l;
+        p.opA = OP_C;
+        p.A = Rnew + (long long)j * ll; p.lda = l;
+        p.B = Lnew + (long long)j * ll; p.ldb = l;
+        p.C = a->d_Moff; p.ldc = l;
+        p.alpha = bcoef[j];
+        p.beta = make_double2(1.0, 0.0);
+        OQB_TRY(zgemm(c, p));
+        if (a->d_Moff2) {
+            p.C = a->d_Moff2;
+            p.alpha = make_double2(bcoef[j].x, -bcoef[j].y);
+            OQB_TRY(zgemm(c, p));
+        }
+    }
+    a->nd += nb_new;
+    OQB_TRY(ame_detect_real(a, a->d_Lstack, (long long)a->nd * ll, &a->dense_real));
+    if (a->d_Rstack && a->dense_real) OQB_TRY(ame_detect_real(a, a->d_Rstack, (long long)a->nd * ll, &a->dense_real));
+    return 0;
+}
+
 // Adds one DaviesGenerator whose per-key values are in d_vals (device, layout of term_vals_ohmic_kernel).
 int add_davies_impl(oqb_ame* a, int k0, int nk, const double* d_vals) {
     oqb_ctx* c = a->ctx;
@@ -575,90 +777,84 @@ int add_davies_impl(oqb_ame* a, int k0, int nk, const double* d_vals) {
         term_rate_kernel<<<cdivu(a->nlamb, 256), 256, 0, c->stream>>>(a->nlamb, a->d_lamb_g, ng, d_vals, nullptr, d_rs);
         c->launches++;
         st = davies_lamb_build(c, l, nk, A, a->nlamb, a->d_lamb_idx, d_rs, a->d_Moff);
+        if (!st && a->d_Moff2) {  // a correlated term is present: the right-hand matrix is kept separately (= M1' for this term)
+            for (int k = 0; k < nk && !st; ++k) {
+                corr_lamb_kernel<<<cdivu(a->nlamb, 256), 256, 0, c->stream>>>(l, A + (long long)k * ll, A + (long long)k * ll, a->nlamb, a->d_lamb_idx, d_rs,
+                                                                             a->d_Mscratch, a->d_Moff2);
+                c->launches++;
+            }
+        }
         cudaFreeAsync(d_rs, c->stream);
         if (st) return st;
     }
-    // ---- dense per-group blocks -------------------------------------------------------------------------------------
-    const int ndg = (int)a->h_dense_groups.size();
-    const int nslots = 2 * ndg + (a->zero_dense ? 1 : 0);
-    if (nslots > 0) {
-        const int zero_slot = a->zero_dense ? 2 * ndg : -1;
-        // squared norms of every candidate block and of the couplings themselves; γ, S of the slots
-        double* d_norm = nullptr;
-        OQB_TRY(ame_alloc(c, (void**)&d_norm, ((size_t)nslots * nk + nk) * sizeof(double)));
-        OQB_CUDA(c, cudaMemsetAsync(d_norm, 0, ((size_t)nslots * nk + nk) * sizeof(double), c->stream));
-        dim3 gridn(std::min<unsigned>(cdivu(ll, 256), 1184u), (unsigned)nk);
-        dense_norm_kernel<<<gridn, 256, 0, c->stream>>>(l, nk, A, a->d_gid, a->d_gslot, zero_slot, d_norm, d_norm + (size_t)nslots * nk);
-        c->launches++;
-        std::vector<double> h_norm((size_t)nslots * nk + nk);
-        cudaError_t e = cudaMemcpyAsync(h_norm.data(), d_norm, h_norm.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
-        // γ, S per slot from the device values (a few scalars)
-        std::vector<double> h_g(nslots), h_S(nslots);
-        auto fetch = [&](double* dst, long long index) {
-            if (e == cudaSuccess) e = cudaMemcpyAsync(dst, d_vals + index, sizeof(double), cudaMemcpyDeviceToHost, c->stream);
-        };
-        for (int d = 0; d < ndg; ++d) {
-            const long long g = a->h_dense_groups[d];
-            fetch(&h_g[2 * d], g); fetch(&h_g[2 * d + 1], ng + g);
-            fetch(&h_S[2 * d], 2 * ng + g); fetch(&h_S[2 * d + 1], 3 * ng + g);
-        }
-        if (a->zero_dense) { fetch(&h_g[2 * ndg], 4 * ng); fetch(&h_S[2 * ndg], 4 * ng + 1); }
-        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-        cudaFreeAsync(d_norm, c->stream);
-        if (e != cudaSuccess) return set_error(c, OQB_ECUDA, "oqb_ame_add_davies: %s", cudaGetErrorString(e));
-        // keep the blocks that matter: ‖L‖² ≤ 1e-26·‖A_k‖² contributes ≤ 1e-26 relative (eigenvectors of a degenerate level
-        // leave "forbidden" blocks at rounding level, ≈1e-32)
-        std::vector<int32_t> bslot, bk;
-        std::vector<double> brate;
-        std::vector<c128> bcoef;
-        for (int s = 0; s < nslots; ++s)
-            for (int k = 0; k < nk; ++k) {
-                const double tot = h_norm[(size_t)nslots * nk + k];
-                if (!(h_norm[(size_t)s * nk + k] > 1e-26 * tot)) continue;
-                if (h_g[s] == 0.0 && h_S[s] == 0.0) continue;
-                bslot.push_back(s);
-                bk.push_back(k);
-                brate.push_back(h_g[s]);
-                bcoef.push_back(make_double2(-0.5 * h_g[s], -h_S[s]));  // −½γ − iS
-            }
-        const int nb_new = (int)bslot.size();
-        if (nb_new > 0) {
-            const size_t blk_bytes = (size_t)ll * sizeof(c128);
-            if (((size_t)a->nd + nb_new) * blk_bytes > ((size_t)24 << 30))
-                return set_error(c, OQB_ENOMEM, "oqb_ame_add_davies: %d dense gap-group blocks of %d×%d exceed the 24 GiB budget",
-                                 a->nd + nb_new, l, l);
-            OQB_TRY(grow(c, a->d_Lstack, (size_t)a->nd * ll, ((size_t)a->nd + nb_new) * ll));
-            OQB_TRY(grow(c, a->d_drate, (size_t)a->nd, (size_t)a->nd + nb_new));
-            int32_t* d_b = nullptr;
-            OQB_TRY(ame_alloc(c, (void**)&d_b, (size_t)2 * nb_new * sizeof(int32_t)));
-            OQB_CUDA(c, cudaMemcpyAsync(d_b, bslot.data(), nb_new * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
-            OQB_CUDA(c, cudaMemcpyAsync(d_b + nb_new, bk.data(), nb_new * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
-            OQB_CUDA(c, cudaMemcpyAsync(a->d_drate + a->nd, brate.data(), nb_new * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-            c128* Lnew = a->d_Lstack + (long long)a->nd * ll;
-            for (int j0 = 0; j0 < nb_new; j0 += 65535) {
-                const int cnt = nb_new - j0 < 65535 ? nb_new - j0 : 65535;
-                dim3 gridm(std::min<unsigned>(cdivu(ll, 256), 1184u), (unsigned)cnt);
-                dense_mask_kernel<<<gridm, 256, 0, c->stream>>>(l, A, a->d_gid, a->d_gslot, zero_slot, d_b + j0, d_b + nb_new + j0, Lnew + (long long)j0 * ll);
-                OQB_LAUNCH_CHECK(c);
-            }
-            OQB_CUDA(c, cudaStreamSynchronize(c->stream));  // host vectors were the copy sources
-            cudaFreeAsync(d_b, c->stream);
-            // Moff += (−½γ − iS) L'L per block
-            for (int j = 0; j < nb_new; ++j) {
-                ZgemmParams p;
-                p.M = p.N = p.K = l;
-                p.opA = OP_C;
-                p.A = Lnew + (long long)j * ll; p.lda = l;
-                p.B = Lnew + (long long)j * ll; p.ldb = l;
-                p.C = a->d_Moff; p.ldc = l;
-                p.alpha = bcoef[j];
-                p.beta = make_double2(1.0, 0.0);
-                OQB_TRY(zgemm(c, p));
-            }
-            a->nd += nb_new;
-            OQB_TRY(ame_detect_real(a, a->d_Lstack, (long long)a->nd * ll, &a->dense_real));
-        }
+    OQB_TRY(add_dense_blocks(a, A, nullptr, nk, d_vals));
+    OQB_CUDA(c, cudaStreamSynchronize(c->stream));
+    a->davies = true;
+    return 0;
+}
+
+// Adds one pair (α,β) of a CorrelatedDaviesGenerator; d_vals as for add_davies_impl (γ_αβ, S_αβ at the keys).
+int add_correlated_impl(oqb_ame* a, int ka, int kb, const double* d_vals) {
+    oqb_ctx* c = a->ctx;
+    const int l = a->lvl;
+    const long long ll = (long long)l * l, ng = a->ng;
+    if (!a->lists_built) OQB_TRY(build_lists(a));
+    const c128* Aa = a->d_A + (long long)ka * ll;
+    const c128* Ab = a->d_A + (long long)kb * ll;
+    if (!a->d_Wt) {
+        OQB_TRY(ame_alloc(c, (void**)&a->d_Gam, l * sizeof(double)));
+        OQB_TRY(ame_alloc(c, (void**)&a->d_hls, l * sizeof(double)));
+        OQB_TRY(ame_alloc(c, (void**)&a->d_Wt, (size_t)ll * sizeof(double)));
+        OQB_CUDA(c, cudaMemsetAsync(a->d_Gam, 0, l * sizeof(double), c->stream));
+        OQB_CUDA(c, cudaMemsetAsync(a->d_hls, 0, l * sizeof(double), c->stream));
+        OQB_CUDA(c, cudaMemsetAsync(a->d_Wt, 0, (size_t)ll * sizeof(double), c->stream));
     }
+    if (!a->d_Wt_im) {
+        OQB_TRY(ame_alloc(c, (void**)&a->d_Wt_im, (size_t)ll * sizeof(double)));
+        OQB_CUDA(c, cudaMemsetAsync(a->d_Wt_im, 0, (size_t)ll * sizeof(double), c->stream));
+    }
+    // M1 (left of ρ) and M2 (right of ρ) are kept separately from now on; M2 starts as M1' of what is there already
+    if (!a->d_Moff) {
+        OQB_TRY(ame_alloc(c, (void**)&a->d_Moff, (size_t)ll * sizeof(c128)));
+        OQB_CUDA(c, cudaMemsetAsync(a->d_Moff, 0, (size_t)ll * sizeof(c128), c->stream));
+    }
+    if (!a->d_Moff2) {
+        OQB_TRY(ame_alloc(c, (void**)&a->d_Moff2, (size_t)ll * sizeof(c128)));
+        OQB_TRY(ame_alloc(c, (void**)&a->d_Mscratch, (size_t)ll * sizeof(c128)));
+        adjoint_kernel<<<cdivu(ll, 256), 256, 0, c->stream>>>(l, a->d_Moff, a->d_Moff2);
+        OQB_LAUNCH_CHECK(c);
+    }
+    a->has_corr = true;
+    double* d_tab = nullptr;
+    OQB_TRY(ame_alloc(c, (void**)&d_tab, ((size_t)2 * ll + 4 * l) * sizeof(double)));
+    double* d_gam = d_tab;
+    double* d_S = d_tab + ll;
+    c128* d_Gt = (c128*)(d_S + ll);
+    c128* d_ht = d_Gt + l;
+    term_table_kernel<<<cdivu(ll, 256), 256, 0, c->stream>>>(l, a->d_gid, a->d_gslot, a->zero_dense ? 1 : 0, ng, d_vals, d_gam, d_S);
+    corr_colsum_kernel<<<l, 256, 0, c->stream>>>(l, Aa, Ab, d_gam, d_S, d_Gt, d_ht, a->d_Wt, a->d_Wt_im);
+    corr_cmat_acc_kernel<<<cdivu(ll, 256), 256, 0, c->stream>>>(l, Aa, Ab, d_Gt, d_ht, d_vals + 4 * ng, a->zero_dense ? 1 : 0, a->d_Cm);
+    c->launches += 3;
+    cudaError_t e = cudaGetLastError();
+    cudaFreeAsync(d_tab, c->stream);
+    if (e != cudaSuccess) return set_error(c, OQB_ECUDA, "oqb_ame_add_correlated: kernel launch failed: %s", cudaGetErrorString(e));
+    CorrTerm t;
+    t.ka = ka; t.kb = kb;
+    if (a->ncross > 0) {
+        OQB_TRY(ame_alloc(c, (void**)&t.d_rate, (size_t)a->ncross * sizeof(double)));
+        term_rate_kernel<<<cdivu(a->ncross, 256), 256, 0, c->stream>>>(a->ncross, a->d_cross_g, ng, d_vals, t.d_rate, nullptr);
+        OQB_LAUNCH_CHECK(c);
+    }
+    a->corr_terms.push_back(t);
+    if (a->nlamb > 0) {
+        double* d_rs = nullptr;
+        OQB_TRY(ame_alloc(c, (void**)&d_rs, (size_t)a->nlamb * 2 * sizeof(double)));
+        term_rate_kernel<<<cdivu(a->nlamb, 256), 256, 0, c->stream>>>(a->nlamb, a->d_lamb_g, ng, d_vals, nullptr, d_rs);
+        corr_lamb_kernel<<<cdivu(a->nlamb, 256), 256, 0, c->stream>>>(l, Aa, Ab, a->nlamb, a->d_lamb_idx, d_rs, a->d_Moff, a->d_Moff2);
+        c->launches += 2;
+        cudaFreeAsync(d_rs, c->stream);
+    }
+    OQB_TRY(add_dense_blocks(a, Ab, Aa, 1, d_vals));
     OQB_CUDA(c, cudaStreamSynchronize(c->stream));
     a->davies = true;
     return 0;
@@ -690,7 +886,13 @@ int ame_clear_terms(oqb_ame* a) {
     ame_free(c, a->d_lamb_g);
     ame_free(c, a->d_gslot);
     ame_free(c, a->d_Lstack);
+    ame_free(c, a->d_Rstack);
     ame_free(c, a->d_drate);
+    for (CorrTerm& t : a->corr_terms) ame_free(c, t.d_rate);
+    a->corr_terms.clear();
+    ame_free(c, a->d_Moff2);
+    ame_free(c, a->d_Mscratch);
+    a->has_corr = false;
     a->h_dense_groups.clear();
     a->zero_dense = false;
     a->lists_built = false;
@@ -876,6 +1078,51 @@ int oqb_ame_add_davies_ohmic(oqb_ame* a, int k0, int nk, double eta, double wc, 
     cudaStreamSynchronize(c->stream);
     cudaFreeAsync(d_vals, c->stream);
     return st;
+}
+
+int oqb_ame_add_correlated(oqb_ame* a, int alpha, int beta, const double* h_gamma_plus, const double* h_gamma_minus, const double* h_S_plus,
+                           const double* h_S_minus, double gamma0, double S0) {
+    if (!a) return OQB_EINVAL;
+    OQB_DEVICE(a, a->ctx);
+    oqb_ctx* c = a->ctx;
+    if (!a->have_gaps) return set_error(c, OQB_EINVAL, "oqb_ame_add_correlated: call oqb_ame_gaps_build first");
+    if (alpha < 0 || alpha >= a->K || beta < 0 || beta >= a->K) return set_error(c, OQB_EINVAL, "oqb_ame_add_correlated: coupling index out of range");
+    const long long ng = a->ng;
+    if (ng > 0 && (!h_gamma_plus || !h_gamma_minus)) return set_error(c, OQB_EINVAL, "oqb_ame_add_correlated: null rate array");
+    std::vector<double> vals((size_t)4 * ng + 2, 0.0);
+    for (long long g = 0; g < ng; ++g) {
+        vals[g] = h_gamma_plus[g];
+        vals[ng + g] = h_gamma_minus[g];
+        vals[2 * ng + g] = h_S_plus ? h_S_plus[g] : 0.0;
+        vals[3 * ng + g] = h_S_minus ? h_S_minus[g] : 0.0;
+    }
+    vals[4 * ng] = gamma0;
+    vals[4 * ng + 1] = S0;
+    double* d_vals = nullptr;
+    OQB_TRY(ame_alloc(c, (void**)&d_vals, vals.size() * sizeof(double)));
+    cudaError_t e = cudaMemcpyAsync(d_vals, vals.data(), vals.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    int st = e == cudaSuccess ? add_correlated_impl(a, alpha, beta, d_vals) : set_error(c, OQB_ECUDA, "oqb_ame_add_correlated: %s", cudaGetErrorString(e));
+    cudaStreamSynchronize(c->stream);
+    cudaFreeAsync(d_vals, c->stream);
+    return st;
+}
+
+// cross terms of the correlated pairs (called by eig_apply in ame.cu)
+int ame_corr_cross(oqb_ame* a, int nb, const c128* R, c128* X) {
+    oqb_ctx* c = a->ctx;
+    const int l = a->lvl;
+    const long long ll = (long long)l * l;
+    if (a->ncross <= 0) return 0;
+    for (const CorrTerm& t : a->corr_terms)
+        for (int b0 = 0; b0 < nb; b0 += 65535) {
+            const int cnt = nb - b0 < 65535 ? nb - b0 : 65535;
+            dim3 grid(cdivu(a->ncross, 256), cnt);
+            corr_cross_kernel<<<grid, 256, 0, c->stream>>>(l, a->d_A + (long long)t.ka * ll, a->d_A + (long long)t.kb * ll, a->ncross, a->d_cross_idx,
+                                                           t.d_rate, R + (long long)b0 * ll, X + (long long)b0 * ll);
+            OQB_LAUNCH_CHECK(c);
+        }
+    return 0;
 }
 
 int oqb_ame_davies_stats(const oqb_ame* a, int64_t* n_terms, int64_t* n_cross, int64_t* n_lamb, int64_t* n_dense_groups, int64_t* n_dense_blocks) {

@@ -3,6 +3,8 @@ same device entry points as the main types:
 
   ConstDaviesGenerator   src/opensys/davies.jl:102-119   → oqb_dense_rhs (H = H_LS, L_k = Linds, γ ≡ 1) + oqb_axpy_batched
   ConstHDaviesGenerator  src/opensys/davies.jl:121-163   → the closed-form Davies tables in a fixed basis (oqb_ame_* with v = I)
+  CorrelatedDaviesGenerator / ConstHCorrelatedDaviesGenerator  src/opensys/davies.jl:220-345 → oqb_ame_gaps_build + one
+                                                           oqb_ame_add_correlated per (α,β) pair (degenerate groups included)
   FluctuatorLiouvillian  src/opensys/stochastic.jl:11-44 → oqb_dense_rhs / update_cache / update_vectorized_cache with the
                                                            noise values n_i as per-member coefficients
 
@@ -151,14 +153,10 @@ class ConstHDaviesGenerator:
 
 
 class CorrelatedDaviesGenerator:
-    """src/opensys/davies.jl:220-296 (also ConstHCorrelatedDaviesGenerator :298-345).  coupling: K matrices (or
-    callables of s); gamma, S: dicts keyed by the 1-based (α,β) pairs of `inds` (array-wise closures welcome).
-    Evaluated through the general closed-form tables (`oqb_ame_set_tables`): for a gap structure whose non-zero
-    groups are single pairs,  X = Cm∘ρ̃ + diag(W·diag ρ̃)  with
-        W[a,b]   = Σ_(α,β) γ_αβ(ω_ab)·A_β[a,b]·conj(A_α[a,b])          (a ≠ b)
-        Cm[a,a'] = −i(w_a−w_a') + Σ γ_αβ(0)A_β[a,a]conj(A_α[a',a']) − ½(G_a+G_a') − i(h_a−h_a'),
-        G_b = Σ_a W[a,b] + Σ γ_αβ(0)conj(A_α[b,b])A_β[b,b],   h_b likewise with S.
-    Degenerate gap groups (several pairs per group) are not on the device path."""
+    """src/opensys/davies.jl:220-296.  coupling: K matrices (or callables of s); gamma, S: dicts keyed by the 1-based (α,β)
+    pairs of `inds` (array-wise closures welcome).  Each pair is one `oqb_ame_add_correlated` call on top of the library's
+    GapIndices (csrc/ame_terms.cu): single-pair gap groups go into complex closed-form tables, degenerate groups onto the
+    cross-term list or the dense per-group products (left operator from A_β, right from A_α)."""
 
     def __init__(self, coupling, gamma, S, inds, digits=8, sigdigits=8, ctx: Optional[Context] = None):
         self.coupling, self.gamma, self.S = list(coupling), gamma, S
@@ -168,8 +166,12 @@ class CorrelatedDaviesGenerator:
         self._ame, self._key = None, None
 
     def _plan(self, w, v, s):
+        import hashlib
         lib, ctx = self.ctx.lib, self.ctx
-        key = (float(s), tuple(np.asarray(w).tolist()), None if v is None else id(v))
+        hh = hashlib.blake2b(np.ascontiguousarray(w, dtype=np.float64).tobytes(), digest_size=16)
+        if v is not None:
+            hh.update(np.ascontiguousarray(v).tobytes())
+        key = (float(s), hh.hexdigest())
         if self._ame is not None and self._key == key:
             return self._ame
         if self._ame is not None:
@@ -178,9 +180,6 @@ class CorrelatedDaviesGenerator:
         coup = [np.asarray(c(s) if callable(c) else c, dtype=C128) for c in self.coupling]
         w = np.ascontiguousarray(np.real(w), dtype=np.float64)
         l, n, K = len(w), coup[0].shape[0], len(coup)
-        groups = GapGroups(w, self.digits, self.sigdigits)
-        if len(groups.cross_idx):
-            raise NotImplementedError("CorrelatedDaviesGenerator with degenerate gap groups is not on the device path")
         h = C.c_void_p()
         cbuf = _colmajor_stack(coup)
         ctx.check(lib.oqb_ame_create(ctx.h, n, l, K, cbuf.ctypes.data, C.byref(h)))
@@ -189,34 +188,17 @@ class CorrelatedDaviesGenerator:
         else:
             vbuf = np.ascontiguousarray(np.asarray(v, dtype=C128).T)
             ctx.check(lib.oqb_ame_set_eigen(h, _lib.dptr(w), vbuf.ctypes.data))
-        Abuf = np.empty((K, l, l), dtype=C128)
-        ctx.check(lib.oqb_ame_get_rotated_couplings(h, Abuf.ctypes.data))
-        A = Abuf.transpose(0, 2, 1)  # (K, row, col)
-        om = groups.omega
-        off = ~np.eye(l, dtype=bool)
-        W = np.zeros((l, l), dtype=C128)
-        Hoff = np.zeros((l, l), dtype=C128)
-        Z = np.zeros((l, l), dtype=C128)
-        g0d = np.zeros(l, dtype=C128)
-        h0d = np.zeros(l, dtype=C128)
+        nk_, nz_ = C.c_int64(), C.c_int64()
+        ctx.check(lib.oqb_ame_gaps_build(h, self.digits, self.sigdigits, C.byref(nk_), C.byref(nz_)))
+        keys = np.empty(nk_.value, dtype=np.float64)
+        ctx.check(lib.oqb_ame_gaps_keys(h, _lib.dptr(keys)))
         zero = np.zeros(1)
-        for (al, be) in self.inds:
-            Aa, Ab = A[al - 1], A[be - 1]
-            prod = Ab * Aa.conj()
-            W += np.where(off, _eval(self.gamma[(al, be)], om.ravel()).reshape(l, l), 0.0) * prod
-            Hoff += np.where(off, _eval(self.S[(al, be)], om.ravel()).reshape(l, l), 0.0) * prod
-            g0 = float(_eval(self.gamma[(al, be)], zero)[0])
-            s0 = float(_eval(self.S[(al, be)], zero)[0])
-            da, db = np.diag(Aa), np.diag(Ab)
-            Z += g0 * np.outer(db, da.conj())
-            g0d += g0 * da.conj() * db
-            h0d += s0 * da.conj() * db
-        G = W.sum(axis=0) + g0d
-        hl = Hoff.sum(axis=0) + h0d
-        Cm = -1j * (w[:, None] - w[None, :]) + Z - 0.5 * (G[:, None] + G[None, :]) - 1j * (hl[:, None] - hl[None, :])
-        cmbuf = np.ascontiguousarray(Cm.T)
-        wre, wim = np.ascontiguousarray(W.real), np.ascontiguousarray(W.imag)
-        ctx.check(lib.oqb_ame_set_tables(h, cmbuf.ctypes.data, _lib.dptr(wre), _lib.dptr(wim)))
+        for (al, be) in self.inds:  # one library call per (α,β): γ_αβ, S_αβ at the distinct gap keys (davies.jl:235-238)
+            g, S_ = self.gamma[(al, be)], self.S[(al, be)]
+            gp, gm = np.ascontiguousarray(_eval(g, keys)), np.ascontiguousarray(_eval(g, -keys))
+            sp_, sm_ = np.ascontiguousarray(_eval(S_, keys)), np.ascontiguousarray(_eval(S_, -keys))
+            ctx.check(lib.oqb_ame_add_correlated(h, al - 1, be - 1, _lib.dptr(gp), _lib.dptr(gm), _lib.dptr(sp_), _lib.dptr(sm_),
+                                                 float(_eval(g, zero)[0]), float(_eval(S_, zero)[0])))
         self._ame, self._key = h, key
         return h
 
@@ -227,6 +209,19 @@ class CorrelatedDaviesGenerator:
         io = _HostIO(rho, du)
         self.ctx.check(self.ctx.lib.oqb_ame_eig_acc(self._plan(w, v, s), io.u.B, io.u.ptr, io.du.ptr, 0))
         return io.finish()
+
+
+class ConstHCorrelatedDaviesGenerator(CorrelatedDaviesGenerator):
+    """src/opensys/davies.jl:297-345 (`build_const_correlated_davies`): constant Hamiltonian — the GapIndices of its
+    eigen-energies `w` are fixed at construction —, couplings given in the eigenbasis (possibly s-dependent).
+    (D)(du, ρ, _, s) ACCUMULATES the correlated Davies terms of ρ in that basis."""
+
+    def __init__(self, w, coupling, gamma, S, inds, digits=8, sigdigits=8, ctx: Optional[Context] = None):
+        super().__init__(coupling, gamma, S, inds, digits, sigdigits, ctx)
+        self.w = np.ascontiguousarray(np.real(w), dtype=np.float64)
+
+    def __call__(self, du, rho, _unused, s):
+        return super().__call__(du, rho, self.w, s)
 
 
 class FluctuatorLiouvillian:

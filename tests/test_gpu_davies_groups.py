@@ -297,3 +297,53 @@ def test_library_liouvillian_degenerate_start(Q):
         du = opg(np.zeros_like(u), u, pg, t)
         ref = np.stack([opo.rhs(x, po, t) for x in u])
         assert relerr(du, ref) < 1e-10, t
+
+
+# ---- CorrelatedDaviesGenerator / ConstHCorrelatedDaviesGenerator on DEGENERATE gap structures -------------------------
+@pytest.mark.parametrize("thr", [0, 2, 10 ** 9])
+@pytest.mark.parametrize("with_v", [False, True])
+def test_correlated_davies_degenerate_groups(Q, thr, with_v):
+    """src/opensys/davies.jl:231-296 with multi-pair gap groups and a non-trivial zero group (degenerate, equally spaced and
+    generic levels mixed), a NON-symmetric pair set (so −½G ∓ iH_LS are two different matrices), complex couplings — against
+    the oracle's literal loop, with every gap group forced onto the dense path, onto the list, and by the cost model."""
+    from oqb_b200.extra_liouvillians import CorrelatedDaviesGenerator
+    rng = np.random.default_rng(55)
+    n, K, nb = 14, 3, 3
+    w = np.sort(np.r_[np.repeat([-1.5, 0.25], 3), np.arange(4) * 0.5 + 1.0, rng.standard_normal(n - 10) * 2])
+    v = np.linalg.qr(rand_c(rng, n, n))[0]
+    coup = [rand_c(rng, n, n) for _ in range(K)]
+    inds = [(1, 2), (2, 1), (1, 3), (2, 2)]  # (3,1) missing on purpose
+    gd = {pq: (lambda x, c=0.3 * (pq[0] + 2 * pq[1]): gamma(x) * c) for pq in inds}
+    Sd = {pq: (lambda x, c=0.1 * pq[0]: lamb(x) * c) for pq in inds}
+    ctx = Q.get_context()
+    Dg = CorrelatedDaviesGenerator(coup, gd, Sd, inds)
+    Do = O.CorrelatedDaviesGenerator(coup, gd, Sd, inds)
+    G = O.build_gap_indices(w, 8, 8)
+    rho = rand_c(rng, nb, n, n)
+    du0 = rand_c(rng, nb, n, n)
+    with ctx.option("davies_dense_min_pairs", thr), ctx.option("debug_checks", 1):
+        got = Dg(du0.copy(), rho, w, v, 0.4) if with_v else Dg(du0.copy(), rho, w, 0.4)
+    ref = np.stack([Do.rhs_acc(du0[b].copy(), rho[b], G, v if with_v else None, 0.4) for b in range(nb)])
+    assert relerr(got, ref) < TOL
+
+
+def test_const_h_correlated_davies(Q):
+    """ConstHCorrelatedDaviesGenerator (src/opensys/davies.jl:297-345): fixed GapIndices of a constant Hamiltonian with
+    UNSORTED, partly degenerate energies, time-dependent couplings given in the eigenbasis."""
+    from oqb_b200.extra_liouvillians import ConstHCorrelatedDaviesGenerator
+    rng = np.random.default_rng(56)
+    l, nb = 9, 2
+    w = np.array([0.4, -1.0, 2.0, 0.4, 1.0, -1.0, 0.0, 1.9, 0.4])
+    c1, c2 = rand_c(rng, l, l), rand_c(rng, l, l)
+    coup = [lambda s: (1 - s) * c1 + s * c2, lambda s: c2 * (1 + s)]
+    inds = [(1, 2), (2, 1), (1, 1)]
+    gd = {pq: (lambda x, c=0.2 * (pq[0] + pq[1]): gamma(x) * c) for pq in inds}
+    Sd = {pq: (lambda x, c=0.05 * pq[1]: lamb(x) * c) for pq in inds}
+    Dg = ConstHCorrelatedDaviesGenerator(w, coup, gd, Sd, inds)
+    Do = O.CorrelatedDaviesGenerator(coup, gd, Sd, inds)  # the same loop on a fixed GapIndices (oracle docstring)
+    G = O.build_gap_indices(w, 8, 8)
+    rho = rand_c(rng, nb, l, l)
+    for s in (0.0, 0.3):
+        got = Dg(np.zeros_like(rho), rho, None, s)
+        ref = np.stack([Do.rhs_acc(np.zeros((l, l), complex), rho[b], G, None, s) for b in range(nb)])
+        assert relerr(got, ref) < TOL
