@@ -778,6 +778,24 @@ class QuadraticBSpline:
         return out.reshape(np.shape(x))
 
 
+class GriddedLinear:
+    """construct_interpolations(x::AbstractArray, y) for a NON-uniform grid, src/interpolation.jl:36-65: Interpolations.jl's
+    Gridded(Linear()) — piecewise linear through the knots — extrapolated with the fill value 0 outside [x₁, x_n].  The
+    Davies tables need S only at the distinct gap keys (oqb_ame_gaps_keys), where this is evaluated array-wise."""
+
+    def __init__(self, x, y):
+        self.x = np.ascontiguousarray(x, dtype=np.float64)
+        self.y = np.ascontiguousarray(y, dtype=np.float64)
+        if self.x.ndim != 1 or self.x.shape != self.y.shape or np.any(np.diff(self.x) <= 0):
+            raise ValueError("GriddedLinear needs strictly increasing knots and one value per knot")
+
+    def vectorized(self, w):
+        return np.interp(np.asarray(w, dtype=np.float64), self.x, self.y, left=0.0, right=0.0)
+
+    def __call__(self, w):
+        return float(self.vectorized(np.asarray([w]))[0])
+
+
 def lambshift(w, gamma, rtol=_SQRT_EPS, atol=0.0):
     """src/integration/ext_util.jl:23-28 for a spectrum given as an arbitrary HOST closure (CustomBath, the entries of
     a CorrelatedBath spectrum matrix, src/bath/custom.jl:61-80): the closure can only be evaluated where it lives, so
@@ -815,7 +833,8 @@ def build_lambshift(w_range, turn_on: bool, bath, rtol=_SQRT_EPS, atol=0.0):
     w_range = np.asarray(w_range, dtype=np.float64)
     step = np.diff(w_range)
     if not np.allclose(step, step[0], rtol=1e-12, atol=0.0):
-        raise NotImplementedError("build_lambshift: non-uniform grids (Gridded(Linear())) are not on the device path")
+        # a non-range grid: construct_interpolations falls to Gridded(Linear()) with fill value 0 (src/interpolation.jl:36-65)
+        return GriddedLinear(w_range, bath.S(w_range, rtol=rtol, atol=atol))
     return QuadraticBSpline(w_range[0], (w_range[-1] - w_range[0]) / (len(w_range) - 1), bath.S(w_range, rtol=rtol, atol=atol))
 
 

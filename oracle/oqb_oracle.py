@@ -733,6 +733,25 @@ class QuadraticBSpline:
         return (c[i] * (d - 0.5) + c[i + 1] * (-2 * d) + c[i + 2] * (d + 0.5)) / self.dx
 
 
+class GriddedLinear:
+    """Interpolations.jl `interpolate((x,), y, Gridded(Linear()))` + `extrapolate(itp, 0)` — what construct_interpolations
+    returns for a non-range grid, src/interpolation.jl:36-65 [external Interpolations.jl — parity unpinned beyond the
+    reference's linear-data known answers, test/interpolations.jl:24-33]: scalar, literal bracket search."""
+
+    def __init__(self, x, y):
+        self.x, self.y = [float(v) for v in x], [float(v) for v in y]
+
+    def __call__(self, w):
+        x, y = self.x, self.y
+        if not (x[0] <= w <= x[-1]):
+            return 0.0
+        i = 0
+        while i < len(x) - 2 and w >= x[i + 1]:
+            i += 1
+        th = (w - x[i]) / (x[i + 1] - x[i])
+        return (1.0 - th) * y[i] + th * y[i + 1]
+
+
 def build_lambshift(w_range, turn_on: bool, bath, **quad_kwargs):
     """src/bath/bath_util.jl:26-38: S ≡ 0 when off; per-call quadgk when `w_range` is empty; else a
     quadratic B-spline through [S(ω) for ω in ω_range] (0 outside the range)."""
@@ -743,6 +762,9 @@ def build_lambshift(w_range, turn_on: bool, bath, **quad_kwargs):
         return lambda w: lambshift(w, gam, **quad_kwargs)
     w_range = np.asarray(w_range, dtype=float)
     s_list = np.array([lambshift(w, gam, **quad_kwargs) for w in w_range])
+    step = np.diff(w_range)
+    if not np.allclose(step, step[0], rtol=1e-12, atol=0.0):  # non-range grid → Gridded(Linear()), src/interpolation.jl:36-65
+        return GriddedLinear(w_range, s_list)
     return QuadraticBSpline(w_range[0], (w_range[-1] - w_range[0]) / (len(w_range) - 1), s_list)
 
 

@@ -213,6 +213,29 @@ def test_c_only_examples_compile(c_liouv_exe, c_comm_exe):
             assert out.returncode == 3 and "no CPU fallback" in out.stderr
 
 
+def test_gridded_linear_lambshift_table():
+    """build_lambshift on a NON-uniform ω grid (src/bath/bath_util.jl:26-38 → construct_interpolations for a non-range grid,
+    src/interpolation.jl:36-65: Gridded(Linear()), fill value 0): host mirror against the oracle's scalar restatement, and
+    the reference's linear-data known answers (test/interpolations.jl:3-20: exact on linear data, 0 outside the grid)."""
+    from oqb_b200 import host as H
+    x = np.array([0.0, 0.4, 1.0, 2.5, 2.6, 4.0, 7.5, 10.0])
+    g, o = H.GriddedLinear(x, 10 - x), O.GriddedLinear(x, 10 - x)
+    tx = np.linspace(0, 10, 77)
+    assert np.allclose(g.vectorized(tx), 10 - tx, rtol=0, atol=1e-14)
+    assert g(-1) == 0 and g(11) == 0 and o(-1) == 0 and o(11) == 0
+    rng = np.random.default_rng(8)
+    y = rng.standard_normal(len(x))
+    g, o = H.GriddedLinear(x, y), O.GriddedLinear(x, y)
+    pts = np.r_[x, rng.uniform(-1, 11, 200)]
+    assert np.allclose(g.vectorized(pts), [o(p) for p in pts], rtol=0, atol=1e-15)
+
+    class Piecewise:  # the spectrum of test/coupling_bath_interaction/bath.jl:72-80
+        def spectrum(self, w):
+            return np.exp(-abs(w)) if w >= 0 else np.exp(-abs(w)) * 0.5
+    S_o = O.build_lambshift(x - 3.0, True, Piecewise())
+    assert isinstance(S_o, O.GriddedLinear)
+
+
 def test_quadratic_bspline_host_coefficients():
     """Host mirror of construct_interpolations (interpolation.jl:22-34): banded prefilter solve and the vectorised
     evaluation agree with the oracle's dense restatement; linear data is reproduced (test/interpolations.jl:3-17)."""
