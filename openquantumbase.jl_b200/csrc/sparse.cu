@@ -189,26 +189,46 @@ int make_term(oqb_ctx* c, const HostCsc& m, TermDev& out) {
     OQB_CUDA(c, cudaMalloc((void**)&out.cols, ci.size() * sizeof(int32_t)));
     OQB_CUDA(c, cudaMemcpy(out.vals, v.data(), v.size() * sizeof(c128), cudaMemcpyHostToDevice));
     OQB_CUDA(c, cudaMemcpy(out.cols, ci.data(), ci.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
-    // XOR form: group the entries by mask = row ^ col
-    {
-        std::map<int, std::pair<long long, c128>> byMask;
+    // XOR form: group the entries by mask = row ^ col.  For every mask the row-dependent value v(r) = M[r, r^mask] (0 where the
+    // entry is absent) must be  a + b·(−1)^popcount(r & z)  for some bit set z — one Pauli string (a = 0: X/Y/Z factors), or two
+    // strings sharing their X-type factors (XX + YY, X + XZ …).  Each non-zero part becomes one slot.
+    if ((n & (n - 1)) == 0) {
+        std::map<int, std::vector<c128>> byMask;
         bool ok = true;
         for (int j = 0; j < n && ok; ++j)
             for (int64_t p = m.colptr[j]; p < m.colptr[j + 1] && ok; ++p) {
                 const int mask = m.row[p] ^ j;
                 auto it = byMask.find(mask);
                 if (it == byMask.end()) {
-                    if ((int)byMask.size() >= 16) { ok = false; break; }
-                    byMask[mask] = {1, m.val[p]};
-                } else {
-                    if (it->second.second.x != m.val[p].x || it->second.second.y != m.val[p].y) ok = false;
-                    it->second.first++;
+                    if ((int)byMask.size() >= 28) { ok = false; break; }
+                    it = byMask.emplace(mask, std::vector<c128>(n, make_double2(0.0, 0.0))).first;
                 }
+                it->second[m.row[p]] = m.val[p];
             }
-        for (auto& e : byMask) ok = ok && e.second.first == n;
-        if (ok && !byMask.empty()) {
+        std::vector<int> masks, zms;
+        std::vector<c128> vals;
+        auto same = [](c128 x, c128 y) { return x.x == y.x && x.y == y.y; };
+        for (auto& e : byMask) {
+            if (!ok) break;
+            const std::vector<c128>& v = e.second;
+            const c128 p0 = v[0];
+            int z = 0;
+            for (int bit = 1; bit < n; bit <<= 1)
+                if (!same(v[bit], p0)) z |= bit;
+            const c128 p1 = z ? v[z & -z] : p0;
+            for (int r = 0; r < n && ok; ++r) ok = same(v[r], (__builtin_popcount(r & z) & 1) ? p1 : p0);
+            if (!ok) break;
+            const c128 a = make_double2(0.5 * (p0.x + p1.x), 0.5 * (p0.y + p1.y)), b = make_double2(0.5 * (p0.x - p1.x), 0.5 * (p0.y - p1.y));
+            // the decomposition must reproduce both values exactly (it does for ±J, {0, 2J}, …); otherwise keep the generic form
+            if (!(same(make_double2(a.x + b.x, a.y + b.y), p0) && same(make_double2(a.x - b.x, a.y - b.y), p1))) { ok = false; break; }
+            if (a.x != 0.0 || a.y != 0.0) { masks.push_back(e.first); vals.push_back(a); zms.push_back(0); }
+            if (z && (b.x != 0.0 || b.y != 0.0)) { masks.push_back(e.first); vals.push_back(b); zms.push_back(z); }
+        }
+        if (ok && !masks.empty() && (int)masks.size() <= 28) {
             out.xor_form = true;
-            for (auto& e : byMask) { out.xor_masks.push_back(e.first); out.xor_vals.push_back(e.second.second); }
+            out.xor_masks = masks;
+            out.xor_vals = vals;
+            out.xor_zmasks = zms;
         }
     }
     // compressed forms for the fast trajectory kernel

@@ -21,10 +21,12 @@ struct TermDev {
     // constant diagonal (value·I) whose coefficient is 1 for every member: folds into one scalar per call
     bool diag_const = false, const_coef_one = false;
     c128 const_val = {0.0, 0.0};
-    // XOR form: M[r, r ^ mask_j] = val_j for every row r (Pauli X-type strings): no per-row data at all
+    // XOR form: M[r, r ^ mask_j] = val_j·(−1)^popcount(r & zmask_j) for every row r (Pauli strings: X-type factors give the mask,
+    // Y/Z factors the sign pattern; two strings sharing a mask give two slots): no per-row data at all
     bool xor_form = false;
     std::vector<int> xor_masks;
     std::vector<c128> xor_vals;
+    std::vector<int> xor_zmasks;  // per slot: value·(−1)^popcount(r & zmask) (0 = unsigned)
 };
 
 // dψ_b = Σ_t coef[b][t] · M_t ψ_b with the operator held in registers (see traj_fast.cu).

@@ -27,7 +27,7 @@ namespace {
 #define OQB_XOR_SPR 4
 #endif
 constexpr int kSPR = OQB_XOR_SPR;  // gather slots issued back to back per round
-constexpr int kXSlots = 16, kXTerms = 4, kXDiag = 2, kCoefPad = 16;  // coefficient area: 16 complex per stage
+constexpr int kXSlots = 28, kXTerms = 4, kXDiag = 2, kCoefPad = 16;  // coefficient area: 16 complex per stage
 
 struct XorDesc {
     int n_x, n_diag, ncoef, coef_shared;
@@ -35,6 +35,8 @@ struct XorDesc {
     int x_nrem[kXTerms];  // slots [begin, begin+nrem) are shared-memory gathers (count padded to even), rest thread-local
     int x_coef[kXTerms];
     int mask[kXSlots + 4];
+    int zmask[kXSlots + 4];  // signed slot: value · (−1)^popcount(row & zmask)  (Pauli strings with Y / Z factors next to their X factors)
+    int any_signed;
     double vre[kXSlots + 4], vim[kXSlots + 4];
     const double* diag_r[kXDiag];
     int diag_coef[kXDiag];
@@ -81,15 +83,29 @@ __device__ __forceinline__ void cacc(double& ar, double& ai, double vr, double v
     }
 }
 
+// ψ ← ±ψ by the parity of (row & zmask): the sign bit of both components is flipped with integer ops (the FP64 pipe is busy)
+__device__ __forceinline__ c128 signed_by_parity(c128 v, int row, int zmask) {
+    const unsigned flip = ((unsigned)__popc(row & zmask) & 1u) << 31;
+    v.x = __hiloint2double(__double2hiint(v.x) ^ (int)flip, __double2loint(v.x));
+    v.y = __hiloint2double(__double2hiint(v.y) ^ (int)flip, __double2loint(v.y));
+    return v;
+}
+
 // acc[kk] += v · xo[(C0 + kk) ^ HK]  — partner rows that live in this thread's own registers
 template <int R, int CH, int C0, int HK, bool RV>
-__device__ __forceinline__ void local_acc(const c128 (&xo)[R], double (&ar)[CH], double (&ai)[CH], double vr, double vi) {
+__device__ __forceinline__ void local_acc(const c128 (&xo)[R], double (&ar)[CH], double (&ai)[CH], double vr, double vi, int row0 = 0,
+                                          int nt = 0, int zmask = 0) {
 #pragma unroll
-    for (int kk = 0; kk < CH; ++kk) cacc<RV>(ar[kk], ai[kk], vr, vi, xo[((C0 + kk) ^ HK) % R]);
+    for (int kk = 0; kk < CH; ++kk) {
+        c128 v = xo[((C0 + kk) ^ HK) % R];
+        if (zmask) v = signed_by_parity(v, row0 + (C0 + kk) * nt, zmask);
+        cacc<RV>(ar[kk], ai[kk], vr, vi, v);
+    }
 }
 template <int R, int CH, int C0, bool RV>
-__device__ __forceinline__ void local_dispatch(int hk, const c128 (&xo)[R], double (&ar)[CH], double (&ai)[CH], double vr, double vi) {
-#define OQB_LC(H) case H: local_acc<R, CH, C0, H, RV>(xo, ar, ai, vr, vi); break;
+__device__ __forceinline__ void local_dispatch(int hk, const c128 (&xo)[R], double (&ar)[CH], double (&ai)[CH], double vr, double vi,
+                                               int row0 = 0, int nt = 0, int zmask = 0) {
+#define OQB_LC(H) case H: local_acc<R, CH, C0, H, RV>(xo, ar, ai, vr, vi, row0, nt, zmask); break;
     if (hk < 4) {
         switch (hk) { OQB_LC(1) OQB_LC(2) OQB_LC(3) default: break; }
     } else if (R > 4 && hk < 8) {
@@ -101,8 +117,8 @@ __device__ __forceinline__ void local_dispatch(int hk, const c128 (&xo)[R], doub
 }
 
 // one chunk of CH rows (rows C0 … C0+CH-1 of this thread)
-template <int R, int NT, int CH, int C0, bool RV, int ND, int EPI, int NG>
-__device__ __forceinline__ void do_chunk(const XorDesc& d, const int* s_mask, const double* s_vre, const double* s_vim,
+template <int R, int NT, int CH, int C0, bool RV, int ND, int EPI, int NG, bool SG>
+__device__ __forceinline__ void do_chunk(const XorDesc& d, const int* s_mask, const int* s_zm, const double* s_vre, const double* s_vim,
                                          const c128* __restrict__ x, const c128* cfs, const c128 (&xo)[R],
                                          const double (&dreg)[R][ND > 0 ? ND : 1], const c128 (&cdiag)[ND > 0 ? ND : 1],
                                          c128* out, int tid, double wa, double wt, const c128* __restrict__ rk_psi0,
@@ -176,6 +192,11 @@ __device__ __forceinline__ void do_chunk(const XorDesc& d, const int* s_mask, co
                     const int m = s_mask[j + q];
     #pragma unroll
                     for (int kk = 0; kk < CH; ++kk) vv[q][kk] = x[(tid + (C0 + kk) * NT) ^ m];
+                    if (SG) {  // M[r, r^m] = v·(−1)^popcount(r & z): the sign goes onto the gathered ψ
+                        const int z = s_zm[j + q];
+    #pragma unroll
+                        for (int kk = 0; kk < CH; ++kk) vv[q][kk] = signed_by_parity(vv[q][kk], tid + (C0 + kk) * NT, z);
+                    }
                 }
     #pragma unroll
                 for (int q = 0; q < kSPR; ++q) {
@@ -185,7 +206,7 @@ __device__ __forceinline__ void do_chunk(const XorDesc& d, const int* s_mask, co
                 }
             }
             for (int j = jb + nrem; j < d.x_begin[e + 1]; ++j)  // partners in this thread's own registers
-                local_dispatch<R, CH, C0, RV>(s_mask[j] / NT, xo, ar, ai, s_vre[j], s_vim[j]);
+                local_dispatch<R, CH, C0, RV>(s_mask[j] / NT, xo, ar, ai, s_vre[j], s_vim[j], tid, NT, SG ? s_zm[j] : 0);
             const c128 cc = cfs[d.x_coef[e]];
     #pragma unroll
             for (int kk = 0; kk < CH; ++kk) {
@@ -216,7 +237,7 @@ __device__ __forceinline__ void do_chunk(const XorDesc& d, const int* s_mask, co
 }
 
 // R rows per thread (r = tid + k·NT), S ring stages, RV: all slot values real, ND: real diagonal terms in registers
-template <int R, int NT, int S, bool RV, int ND, int EPI, int NG>
+template <int R, int NT, int S, bool RV, int ND, int EPI, int NG, bool SG>
 __global__ void __launch_bounds__(NT, 1)
     traj_xor_kernel(int nb, const __grid_constant__ XorDesc d, const c128* __restrict__ coef, long long coef_ld,
                     const c128* psi, c128* dpsi, double wa, double wt, const c128* __restrict__ rk_psi0,
@@ -226,6 +247,7 @@ __global__ void __launch_bounds__(NT, 1)
     c128* ring = reinterpret_cast<c128*>(smem_raw);
     __shared__ __align__(8) unsigned long long bars[2 * S];
     __shared__ int s_mask[kXSlots + 4];
+    __shared__ int s_zm[kXSlots + 4];
     __shared__ double s_vre[kXSlots + 4], s_vim[kXSlots + 4];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned bar_base = s_addr(bars);
@@ -239,6 +261,7 @@ __global__ void __launch_bounds__(NT, 1)
         for (int t = 0; t < ND; ++t) dreg[k][t] = d.diag_r[t][tid + k * NT];
     if (tid < kXSlots + 4) {
         s_mask[tid] = d.mask[tid];
+        s_zm[tid] = d.zmask[tid];
         s_vre[tid] = d.vre[tid];
         s_vim[tid] = d.vim[tid];
     }
@@ -294,9 +317,9 @@ __global__ void __launch_bounds__(NT, 1)
         const c128* p0 = EPI == 2 ? rk_psi0 + (size_t)b * n : nullptr;
         c128* ac = EPI != 0 ? rk_acc + (size_t)b * n : nullptr;
         double nrm = 0.0;
-        do_chunk<R, NT, CH, 0, RV, ND, EPI, NG>(d, s_mask, s_vre, s_vim, x, cfs, xo, dreg, cdiag, out, tid, wa, wt, p0, ac, nrm);
+        do_chunk<R, NT, CH, 0, RV, ND, EPI, NG, SG>(d, s_mask, s_zm, s_vre, s_vim, x, cfs, xo, dreg, cdiag, out, tid, wa, wt, p0, ac, nrm);
         if (R > 8)
-            do_chunk<R, NT, CH, (R > 8 ? 8 : 0), RV, ND, EPI, NG>(d, s_mask, s_vre, s_vim, x, cfs, xo, dreg, cdiag, out, tid, wa, wt, p0, ac, nrm);
+            do_chunk<R, NT, CH, (R > 8 ? 8 : 0), RV, ND, EPI, NG, SG>(d, s_mask, s_zm, s_vre, s_vim, x, cfs, xo, dreg, cdiag, out, tid, wa, wt, p0, ac, nrm);
         if (EPI == 3 && norm_part) {  // per-warp partial of ‖ψ_b‖² in a fixed order: 16 slots per trajectory, unused ones zero
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) nrm += __shfl_xor_sync(0xffffffffu, nrm, o);
@@ -308,7 +331,7 @@ __global__ void __launch_bounds__(NT, 1)
     }
 }
 
-template <int R, int NT, int S, bool RV, int ND, int EPI, int NG = 0>
+template <int R, int NT, int S, bool RV, int ND, int EPI, int NG = 0, bool SG = false>
 int launch(Ctx* c, int nb, const XorDesc& d_in, const c128* coef, long long coef_ld, const c128* psi, c128* dpsi,
            const RkEpilogue* rk) {
     XorDesc d = d_in;
@@ -321,22 +344,22 @@ int launch(Ctx* c, int nb, const XorDesc& d_in, const c128* coef, long long coef
                 const bool local = (d_in.mask[j] & (NT - 1)) == 0;
                 if (local == (pass == 1)) {
                     if (w >= kXSlots + 4) return -1;
-                    d.mask[w] = d_in.mask[j]; d.vre[w] = d_in.vre[j]; d.vim[w] = d_in.vim[j];
+                    d.mask[w] = d_in.mask[j]; d.vre[w] = d_in.vre[j]; d.vim[w] = d_in.vim[j]; d.zmask[w] = d_in.zmask[j];
                     ++w;
                     if (!local) ++nrem;
                 }
             }
             while (pass == 0 && (nrem % kSPR)) {  // dummy gathers with zero weight keep the rounds uniform
                 if (w >= kXSlots + 4) return -1;
-                d.mask[w] = 1; d.vre[w] = 0.0; d.vim[w] = 0.0;
+                d.mask[w] = 1; d.vre[w] = 0.0; d.vim[w] = 0.0; d.zmask[w] = 0;
                 ++w; ++nrem;
             }
         }
         d.x_nrem[e] = nrem;
     }
     d.x_begin[d_in.n_x] = w;
-    for (int j = w; j < kXSlots + 4; ++j) { d.mask[j] = 1; d.vre[j] = d.vim[j] = 0.0; }
-    if constexpr (NG == 0 && RV && ND <= 1) {
+    for (int j = w; j < kXSlots + 4; ++j) { d.mask[j] = 1; d.vre[j] = d.vim[j] = 0.0; d.zmask[j] = 0; }
+    if constexpr (NG == 0 && RV && ND <= 1 && !SG) {
         // One X-type term whose thread-local slots are exactly the single-bit flips NT·{1,2,4,…} (transverse-field
         // drivers): run the fully unrolled variant.  The local slots are put in ascending mask order first.
         constexpr int LOG2R = R == 16 ? 4 : (R == 8 ? 3 : (R == 4 ? 2 : 1));
@@ -373,7 +396,7 @@ int launch(Ctx* c, int nb, const XorDesc& d_in, const c128* coef, long long coef
     const size_t smem = (size_t)S * (R * NT + kCoefPad) * sizeof(c128);
     static DevOnce cfg;
     if (!cfg.done(c->device)) {
-        OQB_CUDA(c, cudaFuncSetAttribute(traj_xor_kernel<R, NT, S, RV, ND, EPI, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        OQB_CUDA(c, cudaFuncSetAttribute(traj_xor_kernel<R, NT, S, RV, ND, EPI, NG, SG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         cfg.set(c->device);
     }
     int sms = 148;
@@ -385,7 +408,7 @@ int launch(Ctx* c, int nb, const XorDesc& d_in, const c128* coef, long long coef
     {
         // algorithmic bytes: read ψ + write dψ (+ the RK operands: 1 extra vector for modes 1/3, 3 for mode 2)
         ProfScope prof(c, (EPI == 0 ? 32.0 : (EPI == 2 ? 80.0 : 48.0)) * R * NT * (double)nb);
-        traj_xor_kernel<R, NT, S, RV, ND, EPI, NG><<<grid, NT, smem, c->stream>>>(nb, d, coef, coef_ld, psi, dpsi, rk ? rk->wa : 0.0,
+        traj_xor_kernel<R, NT, S, RV, ND, EPI, NG, SG><<<grid, NT, smem, c->stream>>>(nb, d, coef, coef_ld, psi, dpsi, rk ? rk->wa : 0.0,
                                                                              rk ? rk->wt : 0.0, rk ? rk->psi0 : nullptr,
                                                                              rk ? rk->acc : nullptr, rk ? rk->norm_part : nullptr);
     }
@@ -398,6 +421,24 @@ int by_size_epi(Ctx* c, int n, int nb, const XorDesc& d, const c128* coef, long 
                 bool* used, const RkEpilogue* rk) {
     *used = true;
     int st = 0;
+    if (d.any_signed) {
+        // signed slots (general Pauli strings): the plain matvec only — the fused RK stages fall back to the unfused sequence
+        if constexpr (EPI != 0) {
+            *used = false;
+            return 0;
+        } else {
+            switch (n) {
+                case 4096: st = launch<16, 256, 3, RV, ND, 0, 0, true>(c, nb, d, coef, coef_ld, psi, dpsi, rk); break;
+                case 2048: st = launch<8, 256, 3, RV, ND, 0, 0, true>(c, nb, d, coef, coef_ld, psi, dpsi, rk); break;
+                case 1024: st = launch<4, 256, 3, RV, ND, 0, 0, true>(c, nb, d, coef, coef_ld, psi, dpsi, rk); break;
+                case 512: st = launch<4, 128, 3, RV, ND, 0, 0, true>(c, nb, d, coef, coef_ld, psi, dpsi, rk); break;
+                case 256: st = launch<2, 128, 3, RV, ND, 0, 0, true>(c, nb, d, coef, coef_ld, psi, dpsi, rk); break;
+                default: *used = false; return 0;
+            }
+            if (st < 0) { *used = false; return 0; }
+            return st;
+        }
+    }
     switch (n) {
         case 4096: {
             const int rsel = c->opt.xor_rows;
@@ -459,6 +500,8 @@ int traj_matvec_xor(Ctx* c, int n, int nb, const std::vector<const TermDev*>& ts
             d.x_begin[d.n_x] = slots;
             for (size_t j = 0; j < td->xor_masks.size(); ++j) {
                 d.mask[slots] = td->xor_masks[j];
+                d.zmask[slots] = j < td->xor_zmasks.size() ? td->xor_zmasks[j] : 0;
+                if (d.zmask[slots]) d.any_signed = 1;
                 d.vre[slots] = td->xor_vals[j].x;
                 d.vim[slots] = td->xor_vals[j].y;
                 all_real = all_real && td->xor_vals[j].y == 0.0;
