@@ -161,6 +161,10 @@ def run_secondary(Q, torch, ctx):
         torch.cuda.empty_cache()
         out["C4_random_pattern"] = OC.run_c4_matvec_only(Q, torch, 3, random_pattern=True)
         torch.cuda.empty_cache()
+        out["C4_pauli_yfield_signed_slots"] = OC.run_c4_matvec_only(Q, torch, 3, pauli="yfield")
+        torch.cuda.empty_cache()
+        out["C4_pauli_heisenberg_signed_slots"] = OC.run_c4_matvec_only(Q, torch, 3, pauli="heisenberg")
+        torch.cuda.empty_cache()
     except Exception as e:  # noqa: BLE001
         out["C4_error"] = f"{type(e).__name__}: {e}"
     try:

@@ -347,12 +347,39 @@ def random_sparse_c4(nq, per_row=6, seed=4100):
     return Hoff, Hdiag
 
 
-def run_c4_matvec_only(Q, torch, steps, generic=False, random_pattern=False):
+def pauli_sparse_c4(nq, model):
+    """12-qubit Pauli-string Hamiltonians WITHOUT pure-X structure: "yfield" = −Σ Y_i driver (imaginary, row-signed entries) +
+    Σ Z_iZ_{i+1}; "heisenberg" = ½Σ(X_iX_{i+1} + Y_iY_{i+1}) (two strings per bond sharing their flip mask) + Σ Z_iZ_{i+1}."""
+    import scipy.sparse as sps
+    n = 1 << nq
+    idx = np.arange(n)
+    bit = lambda q: (idx >> (nq - 1 - q)) & 1
+    z = [1.0 - 2.0 * bit(q) for q in range(nq)]
+    Hz = sps.diags(-sum(z[i] * z[i + 1] for i in range(nq - 1))).tocsc().astype(complex)
+    rows, cols, vals = [], [], []
+    if model == "yfield":
+        for q in range(nq):  # Y = [[0, −i], [i, 0]]: entry (r ^ m, r) = i·(−1)^bit_q(r)
+            m = 1 << (nq - 1 - q)
+            rows.append(idx ^ m); cols.append(idx); vals.append(-1.0 * 1j * z[q])
+    else:
+        for q in range(nq - 1):  # XX + YY on a bond flips both bits and vanishes when they are equal: (1 − z_q z_{q+1})
+            m = (1 << (nq - 1 - q)) | (1 << (nq - 2 - q))
+            v = 0.5 * (1.0 - z[q] * z[q + 1])
+            keep = v != 0
+            rows.append((idx ^ m)[keep]); cols.append(idx[keep]); vals.append(v[keep].astype(complex))
+    Hx = sps.csc_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(n, n), dtype=complex)
+    Ls = [sps.diags(zq).tocsc().astype(complex) for zq in z]
+    return Hx, Hz, Ls
+
+
+def run_c4_matvec_only(Q, torch, steps, generic=False, random_pattern=False, pauli=None):
     """The C4 ensemble matvec alone: `generic=True` forces the generic kernels on the TFIM operators (option "traj_kernel" = 1),
     `random_pattern=True` swaps in an unstructured Hamiltonian (no kernel specialisation applies).  HBM roofline fraction of the kernel."""
     nq, n, B = 12, 4096, 65536
     ctx = Q.get_context()
-    if random_pattern:
+    if pauli:
+        Ha, Hb, Ls = pauli_sparse_c4(nq, pauli)
+    elif random_pattern:
         Ha, Hb = random_sparse_c4(nq)
         _, _, Ls = tfim_sparse_c4(nq)
     else:
@@ -380,7 +407,7 @@ def run_c4_matvec_only(Q, torch, steps, generic=False, random_pattern=False):
     kms, kb = a.value / max(b_.value, 1), w.value / max(b_.value, 1)
     hbm, src = peaks()
     nnz_row = (Ha.nnz + Hb.nnz) / n
-    return {"workload": f"12-qubit {'UNSTRUCTURED random-pattern' if random_pattern else 'TFIM'} SparseHamiltonian, {B} psi of dim {n}, "
+    return {"workload": f"12-qubit {('Pauli-string (' + pauli + ')') if pauli else ('UNSTRUCTURED random-pattern' if random_pattern else 'TFIM')} SparseHamiltonian, {B} psi of dim {n}, "
                         f"{nnz_row:.1f} entries per row, per-trajectory s" + (", generic kernels forced" if generic else ""),
             "value": B / (ms * 1e-3), "ms_per_step": ms,
             "roofline": {"bound": "hbm", "achieved": kb / 1e9 / (kms * 1e-3), "peak": hbm, "unit": "GB/s",
@@ -452,8 +479,9 @@ def main():
             print(json.dumps(r), flush=True)
             torch.cuda.empty_cache()
             continue
-        if c in ("c4generic", "c4random"):
-            r = run_c4_matvec_only(Q, torch, args.steps, generic=c == "c4generic", random_pattern=c == "c4random")
+        if c in ("c4generic", "c4random", "c4yfield", "c4heisenberg"):
+            r = run_c4_matvec_only(Q, torch, args.steps, generic=c == "c4generic", random_pattern=c == "c4random",
+                                   pauli={"c4yfield": "yfield", "c4heisenberg": "heisenberg"}.get(c))
             print(json.dumps(r), flush=True)
             torch.cuda.empty_cache()
             continue
