@@ -190,8 +190,8 @@ int make_term(oqb_ctx* c, const HostCsc& m, TermDev& out) {
     OQB_CUDA(c, cudaMemcpy(out.vals, v.data(), v.size() * sizeof(c128), cudaMemcpyHostToDevice));
     OQB_CUDA(c, cudaMemcpy(out.cols, ci.data(), ci.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
     // XOR form: group the entries by mask = row ^ col.  For every mask the row-dependent value v(r) = M[r, r^mask] (0 where the
-    // entry is absent) must be  a + b·(−1)^popcount(r & z)  for some bit set z — one Pauli string (a = 0: X/Y/Z factors), or two
-    // strings sharing their X-type factors (XX + YY, X + XZ …).  Each non-zero part becomes one slot.
+    // entry is absent) must take at most TWO values, chosen by the parity of popcount(r & z) for some bit set z — one Pauli
+    // string (the two values are ±c: X/Y/Z factors), or two strings sharing their X-type factors (XX + YY, X + XZ …).
     if ((n & (n - 1)) == 0) {
         std::map<int, std::vector<c128>> byMask;
         bool ok = true;
@@ -206,7 +206,7 @@ int make_term(oqb_ctx* c, const HostCsc& m, TermDev& out) {
                 it->second[m.row[p]] = m.val[p];
             }
         std::vector<int> masks, zms;
-        std::vector<c128> vals;
+        std::vector<c128> vals, vals1;
         auto same = [](c128 x, c128 y) { return x.x == y.x && x.y == y.y; };
         for (auto& e : byMask) {
             if (!ok) break;
@@ -218,16 +218,13 @@ int make_term(oqb_ctx* c, const HostCsc& m, TermDev& out) {
             const c128 p1 = z ? v[z & -z] : p0;
             for (int r = 0; r < n && ok; ++r) ok = same(v[r], (__builtin_popcount(r & z) & 1) ? p1 : p0);
             if (!ok) break;
-            const c128 a = make_double2(0.5 * (p0.x + p1.x), 0.5 * (p0.y + p1.y)), b = make_double2(0.5 * (p0.x - p1.x), 0.5 * (p0.y - p1.y));
-            // the decomposition must reproduce both values exactly (it does for ±J, {0, 2J}, …); otherwise keep the generic form
-            if (!(same(make_double2(a.x + b.x, a.y + b.y), p0) && same(make_double2(a.x - b.x, a.y - b.y), p1))) { ok = false; break; }
-            if (a.x != 0.0 || a.y != 0.0) { masks.push_back(e.first); vals.push_back(a); zms.push_back(0); }
-            if (z && (b.x != 0.0 || b.y != 0.0)) { masks.push_back(e.first); vals.push_back(b); zms.push_back(z); }
+            masks.push_back(e.first); vals.push_back(p0); vals1.push_back(p1); zms.push_back(z);
         }
-        if (ok && !masks.empty() && (int)masks.size() <= 28) {
+        if (ok && !masks.empty()) {
             out.xor_form = true;
             out.xor_masks = masks;
             out.xor_vals = vals;
+            out.xor_vals1 = vals1;
             out.xor_zmasks = zms;
         }
     }

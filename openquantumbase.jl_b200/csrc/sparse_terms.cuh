@@ -21,12 +21,13 @@ struct TermDev {
     // constant diagonal (value·I) whose coefficient is 1 for every member: folds into one scalar per call
     bool diag_const = false, const_coef_one = false;
     c128 const_val = {0.0, 0.0};
-    // XOR form: M[r, r ^ mask_j] = val_j·(−1)^popcount(r & zmask_j) for every row r (Pauli strings: X-type factors give the mask,
-    // Y/Z factors the sign pattern; two strings sharing a mask give two slots): no per-row data at all
+    // XOR form: M[r, r ^ mask_j] = (popcount(r & zmask_j) even ? val_j : val1_j) for every row r — Pauli strings: the X-type
+    // factors give the mask, Y/Z factors the row-parity pattern (val1 = −val for one string; {0, 2J} for XX + YY): no per-row data
     bool xor_form = false;
     std::vector<int> xor_masks;
     std::vector<c128> xor_vals;
-    std::vector<int> xor_zmasks;  // per slot: value·(−1)^popcount(r & zmask) (0 = unsigned)
+    std::vector<c128> xor_vals1;  // per slot: the value on rows with popcount(r & zmask) odd (xor_vals: even)
+    std::vector<int> xor_zmasks;  // per slot: which row bits decide between the two values (0 = one value)
 };
 
 // dψ_b = Σ_t coef[b][t] · M_t ψ_b with the operator held in registers (see traj_fast.cu).

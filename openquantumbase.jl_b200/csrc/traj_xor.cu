@@ -35,9 +35,13 @@ struct XorDesc {
     int x_nrem[kXTerms];  // slots [begin, begin+nrem) are shared-memory gathers (count padded to even), rest thread-local
     int x_coef[kXTerms];
     int mask[kXSlots + 4];
-    int zmask[kXSlots + 4];  // signed slot: value · (−1)^popcount(row & zmask)  (Pauli strings with Y / Z factors next to their X factors)
+    // two-valued slot: M[r, r^mask] = (popcount(r & zmask) odd ? w : v) — one Pauli string (w = −v: Y / Z factors next to its X
+    // factors) or two strings sharing their flip mask (XX + YY: v, w ∈ {0, 2J}); zmask = 0 ⇒ one value
+    int zmask[kXSlots + 4];
+    unsigned ktab[kXSlots + 4];  // bit k = parity((k·NT) & zmask): the part of the row parity that depends on the thread's k-th row
     int any_signed;
-    double vre[kXSlots + 4], vim[kXSlots + 4];
+    int x_imag[kXTerms];         // the term's slot values are purely imaginary: stored as real numbers, the factor i goes onto the coefficient
+    double vre[kXSlots + 4], vim[kXSlots + 4], wre[kXSlots + 4], wim[kXSlots + 4];
     const double* diag_r[kXDiag];
     int diag_coef[kXDiag];
     double fconst_re, fconst_im;  // constant diagonal contribution (e.g. −½Σγ_k when every L_k'L_k = c_k·I)
@@ -83,29 +87,21 @@ __device__ __forceinline__ void cacc(double& ar, double& ai, double vr, double v
     }
 }
 
-// ψ ← ±ψ by the parity of (row & zmask): the sign bit of both components is flipped with integer ops (the FP64 pipe is busy)
-__device__ __forceinline__ c128 signed_by_parity(c128 v, int row, int zmask) {
-    const unsigned flip = ((unsigned)__popc(row & zmask) & 1u) << 31;
-    v.x = __hiloint2double(__double2hiint(v.x) ^ (int)flip, __double2loint(v.x));
-    v.y = __hiloint2double(__double2hiint(v.y) ^ (int)flip, __double2loint(v.y));
-    return v;
-}
-
 // acc[kk] += v · xo[(C0 + kk) ^ HK]  — partner rows that live in this thread's own registers
 template <int R, int CH, int C0, int HK, bool RV>
-__device__ __forceinline__ void local_acc(const c128 (&xo)[R], double (&ar)[CH], double (&ai)[CH], double vr, double vi, int row0 = 0,
-                                          int nt = 0, int zmask = 0) {
+__device__ __forceinline__ void local_acc(const c128 (&xo)[R], double (&ar)[CH], double (&ai)[CH], double vr, double vi, unsigned par = 0,
+                                          double wr = 0.0, double wi = 0.0) {
+    // par: bit k set ⇒ row k of this thread takes the slot's second value (w) instead of the first (v)
 #pragma unroll
     for (int kk = 0; kk < CH; ++kk) {
-        c128 v = xo[((C0 + kk) ^ HK) % R];
-        if (zmask) v = signed_by_parity(v, row0 + (C0 + kk) * nt, zmask);
-        cacc<RV>(ar[kk], ai[kk], vr, vi, v);
+        const bool odd = (par >> (C0 + kk)) & 1u;
+        cacc<RV>(ar[kk], ai[kk], odd ? wr : vr, odd ? wi : vi, xo[((C0 + kk) ^ HK) % R]);
     }
 }
 template <int R, int CH, int C0, bool RV>
 __device__ __forceinline__ void local_dispatch(int hk, const c128 (&xo)[R], double (&ar)[CH], double (&ai)[CH], double vr, double vi,
-                                               int row0 = 0, int nt = 0, int zmask = 0) {
-#define OQB_LC(H) case H: local_acc<R, CH, C0, H, RV>(xo, ar, ai, vr, vi, row0, nt, zmask); break;
+                                               unsigned par = 0, double wr = 0.0, double wi = 0.0) {
+#define OQB_LC(H) case H: local_acc<R, CH, C0, H, RV>(xo, ar, ai, vr, vi, par, wr, wi); break;
     if (hk < 4) {
         switch (hk) { OQB_LC(1) OQB_LC(2) OQB_LC(3) default: break; }
     } else if (R > 4 && hk < 8) {
@@ -118,7 +114,8 @@ __device__ __forceinline__ void local_dispatch(int hk, const c128 (&xo)[R], doub
 
 // one chunk of CH rows (rows C0 … C0+CH-1 of this thread)
 template <int R, int NT, int CH, int C0, bool RV, int ND, int EPI, int NG, bool SG>
-__device__ __forceinline__ void do_chunk(const XorDesc& d, const int* s_mask, const int* s_zm, const double* s_vre, const double* s_vim,
+__device__ __forceinline__ void do_chunk(const XorDesc& d, const int* s_mask, const unsigned* s_kt, unsigned pmask, const double* s_vre,
+                                         const double* s_vim, const double* s_wre, const double* s_wim,
                                          const c128* __restrict__ x, const c128* cfs, const c128 (&xo)[R],
                                          const double (&dreg)[R][ND > 0 ? ND : 1], const c128 (&cdiag)[ND > 0 ? ND : 1],
                                          c128* out, int tid, double wa, double wt, const c128* __restrict__ rk_psi0,
@@ -192,22 +189,31 @@ __device__ __forceinline__ void do_chunk(const XorDesc& d, const int* s_mask, co
                     const int m = s_mask[j + q];
     #pragma unroll
                     for (int kk = 0; kk < CH; ++kk) vv[q][kk] = x[(tid + (C0 + kk) * NT) ^ m];
-                    if (SG) {  // M[r, r^m] = v·(−1)^popcount(r & z): the sign goes onto the gathered ψ
-                        const int z = s_zm[j + q];
-    #pragma unroll
-                        for (int kk = 0; kk < CH; ++kk) vv[q][kk] = signed_by_parity(vv[q][kk], tid + (C0 + kk) * NT, z);
-                    }
                 }
     #pragma unroll
                 for (int q = 0; q < kSPR; ++q) {
                     const double vr = s_vre[j + q], vi = s_vim[j + q];
+                    if (SG) {
+                        // row parity = parity(tid & z) ^ parity(k·NT & z): bit k of `par` says which of the slot's two values row k takes
+                        const unsigned par = s_kt[j + q] ^ (0u - ((pmask >> (j + q)) & 1u));
+                        const double wr = s_wre[j + q], wi = s_wim[j + q];
     #pragma unroll
-                    for (int kk = 0; kk < CH; ++kk) cacc<RV>(ar[kk], ai[kk], vr, vi, vv[q][kk]);
+                        for (int kk = 0; kk < CH; ++kk) {
+                            const bool odd = (par >> (C0 + kk)) & 1u;
+                            cacc<RV>(ar[kk], ai[kk], odd ? wr : vr, odd ? wi : vi, vv[q][kk]);
+                        }
+                    } else {
+    #pragma unroll
+                        for (int kk = 0; kk < CH; ++kk) cacc<RV>(ar[kk], ai[kk], vr, vi, vv[q][kk]);
+                    }
                 }
             }
-            for (int j = jb + nrem; j < d.x_begin[e + 1]; ++j)  // partners in this thread's own registers
-                local_dispatch<R, CH, C0, RV>(s_mask[j] / NT, xo, ar, ai, s_vre[j], s_vim[j], tid, NT, SG ? s_zm[j] : 0);
-            const c128 cc = cfs[d.x_coef[e]];
+            for (int j = jb + nrem; j < d.x_begin[e + 1]; ++j) {  // partners in this thread's own registers
+                if (SG) local_dispatch<R, CH, C0, RV>(s_mask[j] / NT, xo, ar, ai, s_vre[j], s_vim[j], s_kt[j] ^ (0u - ((pmask >> j) & 1u)), s_wre[j], s_wim[j]);
+                else local_dispatch<R, CH, C0, RV>(s_mask[j] / NT, xo, ar, ai, s_vre[j], s_vim[j]);
+            }
+            c128 cc = cfs[d.x_coef[e]];
+            if (SG && d.x_imag[e]) cc = make_double2(-cc.y, cc.x);  // the term's slot values were stored without their factor i
     #pragma unroll
             for (int kk = 0; kk < CH; ++kk) {
                 outr[kk] = fma(cc.x, ar[kk], outr[kk]); outr[kk] = fma(-cc.y, ai[kk], outr[kk]);
@@ -247,8 +253,8 @@ __global__ void __launch_bounds__(NT, 1)
     c128* ring = reinterpret_cast<c128*>(smem_raw);
     __shared__ __align__(8) unsigned long long bars[2 * S];
     __shared__ int s_mask[kXSlots + 4];
-    __shared__ int s_zm[kXSlots + 4];
-    __shared__ double s_vre[kXSlots + 4], s_vim[kXSlots + 4];
+    __shared__ unsigned s_kt[kXSlots + 4];
+    __shared__ double s_vre[kXSlots + 4], s_vim[kXSlots + 4], s_wre[kXSlots + 4], s_wim[kXSlots + 4];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned bar_base = s_addr(bars);
     const unsigned psi_bytes = n * (unsigned)sizeof(c128);
@@ -261,9 +267,16 @@ __global__ void __launch_bounds__(NT, 1)
         for (int t = 0; t < ND; ++t) dreg[k][t] = d.diag_r[t][tid + k * NT];
     if (tid < kXSlots + 4) {
         s_mask[tid] = d.mask[tid];
-        s_zm[tid] = d.zmask[tid];
+        s_kt[tid] = d.ktab[tid];
         s_vre[tid] = d.vre[tid];
         s_vim[tid] = d.vim[tid];
+        s_wre[tid] = d.wre[tid];
+        s_wim[tid] = d.wim[tid];
+    }
+    unsigned pmask = 0;  // bit j = parity(tid & zmask_j): this thread's share of the row parity of slot j
+    if (SG) {
+#pragma unroll 4
+        for (int j = 0; j < kXSlots + 4; ++j) pmask |= ((unsigned)__popc(tid & d.zmask[j]) & 1u) << j;
     }
     if (tid == 0) {
         for (int s = 0; s < S; ++s) {
@@ -317,9 +330,9 @@ __global__ void __launch_bounds__(NT, 1)
         const c128* p0 = EPI == 2 ? rk_psi0 + (size_t)b * n : nullptr;
         c128* ac = EPI != 0 ? rk_acc + (size_t)b * n : nullptr;
         double nrm = 0.0;
-        do_chunk<R, NT, CH, 0, RV, ND, EPI, NG, SG>(d, s_mask, s_zm, s_vre, s_vim, x, cfs, xo, dreg, cdiag, out, tid, wa, wt, p0, ac, nrm);
+        do_chunk<R, NT, CH, 0, RV, ND, EPI, NG, SG>(d, s_mask, s_kt, pmask, s_vre, s_vim, s_wre, s_wim, x, cfs, xo, dreg, cdiag, out, tid, wa, wt, p0, ac, nrm);
         if (R > 8)
-            do_chunk<R, NT, CH, (R > 8 ? 8 : 0), RV, ND, EPI, NG, SG>(d, s_mask, s_zm, s_vre, s_vim, x, cfs, xo, dreg, cdiag, out, tid, wa, wt, p0, ac, nrm);
+            do_chunk<R, NT, CH, (R > 8 ? 8 : 0), RV, ND, EPI, NG, SG>(d, s_mask, s_kt, pmask, s_vre, s_vim, s_wre, s_wim, x, cfs, xo, dreg, cdiag, out, tid, wa, wt, p0, ac, nrm);
         if (EPI == 3 && norm_part) {  // per-warp partial of ‖ψ_b‖² in a fixed order: 16 slots per trajectory, unused ones zero
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) nrm += __shfl_xor_sync(0xffffffffu, nrm, o);
@@ -345,20 +358,26 @@ int launch(Ctx* c, int nb, const XorDesc& d_in, const c128* coef, long long coef
                 if (local == (pass == 1)) {
                     if (w >= kXSlots + 4) return -1;
                     d.mask[w] = d_in.mask[j]; d.vre[w] = d_in.vre[j]; d.vim[w] = d_in.vim[j]; d.zmask[w] = d_in.zmask[j];
+                    d.wre[w] = d_in.wre[j]; d.wim[w] = d_in.wim[j];
                     ++w;
                     if (!local) ++nrem;
                 }
             }
             while (pass == 0 && (nrem % kSPR)) {  // dummy gathers with zero weight keep the rounds uniform
                 if (w >= kXSlots + 4) return -1;
-                d.mask[w] = 1; d.vre[w] = 0.0; d.vim[w] = 0.0; d.zmask[w] = 0;
+                d.mask[w] = 1; d.vre[w] = 0.0; d.vim[w] = 0.0; d.zmask[w] = 0; d.wre[w] = 0.0; d.wim[w] = 0.0;
                 ++w; ++nrem;
             }
         }
         d.x_nrem[e] = nrem;
     }
     d.x_begin[d_in.n_x] = w;
-    for (int j = w; j < kXSlots + 4; ++j) { d.mask[j] = 1; d.vre[j] = d.vim[j] = 0.0; d.zmask[j] = 0; }
+    for (int j = w; j < kXSlots + 4; ++j) { d.mask[j] = 1; d.vre[j] = d.vim[j] = d.wre[j] = d.wim[j] = 0.0; d.zmask[j] = 0; }
+    for (int j = 0; j < kXSlots + 4; ++j) {
+        unsigned kt = 0;
+        for (int k = 0; k < R; ++k) kt |= ((unsigned)__builtin_popcount((k * NT) & d.zmask[j]) & 1u) << k;
+        d.ktab[j] = kt;
+    }
     if constexpr (NG == 0 && RV && ND <= 1 && !SG) {
         // One X-type term whose thread-local slots are exactly the single-bit flips NT·{1,2,4,…} (transverse-field
         // drivers): run the fully unrolled variant.  The local slots are put in ascending mask order first.
@@ -498,13 +517,25 @@ int traj_matvec_xor(Ctx* c, int n, int nb, const std::vector<const TermDev*>& ts
         } else {
             if (!td->xor_form || d.n_x >= kXTerms || slots + (int)td->xor_masks.size() > kXSlots) return 0;
             d.x_begin[d.n_x] = slots;
+            // a term whose slot values are all purely imaginary (a Y-field driver) is stored as real numbers: 2 FMAs per gather
+            // instead of 4, the factor i goes onto the term's coefficient inside the kernel
+            bool term_imag = true, term_real = true;
             for (size_t j = 0; j < td->xor_masks.size(); ++j) {
+                const c128 v = td->xor_vals[j], w = j < td->xor_vals1.size() ? td->xor_vals1[j] : v;
+                term_imag = term_imag && v.x == 0.0 && w.x == 0.0;
+                term_real = term_real && v.y == 0.0 && w.y == 0.0;
+            }
+            const bool rot = term_imag && !term_real;
+            d.x_imag[d.n_x] = rot ? 1 : 0;
+            if (rot) d.any_signed = 1;  // the rotation lives in the two-valued code path
+            for (size_t j = 0; j < td->xor_masks.size(); ++j) {
+                const c128 v = td->xor_vals[j], w = j < td->xor_vals1.size() ? td->xor_vals1[j] : v;
                 d.mask[slots] = td->xor_masks[j];
                 d.zmask[slots] = j < td->xor_zmasks.size() ? td->xor_zmasks[j] : 0;
                 if (d.zmask[slots]) d.any_signed = 1;
-                d.vre[slots] = td->xor_vals[j].x;
-                d.vim[slots] = td->xor_vals[j].y;
-                all_real = all_real && td->xor_vals[j].y == 0.0;
+                d.vre[slots] = rot ? v.y : v.x;  d.vim[slots] = rot ? 0.0 : v.y;
+                d.wre[slots] = rot ? w.y : w.x;  d.wim[slots] = rot ? 0.0 : w.y;
+                all_real = all_real && d.vim[slots] == 0.0 && d.wim[slots] == 0.0;
                 ++slots;
             }
             d.x_coef[d.n_x] = (int)t;
