@@ -162,15 +162,35 @@ __device__ __forceinline__ void do_chunk(const XorDesc& d, const int* s_mask, co
 #pragma unroll
             for (int q = 0; q < kSPR; ++q) {
                 const double vr = s_vre[j + q], vi = s_vim[j + q];
+                if (SG) {
+                    const unsigned par = s_kt[j + q] ^ (0u - ((pmask >> (j + q)) & 1u));
+                    const double wr = s_wre[j + q], wi = s_wim[j + q];
 #pragma unroll
-                for (int kk = 0; kk < CH; ++kk) cacc<RV>(ar[kk], ai[kk], vr, vi, vv[q][kk]);
+                    for (int kk = 0; kk < CH; ++kk) {
+                        const bool odd = (par >> (C0 + kk)) & 1u;
+                        cacc<RV>(ar[kk], ai[kk], odd ? wr : vr, odd ? wi : vi, vv[q][kk]);
+                    }
+                } else {
+#pragma unroll
+                    for (int kk = 0; kk < CH; ++kk) cacc<RV>(ar[kk], ai[kk], vr, vi, vv[q][kk]);
+                }
             }
         }
-        local_acc<R, CH, C0, 1, RV>(xo, ar, ai, s_vre[NG], s_vim[NG]);
-        if (R > 2) local_acc<R, CH, C0, 2 % R, RV>(xo, ar, ai, s_vre[NG + 1], s_vim[NG + 1]);
-        if (R > 4) local_acc<R, CH, C0, 4 % R, RV>(xo, ar, ai, s_vre[NG + 2], s_vim[NG + 2]);
-        if (R > 8) local_acc<R, CH, C0, 8 % R, RV>(xo, ar, ai, s_vre[NG + 3], s_vim[NG + 3]);
-        const c128 cc = cfs[d.x_coef[0]];
+        if (SG) {
+#define OQB_PAR(J) (s_kt[J] ^ (0u - ((pmask >> (J)) & 1u)))
+            local_acc<R, CH, C0, 1, RV>(xo, ar, ai, s_vre[NG], s_vim[NG], OQB_PAR(NG), s_wre[NG], s_wim[NG]);
+            if (R > 2) local_acc<R, CH, C0, 2 % R, RV>(xo, ar, ai, s_vre[NG + 1], s_vim[NG + 1], OQB_PAR(NG + 1), s_wre[NG + 1], s_wim[NG + 1]);
+            if (R > 4) local_acc<R, CH, C0, 4 % R, RV>(xo, ar, ai, s_vre[NG + 2], s_vim[NG + 2], OQB_PAR(NG + 2), s_wre[NG + 2], s_wim[NG + 2]);
+            if (R > 8) local_acc<R, CH, C0, 8 % R, RV>(xo, ar, ai, s_vre[NG + 3], s_vim[NG + 3], OQB_PAR(NG + 3), s_wre[NG + 3], s_wim[NG + 3]);
+#undef OQB_PAR
+        } else {
+            local_acc<R, CH, C0, 1, RV>(xo, ar, ai, s_vre[NG], s_vim[NG]);
+            if (R > 2) local_acc<R, CH, C0, 2 % R, RV>(xo, ar, ai, s_vre[NG + 1], s_vim[NG + 1]);
+            if (R > 4) local_acc<R, CH, C0, 4 % R, RV>(xo, ar, ai, s_vre[NG + 2], s_vim[NG + 2]);
+            if (R > 8) local_acc<R, CH, C0, 8 % R, RV>(xo, ar, ai, s_vre[NG + 3], s_vim[NG + 3]);
+        }
+        c128 cc = cfs[d.x_coef[0]];
+        if (SG && d.x_imag[0]) cc = make_double2(-cc.y, cc.x);  // the term's slot values were stored without their factor i
 #pragma unroll
         for (int kk = 0; kk < CH; ++kk) {
             outr[kk] = fma(cc.x, ar[kk], outr[kk]); outr[kk] = fma(-cc.y, ai[kk], outr[kk]);
@@ -344,6 +364,11 @@ __global__ void __launch_bounds__(NT, 1)
     }
 }
 
+inline void swap_slots(XorDesc& d, int a, int b) {
+    std::swap(d.mask[a], d.mask[b]); std::swap(d.zmask[a], d.zmask[b]);
+    std::swap(d.vre[a], d.vre[b]); std::swap(d.vim[a], d.vim[b]); std::swap(d.wre[a], d.wre[b]); std::swap(d.wim[a], d.wim[b]);
+}
+
 template <int R, int NT, int S, bool RV, int ND, int EPI, int NG = 0, bool SG = false>
 int launch(Ctx* c, int nb, const XorDesc& d_in, const c128* coef, long long coef_ld, const c128* psi, c128* dpsi,
            const RkEpilogue* rk) {
@@ -373,12 +398,7 @@ int launch(Ctx* c, int nb, const XorDesc& d_in, const c128* coef, long long coef
     }
     d.x_begin[d_in.n_x] = w;
     for (int j = w; j < kXSlots + 4; ++j) { d.mask[j] = 1; d.vre[j] = d.vim[j] = d.wre[j] = d.wim[j] = 0.0; d.zmask[j] = 0; }
-    for (int j = 0; j < kXSlots + 4; ++j) {
-        unsigned kt = 0;
-        for (int k = 0; k < R; ++k) kt |= ((unsigned)__builtin_popcount((k * NT) & d.zmask[j]) & 1u) << k;
-        d.ktab[j] = kt;
-    }
-    if constexpr (NG == 0 && RV && ND <= 1 && !SG) {
+    if constexpr (NG == 0 && RV && ND <= 1 && (!SG || EPI == 0)) {
         // One X-type term whose thread-local slots are exactly the single-bit flips NT·{1,2,4,…} (transverse-field
         // drivers): run the fully unrolled variant.  The local slots are put in ascending mask order first.
         constexpr int LOG2R = R == 16 ? 4 : (R == 8 ? 3 : (R == 4 ? 2 : 1));
@@ -389,16 +409,14 @@ int launch(Ctx* c, int nb, const XorDesc& d_in, const c128* coef, long long coef
             if (ok) {
                 for (int a = ng; a < ng + nl; ++a)  // sort the local slots by mask
                     for (int b = a + 1; b < ng + nl; ++b)
-                        if (d.mask[b] < d.mask[a]) {
-                            std::swap(d.mask[a], d.mask[b]); std::swap(d.vre[a], d.vre[b]); std::swap(d.vim[a], d.vim[b]);
-                        }
+                        if (d.mask[b] < d.mask[a]) swap_slots(d, a, b);
                 for (int q = 0; q < LOG2R; ++q) ok = ok && d.mask[ng + q] == (NT << q);
             }
             if (ok) {
-                if (ng == 8) return launch<R, NT, S, RV, ND, EPI, 8>(c, nb, d_in, coef, coef_ld, psi, dpsi, rk);
+                if (ng == 8) return launch<R, NT, S, RV, ND, EPI, 8, SG>(c, nb, d_in, coef, coef_ld, psi, dpsi, rk);
                 if constexpr (R == 16) {
-                    if (ng == 4) return launch<R, NT, S, RV, ND, EPI, 4>(c, nb, d_in, coef, coef_ld, psi, dpsi, rk);
-                    return launch<R, NT, S, RV, ND, EPI, 12>(c, nb, d_in, coef, coef_ld, psi, dpsi, rk);
+                    if (ng == 4) return launch<R, NT, S, RV, ND, EPI, 4, SG>(c, nb, d_in, coef, coef_ld, psi, dpsi, rk);
+                    return launch<R, NT, S, RV, ND, EPI, 12, SG>(c, nb, d_in, coef, coef_ld, psi, dpsi, rk);
                 }
             }
         }
@@ -407,9 +425,12 @@ int launch(Ctx* c, int nb, const XorDesc& d_in, const c128* coef, long long coef
         const int ng = d.x_nrem[0], nl = d.x_begin[1] - ng;
         for (int a = ng; a < ng + nl; ++a)
             for (int b = a + 1; b < ng + nl; ++b)
-                if (d.mask[b] < d.mask[a]) {
-                    std::swap(d.mask[a], d.mask[b]); std::swap(d.vre[a], d.vre[b]); std::swap(d.vim[a], d.vim[b]);
-                }
+                if (d.mask[b] < d.mask[a]) swap_slots(d, a, b);
+    }
+    for (int j = 0; j < kXSlots + 4; ++j) {  // after every reordering: the k-dependent half of each slot's row parity
+        unsigned kt = 0;
+        for (int k = 0; k < R; ++k) kt |= ((unsigned)__builtin_popcount((k * NT) & d.zmask[j]) & 1u) << k;
+        d.ktab[j] = kt;
     }
     d.coef_shared = coef_ld == 0 ? 1 : 0;
     const size_t smem = (size_t)S * (R * NT + kCoefPad) * sizeof(c128);
