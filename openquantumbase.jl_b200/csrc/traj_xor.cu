@@ -113,7 +113,7 @@ __device__ __forceinline__ void local_dispatch(int hk, const c128 (&xo)[R], doub
 }
 
 // one chunk of CH rows (rows C0 … C0+CH-1 of this thread)
-template <int R, int NT, int CH, int C0, bool RV, int ND, int EPI, int NG, bool SG, bool LF>
+template <int R, int NT, int CH, int C0, bool RV, int ND, int EPI, int NG, bool SG>
 __device__ __forceinline__ void do_chunk(const XorDesc& d, const int* s_mask, const unsigned* s_kt, unsigned pmask, const double* s_vre,
                                          const double* s_vim, const double* s_wre, const double* s_wim,
                                          const c128* __restrict__ x, const c128* cfs, const c128 (&xo)[R],
@@ -176,13 +176,7 @@ __device__ __forceinline__ void do_chunk(const XorDesc& d, const int* s_mask, co
                 }
             }
         }
-        if (!LF) {
-            // gathered slots fixed at compile time, thread-local partners described at run time (bond masks, mixed fields …)
-            for (int j = NG; j < d.x_begin[1]; ++j) {
-                if (SG) local_dispatch<R, CH, C0, RV>(s_mask[j] / NT, xo, ar, ai, s_vre[j], s_vim[j], s_kt[j] ^ (0u - ((pmask >> j) & 1u)), s_wre[j], s_wim[j]);
-                else local_dispatch<R, CH, C0, RV>(s_mask[j] / NT, xo, ar, ai, s_vre[j], s_vim[j]);
-            }
-        } else if (SG) {
+        if (SG) {
 #define OQB_PAR(J) (s_kt[J] ^ (0u - ((pmask >> (J)) & 1u)))
             local_acc<R, CH, C0, 1, RV>(xo, ar, ai, s_vre[NG], s_vim[NG], OQB_PAR(NG), s_wre[NG], s_wim[NG]);
             if (R > 2) local_acc<R, CH, C0, 2 % R, RV>(xo, ar, ai, s_vre[NG + 1], s_vim[NG + 1], OQB_PAR(NG + 1), s_wre[NG + 1], s_wim[NG + 1]);
@@ -269,7 +263,7 @@ __device__ __forceinline__ void do_chunk(const XorDesc& d, const int* s_mask, co
 }
 
 // R rows per thread (r = tid + k·NT), S ring stages, RV: all slot values real, ND: real diagonal terms in registers
-template <int R, int NT, int S, bool RV, int ND, int EPI, int NG, bool SG, bool LF>
+template <int R, int NT, int S, bool RV, int ND, int EPI, int NG, bool SG>
 __global__ void __launch_bounds__(NT, 1)
     traj_xor_kernel(int nb, const __grid_constant__ XorDesc d, const c128* __restrict__ coef, long long coef_ld,
                     const c128* psi, c128* dpsi, double wa, double wt, const c128* __restrict__ rk_psi0,
@@ -356,9 +350,9 @@ __global__ void __launch_bounds__(NT, 1)
         const c128* p0 = EPI == 2 ? rk_psi0 + (size_t)b * n : nullptr;
         c128* ac = EPI != 0 ? rk_acc + (size_t)b * n : nullptr;
         double nrm = 0.0;
-        do_chunk<R, NT, CH, 0, RV, ND, EPI, NG, SG, LF>(d, s_mask, s_kt, pmask, s_vre, s_vim, s_wre, s_wim, x, cfs, xo, dreg, cdiag, out, tid, wa, wt, p0, ac, nrm);
+        do_chunk<R, NT, CH, 0, RV, ND, EPI, NG, SG>(d, s_mask, s_kt, pmask, s_vre, s_vim, s_wre, s_wim, x, cfs, xo, dreg, cdiag, out, tid, wa, wt, p0, ac, nrm);
         if (R > 8)
-            do_chunk<R, NT, CH, (R > 8 ? 8 : 0), RV, ND, EPI, NG, SG, LF>(d, s_mask, s_kt, pmask, s_vre, s_vim, s_wre, s_wim, x, cfs, xo, dreg, cdiag, out, tid, wa, wt, p0, ac, nrm);
+            do_chunk<R, NT, CH, (R > 8 ? 8 : 0), RV, ND, EPI, NG, SG>(d, s_mask, s_kt, pmask, s_vre, s_vim, s_wre, s_wim, x, cfs, xo, dreg, cdiag, out, tid, wa, wt, p0, ac, nrm);
         if (EPI == 3 && norm_part) {  // per-warp partial of ‖ψ_b‖² in a fixed order: 16 slots per trajectory, unused ones zero
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) nrm += __shfl_xor_sync(0xffffffffu, nrm, o);
@@ -375,7 +369,7 @@ inline void swap_slots(XorDesc& d, int a, int b) {
     std::swap(d.vre[a], d.vre[b]); std::swap(d.vim[a], d.vim[b]); std::swap(d.wre[a], d.wre[b]); std::swap(d.wim[a], d.wim[b]);
 }
 
-template <int R, int NT, int S, bool RV, int ND, int EPI, int NG = 0, bool SG = false, bool LF = true>
+template <int R, int NT, int S, bool RV, int ND, int EPI, int NG = 0, bool SG = false>
 int launch(Ctx* c, int nb, const XorDesc& d_in, const c128* coef, long long coef_ld, const c128* psi, c128* dpsi,
            const RkEpilogue* rk) {
     XorDesc d = d_in;
@@ -425,16 +419,9 @@ int launch(Ctx* c, int nb, const XorDesc& d_in, const c128* coef, long long coef
                     return launch<R, NT, S, RV, ND, EPI, 12, SG>(c, nb, d_in, coef, coef_ld, psi, dpsi, rk);
                 }
             }
-            if constexpr (EPI == 0 && R == 16) {
-                // any thread-local partner set (bond masks: nearest-neighbour XX / YY couplings) with 4, 8 or 12 gathered slots:
-                // the gather rounds are still compiled with fixed bounds, only the local partners are dispatched at run time
-                if (ng == 8) return launch<R, NT, S, RV, ND, 0, 8, SG, false>(c, nb, d_in, coef, coef_ld, psi, dpsi, rk);
-                if (ng == 4) return launch<R, NT, S, RV, ND, 0, 4, SG, false>(c, nb, d_in, coef, coef_ld, psi, dpsi, rk);
-                if (ng == 12) return launch<R, NT, S, RV, ND, 0, 12, SG, false>(c, nb, d_in, coef, coef_ld, psi, dpsi, rk);
-            }
         }
     }
-    if constexpr (NG > 0 && LF) {  // same reordering as the detection above: local slots ascending
+    if constexpr (NG > 0) {  // same reordering as the detection above: local slots ascending
         const int ng = d.x_nrem[0], nl = d.x_begin[1] - ng;
         for (int a = ng; a < ng + nl; ++a)
             for (int b = a + 1; b < ng + nl; ++b)
@@ -449,7 +436,7 @@ int launch(Ctx* c, int nb, const XorDesc& d_in, const c128* coef, long long coef
     const size_t smem = (size_t)S * (R * NT + kCoefPad) * sizeof(c128);
     static DevOnce cfg;
     if (!cfg.done(c->device)) {
-        OQB_CUDA(c, cudaFuncSetAttribute(traj_xor_kernel<R, NT, S, RV, ND, EPI, NG, SG, LF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        OQB_CUDA(c, cudaFuncSetAttribute(traj_xor_kernel<R, NT, S, RV, ND, EPI, NG, SG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         cfg.set(c->device);
     }
     int sms = 148;
@@ -461,7 +448,7 @@ int launch(Ctx* c, int nb, const XorDesc& d_in, const c128* coef, long long coef
     {
         // algorithmic bytes: read ψ + write dψ (+ the RK operands: 1 extra vector for modes 1/3, 3 for mode 2)
         ProfScope prof(c, (EPI == 0 ? 32.0 : (EPI == 2 ? 80.0 : 48.0)) * R * NT * (double)nb);
-        traj_xor_kernel<R, NT, S, RV, ND, EPI, NG, SG, LF><<<grid, NT, smem, c->stream>>>(nb, d, coef, coef_ld, psi, dpsi, rk ? rk->wa : 0.0,
+        traj_xor_kernel<R, NT, S, RV, ND, EPI, NG, SG><<<grid, NT, smem, c->stream>>>(nb, d, coef, coef_ld, psi, dpsi, rk ? rk->wa : 0.0,
                                                                              rk ? rk->wt : 0.0, rk ? rk->psi0 : nullptr,
                                                                              rk ? rk->acc : nullptr, rk ? rk->norm_part : nullptr);
     }
