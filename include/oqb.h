@@ -293,6 +293,7 @@ int oqb_ame_davies_stats(const oqb_ame* ame, int64_t* n_terms, int64_t* n_cross,
 int oqb_ame_set_tables(oqb_ame* ame, const void* h_Cm, const double* h_Wt_re, const double* h_Wt_im);
 int oqb_ame_get_rotated_couplings(oqb_ame* ame, void* h_A);
 int oqb_ame_get_levels(oqb_ame* ame, double* h_w); /* the lvl eigen-energies of the current eigen-system */
+int oqb_ame_get_eigenvectors(oqb_ame* ame, void* h_V); /* its n×lvl eigenvector matrix (column-major, host) */
 /* One-sided AME (src/opensys/davies.jl:367-379): npairs (α,β) 0-based; tables at the UNROUNDED
  * gap matrix ω_ba[i,j] = w[j]−w[i] (src/opensys/opensys_util.jl:65): h_gam/h_S are lvl×lvl per pair,
  * or one shared table when tables_shared != 0 (SingleFunctionMatrix). */

@@ -122,6 +122,7 @@ SIGNATURES = {
     "oqb_expect_diag": [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p],
     "oqb_expect": [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p],
     "oqb_ame_get_levels": [c_void_p, c_dp],
+    "oqb_ame_get_eigenvectors": [c_void_p, c_void_p],
     "oqb_liouv_create": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, C.POINTER(c_void_p)],
     "oqb_liouv_destroy": [c_void_p],
     "oqb_liouv_add_davies_ohmic": [c_void_p, c_int, c_int, C.c_double, C.c_double, C.c_double, c_int, C.c_double, C.c_double, c_void_p],

@@ -431,6 +431,16 @@ int oqb_ame_get_levels(oqb_ame* a, double* h_w) {
     return 0;
 }
 
+int oqb_ame_get_eigenvectors(oqb_ame* a, void* h_V) {
+    OQB_DEVICE(a, a->ctx);
+    oqb_ctx* c = a->ctx;
+    if (!a->have_eigen || !a->has_v) return set_error(c, OQB_EINVAL, "oqb_ame_get_eigenvectors: no eigenvector matrix is set");
+    if (!h_V) return set_error(c, OQB_EINVAL, "oqb_ame_get_eigenvectors: null output");
+    OQB_CUDA(c, cudaMemcpyAsync(h_V, a->d_V, (size_t)a->n * a->lvl * sizeof(c128), cudaMemcpyDeviceToHost, c->stream));
+    OQB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
 int oqb_ame_get_rotated_couplings(oqb_ame* a, void* h_A) {
     OQB_DEVICE(a, a->ctx);
     oqb_ctx* c = a->ctx;

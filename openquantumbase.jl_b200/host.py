@@ -1007,6 +1007,24 @@ class DiffEqLiouvillian:
         self._lind = [x for x in self.opensys if isinstance(x, LindbladLiouvillian)]
         self._other = [x for x in self.opensys if not isinstance(x, LindbladLiouvillian)]
 
+    @property
+    def _v(self):
+        """Eigenvectors of the current plan (n × lvl, numpy).  In library mode they live on the device and are fetched on demand."""
+        val = self.__dict__.get("_v_val")
+        plan = self.__dict__.get("_v_lazy")
+        if val is None and plan is not None:
+            n = self.H.size[0]
+            buf = np.empty((self.lvl, n), dtype=C128)  # column-major n × lvl
+            self.ctx.check(self.ctx.lib.oqb_ame_get_eigenvectors(plan, buf.ctypes.data))
+            val = self.__dict__["_v_val"] = np.ascontiguousarray(buf.T)
+            self.__dict__["_v_lazy"] = None
+        return val
+
+    @_v.setter
+    def _v(self, value):
+        self.__dict__["_v_val"] = value
+        self.__dict__["_v_lazy"] = None
+
     # ---- {false,false} ------------------------------------------------------------------
     def _fused_lindblad(self):
         return (isinstance(self.H, DenseHamiltonian) and len(self._lind) == 1 and not self._lind[0].time_dependent)
@@ -1096,8 +1114,10 @@ class DiffEqLiouvillian:
     # ---- {true,false} -------------------------------------------------------------------
     def _library_eligible(self):
         """The whole call can run inside the library (oqb_liouv, csrc/liouvillian.cu): dense Hamiltonian terms, constant
-        couplings, Davies / one-sided terms.  Opt in with `op.library = True` (the C-only path a ccall user gets)."""
-        return (getattr(self, "library", False) and isinstance(self.H, DenseHamiltonian) and not self.adiabatic_frame
+        couplings, Davies / one-sided terms.  This is the DEFAULT route (the C-only path a ccall user gets); `op.library = False`
+        makes the mirror orchestrate the same pieces itself (host LAPACK or `device_eigh`), and a supplied `(w, v)`
+        (`rhs_with_eig`), a SparseHamiltonian or time-dependent couplings always take that route."""
+        return (getattr(self, "library", True) and isinstance(self.H, DenseHamiltonian) and not self.adiabatic_frame
                 and all(isinstance(lv, (DaviesGenerator, OneSidedAMELiouvillian)) and isinstance(lv.coupling, ConstantCouplings)
                         for lv in self.opensys_eig)
                 and sum(isinstance(lv, OneSidedAMELiouvillian) for lv in self.opensys_eig) <= 1)
@@ -1205,6 +1225,7 @@ class DiffEqLiouvillian:
             self.ctx.check(self.ctx.lib.oqb_ame_get_levels(plan, _lib.dptr(wbuf)))
             self._ame, self._ame_s = plan, (s, None)
             self._w, self._v, self._v_dev, self._plan = wbuf, None, None, {"h": plan, "w": wbuf, "v": None, "v_dev": None, "lvl": self.lvl}
+            self.__dict__["_v_lazy"] = plan  # the eigenvectors stay on the device; `op._v` downloads them on first access
             return
         if w is None:
             key = (s, None)
