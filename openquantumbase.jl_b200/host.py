@@ -1417,6 +1417,8 @@ class DiffEqLiouvillian:
         sv = _svec(p(t), B)
         if w is None and self._library_eligible():  # one C call: grouping by s, eigen-systems, tables, rotations
             cf = _coef(self.H.f, sv)
+            if sv.size == 1 or np.all(sv == sv[0]):
+                self._prepare_ame(float(sv[0]))  # exposes the (cached) plan as op._ame / op._w like the host-orchestrated route
             self.ctx.check(self.ctx.lib.oqb_liouv_rhs(self._liouv(), B, _lib.dptr(cf), int(sv.size == 1), io.u.ptr, io.du.ptr))
             for lv in self.opensys:  # :106-108
                 lv(io.du, io.u, p, t)
