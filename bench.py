@@ -143,9 +143,19 @@ def run_secondary(Q, torch, ctx):
 
     def short(r, keys):
         return {k: r[k] for k in keys if k in r}
+
+    def clocked(fn):  # SM clock / throttle reasons while this configuration runs
+        smp = ClockSampler(ctx.device)
+        smp.start()
+        try:
+            r = fn()
+        finally:
+            ck = smp.stop()
+        r["clocks"] = ck
+        return r
     try:
-        r = OC.run_c2(Q, torch, 3, False)
-        out["C2_dephasing_diagL"] = short(r, ("config", "workload", "value", "ms_per_step", "roofline"))
+        r = clocked(lambda: OC.run_c2(Q, torch, 5, False))
+        out["C2_dephasing_diagL"] = short(r, ("config", "workload", "value", "ms_per_step", "roofline", "clocks"))
         torch.cuda.empty_cache()
         with ctx.option("lindblad_diag", 0):
             r = OC.run_c2(Q, torch, 2, False)
@@ -154,8 +164,8 @@ def run_secondary(Q, torch, ctx):
     except Exception as e:  # noqa: BLE001
         out["C2_error"] = f"{type(e).__name__}: {e}"
     try:
-        r = OC.run_c4(Q, torch, 5)
-        out["C4_traj_xor"] = short(r, ("config", "workload", "value", "ms_per_step", "roofline", "jump_kernel", "evolve"))
+        r = clocked(lambda: OC.run_c4(Q, torch, 5))
+        out["C4_traj_xor"] = short(r, ("config", "workload", "value", "ms_per_step", "roofline", "jump_kernel", "evolve", "clocks"))
         torch.cuda.empty_cache()
         out["C4_generic_kernel_same_operators"] = OC.run_c4_matvec_only(Q, torch, 3, generic=True)
         torch.cuda.empty_cache()
@@ -168,8 +178,8 @@ def run_secondary(Q, torch, ctx):
     except Exception as e:  # noqa: BLE001
         out["C4_error"] = f"{type(e).__name__}: {e}"
     try:
-        r = OC.run_c5(Q, torch, 5)
-        out["C5_per_gpu"] = short(r, ("config", "workload", "value", "ms_per_step", "roofline"))
+        r = clocked(lambda: OC.run_c5(Q, torch, 5))
+        out["C5_per_gpu"] = short(r, ("config", "workload", "value", "ms_per_step", "roofline", "clocks"))
         torch.cuda.empty_cache()
     except Exception as e:  # noqa: BLE001
         out["C5_error"] = f"{type(e).__name__}: {e}"
