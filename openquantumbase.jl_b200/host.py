@@ -195,8 +195,26 @@ def _svec(s, B):
 
 
 def _coef(funcs, svals) -> np.ndarray:
-    """rows = members (1 if shared), cols = closures: [f_i(s_b)] evaluated on the host."""
-    return np.ascontiguousarray([[float(np.real(f(float(s)))) for f in funcs] for s in svals], dtype=np.float64)
+    """rows = members (1 if shared), cols = closures: [f_i(s_b)] evaluated on the host.  A closure is first tried on the whole
+    s vector (one call per closure instead of one per member: a 4096-member schedule sweep otherwise spends 10 ms per RHS
+    call in Python); anything that is not element-wise on arrays falls back to the scalar calls of the reference."""
+    sv = np.asarray(svals, dtype=np.float64).ravel()
+    out = np.empty((sv.size, len(funcs)), dtype=np.float64)
+    for i, f in enumerate(funcs):
+        col = None
+        if sv.size > 8:
+            try:
+                v = np.real(np.asarray(f(sv)))
+                if v.ndim == 0:
+                    v = np.full(sv.size, float(v))
+                if v.shape == sv.shape and np.array_equal(v[:2], [float(np.real(f(float(sv[0])))), float(np.real(f(float(sv[1]))))]):
+                    col = v.astype(np.float64)
+            except Exception:  # noqa: BLE001 — not vectorisable (branches on s, math.* calls …)
+                col = None
+        if col is None:
+            col = [float(np.real(f(float(s)))) for s in sv]
+        out[:, i] = col
+    return np.ascontiguousarray(out)
 
 
 class _HostIO:
