@@ -136,6 +136,45 @@ def test_c3_ame_1024_vs_group_oracle(Q):
     assert relerr(duh.transpose(0, 2, 1), ref) < TOL
 
 
+def test_c3_degenerate_start_1024_vs_group_oracle(Q):
+    """The anneal's starting point at full size: H(0) = −ΣX on 10 qubits (11 levels with binomial degeneracies; the zero-gap
+    group holds 91 866 level pairs, every other group tens of thousands) with the K = 10 per-qubit Z couplings — the dense
+    per-group path (masked couplings as stacked products) against the independent group oracle at 1e-12 with the SAME (w, v),
+    and the library's one-call route (its own device eigensolver: another basis inside every degenerate level, the RHS is
+    invariant) at 1e-9."""
+    import scipy.linalg as sla
+    from oqb_b200 import host as Hm
+    from oracle import davies_groups as DG
+    rng = np.random.default_rng(3100)
+    nq, n = 10, 1024
+    Hd, Hp, z = tfim_dense(nq, rng)
+    coup = [2 * np.pi * np.diag(zq).astype(complex) for zq in z]
+    w, v = sla.eigh((2 * np.pi * Hd).real)
+    v = v.astype(complex)
+    bath, ob = Q.Ohmic(1e-4, 4, 16), O.Ohmic(1e-4, 4, 16)
+    H = Q.DenseHamiltonian([lambda s: 1 - s, lambda s: s], [Hd, Hp])
+    p = Q.ODEParams(H, 10.0)
+    u = np.stack([lowrank_rho(rng, n)])
+    groups = DG.gap_groups(w, 8, 8)
+    assert len(groups[1]) == 91866 and len(groups[0]) == 10
+    rot = [v.conj().T @ c @ v for c in coup]
+    rho = v.conj().T @ u[0] @ v
+    X = -1j * (w[:, None] * rho - rho * w[None, :])
+    DG.davies_eig_acc(X, rho, rot, w, ob.spectrum, lambda x_: 0.0, 8, 8, groups)
+    ref = (v @ X @ v.conj().T)[None]
+    ctx = Q.get_context()
+    op = Q.DiffEqLiouvillian(H, [Q.DaviesGenerator(Q.ConstantCouplings(coup, unit="ħ"), bath, Q.ZERO_LAMBSHIFT)], [], n)
+    with ctx.option("debug_checks", 1):
+        du = op.rhs_with_eig(np.zeros_like(u), u, p, 0.0, w, v)
+        stats = Hm.davies_stats(ctx, op._ame)
+    assert relerr(du, ref) < TOL
+    assert stats[3] >= 3 and 0 < stats[4] <= 40   # zero group and the ±2·(2π) groups dense; only the non-vanishing blocks are kept
+    op.clear_plans()
+    du2 = op(np.zeros_like(u), u, p, 0.0)          # library route: device eigensolver, tables, dense groups behind one call
+    assert relerr(du2, ref) < 1e-9
+    op.clear_plans()
+
+
 def test_long_k_real_operand_kernel_vs_numpy(Q):
     """The kernel the headline number is timed on — zgemm_tma_kernel real-operand variant, K > 512 (128×64 CTA) — checked
     directly: with no eigenbasis term the AME RHS is v(C_H∘(v'uv))v', C_H[a,b] = −i(w_a − w_b), i.e. four long-K products
