@@ -45,8 +45,7 @@ print(json.dumps(res)); print(st.getvalue()[:3500])
 import collections
 acc = collections.OrderedDict()
 lib = ctx.lib
-names = ["oqb_dense_hamiltonian", "oqb_ame_set_eigen_device", "oqb_ame_set_lambshift_spline", "oqb_ame_davies_ohmic_begin",
-         "oqb_ame_davies_fetch_groups", "oqb_ame_davies_ohmic_finish", "oqb_ame_create", "oqb_ame_destroy"]
+names = ["oqb_dense_hamiltonian", "oqb_ame_set_eigen_device", "oqb_ame_set_lambshift_spline", "oqb_ame_gaps_build", "oqb_ame_add_davies_ohmic", "oqb_ame_create", "oqb_ame_destroy"]
 class W:
     def __init__(s, f, n): s.f, s.n = f, n
     def __call__(s, *a):

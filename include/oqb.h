@@ -231,22 +231,12 @@ int oqb_ame_eigenvectors_real(const oqb_ame* ame, int* out);
 int oqb_ame_set_davies(oqb_ame* ame, const double* h_gam, const double* h_S, int64_t ncross,
                        const int32_t* h_cross_idx, const double* h_cross_rate, int64_t nlamb,
                        const int32_t* h_lamb_idx, const double* h_lamb_rate_S);
-/* The same tables built ON THE DEVICE for an Ohmic bath (γ(ω) of src/bath/ohmic.jl:35-41, S ≡ 0), including the
- * device-side part of GapIndices (src/opensys/opensys_util.jl:25-61): the l(l−1)/2 gaps are rounded (Julia's
- * round(x, sigdigits)), sorted and scanned on the GPU; *n_multi / *n_zero return how many level pairs belong to
- * multi-pair gap groups / to the zero group.  oqb_ame_davies_fetch_groups returns those pairs as lexicographic pair
- * indices p(i<j) = i·l − i(i+1)/2 + (j−i−1) (multi pairs sorted by key, stable) with their keys; the host turns them into
- * the cross-term lists (same arrays as oqb_ame_set_davies) and oqb_ame_davies_ohmic_finish installs them. */
 /* Tabulated Lamb shift for the device-built tables: the n+2 prefiltered coefficients of the quadratic B-spline that
  * build_lambshift / construct_interpolations return for a range grid x0 + k·dx, k = 0…n−1 (src/bath/bath_util.jl:26-38,
  * src/interpolation.jl:22-34; Interpolations.jl BSpline(Quadratic(Line(OnGrid()))), value 0 outside the grid).
- * oqb_ame_davies_ohmic_begin then fills S(ω̃_ab) from it on the device; n = 0 restores S ≡ 0. */
+ * oqb_ame_set_onesided_ohmic then fills S at the unrounded gaps from it on the device (the Davies tables take their spline as an
+ * argument of oqb_ame_add_davies_ohmic); n = 0 restores S ≡ 0. */
 int oqb_ame_set_lambshift_spline(oqb_ame* ame, int n, double x0, double dx, const double* h_coef);
-int oqb_ame_davies_ohmic_begin(oqb_ame* ame, double eta, double wc, double beta, int digits, int sigdigits,
-                               int64_t* n_multi, int64_t* n_zero);
-int oqb_ame_davies_fetch_groups(oqb_ame* ame, int32_t* h_multi_pair, double* h_multi_key, int32_t* h_zero_pair);
-int oqb_ame_davies_ohmic_finish(oqb_ame* ame, int64_t ncross, const int32_t* h_cross_idx, const double* h_cross_rate,
-                                int64_t nlamb, const int32_t* h_lamb_idx, const double* h_lamb_rate_S);
 int oqb_ame_clear_davies(oqb_ame* ame);
 
 /* ---- GapIndices and the Davies term list, built inside the library ------------------------------------------------

@@ -75,9 +75,6 @@ SIGNATURES = {
     "oqb_ohmic_timescales": [c_void_p, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, c_int,
                              c_dp, c_dp, c_dp, c_dp],
     "oqb_bspline_eval": [c_void_p, c_int, C.c_double, C.c_double, c_void_p, c_int, c_void_p, c_void_p],
-    "oqb_ame_davies_ohmic_begin": [c_void_p, C.c_double, C.c_double, C.c_double, c_int, c_int, c_i64p, c_i64p],
-    "oqb_ame_davies_fetch_groups": [c_void_p, c_i32p, c_dp, c_i32p],
-    "oqb_ame_davies_ohmic_finish": [c_void_p, c_i64, c_i32p, c_dp, c_i64, c_i32p, c_dp],
     "oqb_ame_clear_davies": [c_void_p],
     "oqb_set_option": [c_void_p, C.c_char_p, c_i64],
     "oqb_get_option": [c_void_p, C.c_char_p, c_i64p],

@@ -321,11 +321,9 @@ int oqb_ame_destroy(oqb_ame* a) {
     oqb_ame_clear_onesided(a);
     oqb_ame_clear_jump(a);
     ame_clear_gaps(a);
-    ame_free(a->ctx, a->d_grp_key);
     ame_free(a->ctx, a->d_flag);
     ame_free(a->ctx, a->d_cdiag);
     ame_free(a->ctx, a->d_Scoef);
-    ame_free(a->ctx, a->d_grp_pair);
     (void)he;
     ame_free(a->ctx, a->d_coup); ame_free(a->ctx, a->d_V); ame_free(a->ctx, a->d_w); ame_free(a->ctx, a->d_A); ame_free(a->ctx, a->d_Cm);
     delete a;

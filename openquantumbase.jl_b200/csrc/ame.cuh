@@ -77,10 +77,6 @@ struct oqb_ame {
     long long* d_slot_ptr = nullptr;  // nslots+1 offsets into the term list
     int32_t* d_term = nullptr;        // (coupling, row, col) per term, sorted by (row, col) within a slot
     double* d_slot_rate = nullptr;    // γ at the slot's gap
-    // device-side GapIndices (ame_gaps.cu): pairs flagged as members of multi-pair groups / of the zero group
-    double* d_grp_key = nullptr;
-    int32_t* d_grp_pair = nullptr;
-    long long n_multi = 0, n_zero = 0;
     // tabulated Lamb shift for the device-built tables: quadratic B-spline coefficients (n_Stab+2) on x0 + k·dx
     int n_Stab = 0;
     double S_x0 = 0.0, S_dx = 1.0;

@@ -170,42 +170,6 @@ class GapGroups:
         return gam, Sm, np.ascontiguousarray(cross_rate), np.ascontiguousarray(lamb_rate_S)
 
 
-_TRIU_CACHE = {}
-
-
-def pair_to_ij(l: int, pairs: np.ndarray):
-    """Lexicographic pair index p(i<j) = i·l − i(i+1)/2 + (j−i−1) → (i, j) (what oqb_ame_davies_fetch_groups returns)."""
-    if l not in _TRIU_CACHE:
-        if len(_TRIU_CACHE) > 4:
-            _TRIU_CACHE.clear()
-        _TRIU_CACHE[l] = np.triu_indices(l, 1)
-    iu, ju = _TRIU_CACHE[l]
-    pairs = np.asarray(pairs, dtype=np.int64)
-    return iu[pairs], ju[pairs]
-
-
-def cross_lists_from_groups(l: int, multi_pair, multi_key, zero_pair):
-    """The cross-term / Lamb-shift lists of `GapGroups` from the device-side grouping (ame_gaps.cu): `multi_pair` are the
-    pairs that share their rounded gap with another pair, sorted by key (stable: the reference's loop order inside a
-    group), `zero_pair` the pairs of the zero group.  Returns (cross_idx, cross_key, lamb_idx, lamb_key)."""
-    parts = []
-    multi_key = np.asarray(multi_key, dtype=np.float64)
-    if len(multi_key):
-        mi, mj = pair_to_ij(l, multi_pair)
-        starts = np.flatnonzero(np.r_[True, multi_key[1:] != multi_key[:-1]])
-        ends = np.r_[starts[1:], len(multi_key)]
-        parts.append(_group_cross_lists(mi, mj, starts, ends, multi_key[starts]))
-    if len(zero_pair):
-        zi, zj = pair_to_ij(l, np.sort(np.asarray(zero_pair)))
-        aa = np.r_[zi, zj, np.arange(l)]
-        bb = np.r_[zj, zi, np.arange(l)]
-        parts.append(_zero_group_lists(aa, bb))
-    if not parts:
-        return np.zeros((0, 4), dtype=np.int32), np.zeros(0), np.zeros((0, 3), dtype=np.int32), np.zeros(0)
-    return (np.concatenate([q[0] for q in parts]), np.concatenate([q[1] for q in parts]),
-            np.concatenate([q[2] for q in parts]), np.concatenate([q[3] for q in parts]))
-
-
 def jump_slots(w, K, digits=8, sigdigits=8):
     """Probability slots of `ame_jump` (reference src/opensys/trajectory_jump.jl:14-51) in the reference's order,
     from the sort-based grouping: unique non-zero gap keys ascending (GapIndices keeps `uniq_w` sorted,

@@ -167,31 +167,6 @@ def test_jump_slots_follow_the_reference_order():
             assert sorted(zip(rows, cols)) == [(int(r), int(c)) for _, r, c in seg] and all(t[0] == i for t in seg)
 
 
-def test_cross_lists_from_device_grouping_match_gapgroups():
-    """gaps.cross_lists_from_groups (fed with what ame_gaps.cu returns: the members of multi-pair groups sorted by key,
-    and the zero-group pairs, as lexicographic pair indices) rebuilds exactly the lists GapGroups builds from w."""
-    from oqb_b200.gaps import cross_lists_from_groups, pair_to_ij
-    for w in (np.array([0.0, 1.0, 1.0, 2.0, 3.0, 3.0 + 1e-12, 5.0]), np.array([-1.5, -0.5, 0.5, 1.5, 2.5]),
-              np.sort(np.random.default_rng(4).standard_normal(9))):
-        l = len(w)
-        G = GapGroups(w, 8, 8)
-        iu, ju = np.triu_indices(l, 1)
-        gap = w[ju] - w[iu]
-        zero = np.abs(gap) <= 1e-8
-        key = np.where(zero, np.inf, round_sigdigits(np.where(zero, 1.0, gap), 8))
-        order = np.argsort(key, kind="stable")           # what the device radix sort produces
-        ks = key[order]
-        fin = np.isfinite(ks)
-        dup = np.zeros(len(ks), dtype=bool)
-        dup[1:] |= (ks[1:] == ks[:-1]) & fin[1:]
-        dup[:-1] |= (ks[:-1] == ks[1:]) & fin[:-1]
-        ci, ck, li, lk = cross_lists_from_groups(l, order[dup], ks[dup], order[~fin])
-        assert np.array_equal(ci, G.cross_idx) and np.array_equal(ck, G.cross_key)
-        assert np.array_equal(li, G.lamb_idx) and np.array_equal(lk, G.lamb_key)
-        i2, j2 = pair_to_ij(l, np.arange(len(iu)))
-        assert np.array_equal(i2, iu) and np.array_equal(j2, ju)
-
-
 def test_c_abi_header_is_plain_c_and_links(c_demo_exe):
     """include/oqb.h is a C header (no C++/torch types) and every symbol the demo uses resolves at link time; without a GPU
     the program stops at oqb_create with a clear message and a non-zero exit code (no CPU fallback)."""
