@@ -274,13 +274,7 @@ int oqb_ame_add_correlated(oqb_ame* ame, int alpha, int beta, const double* h_ga
  * dense blocks kept (blocks whose masked coupling vanishes to rounding are dropped).  Any pointer may be NULL. */
 int oqb_ame_davies_stats(const oqb_ame* ame, int64_t* n_terms, int64_t* n_cross, int64_t* n_lamb, int64_t* n_dense_groups,
                          int64_t* n_dense_blocks);
-/* General closed-form tables, for generators whose rates are not |A_ab|²γ — CorrelatedDaviesGenerator
- * (src/opensys/davies.jl:231-296: du += Σ_(α,β) γ_αβ(ω)(L^β ρ L^α' − ½{L^α'L^β, ρ}) − i[H_LS, ρ]) with a
- * non-degenerate gap structure: the eigenbasis terms become  X = Cm∘ρ̃ + diag(Wᵀ-sum),  X_aa += Σ_b W[a,b]ρ̃_bb, with
- * complex W.  h_Cm: lvl×lvl complex column-major INCLUDING the Hamiltonian part −i(w_a − w_b); h_Wt_re / h_Wt_im:
- * Wt[b + a·lvl] = Re/Im W[a,b] (h_Wt_im may be NULL).  The host builds them from the rotated couplings
- * (oqb_ame_get_rotated_couplings: K lvl×lvl matrices v'A_αv as the device computed them). */
-int oqb_ame_set_tables(oqb_ame* ame, const void* h_Cm, const double* h_Wt_re, const double* h_Wt_im);
+/* K lvl×lvl matrices v'A_αv as the device computed them (column-major, host) */
 int oqb_ame_get_rotated_couplings(oqb_ame* ame, void* h_A);
 int oqb_ame_get_levels(oqb_ame* ame, double* h_w); /* the lvl eigen-energies of the current eigen-system */
 int oqb_ame_get_eigenvectors(oqb_ame* ame, void* h_V); /* its n×lvl eigenvector matrix (column-major, host) */

@@ -86,7 +86,6 @@ SIGNATURES = {
                                  c_void_p],
     "oqb_ame_add_correlated": [c_void_p, c_int, c_int, c_dp, c_dp, c_dp, c_dp, C.c_double, C.c_double],
     "oqb_ame_davies_stats": [c_void_p, c_i64p, c_i64p, c_i64p, c_i64p, c_i64p],
-    "oqb_ame_set_tables": [c_void_p, c_void_p, c_dp, c_dp],
     "oqb_ame_get_rotated_couplings": [c_void_p, c_void_p],
     "oqb_ame_set_onesided": [c_void_p, c_int, c_i32p, c_i32p, c_dp, c_dp, c_int],
     "oqb_ame_clear_onesided": [c_void_p],

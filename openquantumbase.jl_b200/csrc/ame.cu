@@ -400,25 +400,6 @@ int oqb_ame_set_eigen_device(oqb_ame* a, const double* d_w, const void* d_v) {
     return set_eigen_impl(a, d_w, d_v, true, "oqb_ame_set_eigen_device");
 }
 
-int oqb_ame_set_tables(oqb_ame* a, const void* h_Cm, const double* h_Wt_re, const double* h_Wt_im) {
-    OQB_DEVICE(a, a->ctx);
-    oqb_ctx* c = a->ctx;
-    if (!a->have_eigen) return set_error(c, OQB_EINVAL, "oqb_ame_set_tables: call oqb_ame_set_eigen first");
-    if (!h_Cm || !h_Wt_re) return set_error(c, OQB_EINVAL, "oqb_ame_set_tables: null table");
-    OQB_TRY(oqb_ame_clear_davies(a));
-    const size_t ll = (size_t)a->lvl * a->lvl;
-    OQB_TRY(ame_alloc(c, (void**)&a->d_Wt, ll * sizeof(double)));
-    OQB_CUDA(c, cudaMemcpyAsync(a->d_Wt, h_Wt_re, ll * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-    if (h_Wt_im) {
-        OQB_TRY(ame_alloc(c, (void**)&a->d_Wt_im, ll * sizeof(double)));
-        OQB_CUDA(c, cudaMemcpyAsync(a->d_Wt_im, h_Wt_im, ll * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-    }
-    OQB_CUDA(c, cudaMemcpyAsync(a->d_Cm, h_Cm, ll * sizeof(c128), cudaMemcpyHostToDevice, c->stream));
-    OQB_CUDA(c, cudaStreamSynchronize(c->stream));
-    a->davies = true;
-    return 0;
-}
-
 int oqb_ame_get_levels(oqb_ame* a, double* h_w) {
     OQB_DEVICE(a, a->ctx);
     oqb_ctx* c = a->ctx;

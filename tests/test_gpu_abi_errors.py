@@ -39,7 +39,6 @@ def test_status_codes_and_messages(Q):
     w = np.arange(n, dtype=float)
     assert lib.oqb_ame_jump(a, 2, u.ptr, u.ptr, None, None, None, 0) == 1
     assert lib.oqb_ame_set_eigen(a, dp(w), None) == 0
-    assert lib.oqb_ame_set_tables(a, None, None, None) == 1
     lib.oqb_ame_destroy(a)
     # zgemm mode
     assert lib.oqb_set_zgemm_mode(ctx.h, 7) == 1
@@ -108,6 +107,95 @@ def test_plain_c_nccl_reduce(c_comm_exe):
     out = subprocess.run([c_comm_exe], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "c_comm_demo OK" in out.stdout
+
+
+def test_round2_entry_points_reject_bad_arguments(Q):
+    """Argument and ordering checks of the round-2 entry points: options, GapIndices / term builder, the Liouvillian object,
+    resample, the Λ integrator and the communicator calls return a status and a message instead of crashing."""
+    ctx = Q.get_context()
+    lib = ctx.lib
+    dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    assert lib.oqb_set_option(ctx.h, b"no_such_option", 1) == 1 and b"unknown option" in lib.oqb_last_error(ctx.h)
+    v = C.c_int64()
+    assert lib.oqb_set_option(ctx.h, b"davies_dense_min_pairs", 5) == 0 and lib.oqb_get_option(ctx.h, b"davies_dense_min_pairs", C.byref(v)) == 0 and v.value == 5
+    assert lib.oqb_set_option(ctx.h, b"davies_dense_min_pairs", 0) == 0
+    n = 4
+    m = np.ascontiguousarray(np.diag([1.0, -1, 1, -1]).astype(complex)[None])
+    a = C.c_void_p()
+    assert lib.oqb_ame_create(ctx.h, n, n, 1, m.ctypes.data, C.byref(a)) == 0
+    nk, nz = C.c_int64(), C.c_int64()
+    assert lib.oqb_ame_gaps_build(a, 8, 8, C.byref(nk), C.byref(nz)) == 1 and b"set_eigen" in lib.oqb_last_error(ctx.h)
+    assert lib.oqb_ame_add_davies_ohmic(a, 0, 1, 1e-4, 25.0, 0.5, 0, 0.0, 1.0, None) == 1 and b"gaps_build" in lib.oqb_last_error(ctx.h)
+    w = np.array([0.0, 1.0, 1.0, 2.5])
+    assert lib.oqb_ame_set_eigen(a, dp(w), None) == 0
+    assert lib.oqb_ame_gaps_build(a, 8, 8, C.byref(nk), C.byref(nz)) == 0 and nk.value == 3 and nz.value == 1   # gaps 1, 1.5, 2.5; one degenerate pair
+    assert lib.oqb_ame_add_davies_ohmic(a, 0, 2, 1e-4, 25.0, 0.5, 0, 0.0, 1.0, None) == 1 and b"coupling slice" in lib.oqb_last_error(ctx.h)
+    assert lib.oqb_ame_add_davies(a, 0, 1, None, None, None, None, 0.0, 0.0) == 1
+    assert lib.oqb_ame_add_correlated(a, 0, 3, None, None, None, None, 0.0, 0.0) == 1 and b"out of range" in lib.oqb_last_error(ctx.h)
+    assert lib.oqb_ame_add_davies_ohmic(a, 0, 1, 1e-4, 25.0, 0.5, 0, 0.0, 1.0, None) == 0
+    st = [C.c_int64() for _ in range(5)]
+    assert lib.oqb_ame_davies_stats(a, *[C.byref(x) for x in st]) == 0 and st[0].value == 1
+    cache = Q.DeviceBatch(1, n, n)
+    assert lib.oqb_ame_update_cache(a, None) == 1
+    assert lib.oqb_ame_update_cache(a, cache.ptr) == 0
+    lib.oqb_ame_destroy(a)
+    # the Liouvillian object
+    L = C.c_void_p()
+    assert lib.oqb_liouv_create(ctx.h, None, n, 8, 8, 1, m.ctypes.data, C.byref(L)) == 1 and b"null Hamiltonian" in lib.oqb_last_error(ctx.h)
+    hterms = np.ascontiguousarray(np.stack([np.diag([0.0, 1, 1, 2.5]).astype(complex)]))
+    h = C.c_void_p()
+    assert lib.oqb_dense_create(ctx.h, n, 1, hterms.ctypes.data, 0, None, C.byref(h)) == 0
+    assert lib.oqb_liouv_create(ctx.h, h, n, 8, 8, 1, m.ctypes.data, C.byref(L)) == 0
+    assert lib.oqb_liouv_add_davies_ohmic(L, 1, 1, 1e-4, 25.0, 0.5, 0, 0.0, 1.0, None) == 1 and b"coupling slice" in lib.oqb_last_error(ctx.h)
+    assert lib.oqb_liouv_add_davies_fn(L, 0, 1, None, None, None, None) == 1
+    assert lib.oqb_liouv_set_plan_cache(L, 0) == 1
+    assert lib.oqb_liouv_add_davies_ohmic(L, 0, 1, 1e-4, 25.0, 0.5, 0, 0.0, 1.0, None) == 0
+    u = Q.DeviceBatch(2, n, n)
+    one = np.ones((1, 1))
+    assert lib.oqb_liouv_rhs(L, 2, None, 1, u.ptr, u.ptr) == 1
+    assert lib.oqb_liouv_rhs(L, 2, dp(one), 1, u.ptr, u.zeros_like().ptr) == 0
+    pb, ch = C.c_uint64(), C.c_uint64()
+    assert lib.oqb_liouv_stats(L, C.byref(pb), C.byref(ch), None, None) == 0 and pb.value == 1
+    assert lib.oqb_liouv_destroy(L) == 0 and lib.oqb_dense_destroy(h) == 0
+    # resample / communicator
+    assert lib.oqb_resample(ctx.h, 4, 0, None, None, None, None) == 1
+    assert lib.oqb_allreduce_obs(None, None, 1) == 1 and lib.oqb_comm_init_rank(ctx.h, 2, 5, None, C.byref(L)) != 0
+
+
+def test_set_davies_with_host_tables_and_lists(Q):
+    """oqb_ame_set_davies — l×l γ/S tables at the signed rounded gaps and explicit cross-term / L'L lists, everything evaluated by
+    the host (here: the test-side `gaps.GapGroups` statement of GapIndices) — against the oracle's literal gap loop on a
+    spectrum with degenerate levels and equal spacings."""
+    from oqb_b200 import _lib
+    from oqb_b200.gaps import GapGroups
+    from oracle import oqb_oracle as O
+    rng = np.random.default_rng(17)
+    l, nb = 7, 3
+    w = np.array([-2.0, -2.0, -0.5, 0.25, 1.0, 1.75, 1.75])
+    gam_f = lambda x: x + 1 if x >= 0 else (1 - x) * np.exp(x)
+    lam_f = lambda x: x + 0.1
+    cs = [(lambda z: z + z.conj().T)(rng.standard_normal((l, l)) + 1j * rng.standard_normal((l, l))) for _ in range(2)]
+    ctx = Q.get_context()
+    lib = ctx.lib
+    a = C.c_void_p()
+    cbuf = np.ascontiguousarray(np.stack([c.T for c in cs]))
+    ctx.check(lib.oqb_ame_create(ctx.h, l, l, 2, cbuf.ctypes.data, C.byref(a)))
+    ctx.check(lib.oqb_ame_set_eigen(a, _lib.dptr(np.ascontiguousarray(w)), None))
+    G = GapGroups(w, 8, 8)
+    gam, Sm, crate, lrs = G.tables(gam_f, lam_f)
+    gam, Sm = np.ascontiguousarray(gam.T), np.ascontiguousarray(Sm.T)
+    ci, li = np.ascontiguousarray(G.cross_idx), np.ascontiguousarray(G.lamb_idx)
+    ctx.check(lib.oqb_ame_set_davies(a, _lib.dptr(gam), _lib.dptr(Sm), len(ci), ci.ctypes.data_as(_lib.c_i32p), _lib.dptr(crate),
+                                     len(li), li.ctypes.data_as(_lib.c_i32p), _lib.dptr(np.ascontiguousarray(lrs))))
+    rho = rng.standard_normal((nb, l, l)) + 1j * rng.standard_normal((nb, l, l))
+    u, du = Q.DeviceBatch.from_host(rho), Q.DeviceBatch.from_host(np.zeros_like(rho))
+    ctx.check(lib.oqb_ame_eig_acc(a, nb, u.ptr, du.ptr, 0))
+    ctx.sync()
+    gi = O.build_gap_indices(w, 8, 8)
+    ref = np.stack([O.DaviesGenerator(cs, gam_f, lam_f).rhs_acc(np.zeros((l, l), complex), rho[b], gi, None, 0.0) for b in range(nb)])
+    got = du.to_host()
+    assert np.linalg.norm(got - ref) < 1e-12 * np.linalg.norm(ref)
+    lib.oqb_ame_destroy(a)
 
 
 def test_bath_and_option_entry_points_reject_bad_arguments(Q):
