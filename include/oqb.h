@@ -67,6 +67,8 @@ int oqb_launch_count(const oqb_ctx* ctx, uint64_t* n); /* kernels launched throu
  *   "ame_host_chunk_mib" (128)                  — chunk size of oqb_ame_rhs_host's H2D/D2H pipeline
  *   "davies_dense_min_pairs" (0 = cost model)   — gap groups with at least this many level pairs use the dense per-group
  *                                                  products instead of the cross-term list;  "davies_max_cross" (5e7) caps the list.
+ *   "fuse_cross" (1)                            — keep the Hadamard in the rotation product's epilogue when the only extra Davies terms
+ *                                                  are list cross terms (their ρ̃ sources are recovered as X/C); 0: separate passes
  *   "debug_checks" (0)                          — 1: every index list the Davies term builder produces is range- and
  *                                                  consistency-checked on the device before use (an error is returned) */
 int oqb_set_option(oqb_ctx* ctx, const char* name, int64_t value);

@@ -39,6 +39,48 @@ __global__ void rowscale_kernel(int n, int l, const c128* __restrict__ diag, con
 
 }  // namespace
 
+// Cross terms without a separate copy of ρ̃ (the Hadamard stays in the GEMM epilogue): the ρ̃ entries the cross terms read are
+// recovered from X = C∘ρ̃ as X/C — exact to rounding whatever |C| is, as long as C ≠ 0 at those positions (checked once per plan).
+// All sources are gathered BEFORE anything is scattered, because a cross term's target may be another term's source.
+__global__ void cross_gather_kernel(int l, long long ncross, const int32_t* __restrict__ idx, const c128* __restrict__ Cm,
+                                    const c128* __restrict__ X, c128* __restrict__ val) {
+    const int bb = blockIdx.y;
+    const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (e >= ncross) return;
+    const long long pos = idx[4 * e + 1] + (long long)idx[4 * e + 3] * l;  // (b, b2)
+    const c128 x = X[(long long)bb * l * l + pos], cv = Cm[pos];
+    const double den = cv.x * cv.x + cv.y * cv.y;
+    val[(long long)bb * ncross + e] = make_double2((x.x * cv.x + x.y * cv.y) / den, (x.y * cv.x - x.x * cv.y) / den);
+}
+__global__ void cross_scatter_kernel(int l, int K, const c128* __restrict__ A, long long ncross, const int32_t* __restrict__ idx,
+                                     const double* __restrict__ rate, const c128* __restrict__ val, c128* __restrict__ X) {
+    const int bb = blockIdx.y;
+    const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (e >= ncross) return;
+    const int a = idx[4 * e], b = idx[4 * e + 1], a2 = idx[4 * e + 2], b2 = idx[4 * e + 3];
+    double sx = 0.0, sy = 0.0;
+    for (int k = 0; k < K; ++k) {
+        const c128* Ak = A + (long long)k * l * l;
+        const c128 p = Ak[a + (long long)b * l], q = Ak[a2 + (long long)b2 * l];
+        sx += p.x * q.x + p.y * q.y;  // p·conj(q)
+        sy += p.y * q.x - p.x * q.y;
+    }
+    const double r = rate[e];
+    sx *= r; sy *= r;
+    const c128 v = val[(long long)bb * ncross + e];
+    c128* d = X + (long long)bb * l * l + a + (long long)a2 * l;
+    atomicAdd(&d->x, sx * v.x - sy * v.y);
+    atomicAdd(&d->y, sx * v.y + sy * v.x);
+}
+__global__ void cross_source_zero_kernel(int l, long long ncross, const int32_t* __restrict__ idx, const c128* __restrict__ Cm,
+                                         unsigned int* __restrict__ cnt) {
+    const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (e >= ncross) return;
+    const c128 cv = Cm[idx[4 * e + 1] + (long long)idx[4 * e + 3] * l];
+    const double den = cv.x * cv.x + cv.y * cv.y;
+    if (!(den > 1e-280) || !isfinite(den)) atomicAdd(cnt, 1u);
+}
+
 // *out = true when no entry of v[0..n) has a non-zero imaginary part (synchronises the stream)
 int ame_detect_real(oqb_ame* a, const c128* v, long long n, bool* out) {
     oqb_ctx* c = a->ctx;
@@ -61,6 +103,27 @@ int detect_real(oqb_ame* a, const c128* v, long long n, bool* out) { return ame_
 bool needs_general_path(const oqb_ame* a) { return a->ncross > 0 || a->d_Moff || a->npairs > 0 || a->nd > 0; }
 
 const int kDenseSlab = 16;  // dense per-group blocks processed per pair of products (scratch: slab·l² per member)
+
+// Cross terms only (no off-diagonal L'L matrix, no dense groups, no one-sided / correlated terms, a list small enough to
+// keep one recovered value per entry and member): the Hadamard can stay in GEMM 2's epilogue.  Decided once per plan.
+int cross_fusable(oqb_ame* a, bool* out) {
+    oqb_ctx* c = a->ctx;
+    *out = false;
+    if (!c->opt.fuse_cross || !(a->ncross > 0 && a->ncross <= 2000000) || a->d_Moff || a->npairs > 0 || a->nd > 0 || !a->corr_terms.empty() || !a->davies)
+        return 0;
+    if (a->cross_fuse_state < 0) {
+        if (!a->d_flag) OQB_TRY(ame_alloc(c, (void**)&a->d_flag, 256));
+        unsigned int h_cnt = 1;
+        OQB_CUDA(c, cudaMemsetAsync(a->d_flag, 0, sizeof(unsigned int), c->stream));
+        cross_source_zero_kernel<<<(unsigned)((a->ncross + 255) / 256), 256, 0, c->stream>>>(a->lvl, a->ncross, a->d_cross_idx, a->d_Cm, a->d_flag);
+        OQB_LAUNCH_CHECK(c);
+        OQB_CUDA(c, cudaMemcpyAsync(&h_cnt, a->d_flag, sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
+        OQB_CUDA(c, cudaStreamSynchronize(c->stream));
+        a->cross_fuse_state = h_cnt == 0 ? 1 : 0;
+    }
+    *out = a->cross_fuse_state == 1;
+    return 0;
+}
 
 // Eigenbasis terms on ρ̃ = R (lvl×lvl per member).  overwrite: X = …, else X += ….
 // with_h: include −i[diag w, ρ̃].  scratch: nb·l + (npairs > 0 ? (npairs + 1)·nb·l² : 0) complex.
@@ -166,9 +229,11 @@ int ame_rhs_impl(oqb_ame* a, int nb, const c128* u, c128* du) {
     if (!u || !du) return set_error(c, OQB_EINVAL, "oqb_ame_rhs: null state pointer");
     const int n = a->n, l = a->lvl;
     const long long nn = (long long)n * n, ll = (long long)l * l, ln = (long long)l * n;
-    const bool general = needs_general_path(a);
-    // per-member scratch: T (l×n) + X (l×l) [+ R (l×l)] + eig scratch
-    const size_t per = ((size_t)ln + ll + (general ? ll : 0) + eig_scratch_elems(a, 1)) * sizeof(c128);
+    bool fuse_cross = false;
+    OQB_TRY(cross_fusable(a, &fuse_cross));
+    const bool general = needs_general_path(a) && !fuse_cross;
+    // per-member scratch: T (l×n) + X (l×l) [+ R (l×l)] + eig scratch (fused cross terms: one recovered value per entry)
+    const size_t per = ((size_t)ln + ll + (general ? ll : 0) + eig_scratch_elems(a, 1) + (fuse_cross ? (size_t)a->ncross : 0)) * sizeof(c128);
     int chunk = (int)(kAmeBudget / per);
     if (chunk < 1) chunk = 1;
     if (chunk > nb) chunk = nb;
@@ -208,8 +273,29 @@ int ame_rhs_impl(oqb_ame* a, int nb, const c128* u, c128* du) {
             q.E = a->d_Cm; q.lde = l; q.strideE = 0;
             if (a->davies) { q.diag_out = scratch; q.strideDiag = l; }
             OQB_TRY(zgemm(c, q));
+            c128* val = scratch + (size_t)cnt * l;
+            if (fuse_cross) {
+                // ρ̃ at the cross sources = X/C, gathered while X is still exactly C∘ρ̃ (before the diagonal rate term and before
+                // any scatter: a cross term's target may be another term's source)
+                for (int b0 = 0; b0 < cnt; b0 += 65535) {
+                    const int bc = cnt - b0 < 65535 ? cnt - b0 : 65535;
+                    dim3 grid((unsigned)((a->ncross + 255) / 256), (unsigned)bc);
+                    cross_gather_kernel<<<grid, 256, 0, c->stream>>>(l, a->ncross, a->d_cross_idx, a->d_Cm, X + (long long)b0 * ll, val + (long long)b0 * a->ncross);
+                    OQB_LAUNCH_CHECK(c);
+                }
+            }
             if (a->davies) OQB_TRY(davies_diag(c, l, a->d_Wt, scratch, X, cnt));
             if (a->davies && a->d_Wt_im) OQB_TRY(davies_diag(c, l, a->d_Wt_im, scratch, X, cnt, true));
+            if (fuse_cross) {
+                for (const DaviesTerm& t : a->terms)
+                    for (int b0 = 0; b0 < cnt; b0 += 65535) {
+                        const int bc = cnt - b0 < 65535 ? cnt - b0 : 65535;
+                        dim3 grid((unsigned)((a->ncross + 255) / 256), (unsigned)bc);
+                        cross_scatter_kernel<<<grid, 256, 0, c->stream>>>(l, t.nk, a->d_A + (long long)t.k0 * ll, a->ncross, a->d_cross_idx, t.d_rate,
+                                                                          val + (long long)b0 * a->ncross, X + (long long)b0 * ll);
+                        OQB_LAUNCH_CHECK(c);
+                    }
+            }
         } else {
             q.C = R;
             OQB_TRY(zgemm(c, q));
@@ -479,6 +565,7 @@ int ame_davies_finish(oqb_ame* a, int64_t ncross, const int32_t* h_cross_idx, co
     }
     OQB_CUDA(c, cudaStreamSynchronize(c->stream));
     a->davies = true;
+    a->cross_fuse_state = -1;
     return 0;
 }
 

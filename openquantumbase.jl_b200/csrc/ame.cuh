@@ -37,6 +37,7 @@ struct oqb_ame {
     long long ncross = 0, nlamb = 0;
     int32_t* d_cross_idx = nullptr;  // (a,b,a2,b2) per cross entry — shared by all Davies terms (it depends on the gaps only)
     std::vector<DaviesTerm> terms;
+    int cross_fuse_state = -1;  // −1 unknown, 1: C ≠ 0 at every cross-term source (the Hadamard may stay in the GEMM epilogue), 0: not
     oqb::c128* d_Moff = nullptr;  // dense lvl×lvl off-diagonal part of −½G − iH_LS (nullptr when empty)
     // gap structure of the current eigen-system (ame_terms.cu, GapIndices of src/opensys/opensys_util.jl:25-61)
     bool have_gaps = false, lists_built = false;

@@ -790,6 +790,7 @@ int add_davies_impl(oqb_ame* a, int k0, int nk, const double* d_vals) {
     OQB_TRY(add_dense_blocks(a, A, nullptr, nk, d_vals));
     OQB_CUDA(c, cudaStreamSynchronize(c->stream));
     a->davies = true;
+    a->cross_fuse_state = -1;  // the Hadamard coefficients changed
     return 0;
 }
 
@@ -896,6 +897,7 @@ int ame_clear_terms(oqb_ame* a) {
     a->h_dense_groups.clear();
     a->zero_dense = false;
     a->lists_built = false;
+    a->cross_fuse_state = -1;
     a->dense_real = false;
     a->nd = 0;
     a->ncross = a->nlamb = 0;

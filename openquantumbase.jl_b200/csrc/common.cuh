@@ -29,6 +29,7 @@ struct Options {
     int ame_host_chunk_mib = 128;
     int davies_dense_min_pairs = 0;        // gap groups with at least this many level pairs take the dense per-group path (0 = cost model)
     long long davies_max_cross = 50000000; // cap on the cross-term list; larger groups go dense first
+    int fuse_cross = 1;       // keep the Hadamard in GEMM 2's epilogue when the only extra Davies terms are list cross terms
     int debug_checks = 0;     // device-side range / consistency checks of every index list the term builder produces
 };
 

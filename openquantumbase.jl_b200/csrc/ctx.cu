@@ -165,7 +165,7 @@ const OptEntry kOpts[] = {
     {"lindblad_diag", &Options::lindblad_diag}, {"coupling_diag", &Options::coupling_diag}, {"traj_kernel", &Options::traj_kernel},
     {"traj_ell", &Options::traj_ell}, {"rk_fuse", &Options::rk_fuse}, {"xor_fixed", &Options::xor_fixed}, {"xor_rows", &Options::xor_rows},
     {"ame_host_chunk_mib", &Options::ame_host_chunk_mib}, {"davies_dense_min_pairs", &Options::davies_dense_min_pairs},
-    {"debug_checks", &Options::debug_checks},
+    {"debug_checks", &Options::debug_checks}, {"fuse_cross", &Options::fuse_cross},
 };
 }  // namespace
 

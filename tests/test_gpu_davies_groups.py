@@ -164,6 +164,18 @@ def test_two_davies_generators_and_onesided(Q):
             du = opg.rhs_with_eig(np.zeros_like(u), u, Q.ODEParams(None, 1.0), 0.5, w, v)
         ref = np.stack([opo.rhs_with_eig(x, O.ODEParams(None, 1.0), 0.5, w, v) for x in u])
         assert relerr(du, ref) < TOL, thr
+    # cross terms only (two generators, equally spaced levels, no degenerate level ⇒ no L'L list): the fused-epilogue form
+    # (cross-term sources recovered as X/C, also on the diagonal) and the separate-pass form
+    w2 = np.sort(np.r_[np.arange(8) * 0.5, rng.standard_normal(n - 8) * 2 + 7.0])
+    H2 = v @ np.diag(w2) @ v.conj().T
+    Hg2, Ho2 = Q.DenseHamiltonian([lambda x: 1.0], [H2], unit="ħ"), O.DenseHamiltonian([lambda x: 1.0], [H2], unit="ħ")
+    og2 = Q.DiffEqLiouvillian(Hg2, terms_g[:2], [], n)
+    oo2 = O.DiffEqLiouvillian(Ho2, terms_o[:2], [], n)
+    ref2 = np.stack([oo2.rhs_with_eig(x, O.ODEParams(None, 1.0), 0.5, w2, v) for x in u])
+    for fuse in (1, 0):
+        with ctx.option("fuse_cross", fuse), ctx.option("davies_dense_min_pairs", 10 ** 9):
+            og2.clear_plans()
+            assert relerr(og2.rhs_with_eig(np.zeros_like(u), u, Q.ODEParams(None, 1.0), 0.5, w2, v), ref2) < TOL, fuse
     # update_cache! accumulates both generators (src/opensys/diffeq_liouvillian.jl:118-120)
     opg2 = Q.DiffEqLiouvillian(Hg, terms_g[:2], [], n)
     opo2 = O.DiffEqLiouvillian(Ho, terms_o[:2], [], n)

@@ -127,6 +127,13 @@ def test_c3_ame_1024_vs_group_oracle(Q):
                     op.clear_plans()
                     du = op.rhs_with_eig(np.zeros_like(u), u, p, 5.0, w, v)
                     assert relerr(du, ref) < TOL, (real_op, mode3m, op is op_dev)
+    # the Hadamard kept in the rotation product's epilogue with the cross-term sources recovered as X/C (default) against
+    # the separate-pass form: both against the oracle
+    for fuse in (1, 0):
+        with ctx.option("fuse_cross", fuse):
+            op_dev.clear_plans()
+            du = op_dev.rhs_with_eig(np.zeros_like(u), u, p, 5.0, w, v)
+            assert relerr(du, ref) < TOL, fuse
     # host-buffer entry point (Julia layout: column-major blocks)
     op_dev.clear_plans()
     op_dev._prepare_ame(0.5, w, v)
