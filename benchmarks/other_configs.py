@@ -407,7 +407,16 @@ def run_c4_matvec_only(Q, torch, steps, generic=False, random_pattern=False, pau
     kms, kb = a.value / max(b_.value, 1), w.value / max(b_.value, 1)
     hbm, src = peaks()
     nnz_row = (Ha.nnz + Hb.nnz) / n
-    return {"workload": f"12-qubit {('Pauli-string (' + pauli + ')') if pauli else ('UNSTRUCTURED random-pattern' if random_pattern else 'TFIM')} SparseHamiltonian, {B} psi of dim {n}, "
+    ceil = None
+    if random_pattern or generic:
+        # what the shared-memory gathers alone allow (measured on this device): gathers/s ÷ off-diagonal entries per row × 32 B
+        g = C.c_double()
+        ctx.check(ctx.lib.oqb_probe_smem_gather(ctx.h, 1 if random_pattern else 0, C.byref(g)))
+        per_row = Ha.nnz / n
+        ceil = {"gathers_per_sec": g.value, "pattern": "pseudo-random indices" if random_pattern else "XOR-permuted (conflict-free) indices",
+                "gathers_per_row": per_row, "ceiling_GBs": g.value / per_row * 32.0 / 1e9, "ceiling_frac_of_hbm": g.value / per_row * 32.0 / 1e9 / hbm,
+                "what": "oqb_probe_smem_gather: LDS.128 gathers from a staged 4096-entry state, nothing else in the kernel — an upper bound for any kernel that gathers psi from shared memory"}
+    return {"smem_gather_ceiling": ceil, "workload": f"12-qubit {('Pauli-string (' + pauli + ')') if pauli else ('UNSTRUCTURED random-pattern' if random_pattern else 'TFIM')} SparseHamiltonian, {B} psi of dim {n}, "
                         f"{nnz_row:.1f} entries per row, per-trajectory s" + (", generic kernels forced" if generic else ""),
             "value": B / (ms * 1e-3), "ms_per_step": ms,
             "roofline": {"bound": "hbm", "achieved": kb / 1e9 / (kms * 1e-3), "peak": hbm, "unit": "GB/s",

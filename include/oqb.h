@@ -495,6 +495,11 @@ int oqb_expect_diag(oqb_ctx* ctx, int n, int nobs, const double* d_diag, int nb,
 /* Measures FP64 DMMA / DFMA issue throughput of this device (TFLOP/s) — used by bench.py to state
  * the FP64 tensor ceiling next to the cuBLAS DGEMM figure. */
 int oqb_probe_fp64(oqb_ctx* ctx, double* dmma_tflops, double* dfma_tflops);
+/* Measures the shared-memory gather ceiling of this device for the trajectory matvec: 16-byte gathers per second from a staged
+ * 4096-entry state, with conflict-free XOR-permuted indices (pattern 0) or pseudo-random indices (pattern 1).  An operator with
+ * m entries per row cannot run faster than (gathers/s ÷ m)·32 algorithmic bytes per second, whatever the rest of the kernel does
+ * (why an unstructured sparse operator cannot reach the HBM roofline). */
+int oqb_probe_smem_gather(oqb_ctx* ctx, int pattern, double* gathers_per_sec);
 /* Per-launch CUDA-event timing of the ZGEMM kernel (the dominant kernel of every dense path) on the
  * context stream: between begin and end every ZGEMM launch is bracketed by an event pair;
  * end returns the summed kernel time, the launch count and the algorithmic flops (8·M·N·K·batch). */

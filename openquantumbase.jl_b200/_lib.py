@@ -146,6 +146,7 @@ SIGNATURES = {
     "oqb_allreduce_obs": [c_void_p, c_void_p, c_i64],
     "oqb_allgather_obs": [c_void_p, c_void_p, c_void_p, c_i64],
     "oqb_probe_fp64": [c_void_p, c_dp, c_dp],
+    "oqb_probe_smem_gather": [c_void_p, c_int, c_dp],
     "oqb_profile_begin": [c_void_p],
     "oqb_profile_end": [c_void_p, c_dp, C.POINTER(C.c_uint64), c_dp],
 }
