@@ -372,9 +372,11 @@ def pauli_sparse_c4(nq, model):
     return Hx, Hz, Ls
 
 
-def run_c4_matvec_only(Q, torch, steps, generic=False, random_pattern=False, pauli=None):
-    """The C4 ensemble matvec alone: `generic=True` forces the generic kernels on the TFIM operators (option "traj_kernel" = 1),
-    `random_pattern=True` swaps in an unstructured Hamiltonian (no kernel specialisation applies).  HBM roofline fraction of the kernel."""
+def run_c4_matvec_only(Q, torch, steps, generic=False, random_pattern=False, pauli=None, plain_ell=False):
+    """The C4 ensemble matvec alone: `generic=True` forces the kernels for operators WITHOUT Pauli structure on the TFIM operators
+    (option "traj_kernel" = 1), `random_pattern=True` swaps in an unstructured Hamiltonian (no Pauli specialisation applies); both take
+    the sliced-ELL kernel (csrc/traj_sell.cu) unless `plain_ell` (option "traj_ell" = 0: the round-1 ELL kernel).  HBM roofline
+    fraction of the kernel."""
     nq, n, B = 12, 4096, 65536
     ctx = Q.get_context()
     if pauli:
@@ -397,7 +399,7 @@ def run_c4_matvec_only(Q, torch, steps, generic=False, random_pattern=False, pau
     gam = np.full((1, nq), 0.05)
     dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
     mv = lambda: ctx.check(ctx.lib.oqb_traj_matvec(ens.sp, B, dp(cf), 0, dp(gam), 1, psi.ptr, dpsi.ptr))
-    with ctx.option("traj_kernel", 1 if generic else 0):
+    with ctx.option("traj_kernel", 1 if generic else 0), ctx.option("traj_ell", 0 if plain_ell else 1):
         ms = timed(mv, steps, 3, torch)
         ctx.check(ctx.lib.oqb_profile_begin(ctx.h))
         for _ in range(steps):
@@ -407,16 +409,24 @@ def run_c4_matvec_only(Q, torch, steps, generic=False, random_pattern=False, pau
     kms, kb = a.value / max(b_.value, 1), w.value / max(b_.value, 1)
     hbm, src = peaks()
     nnz_row = (Ha.nnz + Hb.nnz) / n
+    pl, pad = C.c_int(), C.c_double()
+    ctx.check(ctx.lib.oqb_traj_sell_stats(ens.sp, C.byref(pl), C.byref(pad)))
+    kernel = "traj_xor_kernel" if not (generic or random_pattern) else ("traj_matvec_kernel (plain ELL)" if plain_ell or not pl.value else "traj_sell_kernel")
     ceil = None
     if random_pattern or generic:
-        # what the shared-memory gathers alone allow (measured on this device): gathers/s ÷ off-diagonal entries per row × 32 B
-        g = C.c_double()
-        ctx.check(ctx.lib.oqb_probe_smem_gather(ctx.h, 1 if random_pattern else 0, C.byref(g)))
+        # what the shared-memory gathers alone allow (measured on this device): gathers/s ÷ off-diagonal entries per row × 32 B.
+        # Conflict-free order is what traj_sell_kernel's slot colouring buys (at `sell_padding` × the gathers); the random
+        # order is what a kernel that takes the columns as they come is capped at.
         per_row = Ha.nnz / n
-        ceil = {"gathers_per_sec": g.value, "pattern": "pseudo-random indices" if random_pattern else "XOR-permuted (conflict-free) indices",
-                "gathers_per_row": per_row, "ceiling_GBs": g.value / per_row * 32.0 / 1e9, "ceiling_frac_of_hbm": g.value / per_row * 32.0 / 1e9 / hbm,
+        ceil = {"gathers_per_row": per_row,
                 "what": "oqb_probe_smem_gather: LDS.128 gathers from a staged 4096-entry state, nothing else in the kernel — an upper bound for any kernel that gathers psi from shared memory"}
-    return {"smem_gather_ceiling": ceil, "workload": f"12-qubit {('Pauli-string (' + pauli + ')') if pauli else ('UNSTRUCTURED random-pattern' if random_pattern else 'TFIM')} SparseHamiltonian, {B} psi of dim {n}, "
+        for pat, label in ((0, "conflict_free"), (1, "random_order")):
+            if pat == 1 and not random_pattern:
+                continue
+            g = C.c_double()
+            ctx.check(ctx.lib.oqb_probe_smem_gather(ctx.h, pat, C.byref(g)))
+            ceil[label] = {"gathers_per_sec": g.value, "ceiling_GBs": g.value / per_row * 32.0 / 1e9, "ceiling_frac_of_hbm": g.value / per_row * 32.0 / 1e9 / hbm}
+    return {"kernel": kernel, "sell_padding": pad.value if pl.value else None, "smem_gather_ceiling": ceil, "workload": f"12-qubit {('Pauli-string (' + pauli + ')') if pauli else ('UNSTRUCTURED random-pattern' if random_pattern else 'TFIM')} SparseHamiltonian, {B} psi of dim {n}, "
                         f"{nnz_row:.1f} entries per row, per-trajectory s" + (", generic kernels forced" if generic else ""),
             "value": B / (ms * 1e-3), "ms_per_step": ms,
             "roofline": {"bound": "hbm", "achieved": kb / 1e9 / (kms * 1e-3), "peak": hbm, "unit": "GB/s",
@@ -488,8 +498,8 @@ def main():
             print(json.dumps(r), flush=True)
             torch.cuda.empty_cache()
             continue
-        if c in ("c4generic", "c4random", "c4yfield", "c4heisenberg"):
-            r = run_c4_matvec_only(Q, torch, args.steps, generic=c == "c4generic", random_pattern=c == "c4random",
+        if c in ("c4generic", "c4random", "c4yfield", "c4heisenberg", "c4generic_plain", "c4random_plain"):
+            r = run_c4_matvec_only(Q, torch, args.steps, generic=c.startswith("c4generic"), random_pattern=c.startswith("c4random"), plain_ell=c.endswith("_plain"),
                                    pauli={"c4yfield": "yfield", "c4heisenberg": "heisenberg"}.get(c))
             print(json.dumps(r), flush=True)
             torch.cuda.empty_cache()

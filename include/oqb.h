@@ -391,6 +391,9 @@ int oqb_traj_matvec(oqb_sparse* sp, int nb, const double* h_coefH, int coef_shar
                     const double* h_gamma, int gamma_shared, const void* d_psi, void* d_dpsi);
 int oqb_traj_matvec_host(oqb_sparse* sp, int nb, const double* h_coefH, int coef_shared,
                          const double* h_gamma, int gamma_shared, const void* h_psi, void* h_dpsi);
+/* Diagnostics of the sliced-ELL plans oqb_traj_matvec builds for operators without Pauli structure (csrc/traj_sell.cu):
+ *   *plans = plans held by this handle, *padding = stored ÷ real entries of the newest one (1.0 = no padding). */
+int oqb_traj_sell_stats(oqb_sparse* sp, int* plans, double* padding);
 /* out[b] = ‖ψ[b]‖²  (jump condition of the external callback) */
 int oqb_traj_norm2(oqb_sparse* sp, int nb, const void* d_psi, double* d_out);
 /* lind_jump / lindblad_jump{false,false}: prob[b][k] = γ_k‖L_k ψ[b]‖² (src/opensys/trajectory_jump.jl:2-12),

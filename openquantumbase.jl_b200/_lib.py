@@ -106,6 +106,7 @@ SIGNATURES = {
     "oqb_sparse_commutator": [c_void_p, c_int, c_dp, c_int, c_void_p, c_void_p],
     "oqb_traj_matvec": [c_void_p, c_int, c_dp, c_int, c_dp, c_int, c_void_p, c_void_p],
     "oqb_traj_matvec_host": [c_void_p, c_int, c_dp, c_int, c_dp, c_int, c_void_p, c_void_p],
+    "oqb_traj_sell_stats": [c_void_p, C.POINTER(C.c_int), c_dp],
     "oqb_traj_norm2": [c_void_p, c_int, c_void_p, c_void_p],
     "oqb_traj_jump": [c_void_p, c_int, c_dp, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int],
     "oqb_traj_apply_choice": [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int],

@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "liboqb_b200.so")
-SOURCES = ["ctx.cu", "zgemm.cu", "zgemm_tma.cu", "elementwise.cu", "dense.cu", "redfield_lambda.cu", "lambda_integrate.cu", "ame.cu", "ame_jump.cu", "ame_gaps.cu", "ame_terms.cu", "liouvillian.cu", "comm.cu", "bath.cu", "sparse.cu", "traj_fast.cu", "traj_xor.cu", "traj_evolve.cu", "probe.cu"]
+SOURCES = ["ctx.cu", "zgemm.cu", "zgemm_tma.cu", "elementwise.cu", "dense.cu", "redfield_lambda.cu", "lambda_integrate.cu", "ame.cu", "ame_jump.cu", "ame_gaps.cu", "ame_terms.cu", "liouvillian.cu", "comm.cu", "bath.cu", "sparse.cu", "traj_fast.cu", "traj_xor.cu", "traj_sell.cu", "traj_evolve.cu", "probe.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default"]
 

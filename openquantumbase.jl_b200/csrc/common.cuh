@@ -22,7 +22,9 @@ struct Options {
     int lindblad_diag = 1;    // exploit diagonal L_k
     int coupling_diag = 1;    // exploit diagonal couplings in the rotation v'c_αv
     int traj_kernel = 0;      // 0 = pick by operator structure, 1 = generic kernels only, 2 = no XOR specialisation
-    int traj_ell = 1;         // width-specialised ELL trajectory kernel for unstructured sparse operators
+    int traj_ell = 1;         // sliced-ELL trajectory kernel (traj_sell.cu) for operators without XOR structure; 0 = the plain ELL kernels
+    int sell_r = 0;           // trajectories per operator read in that kernel (0 = pick)
+    int sell_unit = 2;        // rows permuted in units of 2 neighbours (full 32-byte sectors per store) or 1
     int rk_fuse = 1;          // RK4 stage arithmetic fused into the trajectory matvec
     int xor_fixed = 1;        // fully unrolled transverse-field variant of the XOR kernel
     int xor_rows = 16;        // rows per thread of the XOR kernel at n = 4096

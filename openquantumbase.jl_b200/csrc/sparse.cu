@@ -112,6 +112,7 @@ struct oqb_sparse {
     long long comb_len = 0;
     bool ldl_all_const = false;      // every L_k'L_k is c_k·I (e.g. Pauli jump operators)
     std::vector<double> ldl_const;   // the c_k
+    SellCache* sell = nullptr;       // sliced-ELL plans of the term lists seen so far (traj_sell.cu)
 };
 
 namespace {
@@ -185,6 +186,13 @@ int make_term(oqb_ctx* c, const HostCsc& m, TermDev& out) {
         }
     out.is_diag = 0;
     out.width = width;
+    out.h_cols = ci;
+    out.h_cnt = cnt;
+    out.ell_real = out.ell_imag = true;
+    for (const c128& e : m.val) {
+        if (e.y != 0.0) out.ell_real = false;
+        if (e.x != 0.0) out.ell_imag = false;
+    }
     OQB_CUDA(c, cudaMalloc((void**)&out.vals, v.size() * sizeof(c128)));
     OQB_CUDA(c, cudaMalloc((void**)&out.cols, ci.size() * sizeof(int32_t)));
     OQB_CUDA(c, cudaMemcpy(out.vals, v.data(), v.size() * sizeof(c128), cudaMemcpyHostToDevice));
@@ -722,6 +730,11 @@ int traj_matvec_impl(oqb_sparse* sp, int nb, const double* coefH, int coef_share
         }
         if (rk) return 0;
     }
+    if (c->opt.traj_ell) {
+        bool used = false;  // unstructured operator: sliced ELL with conflict-free slot order, ψ ring, several ψ per operator read
+        OQB_TRY(traj_matvec_sell(c, n, nb, ts, (const c128*)d_stage, shared ? 0 : ncoef, psi, dpsi, &used, &sp->sell));
+        if (used) return 0;
+    }
     {
         bool used = false;  // register-resident operator + bulk-async ψ staging when the term list allows it
         OQB_TRY(traj_matvec_fast(c, n, nb, ts, (const c128*)d_stage, shared ? 0 : ncoef, psi, dpsi, &used));
@@ -771,6 +784,8 @@ int oqb_sparse_destroy(oqb_sparse* sp) {
     for (auto& t : sp->ldl_terms) free_term(t);
     for (auto& t : sp->l_terms) free_term(t);
     free_term(sp->ldl_comb);
+    sell_cache_free(sp->sell);
+    sp->sell = nullptr;
     if (sp->d_ldl_src) cudaFree(sp->d_ldl_src);
     if (sp->d_termvals) cudaFree(sp->d_termvals);
     if (sp->d_u_colptr) cudaFree(sp->d_u_colptr);
@@ -866,6 +881,8 @@ int oqb_sparse_create(oqb_ctx* c, int n, int nterms, const int64_t* h_colptr, co
         HostCsc LU = union_pattern(ls, n);
         for (size_t p = 0; p < LU.val.size(); ++p) LU.val[p] = make_double2(1.0, 0.0);  // structure only
         s = make_term(c, LU, sp->ldl_comb);
+        sp->ldl_comb.dynamic_vals = true;
+        sp->ldl_comb.ell_real = sp->ldl_comb.ell_imag = false;
         if (!s) {
             const int width = sp->ldl_comb.width;
             sp->comb_len = sp->ldl_comb.is_diag ? n : (long long)width * n;
@@ -893,6 +910,12 @@ int oqb_sparse_create(oqb_ctx* c, int n, int nterms, const int64_t* h_colptr, co
     if (s) return fail(s);
     *out = sp;
     return OQB_OK;
+}
+
+int oqb_traj_sell_stats(oqb_sparse* sp, int* plans, double* padding) {
+    if (!sp || !plans || !padding) return OQB_EINVAL;
+    sell_cache_stats(sp->sell, plans, padding);
+    return 0;
 }
 
 int oqb_sparse_pattern_nnz(oqb_sparse* sp, int64_t* nnz) { *nnz = sp->nnzU; return 0; }

@@ -28,6 +28,11 @@ struct TermDev {
     std::vector<c128> xor_vals;
     std::vector<c128> xor_vals1;  // per slot: the value on rows with popcount(r & zmask) odd (xor_vals: even)
     std::vector<int> xor_zmasks;  // per slot: which row bits decide between the two values (0 = one value)
+    // host copy of the ELL structure for the SELL planner (traj_sell.cu): entry j < h_cnt[r] of row r sits at [j*n + r]
+    std::vector<int32_t> h_cols;
+    std::vector<int> h_cnt;
+    bool ell_real = false, ell_imag = false;  // every stored value real / purely imaginary
+    bool dynamic_vals = false;                // values rewritten on the device between calls (−½Σγ_k L_k'L_k)
 };
 
 // dψ_b = Σ_t coef[b][t] · M_t ψ_b with the operator held in registers (see traj_fast.cu).
@@ -53,5 +58,14 @@ struct RkEpilogue {
 // no CTA-wide barrier): traj_xor.cu.
 int traj_matvec_xor(Ctx* c, int n, int nb, const std::vector<const TermDev*>& ts, const c128* d_coef,
                     long long coef_ld, const c128* psi, c128* dpsi, bool* used, const RkEpilogue* rk = nullptr);
+
+// Unstructured operators: sliced-ELL (32-row slices, rows sorted by length, slots ordered so that the 8 threads of a
+// shared-memory phase gather from 8 different bank groups), ψ staged by bulk-async copies, R trajectories per operator
+// read: traj_sell.cu.  `cache` is owned by the caller's oqb_sparse (sell_cache_free releases it).
+struct SellCache;
+int traj_matvec_sell(Ctx* c, int n, int nb, const std::vector<const TermDev*>& ts, const c128* d_coef, long long coef_ld,
+                     const c128* psi, c128* dpsi, bool* used, SellCache** cache);
+void sell_cache_free(SellCache* cache);
+void sell_cache_stats(const SellCache* cache, int* plans, double* padding);  // padding = stored ÷ real entries of the newest plan
 
 }  // namespace oqb
