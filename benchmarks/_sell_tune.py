@@ -28,7 +28,7 @@ for name in sys.argv[1].split(","):
         _, _, Ls = tfim_sparse_c4(nq)
     else:
         Ha, Hb, Ls = tfim_sparse_c4(nq)
-    for opts in [dict(sell_r=2), dict(sell_r=3), dict(sell_r=2, sell_unit=1), dict(sell_r=3, sell_unit=1), dict()]:
+    for opts in [dict(), dict(sell_r=3)]:
         import contextlib
         H = Q.SparseHamiltonian([lambda x: 1 - x, lambda x: x], [Ha, Hb], unit="ħ")
         op = Q.DiffEqLiouvillian(H, [], [Q.LindbladLiouvillian([Q.Lindblad(0.05, L) for L in Ls])], n)

@@ -88,23 +88,24 @@ template <int R, int U, typename VT>
 __device__ __forceinline__ void sell_row(const uint16_t* __restrict__ cp, const VT* __restrict__ vp, unsigned o0, unsigned o1,
                                          const c128* const (&x)[R], double (&ar)[R], double (&ai)[R]) {
     const unsigned lane = threadIdx.x & 31;
-    for (unsigned j = o0; j < o1; j += U) {
+    const uint16_t* __restrict__ cq = cp + (size_t)o0 * 32;  // walking pointers: the U loads of a batch use immediate offsets
+    const VT* __restrict__ vq = vp + (size_t)o0 * 32;
+    for (int left = (int)(o1 - o0); left > 0; left -= U, cq += U * 32, vq += U * 32) {
         unsigned cj[U];
         VT v[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             // past the slice: gather ψ[lane] (conflict-free) with a zero value — no branch anywhere in the batch
-            const bool ok = j + u < o1;
             cj[u] = lane;
             memset(&v[u], 0, sizeof(VT));
-            if (ok) {
-                cj[u] = (unsigned)cp[(size_t)(j + u) * 32];
-                v[u] = vp[(size_t)(j + u) * 32];
+            if (u < left) {
+                cj[u] = (unsigned)cq[u * 32];
+                v[u] = vq[u * 32];
             }
         }
 #pragma unroll
         for (int u0 = 0; u0 < U; u0 += 4) {
-            if (u0 && j + u0 >= o1) break;  // warp-uniform (a slice has one width): whole groups of 4 past the end are skipped
+            if (u0 && u0 >= left) break;  // warp-uniform (a slice has one width): whole groups of 4 past the end are skipped
 #pragma unroll
             for (int u = u0; u < u0 + 4; ++u) {
 #pragma unroll
