@@ -728,13 +728,16 @@ int traj_matvec_impl(oqb_sparse* sp, int nb, const double* coefH, int coef_share
             if (fused) *fused = 1;
             return 0;
         }
-        if (rk) return 0;
     }
     if (c->opt.traj_ell) {
         bool used = false;  // unstructured operator: sliced ELL with conflict-free slot order, ψ ring, several ψ per operator read
-        OQB_TRY(traj_matvec_sell(c, n, nb, ts, (const c128*)d_stage, shared ? 0 : ncoef, psi, dpsi, &used, &sp->sell));
-        if (used) return 0;
+        OQB_TRY(traj_matvec_sell(c, n, nb, ts, (const c128*)d_stage, shared ? 0 : ncoef, psi, dpsi, &used, &sp->sell, rk));
+        if (used) {
+            if (fused) *fused = rk ? 1 : 0;
+            return 0;
+        }
     }
+    if (rk) return 0;
     {
         bool used = false;  // register-resident operator + bulk-async ψ staging when the term list allows it
         OQB_TRY(traj_matvec_fast(c, n, nb, ts, (const c128*)d_stage, shared ? 0 : ncoef, psi, dpsi, &used));

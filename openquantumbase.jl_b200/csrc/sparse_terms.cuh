@@ -64,7 +64,7 @@ int traj_matvec_xor(Ctx* c, int n, int nb, const std::vector<const TermDev*>& ts
 // read: traj_sell.cu.  `cache` is owned by the caller's oqb_sparse (sell_cache_free releases it).
 struct SellCache;
 int traj_matvec_sell(Ctx* c, int n, int nb, const std::vector<const TermDev*>& ts, const c128* d_coef, long long coef_ld,
-                     const c128* psi, c128* dpsi, bool* used, SellCache** cache);
+                     const c128* psi, c128* dpsi, bool* used, SellCache** cache, const RkEpilogue* rk = nullptr);
 void sell_cache_free(SellCache* cache);
 void sell_cache_stats(const SellCache* cache, int* plans, double* padding);  // padding = stored ÷ real entries of the newest plan
 

@@ -154,3 +154,91 @@ def test_default_dispatch_uses_it_for_unstructured_operators(Q):
     s = rng.random(nb)
     got = run(Q, H1, H2, [], psi, s, np.zeros((1, 0)))
     assert relerr(got, reference(H1, H2, [], np.zeros((1, 0)), s, psi)) < TOL
+
+
+def circulant_h(n, rng):
+    """Hermitian band/circulant matrix with random complex values: every row has 6 entries, no Pauli structure — the plan
+    keeps the natural row order (σ = identity), which is when the RK4 stages are fused into the kernel's store."""
+    rows, cols, vals = [], [], []
+    for k in (1, 5, 17):
+        v = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+        rows.append(np.arange(n)); cols.append((np.arange(n) + k) % n); vals.append(v)
+    A = sps.csc_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(n, n))
+    return (A + A.conj().T).tocsc()
+
+
+@pytest.mark.parametrize("n,nb,fuse,kind", [(48, 7, 1, "random"), (200, 5, 1, "random"), (256, 6, 1, "random"), (256, 6, 0, "random"),
+                                            (64, 5, 1, "circulant"), (100, 6, 1, "circulant"), (256, 5, 1, "circulant"), (256, 5, 0, "circulant")])
+def test_evolve_unstructured_hamiltonian_matches_oracle(Q, n, nb, fuse, kind):
+    """oqb_traj_evolve on a SparseHamiltonian without Pauli structure.  With the natural row order kept (circulant) the RK4
+    stage arithmetic rides in the sliced-ELL kernel's store (option rk_fuse = 0: separate stage kernels); with permuted rows
+    (random pattern) the stage kernels stay separate.  Jump steps, operator indices and RNG consumption identical to the
+    oracle's loop, ψ within 1e-12."""
+    from oracle import oqb_oracle as O
+    rng = np.random.default_rng(n + nb)
+    H1 = random_h(n, 4, rng) if kind == "random" else circulant_h(n, rng)
+    H2 = sps.diags(rng.standard_normal(n)).tocsc().astype(complex)
+    Ls = [sps.diags(np.where(rng.random(n) < 0.5, 1.0, -0.5)).tocsc().astype(complex) for _ in range(3)]
+    fa, fb = (lambda s: 1 - s), (lambda s: s)
+    gfs = [(lambda s, k=k: 0.5 * (1 + 0.3 * k + 0.5 * s)) for k in range(3)]
+    Hg, Ho = Q.SparseHamiltonian([fa, fb], [H1, H2], unit="ħ"), O.SparseHamiltonian([fa, fb], [H1, H2], unit="ħ")
+    opg = Q.DiffEqLiouvillian(Hg, [], [Q.LindbladLiouvillian([Q.Lindblad(g, L) for g, L in zip(gfs, Ls)])], n)
+    opo = O.DiffEqLiouvillian(Ho, [], [O.LindbladLiouvillian([O.Lindblad(g, L.toarray()) for g, L in zip(gfs, Ls)])], n)
+    ens = Q.TrajectoryEnsemble(opg)
+    tf, dt, nsteps, seed = 2.0, 0.02, 50, 91
+    pg, po = Q.ODEParams(None, tf), O.ODEParams(None, tf)
+    psi0 = rng.standard_normal((nb, n)) + 1j * rng.standard_normal((nb, n))
+    psi0 /= np.linalg.norm(psi0, axis=1, keepdims=True)
+    pd = Q.DeviceBatch.from_host(psi0)
+    st = Q.TrajectoryStepper(ens, nb, seed=seed, max_log=64)
+    ctx = Q.get_context()
+    with ctx.option("rk_fuse", fuse):
+        st.evolve(pd, pg, 0.0, dt, 20)
+        st.evolve(pd, pg, 20 * dt, dt, nsteps - 20)
+    got = pd.to_host().reshape(nb, n)
+    nj, log, thr = st.njumps.cpu().numpy(), st.log.cpu().numpy(), st.thr.cpu().numpy()
+    Ld = [L.toarray() for L in Ls]
+    total = 0
+    for b in range(nb):
+        r = O.Xoshiro256pp.from_seed(seed, b)
+        thr0 = r.rand()
+        ref, thr_end, lg_ref = O.traj_evolve_rk4(lambda t: opo.update_cache(po, t), lambda t: Ld, lambda t: [g(po(t)) for g in gfs],
+                                                 psi0[b], r, thr0, 0.0, dt, nsteps)
+        assert nj[b] == len(lg_ref)
+        assert [tuple(x) for x in log[b, :nj[b]]] == lg_ref
+        assert thr[b] == thr_end
+        assert relerr(got[b], ref) < 1e-12
+        total += len(lg_ref)
+    assert total > 0
+
+
+@pytest.mark.parametrize("kind", ["circulant", "random"])
+def test_rk4_stage_fusion_follows_the_row_order(Q, kind):
+    """Launch counts of oqb_traj_evolve: with σ = identity the 4 stage kernels and the norm pass of a step disappear into the
+    matvec launches; with permuted rows the option changes nothing."""
+    n, nb, steps = 256, 4, 10
+    rng = np.random.default_rng(3)
+    H1 = random_h(n, 4, rng) if kind == "random" else circulant_h(n, rng)
+    H2 = sps.diags(rng.standard_normal(n)).tocsc().astype(complex)
+    Ls = [sps.diags(np.where(rng.random(n) < 0.5, 1.0, -0.5)).tocsc().astype(complex) for _ in range(2)]
+    H = Q.SparseHamiltonian([lambda s: 1 - s, lambda s: s], [H1, H2], unit="ħ")
+    op = Q.DiffEqLiouvillian(H, [], [Q.LindbladLiouvillian([Q.Lindblad(1e-9, L) for L in Ls])], n)  # no jumps within the run
+    ens = Q.TrajectoryEnsemble(op)
+    ctx = Q.get_context()
+    psi0 = rng.standard_normal((nb, n)) + 1j * rng.standard_normal((nb, n))
+    psi0 /= np.linalg.norm(psi0, axis=1, keepdims=True)
+    counts, outs = {}, {}
+    for fuse in (1, 0):
+        pd = Q.DeviceBatch.from_host(psi0)
+        st = Q.TrajectoryStepper(ens, nb, seed=5)
+        with ctx.option("rk_fuse", fuse):
+            st.evolve(pd, Q.ODEParams(None, 1.0), 0.0, 0.01, 2)
+            l0 = ctx.launch_count()
+            st.evolve(pd, Q.ODEParams(None, 1.0), 0.02, 0.01, steps)
+            counts[fuse] = (ctx.launch_count() - l0) / steps
+        outs[fuse] = pd.to_host()
+    assert relerr(outs[1], outs[0]) < 1e-13
+    if kind == "circulant":
+        assert counts[1] <= counts[0] - 4, counts
+    else:
+        assert abs(counts[1] - counts[0]) <= 1, counts
