@@ -62,8 +62,10 @@ int oqb_launch_count(const oqb_ctx* ctx, uint64_t* n); /* kernels launched throu
  *   "zgemm_3m" (1), "real_operand" (1)        — as oqb_set_zgemm_mode / oqb_set_real_operand_mode below
  *   "zgemm_tma" (1)  0 = cp.async ZGEMM only;  "zgemm_bm" (0) 64/128 force the CTA tile height;  "tma_oneshot" (1)
  *   "lindblad_diag" (1), "coupling_diag" (1)   — treat diagonal L_k / couplings as general dense matrices when 0
- *   "traj_kernel" (0)  0 = pick by operator structure, 1 = generic kernels only, 2 = no XOR specialisation
- *   "traj_ell" (1)     width-specialised ELL kernel for unstructured sparse operators;  "rk_fuse" (1), "xor_fixed" (1), "xor_rows" (16)
+ *   "traj_kernel" (0)  0 = pick by operator structure, 1 = no Pauli/XOR specialisation at all, 2 = no XOR specialisation
+ *   "traj_ell" (1)     operators without Pauli structure take the sliced-ELL kernel (csrc/traj_sell.cu); 0 = the plain ELL kernels
+ *   "sell_r" (0)       trajectories per operator fetch in that kernel (0 = pick: 2);  "sell_unit" (2) rows permuted in pairs or singly
+ *   "rk_fuse" (1), "xor_fixed" (1), "xor_rows" (16)
  *   "ame_host_chunk_mib" (128)                  — chunk size of oqb_ame_rhs_host's H2D/D2H pipeline
  *   "davies_dense_min_pairs" (0 = cost model)   — gap groups with at least this many level pairs use the dense per-group
  *                                                  products instead of the cross-term list;  "davies_max_cross" (5e7) caps the list.
@@ -394,6 +396,13 @@ int oqb_traj_matvec_host(oqb_sparse* sp, int nb, const double* h_coefH, int coef
 /* Diagnostics of the sliced-ELL plans oqb_traj_matvec builds for operators without Pauli structure (csrc/traj_sell.cu):
  *   *plans = plans held by this handle, *padding = stored ÷ real entries of the newest one (1.0 = no padding). */
 int oqb_traj_sell_stats(oqb_sparse* sp, int* plans, double* padding);
+/* The host planner of that kernel run on its own — needs NO GPU and no context.  Input: the off-diagonal terms as 0-based
+ * CSC patterns (colptr[t][n+1], rowval[t][nnz]); unit = 2 (default: rows permuted in pairs) or 1.  Output: *padding as above;
+ * *phases = LDS.128 phases (8 lanes × one slot) of one matvec, *conflicting_phases = those in which two lanes gather from the
+ * same 16-byte bank group (0 by construction); *identity = 1 when the natural row order was kept; *misplaced = entries
+ * lost, duplicated or attached to the wrong row/column (0 for a valid plan). */
+int oqb_sell_plan_probe(int n, int nterms, const int64_t* const* colptr, const int32_t* const* rowval, int unit,
+                        double* padding, int64_t* phases, int64_t* conflicting_phases, int* identity, int* misplaced);
 /* out[b] = ‖ψ[b]‖²  (jump condition of the external callback) */
 int oqb_traj_norm2(oqb_sparse* sp, int nb, const void* d_psi, double* d_out);
 /* lind_jump / lindblad_jump{false,false}: prob[b][k] = γ_k‖L_k ψ[b]‖² (src/opensys/trajectory_jump.jl:2-12),

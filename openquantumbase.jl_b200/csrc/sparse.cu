@@ -915,6 +915,16 @@ int oqb_sparse_create(oqb_ctx* c, int n, int nterms, const int64_t* h_colptr, co
     return OQB_OK;
 }
 
+int oqb_sell_plan_probe(int n, int nterms, const int64_t* const* colptr, const int32_t* const* rowval, int unit, double* padding,
+                        int64_t* phases, int64_t* conflicting_phases, int* identity, int* misplaced) {
+    if (!colptr || !rowval || !padding || !phases || !conflicting_phases || !identity || !misplaced) return OQB_EINVAL;
+    long long ph = 0, cf = 0;
+    const int s = sell_plan_probe(n, nterms, colptr, rowval, unit, padding, &ph, &cf, identity, misplaced);
+    *phases = ph;
+    *conflicting_phases = cf;
+    return s;
+}
+
 int oqb_traj_sell_stats(oqb_sparse* sp, int* plans, double* padding) {
     if (!sp || !plans || !padding) return OQB_EINVAL;
     sell_cache_stats(sp->sell, plans, padding);

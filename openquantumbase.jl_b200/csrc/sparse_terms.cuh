@@ -66,6 +66,8 @@ struct SellCache;
 int traj_matvec_sell(Ctx* c, int n, int nb, const std::vector<const TermDev*>& ts, const c128* d_coef, long long coef_ld,
                      const c128* psi, c128* dpsi, bool* used, SellCache** cache, const RkEpilogue* rk = nullptr);
 void sell_cache_free(SellCache* cache);
-void sell_cache_stats(const SellCache* cache, int* plans, double* padding);  // padding = stored ÷ real entries of the newest plan
+void sell_cache_stats(const SellCache* cache, int* plans, double* padding);
+int sell_plan_probe(int n, int nterms, const int64_t* const* colptr, const int32_t* const* rowval, int unit, double* padding,
+                    long long* phases, long long* conflicting, int* identity, int* misplaced);  // padding = stored ÷ real entries of the newest plan
 
 }  // namespace oqb

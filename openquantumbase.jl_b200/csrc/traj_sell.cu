@@ -19,6 +19,7 @@
 #include <map>
 #include <numeric>
 
+#include "../../include/oqb.h"
 #include "sparse_terms.cuh"
 
 namespace oqb {
@@ -406,35 +407,40 @@ int colour_group(const std::vector<std::pair<int, int>>& edges, std::vector<int>
     return delta;
 }
 
-int build_plan(Ctx* c, int n, const std::vector<const TermDev*>& ts, SellPlan* plan) {
-    plan->key = ts;
-    plan->usable = false;
-    if (n > 8192 || n < 32) return 0;
-    std::vector<int> offs;
-    int ndiag = 0;
-    for (int i = 0; i < (int)ts.size(); ++i) {
-        if (ts[i]->is_diag) ++ndiag;
-        else {
-            if ((int)ts[i]->h_cnt.size() != n) return 0;
-            offs.push_back(i);
-        }
-    }
-    if (offs.empty() || (int)offs.size() > kSellOff || ndiag > kSellDiag) return 0;
+// ---- host planner (no CUDA calls: oqb_sell_plan_probe runs it without a GPU) ---------------------------------------------
+struct EllPattern {  // one off-diagonal term: entry j < cnt[r] of row r has column cols[j*n + r]
+    const int32_t* cols;
+    const int* cnt;
+};
+struct HostTermPlan {
+    std::vector<uint32_t> off;   // [nslices + 1]
+    std::vector<uint16_t> cols;  // [off.back() * 32] (padded entries: a filler column of an unused bank group)
+    std::vector<int32_t> src;    // ELL index j*n + r of the entry, −1 = padding
+};
+struct HostPlan {
+    int npos = 0;
+    std::vector<uint16_t> sigma;
+    std::vector<HostTermPlan> terms;
+    long long real_entries = 0, stored_entries = 0;
+    bool identity = true;
+};
+
+void plan_host(int n, const std::vector<EllPattern>& pats, int unit, HostPlan& hp) {
     const int npos = (n + 31) / 32 * 32;
-    // rows by total length, longest first (stable: equal lengths keep their order, so regular operators stay unpermuted)
+    hp.npos = npos;
+    // rows by total length; the term with most entries decides the bank balance of the groups
     std::vector<int> deg(n, 0);
-    int primary = offs[0];
+    size_t primary = 0;
     long long best_nnz = -1;
-    for (int i : offs) {
+    for (size_t i = 0; i < pats.size(); ++i) {
         long long nnz = 0;
-        for (int r = 0; r < n; ++r) { deg[r] += ts[i]->h_cnt[r]; nnz += ts[i]->h_cnt[r]; }
+        for (int r = 0; r < n; ++r) { deg[r] += pats[i].cnt[r]; nnz += pats[i].cnt[r]; }
         if (nnz > best_nnz) { best_nnz = nnz; primary = i; }
     }
-    // Rows travel in units of kUnit = 2 neighbours (2k, 2k+1): their 16-byte results share a 32-byte sector, and a sector
+    // Rows travel in units of 2 neighbours (2k, 2k+1): their 16-byte results share a 32-byte sector, and a sector
     // written half by one warp and half by another costs a fill read and a second write in L2/HBM (measured: 12.5 GB of
     // DRAM traffic per launch instead of 8.6 GB with single-row units).  Units by length, longest first (stable: equal
     // lengths keep their order, so regular operators stay unpermuted); a trailing single row (odd n) goes last.
-    const int unit = c->opt.sell_unit >= 2 ? 2 : 1;
     const int nunits = (n + unit - 1) / unit;
     std::vector<int> udeg(nunits, 0);
     for (int u = 0; u < nunits; ++u)
@@ -445,14 +451,15 @@ int build_plan(Ctx* c, int n, const std::vector<const TermDev*>& ts, SellPlan* p
     std::stable_sort(sorted.begin(), sorted.end(), [&](int a, int b) { return udeg[a] > udeg[b]; });
     // 8-row groups: first unused unit, then more out of a window of similar units, each minimising the largest bank-group
     // degree of the group (ties: the earliest unit)
-    const TermDev& P = *ts[primary];
-    std::vector<uint16_t> sigma(npos, kPad);
+    const EllPattern& P = pats[primary];
+    std::vector<uint16_t>& sigma = hp.sigma;
+    sigma.assign(npos, kPad);
     std::vector<char> used(nunits, 0);
     constexpr int kWindow = 64;
     int head = 0, pos = 0;
     auto add_unit = [&](int u, int* bk) {
         for (int r = u * unit; r < std::min(n, (u + 1) * unit); ++r)
-            for (int j = 0; j < P.h_cnt[r]; ++j) bk[P.h_cols[(size_t)j * n + r] & 7]++;
+            for (int j = 0; j < P.cnt[r]; ++j) bk[P.cols[(size_t)j * n + r] & 7]++;
     };
     auto place = [&](int u) {
         used[u] = 1;
@@ -483,84 +490,109 @@ int build_plan(Ctx* c, int n, const std::vector<const TermDev*>& ts, SellPlan* p
             add_unit(best, bank);
         }
     }
+    for (int p = 0; p < n; ++p) hp.identity = hp.identity && sigma[p] == p;
     // per term: colour every 8-row group, slice widths = max over the 4 groups of a slice
-    const int nslices = npos / 32;
-    long long real_entries = 0, stored_entries = 0;
-    for (int ti : offs) {
-        const TermDev& T = *ts[ti];
-        SellOffPlan op;
-        op.term = &T;
-        op.list_idx = ti;
-        op.real = T.ell_real && !T.dynamic_vals;
-        op.imag = T.ell_imag && !T.dynamic_vals && !op.real;
-        std::vector<uint32_t> off(nslices + 1, 0);
-        std::vector<std::vector<int>> gcol(npos / 8);
-        std::vector<int> gdelta(npos / 8, 0);
-        std::vector<std::vector<std::pair<int, int>>> gedges(npos / 8);
-        std::vector<std::vector<std::pair<int, int32_t>>> gent(npos / 8);  // (col, ELL index) per edge
-        for (int g = 0; g < npos / 8; ++g) {
+    const int nslices = npos / 32, ngroups = npos / 8;
+    for (const EllPattern& T : pats) {
+        HostTermPlan tp;
+        tp.off.assign(nslices + 1, 0);
+        std::vector<std::vector<int>> gcol(ngroups);
+        std::vector<int> gdelta(ngroups, 0);
+        std::vector<std::vector<std::pair<int, int>>> gedges(ngroups);
+        std::vector<std::vector<std::pair<int, int32_t>>> gent(ngroups);  // (col, ELL index) per edge
+        for (int g = 0; g < ngroups; ++g) {
             for (int i = 0; i < 8; ++i) {
                 const unsigned r = sigma[g * 8 + i];
                 if (r == kPad) continue;
-                for (int j = 0; j < T.h_cnt[r]; ++j) {
-                    const int col = T.h_cols[(size_t)j * n + r];
+                for (int j = 0; j < T.cnt[r]; ++j) {
+                    const int col = T.cols[(size_t)j * n + r];
                     gedges[g].push_back({i, col & 7});
                     gent[g].push_back({col, (int32_t)((size_t)j * n + r)});
                 }
             }
             gdelta[g] = colour_group(gedges[g], gcol[g]);
-            real_entries += (long long)gedges[g].size();
+            hp.real_entries += (long long)gedges[g].size();
         }
         for (int s = 0; s < nslices; ++s) {
             int w = 0;
             for (int q = 0; q < 4; ++q) w = std::max(w, gdelta[s * 4 + q]);
-            off[s + 1] = off[s] + (uint32_t)w;
+            tp.off[s + 1] = tp.off[s] + (uint32_t)w;
         }
-        op.len = (long long)off[nslices] * 32;
-        stored_entries += op.len;
-        std::vector<uint16_t> cols((size_t)std::max<long long>(op.len, 1), kPad);
-        std::vector<int32_t> src((size_t)std::max<long long>(op.len, 1), -1);
-        for (int g = 0; g < npos / 8; ++g) {
+        const long long len = (long long)tp.off[nslices] * 32;
+        hp.stored_entries += len;
+        tp.cols.assign((size_t)std::max<long long>(len, 1), kPad);
+        tp.src.assign((size_t)std::max<long long>(len, 1), -1);
+        for (int g = 0; g < ngroups; ++g) {
             const int s = g / 4, lane0 = (g % 4) * 8;
             for (size_t e = 0; e < gedges[g].size(); ++e) {
-                const size_t at = ((size_t)off[s] + gcol[g][e]) * 32 + lane0 + gedges[g][e].first;
-                cols[at] = (uint16_t)gent[g][e].first;
-                src[at] = gent[g][e].second;
+                const size_t at = ((size_t)tp.off[s] + gcol[g][e]) * 32 + lane0 + gedges[g][e].first;
+                tp.cols[at] = (uint16_t)gent[g][e].first;
+                tp.src[at] = gent[g][e].second;
             }
             // padded entries carry the value 0 and gather ψ[b] for a bank group b that no real entry of the phase uses
-            for (uint32_t j = off[s]; j < off[s + 1]; ++j) {
+            for (uint32_t j = tp.off[s]; j < tp.off[s + 1]; ++j) {
                 bool taken[8] = {false};
                 for (int i = 0; i < 8; ++i) {
                     const size_t at = (size_t)j * 32 + lane0 + i;
-                    if (cols[at] != kPad) taken[cols[at] & 7] = true;
+                    if (tp.cols[at] != kPad) taken[tp.cols[at] & 7] = true;
                 }
                 int b = 0;
                 for (int i = 0; i < 8; ++i) {
                     const size_t at = (size_t)j * 32 + lane0 + i;
-                    if (cols[at] != kPad) continue;
+                    if (tp.cols[at] != kPad) continue;
                     while (taken[b]) ++b;
                     taken[b] = true;
-                    cols[at] = (uint16_t)b;
+                    tp.cols[at] = (uint16_t)b;
                 }
             }
         }
-        OQB_CUDA(c, cudaMalloc((void**)&op.d_off, off.size() * sizeof(uint32_t)));
-        OQB_CUDA(c, cudaMalloc((void**)&op.d_cols, cols.size() * sizeof(uint16_t)));
-        OQB_CUDA(c, cudaMalloc((void**)&op.d_src, src.size() * sizeof(int32_t)));
-        if (op.real || op.imag) OQB_CUDA(c, cudaMalloc((void**)&op.d_rvals, cols.size() * sizeof(double)));
-        else OQB_CUDA(c, cudaMalloc((void**)&op.d_vals, cols.size() * sizeof(c128)));
-        OQB_CUDA(c, cudaMemcpyAsync(op.d_off, off.data(), off.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
-        OQB_CUDA(c, cudaMemcpyAsync(op.d_cols, cols.data(), cols.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, c->stream));
-        OQB_CUDA(c, cudaMemcpyAsync(op.d_src, src.data(), src.size() * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
-        OQB_CUDA(c, cudaStreamSynchronize(c->stream));  // the host vectors die with this scope
+        hp.terms.push_back(std::move(tp));
+    }
+}
+
+int build_plan(Ctx* c, int n, const std::vector<const TermDev*>& ts, SellPlan* plan) {
+    plan->key = ts;
+    plan->usable = false;
+    if (n > 8192 || n < 32) return 0;
+    std::vector<int> offs;
+    std::vector<EllPattern> pats;
+    int ndiag = 0;
+    for (int i = 0; i < (int)ts.size(); ++i) {
+        if (ts[i]->is_diag) ++ndiag;
+        else {
+            if ((int)ts[i]->h_cnt.size() != n) return 0;
+            offs.push_back(i);
+            pats.push_back({ts[i]->h_cols.data(), ts[i]->h_cnt.data()});
+        }
+    }
+    if (offs.empty() || (int)offs.size() > kSellOff || ndiag > kSellDiag) return 0;
+    HostPlan hp;
+    plan_host(n, pats, c->opt.sell_unit >= 2 ? 2 : 1, hp);
+    for (size_t k = 0; k < offs.size(); ++k) {
+        const TermDev& T = *ts[offs[k]];
+        const HostTermPlan& tp = hp.terms[k];
+        SellOffPlan op;
+        op.term = &T;
+        op.list_idx = offs[k];
+        op.real = T.ell_real && !T.dynamic_vals;
+        op.imag = T.ell_imag && !T.dynamic_vals && !op.real;
+        op.len = (long long)tp.off.back() * 32;
+        OQB_CUDA(c, cudaMalloc((void**)&op.d_off, tp.off.size() * sizeof(uint32_t)));
+        OQB_CUDA(c, cudaMalloc((void**)&op.d_cols, tp.cols.size() * sizeof(uint16_t)));
+        OQB_CUDA(c, cudaMalloc((void**)&op.d_src, tp.src.size() * sizeof(int32_t)));
+        if (op.real || op.imag) OQB_CUDA(c, cudaMalloc((void**)&op.d_rvals, tp.cols.size() * sizeof(double)));
+        else OQB_CUDA(c, cudaMalloc((void**)&op.d_vals, tp.cols.size() * sizeof(c128)));
+        OQB_CUDA(c, cudaMemcpyAsync(op.d_off, tp.off.data(), tp.off.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+        OQB_CUDA(c, cudaMemcpyAsync(op.d_cols, tp.cols.data(), tp.cols.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, c->stream));
+        OQB_CUDA(c, cudaMemcpyAsync(op.d_src, tp.src.data(), tp.src.size() * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
         plan->off.push_back(op);
     }
-    OQB_CUDA(c, cudaMalloc((void**)&plan->d_sigma, sigma.size() * sizeof(uint16_t)));
-    OQB_CUDA(c, cudaMemcpyAsync(plan->d_sigma, sigma.data(), sigma.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, c->stream));
-    OQB_CUDA(c, cudaStreamSynchronize(c->stream));
-    plan->npos = npos;
-    for (int p = 0; p < n; ++p) plan->identity = plan->identity && sigma[p] == p;
-    plan->padding = real_entries ? (double)stored_entries / (double)real_entries : 1.0;
+    OQB_CUDA(c, cudaMalloc((void**)&plan->d_sigma, hp.sigma.size() * sizeof(uint16_t)));
+    OQB_CUDA(c, cudaMemcpyAsync(plan->d_sigma, hp.sigma.data(), hp.sigma.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, c->stream));
+    OQB_CUDA(c, cudaStreamSynchronize(c->stream));  // the host vectors die with this scope
+    plan->npos = hp.npos;
+    plan->identity = hp.identity;
+    plan->padding = hp.real_entries ? (double)hp.stored_entries / (double)hp.real_entries : 1.0;
     plan->usable = true;
     return 0;
 }
@@ -621,6 +653,75 @@ int launch_r(Ctx* c, int R, int n, int ns, int nb, const SellDesc& d, const c128
 }
 
 }  // namespace
+
+// Host-only check of the planner (no GPU): see oqb_sell_plan_probe in include/oqb.h
+int sell_plan_probe(int n, int nterms, const int64_t* const* colptr, const int32_t* const* rowval, int unit, double* padding,
+                    long long* phases, long long* conflicting, int* identity, int* misplaced) {
+    if (n < 32 || n > 8192 || nterms <= 0 || nterms > kSellOff) return OQB_EINVAL;
+    std::vector<std::vector<int32_t>> cols(nterms);
+    std::vector<std::vector<int>> cnt(nterms);
+    std::vector<EllPattern> pats;
+    for (int t = 0; t < nterms; ++t) {
+        cnt[t].assign(n, 0);
+        for (int j = 0; j < n; ++j)
+            for (int64_t p = colptr[t][j]; p < colptr[t][j + 1]; ++p) {
+                if (rowval[t][p] < 0 || rowval[t][p] >= n) return OQB_EINVAL;
+                cnt[t][rowval[t][p]]++;
+            }
+        int width = 0;
+        for (int r = 0; r < n; ++r) width = std::max(width, cnt[t][r]);
+        cols[t].assign((size_t)std::max(width, 1) * n, 0);
+        std::vector<int> fill(n, 0);
+        for (int j = 0; j < n; ++j)
+            for (int64_t p = colptr[t][j]; p < colptr[t][j + 1]; ++p) {
+                const int r = rowval[t][p];
+                cols[t][(size_t)(fill[r]++) * n + r] = j;
+            }
+        pats.push_back({cols[t].data(), cnt[t].data()});
+    }
+    HostPlan hp;
+    plan_host(n, pats, unit >= 2 ? 2 : 1, hp);
+    *padding = hp.real_entries ? (double)hp.stored_entries / (double)hp.real_entries : 1.0;
+    *identity = hp.identity ? 1 : 0;
+    *phases = *conflicting = 0;
+    *misplaced = 0;
+    // σ is a permutation of the rows
+    std::vector<int> seen_row(n, 0);
+    for (int p = 0; p < hp.npos; ++p)
+        if (hp.sigma[p] != kPad) {
+            if (hp.sigma[p] >= n || seen_row[hp.sigma[p]]++) ++*misplaced;
+        }
+    for (int r = 0; r < n; ++r)
+        if (!seen_row[r]) ++*misplaced;
+    for (int t = 0; t < nterms; ++t) {
+        const HostTermPlan& tp = hp.terms[t];
+        std::vector<char> hit((size_t)cols[t].size(), 0);
+        const int nslices = hp.npos / 32;
+        for (int s = 0; s < nslices; ++s)
+            for (uint32_t j = tp.off[s]; j < tp.off[s + 1]; ++j)
+                for (int q = 0; q < 4; ++q) {  // one LDS.128 phase = 8 consecutive lanes
+                    int banks[8] = {0};
+                    bool clash = false;
+                    for (int i = 0; i < 8; ++i) {
+                        const size_t at = (size_t)j * 32 + q * 8 + i;
+                        const int32_t e = tp.src[at];
+                        if (++banks[tp.cols[at] & 7] > 1) clash = true;  // fillers count: they are gathered too
+                        if (e < 0) continue;
+                        const unsigned r = hp.sigma[s * 32 + q * 8 + i];
+                        // the entry must belong to the row this lane computes and carry that entry's column
+                        if (r == kPad || (size_t)e >= hit.size() || e % n != (int)r || e / n >= cnt[t][r] || hit[e]++ ||
+                            cols[t][e] != tp.cols[at])
+                            ++*misplaced;
+                    }
+                    ++*phases;
+                    if (clash) ++*conflicting;
+                }
+        for (int r = 0; r < n; ++r)
+            for (int j = 0; j < cnt[t][r]; ++j)
+                if (!hit[(size_t)j * n + r]) ++*misplaced;  // an entry the plan lost
+    }
+    return 0;
+}
 
 void sell_cache_free(SellCache* cache) {
     if (!cache) return;
