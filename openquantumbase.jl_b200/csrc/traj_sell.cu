@@ -455,7 +455,7 @@ void plan_host(int n, const std::vector<EllPattern>& pats, int unit, HostPlan& h
     std::vector<uint16_t>& sigma = hp.sigma;
     sigma.assign(npos, kPad);
     std::vector<char> used(nunits, 0);
-    constexpr int kWindow = 64;
+    constexpr int kWindow = 1024;  // candidates per pick: 64 → 1024 takes the random-pattern padding from 1.23 to 1.18
     int head = 0, pos = 0;
     auto add_unit = [&](int u, int* bk) {
         for (int r = u * unit; r < std::min(n, (u + 1) * unit); ++r)
