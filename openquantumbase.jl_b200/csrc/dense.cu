@@ -108,6 +108,47 @@ __global__ void lindblad_diag_sandwich_kernel(int n, int K, const c128* __restri
     }
 }
 
+// Shared rates: G[a,c] = Σ_k γ_k d_k[a] conj(d_k[c]) (− ½γ_k(|d_k[a]|² + |d_k[c]|²) with_anti) once per call; the sandwich
+// Σ_k γ_k L_k u L_k' = G∘u is then a pure streaming pass (hadamard_acc_kernel: G stays in L2, no K-loop per element).
+// Folding G∘u into the epilogue of the second commutator product instead was measured SLOWER (25.1 vs 22.8 ms per C2 step):
+// two more operand arrays in the epilogue push every zgemm_tma variant into register spills.
+__global__ void lindblad_diag_gmat_kernel(int n, int K, const c128* __restrict__ ldiag, const double* __restrict__ gamma, int with_anti,
+                                          c128* __restrict__ G) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (long long)n * n) return;
+    const int a = (int)(e % n), cc = (int)(e / n);
+    double gr = 0.0, gi = 0.0;
+    for (int k = 0; k < K; ++k) {  // same operation order as lindblad_diag_sandwich_kernel
+        const c128 da = ldiag[(size_t)k * n + a], dc = ldiag[(size_t)k * n + cc];
+        const double g = gamma[k];
+        gr = fma(g, da.x * dc.x + da.y * dc.y, gr);
+        gi = fma(g, da.y * dc.x - da.x * dc.y, gi);
+        if (with_anti) gr = fma(-0.5 * g, (da.x * da.x + da.y * da.y) + (dc.x * dc.x + dc.y * dc.y), gr);
+    }
+    G[e] = make_double2(gr, gi);
+}
+
+// du[b] += G ∘ u[b]  (G shared by the batch): 2 elements per thread, grid (tiles, members)
+__global__ void hadamard_acc_kernel(long long nn, const c128* __restrict__ G, const c128* __restrict__ u, c128* __restrict__ du) {
+    const long long b = blockIdx.y;
+    const c128* ub = u + b * nn;
+    c128* dub = du + b * nn;
+    for (long long e = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 2; e < nn; e += (long long)gridDim.x * blockDim.x * 2) {
+        if (e + 1 < nn) {
+            const c128 g0 = G[e], g1 = G[e + 1], x0 = ub[e], x1 = ub[e + 1];
+            c128 o0 = dub[e], o1 = dub[e + 1];
+            o0.x += g0.x * x0.x - g0.y * x0.y; o0.y += g0.x * x0.y + g0.y * x0.x;
+            o1.x += g1.x * x1.x - g1.y * x1.y; o1.y += g1.x * x1.y + g1.y * x1.x;
+            dub[e] = o0; dub[e + 1] = o1;
+        } else {
+            const c128 g0 = G[e], x0 = ub[e];
+            c128 o0 = dub[e];
+            o0.x += g0.x * x0.x - g0.y * x0.y; o0.y += g0.x * x0.y + g0.y * x0.x;
+            dub[e] = o0;
+        }
+    }
+}
+
 // He[b][a,a] += Σ_k coef[b][k]·|d_k[a]|²  — the L_k'L_k part of H_eff for diagonal L_k (coef already carries −(i/2)γ_bk or −½γ_bk)
 __global__ void heff_diag_add_kernel(int n, int K, const c128* __restrict__ ldiag, const c128* __restrict__ coef, long long coef_ld,
                                      c128* __restrict__ He, long long strideHe) {
@@ -139,6 +180,11 @@ int dense_rhs_impl(oqb_dense* op, int nb, const double* coefH, int coef_shared, 
     const long long n = op->n, nn = n * n;
     const int K = (gamma && op->K > 0) ? op->K : 0;
     if (!with_h && K == 0) return 0;
+    if (K && !gamma_shared) {  // constant rates handed over per member (per-member s): one row serves everybody
+        bool same = true;
+        for (int b = 1; b < nb && same; ++b) same = memcmp(gamma, gamma + (size_t)b * K, (size_t)K * sizeof(double)) == 0;
+        if (same) gamma_shared = 1;
+    }
 
     // He_b = H(s_b) − (i/2) Σ γ_bk L_k'L_k    (or G_b = −½ Σ γ L'L for the accumulate form)
     std::vector<c128> coef;
@@ -169,9 +215,12 @@ int dense_rhs_impl(oqb_dense* op, int nb, const double* coefH, int coef_shared, 
     if (chunk > nb) chunk = nb;
     chunk = (nb + (nb + chunk - 1) / chunk - 1) / ((nb + chunk - 1) / chunk);  // balance the chunks
     const size_t he_elems = (size_t)(rows == 1 ? 1 : chunk) * nn;
-    OQB_TRY(ws_reserve(c, (he_elems + (size_t)chunk * Kws * nn) * sizeof(c128)));
+    // shared rates + diagonal L_k: the sandwich is one n×n Hadamard factor for every member, folded into the second product
+    const bool fuse_sandwich = use_diag && gamma_shared && c->opt.lindblad_fuse;
+    OQB_TRY(ws_reserve(c, (he_elems + (size_t)chunk * Kws * nn + (fuse_sandwich ? nn : 0)) * sizeof(c128)));
     c128* He = (c128*)c->ws;
     c128* T = He + he_elems;
+    c128* Gmat = T + (size_t)chunk * Kws * nn;
 
     // diagonal L_k: L_k'L_k = diag|d_k|² — assemble H_eff from the Hamiltonian terms only and add the diagonal afterwards
     // (the per-member lincomb then reads nterms matrices instead of nterms + K)
@@ -194,6 +243,11 @@ int dense_rhs_impl(oqb_dense* op, int nb, const double* coefH, int coef_shared, 
         return 0;
     };
     if (rows == 1) OQB_TRY(assemble((const c128*)d_coef, 0, 1));
+    if (fuse_sandwich) {
+        lindblad_diag_gmat_kernel<<<(unsigned)((nn + 255) / 256), 256, 0, c->stream>>>((int)n, K, op->d_ldiag, (const double*)d_gamma,
+                                                                                       real_h ? 1 : 0, Gmat);
+        OQB_LAUNCH_CHECK(c);
+    }
     for (int b0 = 0; b0 < nb; b0 += chunk) {
         const int cnt = nb - b0 < chunk ? nb - b0 : chunk;
         const c128* ub = u + (long long)b0 * nn;
@@ -217,7 +271,14 @@ int dense_rhs_impl(oqb_dense* op, int nb, const double* coefH, int coef_shared, 
         q.alpha = with_h ? make_double2(0.0, 1.0) : make_double2(1.0, 0.0);
         q.beta = make_double2(1.0, 0.0);
         OQB_TRY(zgemm(c, q));
-        if (K) {
+        if (fuse_sandwich) {
+            for (int m0 = 0; m0 < cnt; m0 += 65535) {
+                const int mc = cnt - m0 < 65535 ? cnt - m0 : 65535;
+                dim3 grid((unsigned)std::min<long long>((nn / 2 + 255) / 256, 64), mc);
+                hadamard_acc_kernel<<<grid, 256, 0, c->stream>>>(nn, Gmat, ub + (long long)m0 * nn, dub + (long long)m0 * nn);
+                OQB_LAUNCH_CHECK(c);
+            }
+        } else if (K) {
             const double* dg = (const double*)d_gamma + (gamma_shared ? 0 : (long long)b0 * K);
             const size_t sm = diag_sm;
             if (use_diag) {

@@ -1,0 +1,89 @@
+"""Diagonal Lindblad operators with rates shared by the batch (config C2: per-qubit dephasing, per-member s): the sandwich
+Σ_k γ_k L_k ρ L_k' = G∘ρ uses ONE n×n factor G for the whole batch (built once per call) and a pure streaming pass, instead of a
+K-term sum per element and member.  Against the oracle's literal `γ(LρL' − ½{L'L, ρ})` loop (src/opensys/lindblad.jl:94-101) at 1e-12, and against the
+unfused route (option lindblad_fuse = 0)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from oracle import oqb_oracle as O  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+
+@pytest.fixture(scope="module")
+def Q():
+    import oqb_b200
+    return oqb_b200
+
+
+def relerr(a, b):
+    return float(np.linalg.norm(np.asarray(a) - np.asarray(b)) / max(np.linalg.norm(np.asarray(b)), 1e-300))
+
+
+def rand_c(rng, *shape):
+    return rng.standard_normal(shape) + 1j * rng.standard_normal(shape)
+
+
+@pytest.mark.parametrize("n,K,nb", [(8, 3, 5), (50, 4, 7), (64, 8, 6), (100, 2, 3), (256, 8, 9)])
+@pytest.mark.parametrize("real_h", [True, False])
+@pytest.mark.parametrize("per_member_s", [True, False])
+def test_fused_sandwich_vs_oracle(Q, n, K, nb, real_h, per_member_s):
+    rng = np.random.default_rng(n * 13 + K + nb + 2 * real_h + per_member_s)
+    mk = (lambda: (lambda g: g + g.T)(rng.standard_normal((n, n))).astype(complex)) if real_h else (lambda: (lambda g: g + g.conj().T)(rand_c(rng, n, n)))
+    m1, m2 = mk(), mk()
+    fs = [lambda s: -(1 - s), lambda s: s]
+    Ls = [np.diag(np.exp(1j * rng.uniform(0, 2 * np.pi, n)) * rng.uniform(0.5, 1.5, n)) for _ in range(K)]  # complex diagonals
+    gam = [0.1 * (1 + k / 8) for k in range(K)]  # constant rates: shared by the batch whatever s is
+    Hg, Ho = Q.DenseHamiltonian(fs, [m1, m2], unit="ħ"), O.DenseHamiltonian(fs, [m1, m2], unit="ħ")
+    opg = Q.DiffEqLiouvillian(Hg, [], [Q.LindbladLiouvillian([Q.Lindblad(g, L) for g, L in zip(gam, Ls)])], n)
+    opo = O.DiffEqLiouvillian(Ho, [], [O.LindbladLiouvillian([O.Lindblad(g, L) for g, L in zip(gam, Ls)])], n)
+    u = rand_c(rng, nb, n, n)  # NOT Hermitian: the reference assumes nothing
+    tf = 10.0
+    t = rng.random(nb) * tf if per_member_s else 3.7
+    tl = t if per_member_s else [t] * nb
+    ctx = Q.get_context()
+    ref = np.stack([opo.rhs(u[b], O.ODEParams(None, tf), tl[b]) for b in range(nb)])
+    fused = opg(np.zeros_like(u), u, Q.ODEParams(None, tf), t)
+    with ctx.option("lindblad_fuse", 0):
+        plain = opg(np.zeros_like(u), u, Q.ODEParams(None, tf), t)
+    assert relerr(fused, ref) < TOL and relerr(plain, ref) < TOL
+    assert relerr(fused, plain) < 1e-13
+
+
+def test_per_member_rates_keep_the_separate_pass(Q):
+    """γ_k(s) with per-member s: G differs per member, the Hadamard pass stays (and stays correct)."""
+    n, K, nb = 64, 3, 6
+    rng = np.random.default_rng(9)
+    m1, m2 = [(lambda g: g + g.T)(rng.standard_normal((n, n))).astype(complex) for _ in range(2)]
+    fs = [lambda s: -(1 - s), lambda s: s]
+    Ls = [np.diag(rng.choice([-1.0, 1.0], n)).astype(complex) for _ in range(K)]
+    gfs = [lambda s, k=k: 0.1 * (1 + k) * (1 + s) for k in range(K)]
+    opg = Q.DiffEqLiouvillian(Q.DenseHamiltonian(fs, [m1, m2], unit="ħ"), [], [Q.LindbladLiouvillian([Q.Lindblad(g, L) for g, L in zip(gfs, Ls)])], n)
+    opo = O.DiffEqLiouvillian(O.DenseHamiltonian(fs, [m1, m2], unit="ħ"), [], [O.LindbladLiouvillian([O.Lindblad(g, L) for g, L in zip(gfs, Ls)])], n)
+    u = rand_c(rng, nb, n, n)
+    t = rng.random(nb) * 10.0
+    got = opg(np.zeros_like(u), u, Q.ODEParams(None, 10.0), t)
+    ref = np.stack([opo.rhs(u[b], O.ODEParams(None, 10.0), t[b]) for b in range(nb)])
+    assert relerr(got, ref) < TOL
+
+
+def test_shared_factor_with_the_fallback_product(Q):
+    """The same route with the cp.async fallback product (option zgemm_tma = 0)."""
+    n, K, nb = 40, 2, 4
+    rng = np.random.default_rng(10)
+    m1, m2 = [(lambda g: g + g.conj().T)(rand_c(rng, n, n)) for _ in range(2)]
+    fs = [lambda s: -(1 - s), lambda s: s]
+    Ls = [np.diag(rand_c(rng, n)) for _ in range(K)]
+    opg = Q.DiffEqLiouvillian(Q.DenseHamiltonian(fs, [m1, m2], unit="ħ"), [], [Q.LindbladLiouvillian([Q.Lindblad(0.3, L) for L in Ls])], n)
+    opo = O.DiffEqLiouvillian(O.DenseHamiltonian(fs, [m1, m2], unit="ħ"), [], [O.LindbladLiouvillian([O.Lindblad(0.3, L) for L in Ls])], n)
+    u = rand_c(rng, nb, n, n)
+    ctx = Q.get_context()
+    with ctx.option("zgemm_tma", 0):
+        got = opg(np.zeros_like(u), u, Q.ODEParams(None, 10.0), 4.0)
+    ref = np.stack([opo.rhs(u[b], O.ODEParams(None, 10.0), 4.0) for b in range(nb)])
+    assert relerr(got, ref) < TOL
