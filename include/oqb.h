@@ -63,6 +63,7 @@ int oqb_launch_count(const oqb_ctx* ctx, uint64_t* n); /* kernels launched throu
  *   "zgemm_tma" (1)  0 = cp.async ZGEMM only;  "zgemm_bm" (0) 64/128 force the CTA tile height;  "tma_oneshot" (1)
  *   "lindblad_diag" (1), "coupling_diag" (1)   — treat diagonal L_k / couplings as general dense matrices when 0
  *   "lindblad_fuse" (1)  diagonal L_k with rates shared by the batch: one n×n factor G per call and du += G∘u as a streaming pass
+ *   "lindblad_split" (1) … and one off-diagonal Hamiltonian term: shared-operand products scaled by f_N(s_b), diagonal terms in that pass
  *   "traj_kernel" (0)  0 = pick by operator structure, 1 = no Pauli/XOR specialisation at all, 2 = no XOR specialisation
  *   "traj_ell" (1)     operators without Pauli structure take the sliced-ELL kernel (csrc/traj_sell.cu); 0 = the plain ELL kernels
  *   "sell_r" (0)       trajectories per operator fetch in that kernel (0 = pick: 2);  "sell_unit" (2) rows permuted in pairs or singly

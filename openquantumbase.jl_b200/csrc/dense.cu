@@ -19,6 +19,10 @@ struct oqb_dense {
     c128* d_ldiag = nullptr; // K × n diagonals when EVERY L_k is diagonal (dephasing Z_k, …), else nullptr
     bool lops_real = false;   // every L_k has zero imaginary part (σx, σ±, σz, …): both sandwich products are real-operand products
     bool terms_real = false;  // every Hamiltonian term matrix has zero imaginary part: H(s)ρ and ρH(s) take the real-operand product
+    // split form of H(s) = f_N(s)·m_N + Σ_{i diagonal} f_i(s)·diag(h_i): exactly one term has off-diagonal entries
+    int offdiag_term = -1;       // its index, −1 when the split does not apply
+    bool offdiag_real = false;   // … and it has no imaginary part
+    c128* d_hdiag = nullptr;     // nterms × n: the diagonals h_i (zero row for m_N)
 };
 
 namespace {
@@ -149,6 +153,39 @@ __global__ void hadamard_acc_kernel(long long nn, const c128* __restrict__ G, co
     }
 }
 
+// du[b][a,c] += (G[a,c] − i Σ_i f_bi (h_i[a] − h_i[c])) · u[b][a,c]: the shared Lindblad factor plus the commutator with the
+// DIAGONAL Hamiltonian terms (−i(Hu − uH) for H = diag h is −i(h_a − h_c)u_ac, src/hamiltonian/dense_hamiltonian.jl:84-89);
+// coef row b holds (f_bi, 0); the nt diagonals sit in shared memory (zero row for the off-diagonal term).
+__global__ void hadamard_acc_split_kernel(int n, int nt, const c128* __restrict__ G, const c128* __restrict__ hdiag,
+                                          const c128* __restrict__ coef, long long coef_ld, const c128* __restrict__ u,
+                                          c128* __restrict__ du) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    c128* sh = reinterpret_cast<c128*>(smem_raw);  // nt × n
+    double* sf = reinterpret_cast<double*>(sh + (size_t)nt * n);
+    const long long b = blockIdx.y, nn = (long long)n * n;
+    for (int e = threadIdx.x; e < nt * n; e += blockDim.x) sh[e] = hdiag[e];
+    if (threadIdx.x < nt) sf[threadIdx.x] = coef[b * coef_ld + threadIdx.x].x;
+    __syncthreads();
+    const c128* ub = u + b * nn;
+    c128* dub = du + b * nn;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < nn; e += (long long)gridDim.x * blockDim.x) {
+        const int a = (int)(e % n), cc = (int)(e / n);
+        c128 g = G ? G[e] : make_double2(0.0, 0.0);
+        for (int i = 0; i < nt; ++i) {
+            const c128 ha = sh[i * n + a], hc = sh[i * n + cc];
+            const double f = sf[i];
+            // −i f (ha − hc) = f·((ha − hc).y, −(ha − hc).x)
+            g.x = fma(f, ha.y - hc.y, g.x);
+            g.y = fma(-f, ha.x - hc.x, g.y);
+        }
+        const c128 x = ub[e];
+        c128 o = dub[e];
+        o.x += g.x * x.x - g.y * x.y;
+        o.y += g.x * x.y + g.y * x.x;
+        dub[e] = o;
+    }
+}
+
 // He[b][a,a] += Σ_k coef[b][k]·|d_k[a]|²  — the L_k'L_k part of H_eff for diagonal L_k (coef already carries −(i/2)γ_bk or −½γ_bk)
 __global__ void heff_diag_add_kernel(int n, int K, const c128* __restrict__ ldiag, const c128* __restrict__ coef, long long coef_ld,
                                      c128* __restrict__ He, long long strideHe) {
@@ -197,13 +234,21 @@ int dense_rhs_impl(oqb_dense* op, int nb, const double* coefH, int coef_shared, 
     // one staged upload: [complex coefficient rows | raw γ rows]
     const size_t coef_bytes = coef.size() * sizeof(c128);
     const size_t gam_elems = K ? (gamma_shared ? (size_t)K : (size_t)nb * K) : 0;
-    std::vector<char> stage(coef_bytes + gam_elems * sizeof(double));
+    // split form (one off-diagonal Hamiltonian term): its coefficient f_N(s_b) per member, as the real scale of alpha
+    const bool may_split = with_h && op->offdiag_term >= 0 && K > 0 && gamma_shared && c->opt.lindblad_split;
+    const size_t fn_elems = may_split ? (size_t)(coef_shared ? 1 : nb) : 0;
+    std::vector<char> stage(coef_bytes + (gam_elems + fn_elems) * sizeof(double));
     memcpy(stage.data(), coef.data(), coef_bytes);
     if (gam_elems) memcpy(stage.data() + coef_bytes, gamma, gam_elems * sizeof(double));
+    if (fn_elems) {
+        double* fn = (double*)(stage.data() + coef_bytes + gam_elems * sizeof(double));
+        for (size_t b = 0; b < fn_elems; ++b) fn[b] = coefH[b * op->nterms + op->offdiag_term];
+    }
     void* d_stage = nullptr;
     OQB_TRY(coef_upload(c, stage.data(), stage.size(), &d_stage));
     void* d_coef = d_stage;
     void* d_gamma = (char*)d_stage + coef_bytes;
+    const double* d_fn = (const double*)((char*)d_stage + coef_bytes + gam_elems * sizeof(double));
 
     const bool no_diag = !c->opt.lindblad_diag;
     const size_t diag_sm = (size_t)K * n * sizeof(c128) + (size_t)K * sizeof(double);
@@ -221,6 +266,48 @@ int dense_rhs_impl(oqb_dense* op, int nb, const double* coefH, int coef_shared, 
     c128* He = (c128*)c->ws;
     c128* T = He + he_elems;
     c128* Gmat = T + (size_t)chunk * Kws * nn;
+
+    // Split form: H(s_b) = f_N(s_b)·m_N + diagonal terms, diagonal L_k, shared rates (config C2: −ΣX driver, ZZ problem term,
+    // dephasing).  No per-member H_eff is assembled at all: both products use the SHARED operand m_N with alpha scaled by
+    // f_N(s_b), and the diagonal terms' commutator joins the Lindblad factor in the one Hadamard pass.
+    const size_t split_sm = (size_t)op->nterms * n * sizeof(c128) + (size_t)op->nterms * sizeof(double);
+    if (may_split && fuse_sandwich && split_sm <= 160 * 1024) {
+        c128* G2 = (c128*)c->ws;  // the workspace was reserved for at least nn elements (he_elems ≥ nn)
+        lindblad_diag_gmat_kernel<<<(unsigned)((nn + 255) / 256), 256, 0, c->stream>>>((int)n, K, op->d_ldiag, (const double*)d_gamma, 1, G2);
+        OQB_LAUNCH_CHECK(c);
+        const c128* mN = op->d_mats + (long long)op->offdiag_term * nn;
+        const bool rN = op->offdiag_real && c->real_operand;
+        ZgemmParams p;  // du = −i f_N(s_b) m_N u
+        p.M = p.N = p.K = (int)n; p.batch = nb;
+        p.A = mN; p.lda = n; p.strideA = 0;
+        p.real_operand = rN ? 1 : 0;
+        p.B = u; p.ldb = n; p.strideB = nn;
+        p.C = du; p.ldc = n; p.strideC = nn;
+        p.alpha = make_double2(0.0, -1.0);
+        p.alpha_scale = d_fn; p.alpha_scale_mod = coef_shared ? 1 : 0;
+        OQB_TRY(zgemm(c, p));
+        ZgemmParams q;  // du += +i f_N(s_b) u m_N'
+        q.M = q.N = q.K = (int)n; q.batch = nb;
+        q.A = u; q.lda = n; q.strideA = nn;
+        q.B = mN; q.ldb = n; q.strideB = 0; q.opB = OP_C;
+        q.real_operand = rN ? 2 : 0;
+        q.C = du; q.ldc = n; q.strideC = nn;
+        q.alpha = make_double2(0.0, 1.0);
+        q.alpha_scale = d_fn; q.alpha_scale_mod = coef_shared ? 1 : 0;
+        q.beta = make_double2(1.0, 0.0);
+        OQB_TRY(zgemm(c, q));
+        static DevOnce cfg;
+        if (!cfg.done(c->device)) { OQB_CUDA(c, cudaFuncSetAttribute(hadamard_acc_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); cfg.set(c->device); }
+        for (int m0 = 0; m0 < nb; m0 += 65535) {
+            const int mc = nb - m0 < 65535 ? nb - m0 : 65535;
+            dim3 grid((unsigned)std::min<long long>((nn + 255) / 256, 64), mc);
+            hadamard_acc_split_kernel<<<grid, 256, split_sm, c->stream>>>((int)n, op->nterms, G2, op->d_hdiag,
+                                                                          (const c128*)d_coef + (rows == 1 ? 0 : (long long)m0 * nmat), rows == 1 ? 0 : nmat,
+                                                                          u + (long long)m0 * nn, du + (long long)m0 * nn);
+            OQB_LAUNCH_CHECK(c);
+        }
+        return 0;
+    }
 
     // diagonal L_k: L_k'L_k = diag|d_k|² — assemble H_eff from the Hamiltonian terms only and add the diagonal afterwards
     // (the per-member lincomb then reads nterms matrices instead of nterms + K)
@@ -323,6 +410,29 @@ int oqb_dense_create(oqb_ctx* c, int n, int nterms, const void* h_mats, int K, c
         bool re = nterms > 0;
         for (size_t e = 0; re && e < (size_t)nterms * nn; ++e) re = Hm[e].y == 0.0;
         op->terms_real = re;
+        // which terms are diagonal matrices (σz / σzσz problem Hamiltonians stored densely)?
+        int noff = 0, last = -1;
+        std::vector<c128> hd((size_t)std::max(nterms, 1) * n, make_double2(0.0, 0.0));
+        for (int i = 0; i < nterms; ++i) {
+            bool diag = true;
+            for (size_t e = 0; e < nn && diag; ++e)
+                if (e % n != e / n && (Hm[i * nn + e].x != 0.0 || Hm[i * nn + e].y != 0.0)) diag = false;
+            if (diag) {
+                for (int r = 0; r < n; ++r) hd[(size_t)i * n + r] = Hm[i * nn + (size_t)r * n + r];
+            } else {
+                ++noff;
+                last = i;
+            }
+        }
+        if (noff == 1 && nterms >= 2) {
+            op->offdiag_term = last;
+            bool r2 = true;
+            for (size_t e = 0; r2 && e < nn; ++e) r2 = Hm[last * nn + e].y == 0.0;
+            op->offdiag_real = r2;
+            if (cudaMalloc((void**)&op->d_hdiag, hd.size() * sizeof(c128)) != cudaSuccess) { oqb_dense_destroy(op); return set_error(c, OQB_ENOMEM, "oqb_dense_create: cudaMalloc failed"); }
+            OQB_CUDA(c, cudaMemcpyAsync(op->d_hdiag, hd.data(), hd.size() * sizeof(c128), cudaMemcpyHostToDevice, c->stream));
+            OQB_CUDA(c, cudaStreamSynchronize(c->stream));
+        }
     }
     if (K) {
         OQB_CUDA(c, cudaMemcpyAsync(op->d_lops, h_lops, K * nn * sizeof(c128), cudaMemcpyHostToDevice, c->stream));
@@ -367,6 +477,7 @@ int oqb_dense_destroy(oqb_dense* op) {
     if (op->d_mats) cudaFree(op->d_mats);
     if (op->d_lops) cudaFree(op->d_lops);
     if (op->d_ldiag) cudaFree(op->d_ldiag);
+    if (op->d_hdiag) cudaFree(op->d_hdiag);
     delete op;
     return OQB_OK;
 }
