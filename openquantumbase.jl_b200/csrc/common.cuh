@@ -30,6 +30,7 @@ struct Options {
     int rk_fuse = 1;          // RK4 stage arithmetic fused into the trajectory matvec
     int xor_fixed = 1;        // fully unrolled transverse-field variant of the XOR kernel
     int xor_rows = 16;        // rows per thread of the XOR kernel at n = 4096
+    int host_slots = 2;       // device buffers per direction in the host-buffer pipelines (2–4; more than 2 measured no faster)
     int ame_host_chunk_mib = 128;
     int davies_dense_min_pairs = 0;        // gap groups with at least this many level pairs take the dense per-group path (0 = cost model)
     long long davies_max_cross = 50000000; // cap on the cross-term list; larger groups go dense first
@@ -52,7 +53,7 @@ struct Ctx {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     cudaStream_t copy_stream[2] = {nullptr, nullptr};
-    cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[16] = {};  // host_pipeline: 4 upload, 4 compute, 4 download events + 1 ordering event
     std::string err;
     uint64_t launches = 0;
     // complex product of the TMA ZGEMM: 1 = 3-multiplication (default), 0 = classic 4-multiplication
@@ -178,15 +179,23 @@ int host_pipeline(Ctx* c, int nb, size_t in_bytes, size_t out_bytes, const void*
                   F compute) {
     if (nb <= 0) return 0;
     if (chunk > nb) chunk = nb;
+    // NBUF device slots per direction (option host_slots, default 2).  A third or fourth slot — taking the upload of chunk
+    // i+2 off the download of chunk i−2 — was measured and changes nothing: C3 e2e 1 794 / 1 803 / 1 803 evals/s with
+    // 2 / 3 / 4 slots on one GPU, 3 905 / 3 880 / 3 896 on eight (0.84 of the host link either way).
+    const int NBUF = c->opt.host_slots >= 2 && c->opt.host_slots <= 4 ? c->opt.host_slots : 2;
     const size_t inb = (size_t)chunk * in_bytes, outb = (size_t)chunk * out_bytes;
-    OQB_TRY(io_reserve(c, 2 * (inb + outb)));
+    OQB_TRY(io_reserve(c, NBUF * (inb + outb)));
     char* base = (char*)c->io;
-    char* d_in[2] = {base, base + inb};
-    char* d_out[2] = {base + 2 * inb, base + 2 * inb + outb};
+    char* d_in[4];
+    char* d_out[4];
+    for (int s = 0; s < NBUF; ++s) {
+        d_in[s] = base + (size_t)s * inb;
+        d_out[s] = base + (size_t)NBUF * inb + (size_t)s * outb;
+    }
     cudaStream_t up = c->copy_stream[0], down = c->copy_stream[1];
     cudaEvent_t* ev_up = &c->ev[0];
-    cudaEvent_t* ev_comp = &c->ev[2];
-    cudaEvent_t* ev_down = &c->ev[4];
+    cudaEvent_t* ev_comp = &c->ev[4];
+    cudaEvent_t* ev_down = &c->ev[8];
     // Chunk sizes ramp up at the start and down at the end (chunk/4, chunk/2, chunk, …, chunk/2, chunk/4): only the
     // first upload and the last download are not hidden behind compute, so they are made small.
     std::vector<int> sizes;
@@ -210,18 +219,18 @@ int host_pipeline(Ctx* c, int nb, size_t in_bytes, size_t out_bytes, const void*
         sizes.insert(sizes.end(), tail.begin(), tail.end());
     }
     // order the pipeline after whatever is already queued on the compute stream
-    OQB_CUDA(c, cudaEventRecord(c->ev[6], c->stream));
-    OQB_CUDA(c, cudaStreamWaitEvent(up, c->ev[6], 0));
+    OQB_CUDA(c, cudaEventRecord(c->ev[12], c->stream));
+    OQB_CUDA(c, cudaStreamWaitEvent(up, c->ev[12], 0));
     int b0 = 0;
     for (int i = 0; i < (int)sizes.size(); ++i) {
         const int cnt = sizes[i];
-        const int s = i & 1;
-        if (i >= 2) OQB_CUDA(c, cudaStreamWaitEvent(up, ev_comp[s], 0));
+        const int s = i % NBUF;
+        if (i >= NBUF) OQB_CUDA(c, cudaStreamWaitEvent(up, ev_comp[s], 0));
         OQB_CUDA(c, cudaMemcpyAsync(d_in[s], (const char*)h_in + (size_t)b0 * in_bytes, (size_t)cnt * in_bytes,
                                     cudaMemcpyHostToDevice, up));
         OQB_CUDA(c, cudaEventRecord(ev_up[s], up));
         OQB_CUDA(c, cudaStreamWaitEvent(c->stream, ev_up[s], 0));
-        if (i >= 2) OQB_CUDA(c, cudaStreamWaitEvent(c->stream, ev_down[s], 0));
+        if (i >= NBUF) OQB_CUDA(c, cudaStreamWaitEvent(c->stream, ev_down[s], 0));
         OQB_TRY(compute(b0, cnt, (const void*)d_in[s], (void*)d_out[s]));
         OQB_CUDA(c, cudaEventRecord(ev_comp[s], c->stream));
         OQB_CUDA(c, cudaStreamWaitEvent(down, ev_comp[s], 0));

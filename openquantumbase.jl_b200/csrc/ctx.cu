@@ -114,7 +114,7 @@ int oqb_create(int device, oqb_ctx** out) {
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return OQB_ECUDA; }
     c->own_stream = true;
     for (int i = 0; i < 2; ++i) cudaStreamCreateWithFlags(&c->copy_stream[i], cudaStreamNonBlocking);
-    for (int i = 0; i < 8; ++i) cudaEventCreateWithFlags(&c->ev[i], cudaEventDisableTiming);
+    for (int i = 0; i < 16; ++i) cudaEventCreateWithFlags(&c->ev[i], cudaEventDisableTiming);
     *out = c;
     return OQB_OK;
 }
@@ -129,7 +129,7 @@ int oqb_destroy(oqb_ctx* c) {
     if (c->pin) cudaFreeHost(c->pin);
     if (c->dcoef) cudaFree(c->dcoef);
     for (int i = 0; i < 2; ++i) if (c->copy_stream[i]) cudaStreamDestroy(c->copy_stream[i]);
-    for (int i = 0; i < 8; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    for (int i = 0; i < 16; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
     return OQB_OK;
@@ -162,7 +162,7 @@ namespace {
 struct OptEntry { const char* name; int Options::* field; };
 const OptEntry kOpts[] = {
     {"zgemm_tma", &Options::zgemm_tma}, {"zgemm_bm", &Options::zgemm_bm}, {"tma_oneshot", &Options::tma_oneshot},
-    {"lindblad_diag", &Options::lindblad_diag}, {"lindblad_fuse", &Options::lindblad_fuse}, {"lindblad_split", &Options::lindblad_split}, {"coupling_diag", &Options::coupling_diag}, {"traj_kernel", &Options::traj_kernel},
+    {"host_slots", &Options::host_slots}, {"lindblad_diag", &Options::lindblad_diag}, {"lindblad_fuse", &Options::lindblad_fuse}, {"lindblad_split", &Options::lindblad_split}, {"coupling_diag", &Options::coupling_diag}, {"traj_kernel", &Options::traj_kernel},
     {"traj_ell", &Options::traj_ell}, {"sell_r", &Options::sell_r}, {"sell_unit", &Options::sell_unit}, {"rk_fuse", &Options::rk_fuse}, {"xor_fixed", &Options::xor_fixed}, {"xor_rows", &Options::xor_rows},
     {"ame_host_chunk_mib", &Options::ame_host_chunk_mib}, {"davies_dense_min_pairs", &Options::davies_dense_min_pairs},
     {"debug_checks", &Options::debug_checks}, {"fuse_cross", &Options::fuse_cross},

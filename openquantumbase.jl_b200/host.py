@@ -36,7 +36,7 @@ _ENV_OPTIONS = {
     "OQB_ZGEMM_3M": ("zgemm_3m", int), "OQB_REAL_OPERAND": ("real_operand", int),
     "OQB_LINDBLAD_DIAG": ("lindblad_diag", int), "OQB_COUPLING_DIAG": ("coupling_diag", int),
     "OQB_RK_FUSE": ("rk_fuse", int), "OQB_TMA_ONESHOT": ("tma_oneshot", int), "OQB_ZGEMM_BM": ("zgemm_bm", int),
-    "OQB_AME_HOST_CHUNK_MIB": ("ame_host_chunk_mib", int), "OQB_XOR_FIXED": ("xor_fixed", int), "OQB_XOR_R": ("xor_rows", int),
+    "OQB_AME_HOST_CHUNK_MIB": ("ame_host_chunk_mib", int), "OQB_HOST_SLOTS": ("host_slots", int), "OQB_XOR_FIXED": ("xor_fixed", int), "OQB_XOR_R": ("xor_rows", int),
     "OQB_TRAJ": ("traj_kernel", lambda v: {"g": 1, "f": 2}.get(v[:1], 0)),
     "OQB_ZGEMM": ("zgemm_tma", lambda v: 0 if v[:1] == "c" else 1),
 }
