@@ -308,3 +308,90 @@ def test_c5_redfield_128(Q):
         assert relerr(du[b], ref) < TOL
     for b in range(nb):
         assert abs(np.trace(du[b])) < 1e-12 * np.linalg.norm(du[b]) * n
+
+
+# ---- full-size cross-route checks of the round-2 fast paths --------------------------------------------------------
+def test_c4_unstructured_4096_sell_vs_plain_and_scipy(Q):
+    """An operator WITHOUT Pauli structure at the C4 dimension (n = 4096, ≈13 random entries per row, complex values) over
+    8192 trajectories with per-trajectory s: the sliced-ELL kernel against the plain ELL kernel on the whole ensemble (1e-13),
+    against scipy on sampled members (1e-12), and linear in ψ."""
+    import ctypes as C
+    import torch
+    nq, n, nb = 12, 4096, 8192
+    rng = np.random.default_rng(4100)
+    rows = np.repeat(np.arange(n), 6)
+    cols = rng.integers(0, n, size=n * 6)
+    keep = rows != cols
+    vals = rng.standard_normal(n * 6) + 1j * rng.standard_normal(n * 6)
+    A = sps.csc_matrix((vals[keep], (rows[keep], cols[keep])), shape=(n, n))
+    H1 = (A + A.conj().T).tocsc()
+    H2 = sps.diags(rng.standard_normal(n)).tocsc().astype(complex)
+    _, _, Ls = tfim_sparse(nq)
+    H = Q.SparseHamiltonian([lambda s: 1 - s, lambda s: s], [H1, H2], unit="ħ")
+    ens = Q.TrajectoryEnsemble(Q.DiffEqLiouvillian(H, [], [Q.LindbladLiouvillian([Q.Lindblad(0.05, L) for L in Ls])], n))
+    ctx = Q.get_context()
+    gen = torch.Generator(device="cuda").manual_seed(41)
+    psi_t = torch.randn((nb, 1, n), dtype=torch.complex128, device="cuda", generator=gen)
+    psi = Q.DeviceBatch(nb, n, 1, ctx, psi_t.contiguous())
+    s = rng.random(nb)
+    cf = np.ascontiguousarray(np.stack([1 - s, s], axis=1))
+    gam = np.full((1, nq), 0.05)
+    dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+
+    def matvec(x):
+        out = x.zeros_like()
+        ctx.check(ctx.lib.oqb_traj_matvec(ens.sp, nb, dp(cf), 0, dp(gam), 1, x.ptr, out.ptr))
+        return out
+
+    sell = matvec(psi)
+    pl, pad = C.c_int(), C.c_double()
+    ctx.check(ctx.lib.oqb_traj_sell_stats(ens.sp, C.byref(pl), C.byref(pad)))
+    assert pl.value == 1 and 1.0 < pad.value < 1.3  # the sliced-ELL plan was built and used
+    with ctx.option("traj_ell", 0):
+        plain = matvec(psi)
+    assert float(torch.linalg.vector_norm(sell.t - plain.t) / torch.linalg.vector_norm(plain.t)) < 1e-13
+    hs = sell.t.reshape(nb, n)
+    for b in (0, 4097, nb - 1):
+        M = -1j * ((1 - s[b]) * H1 + s[b] * H2) - 0.5 * 0.05 * nq * sps.identity(n)
+        assert relerr(hs[b].cpu().numpy(), M @ psi_t[b, 0].cpu().numpy()) < TOL
+    # linearity: A(2ψ − iψ') = 2Aψ − iAψ'
+    psi2_t = torch.randn((nb, 1, n), dtype=torch.complex128, device="cuda", generator=gen)
+    comb = Q.DeviceBatch(nb, n, 1, ctx, (2 * psi_t - 1j * psi2_t).contiguous())
+    lhs = matvec(comb).t
+    rhs = 2 * sell.t - 1j * matvec(Q.DeviceBatch(nb, n, 1, ctx, psi2_t.contiguous())).t
+    assert float(torch.linalg.vector_norm(lhs - rhs) / torch.linalg.vector_norm(rhs)) < 1e-13
+
+
+def test_c2_full_batch_split_route_vs_assembled(Q):
+    """C2 at its full batch (4096 ρ of 256×256, per-member s, dephasing): the split-Hamiltonian route (shared driver operand
+    scaled per member, diagonal terms and the Lindblad factor in one Hadamard pass) against the assembled-H_eff route on
+    every member (1e-13), the oracle on sampled members (1e-12), trace and Hermiticity on all."""
+    import torch
+    rng = np.random.default_rng(2001)
+    nq, n, K, nb = 8, 256, 8, 4096
+    Hd, Hp, z = tfim_dense(nq)
+    Ls = [np.diag(zq).astype(complex) for zq in z]
+    fs = [lambda s: 1 - s, lambda s: s]
+    gam = [0.1 * (1 + k / 8) for k in range(K)]
+    opg = Q.DiffEqLiouvillian(Q.DenseHamiltonian(fs, [Hd, Hp], unit="ħ"), [], [Q.LindbladLiouvillian([Q.Lindblad(g, L) for g, L in zip(gam, Ls)])], n)
+    opo = O.DiffEqLiouvillian(O.DenseHamiltonian(fs, [Hd, Hp], unit="ħ"), [], [O.LindbladLiouvillian([O.Lindblad(g, L) for g, L in zip(gam, Ls)])], n)
+    ctx = Q.get_context()
+    gen = torch.Generator(device="cuda").manual_seed(7)
+    g = torch.randn((nb, 16, n), dtype=torch.complex128, device="cuda", generator=gen)
+    rho = g.transpose(1, 2) @ g.conj()
+    rho = rho / torch.diagonal(rho, dim1=1, dim2=2).sum(-1).real[:, None, None]
+    u = Q.DeviceBatch(nb, n, n, ctx, rho.contiguous())
+    t = np.arange(nb) / nb * 10.0
+    p = Q.ODEParams(None, 10.0)
+    du = opg(u.zeros_like(), u, p, t)
+    with ctx.option("lindblad_split", 0), ctx.option("lindblad_fuse", 0):
+        du0 = opg(u.zeros_like(), u, p, t)
+    assert float(torch.linalg.vector_norm(du.t - du0.t) / torch.linalg.vector_norm(du0.t)) < 1e-13
+    # DeviceBatch blocks are column-major (Julia layout): block[b] read row-major is the transpose
+    for b in (0, 1234, nb - 1):
+        ub = u.t[b].cpu().numpy().T
+        assert relerr(du.t[b].cpu().numpy().T, opo.rhs(ub, O.ODEParams(None, 10.0), t[b])) < TOL
+    tr = torch.diagonal(du.t, dim1=1, dim2=2).sum(-1)
+    nrm = torch.linalg.matrix_norm(du.t)
+    assert float((tr.abs() / (nrm * n)).max()) < 1e-12
+    assert float(torch.linalg.vector_norm(du.t - du.t.transpose(1, 2).conj()) / torch.linalg.vector_norm(du.t)) < 1e-12
