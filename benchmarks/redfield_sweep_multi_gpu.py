@@ -86,21 +86,43 @@ def main():
     tms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-    # per-schedule observables of this rank's block, then the one collective: all_gather into the full sweep
+    # per-schedule observables of this rank's block, then the one collective of the path: an all-gather into the full sweep
+    # through the LIBRARY's communicator (oqb_allgather_obs: ncclAllGather on the context stream, csrc/comm.cu);
+    # torch.distributed on the same buffers is timed beside it.  Median of 20 warmed calls.
+    import ctypes as C
     ev = Q.expect(obs, u)  # (B, K+1) complex
     loc = torch.view_as_real(ev).contiguous()
     full = torch.empty((world,) + tuple(loc.shape), dtype=loc.dtype, device=dev)
+    full_t = torch.empty_like(full)
+    lib_ms = torch_ms = 0.0
     if world > 1:
-        dist.all_gather_into_tensor(full, loc)  # warm-up
-        torch.cuda.synchronize()
-    a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a0.record()
-    if world > 1:
-        dist.all_gather_into_tensor(full, loc)
+        idbuf = [None]
+        if rank == 0:
+            raw = (C.c_char * 128)()
+            ctx.check(ctx.lib.oqb_comm_unique_id(raw))
+            idbuf = [bytes(raw)]
+        dist.broadcast_object_list(idbuf, src=0)
+        comm = C.c_void_p()
+        ctx.check(ctx.lib.oqb_comm_init_rank(ctx.h, world, rank, idbuf[0], C.byref(comm)))
+
+        def med(fn, reps=20, warm=5):
+            for _ in range(warm):
+                fn()
+            torch.cuda.synchronize()
+            ts = []
+            for _ in range(reps):
+                a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                dist.barrier()
+                a0.record(); fn(); a1.record()
+                torch.cuda.synchronize()
+                ts.append(a0.elapsed_time(a1))
+            return float(np.median(ts))
+        lib_ms = med(lambda: ctx.check(ctx.lib.oqb_allgather_obs(comm, C.c_void_p(loc.data_ptr()), C.c_void_p(full.data_ptr()), loc.numel())))
+        torch_ms = med(lambda: dist.all_gather_into_tensor(full_t, loc))
+        assert torch.equal(full, full_t)
+        ctx.check(ctx.lib.oqb_comm_destroy(comm))
     else:
         full[0].copy_(loc)
-    a1.record()
-    torch.cuda.synchronize()
     if rank == 0:
         ms = float(tms.item()) / args.steps
         flops = 8.0 * n ** 3 * (2 + (K if diag_path else 3 * K)) * total
@@ -109,8 +131,8 @@ def main():
             "config": "C5" + ("-diagS" if diag_path else ""), "diagonal_couplings_exploited": diag_path, "workload": f"{total} schedules x 7-qubit Redfield RHS (commutator + apply, supplied Lambda), n={n}, K={K}, {B} per GPU x {world} GPUs",
             "metric": "rho_rhs_evals_per_sec", "value": total / (ms * 1e-3), "n_gpus": world, "scaling": "weak", "ms_per_step": ms,
             "algorithmic_tflop_per_step": flops / 1e12, "aggregate_tflops_algorithmic": flops / (ms * 1e-3) / 1e12,
-            "observables": {"per_schedule": K + 1, "allgather_ms": a0.elapsed_time(a1), "gathered_shape": list(full.shape),
-                            "collective": "one all_gather of (K+1) complex numbers per schedule (NCCL)" if world > 1 else "none (1 GPU)",
+            "observables": {"per_schedule": K + 1, "allgather_ms": lib_ms, "torch_distributed_allgather_ms": torch_ms, "gathered_shape": list(full.shape),
+                            "collective": "one oqb_allgather_obs (ncclAllGather through the library's communicator) of (K+1) complex numbers per schedule, median of 20 calls" if world > 1 else "none (1 GPU)",
                             "trace_min": float(tr.min().item()), "trace_max": float(tr.max().item())}}) + "\n")
         real_stdout.flush()
     if world > 1:
