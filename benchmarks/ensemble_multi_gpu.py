@@ -77,13 +77,48 @@ def main():
     zd = torch.as_tensor(np.stack(zdiag), device=f"cuda:{local}")
     ensemble_average(zd @ Q.ensemble_population(psi), hi - lo)  # warm-up (allocator, NCCL channel set-up)
     torch.cuda.synchronize()
-    a0, a1, a2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    a0, a1 = (torch.cuda.Event(enable_timing=True) for _ in range(2))
     a0.record()
     part = zd @ Q.ensemble_population(psi)
     a1.record()
-    avg = ensemble_average(part, hi - lo)
-    a2.record()
     torch.cuda.synchronize()
+    # the collective itself through the LIBRARY's communicator (oqb_allreduce_obs: ncclAllReduce on the context stream,
+    # csrc/comm.cu), torch.distributed on the same numbers beside it; median of 20 warmed calls
+    import ctypes as C
+    buf = torch.cat([part.to(torch.float64), torch.tensor([float(hi - lo)], dtype=torch.float64, device=part.device)]).contiguous()
+    lib_ms = torch_ms = 0.0
+    if world > 1:
+        idbuf = [None]
+        if rank == 0:
+            raw = (C.c_char * 128)()
+            ctx.check(ctx.lib.oqb_comm_unique_id(raw))
+            idbuf = [bytes(raw)]
+        dist.broadcast_object_list(idbuf, src=0)
+        comm = C.c_void_p()
+        ctx.check(ctx.lib.oqb_comm_init_rank(ctx.h, world, rank, idbuf[0], C.byref(comm)))
+
+        def med(fn, reps=20, warm=5):
+            for _ in range(warm):
+                fn()
+            torch.cuda.synchronize()
+            ts = []
+            for _ in range(reps):
+                b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                dist.barrier()
+                b0.record(); fn(); b1.record()
+                torch.cuda.synchronize()
+                ts.append(b0.elapsed_time(b1))
+            return float(np.median(ts))
+        scratch = buf.clone()
+        lib_ms = med(lambda: ctx.check(ctx.lib.oqb_allreduce_obs(comm, C.c_void_p(scratch.data_ptr()), scratch.numel())))
+        torch_ms = med(lambda: dist.all_reduce(scratch))
+        red = buf.clone()
+        ctx.check(ctx.lib.oqb_allreduce_obs(comm, C.c_void_p(red.data_ptr()), red.numel()))
+        torch.cuda.synchronize()
+        ctx.check(ctx.lib.oqb_comm_destroy(comm))
+    else:
+        red = buf
+    avg = red[:-1] / red[-1]
     jumps = st.njumps.sum().to(torch.float64)
     if world > 1:
         dist.all_reduce(jumps)
@@ -100,9 +135,9 @@ def main():
             "metric": "trajectory_steps_per_sec", "value": world * B * args.steps / (ms * 1e-3), "n_gpus": world, "scaling": "weak",
             "ms_per_rk4_step": ms / args.steps, "per_gpu_GBs": gb / (ms / args.steps * 1e-3),
             "per_gpu_frac_of_measured_hbm": gb / (ms / args.steps * 1e-3) / hbm,
-            "observables": {"n": len(zdiag), "local_reduce_ms": a0.elapsed_time(a1), "allreduce_ms": a1.elapsed_time(a2),
-                            "collective": "one all_reduce(sum) of nobs+1 complex numbers (NCCL)" if world > 1 else "none (1 GPU)",
-                            "mean_norm2": float(avg[-1].real), "mean_Z1": float(avg[0].real)},
+            "observables": {"n": len(zdiag), "local_reduce_ms": a0.elapsed_time(a1), "allreduce_ms": lib_ms, "torch_distributed_allreduce_ms": torch_ms,
+                            "collective": "one oqb_allreduce_obs (ncclAllReduce through the library's communicator) of nobs+1 doubles, median of 20 calls" if world > 1 else "none (1 GPU)",
+                            "mean_norm2": float(avg[-1]), "mean_Z1": float(avg[0])},
             "jumps_total": float(jumps.item())}) + "\n")
         real_stdout.flush()
     if world > 1:
