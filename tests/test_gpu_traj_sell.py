@@ -242,3 +242,40 @@ def test_rk4_stage_fusion_follows_the_row_order(Q, kind):
         assert counts[1] <= counts[0] - 4, counts
     else:
         assert abs(counts[1] - counts[0]) <= 1, counts
+
+
+@pytest.mark.parametrize("n,nb", [(5000, 5), (8192, 3)])
+def test_large_dimensions_with_one_or_two_ring_slots(Q, n, nb):
+    """n = 5000: two 80 KB slots (both members of a pair are loaded at the top of their own iteration); n = 8192 (13 qubits):
+    a single 131 KB slot, one trajectory per operator fetch."""
+    rng = np.random.default_rng(n)
+    H1 = random_h(n, 4, rng)
+    H2 = sps.diags(rng.standard_normal(n)).tocsc().astype(complex)
+    psi = rng.standard_normal((nb, n)) + 1j * rng.standard_normal((nb, n))
+    s = rng.random(nb)
+    got = run(Q, H1, H2, [], psi, s, np.zeros((1, 0)), traj_kernel=1)
+    assert relerr(got, reference(H1, H2, [], np.zeros((1, 0)), s, psi)) < TOL
+
+
+def test_more_terms_than_the_plan_holds_fall_back(Q):
+    """7 off-diagonal terms exceed the sliced-ELL plan's 6: the plain kernels take over, same answer."""
+    import ctypes as C
+    n, nb, nt = 64, 5, 7
+    rng = np.random.default_rng(21)
+    mats = [random_h(n, 3, rng) for _ in range(nt)]
+    fs = [(lambda s, a=a: a + s) for a in rng.standard_normal(nt)]
+    H = Q.SparseHamiltonian(fs, mats, unit="ħ")
+    ens = Q.TrajectoryEnsemble(Q.DiffEqLiouvillian(H, [], [], n))
+    ctx = Q.get_context()
+    psi = rng.standard_normal((nb, n)) + 1j * rng.standard_normal((nb, n))
+    s = rng.random(nb)
+    cf = np.ascontiguousarray(np.stack([[f(x) for f in fs] for x in s]))
+    pd = Q.DeviceBatch.from_host(psi)
+    out = pd.zeros_like()
+    with ctx.option("traj_kernel", 1):
+        ctx.check(ctx.lib.oqb_traj_matvec(ens.sp, nb, cf.ctypes.data_as(C.POINTER(C.c_double)), 0, None, 1, pd.ptr, out.ptr))
+    pl, pad = C.c_int(), C.c_double()
+    ctx.check(ctx.lib.oqb_traj_sell_stats(ens.sp, C.byref(pl), C.byref(pad)))
+    assert pl.value == 0
+    ref = np.stack([sum(-1j * cf[b, i] * mats[i] for i in range(nt)) @ psi[b] for b in range(nb)])
+    assert relerr(out.to_host().reshape(nb, n), ref) < TOL
