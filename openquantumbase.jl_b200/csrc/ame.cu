@@ -401,7 +401,6 @@ int oqb_ame_clear_onesided(oqb_ame* a) {
 int oqb_ame_destroy(oqb_ame* a) {
     OQB_DEVICE(a, a->ctx);
     if (!a) return OQB_OK;
-    bool he = a->have_eigen;
     a->have_eigen = false;
     oqb_ame_clear_davies(a);
     oqb_ame_clear_onesided(a);
