@@ -409,7 +409,6 @@ int oqb_ame_destroy(oqb_ame* a) {
     ame_free(a->ctx, a->d_flag);
     ame_free(a->ctx, a->d_cdiag);
     ame_free(a->ctx, a->d_Scoef);
-    (void)he;
     ame_free(a->ctx, a->d_coup); ame_free(a->ctx, a->d_V); ame_free(a->ctx, a->d_w); ame_free(a->ctx, a->d_A); ame_free(a->ctx, a->d_Cm);
     delete a;
     return OQB_OK;
