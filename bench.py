@@ -161,6 +161,10 @@ def run_secondary(Q, torch, ctx):
             r = OC.run_c2(Q, torch, 2, False)
         out["C2_general_2plus2K_gemms"] = short(r, ("config", "value", "ms_per_step", "roofline"))
         torch.cuda.empty_cache()
+        # north_star's "batched 10-qubit Lindblad RHS": the same operators at 10 qubits, 64 rho of 1024 x 1024
+        r = OC.run_c2(Q, torch, 3, False, nq=10, B=64)
+        out["C2prime_10q_dephasing"] = short(r, ("config", "workload", "value", "ms_per_step", "roofline"))
+        torch.cuda.empty_cache()
     except Exception as e:  # noqa: BLE001
         out["C2_error"] = f"{type(e).__name__}: {e}"
     try:

@@ -477,7 +477,7 @@ def run_c5(Q, torch, steps):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--configs", default="c2,c2general,c2dense,c2prime,c3onesided,c4,c5,c5general")
+    ap.add_argument("--configs", default="c2,c2general,c2dense,c2prime,c2prime_diag,c3onesided,c4,c5,c5general")
     ap.add_argument("--steps", type=int, default=5)
     args = ap.parse_args()
     import torch
@@ -510,6 +510,8 @@ def main():
             r = run_c2(Q, torch, args.steps, True)
         elif c == "c2prime":
             r = run_c2(Q, torch, args.steps, True, nq=10, B=64)
+        elif c == "c2prime_diag":  # the 10-qubit Lindblad RHS with per-qubit dephasing (north_star's "batched 10-qubit Lindblad RHS")
+            r = run_c2(Q, torch, args.steps, False, nq=10, B=64)
         elif c == "c3onesided":
             r = run_c3_onesided(Q, torch, args.steps)
         elif c == "c3lamb":

@@ -252,7 +252,10 @@ int dense_rhs_impl(oqb_dense* op, int nb, const double* coefH, int coef_shared, 
 
     const bool no_diag = !c->opt.lindblad_diag;
     const size_t diag_sm = (size_t)K * n * sizeof(c128) + (size_t)K * sizeof(double);
-    const bool use_diag = K > 0 && op->d_ldiag && !no_diag && diag_sm <= 160 * 1024;
+    // rates shared by the batch: the Hadamard factor is one n×n matrix built from global memory — no shared-memory limit;
+    // per-member rates keep the K diagonals in shared memory (K·n ≤ 13 300: K = 12 at 10 qubits)
+    const bool can_fuse = K > 0 && op->d_ldiag && !no_diag && gamma_shared && c->opt.lindblad_fuse;
+    const bool use_diag = K > 0 && op->d_ldiag && !no_diag && (can_fuse || diag_sm <= 208 * 1024);
     const int Kws = use_diag ? 0 : K;  // the Hadamard form of the sandwich needs no L_k u scratch
     const size_t per = (size_t)(1 + Kws) * nn * sizeof(c128);
     int chunk = (int)(kWorkspaceBudget / per);
@@ -261,7 +264,7 @@ int dense_rhs_impl(oqb_dense* op, int nb, const double* coefH, int coef_shared, 
     chunk = (nb + (nb + chunk - 1) / chunk - 1) / ((nb + chunk - 1) / chunk);  // balance the chunks
     const size_t he_elems = (size_t)(rows == 1 ? 1 : chunk) * nn;
     // shared rates + diagonal L_k: the sandwich is one n×n Hadamard factor for every member, folded into the second product
-    const bool fuse_sandwich = use_diag && gamma_shared && c->opt.lindblad_fuse;
+    const bool fuse_sandwich = can_fuse;
     OQB_TRY(ws_reserve(c, (he_elems + (size_t)chunk * Kws * nn + (fuse_sandwich ? nn : 0)) * sizeof(c128)));
     c128* He = (c128*)c->ws;
     c128* T = He + he_elems;
@@ -370,7 +373,7 @@ int dense_rhs_impl(oqb_dense* op, int nb, const double* coefH, int coef_shared, 
             const size_t sm = diag_sm;
             if (use_diag) {
                 static DevOnce cfg;
-                if (!cfg.done(c->device)) { OQB_CUDA(c, cudaFuncSetAttribute(lindblad_diag_sandwich_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); cfg.set(c->device); }
+                if (!cfg.done(c->device)) { OQB_CUDA(c, cudaFuncSetAttribute(lindblad_diag_sandwich_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024)); cfg.set(c->device); }
                 for (int m0 = 0; m0 < cnt; m0 += 65535) {
                     const int mc = cnt - m0 < 65535 ? cnt - m0 : 65535;
                     const int tiles = (int)std::min<long long>((nn + 255) / 256, 64);

@@ -127,3 +127,39 @@ def test_split_hamiltonian_vs_oracle(Q, nq, nb, per_member_s, complex_driver):
     duh = opg.rhs_host(np.zeros_like(uh), uh, Q.ODEParams(None, tf), t) if hasattr(opg, "rhs_host") else None
     if duh is not None:
         assert relerr(duh.transpose(0, 2, 1), ref) < TOL
+
+
+@pytest.mark.parametrize("K,rates", [(10, "const"), (10, "per_member"), (14, "per_member"), (14, "const")])
+def test_ten_qubit_dephasing_takes_the_diagonal_route(Q, K, rates):
+    """10 qubits, per-qubit dephasing (north_star's batched 10-qubit Lindblad RHS): the K diagonals (K·n·16 B = 164 KB at
+    K = 10) must not push the RHS onto the 2+2K-product route.  Shared rates need no shared memory at all; per-member rates
+    keep the diagonals in shared memory up to 208 KB and take the general products beyond.  All against the oracle."""
+    nq, n, nb = 10, 1024, 2
+    rng = np.random.default_rng(K + len(rates))
+    idx = np.arange(n)
+    Hd = np.zeros((n, n), dtype=complex)
+    for q in range(nq):
+        Hd[idx ^ (1 << q), idx] = -1.0
+    z = [1.0 - 2.0 * ((idx >> (nq - 1 - q)) & 1) for q in range(nq)]
+    Hp = np.diag(-sum(z[i] * z[i + 1] for i in range(nq - 1))).astype(complex)
+    Ls = [np.diag(z[k % nq] * (1.0 + 0.1 * (k // nq))).astype(complex) for k in range(K)]
+    fs = [lambda s: 1 - s, lambda s: s]
+    gfs = [(lambda s, k=k: 0.05 * (1 + k)) if rates == "const" else (lambda s, k=k: 0.05 * (1 + k) * (1 + s)) for k in range(K)]
+    opg = Q.DiffEqLiouvillian(Q.DenseHamiltonian(fs, [Hd, Hp], unit="ħ"), [], [Q.LindbladLiouvillian([Q.Lindblad(g, L) for g, L in zip(gfs, Ls)])], n)
+    opo = O.DiffEqLiouvillian(O.DenseHamiltonian(fs, [Hd, Hp], unit="ħ"), [], [O.LindbladLiouvillian([O.Lindblad(g, L) for g, L in zip(gfs, Ls)])], n)
+    u = rand_c(rng, nb, n, n) / n
+    t = np.array([2.0, 7.5])
+    ctx = Q.get_context()
+    opg(np.zeros_like(u), u, Q.ODEParams(None, 10.0), t)  # first call builds the device operator (its L_k'L_k products are not the RHS)
+    ctx.check(ctx.lib.oqb_profile_begin(ctx.h))
+    got = opg(np.zeros_like(u), u, Q.ODEParams(None, 10.0), t)
+    import ctypes as C
+    ms, nl, fl = C.c_double(), C.c_uint64(), C.c_double()
+    ctx.check(ctx.lib.oqb_profile_end(ctx.h, C.byref(ms), C.byref(nl), C.byref(fl)))
+    ref = np.stack([opo.rhs(u[b], O.ODEParams(None, 10.0), t[b]) for b in range(nb)])
+    assert relerr(got, ref) < TOL
+    gemm_flops_per_rho = fl.value / nb / (8.0 * n ** 3)  # products per ρ as the profile hooks counted them
+    if rates == "const" or K <= 12:
+        assert gemm_flops_per_rho <= 2.01, gemm_flops_per_rho     # 2 products per ρ
+    else:
+        assert gemm_flops_per_rho >= 2 * K, gemm_flops_per_rho    # the general route: 2 + 2K products per ρ
