@@ -70,14 +70,25 @@ def rand_states(torch, B, n, cols, seed):
     return torch.randn((B, cols, n), dtype=torch.complex128, device="cuda", generator=gen)
 
 
-def run_c2(Q, torch, steps, dense_L, nq=8, B=4096):
+def sigma_minus(nq, q):
+    """σ⁻ on qubit q (0-based, qubit 0 = most significant bit): |0><1| on that qubit — amplitude damping."""
+    n = 1 << nq
+    idx = np.arange(n)
+    bit = 1 << (nq - 1 - q)
+    L = np.zeros((n, n), dtype=complex)
+    src = idx[(idx & bit) != 0]
+    L[src ^ bit, src] = 1.0
+    return L
+
+
+def run_c2(Q, torch, steps, dense_L, nq=8, B=4096, damping=False):
     """C2: 8-qubit dense TFIM + 8 Lindblad operators, batch 4096 of 256×256 ρ, per-member s_b = b/B.
     C2' (SURVEY §8(d)): the same at 10 qubits — n = 1024, K = 10, B = 64."""
     n, K = 2 ** nq, nq
     rng = np.random.default_rng(2000)
     Hd, Hp, z = tfim_dense(nq)
     Ls = [rng.standard_normal((n, n)) / np.sqrt(n) + 1j * rng.standard_normal((n, n)) / np.sqrt(n) for _ in range(K)] if dense_L \
-        else [np.diag(zq).astype(complex) for zq in z]
+        else ([sigma_minus(nq, q) for q in range(nq)] if damping else [np.diag(zq).astype(complex) for zq in z])
     H = Q.DenseHamiltonian([lambda s: 1 - s, lambda s: s], [Hd, Hp], unit="ħ")
     lind = Q.LindbladLiouvillian([Q.Lindblad(0.1 * (1 + k / nq), L) for k, L in enumerate(Ls)])
     op = Q.DiffEqLiouvillian(H, [], [lind], n)
@@ -95,7 +106,7 @@ def run_c2(Q, torch, steps, dense_L, nq=8, B=4096):
     ms = timed(fn, steps, 3, torch)
     zms, zn, zfl = C.c_double(), C.c_uint64(), C.c_double()
     ctx.check(ctx.lib.oqb_profile_end(ctx.h, C.byref(zms), C.byref(zn), C.byref(zfl)))
-    diag_path = (not dense_L) and ctx.get_option("lindblad_diag") != 0
+    diag_path = (not dense_L) and ctx.get_option("lindblad_diag") != 0 and (not damping or ctx.get_option("lindblad_mono") != 0)
     # general L_k: 2 + 2K GEMMs per rho; diagonal L_k exploited (its own row): 2 GEMMs + one Hadamard pass
     flops = 8.0 * n ** 3 * ((2 if diag_path else 2 + 2 * K)) * B
     dmma, _ = ctx.probe_fp64()
@@ -105,7 +116,11 @@ def run_c2(Q, torch, steps, dense_L, nq=8, B=4096):
         extra = {"note": "diagonal L_k exploited: sum_k gamma_k L_k rho L_k' is a Hadamard product with G_b[a,c] = sum_k gamma_bk d_k[a] conj(d_k[c]) "
                          "(lindblad_diag_sandwich_kernel, 48 B per element) — 2 GEMMs per rho instead of 2+2K; OQB_LINDBLAD_DIAG=0 gives the general row",
                  "hadamard_bytes_per_step_GB": 48.0 * n * n * B / 1e9}
-    return {**extra, "config": ("C2" if nq == 8 else "C2prime") + ("-denseL" if dense_L else ("-Zk-diagL" if diag_path else "-Zk")), "workload": f"{nq}-qubit dense TFIM + {K} {'random dense' if dense_L else 'dense-stored Z_k'} Lindblad ops, batch {B} of {n}x{n} rho, per-member s",
+    if damping and diag_path:
+        extra = {"note": "monomial L_k (sigma-minus per qubit: one entry per row and column) exploited: L_k rho L_k' is a gather of rho (lindblad_mono_sandwich_kernel), "
+                         "L_k'L_k diagonal — 2 GEMMs per rho instead of 2+2K; option lindblad_mono = 0 gives the general row"}
+    return {**extra, "config": ("C2" if nq == 8 else "C2prime") + ("-denseL" if dense_L else (("-damping-monoL" if damping else "-Zk-diagL") if diag_path else ("-damping" if damping else "-Zk"))),
+            "workload": f"{nq}-qubit dense TFIM + {K} {'random dense' if dense_L else ('dense-stored sigma-minus_k (amplitude damping)' if damping else 'dense-stored Z_k')} Lindblad ops, batch {B} of {n}x{n} rho, per-member s",
             "metric": "rho_rhs_evals_per_sec", "value": B / (ms * 1e-3), "ms_per_step": ms,
             "algorithmic_tflop_per_step": flops / 1e12, "step_tflops": flops / (ms * 1e-3) / 1e12,
             "roofline": {"bound": "tensor", "kernel": "zgemm_tma_kernel", "achieved": ach, "peak": dmma, "unit": "TFLOP/s",
@@ -510,6 +525,10 @@ def main():
             r = run_c2(Q, torch, args.steps, True)
         elif c == "c2prime":
             r = run_c2(Q, torch, args.steps, True, nq=10, B=64)
+        elif c == "c2prime_damping":  # 10-qubit amplitude damping: monomial operators
+            r = run_c2(Q, torch, args.steps, False, nq=10, B=64, damping=True)
+        elif c == "c2_damping":
+            r = run_c2(Q, torch, args.steps, False, damping=True)
         elif c == "c2prime_diag":  # the 10-qubit Lindblad RHS with per-qubit dephasing (north_star's "batched 10-qubit Lindblad RHS")
             r = run_c2(Q, torch, args.steps, False, nq=10, B=64)
         elif c == "c3onesided":

@@ -62,6 +62,7 @@ int oqb_launch_count(const oqb_ctx* ctx, uint64_t* n); /* kernels launched throu
  *   "zgemm_3m" (1), "real_operand" (1)        — as oqb_set_zgemm_mode / oqb_set_real_operand_mode below
  *   "zgemm_tma" (1)  0 = cp.async ZGEMM only;  "zgemm_bm" (0) 64/128 force the CTA tile height;  "tma_oneshot" (1)
  *   "lindblad_diag" (1), "coupling_diag" (1)   — treat diagonal L_k / couplings as general dense matrices when 0
+ *   "lindblad_mono" (1)  monomial L_k (one entry per row and column: sigma+-, Pauli strings): gather of rho instead of 2K products
  *   "lindblad_fuse" (1)  diagonal L_k with rates shared by the batch: one n×n factor G per call and du += G∘u as a streaming pass
  *   "lindblad_split" (1) … and one off-diagonal Hamiltonian term: shared-operand products scaled by f_N(s_b), diagonal terms in that pass
  *   "traj_kernel" (0)  0 = pick by operator structure, 1 = no Pauli/XOR specialisation at all, 2 = no XOR specialisation

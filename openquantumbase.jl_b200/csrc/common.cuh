@@ -21,6 +21,7 @@ struct Options {
     int tma_oneshot = 1;      // one-instruction 5-D operand tiles
     int lindblad_fuse = 1;    // diagonal L_k with shared rates: one n×n factor G for the whole batch, du += G∘u as a pure streaming pass
     int lindblad_split = 1;   // … and one off-diagonal Hamiltonian term: shared-operand products scaled by f_N(s_b), diagonal terms in the Hadamard pass
+    int lindblad_mono = 1;    // exploit monomial L_k (one entry per row and column: σ±, Pauli strings): gather instead of 2K products
     int lindblad_diag = 1;    // exploit diagonal L_k
     int coupling_diag = 1;    // exploit diagonal couplings in the rotation v'c_αv
     int traj_kernel = 0;      // 0 = pick by operator structure, 1 = generic kernels only, 2 = no XOR specialisation

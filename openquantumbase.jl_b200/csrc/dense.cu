@@ -17,6 +17,11 @@ struct oqb_dense {
     c128* d_mats = nullptr;  // (nterms + K) n×n : m_1..m_nterms, L_1'L_1..L_K'L_K
     c128* d_lops = nullptr;  // K n×n == the n × (K n) matrix [L_1 | … | L_K]
     c128* d_ldiag = nullptr; // K × n diagonals when EVERY L_k is diagonal (dephasing Z_k, …), else nullptr
+    // every L_k MONOMIAL (at most one entry per row and per column: σ±, Pauli strings, their products — amplitude damping,
+    // Pauli channels) but not all diagonal: L_k[a, π_k(a)] = v_k[a]; L_k'L_k is then diagonal with entries lld_k
+    int32_t* d_mperm = nullptr;  // K × n: π_k(a), −1 for an empty row
+    c128* d_mval = nullptr;      // K × n: v_k[a]
+    double* d_mlld = nullptr;    // K × n: (L_k'L_k)[j, j]
     bool lops_real = false;   // every L_k has zero imaginary part (σx, σ±, σz, …): both sandwich products are real-operand products
     bool terms_real = false;  // every Hamiltonian term matrix has zero imaginary part: H(s)ρ and ρH(s) take the real-operand product
     // split form of H(s) = f_N(s)·m_N + Σ_{i diagonal} f_i(s)·diag(h_i): exactly one term has off-diagonal entries
@@ -186,6 +191,63 @@ __global__ void hadamard_acc_split_kernel(int n, int nt, const c128* __restrict_
     }
 }
 
+// Monomial L_k: (L_k u L_k')[a,c] = v_k[a] conj(v_k[c]) u[π_k(a), π_k(c)] — a gather of u instead of two n³ products.
+// One block per column c (π_k(c), v_k[c] are block-uniform), threads over the rows; u_b (n² entries) is read K times from L2.
+// with_anti: also −½ Σ_k γ_bk (lld_k[a] + lld_k[c]) u[a,c] (the anticommutator, when it was kept out of the GEMM operand).
+__global__ void lindblad_mono_sandwich_kernel(int n, int K, const int32_t* __restrict__ perm, const c128* __restrict__ val,
+                                              const double* __restrict__ lld, const double* __restrict__ gamma, int gamma_ld,
+                                              const c128* __restrict__ u, c128* __restrict__ du, int with_anti) {
+    const int cc = blockIdx.x;
+    const long long b = blockIdx.y, nn = (long long)n * n;
+    const c128* ub = u + b * nn;
+    c128* dub = du + b * nn;
+    const double* g = gamma + b * gamma_ld;
+    for (int a = threadIdx.x; a < n; a += blockDim.x) {
+        double sr = 0.0, si = 0.0, anti = 0.0;
+        for (int k = 0; k < K; ++k) {
+            const int pc = perm[(size_t)k * n + cc], pa = perm[(size_t)k * n + a];
+            const double gk = g[k];
+            if (with_anti) anti = fma(-0.5 * gk, lld[(size_t)k * n + a] + lld[(size_t)k * n + cc], anti);
+            if (pc < 0 || pa < 0) continue;
+            const c128 va = val[(size_t)k * n + a], vc = val[(size_t)k * n + cc];
+            const double wr = gk * (va.x * vc.x + va.y * vc.y), wi = gk * (va.y * vc.x - va.x * vc.y);  // γ v_a conj(v_c)
+            const c128 x = ub[pa + (long long)pc * n];
+            sr = fma(wr, x.x, sr); sr = fma(-wi, x.y, sr);
+            si = fma(wr, x.y, si); si = fma(wi, x.x, si);
+        }
+        const long long e = a + (long long)cc * n;
+        c128 o = dub[e];
+        if (with_anti) {
+            const c128 x = ub[e];
+            sr = fma(anti, x.x, sr);
+            si = fma(anti, x.y, si);
+        }
+        o.x += sr;
+        o.y += si;
+        dub[e] = o;
+    }
+}
+
+// He[b][a,a] += Σ_k coef[b][k]·lld_k[a]   (monomial L_k: L_k'L_k is diagonal)
+__global__ void heff_lld_add_kernel(int n, int K, const double* __restrict__ lld, const c128* __restrict__ coef, long long coef_ld,
+                                    c128* __restrict__ He, long long strideHe) {
+    const int b = blockIdx.y;
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= n) return;
+    double sr = 0.0, si = 0.0;
+    for (int k = 0; k < K; ++k) {
+        const double m2 = lld[(size_t)k * n + a];
+        const c128 cf = coef[(size_t)b * coef_ld + k];
+        sr = fma(cf.x, m2, sr);
+        si = fma(cf.y, m2, si);
+    }
+    c128* h = He + (long long)b * strideHe + a + (long long)a * n;
+    c128 v = *h;
+    v.x += sr;
+    v.y += si;
+    *h = v;
+}
+
 // He[b][a,a] += Σ_k coef[b][k]·|d_k[a]|²  — the L_k'L_k part of H_eff for diagonal L_k (coef already carries −(i/2)γ_bk or −½γ_bk)
 __global__ void heff_diag_add_kernel(int n, int K, const c128* __restrict__ ldiag, const c128* __restrict__ coef, long long coef_ld,
                                      c128* __restrict__ He, long long strideHe) {
@@ -256,7 +318,8 @@ int dense_rhs_impl(oqb_dense* op, int nb, const double* coefH, int coef_shared, 
     // per-member rates keep the K diagonals in shared memory (K·n ≤ 13 300: K = 12 at 10 qubits)
     const bool can_fuse = K > 0 && op->d_ldiag && !no_diag && gamma_shared && c->opt.lindblad_fuse;
     const bool use_diag = K > 0 && op->d_ldiag && !no_diag && (can_fuse || diag_sm <= 208 * 1024);
-    const int Kws = use_diag ? 0 : K;  // the Hadamard form of the sandwich needs no L_k u scratch
+    const bool use_mono = K > 0 && !use_diag && op->d_mperm && c->opt.lindblad_mono;
+    const int Kws = (use_diag || use_mono) ? 0 : K;  // the Hadamard / gather forms of the sandwich need no L_k u scratch
     const size_t per = (size_t)(1 + Kws) * nn * sizeof(c128);
     int chunk = (int)(kWorkspaceBudget / per);
     if (chunk < 1) chunk = 1;
@@ -314,7 +377,7 @@ int dense_rhs_impl(oqb_dense* op, int nb, const double* coefH, int coef_shared, 
 
     // diagonal L_k: L_k'L_k = diag|d_k|² — assemble H_eff from the Hamiltonian terms only and add the diagonal afterwards
     // (the per-member lincomb then reads nterms matrices instead of nterms + K)
-    const bool diag_heff = use_diag && with_h;
+    const bool diag_heff = (use_diag || use_mono) && with_h;
     const int nlin = diag_heff ? op->nterms : nmat;
     // real Hamiltonian terms: keep the (imaginary) L'L diagonal out of the operand — it moves into the Hadamard pass —
     // and run both products with the real-operand kernel; without Lindblad operators the operand is H(s) itself
@@ -325,8 +388,12 @@ int dense_rhs_impl(oqb_dense* op, int nb, const double* coefH, int coef_shared, 
             for (int m0 = 0; m0 < cnt; m0 += 65535) {
                 const int mc = cnt - m0 < 65535 ? cnt - m0 : 65535;
                 dim3 grid((unsigned)((n + 255) / 256), mc);
-                heff_diag_add_kernel<<<grid, 256, 0, c->stream>>>((int)n, K, op->d_ldiag, cf + op->nterms + (long long)m0 * cf_ld, cf_ld,
-                                                                  He + (long long)m0 * nn, nn);
+                if (use_mono)
+                    heff_lld_add_kernel<<<grid, 256, 0, c->stream>>>((int)n, K, op->d_mlld, cf + op->nterms + (long long)m0 * cf_ld, cf_ld,
+                                                                     He + (long long)m0 * nn, nn);
+                else
+                    heff_diag_add_kernel<<<grid, 256, 0, c->stream>>>((int)n, K, op->d_ldiag, cf + op->nterms + (long long)m0 * cf_ld, cf_ld,
+                                                                      He + (long long)m0 * nn, nn);
                 OQB_LAUNCH_CHECK(c);
             }
         }
@@ -380,6 +447,15 @@ int dense_rhs_impl(oqb_dense* op, int nb, const double* coefH, int coef_shared, 
                     dim3 grid(tiles, mc);
                     lindblad_diag_sandwich_kernel<<<grid, 256, sm, c->stream>>>(
                         (int)n, K, op->d_ldiag, dg + (gamma_shared ? 0 : (long long)m0 * K), gamma_shared ? 0 : K,
+                        ub + (long long)m0 * nn, dub + (long long)m0 * nn, real_h ? 1 : 0);
+                    OQB_LAUNCH_CHECK(c);
+                }
+            } else if (use_mono) {
+                for (int m0 = 0; m0 < cnt; m0 += 65535) {
+                    const int mc = cnt - m0 < 65535 ? cnt - m0 : 65535;
+                    dim3 grid((unsigned)n, mc);
+                    lindblad_mono_sandwich_kernel<<<grid, 256, 0, c->stream>>>(
+                        (int)n, K, op->d_mperm, op->d_mval, op->d_mlld, dg + (gamma_shared ? 0 : (long long)m0 * K), gamma_shared ? 0 : K,
                         ub + (long long)m0 * nn, dub + (long long)m0 * nn, real_h ? 1 : 0);
                     OQB_LAUNCH_CHECK(c);
                 }
@@ -466,6 +542,37 @@ int oqb_dense_create(oqb_ctx* c, int n, int nterms, const void* h_mats, int K, c
             if (cudaMalloc((void**)&op->d_ldiag, d.size() * sizeof(c128)) != cudaSuccess) { oqb_dense_destroy(op); return set_error(c, OQB_ENOMEM, "oqb_dense_create: cudaMalloc failed"); }
             OQB_CUDA(c, cudaMemcpyAsync(op->d_ldiag, d.data(), d.size() * sizeof(c128), cudaMemcpyHostToDevice, c->stream));
             OQB_CUDA(c, cudaStreamSynchronize(c->stream));
+        } else {
+            // monomial operators: at most one entry per row and per column
+            std::vector<int32_t> perm((size_t)K * n, -1);
+            std::vector<c128> val((size_t)K * n, make_double2(0.0, 0.0));
+            std::vector<double> lld((size_t)K * n, 0.0);
+            bool mono = true;
+            for (long long k = 0; k < K && mono; ++k) {
+                std::vector<char> col_used(n, 0);
+                for (int j = 0; j < n && mono; ++j)          // column j of the column-major block
+                    for (int r = 0; r < n && mono; ++r) {
+                        const c128 v = L[k * nn + (size_t)j * n + r];
+                        if (v.x == 0.0 && v.y == 0.0) continue;
+                        if (perm[k * n + r] >= 0 || col_used[j]) { mono = false; break; }
+                        perm[k * n + r] = j;
+                        val[k * n + r] = v;
+                        col_used[j] = 1;
+                        lld[k * n + j] = v.x * v.x + v.y * v.y;
+                    }
+            }
+            if (mono) {
+                if (cudaMalloc((void**)&op->d_mperm, perm.size() * sizeof(int32_t)) != cudaSuccess ||
+                    cudaMalloc((void**)&op->d_mval, val.size() * sizeof(c128)) != cudaSuccess ||
+                    cudaMalloc((void**)&op->d_mlld, lld.size() * sizeof(double)) != cudaSuccess) {
+                    oqb_dense_destroy(op);
+                    return set_error(c, OQB_ENOMEM, "oqb_dense_create: cudaMalloc failed");
+                }
+                OQB_CUDA(c, cudaMemcpyAsync(op->d_mperm, perm.data(), perm.size() * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+                OQB_CUDA(c, cudaMemcpyAsync(op->d_mval, val.data(), val.size() * sizeof(c128), cudaMemcpyHostToDevice, c->stream));
+                OQB_CUDA(c, cudaMemcpyAsync(op->d_mlld, lld.data(), lld.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+                OQB_CUDA(c, cudaStreamSynchronize(c->stream));
+            }
         }
     }
     OQB_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -480,6 +587,9 @@ int oqb_dense_destroy(oqb_dense* op) {
     if (op->d_mats) cudaFree(op->d_mats);
     if (op->d_lops) cudaFree(op->d_lops);
     if (op->d_ldiag) cudaFree(op->d_ldiag);
+    if (op->d_mperm) cudaFree(op->d_mperm);
+    if (op->d_mval) cudaFree(op->d_mval);
+    if (op->d_mlld) cudaFree(op->d_mlld);
     if (op->d_hdiag) cudaFree(op->d_hdiag);
     delete op;
     return OQB_OK;

@@ -163,3 +163,77 @@ def test_ten_qubit_dephasing_takes_the_diagonal_route(Q, K, rates):
         assert gemm_flops_per_rho <= 2.01, gemm_flops_per_rho     # 2 products per ρ
     else:
         assert gemm_flops_per_rho >= 2 * K, gemm_flops_per_rho    # the general route: 2 + 2K products per ρ
+
+
+def _sigma_minus(nq, q):
+    """σ⁻ on qubit q (1-based, qubit 1 = most significant bit) as a dense 2^nq matrix: |0⟩⟨1| on that qubit."""
+    n = 1 << nq
+    idx = np.arange(n)
+    bit = 1 << (nq - q)
+    L = np.zeros((n, n), dtype=complex)
+    src = idx[(idx & bit) != 0]
+    L[src ^ bit, src] = 1.0
+    return L
+
+
+@pytest.mark.parametrize("kind", ["amplitude_damping", "pauli_channel", "random_partial_permutation", "mixed_with_dephasing"])
+@pytest.mark.parametrize("nq,nb", [(3, 5), (6, 4), (8, 3)])
+@pytest.mark.parametrize("real_h", [True, False])
+def test_monomial_operators_take_the_gather_route(Q, kind, nq, nb, real_h):
+    """L_k with at most one entry per row and per column (σ⁻: amplitude damping; Pauli X/Y strings; any partial permutation
+    with phases): L_k ρ L_k' is a gather of ρ and L_k'L_k is diagonal — 2 products per ρ instead of 2 + 2K.  Against the
+    oracle's literal loop (src/opensys/lindblad.jl:94-101) and against the general route (option lindblad_mono = 0)."""
+    import ctypes as C
+    n = 1 << nq
+    rng = np.random.default_rng(nq * 11 + nb + len(kind) + real_h)
+    if kind == "amplitude_damping":
+        Ls = [_sigma_minus(nq, q) for q in range(1, nq + 1)]
+    elif kind == "pauli_channel":
+        X = np.array([[0, 1], [1, 0]], dtype=complex); Y = np.array([[0, -1j], [1j, 0]]); I2 = np.eye(2, dtype=complex)
+        def on(P, q):
+            m = np.eye(1, dtype=complex)
+            for j in range(1, nq + 1):
+                m = np.kron(m, P if j == q else I2)
+            return m
+        Ls = [on(X, 1), on(Y, nq), on(X, 1) @ on(Y, 2)]
+    elif kind == "random_partial_permutation":
+        Ls = []
+        for _ in range(3):
+            L = np.zeros((n, n), dtype=complex)
+            rows = rng.permutation(n)[: n - n // 4]
+            cols = rng.permutation(n)[: n - n // 4]
+            L[rows, cols] = rand_c(rng, n - n // 4)
+            Ls.append(L)
+    else:
+        idx = np.arange(n)
+        Ls = [_sigma_minus(nq, 1), np.diag(1.0 - 2.0 * ((idx >> (nq - 2)) & 1)).astype(complex), _sigma_minus(nq, nq).conj().T]
+    K = len(Ls)
+    herm = (lambda g: (g + g.T).astype(complex)) if real_h else (lambda g: g + g.conj().T)
+    m1 = herm(rng.standard_normal((n, n)) if real_h else rand_c(rng, n, n))
+    m2 = np.diag(rng.standard_normal(n)).astype(complex)
+    fs = [lambda s: 1 - s, lambda s: s]
+    gfs = [(lambda s, k=k: 0.1 * (1 + k) * (1 + 0.5 * s)) for k in range(K)]
+    opg = Q.DiffEqLiouvillian(Q.DenseHamiltonian(fs, [m1, m2], unit="ħ"), [], [Q.LindbladLiouvillian([Q.Lindblad(g, L) for g, L in zip(gfs, Ls)])], n)
+    opo = O.DiffEqLiouvillian(O.DenseHamiltonian(fs, [m1, m2], unit="ħ"), [], [O.LindbladLiouvillian([O.Lindblad(g, L) for g, L in zip(gfs, Ls)])], n)
+    u = rand_c(rng, nb, n, n)
+    t = rng.random(nb) * 10.0
+    p = Q.ODEParams(None, 10.0)
+    ref = np.stack([opo.rhs(u[b], O.ODEParams(None, 10.0), t[b]) for b in range(nb)])
+    ctx = Q.get_context()
+    opg(np.zeros_like(u), u, p, t)  # builds the device operator
+    ctx.check(ctx.lib.oqb_profile_begin(ctx.h))
+    got = opg(np.zeros_like(u), u, p, t)
+    ms, nl, fl = C.c_double(), C.c_uint64(), C.c_double()
+    ctx.check(ctx.lib.oqb_profile_end(ctx.h, C.byref(ms), C.byref(nl), C.byref(fl)))
+    assert relerr(got, ref) < TOL
+    assert fl.value / nb / (8.0 * n ** 3) <= 2.01  # two products per ρ
+    with ctx.option("lindblad_mono", 0):
+        plain = opg(np.zeros_like(u), u, p, t)
+    assert relerr(plain, ref) < TOL and relerr(got, plain) < 1e-12
+    # the accumulate-only Lindblad form and shared s
+    acc0 = rand_c(rng, nb, n, n)
+    lg, lo = opg._lind[0], opo.opensys[0] if hasattr(opo, "opensys") else None
+    d2 = lg(acc0.copy(), u, p, 2.5)
+    if lo is not None:
+        ref2 = np.stack([lo.rhs_acc(acc0[b].copy(), u[b], O.ODEParams(None, 10.0), 2.5) for b in range(nb)])
+        assert relerr(d2, ref2) < TOL
