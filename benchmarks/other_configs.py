@@ -490,6 +490,48 @@ def run_c5(Q, torch, steps):
                          "frac": ach / dmma, "frac_executed": ach * _exec_ratio() / dmma, "kernel_share_of_step": zms.value / ((3 + steps) * ms), "peak_source": "DMMA issue probe, this run"}}
 
 
+def run_c5_sigmax(Q, torch, steps, mono=True):
+    """C5 with TRANSVERSE couplings S_α = X_α (monomial: one entry per row and column) instead of Z_α: the apply with the
+    gather form of S M − M S (oqb_redfield_apply_mono_acc: K products per schedule) or, mono=False, the general 3K products."""
+    nq, n, K, B = 7, 128, 7, 1024
+    Hd, Hp, z = tfim_dense(nq)
+    idx = np.arange(n)
+    S = []
+    for q in range(nq):
+        m = np.zeros((n, n), dtype=complex)
+        m[idx ^ (1 << (nq - 1 - q)), idx] = 1.0
+        S.append(m)
+    H = Q.DenseHamiltonian([lambda s: 1 - s, lambda s: s], [Hd, Hp], unit="ħ")
+    ctx = Q.get_context()
+    g = rand_states(torch, B, n, 16, 5000)
+    rho = g.transpose(1, 2) @ g.conj()
+    rho = rho / torch.diagonal(rho, dim1=1, dim2=2).sum(-1).real[:, None, None]
+    u = Q.DeviceBatch(B, n, n, ctx, rho.contiguous())
+    du = u.zeros_like()
+    Lam = Q.DeviceBatch(B * K, n, n, ctx, rand_states(torch, B * K, n, n, 5001) / n)
+    Sd = Q.DeviceBatch.from_host(np.stack(S), ctx)
+    perm = np.stack([np.nonzero(x)[1][np.argsort(np.nonzero(x)[0])] for x in S]).astype(np.int32)   # row a -> its column
+    pinv = np.stack([np.nonzero(x)[0][np.argsort(np.nonzero(x)[1])] for x in S]).astype(np.int32)   # column c -> its row
+    dperm, dpinv = torch.as_tensor(perm, device="cuda"), torch.as_tensor(pinv, device="cuda")
+    dval = Q.DeviceBatch.from_host(np.ones((K, n), dtype=complex), ctx)
+    pw = 0.5 + 1.5 * np.arange(B) / B
+    s = 0.37 ** pw
+
+    def fn():
+        H.commutator(du, u, s)
+        if mono:
+            ctx.check(ctx.lib.oqb_redfield_apply_mono_acc(ctx.h, n, K, C.c_void_p(dperm.data_ptr()), C.c_void_p(dpinv.data_ptr()), dval.ptr,
+                                                          Lam.ptr, B, u.ptr, du.ptr))
+        else:
+            ctx.check(ctx.lib.oqb_redfield_apply_acc(ctx.h, n, K, Sd.ptr, 1 | 2, Lam.ptr, B, u.ptr, du.ptr))
+    fn()
+    ms = timed(fn, steps, 3, torch)
+    return {"config": "C5-per-GPU-sigmax" + ("-mono" if mono else "-general"),
+            "workload": f"{B} schedules x 7-qubit Redfield RHS with transverse couplings X_α (commutator + apply, supplied Lambda), n={n}, K={K}: "
+                        + ("monomial couplings as gathers, K GEMMs per schedule" if mono else "general route, 3K GEMMs per schedule"),
+            "metric": "rho_rhs_evals_per_sec", "value": B / (ms * 1e-3), "ms_per_step": ms}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--configs", default="c2,c2general,c2dense,c2prime,c2prime_diag,c3onesided,c4,c5,c5general")
@@ -506,6 +548,10 @@ def main():
                                  env=env, capture_output=True, text=True)
             sys.stderr.write(out.stderr[-2000:])
             print(out.stdout.strip().splitlines()[-1], flush=True)
+            continue
+        if c in ("c5sigmax", "c5sigmax_general"):
+            print(json.dumps(run_c5_sigmax(Q, torch, args.steps, mono=c == "c5sigmax")), flush=True)
+            torch.cuda.empty_cache()
             continue
         if c == "c2general":  # same operators, diagonal structure NOT exploited
             with Q.get_context().option("lindblad_diag", 0):

@@ -62,6 +62,7 @@ int oqb_launch_count(const oqb_ctx* ctx, uint64_t* n); /* kernels launched throu
  *   "zgemm_3m" (1), "real_operand" (1)        — as oqb_set_zgemm_mode / oqb_set_real_operand_mode below
  *   "zgemm_tma" (1)  0 = cp.async ZGEMM only;  "zgemm_bm" (0) 64/128 force the CTA tile height;  "tma_oneshot" (1)
  *   "lindblad_diag" (1), "coupling_diag" (1)   — treat diagonal L_k / couplings as general dense matrices when 0
+ *   "coupling_mono" (1)  consulted by host bindings: route monomial Redfield couplings to oqb_redfield_apply_mono_acc
  *   "lindblad_mono" (1)  monomial L_k (one entry per row and column: sigma+-, Pauli strings): gather of rho instead of 2K products
  *   "lindblad_fuse" (1)  diagonal L_k with rates shared by the batch: one n×n factor G per call and du += G∘u as a streaming pass
  *   "lindblad_split" (1) … and one off-diagonal Hamiltonian term: shared-operand products scaled by f_N(s_b), diagonal terms in that pass
@@ -155,6 +156,12 @@ int oqb_redfield_apply_acc(oqb_ctx* ctx, int n, int K, const void* d_S, int S_sh
  * member instead of 3K.  d_Sdiag: K×n complex diagonals (device).  Its own roofline row. */
 int oqb_redfield_apply_diag_acc(oqb_ctx* ctx, int n, int K, const void* d_Sdiag, const void* d_Lambda, int nb,
                                 const void* d_u, void* d_du);
+/* The same for MONOMIAL couplings (at most one entry per row and per column: σx, σy, σ±, Pauli strings):
+ * S_α[a, perm_α[a]] = val_α[a] (perm −1 = empty row), pinv_α[c] = the row holding column c's entry (−1 = none); all K×n,
+ * on the device.  (S_αM − MS_α)[a,c] = val_α[a]·M[perm_α[a], c] − M[a, pinv_α[c]]·val_α[pinv_α[c]] with M = Λ_α u: two
+ * gathers instead of two products — K GEMMs per member instead of 3K (src/opensys/redfield.jl:57-64). */
+int oqb_redfield_apply_mono_acc(oqb_ctx* ctx, int n, int K, const int32_t* d_perm, const int32_t* d_pinv, const void* d_val,
+                                const void* d_Lambda, int nb, const void* d_u, void* d_du);
 /* cache[b] (n²×n²) −= I⊗SΛ + conj(SΛ)⊗I − Sᵀ⊗Λ − conj(Λ)⊗S   (ACCUMULATES)
  *   — update_vectorized_cache!(cache, R::RedfieldLiouvillian, p, t) src/opensys/redfield.jl:97-102 */
 int oqb_redfield_vectorized_acc(oqb_ctx* ctx, int n, int K, const void* d_S, int S_shared,

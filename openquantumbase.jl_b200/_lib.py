@@ -46,6 +46,7 @@ SIGNATURES = {
     "oqb_lindblad_acc": [c_void_p, c_int, c_dp, c_int, c_void_p, c_void_p],
     "oqb_redfield_apply_acc": [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p],
     "oqb_redfield_apply_diag_acc": [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p],
+    "oqb_redfield_apply_mono_acc": [c_void_p, C.c_int, C.c_int, c_void_p, c_void_p, c_void_p, c_void_p, C.c_int, c_void_p, c_void_p],
     "oqb_redfield_vectorized_acc": [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p],
     "oqb_lambda_create": [c_void_p, c_int, c_int, c_void_p, C.POINTER(c_void_p)],
     "oqb_lambda_destroy": [c_void_p],

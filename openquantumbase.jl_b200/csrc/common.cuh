@@ -21,6 +21,7 @@ struct Options {
     int tma_oneshot = 1;      // one-instruction 5-D operand tiles
     int lindblad_fuse = 1;    // diagonal L_k with shared rates: one n×n factor G for the whole batch, du += G∘u as a pure streaming pass
     int lindblad_split = 1;   // … and one off-diagonal Hamiltonian term: shared-operand products scaled by f_N(s_b), diagonal terms in the Hadamard pass
+    int coupling_mono = 1;    // Redfield: monomial couplings (σx, σ±, Pauli strings) as gathers (host mirrors consult it when choosing the entry point)
     int lindblad_mono = 1;    // exploit monomial L_k (one entry per row and column: σ±, Pauli strings): gather instead of 2K products
     int lindblad_diag = 1;    // exploit diagonal L_k
     int coupling_diag = 1;    // exploit diagonal couplings in the rotation v'c_αv
@@ -267,6 +268,8 @@ int extract_diag(Ctx* c, int l, const c128* R, c128* pop, int nb);
 int add_adjoint(Ctx* c, int l, int nk, double alpha, const c128* Kb, c128* X, int nb);
 // X[b] −= K₂ + K₂',  K₂[i,j] = Σ_k (s_k[i] − s_k[j])·Mb[(b*nk+k)][i,j]   (Redfield apply, diagonal couplings)
 int redfield_diag_combine(Ctx* c, int l, int nk, const c128* sdiag, const c128* Mb, c128* X, int nb);
+// the same for monomial couplings S_k[a, perm_k[a]] = val_k[a] (pinv_k[c] = row of column c's entry, −1 = none)
+int redfield_mono_combine(Ctx* c, int l, int nk, const int32_t* perm, const int32_t* pinv, const c128* val, const c128* Mb, c128* X, int nb);
 // Davies tables from rotated couplings A (K l×l), gam/S (l×l real), w (l):
 //   Gam[b], hls[b] (column sums), Wt (l×l, transposed, zero diagonal), Cm (l×l complex)
 int davies_tables(Ctx* c, int l, int K, const c128* A, const double* gam, const double* S,

@@ -746,6 +746,32 @@ int oqb_redfield_apply_diag_acc(oqb_ctx* c, int n, int K, const void* d_Sdiag, c
     return 0;
 }
 
+int oqb_redfield_apply_mono_acc(oqb_ctx* c, int n, int K, const int32_t* d_perm, const int32_t* d_pinv, const void* d_val,
+                                const void* d_Lambda, int nb, const void* d_u, void* d_du) {
+    OQB_DEVICE(c, c);
+    if (nb <= 0 || K <= 0) return 0;
+    if (!d_perm || !d_pinv || !d_val || !d_Lambda || !d_u || !d_du) return set_error(c, OQB_EINVAL, "oqb_redfield_apply_mono_acc: null argument");
+    const long long nn = (long long)n * n;
+    const size_t per = (size_t)K * nn * sizeof(c128);
+    int chunk = (int)(kWorkspaceBudget / per);
+    if (chunk < 1) chunk = 1;
+    if (chunk > nb) chunk = nb;
+    chunk = (nb + (nb + chunk - 1) / chunk - 1) / ((nb + chunk - 1) / chunk);  // balance the chunks
+    OQB_TRY(ws_reserve(c, (size_t)chunk * per));
+    c128* M1 = (c128*)c->ws;
+    for (int b0 = 0; b0 < nb; b0 += chunk) {
+        const int cnt = nb - b0 < chunk ? nb - b0 : chunk;
+        ZgemmParams p;  // M1[b,α] = Λ[b,α] u_b
+        p.M = p.N = p.K = n; p.batch = cnt; p.batch2 = K;
+        p.A = (const c128*)d_Lambda + (long long)b0 * K * nn; p.lda = n; p.strideA = K * nn; p.strideA2 = nn;
+        p.B = (const c128*)d_u + (long long)b0 * nn; p.ldb = n; p.strideB = nn; p.strideB2 = 0;
+        p.C = M1; p.ldc = n; p.strideC = K * nn; p.strideC2 = nn;
+        OQB_TRY(zgemm(c, p));
+        OQB_TRY(redfield_mono_combine(c, n, K, d_perm, d_pinv, (const c128*)d_val, M1, (c128*)d_du + (long long)b0 * nn, cnt));
+    }
+    return 0;
+}
+
 int oqb_redfield_vectorized_acc(oqb_ctx* c, int n, int K, const void* d_S, int S_shared, const void* d_Lambda,
                                 int nb, void* d_cache) {
     OQB_DEVICE(c, c);

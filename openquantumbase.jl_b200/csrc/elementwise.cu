@@ -274,6 +274,76 @@ int redfield_diag_combine(Ctx* c, int l, int nk, const c128* sdiag, const c128* 
     return 0;
 }
 
+// Redfield apply with MONOMIAL couplings (at most one entry per row and per column: σx, σy, σ±, Pauli strings):
+// S_k[a, π_k(a)] = v_k[a], r_k(c) = the row holding column c's entry.  (S_k M_k − M_k S_k)[a,c] = v_k[a]·M_k[π_k(a), c] − M_k[a, r_k(c)]·v_k[r_k(c)]
+// — two gathers per block instead of two n³ products; X −= K₂ + K₂' as in the diagonal kernel (32x32 tiles, adjoint through
+// shared memory).
+__global__ void redfield_mono_combine_kernel(int l, int nk, const int32_t* __restrict__ perm, const int32_t* __restrict__ pinv,
+                                             const c128* __restrict__ val, const c128* __restrict__ Mb, c128* __restrict__ X) {
+    __shared__ c128 tile[32][33];
+    const int b = blockIdx.z;
+    const int i0 = blockIdx.x * 32, j0 = blockIdx.y * 32;
+    const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
+    c128 acc[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) acc[r] = make_double2(0.0, 0.0);
+    for (int k = 0; k < nk; ++k) {
+        const c128* Km = Mb + ((long long)b * nk + k) * l * l;
+        const int32_t* pk = perm + (long long)k * l;
+        const int32_t* rk = pinv + (long long)k * l;
+        const c128* vk = val + (long long)k * l;
+        auto k2 = [&](int a, int cc) -> c128 {  // (S_k M_k − M_k S_k)[a, cc]
+            c128 o = make_double2(0.0, 0.0);
+            const int pa = pk[a], rc = rk[cc];
+            if (pa >= 0) o = cmul(vk[a], Km[pa + (long long)cc * l]);
+            if (rc >= 0) {
+                const c128 t = cmul(Km[a + (long long)rc * l], vk[rc]);
+                o.x -= t.x;
+                o.y -= t.y;
+            }
+            return o;
+        };
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {  // transposed block: element (jj, ii)
+            const int jj = j0 + tx, ii = i0 + ty + r * 8;
+            tile[ty + r * 8][tx] = (jj < l && ii < l) ? k2(jj, ii) : make_double2(0.0, 0.0);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int i = i0 + tx, j = j0 + ty + r * 8;
+            if (i < l && j < l) {
+                const c128 d = k2(i, j);
+                const c128 tt = tile[tx][ty + r * 8];  // = K₂_k[j, i]
+                acc[r].x += d.x + tt.x;
+                acc[r].y += d.y - tt.y;
+            }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int i = i0 + tx, j = j0 + ty + r * 8;
+        if (i < l && j < l) {
+            c128* d = X + (long long)b * l * l + i + (long long)j * l;
+            c128 v = *d;
+            v.x -= acc[r].x;
+            v.y -= acc[r].y;
+            *d = v;
+        }
+    }
+}
+int redfield_mono_combine(Ctx* c, int l, int nk, const int32_t* perm, const int32_t* pinv, const c128* val, const c128* Mb, c128* X, int nb) {
+    if (nb <= 0) return 0;
+    for (int b0 = 0; b0 < nb; b0 += 65535) {
+        const int cnt = nb - b0 < 65535 ? nb - b0 : 65535;
+        dim3 grid(cdiv(l, 32), cdiv(l, 32), cnt), block(32, 8);
+        redfield_mono_combine_kernel<<<grid, block, 0, c->stream>>>(l, nk, perm, pinv, val, Mb + (long long)b0 * nk * l * l, X + (long long)b0 * l * l);
+        OQB_LAUNCH_CHECK(c);
+    }
+    return 0;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Davies tables (per distinct s, shared by the batch).  One block per column b for the sums.
 // ---------------------------------------------------------------------------------------------

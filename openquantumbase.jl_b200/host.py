@@ -42,6 +42,12 @@ _ENV_OPTIONS = {
 }
 
 
+def _is_monomial(x) -> bool:
+    """At most one non-zero entry per row and per column (σx, σy, σ±, Pauli strings, partial permutations with phases)."""
+    nz = x != 0
+    return bool(np.all(nz.sum(axis=0) <= 1) and np.all(nz.sum(axis=1) <= 1))
+
+
 _SPECTRUM_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int64, C.POINTER(C.c_double), C.POINTER(C.c_double))  # oqb_spectrum_fn
 
 
@@ -1611,6 +1617,20 @@ class RedfieldLiouvillian:
             # diagonal couplings: (S_αM − MS_α)[i,j] = (s_α[i] − s_α[j])·M[i,j] — K GEMMs + one elementwise pass
             Sdiag = DeviceBatch.from_host(np.stack([np.diag(x) for x in Sh]), ctx)  # (K, n) vectors
             ctx.check(ctx.lib.oqb_redfield_apply_diag_acc(ctx.h, n, K, Sdiag.ptr, Ld.ptr, B, io.u.ptr, io.du.ptr))
+        elif ctx.get_option("coupling_mono") and all(_is_monomial(x) for x in Sh):
+            # monomial couplings (σx, σy, σ±, Pauli strings): S M and M S are gathers of M = Λu — K GEMMs + one pass
+            import torch
+            perm = np.full((K, n), -1, dtype=np.int32)
+            pinv = np.full((K, n), -1, dtype=np.int32)
+            val = np.zeros((K, n), dtype=C128)
+            for k, x in enumerate(Sh):
+                r, c_ = np.nonzero(x)
+                perm[k, r], pinv[k, c_], val[k, r] = c_, r, x[r, c_]
+            dev = io.u.t.device
+            dperm, dpinv = torch.as_tensor(perm, device=dev), torch.as_tensor(pinv, device=dev)
+            dval = DeviceBatch.from_host(val, ctx)  # (K, n) vectors
+            ctx.check(ctx.lib.oqb_redfield_apply_mono_acc(ctx.h, n, K, C.c_void_p(dperm.data_ptr()), C.c_void_p(dpinv.data_ptr()), dval.ptr,
+                                                          Ld.ptr, B, io.u.ptr, io.du.ptr))
         else:
             Sd = DeviceBatch.from_host(np.stack(Sh), ctx)
             s_real = 2 if not any(np.any(np.imag(x)) for x in Sh) else 0  # real couplings: real-operand products
