@@ -309,6 +309,39 @@ function redfield_apply!(du::DeviceBatch, u::DeviceBatch, S::DeviceBatch, Λ::De
                      u.c, n, K, S.ptr, 1 | (real_couplings ? 2 : 0), Λ.ptr, size(u, 3), u.ptr, du.ptr))
 end
 
+"raw device copy of a host array (freed by the caller with oqb_free)"
+function device_copy(c, a::Array)
+    d = Ref{Ptr{Cvoid}}(C_NULL)
+    check(c, ccall((:oqb_malloc, LIB), Cint, (Ptr{Cvoid}, Csize_t, Ref{Ptr{Cvoid}}), c, sizeof(a), d))
+    check(c, ccall((:oqb_upload, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Csize_t), c, d[], a, sizeof(a)))
+    d[]
+end
+
+"The same with the couplings given as host matrices: diagonal S_α take the elementwise form, monomial ones (σx, σ±, Pauli strings: one entry per row and column) the gather form — K products per member instead of 3K"
+function redfield_apply!(du::DeviceBatch, u::DeviceBatch, S::Vector{<:AbstractMatrix}, Λ::DeviceBatch)
+    n, K, c = size(S[1], 1), length(S), u.c
+    if all(isdiag, S)
+        sd = DeviceBatch(c, reshape(ComplexF64[S[k][i, i] for i in 1:n, k in 1:K], n, 1, K))
+        return check(c, ccall((:oqb_redfield_apply_diag_acc, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{Cvoid}, Ptr{Cvoid}, Cint, Ptr{Cvoid}, Ptr{Cvoid}),
+                              c, n, K, sd.ptr, Λ.ptr, size(u, 3), u.ptr, du.ptr))
+    end
+    if all(m -> all(<=(1), count(!iszero, m; dims=1)) && all(<=(1), count(!iszero, m; dims=2)), S)
+        perm = fill(Int32(-1), n, K); pinv = fill(Int32(-1), n, K); val = zeros(ComplexF64, n, 1, K)
+        for k in 1:K, idx in findall(!iszero, S[k])
+            perm[idx[1], k] = idx[2] - 1; pinv[idx[2], k] = idx[1] - 1; val[idx[1], 1, k] = S[k][idx]
+        end
+        dperm, dpinv, dval = device_copy(c, perm), device_copy(c, pinv), DeviceBatch(c, val)
+        st = ccall((:oqb_redfield_apply_mono_acc, LIB), Cint,
+                   (Ptr{Cvoid}, Cint, Cint, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cint, Ptr{Cvoid}, Ptr{Cvoid}),
+                   c, n, K, dperm, dpinv, dval.ptr, Λ.ptr, size(u, 3), u.ptr, du.ptr)
+        ccall((:oqb_sync, LIB), Cint, (Ptr{Cvoid},), c)
+        ccall((:oqb_free, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), c, dperm); ccall((:oqb_free, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), c, dpinv)
+        return check(c, st)
+    end
+    Sd = DeviceBatch(c, reshape(reduce(hcat, [ComplexF64.(vec(m)) for m in S]), n, n, K))
+    redfield_apply!(du, u, Sd, Λ; real_couplings=all(m -> all(isreal, m), S))
+end
+
 # ---------------------------------------------------------------- trajectories (ψ ensembles, n×1×B)
 "dψ = (−iH(s_b) − ½Σγ_k L_k'L_k)ψ: the `cache*u` of the external solver with the cache of diffeq_liouvillian.jl:78-83"
 function traj_matvec!(dψ::DeviceBatch, Op::DiffEqLiouvillian{false,false}, ψ::DeviceBatch, p, t)
