@@ -154,8 +154,15 @@ def run_secondary(Q, torch, ctx):
         r["clocks"] = ck
         return r
     try:
+        # C2 as BASELINE words it.  The driver −ΣX is Pauli-structured, the problem term and the dephasing operators are diagonal:
+        # the library runs the whole RHS as one stencil + Hadamard pass (HBM row).  The same operators with that route off:
+        # 2 real-operand ZGEMMs + one Hadamard pass per rho (FP64 tensor row).
         r = clocked(lambda: OC.run_c2(Q, torch, 5, False))
-        out["C2_dephasing_diagL"] = short(r, ("config", "workload", "value", "ms_per_step", "roofline", "clocks"))
+        out["C2_dephasing_diagL"] = short(r, ("note", "config", "workload", "value", "ms_per_step", "roofline", "clocks"))
+        torch.cuda.empty_cache()
+        with ctx.option("lindblad_stencil", 0):
+            r = OC.run_c2(Q, torch, 3, False)
+        out["C2_dephasing_2gemm_route"] = short(r, ("config", "value", "ms_per_step", "roofline"))
         torch.cuda.empty_cache()
         with ctx.option("lindblad_diag", 0):
             r = OC.run_c2(Q, torch, 2, False)
@@ -164,6 +171,10 @@ def run_secondary(Q, torch, ctx):
         # north_star's "batched 10-qubit Lindblad RHS": the same operators at 10 qubits, 64 rho of 1024 x 1024
         r = OC.run_c2(Q, torch, 3, False, nq=10, B=64)
         out["C2prime_10q_dephasing"] = short(r, ("config", "workload", "value", "ms_per_step", "roofline"))
+        torch.cuda.empty_cache()
+        with ctx.option("lindblad_stencil", 0):
+            r = OC.run_c2(Q, torch, 3, False, nq=10, B=64)
+        out["C2prime_10q_dephasing_2gemm_route"] = short(r, ("config", "value", "ms_per_step", "roofline"))
         torch.cuda.empty_cache()
     except Exception as e:  # noqa: BLE001
         out["C2_error"] = f"{type(e).__name__}: {e}"

@@ -110,6 +110,20 @@ def run_c2(Q, torch, steps, dense_L, nq=8, B=4096, damping=False):
     # general L_k: 2 + 2K GEMMs per rho; diagonal L_k exploited (its own row): 2 GEMMs + one Hadamard pass
     flops = 8.0 * n ** 3 * ((2 if diag_path else 2 + 2 * K)) * B
     dmma, _ = ctx.probe_fp64()
+    if zfl.value == 0.0:
+        # no product launched: the Pauli-structured driver's commutator ran as a hypercube stencil fused with the Hadamard factor
+        # (lindblad_stencil_kernel) — an HBM-bound pass: read rho, write drho = 32 B per element
+        hbm, src = peaks()
+        gbs = 32.0 * n * n * B / 1e9 / (ms * 1e-3)
+        return {"note": "Pauli-structured driver (XOR diagonals) + diagonal problem terms + diagonal L_k with shared rates: the whole RHS is ONE pass "
+                        "(lindblad_stencil_kernel: commutator as a stencil over the driver's XOR diagonals, fused with the Hadamard factor) — no GEMM; "
+                        "option lindblad_stencil = 0 gives the 2-GEMM row",
+                "config": ("C2" if nq == 8 else "C2prime") + ("-damping" if damping else "-Zk") + "-stencil",
+                "workload": f"{nq}-qubit dense TFIM + {K} dense-stored {'sigma-minus_k' if damping else 'Z_k'} Lindblad ops, batch {B} of {n}x{n} rho, per-member s",
+                "metric": "rho_rhs_evals_per_sec", "value": B / (ms * 1e-3), "ms_per_step": ms,
+                "algorithmic_tflop_per_step": flops / 1e12, "step_tflops": flops / (ms * 1e-3) / 1e12,
+                "roofline": {"bound": "hbm", "kernel": "lindblad_stencil_kernel", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm,
+                             "algorithmic_bytes_per_step": 32.0 * n * n * B, "peak_source": src}}
     ach = zfl.value / (zms.value * 1e-3) / 1e12
     extra = {}
     if diag_path:

@@ -162,7 +162,7 @@ namespace {
 struct OptEntry { const char* name; int Options::* field; };
 const OptEntry kOpts[] = {
     {"zgemm_tma", &Options::zgemm_tma}, {"zgemm_bm", &Options::zgemm_bm}, {"tma_oneshot", &Options::tma_oneshot},
-    {"host_slots", &Options::host_slots}, {"lindblad_diag", &Options::lindblad_diag}, {"lindblad_fuse", &Options::lindblad_fuse}, {"lindblad_mono", &Options::lindblad_mono}, {"coupling_mono", &Options::coupling_mono}, {"lindblad_split", &Options::lindblad_split}, {"coupling_diag", &Options::coupling_diag}, {"traj_kernel", &Options::traj_kernel},
+    {"host_slots", &Options::host_slots}, {"lindblad_diag", &Options::lindblad_diag}, {"lindblad_fuse", &Options::lindblad_fuse}, {"lindblad_mono", &Options::lindblad_mono}, {"coupling_mono", &Options::coupling_mono}, {"lindblad_split", &Options::lindblad_split}, {"lindblad_stencil", &Options::lindblad_stencil}, {"coupling_diag", &Options::coupling_diag}, {"traj_kernel", &Options::traj_kernel},
     {"traj_ell", &Options::traj_ell}, {"sell_r", &Options::sell_r}, {"sell_unit", &Options::sell_unit}, {"rk_fuse", &Options::rk_fuse}, {"xor_fixed", &Options::xor_fixed}, {"xor_rows", &Options::xor_rows},
     {"ame_host_chunk_mib", &Options::ame_host_chunk_mib}, {"davies_dense_min_pairs", &Options::davies_dense_min_pairs},
     {"debug_checks", &Options::debug_checks}, {"fuse_cross", &Options::fuse_cross},

@@ -28,6 +28,13 @@ struct oqb_dense {
     int offdiag_term = -1;       // its index, −1 when the split does not apply
     bool offdiag_real = false;   // … and it has no imaginary part
     c128* d_hdiag = nullptr;     // nterms × n: the diagonals h_i (zero row for m_N)
+    // … and that term is a sum of Pauli strings stored densely (−ΣX drivers, XX catalysts, σy terms): its non-zeros sit on
+    // at most 16 XOR diagonals, m_N[r, r ^ mask_j] = xval_j[r] — the commutator with it is a stencil on the hypercube
+    int nxmask = 0;
+    int xmask[16] = {0};
+    int xconst[16] = {0};        // xval_j is one value for every row
+    c128 xcval[16] = {};
+    c128* d_xval = nullptr;      // nxmask × n
 };
 
 namespace {
@@ -228,6 +235,86 @@ __global__ void lindblad_mono_sandwich_kernel(int n, int K, const int32_t* __res
     }
 }
 
+// The whole split-form RHS in ONE pass when the off-diagonal Hamiltonian term is Pauli-structured (m_N[r, r^mask_j] = x_j[r]):
+//   du[r,c] = −i f_N(s_b) Σ_j (x_j[r]·u[r^mask_j, c] − u[r, c^mask_j]·x_j[c^mask_j]) + (G[r,c] − i Σ_i f_bi (h_i[r] − h_i[c]))·u[r,c]
+// — −i(Hu − uH) of src/hamiltonian/dense_hamiltonian.jl:84-89 with H = f_N m_N + Σ f_i diag(h_i), plus the diagonal-L_k
+// dissipator as the factor G.  One CTA per TS×TS tile of one ρ (TS = 64): partners whose mask lies inside the tile come
+// from shared memory, the others from global memory (coalesced: r^mask moves a warp's rows as a block); no product at all.
+struct StencilDesc {
+    int nmask, nt;
+    int mask[16], isconst[16];
+    double cre[16], cim[16];
+};
+__global__ void __launch_bounds__(256) lindblad_stencil_kernel(int n, int TS, const __grid_constant__ StencilDesc d,
+                                                               const c128* __restrict__ xval, const double* __restrict__ fn, int fn_shared,
+                                                               const c128* __restrict__ G, const c128* __restrict__ hdiag,
+                                                               const c128* __restrict__ coef, long long coef_ld, const c128* __restrict__ u,
+                                                               c128* __restrict__ du) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    c128* tile = reinterpret_cast<c128*>(smem_raw);  // [TS cols][TS rows]
+    __shared__ double sf[16];
+    const long long b = blockIdx.z, nn = (long long)n * n;
+    const int r0 = blockIdx.x * TS, c0 = blockIdx.y * TS;
+    const c128* ub = u + b * nn;
+    c128* dub = du + b * nn;
+    if (threadIdx.x < d.nt) sf[threadIdx.x] = coef[b * coef_ld + threadIdx.x].x;
+    // a thread keeps ONE row of the tile (TS ≤ 64 divides 256) and walks over columns: everything that depends on the row only
+    // — its diagonal-term values, its non-constant stencil values — is fetched once
+    const int rl = threadIdx.x & (TS - 1), cl0 = threadIdx.x / TS, cstep = blockDim.x / TS;
+    const int r = r0 + rl;
+    for (int cl = cl0; cl < TS; cl += cstep) tile[cl * TS + rl] = ub[r + (long long)(c0 + cl) * n];
+    __syncthreads();
+    const double f = fn[fn_shared ? 0 : b];
+    // −i Σ_i f_bi h_i[r]  (row part of the diagonal terms' commutator) as one complex number per thread
+    double hrr = 0.0, hri = 0.0;
+    for (int i = 0; i < d.nt; ++i) {
+        const c128 ha = hdiag[(size_t)i * n + r];
+        hrr = fma(sf[i], ha.y, hrr);
+        hri = fma(-sf[i], ha.x, hri);
+    }
+    for (int cl = cl0; cl < TS; cl += cstep) {
+        const int c = c0 + cl;
+        double ar = 0.0, ai = 0.0;
+#pragma unroll 4
+        for (int j = 0; j < d.nmask; ++j) {
+            const int m = d.mask[j];
+            c128 x1, x2;
+            if (m < TS) {
+                x1 = tile[cl * TS + (rl ^ m)];
+                x2 = tile[(cl ^ m) * TS + rl];
+            } else {
+                x1 = ub[(r ^ m) + (long long)c * n];
+                x2 = ub[r + (long long)(c ^ m) * n];
+            }
+            if (d.isconst[j]) {
+                const double vr_ = d.cre[j], vi_ = d.cim[j];
+                const double dx = x1.x - x2.x, dy = x1.y - x2.y;  // v·(x1 − x2)
+                ar += vr_ * dx - vi_ * dy;
+                ai += vr_ * dy + vi_ * dx;
+            } else {
+                const c128 vr = xval[(size_t)j * n + r], vc = xval[(size_t)j * n + (c ^ m)];
+                ar += (vr.x * x1.x - vr.y * x1.y) - (x2.x * vc.x - x2.y * vc.y);
+                ai += (vr.x * x1.y + vr.y * x1.x) - (x2.x * vc.y + x2.y * vc.x);
+            }
+        }
+        // −i f (ar + i ai) = f (ai − i ar)
+        double outr = f * ai, outi = -f * ar;
+        c128 g = G ? G[(long long)r + (long long)c * n] : make_double2(0.0, 0.0);
+        double hcr = 0.0, hci = 0.0;  // −i Σ_i f_bi h_i[c]
+        for (int i = 0; i < d.nt; ++i) {
+            const c128 hc = hdiag[(size_t)i * n + c];
+            hcr = fma(sf[i], hc.y, hcr);
+            hci = fma(-sf[i], hc.x, hci);
+        }
+        g.x += hrr - hcr;
+        g.y += hri - hci;
+        const c128 x0 = tile[cl * TS + rl];
+        outr += g.x * x0.x - g.y * x0.y;
+        outi += g.x * x0.y + g.y * x0.x;
+        dub[(long long)r + (long long)c * n] = make_double2(outr, outi);
+    }
+}
+
 // He[b][a,a] += Σ_k coef[b][k]·lld_k[a]   (monomial L_k: L_k'L_k is diagonal)
 __global__ void heff_lld_add_kernel(int n, int K, const double* __restrict__ lld, const c128* __restrict__ coef, long long coef_ld,
                                     c128* __restrict__ He, long long strideHe) {
@@ -341,6 +428,30 @@ int dense_rhs_impl(oqb_dense* op, int nb, const double* coefH, int coef_shared, 
         c128* G2 = (c128*)c->ws;  // the workspace was reserved for at least nn elements (he_elems ≥ nn)
         lindblad_diag_gmat_kernel<<<(unsigned)((nn + 255) / 256), 256, 0, c->stream>>>((int)n, K, op->d_ldiag, (const double*)d_gamma, 1, G2);
         OQB_LAUNCH_CHECK(c);
+        if (op->nxmask > 0 && op->nterms <= 16 && c->opt.lindblad_stencil) {
+            StencilDesc sd;
+            memset(&sd, 0, sizeof(sd));
+            sd.nmask = op->nxmask;
+            sd.nt = op->nterms;
+            for (int j = 0; j < op->nxmask; ++j) {
+                sd.mask[j] = op->xmask[j];
+                sd.isconst[j] = op->xconst[j];
+                sd.cre[j] = op->xcval[j].x;
+                sd.cim[j] = op->xcval[j].y;
+            }
+            const int TS = n >= 64 ? 64 : (int)n;
+            static DevOnce cfg;
+            if (!cfg.done(c->device)) { OQB_CUDA(c, cudaFuncSetAttribute(lindblad_stencil_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)); cfg.set(c->device); }
+            for (int m0 = 0; m0 < nb; m0 += 65535) {
+                const int mc = nb - m0 < 65535 ? nb - m0 : 65535;
+                dim3 grid((unsigned)(n / TS), (unsigned)(n / TS), mc);
+                lindblad_stencil_kernel<<<grid, 256, (size_t)TS * TS * sizeof(c128), c->stream>>>(
+                    (int)n, TS, sd, op->d_xval, d_fn + (coef_shared ? 0 : m0), coef_shared ? 1 : 0, G2, op->d_hdiag,
+                    (const c128*)d_coef + (rows == 1 ? 0 : (long long)m0 * nmat), rows == 1 ? 0 : nmat, u + (long long)m0 * nn, du + (long long)m0 * nn);
+                OQB_LAUNCH_CHECK(c);
+            }
+            return 0;
+        }
         const c128* mN = op->d_mats + (long long)op->offdiag_term * nn;
         const bool rN = op->offdiag_real && c->real_operand;
         ZgemmParams p;  // du = −i f_N(s_b) m_N u
@@ -511,6 +622,39 @@ int oqb_dense_create(oqb_ctx* c, int n, int nterms, const void* h_mats, int K, c
             if (cudaMalloc((void**)&op->d_hdiag, hd.size() * sizeof(c128)) != cudaSuccess) { oqb_dense_destroy(op); return set_error(c, OQB_ENOMEM, "oqb_dense_create: cudaMalloc failed"); }
             OQB_CUDA(c, cudaMemcpyAsync(op->d_hdiag, hd.data(), hd.size() * sizeof(c128), cudaMemcpyHostToDevice, c->stream));
             OQB_CUDA(c, cudaStreamSynchronize(c->stream));
+            // Pauli structure of that term: the XOR diagonals r ^ col of its non-zeros (≤ 16, n a power of two)
+            if ((n & (n - 1)) == 0 && n >= 2) {
+                std::vector<int> masks;
+                bool ok = true;
+                for (int j = 0; j < n && ok; ++j)
+                    for (int r = 0; r < n && ok; ++r) {
+                        const c128 v = Hm[last * nn + (size_t)j * n + r];
+                        if (v.x == 0.0 && v.y == 0.0) continue;
+                        const int m = r ^ j;
+                        if (std::find(masks.begin(), masks.end(), m) == masks.end()) {
+                            if (masks.size() >= 16) { ok = false; break; }
+                            masks.push_back(m);
+                        }
+                    }
+                if (ok && !masks.empty()) {
+                    std::sort(masks.begin(), masks.end());
+                    std::vector<c128> xv(masks.size() * (size_t)n);
+                    for (size_t q = 0; q < masks.size(); ++q) {
+                        bool cst = true;
+                        for (int r = 0; r < n; ++r) {
+                            xv[q * n + r] = Hm[last * nn + (size_t)(r ^ masks[q]) * n + r];  // element (row r, col r ^ mask)
+                            if (xv[q * n + r].x != xv[q * n].x || xv[q * n + r].y != xv[q * n].y) cst = false;
+                        }
+                        op->xmask[q] = masks[q];
+                        op->xconst[q] = cst ? 1 : 0;
+                        op->xcval[q] = xv[q * n];
+                    }
+                    if (cudaMalloc((void**)&op->d_xval, xv.size() * sizeof(c128)) != cudaSuccess) { oqb_dense_destroy(op); return set_error(c, OQB_ENOMEM, "oqb_dense_create: cudaMalloc failed"); }
+                    OQB_CUDA(c, cudaMemcpyAsync(op->d_xval, xv.data(), xv.size() * sizeof(c128), cudaMemcpyHostToDevice, c->stream));
+                    OQB_CUDA(c, cudaStreamSynchronize(c->stream));
+                    op->nxmask = (int)masks.size();
+                }
+            }
         }
     }
     if (K) {
@@ -587,6 +731,7 @@ int oqb_dense_destroy(oqb_dense* op) {
     if (op->d_mats) cudaFree(op->d_mats);
     if (op->d_lops) cudaFree(op->d_lops);
     if (op->d_ldiag) cudaFree(op->d_ldiag);
+    if (op->d_xval) cudaFree(op->d_xval);
     if (op->d_mperm) cudaFree(op->d_mperm);
     if (op->d_mval) cudaFree(op->d_mval);
     if (op->d_mlld) cudaFree(op->d_mlld);

@@ -286,3 +286,62 @@ def test_redfield_apply_with_monomial_couplings(Q, kind, nq, nb):
     with ctx.option("coupling_mono", 0):
         plain = rg.apply(du0.copy(), u, S, Lam)
     assert relerr(plain, ref) < TOL and relerr(got, plain) < 1e-12
+
+
+def _pauli_sum_dense(nq, strings):
+    P = {"X": np.array([[0, 1], [1, 0]], dtype=complex), "Y": np.array([[0, -1j], [1j, 0]]), "Z": np.array([[1, 0], [0, -1]], dtype=complex),
+         "I": np.eye(2, dtype=complex)}
+    n = 1 << nq
+    H = np.zeros((n, n), dtype=complex)
+    for cf, ops in strings:
+        m = np.eye(1, dtype=complex)
+        for q in range(1, nq + 1):
+            m = np.kron(m, P[ops.get(q, "I")])
+        H = H + cf * m
+    return H
+
+
+@pytest.mark.parametrize("driver", ["transverse_field", "xx_catalyst", "y_field", "xz_products"])
+@pytest.mark.parametrize("nq,nb", [(2, 3), (4, 5), (6, 4), (7, 3), (8, 5)])
+@pytest.mark.parametrize("per_member_s", [True, False])
+def test_pauli_structured_driver_takes_the_stencil_route(Q, driver, nq, nb, per_member_s):
+    """DenseHamiltonian whose one off-diagonal term is a sum of Pauli strings (−ΣX; + XX catalysts: two-bit masks; Y fields:
+    imaginary, row-signed entries; X·Z products: real, row-signed) + diagonal problem terms + dephasing: −i[H,ρ] is a
+    stencil over ≤ 16 XOR diagonals fused with the Hadamard factor — no product launched at all.  Against the oracle's
+    literal commutator + Lindblad loop and against the shared-operand product route (option lindblad_stencil = 0)."""
+    import ctypes as C
+    from oracle import fixtures as F
+    n = 1 << nq
+    rng = np.random.default_rng(nq * 19 + nb + len(driver) + per_member_s)
+    if driver == "transverse_field":
+        Hd = _pauli_sum_dense(nq, [(-1.0 - 0.1 * q, {q: "X"}) for q in range(1, nq + 1)])
+    elif driver == "xx_catalyst":
+        Hd = _pauli_sum_dense(nq, [(-1.0, {q: "X"}) for q in range(1, nq + 1)] + [(0.4, {q: "X", q + 1: "X"}) for q in range(1, nq)])
+    elif driver == "y_field":
+        Hd = _pauli_sum_dense(nq, [(0.7 + 0.1 * q, {q: "Y"}) for q in range(1, nq + 1)])
+    else:
+        Hd = _pauli_sum_dense(nq, [(-1.0, {q: "X"}) for q in range(1, nq + 1)] + [(0.3, {q: "X", (q % nq) + 1: "Z"}) for q in range(1, nq + 1) if nq > 1])
+    Hp = np.diag(rng.standard_normal(n)).astype(complex)
+    Hb = np.diag(rng.standard_normal(n)).astype(complex)
+    fs = [lambda s: 1 - s, lambda s: s, lambda s: 0.5 * s * s]
+    idx = np.arange(n)
+    Ls = [np.diag(1.0 - 2.0 * ((idx >> (nq - 1 - q)) & 1)).astype(complex) for q in range(nq)]
+    gam = [0.05 * (1 + k) for k in range(nq)]
+    opg = Q.DiffEqLiouvillian(Q.DenseHamiltonian(fs, [Hd, Hp, Hb], unit="ħ"), [], [Q.LindbladLiouvillian([Q.Lindblad(g, L) for g, L in zip(gam, Ls)])], n)
+    opo = O.DiffEqLiouvillian(O.DenseHamiltonian(fs, [Hd, Hp, Hb], unit="ħ"), [], [O.LindbladLiouvillian([O.Lindblad(g, L) for g, L in zip(gam, Ls)])], n)
+    u = rand_c(rng, nb, n, n)
+    tf = 10.0
+    t = rng.random(nb) * tf if per_member_s else 4.2
+    tl = t if per_member_s else [t] * nb
+    ref = np.stack([opo.rhs(u[b], O.ODEParams(None, tf), tl[b]) for b in range(nb)])
+    ctx = Q.get_context()
+    opg(np.zeros_like(u), u, Q.ODEParams(None, tf), t)
+    ctx.check(ctx.lib.oqb_profile_begin(ctx.h))
+    got = opg(np.zeros_like(u), u, Q.ODEParams(None, tf), t)
+    ms, nl, fl = C.c_double(), C.c_uint64(), C.c_double()
+    ctx.check(ctx.lib.oqb_profile_end(ctx.h, C.byref(ms), C.byref(nl), C.byref(fl)))
+    assert relerr(got, ref) < TOL
+    assert fl.value == 0.0  # no product was launched
+    with ctx.option("lindblad_stencil", 0):
+        plain = opg(np.zeros_like(u), u, Q.ODEParams(None, tf), t)
+    assert relerr(plain, ref) < TOL and relerr(got, plain) < 1e-12
