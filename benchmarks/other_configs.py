@@ -579,6 +579,13 @@ def main():
             print(json.dumps(r), flush=True)
             torch.cuda.empty_cache()
             continue
+        if c in ("c2_tiles", "c2prime_diag_tiles"):  # stencil route with the plain kernel (no register micro-tiles)
+            with Q.get_context().option("lindblad_stencil", 1):
+                r = run_c2(Q, torch, args.steps, False) if c == "c2_tiles" else run_c2(Q, torch, args.steps, False, nq=10, B=64)
+            r["config"] += "-plain-kernel"
+            print(json.dumps(r), flush=True)
+            torch.cuda.empty_cache()
+            continue
         if c == "c2":
             r = run_c2(Q, torch, args.steps, False)
         elif c == "c2dense":

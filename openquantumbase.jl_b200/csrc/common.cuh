@@ -20,7 +20,7 @@ struct Options {
     int zgemm_bm = 0;         // 0 = by K, 64 / 128 force the CTA tile height of the TMA ZGEMM
     int tma_oneshot = 1;      // one-instruction 5-D operand tiles
     int lindblad_fuse = 1;    // diagonal L_k with shared rates: one n×n factor G for the whole batch, du += G∘u as a pure streaming pass
-    int lindblad_stencil = 1; // … and that term Pauli-structured (≤ 16 XOR diagonals): the commutator as a hypercube stencil fused with the Hadamard factor — no product at all
+    int lindblad_stencil = 2; // … and that term Pauli-structured (≤ 16 XOR diagonals): the commutator as a hypercube stencil fused with the Hadamard factor — no product at all (2: register micro-tiles for n ≥ 64, 1: the plain kernel)
     int lindblad_split = 1;   // … and one off-diagonal Hamiltonian term: shared-operand products scaled by f_N(s_b), diagonal terms in the Hadamard pass
     int coupling_mono = 1;    // Redfield: monomial couplings (σx, σ±, Pauli strings) as gathers (host mirrors consult it when choosing the entry point)
     int lindblad_mono = 1;    // exploit monomial L_k (one entry per row and column: σ±, Pauli strings): gather instead of 2K products

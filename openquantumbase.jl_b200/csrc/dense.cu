@@ -35,6 +35,7 @@ struct oqb_dense {
     int xconst[16] = {0};        // xval_j is one value for every row
     c128 xcval[16] = {};
     c128* d_xval = nullptr;      // nxmask × n
+    bool xreal = false;          // every x_j is real
 };
 
 namespace {
@@ -315,6 +316,181 @@ __global__ void __launch_bounds__(256) lindblad_stencil_kernel(int n, int TS, co
     }
 }
 
+// The same pass for n ≥ 64 with register micro-tiles (the version above issues ≈ 445 instructions per element and is issue-bound
+// at 0.24 of the HBM bandwidth).  256 threads own a tile of 64 rows × 32 columns of one ρ; thread (a, q) keeps the 4 × 2
+// elements (rows a + 16 i, columns q + 16 j) in registers, so that
+//   – masks 16 / 32 / 48 on the row side and 16 on the column side pair elements of the SAME thread: no memory traffic at all,
+//   – the other in-tile masks read shared memory with addresses that differ by compile-time offsets over (i, j):
+//     2 LDS.128 + 4 (real values) or 8 DFMA per element and mask, ≈ 0.5 integer instructions,
+//   – masks that leave the tile read the partner tile from global memory (L2),
+//   – everything that depends on the row or the column only (stencil values, the diagonal terms' −i f h) is fetched once per
+//     thread for its 4 rows / 2 columns.
+// REALV: every stencil value is real (−ΣX, XX, X·Z products; not σy fields): half the multiplications.
+template <bool REALV>
+struct StencilAcc {
+    double ar[4][2], ai[4][2];
+    double vrr[4], vri[4], vcr[2], vci[2];  // value at the thread's rows (times u[r^m, c]) and at its partner columns (times u[r, c^m])
+    __device__ __forceinline__ void row(int i, int j, const c128 x1) {  // += v[r_i] · u[r_i ^ m, c_j]
+        if (REALV) {
+            ar[i][j] = fma(vrr[i], x1.x, ar[i][j]);
+            ai[i][j] = fma(vrr[i], x1.y, ai[i][j]);
+        } else {
+            ar[i][j] = fma(vrr[i], x1.x, fma(-vri[i], x1.y, ar[i][j]));
+            ai[i][j] = fma(vrr[i], x1.y, fma(vri[i], x1.x, ai[i][j]));
+        }
+    }
+    __device__ __forceinline__ void col(int i, int j, const c128 x2) {  // −= u[r_i, c_j ^ m] · v[c_j ^ m]
+        if (REALV) {
+            ar[i][j] = fma(-vcr[j], x2.x, ar[i][j]);
+            ai[i][j] = fma(-vcr[j], x2.y, ai[i][j]);
+        } else {
+            ar[i][j] = fma(-vcr[j], x2.x, fma(vci[j], x2.y, ar[i][j]));
+            ai[i][j] = fma(-vcr[j], x2.y, fma(-vci[j], x2.x, ai[i][j]));
+        }
+    }
+    template <int MH>
+    __device__ __forceinline__ void own_rows(const c128 (&x0)[4][2]) {  // row partners inside the thread's own elements
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 2; ++j) row(i, j, x0[i ^ MH][j]);
+    }
+};
+
+template <bool REALV>
+__global__ void __launch_bounds__(256, 2) lindblad_stencil64_kernel(int n, const __grid_constant__ StencilDesc d, const c128* __restrict__ xval,
+                                                                    const double* __restrict__ fn, int fn_shared, const c128* __restrict__ G,
+                                                                    const c128* __restrict__ hdiag, const c128* __restrict__ coef, long long coef_ld,
+                                                                    const c128* __restrict__ u, c128* __restrict__ du) {
+    __shared__ __align__(16) c128 tile[32 * 64];  // [32 cols][64 rows]
+    const long long b = blockIdx.z, nn = (long long)n * n;
+    const int a = threadIdx.x & 15, q = threadIdx.x >> 4;
+    const int r0 = blockIdx.x * 64 + a, c0 = blockIdx.y * 32 + q;  // the thread's first row / column; the others are + 16 i / + 16 j
+    const c128* ub = u + b * nn;
+    const long long cs = 16LL * n;  // element distance of the thread's two columns
+    c128 x0[4][2];
+    {
+        const c128* up = ub + r0 + (long long)c0 * n;
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) x0[i][j] = up[16 * i + j * cs];
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) tile[(q + 16 * j) * 64 + a + 16 * i] = x0[i][j];
+    }
+    __syncthreads();
+    StencilAcc<REALV> A;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) A.ar[i][j] = A.ai[i][j] = 0.0;
+    for (int jm = 0; jm < d.nmask; ++jm) {
+        const int m = d.mask[jm];
+        if (d.isconst[jm]) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) A.vrr[i] = d.cre[jm], A.vri[i] = d.cim[jm];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) A.vcr[j] = d.cre[jm], A.vci[j] = d.cim[jm];
+        } else {
+            const c128* xv = xval + (size_t)jm * n;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const c128 v1 = xv[r0 + 16 * i];
+                A.vrr[i] = v1.x, A.vri[i] = v1.y;
+            }
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const c128 v2 = xv[(c0 + 16 * j) ^ m];
+                A.vcr[j] = v2.x, A.vci[j] = v2.y;
+            }
+        }
+        const int ml = m & 15, mh = m >> 4;
+        // row side: u[r_i ^ m, c_j]
+        if (m >= 64) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const c128* t1 = ub + ((r0 + 16 * i) ^ m) + (long long)c0 * n;
+#pragma unroll
+                for (int j = 0; j < 2; ++j) A.row(i, j, t1[j * cs]);
+            }
+        } else if (ml == 0) {
+            if (mh == 0) A.template own_rows<0>(x0);  // mask 0: the term's own diagonal
+            else if (mh == 1) A.template own_rows<1>(x0);
+            else if (mh == 2) A.template own_rows<2>(x0);
+            else A.template own_rows<3>(x0);
+        } else {
+            const c128* p1 = tile + (a ^ ml) + q * 64;  // u[r_i ^ m, c_j] = p1[((i ^ mh) << 4) + j·1024]
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const c128* t1 = p1 + ((i ^ mh) << 4);
+#pragma unroll
+                for (int j = 0; j < 2; ++j) A.row(i, j, t1[j * 1024]);
+            }
+        }
+        // column side: u[r_i, c_j ^ m]
+        if (m >= 32) {
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const c128* t2 = ub + r0 + (long long)((c0 + 16 * j) ^ m) * n;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) A.col(i, j, t2[16 * i]);
+            }
+        } else if (m == 16) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 2; ++j) A.col(i, j, x0[i][j ^ 1]);
+        } else {
+            const c128* p2 = tile + a + (q ^ ml) * 64;  // u[r_i, c_j ^ m] = p2[16 i + ((j ^ mh) << 10)]
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const c128* t2 = p2 + ((j ^ mh) << 10);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) A.col(i, j, t2[16 * i]);
+            }
+        }
+    }
+    // −i Σ_t f_bt h_t[·] at the thread's rows and columns
+    double hrr[4], hri[4], hcr[2], hci[2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) hrr[i] = hri[i] = 0.0;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) hcr[j] = hci[j] = 0.0;
+    for (int t = 0; t < d.nt; ++t) {
+        const double sf = coef[b * coef_ld + t].x;
+        const c128* ht = hdiag + (size_t)t * n;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const c128 ha = ht[r0 + 16 * i];
+            hrr[i] = fma(sf, ha.y, hrr[i]);
+            hri[i] = fma(-sf, ha.x, hri[i]);
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const c128 hc = ht[c0 + 16 * j];
+            hcr[j] = fma(sf, hc.y, hcr[j]);
+            hci[j] = fma(-sf, hc.x, hci[j]);
+        }
+    }
+    const double f = fn[fn_shared ? 0 : b];
+    c128* dp = du + b * nn + r0 + (long long)c0 * n;
+    const c128* gp = G ? G + r0 + (long long)c0 * n : nullptr;
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            c128 g = gp ? gp[16 * i + j * cs] : make_double2(0.0, 0.0);
+            g.x += hrr[i] - hcr[j];
+            g.y += hri[i] - hci[j];
+            // −i f (ar + i ai) = f (ai − i ar)
+            const double outr = fma(g.x, x0[i][j].x, fma(-g.y, x0[i][j].y, f * A.ai[i][j]));
+            const double outi = fma(g.x, x0[i][j].y, fma(g.y, x0[i][j].x, -f * A.ar[i][j]));
+            dp[16 * i + j * cs] = make_double2(outr, outi);
+        }
+}
+
 // He[b][a,a] += Σ_k coef[b][k]·lld_k[a]   (monomial L_k: L_k'L_k is diagonal)
 __global__ void heff_lld_add_kernel(int n, int K, const double* __restrict__ lld, const c128* __restrict__ coef, long long coef_ld,
                                     c128* __restrict__ He, long long strideHe) {
@@ -441,13 +617,26 @@ int dense_rhs_impl(oqb_dense* op, int nb, const double* coefH, int coef_shared, 
             }
             const int TS = n >= 64 ? 64 : (int)n;
             static DevOnce cfg;
-            if (!cfg.done(c->device)) { OQB_CUDA(c, cudaFuncSetAttribute(lindblad_stencil_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)); cfg.set(c->device); }
+            if (!cfg.done(c->device)) {
+                OQB_CUDA(c, cudaFuncSetAttribute(lindblad_stencil_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+                cfg.set(c->device);
+            }
+            const bool micro = n >= 64 && c->opt.lindblad_stencil >= 2;  // 2 (default): register micro-tiles; 1: the plain one-element-at-a-time kernel
             for (int m0 = 0; m0 < nb; m0 += 65535) {
                 const int mc = nb - m0 < 65535 ? nb - m0 : 65535;
-                dim3 grid((unsigned)(n / TS), (unsigned)(n / TS), mc);
-                lindblad_stencil_kernel<<<grid, 256, (size_t)TS * TS * sizeof(c128), c->stream>>>(
-                    (int)n, TS, sd, op->d_xval, d_fn + (coef_shared ? 0 : m0), coef_shared ? 1 : 0, G2, op->d_hdiag,
-                    (const c128*)d_coef + (rows == 1 ? 0 : (long long)m0 * nmat), rows == 1 ? 0 : nmat, u + (long long)m0 * nn, du + (long long)m0 * nn);
+                dim3 grid((unsigned)(n / TS), (unsigned)(n / TS), mc), grid64((unsigned)(n / 64), (unsigned)(n / 32), mc);
+                const double* fnp = d_fn + (coef_shared ? 0 : m0);
+                const c128* cfp = (const c128*)d_coef + (rows == 1 ? 0 : (long long)m0 * nmat);
+                const long long cld = rows == 1 ? 0 : nmat;
+                if (micro && op->xreal)
+                    lindblad_stencil64_kernel<true><<<grid64, 256, 0, c->stream>>>((int)n, sd, op->d_xval, fnp, coef_shared ? 1 : 0, G2, op->d_hdiag, cfp, cld,
+                                                                                   u + (long long)m0 * nn, du + (long long)m0 * nn);
+                else if (micro)
+                    lindblad_stencil64_kernel<false><<<grid64, 256, 0, c->stream>>>((int)n, sd, op->d_xval, fnp, coef_shared ? 1 : 0, G2, op->d_hdiag, cfp, cld,
+                                                                                    u + (long long)m0 * nn, du + (long long)m0 * nn);
+                else
+                    lindblad_stencil_kernel<<<grid, 256, (size_t)TS * TS * sizeof(c128), c->stream>>>((int)n, TS, sd, op->d_xval, fnp, coef_shared ? 1 : 0, G2, op->d_hdiag,
+                                                                                                      cfp, cld, u + (long long)m0 * nn, du + (long long)m0 * nn);
                 OQB_LAUNCH_CHECK(c);
             }
             return 0;
@@ -653,6 +842,9 @@ int oqb_dense_create(oqb_ctx* c, int n, int nterms, const void* h_mats, int K, c
                     OQB_CUDA(c, cudaMemcpyAsync(op->d_xval, xv.data(), xv.size() * sizeof(c128), cudaMemcpyHostToDevice, c->stream));
                     OQB_CUDA(c, cudaStreamSynchronize(c->stream));
                     op->nxmask = (int)masks.size();
+                    op->xreal = true;
+                    for (const c128& v : xv)
+                        if (v.y != 0.0) op->xreal = false;
                 }
             }
         }
