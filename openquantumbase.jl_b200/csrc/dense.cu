@@ -560,7 +560,10 @@ int dense_rhs_impl(oqb_dense* op, int nb, const double* coefH, int coef_shared, 
     const size_t coef_bytes = coef.size() * sizeof(c128);
     const size_t gam_elems = K ? (gamma_shared ? (size_t)K : (size_t)nb * K) : 0;
     // split form (one off-diagonal Hamiltonian term): its coefficient f_N(s_b) per member, as the real scale of alpha
-    const bool may_split = with_h && op->offdiag_term >= 0 && K > 0 && gamma_shared && c->opt.lindblad_split;
+    // … and the plain commutator −i[H(s_b), u] (no Lindblad term: the H-d row itself, Redfield's Hamiltonian part) of a
+    // Pauli-structured Hamiltonian needs no product either: the same stencil pass without the Hadamard factor
+    const bool h_only_stencil = with_h && K == 0 && op->offdiag_term >= 0 && op->nxmask > 0 && op->nterms <= 16 && c->opt.lindblad_stencil;
+    const bool may_split = (with_h && op->offdiag_term >= 0 && K > 0 && gamma_shared && c->opt.lindblad_split) || h_only_stencil;
     const size_t fn_elems = may_split ? (size_t)(coef_shared ? 1 : nb) : 0;
     std::vector<char> stage(coef_bytes + (gam_elems + fn_elems) * sizeof(double));
     memcpy(stage.data(), coef.data(), coef_bytes);
@@ -600,10 +603,13 @@ int dense_rhs_impl(oqb_dense* op, int nb, const double* coefH, int coef_shared, 
     // dephasing).  No per-member H_eff is assembled at all: both products use the SHARED operand m_N with alpha scaled by
     // f_N(s_b), and the diagonal terms' commutator joins the Lindblad factor in the one Hadamard pass.
     const size_t split_sm = (size_t)op->nterms * n * sizeof(c128) + (size_t)op->nterms * sizeof(double);
-    if (may_split && fuse_sandwich && split_sm <= 160 * 1024) {
-        c128* G2 = (c128*)c->ws;  // the workspace was reserved for at least nn elements (he_elems ≥ nn)
-        lindblad_diag_gmat_kernel<<<(unsigned)((nn + 255) / 256), 256, 0, c->stream>>>((int)n, K, op->d_ldiag, (const double*)d_gamma, 1, G2);
-        OQB_LAUNCH_CHECK(c);
+    if (may_split && (fuse_sandwich || h_only_stencil) && split_sm <= 160 * 1024) {
+        c128* G2 = nullptr;
+        if (K) {
+            G2 = (c128*)c->ws;  // the workspace was reserved for at least nn elements (he_elems ≥ nn)
+            lindblad_diag_gmat_kernel<<<(unsigned)((nn + 255) / 256), 256, 0, c->stream>>>((int)n, K, op->d_ldiag, (const double*)d_gamma, 1, G2);
+            OQB_LAUNCH_CHECK(c);
+        }
         if (op->nxmask > 0 && op->nterms <= 16 && c->opt.lindblad_stencil) {
             StencilDesc sd;
             memset(&sd, 0, sizeof(sd));

@@ -350,3 +350,42 @@ def test_pauli_structured_driver_takes_the_stencil_route(Q, driver, nq, nb, per_
     with ctx.option("lindblad_stencil", 0):
         plain = opg(np.zeros_like(u), u, Q.ODEParams(None, tf), t)
     assert relerr(plain, ref) < TOL and relerr(got, plain) < 1e-12
+
+
+@pytest.mark.parametrize("driver", ["transverse_field", "xx_catalyst", "y_field", "x_plus_z"])
+@pytest.mark.parametrize("nq,nb", [(3, 4), (6, 5), (7, 3), (8, 4), (10, 2)])
+@pytest.mark.parametrize("unit", ["h", "ħ"])
+def test_plain_commutator_of_a_pauli_structured_hamiltonian_is_a_stencil(Q, driver, nq, nb, unit):
+    """(h::DenseHamiltonian)(du, u, p, s) — src/hamiltonian/dense_hamiltonian.jl:84-89 — with no Lindblad term at all: for a
+    Pauli-structured driver + diagonal problem terms the commutator is the same stencil pass without the Hadamard factor
+    (no product launched; OVERWRITES du).  Against the oracle's −i(Hu − uH) and against the two-product route."""
+    import ctypes as C
+    n = 1 << nq
+    rng = np.random.default_rng(nq * 23 + nb + len(driver))
+    if driver == "transverse_field":
+        Hd = _pauli_sum_dense(nq, [(-1.0 - 0.1 * q, {q: "X"}) for q in range(1, nq + 1)])
+    elif driver == "xx_catalyst":
+        Hd = _pauli_sum_dense(nq, [(-1.0, {q: "X"}) for q in range(1, min(nq, 8) + 1)] + [(0.4, {q: "X", q + 1: "X"}) for q in range(1, min(nq, 8))])
+    elif driver == "y_field":
+        Hd = _pauli_sum_dense(nq, [(0.7 + 0.1 * q, {q: "Y"}) for q in range(1, nq + 1)])
+    else:
+        Hd = _pauli_sum_dense(nq, [(-1.0, {q: "X"}) for q in range(1, nq + 1)] + [(0.3 + 0.05 * q, {q: "Z"}) for q in range(1, nq + 1)])
+    Hp = np.diag(rng.standard_normal(n)).astype(complex)
+    fs = [lambda s: 1 - s, lambda s: s * s]
+    Hg = Q.DenseHamiltonian(fs, [Hd, Hp], unit=unit)
+    Ho = O.DenseHamiltonian(fs, [Hd, Hp], unit=unit)
+    u = rand_c(rng, nb, n, n)
+    s = rng.random(nb)
+    ref = np.stack([Ho.rhs(u[b], s[b]) for b in range(nb)])
+    ctx = Q.get_context()
+    ctx.check(ctx.lib.oqb_profile_begin(ctx.h))
+    got = Hg(np.full_like(u, 7.0), u, None, s)
+    ms, nl, fl = C.c_double(), C.c_uint64(), C.c_double()
+    ctx.check(ctx.lib.oqb_profile_end(ctx.h, C.byref(ms), C.byref(nl), C.byref(fl)))
+    assert relerr(got, ref) < TOL
+    assert fl.value == 0.0  # no product was launched
+    shared = Hg(np.full_like(u, 7.0), u, None, 0.3)  # one s for the whole batch
+    assert relerr(shared, np.stack([Ho.rhs(u[b], 0.3) for b in range(nb)])) < TOL
+    with ctx.option("lindblad_stencil", 0):
+        plain = Hg(np.full_like(u, 7.0), u, None, s)
+    assert relerr(plain, ref) < TOL and relerr(got, plain) < 1e-12
