@@ -562,9 +562,10 @@ int dense_rhs_impl(oqb_dense* op, int nb, const double* coefH, int coef_shared, 
     // split form (one off-diagonal Hamiltonian term): its coefficient f_N(s_b) per member, as the real scale of alpha
     // … and the plain commutator −i[H(s_b), u] (no Lindblad term: the H-d row itself, Redfield's Hamiltonian part) of a
     // Pauli-structured Hamiltonian needs no product either: the same stencil pass without the Hadamard factor
-    const bool h_only_stencil = with_h && K == 0 && op->offdiag_term >= 0 && op->nxmask > 0 && op->nterms <= 16 && c->opt.lindblad_stencil;
+    const bool stencil_h = with_h && op->offdiag_term >= 0 && op->nxmask > 0 && op->nterms <= 16 && c->opt.lindblad_stencil;
+    const bool h_only_stencil = stencil_h && K == 0;
     const bool may_split = (with_h && op->offdiag_term >= 0 && K > 0 && gamma_shared && c->opt.lindblad_split) || h_only_stencil;
-    const size_t fn_elems = may_split ? (size_t)(coef_shared ? 1 : nb) : 0;
+    const size_t fn_elems = (may_split || stencil_h) ? (size_t)(coef_shared ? 1 : nb) : 0;
     std::vector<char> stage(coef_bytes + (gam_elems + fn_elems) * sizeof(double));
     memcpy(stage.data(), coef.data(), coef_bytes);
     if (gam_elems) memcpy(stage.data() + coef_bytes, gamma, gam_elems * sizeof(double));
@@ -599,6 +600,45 @@ int dense_rhs_impl(oqb_dense* op, int nb, const double* coefH, int coef_shared, 
     c128* T = He + he_elems;
     c128* Gmat = T + (size_t)chunk * Kws * nn;
 
+    // −i[H(s_b), u_b] (+ G∘u_b) of members [m_first, m_first + cnt) as one stencil pass (Pauli-structured off-diagonal term), OVERWRITES du
+    auto stencil_pass = [&](const c128* G2, int m_first, int cnt) -> int {
+        StencilDesc sd;
+        memset(&sd, 0, sizeof(sd));
+        sd.nmask = op->nxmask;
+        sd.nt = op->nterms;
+        for (int j = 0; j < op->nxmask; ++j) {
+            sd.mask[j] = op->xmask[j];
+            sd.isconst[j] = op->xconst[j];
+            sd.cre[j] = op->xcval[j].x;
+            sd.cim[j] = op->xcval[j].y;
+        }
+        const int TS = n >= 64 ? 64 : (int)n;
+        static DevOnce cfg;
+        if (!cfg.done(c->device)) {
+            OQB_CUDA(c, cudaFuncSetAttribute(lindblad_stencil_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+            cfg.set(c->device);
+        }
+        const bool micro = n >= 64 && c->opt.lindblad_stencil >= 2;  // 2 (default): register micro-tiles; 1: the plain one-element-at-a-time kernel
+        for (int m0 = m_first; m0 < m_first + cnt; m0 += 65535) {
+            const int mc = m_first + cnt - m0 < 65535 ? m_first + cnt - m0 : 65535;
+            dim3 grid((unsigned)(n / TS), (unsigned)(n / TS), mc), grid64((unsigned)(n / 64), (unsigned)(n / 32), mc);
+            const double* fnp = d_fn + (coef_shared ? 0 : m0);
+            const c128* cfp = (const c128*)d_coef + (rows == 1 ? 0 : (long long)m0 * nmat);
+            const long long cld = rows == 1 ? 0 : nmat;
+            if (micro && op->xreal)
+                lindblad_stencil64_kernel<true><<<grid64, 256, 0, c->stream>>>((int)n, sd, op->d_xval, fnp, coef_shared ? 1 : 0, G2, op->d_hdiag, cfp, cld,
+                                                                               u + (long long)m0 * nn, du + (long long)m0 * nn);
+            else if (micro)
+                lindblad_stencil64_kernel<false><<<grid64, 256, 0, c->stream>>>((int)n, sd, op->d_xval, fnp, coef_shared ? 1 : 0, G2, op->d_hdiag, cfp, cld,
+                                                                                u + (long long)m0 * nn, du + (long long)m0 * nn);
+            else
+                lindblad_stencil_kernel<<<grid, 256, (size_t)TS * TS * sizeof(c128), c->stream>>>((int)n, TS, sd, op->d_xval, fnp, coef_shared ? 1 : 0, G2, op->d_hdiag,
+                                                                                                  cfp, cld, u + (long long)m0 * nn, du + (long long)m0 * nn);
+            OQB_LAUNCH_CHECK(c);
+        }
+        return 0;
+    };
+
     // Split form: H(s_b) = f_N(s_b)·m_N + diagonal terms, diagonal L_k, shared rates (config C2: −ΣX driver, ZZ problem term,
     // dephasing).  No per-member H_eff is assembled at all: both products use the SHARED operand m_N with alpha scaled by
     // f_N(s_b), and the diagonal terms' commutator joins the Lindblad factor in the one Hadamard pass.
@@ -610,41 +650,8 @@ int dense_rhs_impl(oqb_dense* op, int nb, const double* coefH, int coef_shared, 
             lindblad_diag_gmat_kernel<<<(unsigned)((nn + 255) / 256), 256, 0, c->stream>>>((int)n, K, op->d_ldiag, (const double*)d_gamma, 1, G2);
             OQB_LAUNCH_CHECK(c);
         }
-        if (op->nxmask > 0 && op->nterms <= 16 && c->opt.lindblad_stencil) {
-            StencilDesc sd;
-            memset(&sd, 0, sizeof(sd));
-            sd.nmask = op->nxmask;
-            sd.nt = op->nterms;
-            for (int j = 0; j < op->nxmask; ++j) {
-                sd.mask[j] = op->xmask[j];
-                sd.isconst[j] = op->xconst[j];
-                sd.cre[j] = op->xcval[j].x;
-                sd.cim[j] = op->xcval[j].y;
-            }
-            const int TS = n >= 64 ? 64 : (int)n;
-            static DevOnce cfg;
-            if (!cfg.done(c->device)) {
-                OQB_CUDA(c, cudaFuncSetAttribute(lindblad_stencil_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-                cfg.set(c->device);
-            }
-            const bool micro = n >= 64 && c->opt.lindblad_stencil >= 2;  // 2 (default): register micro-tiles; 1: the plain one-element-at-a-time kernel
-            for (int m0 = 0; m0 < nb; m0 += 65535) {
-                const int mc = nb - m0 < 65535 ? nb - m0 : 65535;
-                dim3 grid((unsigned)(n / TS), (unsigned)(n / TS), mc), grid64((unsigned)(n / 64), (unsigned)(n / 32), mc);
-                const double* fnp = d_fn + (coef_shared ? 0 : m0);
-                const c128* cfp = (const c128*)d_coef + (rows == 1 ? 0 : (long long)m0 * nmat);
-                const long long cld = rows == 1 ? 0 : nmat;
-                if (micro && op->xreal)
-                    lindblad_stencil64_kernel<true><<<grid64, 256, 0, c->stream>>>((int)n, sd, op->d_xval, fnp, coef_shared ? 1 : 0, G2, op->d_hdiag, cfp, cld,
-                                                                                   u + (long long)m0 * nn, du + (long long)m0 * nn);
-                else if (micro)
-                    lindblad_stencil64_kernel<false><<<grid64, 256, 0, c->stream>>>((int)n, sd, op->d_xval, fnp, coef_shared ? 1 : 0, G2, op->d_hdiag, cfp, cld,
-                                                                                    u + (long long)m0 * nn, du + (long long)m0 * nn);
-                else
-                    lindblad_stencil_kernel<<<grid, 256, (size_t)TS * TS * sizeof(c128), c->stream>>>((int)n, TS, sd, op->d_xval, fnp, coef_shared ? 1 : 0, G2, op->d_hdiag,
-                                                                                                      cfp, cld, u + (long long)m0 * nn, du + (long long)m0 * nn);
-                OQB_LAUNCH_CHECK(c);
-            }
+        if (stencil_h) {
+            OQB_TRY(stencil_pass(G2, 0, nb));
             return 0;
         }
         const c128* mN = op->d_mats + (long long)op->offdiag_term * nn;
@@ -705,7 +712,10 @@ int dense_rhs_impl(oqb_dense* op, int nb, const double* coefH, int coef_shared, 
         }
         return 0;
     };
-    if (rows == 1) OQB_TRY(assemble((const c128*)d_coef, 0, 1));
+    // Pauli-structured Hamiltonian + diagonal or monomial L_k (per-member rates, amplitude damping, Pauli channels): the
+    // commutator is the stencil pass, the dissipator — anticommutator included — the Hadamard / gather pass: no product at all
+    const bool stencil_comm = stencil_h && (use_diag || use_mono) && !fuse_sandwich;
+    if (rows == 1 && !stencil_comm) OQB_TRY(assemble((const c128*)d_coef, 0, 1));
     if (fuse_sandwich) {
         lindblad_diag_gmat_kernel<<<(unsigned)((nn + 255) / 256), 256, 0, c->stream>>>((int)n, K, op->d_ldiag, (const double*)d_gamma,
                                                                                        real_h ? 1 : 0, Gmat);
@@ -715,6 +725,8 @@ int dense_rhs_impl(oqb_dense* op, int nb, const double* coefH, int coef_shared, 
         const int cnt = nb - b0 < chunk ? nb - b0 : chunk;
         const c128* ub = u + (long long)b0 * nn;
         c128* dub = du + (long long)b0 * nn;
+        if (stencil_comm) OQB_TRY(stencil_pass(nullptr, b0, cnt));
+        else {
         if (rows != 1) OQB_TRY(assemble((const c128*)d_coef + (long long)b0 * nmat, nmat, cnt));
         ZgemmParams p;  // du = (−i) He u      [accumulate form: du += G u]
         p.M = p.N = p.K = (int)n; p.batch = cnt;
@@ -734,6 +746,8 @@ int dense_rhs_impl(oqb_dense* op, int nb, const double* coefH, int coef_shared, 
         q.alpha = with_h ? make_double2(0.0, 1.0) : make_double2(1.0, 0.0);
         q.beta = make_double2(1.0, 0.0);
         OQB_TRY(zgemm(c, q));
+        }
+        const int anti = (real_h || stencil_comm) ? 1 : 0;  // the anticommutator −½{Σγ L'L, u} was kept out of the commutator's operand
         if (fuse_sandwich) {
             for (int m0 = 0; m0 < cnt; m0 += 65535) {
                 const int mc = cnt - m0 < 65535 ? cnt - m0 : 65535;
@@ -753,7 +767,7 @@ int dense_rhs_impl(oqb_dense* op, int nb, const double* coefH, int coef_shared, 
                     dim3 grid(tiles, mc);
                     lindblad_diag_sandwich_kernel<<<grid, 256, sm, c->stream>>>(
                         (int)n, K, op->d_ldiag, dg + (gamma_shared ? 0 : (long long)m0 * K), gamma_shared ? 0 : K,
-                        ub + (long long)m0 * nn, dub + (long long)m0 * nn, real_h ? 1 : 0);
+                        ub + (long long)m0 * nn, dub + (long long)m0 * nn, anti);
                     OQB_LAUNCH_CHECK(c);
                 }
             } else if (use_mono) {
@@ -762,7 +776,7 @@ int dense_rhs_impl(oqb_dense* op, int nb, const double* coefH, int coef_shared, 
                     dim3 grid((unsigned)n, mc);
                     lindblad_mono_sandwich_kernel<<<grid, 256, 0, c->stream>>>(
                         (int)n, K, op->d_mperm, op->d_mval, op->d_mlld, dg + (gamma_shared ? 0 : (long long)m0 * K), gamma_shared ? 0 : K,
-                        ub + (long long)m0 * nn, dub + (long long)m0 * nn, real_h ? 1 : 0);
+                        ub + (long long)m0 * nn, dub + (long long)m0 * nn, anti);
                     OQB_LAUNCH_CHECK(c);
                 }
             } else {

@@ -389,3 +389,52 @@ def test_plain_commutator_of_a_pauli_structured_hamiltonian_is_a_stencil(Q, driv
     with ctx.option("lindblad_stencil", 0):
         plain = Hg(np.full_like(u, 7.0), u, None, s)
     assert relerr(plain, ref) < TOL and relerr(got, plain) < 1e-12
+
+
+@pytest.mark.parametrize("kind", ["amplitude_damping", "pauli_channel", "dephasing_per_member_rates", "mixed_with_dephasing"])
+@pytest.mark.parametrize("nq,nb", [(3, 5), (6, 4), (8, 3)])
+@pytest.mark.parametrize("driver", ["transverse_field", "y_field"])
+def test_pauli_structured_hamiltonian_with_monomial_or_rate_dependent_operators(Q, kind, nq, nb, driver):
+    """Pauli-structured H(s) with L_k that are monomial (σ⁻, Pauli strings) or diagonal with rates that depend on s_b: the
+    commutator is the stencil pass and the dissipator (anticommutator included) the gather / Hadamard pass — no product.
+    Against the oracle's literal loop (src/opensys/lindblad.jl:94-101) and the product route (option lindblad_stencil = 0)."""
+    import ctypes as C
+    n = 1 << nq
+    rng = np.random.default_rng(nq * 29 + nb + len(kind) + len(driver))
+    idx = np.arange(n)
+    zq = lambda q: np.diag(1.0 - 2.0 * ((idx >> (nq - q)) & 1)).astype(complex)
+    if kind == "amplitude_damping":
+        Ls = [_sigma_minus(nq, q) for q in range(1, nq + 1)]
+    elif kind == "pauli_channel":
+        Ls = [_pauli_sum_dense(nq, [(1.0, {1: "X"})]), _pauli_sum_dense(nq, [(1.0, {nq: "Y"})]), _pauli_sum_dense(nq, [(1.0, {1: "X", 2: "Y"})])]
+    elif kind == "dephasing_per_member_rates":
+        Ls = [zq(q) for q in range(1, nq + 1)]
+    else:
+        Ls = [_sigma_minus(nq, 1), zq(2), _sigma_minus(nq, nq).conj().T]
+    K = len(Ls)
+    if driver == "transverse_field":
+        Hd = _pauli_sum_dense(nq, [(-1.0 - 0.1 * q, {q: "X"}) for q in range(1, nq + 1)])
+    else:
+        Hd = _pauli_sum_dense(nq, [(0.7 + 0.1 * q, {q: "Y"}) for q in range(1, nq + 1)])
+    Hp = np.diag(rng.standard_normal(n)).astype(complex)
+    fs = [lambda s: 1 - s, lambda s: s]
+    gfs = [(lambda s, k=k: 0.1 * (1 + k) * (1 + 0.5 * s)) for k in range(K)]
+    opg = Q.DiffEqLiouvillian(Q.DenseHamiltonian(fs, [Hd, Hp], unit="ħ"), [], [Q.LindbladLiouvillian([Q.Lindblad(g, L) for g, L in zip(gfs, Ls)])], n)
+    opo = O.DiffEqLiouvillian(O.DenseHamiltonian(fs, [Hd, Hp], unit="ħ"), [], [O.LindbladLiouvillian([O.Lindblad(g, L) for g, L in zip(gfs, Ls)])], n)
+    u = rand_c(rng, nb, n, n)
+    t = rng.random(nb) * 10.0
+    p = Q.ODEParams(None, 10.0)
+    ref = np.stack([opo.rhs(u[b], O.ODEParams(None, 10.0), t[b]) for b in range(nb)])
+    ctx = Q.get_context()
+    opg(np.zeros_like(u), u, p, t)  # builds the device operator
+    ctx.check(ctx.lib.oqb_profile_begin(ctx.h))
+    got = opg(np.zeros_like(u), u, p, t)
+    ms, nl, fl = C.c_double(), C.c_uint64(), C.c_double()
+    ctx.check(ctx.lib.oqb_profile_end(ctx.h, C.byref(ms), C.byref(nl), C.byref(fl)))
+    assert relerr(got, ref) < TOL
+    assert fl.value == 0.0  # no product was launched
+    shared = opg(np.zeros_like(u), u, p, 4.2)  # one time for the whole batch
+    assert relerr(shared, np.stack([opo.rhs(u[b], O.ODEParams(None, 10.0), 4.2) for b in range(nb)])) < TOL
+    with ctx.option("lindblad_stencil", 0):
+        plain = opg(np.zeros_like(u), u, p, t)
+    assert relerr(plain, ref) < TOL and relerr(got, plain) < 1e-12
