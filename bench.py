@@ -176,6 +176,10 @@ def run_secondary(Q, torch, ctx):
             r = OC.run_c2(Q, torch, 3, False, nq=10, B=64)
         out["C2prime_10q_dephasing_2gemm_route"] = short(r, ("config", "value", "ms_per_step", "roofline"))
         torch.cuda.empty_cache()
+        # … with amplitude damping (sigma-minus_k: monomial operators) instead of dephasing: stencil pass for the commutator + gather pass for the dissipator
+        r = OC.run_c2(Q, torch, 3, False, nq=10, B=64, damping=True)
+        out["C2prime_10q_amplitude_damping"] = short(r, ("config", "workload", "value", "ms_per_step", "roofline"))
+        torch.cuda.empty_cache()
     except Exception as e:  # noqa: BLE001
         out["C2_error"] = f"{type(e).__name__}: {e}"
     try:

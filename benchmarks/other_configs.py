@@ -115,14 +115,19 @@ def run_c2(Q, torch, steps, dense_L, nq=8, B=4096, damping=False):
         # (lindblad_stencil_kernel) — an HBM-bound pass: read rho, write drho = 32 B per element
         hbm, src = peaks()
         gbs = 32.0 * n * n * B / 1e9 / (ms * 1e-3)
-        return {"note": "Pauli-structured driver (XOR diagonals) + diagonal problem terms + diagonal L_k with shared rates: the whole RHS is ONE pass "
-                        "(lindblad_stencil_kernel: commutator as a stencil over the driver's XOR diagonals, fused with the Hadamard factor) — no GEMM; "
-                        "option lindblad_stencil = 0 gives the 2-GEMM row",
+        note = ("Pauli-structured driver (XOR diagonals) + diagonal problem terms + diagonal L_k with shared rates: the whole RHS is ONE pass "
+                "(lindblad_stencil64_kernel: commutator as a stencil over the driver's XOR diagonals, fused with the Hadamard factor) — no GEMM; "
+                "option lindblad_stencil = 0 gives the 2-GEMM row")
+        if damping:
+            note = ("Pauli-structured driver + diagonal problem terms + monomial L_k (sigma-minus per qubit): TWO passes, no GEMM — the commutator as a stencil "
+                    "(lindblad_stencil64_kernel) and the dissipator incl. its anticommutator as a gather (lindblad_mono_sandwich_kernel, reads rho K times from L2); "
+                    "frac counts the RHS's minimal 32 B per element against both passes' time; option lindblad_stencil = 0 gives the 2-GEMM + gather row")
+        return {"note": note,
                 "config": ("C2" if nq == 8 else "C2prime") + ("-damping" if damping else "-Zk") + "-stencil",
                 "workload": f"{nq}-qubit dense TFIM + {K} dense-stored {'sigma-minus_k' if damping else 'Z_k'} Lindblad ops, batch {B} of {n}x{n} rho, per-member s",
                 "metric": "rho_rhs_evals_per_sec", "value": B / (ms * 1e-3), "ms_per_step": ms,
                 "algorithmic_tflop_per_step": flops / 1e12, "step_tflops": flops / (ms * 1e-3) / 1e12,
-                "roofline": {"bound": "hbm", "kernel": "lindblad_stencil_kernel", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm,
+                "roofline": {"bound": "hbm", "kernel": "lindblad_stencil64_kernel" + (" + lindblad_mono_sandwich_kernel" if damping else ""), "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm,
                              "algorithmic_bytes_per_step": 32.0 * n * n * B, "peak_source": src}}
     ach = zfl.value / (zms.value * 1e-3) / 1e12
     extra = {}
