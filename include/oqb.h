@@ -118,6 +118,15 @@ int oqb_zgemm_batched(oqb_ctx* ctx, int opA, int opB, int M, int N, int K, const
  * src/opensys/lindblad.jl:76-92.  Uploads once and precomputes L_k'L_k on the device. */
 int oqb_dense_create(oqb_ctx* ctx, int n, int nterms, const void* h_mats, int K, const void* h_lops,
                      oqb_dense** out);
+/* The host-only structure analysis oqb_dense_create runs on the Hamiltonian terms — needs NO GPU and no context.
+ *   *offdiag_term = index of the ONE term with off-diagonal entries when every other term is a diagonal matrix (and
+ *   nterms ≥ 2), else −1: H(s) = f_N(s)·m_N + Σ f_i(s)·diag(h_i), src/hamiltonian/dense_hamiltonian.jl:60-66, is then never
+ *   assembled.  *nmask = number of XOR diagonals that hold the non-zeros of m_N (m_N[r, r ^ masks16[j]] = x_j[r]; 0 when there
+ *   are more than 16 or n is not a power of two): with nmask > 0 the commutator :84-89 runs as a stencil pass instead of
+ *   two products.  isconst16[j] = x_j is one value for every row; *all_real = every x_j is real; xval (may be NULL):
+ *   nmask × n complex values x_j[r]. */
+int oqb_dense_structure_probe(int n, int nterms, const void* h_mats, int* offdiag_term, int* nmask, int* masks16, int* isconst16,
+                              int* all_real, void* xval);
 int oqb_dense_destroy(oqb_dense* op);
 
 /* out[b] = Σ_i coefH[b][i] m_i                      — (h::DenseHamiltonian)(s), :60-66          */

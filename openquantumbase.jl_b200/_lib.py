@@ -108,6 +108,8 @@ SIGNATURES = {
     "oqb_traj_matvec": [c_void_p, c_int, c_dp, c_int, c_dp, c_int, c_void_p, c_void_p],
     "oqb_traj_matvec_host": [c_void_p, c_int, c_dp, c_int, c_dp, c_int, c_void_p, c_void_p],
     "oqb_traj_sell_stats": [c_void_p, C.POINTER(C.c_int), c_dp],
+    "oqb_dense_structure_probe": [C.c_int, C.c_int, c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                  C.POINTER(C.c_int), c_void_p],
     "oqb_sell_plan_probe": [C.c_int, C.c_int, C.POINTER(C.POINTER(C.c_int64)), C.POINTER(C.POINTER(C.c_int32)), C.c_int, c_dp,
                             C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int), C.POINTER(C.c_int)],
     "oqb_traj_norm2": [c_void_p, c_int, c_void_p, c_void_p],

@@ -789,7 +789,85 @@ int dense_rhs_impl(oqb_dense* op, int nb, const double* coefH, int coef_shared, 
 
 }  // namespace
 
+// Host-only analysis of the Hamiltonian terms (no GPU needed; also behind oqb_dense_structure_probe):
+//   – exactly one term with off-diagonal entries among ≥ 2 terms → the split form H(s) = f_N(s)·m_N + Σ f_i(s)·diag(h_i);
+//   – … and that term's non-zeros on ≤ 16 XOR diagonals (n a power of two): m_N[r, r ^ mask_j] = x_j[r] — a sum of Pauli strings.
+struct TermStructure {
+    int offdiag_term = -1;
+    bool offdiag_real = false;
+    std::vector<c128> hdiag;    // nterms × n diagonals (zero row for the off-diagonal term)
+    std::vector<int> masks;     // sorted XOR masks, empty when the term has no such structure
+    std::vector<int> isconst;   // x_j is one value for every row
+    std::vector<c128> xval;     // masks.size() × n
+    bool xreal = false;         // every x_j is real
+};
+static void analyze_terms(const c128* Hm, int n, int nterms, TermStructure& ts) {
+    const size_t nn = (size_t)n * n;
+    int noff = 0, last = -1;
+    ts.hdiag.assign((size_t)std::max(nterms, 1) * n, make_double2(0.0, 0.0));
+    for (int i = 0; i < nterms; ++i) {
+        bool diag = true;
+        for (size_t e = 0; e < nn && diag; ++e)
+            if (e % n != e / n && (Hm[i * nn + e].x != 0.0 || Hm[i * nn + e].y != 0.0)) diag = false;
+        if (diag) {
+            for (int r = 0; r < n; ++r) ts.hdiag[(size_t)i * n + r] = Hm[i * nn + (size_t)r * n + r];
+        } else {
+            ++noff;
+            last = i;
+        }
+    }
+    if (noff != 1 || nterms < 2) return;
+    ts.offdiag_term = last;
+    bool r2 = true;
+    for (size_t e = 0; r2 && e < nn; ++e) r2 = Hm[last * nn + e].y == 0.0;
+    ts.offdiag_real = r2;
+    if ((n & (n - 1)) != 0 || n < 2) return;
+    std::vector<int> masks;
+    for (int j = 0; j < n; ++j)
+        for (int r = 0; r < n; ++r) {
+            const c128 v = Hm[last * nn + (size_t)j * n + r];
+            if (v.x == 0.0 && v.y == 0.0) continue;
+            const int m = r ^ j;
+            if (std::find(masks.begin(), masks.end(), m) == masks.end()) {
+                if (masks.size() >= 16) return;  // more than 16 XOR diagonals: no stencil
+                masks.push_back(m);
+            }
+        }
+    if (masks.empty()) return;
+    std::sort(masks.begin(), masks.end());
+    ts.xval.resize(masks.size() * (size_t)n);
+    ts.isconst.resize(masks.size());
+    ts.xreal = true;
+    for (size_t q = 0; q < masks.size(); ++q) {
+        bool cst = true;
+        for (int r = 0; r < n; ++r) {
+            const c128 v = Hm[last * nn + (size_t)(r ^ masks[q]) * n + r];  // element (row r, col r ^ mask)
+            ts.xval[q * n + r] = v;
+            if (v.x != ts.xval[q * n].x || v.y != ts.xval[q * n].y) cst = false;
+            if (v.y != 0.0) ts.xreal = false;
+        }
+        ts.isconst[q] = cst ? 1 : 0;
+    }
+    ts.masks = masks;
+}
+
 extern "C" {
+
+int oqb_dense_structure_probe(int n, int nterms, const void* h_mats, int* offdiag_term, int* nmask, int* masks16, int* isconst16,
+                               int* all_real, void* xval) {
+    if (n <= 0 || nterms <= 0 || !h_mats) return OQB_EINVAL;
+    TermStructure ts;
+    analyze_terms((const c128*)h_mats, n, nterms, ts);
+    if (offdiag_term) *offdiag_term = ts.offdiag_term;
+    if (nmask) *nmask = (int)ts.masks.size();
+    for (size_t q = 0; q < ts.masks.size(); ++q) {
+        if (masks16) masks16[q] = ts.masks[q];
+        if (isconst16) isconst16[q] = ts.isconst[q];
+    }
+    if (all_real) *all_real = ts.xreal ? 1 : 0;
+    if (xval && !ts.xval.empty()) memcpy(xval, ts.xval.data(), ts.xval.size() * sizeof(c128));
+    return 0;
+}
 
 int oqb_dense_create(oqb_ctx* c, int n, int nterms, const void* h_mats, int K, const void* h_lops, oqb_dense** out) {
     OQB_DEVICE(c, c);
@@ -809,63 +887,26 @@ int oqb_dense_create(oqb_ctx* c, int n, int nterms, const void* h_mats, int K, c
         bool re = nterms > 0;
         for (size_t e = 0; re && e < (size_t)nterms * nn; ++e) re = Hm[e].y == 0.0;
         op->terms_real = re;
-        // which terms are diagonal matrices (σz / σzσz problem Hamiltonians stored densely)?
-        int noff = 0, last = -1;
-        std::vector<c128> hd((size_t)std::max(nterms, 1) * n, make_double2(0.0, 0.0));
-        for (int i = 0; i < nterms; ++i) {
-            bool diag = true;
-            for (size_t e = 0; e < nn && diag; ++e)
-                if (e % n != e / n && (Hm[i * nn + e].x != 0.0 || Hm[i * nn + e].y != 0.0)) diag = false;
-            if (diag) {
-                for (int r = 0; r < n; ++r) hd[(size_t)i * n + r] = Hm[i * nn + (size_t)r * n + r];
-            } else {
-                ++noff;
-                last = i;
-            }
-        }
-        if (noff == 1 && nterms >= 2) {
-            op->offdiag_term = last;
-            bool r2 = true;
-            for (size_t e = 0; r2 && e < nn; ++e) r2 = Hm[last * nn + e].y == 0.0;
-            op->offdiag_real = r2;
-            if (cudaMalloc((void**)&op->d_hdiag, hd.size() * sizeof(c128)) != cudaSuccess) { oqb_dense_destroy(op); return set_error(c, OQB_ENOMEM, "oqb_dense_create: cudaMalloc failed"); }
-            OQB_CUDA(c, cudaMemcpyAsync(op->d_hdiag, hd.data(), hd.size() * sizeof(c128), cudaMemcpyHostToDevice, c->stream));
+        // which terms are diagonal matrices (σz / σzσz problem Hamiltonians stored densely)?  Does the remaining one have Pauli structure?
+        TermStructure ts;
+        analyze_terms(Hm, n, nterms, ts);
+        if (ts.offdiag_term >= 0) {
+            op->offdiag_term = ts.offdiag_term;
+            op->offdiag_real = ts.offdiag_real;
+            if (cudaMalloc((void**)&op->d_hdiag, ts.hdiag.size() * sizeof(c128)) != cudaSuccess) { oqb_dense_destroy(op); return set_error(c, OQB_ENOMEM, "oqb_dense_create: cudaMalloc failed"); }
+            OQB_CUDA(c, cudaMemcpyAsync(op->d_hdiag, ts.hdiag.data(), ts.hdiag.size() * sizeof(c128), cudaMemcpyHostToDevice, c->stream));
             OQB_CUDA(c, cudaStreamSynchronize(c->stream));
-            // Pauli structure of that term: the XOR diagonals r ^ col of its non-zeros (≤ 16, n a power of two)
-            if ((n & (n - 1)) == 0 && n >= 2) {
-                std::vector<int> masks;
-                bool ok = true;
-                for (int j = 0; j < n && ok; ++j)
-                    for (int r = 0; r < n && ok; ++r) {
-                        const c128 v = Hm[last * nn + (size_t)j * n + r];
-                        if (v.x == 0.0 && v.y == 0.0) continue;
-                        const int m = r ^ j;
-                        if (std::find(masks.begin(), masks.end(), m) == masks.end()) {
-                            if (masks.size() >= 16) { ok = false; break; }
-                            masks.push_back(m);
-                        }
-                    }
-                if (ok && !masks.empty()) {
-                    std::sort(masks.begin(), masks.end());
-                    std::vector<c128> xv(masks.size() * (size_t)n);
-                    for (size_t q = 0; q < masks.size(); ++q) {
-                        bool cst = true;
-                        for (int r = 0; r < n; ++r) {
-                            xv[q * n + r] = Hm[last * nn + (size_t)(r ^ masks[q]) * n + r];  // element (row r, col r ^ mask)
-                            if (xv[q * n + r].x != xv[q * n].x || xv[q * n + r].y != xv[q * n].y) cst = false;
-                        }
-                        op->xmask[q] = masks[q];
-                        op->xconst[q] = cst ? 1 : 0;
-                        op->xcval[q] = xv[q * n];
-                    }
-                    if (cudaMalloc((void**)&op->d_xval, xv.size() * sizeof(c128)) != cudaSuccess) { oqb_dense_destroy(op); return set_error(c, OQB_ENOMEM, "oqb_dense_create: cudaMalloc failed"); }
-                    OQB_CUDA(c, cudaMemcpyAsync(op->d_xval, xv.data(), xv.size() * sizeof(c128), cudaMemcpyHostToDevice, c->stream));
-                    OQB_CUDA(c, cudaStreamSynchronize(c->stream));
-                    op->nxmask = (int)masks.size();
-                    op->xreal = true;
-                    for (const c128& v : xv)
-                        if (v.y != 0.0) op->xreal = false;
+            if (!ts.masks.empty()) {
+                for (size_t q = 0; q < ts.masks.size(); ++q) {
+                    op->xmask[q] = ts.masks[q];
+                    op->xconst[q] = ts.isconst[q];
+                    op->xcval[q] = ts.xval[q * n];
                 }
+                if (cudaMalloc((void**)&op->d_xval, ts.xval.size() * sizeof(c128)) != cudaSuccess) { oqb_dense_destroy(op); return set_error(c, OQB_ENOMEM, "oqb_dense_create: cudaMalloc failed"); }
+                OQB_CUDA(c, cudaMemcpyAsync(op->d_xval, ts.xval.data(), ts.xval.size() * sizeof(c128), cudaMemcpyHostToDevice, c->stream));
+                OQB_CUDA(c, cudaStreamSynchronize(c->stream));
+                op->nxmask = (int)ts.masks.size();
+                op->xreal = ts.xreal;
             }
         }
     }
