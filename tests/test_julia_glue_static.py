@@ -125,3 +125,36 @@ def test_every_ccall_matches_its_c_prototype():
             if jc != cc and not (jc == "i64" and cc == "size") and not (jc == "size" and cc == "i64"):
                 problems.append(f"{where}: argument {k + 1} is {jt} ({jc}), the prototype says `{cp}` ({cc})")
     assert not problems, "\n".join(problems)
+
+
+def ctypes_class(t):
+    if t is None:
+        return "void"
+    if t in (C.c_void_p, C.c_char_p) or hasattr(t, "_type_") and not isinstance(t._type_, str) or "CFunctionType" in str(getattr(t, "__mro__", "")):
+        return "ptr"
+    return {C.c_int: "i32", C.c_int32: "i32", C.c_uint: "i32", C.c_int64: "i64", C.c_uint64: "i64", C.c_longlong: "i64", C.c_size_t: "size",
+            C.c_double: "f64"}.get(t, str(t))
+
+
+def test_the_python_binding_matches_the_header_one_to_one():
+    """openquantumbase.jl_b200/_lib.py SIGNATURES against include/oqb.h: same set of functions, same argument count, same
+    argument class per position."""
+    protos = c_prototypes()
+    import oqb_b200  # noqa: F401
+    from oqb_b200 import _lib
+    problems = []
+    for name in sorted(set(protos) - set(_lib.SIGNATURES)):
+        problems.append(f"{name}: declared in include/oqb.h, no ctypes signature")
+    for name, argtypes in _lib.SIGNATURES.items():
+        if name not in protos:
+            problems.append(f"{name}: ctypes signature without a declaration in include/oqb.h")
+            continue
+        params = protos[name][1]
+        if len(params) != len(argtypes):
+            problems.append(f"{name}: {len(argtypes)} ctypes arguments, the prototype has {len(params)}")
+            continue
+        for k, (at, cp) in enumerate(zip(argtypes, params)):
+            ac, cc = ctypes_class(at), c_class(cp)
+            if ac != cc and {ac, cc} != {"i64", "size"}:
+                problems.append(f"{name}: argument {k + 1} is {at} ({ac}), the prototype says `{cp}` ({cc})")
+    assert not problems, "\n".join(problems)
