@@ -6,7 +6,7 @@ package raises if the CUDA library has not been built or no B200 is present.
 """
 from . import _lib  # noqa: F401
 from .host import (  # noqa: F401
-    ZERO_LAMBSHIFT, AdiabaticFrameHamiltonian, ConstantCouplings, Context, DaviesGenerator, DenseHamiltonian, DensityStepper, DeviceBatch,
+    ZERO_LAMBSHIFT, AdiabaticFrameHamiltonian, ConstantCouplings, ConstantDenseHamiltonian, ConstantHamiltonian, ConstantSparseHamiltonian, Context, Hamiltonian, DaviesGenerator, DenseHamiltonian, DensityStepper, DeviceBatch,
     DiffEqLiouvillian, GapIndices, Lindblad, LindbladLiouvillian, ODEParams, Ohmic, OhmicBath,
     OneSidedAMELiouvillian, QuadraticBSpline, RedfieldLiouvillian, SparseHamiltonian, TrajectoryEnsemble, TrajectoryStepper, ensemble_population, expect, expect_diag,
     build_lambshift, get_context, haml_eigs, lambshift, unit_scale, update_cache_, update_vectorized_cache_,

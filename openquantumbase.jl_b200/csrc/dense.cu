@@ -790,7 +790,8 @@ int dense_rhs_impl(oqb_dense* op, int nb, const double* coefH, int coef_shared, 
 }  // namespace
 
 // Host-only analysis of the Hamiltonian terms (no GPU needed; also behind oqb_dense_structure_probe):
-//   – exactly one term with off-diagonal entries among ≥ 2 terms → the split form H(s) = f_N(s)·m_N + Σ f_i(s)·diag(h_i);
+//   – exactly one term with off-diagonal entries among ≥ 2 terms (or a single Pauli-structured term) → the split form
+//     H(s) = f_N(s)·m_N + Σ f_i(s)·diag(h_i);
 //   – … and that term's non-zeros on ≤ 16 XOR diagonals (n a power of two): m_N[r, r ^ mask_j] = x_j[r] — a sum of Pauli strings.
 struct TermStructure {
     int offdiag_term = -1;
@@ -816,11 +817,16 @@ static void analyze_terms(const c128* Hm, int n, int nterms, TermStructure& ts) 
             last = i;
         }
     }
-    if (noff != 1 || nterms < 2) return;
-    ts.offdiag_term = last;
+    if (noff != 1) return;
+    // a single-term Hamiltonian (ConstantDenseHamiltonian, src/hamiltonian/dense_hamiltonian.jl:149-168) has nothing to split;
+    // it is recorded only when it has Pauli structure (its diagonal part is XOR diagonal 0)
+    const bool single = nterms < 2;
     bool r2 = true;
     for (size_t e = 0; r2 && e < nn; ++e) r2 = Hm[last * nn + e].y == 0.0;
-    ts.offdiag_real = r2;
+    if (!single) {
+        ts.offdiag_term = last;
+        ts.offdiag_real = r2;
+    }
     if ((n & (n - 1)) != 0 || n < 2) return;
     std::vector<int> masks;
     for (int j = 0; j < n; ++j)
@@ -849,6 +855,8 @@ static void analyze_terms(const c128* Hm, int n, int nterms, TermStructure& ts) 
         ts.isconst[q] = cst ? 1 : 0;
     }
     ts.masks = masks;
+    ts.offdiag_term = last;
+    ts.offdiag_real = r2;
 }
 
 extern "C" {

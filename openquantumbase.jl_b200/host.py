@@ -370,6 +370,29 @@ class DenseHamiltonian:
         return H
 
 
+class ConstantDenseHamiltonian(DenseHamiltonian):
+    """src/hamiltonian/dense_hamiltonian.jl:134-168 — a time-independent dense Hamiltonian.  On the device it is the one-term
+    DenseHamiltonian with the coefficient 1 (the s argument of every method is ignored, as in the reference); a single
+    Pauli-structured matrix (a TFIM at fixed s, say) takes the stencil pass like its time-dependent relatives."""
+    isconstant = True
+
+    def __init__(self, mat, unit="h", ctx: Optional[Context] = None):
+        super().__init__([_one], [np.asarray(mat)], unit=unit, ctx=ctx)
+
+    @property
+    def u_cache(self):
+        return self.m[0]
+
+    def __call__(self, *args):
+        if len(args) <= 1:
+            return self.m[0].copy()  # :149-151
+        return super().__call__(*args)
+
+
+def _one(s):
+    return np.ones_like(np.asarray(s, dtype=np.float64))
+
+
 class SparseHamiltonian:
     """src/hamiltonian/sparse_hamiltonian.jl:10-91.  mats: scipy.sparse matrices."""
 
@@ -480,6 +503,39 @@ class SparseHamiltonian:
         for f, m in zip(self.f, self.m):
             H = f(s) * m if H is None else H + f(s) * m
         return H
+
+
+
+class ConstantSparseHamiltonian(SparseHamiltonian):
+    """src/hamiltonian/sparse_hamiltonian.jl:166-203 — a time-independent sparse Hamiltonian: the one-term SparseHamiltonian
+    with the coefficient 1."""
+    isconstant = True
+
+    def __init__(self, mat, unit="h", ctx: Optional[Context] = None):
+        super().__init__([_one], [mat], unit=unit, ctx=ctx)
+
+    @property
+    def u_cache(self):
+        return self.m[0]
+
+
+def ConstantHamiltonian(mat, unit="h", static=True, ctx: Optional[Context] = None):
+    """src/hamiltonian/interface.jl:1-16 (`static` selects the StaticArrays storage in the reference; the arithmetic is the same)."""
+    import scipy.sparse as sps
+    if sps.issparse(mat):
+        return ConstantSparseHamiltonian(mat, unit=unit, ctx=ctx)
+    return ConstantDenseHamiltonian(mat, unit=unit, ctx=ctx)
+
+
+def Hamiltonian(*args, unit="h", dimensionless_time=True, static=True, ctx: Optional[Context] = None):
+    """src/hamiltonian/interface.jl:18-35 — Hamiltonian(mat) is the constant interface, Hamiltonian(f, mats) the time-dependent one."""
+    import scipy.sparse as sps
+    if len(args) == 1:
+        return ConstantHamiltonian(args[0], unit=unit, static=static, ctx=ctx)
+    f, mats = args
+    if sps.issparse(mats[0]):
+        return SparseHamiltonian(f, mats, unit=unit, ctx=ctx)
+    return DenseHamiltonian(f, mats, unit=unit, dimensionless_time=dimensionless_time, ctx=ctx)
 
 
 class AdiabaticFrameHamiltonian:

@@ -79,16 +79,26 @@ shared(s) = Cint(length(s) == 1)
 # ---------------------------------------------------------------- operators: uploaded once per object, immutable afterwards
 const HANDLES = IdDict{Any,Ptr{Cvoid}}()
 
-function dev(H::DenseHamiltonian, lind::Union{Nothing,LindbladLiouvillian}=nothing; c=ctx())
+# Constant Hamiltonians (dense_hamiltonian.jl:134-168, sparse_hamiltonian.jl:166-203) are the one-term case with coefficient 1:
+# the same device operator and entry points (a single Pauli-structured matrix takes the stencil pass inside oqb_dense_rhs).
+const AnyDense = Union{DenseHamiltonian,OpenQuantumBase.ConstantDenseHamiltonian}
+const AnySparse = Union{SparseHamiltonian,OpenQuantumBase.ConstantSparseHamiltonian}
+const ONE = (s -> 1.0,)
+hf(H::Union{DenseHamiltonian,SparseHamiltonian}) = H.f
+hf(::Union{OpenQuantumBase.ConstantDenseHamiltonian,OpenQuantumBase.ConstantSparseHamiltonian}) = ONE
+hm(H::Union{DenseHamiltonian,SparseHamiltonian}) = H.m
+hm(H::Union{OpenQuantumBase.ConstantDenseHamiltonian,OpenQuantumBase.ConstantSparseHamiltonian}) = [H.u_cache]   # already unit-scaled (:141-142)
+
+function dev(H::AnyDense, lind::Union{Nothing,LindbladLiouvillian}=nothing; c=ctx())
     get!(HANDLES, (H, lind)) do
         n = size(H, 1)
-        mats = cat([ComplexF64.(m) for m in H.m]...; dims=3)          # already unit-scaled (dense_hamiltonian.jl:38)
+        mats = cat([ComplexF64.(m) for m in hm(H)]...; dims=3)          # already unit-scaled (dense_hamiltonian.jl:38)
         K = lind === nothing ? 0 : length(lind.L)
         lops = K == 0 ? ComplexF64[] : cat([ComplexF64.(Matrix(L(0.0))) for L in lind.L]...; dims=3)  # constant L_k
         h = Ref{Ptr{Cvoid}}(C_NULL)
         check(c, ccall((:oqb_dense_create, LIB), Cint,
                        (Ptr{Cvoid}, Cint, Cint, Ptr{ComplexF64}, Cint, Ptr{ComplexF64}, Ref{Ptr{Cvoid}}),
-                       c, n, length(H.m), mats, K, lops, h))
+                       c, n, length(hm(H)), mats, K, lops, h))
         h[]
     end
 end
@@ -103,60 +113,60 @@ function pack(ms)
     colptr, rowval, nzval, off
 end
 
-function dev(H::SparseHamiltonian, lind::Union{Nothing,LindbladLiouvillian}=nothing; c=ctx())
+function dev(H::AnySparse, lind::Union{Nothing,LindbladLiouvillian}=nothing; c=ctx())
     get!(HANDLES, (H, lind)) do
         n = size(H, 1)
-        cp, rv, nz, off = pack(H.m)
+        cp, rv, nz, off = pack(hm(H))
         K = lind === nothing ? 0 : length(lind.L)
         h = Ref{Ptr{Cvoid}}(C_NULL)
         if K == 0
             check(c, ccall((:oqb_sparse_create, LIB), Cint,
                            (Ptr{Cvoid}, Cint, Cint, Ptr{Int64}, Ptr{Int64}, Ptr{ComplexF64}, Ptr{Int64}, Cint, Ptr{Int64}, Ptr{Int64},
                             Ptr{ComplexF64}, Ptr{Int64}, Ref{Ptr{Cvoid}}),
-                           c, n, length(H.m), cp, rv, nz, off, 0, C_NULL, C_NULL, C_NULL, C_NULL, h))
+                           c, n, length(hm(H)), cp, rv, nz, off, 0, C_NULL, C_NULL, C_NULL, C_NULL, h))
         else
             lcp, lrv, lnz, loff = pack([sparse(ComplexF64.(L(0.0))) for L in lind.L])
             check(c, ccall((:oqb_sparse_create, LIB), Cint,
                            (Ptr{Cvoid}, Cint, Cint, Ptr{Int64}, Ptr{Int64}, Ptr{ComplexF64}, Ptr{Int64}, Cint, Ptr{Int64}, Ptr{Int64},
                             Ptr{ComplexF64}, Ptr{Int64}, Ref{Ptr{Cvoid}}),
-                           c, n, length(H.m), cp, rv, nz, off, K, lcp, lrv, lnz, loff, h))
+                           c, n, length(hm(H)), cp, rv, nz, off, K, lcp, lrv, lnz, loff, h))
         end
         h[]
     end
 end
 
 # ---------------------------------------------------------------- Hamiltonians
-function (H::DenseHamiltonian)(du::DeviceBatch, u::DeviceBatch, p, s)                  # du = −i[H(s),u]  (OVERWRITES)
+function (H::AnyDense)(du::DeviceBatch, u::DeviceBatch, p, s)                  # du = −i[H(s),u]  (OVERWRITES)
     sv = s isa Real ? Float64[s] : Float64.(s)
     check(u.c, ccall((:oqb_dense_rhs, LIB), Cint,
                      (Ptr{Cvoid}, Cint, Ptr{Float64}, Cint, Ptr{Float64}, Cint, Ptr{Cvoid}, Ptr{Cvoid}),
-                     dev(H), size(u, 3), coef_rows(H.f, sv), shared(sv), C_NULL, 1, u.ptr, du.ptr))
+                     dev(H), size(u, 3), coef_rows(hf(H), sv), shared(sv), C_NULL, 1, u.ptr, du.ptr))
 end
-function update_cache!(cache::DeviceBatch, H::DenseHamiltonian, p, s)                   # cache = −iH(s)
+function update_cache!(cache::DeviceBatch, H::AnyDense, p, s)                   # cache = −iH(s)
     sv = s isa Real ? Float64[s] : Float64.(s)
     check(cache.c, ccall((:oqb_dense_update_cache, LIB), Cint,
                          (Ptr{Cvoid}, Cint, Ptr{Float64}, Cint, Ptr{Float64}, Cint, Ptr{Cvoid}),
-                         dev(H), size(cache, 3), coef_rows(H.f, sv), shared(sv), C_NULL, 1, cache.ptr))
+                         dev(H), size(cache, 3), coef_rows(hf(H), sv), shared(sv), C_NULL, 1, cache.ptr))
 end
-function update_vectorized_cache!(cache::DeviceBatch, H::DenseHamiltonian, p, s)        # cache = i(Hᵀ⊗I − I⊗H)
+function update_vectorized_cache!(cache::DeviceBatch, H::AnyDense, p, s)        # cache = i(Hᵀ⊗I − I⊗H)
     sv = s isa Real ? Float64[s] : Float64.(s)
     check(cache.c, ccall((:oqb_dense_update_vectorized_cache, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}, Cint, Ptr{Cvoid}),
-                         dev(H), size(cache, 3), coef_rows(H.f, sv), shared(sv), cache.ptr))
+                         dev(H), size(cache, 3), coef_rows(hf(H), sv), shared(sv), cache.ptr))
 end
-function (H::SparseHamiltonian)(du::DeviceBatch, u::DeviceBatch, p, s)
+function (H::AnySparse)(du::DeviceBatch, u::DeviceBatch, p, s)
     sv = s isa Real ? Float64[s] : Float64.(s)
     check(u.c, ccall((:oqb_sparse_commutator, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}, Cint, Ptr{Cvoid}, Ptr{Cvoid}),
-                     dev(H), size(u, 3), coef_rows(H.f, sv), shared(sv), u.ptr, du.ptr))
+                     dev(H), size(u, 3), coef_rows(hf(H), sv), shared(sv), u.ptr, du.ptr))
 end
 "update_cache!(cache, H::SparseHamiltonian, p, s): the values on the union pattern, as a SparseMatrixCSC (one member)"
-function update_cache!(cache::SparseMatrixCSC{ComplexF64,Int}, H::SparseHamiltonian, p, s::Real; c=ctx())
+function update_cache!(cache::SparseMatrixCSC{ComplexF64,Int}, H::AnySparse, p, s::Real; c=ctx())
     h = dev(H)
     nnzU = Ref{Int64}(0)
     check(c, ccall((:oqb_sparse_pattern_nnz, LIB), Cint, (Ptr{Cvoid}, Ref{Int64}), h, nnzU))
     d = Ref{Ptr{Cvoid}}(C_NULL)
     check(c, ccall((:oqb_malloc, LIB), Cint, (Ptr{Cvoid}, Csize_t, Ref{Ptr{Cvoid}}), c, 16nnzU[], d))
     check(c, ccall((:oqb_sparse_update_cache, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}, Cint, Ptr{Float64}, Cint, Ptr{Cvoid}),
-                   h, 1, coef_rows(H.f, Float64[s]), 1, C_NULL, 1, d[]))
+                   h, 1, coef_rows(hf(H), Float64[s]), 1, C_NULL, 1, d[]))
     length(cache.nzval) == nnzU[] || error("cache must have the union sparsity pattern of the terms (sparse_hamiltonian.jl:33-34)")
     check(c, ccall((:oqb_download, LIB), Cint, (Ptr{Cvoid}, Ptr{ComplexF64}, Ptr{Cvoid}, Csize_t), c, cache.nzval, d[], 16nnzU[]))
     ccall((:oqb_free, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), c, d[])
@@ -173,7 +183,7 @@ function (Op::DiffEqLiouvillian{false,false})(du::DeviceBatch, u::DeviceBatch, p
         gam = lind === nothing ? C_NULL : Float64[g(sb) for g in lind.γ, sb in s]
         check(u.c, ccall((:oqb_dense_rhs, LIB), Cint,
                          (Ptr{Cvoid}, Cint, Ptr{Float64}, Cint, Ptr{Float64}, Cint, Ptr{Cvoid}, Ptr{Cvoid}),
-                         dev(Op.H, lind), size(u, 3), coef_rows(Op.H.f, s), shared(s), gam, shared(s), u.ptr, du.ptr))
+                         dev(Op.H, lind), size(u, 3), coef_rows(hf(Op.H), s), shared(s), gam, shared(s), u.ptr, du.ptr))
     else
         Op.H(du, u, p, s)                                                # diffeq_liouvillian.jl:72 (s to H …)
     end
@@ -190,7 +200,7 @@ function update_cache!(cache::DeviceBatch, Op::DiffEqLiouvillian{false,false}, p
     gam = lind === nothing ? C_NULL : Float64[g(sb) for g in lind.γ, sb in s]
     check(cache.c, ccall((:oqb_dense_update_cache, LIB), Cint,
                          (Ptr{Cvoid}, Cint, Ptr{Float64}, Cint, Ptr{Float64}, Cint, Ptr{Cvoid}),
-                         dev(Op.H, lind), size(cache, 3), coef_rows(Op.H.f, s), shared(s), gam, shared(s), cache.ptr))
+                         dev(Op.H, lind), size(cache, 3), coef_rows(hf(Op.H), s), shared(s), gam, shared(s), cache.ptr))
 end
 
 "a LindbladLiouvillian on its own ACCUMULATES (lindblad.jl:94-101)"
@@ -265,7 +275,7 @@ end
 function (Op::DiffEqLiouvillian{true,false})(du::DeviceBatch, u::DeviceBatch, p, t)
     s = batch_s(p, t)
     check(u.c, ccall((:oqb_liouv_rhs, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}, Cint, Ptr{Cvoid}, Ptr{Cvoid}),
-                     liouv(Op), size(u, 3), coef_rows(Op.H.f, s), shared(s), u.ptr, du.ptr))   # :92-105 (OVERWRITES)
+                     liouv(Op), size(u, 3), coef_rows(hf(Op.H), s), shared(s), u.ptr, du.ptr))   # :92-105 (OVERWRITES)
     for lv in Op.opensys; lv(du, u, p, t); end                                                 # :106-108
     du
 end
@@ -275,12 +285,12 @@ function (Op::DiffEqLiouvillian{true,false})(du::Array{ComplexF64,3}, u::Array{C
     s = batch_s(p, t)
     c = ctx()
     check(c, ccall((:oqb_liouv_rhs_host, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}, Cint, Ptr{ComplexF64}, Ptr{ComplexF64}),
-                   liouv(Op), size(u, 3), coef_rows(Op.H.f, s), shared(s), u, du))
+                   liouv(Op), size(u, 3), coef_rows(hf(Op.H), s), shared(s), u, du))
     du
 end
 function update_cache!(cache::DeviceBatch, Op::DiffEqLiouvillian{true,false}, p, t::Real)
     check(cache.c, ccall((:oqb_liouv_update_cache, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Cvoid}),
-                         liouv(Op), coef_rows(Op.H.f, Float64[p(t)]), cache.ptr))              # :111-125 (OVERWRITES)
+                         liouv(Op), coef_rows(hf(Op.H), Float64[p(t)]), cache.ptr))              # :111-125 (OVERWRITES)
     for lv in Op.opensys; update_cache!(cache, lv, p, t); end
     cache
 end
@@ -288,7 +298,7 @@ end
 "GapIndices of H(s) from the device grouping, in the reference's own form (uniq_w, uniq_a, uniq_b, a0, b0)"
 function device_gap_indices(Op::DiffEqLiouvillian{true,false}, p, t::Real)
     c = ctx(); plan = Ref{Ptr{Cvoid}}(C_NULL)
-    check(c, ccall((:oqb_liouv_prepare, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ref{Ptr{Cvoid}}), liouv(Op), coef_rows(Op.H.f, Float64[p(t)]), plan))
+    check(c, ccall((:oqb_liouv_prepare, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ref{Ptr{Cvoid}}), liouv(Op), coef_rows(hf(Op.H), Float64[p(t)]), plan))
     nk = Ref{Int64}(0); nz = Ref{Int64}(0)
     check(c, ccall((:oqb_ame_gaps_build, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Ref{Int64}, Ref{Int64}), plan[], Op.digits, Op.sigdigits, nk, nz))
     l = Op.lvl; np = l * (l - 1) ÷ 2 - nz[]
@@ -349,7 +359,7 @@ function traj_matvec!(dψ::DeviceBatch, Op::DiffEqLiouvillian{false,false}, ψ::
     gam = lind === nothing ? C_NULL : Float64[g(sb) for g in lind.γ, sb in s]
     check(ψ.c, ccall((:oqb_traj_matvec, LIB), Cint,
                      (Ptr{Cvoid}, Cint, Ptr{Float64}, Cint, Ptr{Float64}, Cint, Ptr{Cvoid}, Ptr{Cvoid}),
-                     dev(Op.H, lind), size(ψ, 3), coef_rows(Op.H.f, s), shared(s), gam, shared(s), ψ.ptr, dψ.ptr))
+                     dev(Op.H, lind), size(ψ, 3), coef_rows(hf(Op.H), s), shared(s), gam, shared(s), ψ.ptr, dψ.ptr))
 end
 
 "lindblad_jump(Op{false,false}, ψ, p, t) on a batch (trajectory_jump.jl:2-12, :71-74): `uniforms` are the rand() values; returns the chosen operator index per member (0-based) — apply=true performs ψ ← Lψ/‖Lψ‖"

@@ -224,6 +224,70 @@ class SparseHamiltonian:
         return -1.0j * (H @ u - (H.T @ u.T).T)
 
 
+class ConstantDenseHamiltonian:
+    """src/hamiltonian/dense_hamiltonian.jl:134-168: a time-independent dense Hamiltonian (u_cache = unit_scale·mat)."""
+    isconstant = True
+
+    def __init__(self, mat, unit="h"):
+        self.u_cache = unit_scale(unit) * np.asarray(mat, dtype=C128)  # :141
+        self.size = self.u_cache.shape
+
+    def __call__(self, s: float = 0.0) -> np.ndarray:
+        return self.u_cache  # :149-151
+
+    def update_cache(self, s: float = 0.0) -> np.ndarray:
+        return -1.0j * self.u_cache  # :153-155
+
+    def update_vectorized_cache(self, s: float = 0.0) -> np.ndarray:
+        h = self.u_cache  # :157-161
+        iden = np.eye(h.shape[0], dtype=C128)
+        return 1.0j * (np.kron(h.T, iden) - np.kron(iden, h))
+
+    def rhs(self, u: np.ndarray, s: float = 0.0) -> np.ndarray:
+        """:163-168  fill!(du, 0); gemm!(-i, H, u, 1, du); gemm!(+i, u, H, 1, du)."""
+        du = np.zeros_like(u, dtype=C128)
+        du += -1.0j * (self.u_cache @ u)
+        du += 1.0j * (u @ self.u_cache)
+        return du
+
+
+class ConstantSparseHamiltonian:
+    """src/hamiltonian/sparse_hamiltonian.jl:166-203."""
+    isconstant = True
+
+    def __init__(self, mat, unit="h"):
+        self.u_cache = sps.csc_matrix(unit_scale(unit) * sps.csc_matrix(mat).astype(C128))  # interface.jl:13-16
+        self.size = self.u_cache.shape
+
+    def __call__(self, s: float = 0.0):
+        return self.u_cache  # :181-183
+
+    def update_cache(self, s: float = 0.0):
+        return -1.0j * self.u_cache  # :185-187
+
+    def update_vectorized_cache(self, s: float = 0.0):
+        h = self.u_cache  # :189-193
+        iden = sps.identity(self.size[0], dtype=C128, format="csc")
+        return 1.0j * (sps.kron(h.T, iden) - sps.kron(iden, h))
+
+    def rhs(self, u: np.ndarray, s: float = 0.0) -> np.ndarray:
+        H = self.u_cache  # :195-203  du .= -i (H*u - u*H)
+        return -1.0j * (H @ u - (H.T @ u.T).T)
+
+
+def ConstantHamiltonian(mat, unit="h"):
+    """src/hamiltonian/interface.jl:1-16 (the static-array variant only differs in storage)."""
+    return ConstantSparseHamiltonian(mat, unit=unit) if sps.issparse(mat) else ConstantDenseHamiltonian(mat, unit=unit)
+
+
+def Hamiltonian(*args, unit="h"):
+    """src/hamiltonian/interface.jl:18-35: Hamiltonian(mat) is the constant interface, Hamiltonian(f, mats) the time-dependent one."""
+    if len(args) == 1:
+        return ConstantHamiltonian(args[0], unit=unit)
+    f, mats = args
+    return SparseHamiltonian(f, mats, unit=unit) if sps.issparse(mats[0]) else DenseHamiltonian(f, mats, unit=unit)
+
+
 def haml_eigs(H, s: float, lvl: Optional[int]):
     """src/hamiltonian/hamiltonian_base.jl:155-160: eigen!(Hermitian(Array(H(t))), 1:lvl).
     LAPACK's eigenvector gauge is not reproducible across builds; every parity test feeds

@@ -122,7 +122,8 @@ def test_no_structure_cases():
     A, B = herm(rng.standard_normal((n, n)) + 0j), herm(rng.standard_normal((n, n)) + 0j)
     D = np.diag(rng.standard_normal(n)).astype(complex)
     assert probe([A, B])["offdiag_term"] == -1                     # two terms with off-diagonal entries
-    assert probe([A])["offdiag_term"] == -1                        # a single term: nothing to split
+    A32 = herm(rng.standard_normal((32, 32)) + 0j)
+    assert probe([A32])["offdiag_term"] == -1                      # a single term without Pauli structure: nothing to split
     st = probe([A, D])                                             # split form, but a dense random term has n XOR diagonals ≤ 16 here
     assert st["offdiag_term"] == 0 and len(st["masks"]) == 16
     n = 32
@@ -143,3 +144,18 @@ def test_probe_rejects_bad_arguments():
     lib = _lib.load()
     assert lib.oqb_dense_structure_probe(0, 1, None, None, None, None, None, None, None) != 0
     assert lib.oqb_dense_structure_probe(4, 1, None, None, None, None, None, None, None) != 0
+
+
+def test_single_term_pauli_hamiltonian_is_recorded():
+    """ConstantDenseHamiltonian-shaped input (src/hamiltonian/dense_hamiltonian.jl:149-168): the whole TFIM at fixed s as ONE
+    matrix — X part on one XOR diagonal per qubit, ZZ part on XOR diagonal 0."""
+    nq, n = 5, 32
+    H = pauli_sum(nq, [(-0.6, {q: "X"}) for q in range(1, nq + 1)] + [(-0.4, {q: "Z", q + 1: "Z"}) for q in range(1, nq)])
+    st = probe([H])
+    assert st["offdiag_term"] == 0 and st["masks"] == [0] + [1 << b for b in range(nq)]
+    assert st["isconst"][0] == 0 and st["isconst"][1:] == [1] * nq and st["all_real"]
+    rng = np.random.default_rng(9)
+    u = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))
+    got = stencil_commutator(u, [1.0], [H], st)
+    ref = -1j * (H @ u - u @ H)
+    assert np.linalg.norm(got - ref) / np.linalg.norm(ref) < 1e-13

@@ -89,6 +89,37 @@ def test_constant_hamiltonian_values():
     assert np.allclose(H3.rhs(r3, 1), -1j * (h3 @ r3 - r3 @ h3), atol=1e-15)          # :46
 
 
+def test_constant_hamiltonian_interface():
+    """test/hamiltonian/constant_hamiltonian.jl through the oracle's ConstantHamiltonian / Hamiltonian interface
+    (src/hamiltonian/interface.jl:1-35, dense_hamiltonian.jl:134-168, sparse_hamiltonian.jl:166-203)."""
+    H1 = O.ConstantHamiltonian(sx, unit="ħ")
+    H2 = O.ConstantHamiltonian(sx)
+    H3 = O.ConstantHamiltonian(sps.csc_matrix(np.kron(sx, sx)))
+    Hs1, Hs3 = O.Hamiltonian(sx, unit="ħ"), O.Hamiltonian(sps.csc_matrix(np.kron(sx, sx)))
+    assert isinstance(H1, O.ConstantDenseHamiltonian) and isinstance(H3, O.ConstantSparseHamiltonian) and H1.isconstant and H3.isconstant
+    assert np.array_equal(H1(2), sx) and np.array_equal(Hs1(2), sx)                                 # :17
+    assert np.array_equal(H2(1), 2 * np.pi * sx)                                                     # :18
+    assert np.array_equal(H3(0.2).toarray(), 2 * np.pi * np.kron(sx, sx))                            # :19
+    assert np.array_equal(Hs3(0.2).toarray(), H3(0.2).toarray())
+    assert np.array_equal(H1.update_cache(0.2), -1j * sx)                                            # :26
+    assert np.array_equal(H2.update_cache(0.1), -2 * np.pi * 1j * sx)                                # :27
+    assert np.array_equal(H3.update_cache(0.5).toarray(), -2 * np.pi * 1j * np.kron(sx, sx))         # :28
+    assert np.array_equal(H1.update_vectorized_cache(0.2), -1j * O.vectorized_commutator(H1(0.1)))   # :36
+    assert np.allclose(H3.update_vectorized_cache(0.5).toarray(), -1j * O.vectorized_commutator(H3(2).toarray()))  # :38
+    r1 = np.ones((2, 2), dtype=complex) / 2
+    r3 = np.ones((4, 4), dtype=complex) / 4
+    assert np.allclose(H1.rhs(r1, 0), -1j * (H1(0) @ r1 - r1 @ H1(0)), atol=1e-15)                   # :44
+    h3 = H3(1).toarray()
+    assert np.allclose(H3.rhs(r3, 1), -1j * (h3 @ r3 - r3 @ h3), atol=1e-15)                         # :46
+    w1, _ = O.eigen_decomp(H1, 0)
+    w2, _ = O.eigen_decomp(H2, 0.5)
+    w3, _ = O.eigen_decomp(H3, 1, lvl=4)
+    assert np.allclose(w1, np.array([-1, 1]) / 2 / np.pi) and np.allclose(w2, [-1, 1]) and np.allclose(w3, [-1, -1, 1, 1])  # :48-57
+    # the time-dependent interface picks the storage by the matrix type (interface.jl:18-33)
+    assert isinstance(O.Hamiltonian([lambda s: s], [sx]), O.DenseHamiltonian)
+    assert isinstance(O.Hamiltonian([lambda s: s], [sps.csc_matrix(sx)]), O.SparseHamiltonian)
+
+
 # ---- test/annealing.jl:19-22 ; test/coupling_bath_interaction/bath.jl:3-14 -----------------
 def test_odeparams_and_ohmic():
     p = O.ODEParams(None, 10.0, lambda tf, t: t / tf)
