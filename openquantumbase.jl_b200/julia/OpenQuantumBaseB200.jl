@@ -16,7 +16,12 @@
 #   (Op::DiffEqLiouvillian{true,false})(du, u, p, t), update_cache!            diffeq_liouvillian.jl:92,111
 #   (R::RedfieldLiouvillian)(du, u, p, t) with Λ supplied on the device        redfield.jl:65-68
 #   traj_matvec!(dψ, Op, ψ, p, t), lindblad_jump(Op{false,false}, ψ, p, t; uniforms)   trajectory_jump.jl:71-74
-#   ensemble_expect_allreduce!(comm, out, obs, ψ)                               the ensemble-average reduce (SURVEY §8(e))
+#   lindblad_jump(Op{false,false}, ψ, p, t, uniforms::Matrix) with several Liouvillians + resample   trajectory_jump.jl:71-88
+#   the same methods for ConstantDenseHamiltonian / ConstantSparseHamiltonian (one term, coefficient 1)   dense_hamiltonian.jl:134-168
+#   redfield_vectorized!(cache, S, Λ)                                          redfield.jl:97-102
+#   norm2(Op, ψ), expect(obs, state), free!(H)
+#   ensemble_expect_allreduce!(comm, out, obs, ψ), allgather_obs!               the ensemble-average reduce / per-schedule gather (SURVEY §8(e))
+# tests/test_julia_glue_static.py checks every ccall below against include/oqb.h (symbol exported, argument count, argument classes).
 module OpenQuantumBaseB200
 
 using OpenQuantumBase
@@ -173,6 +178,19 @@ function update_cache!(cache::SparseMatrixCSC{ComplexF64,Int}, H::AnySparse, p, 
     cache
 end
 
+function update_vectorized_cache!(cache::DeviceBatch, H::AnySparse, p, s)                 # cache = i(Hᵀ⊗I − I⊗H), dense n²×n² (small n)
+    sv = s isa Real ? Float64[s] : Float64.(s)
+    check(cache.c, ccall((:oqb_sparse_update_vectorized_cache, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}, Cint, Ptr{Cvoid}),
+                         dev(H), size(cache, 3), coef_rows(hf(H), sv), shared(sv), cache.ptr))
+end
+"release the device operator of a Hamiltonian (and Lindblad set) explicitly; otherwise it lives as long as the process"
+function free!(H::Union{AnyDense,AnySparse}, lind::Union{Nothing,LindbladLiouvillian}=nothing)
+    h = pop!(HANDLES, (H, lind), C_NULL)
+    h == C_NULL && return
+    H isa AnyDense ? ccall((:oqb_dense_destroy, LIB), Cint, (Ptr{Cvoid},), h) : ccall((:oqb_sparse_destroy, LIB), Cint, (Ptr{Cvoid},), h)
+    nothing
+end
+
 # ---------------------------------------------------------------- DiffEqLiouvillian{false,false}: H + Lindblad (+ others)
 lindblad_of(Op) = (i = findfirst(x -> x isa LindbladLiouvillian, Op.opensys); i === nothing ? nothing : Op.opensys[i])
 
@@ -319,6 +337,13 @@ function redfield_apply!(du::DeviceBatch, u::DeviceBatch, S::DeviceBatch, Λ::De
                      u.c, n, K, S.ptr, 1 | (real_couplings ? 2 : 0), Λ.ptr, size(u, 3), u.ptr, du.ptr))
 end
 
+"cache (n²×n²×B) −= I⊗SΛ + conj(SΛ)⊗I − Sᵀ⊗Λ − conj(Λ)⊗S: update_vectorized_cache!(cache, R::RedfieldLiouvillian, p, t), redfield.jl:97-102 (ACCUMULATES)"
+function redfield_vectorized!(cache::DeviceBatch, S::DeviceBatch, Λ::DeviceBatch)
+    n, K = size(S, 1), size(S, 3)
+    check(cache.c, ccall((:oqb_redfield_vectorized_acc, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{Cvoid}, Cint, Ptr{Cvoid}, Cint, Ptr{Cvoid}),
+                         cache.c, n, K, S.ptr, 1, Λ.ptr, size(cache, 3), cache.ptr))
+end
+
 "raw device copy of a host array (freed by the caller with oqb_free)"
 function device_copy(c, a::Array)
     d = Ref{Ptr{Cvoid}}(C_NULL)
@@ -364,7 +389,7 @@ end
 
 "lindblad_jump(Op{false,false}, ψ, p, t) on a batch (trajectory_jump.jl:2-12, :71-74): `uniforms` are the rand() values; returns the chosen operator index per member (0-based) — apply=true performs ψ ← Lψ/‖Lψ‖"
 function lindblad_jump(Op::DiffEqLiouvillian{false,false}, ψ::DeviceBatch, p, t::Real; uniforms::Vector{Float64}, apply=false)
-    length(Op.opensys) == 1 || error("several Liouvillians: propose per Liouvillian with this method, then oqb_traj_apply_choice + oqb_resample (include/oqb.h)")
+    length(Op.opensys) == 1 || error("several Liouvillians: use lindblad_jump(Op, ψ, p, t, uniforms::Matrix) — one uniform per Liouvillian and one for resample")
     lind = Op.opensys[1]::LindbladLiouvillian
     c = ψ.c; B = size(ψ, 3); s = p(t)
     gam = Float64[g(s) for g in lind.γ]
@@ -381,6 +406,72 @@ function lindblad_jump(Op::DiffEqLiouvillian{false,false}, ψ::DeviceBatch, p, t
     choice
 end
 
+"lindblad_jump with SEVERAL LindbladLiouvillians in Op.opensys (trajectory_jump.jl:71-79): Liouvillian m proposes one operator with its own
+uniform `uniforms[:, m]`; `resample` (:81-88) draws the winner with `uniforms[:, M+1]` and the weights ‖L_mψ‖ (first power).  Returns
+(pick, choices): the winning Liouvillian and every proposal per member, 0-based; apply=true performs ψ ← Lψ/‖Lψ‖ with the winner"
+function lindblad_jump(Op::DiffEqLiouvillian{false,false}, ψ::DeviceBatch, p, t::Real, uniforms::Matrix{Float64}; apply=false)
+    M = length(Op.opensys); c = ψ.c; B = size(ψ, 3); s = p(t)
+    size(uniforms) == (B, M + 1) || error("uniforms must be B × (M+1): one column per Liouvillian and one for resample")
+    dchoice = Ref{Ptr{Cvoid}}(C_NULL); dw = Ref{Ptr{Cvoid}}(C_NULL); dpick = Ref{Ptr{Cvoid}}(C_NULL)
+    check(c, ccall((:oqb_malloc, LIB), Cint, (Ptr{Cvoid}, Csize_t, Ref{Ptr{Cvoid}}), c, 4B * M, dchoice))
+    check(c, ccall((:oqb_malloc, LIB), Cint, (Ptr{Cvoid}, Csize_t, Ref{Ptr{Cvoid}}), c, 8B * M, dw))
+    check(c, ccall((:oqb_malloc, LIB), Cint, (Ptr{Cvoid}, Csize_t, Ref{Ptr{Cvoid}}), c, 4B, dpick))
+    for m in 1:M
+        lind = Op.opensys[m]::LindbladLiouvillian
+        gam = Float64[g(s) for g in lind.γ]
+        du = device_copy(c, uniforms[:, m])
+        check(c, ccall((:oqb_traj_jump, LIB), Cint,
+                       (Ptr{Cvoid}, Cint, Ptr{Float64}, Cint, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cint),
+                       dev(Op.H, lind), B, gam, 1, ψ.ptr, du, C_NULL, dchoice[] + 4B * (m - 1), C_NULL, 0))
+        check(c, ccall((:oqb_traj_apply_choice, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cint),
+                       dev(Op.H, lind), B, ψ.ptr, dchoice[] + 4B * (m - 1), C_NULL, dw[] + 8B * (m - 1), 0))      # weight row m = ‖L_mψ‖
+        ccall((:oqb_sync, LIB), Cint, (Ptr{Cvoid},), c); ccall((:oqb_free, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), c, du)
+    end
+    dur = device_copy(c, uniforms[:, M + 1])
+    check(c, ccall((:oqb_resample, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}),
+                   c, B, M, dw[], dur, C_NULL, dpick[]))
+    pick = Vector{Int32}(undef, B); choices = Matrix{Int32}(undef, B, M)
+    check(c, ccall((:oqb_download, LIB), Cint, (Ptr{Cvoid}, Ptr{Int32}, Ptr{Cvoid}, Csize_t), c, pick, dpick[], 4B))
+    check(c, ccall((:oqb_download, LIB), Cint, (Ptr{Cvoid}, Ptr{Int32}, Ptr{Cvoid}, Csize_t), c, choices, dchoice[], 4B * M))
+    if apply
+        for m in 1:M
+            dmask = device_copy(c, UInt8.(pick .== m - 1))
+            check(c, ccall((:oqb_traj_apply_choice, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cint),
+                           dev(Op.H, Op.opensys[m]), B, ψ.ptr, dchoice[] + 4B * (m - 1), dmask, C_NULL, 1))
+            ccall((:oqb_sync, LIB), Cint, (Ptr{Cvoid},), c); ccall((:oqb_free, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), c, dmask)
+        end
+    end
+    for d in (dchoice[], dw[], dpick[], dur)
+        ccall((:oqb_free, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), c, d)
+    end
+    pick, choices
+end
+
+"‖ψ_b‖² per member — the jump condition of the external callback"
+function norm2(Op::DiffEqLiouvillian{false,false}, ψ::DeviceBatch)
+    c = ψ.c; B = size(ψ, 3)
+    d = Ref{Ptr{Cvoid}}(C_NULL)
+    check(c, ccall((:oqb_malloc, LIB), Cint, (Ptr{Cvoid}, Csize_t, Ref{Ptr{Cvoid}}), c, 8B, d))
+    check(c, ccall((:oqb_traj_norm2, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Cvoid}, Ptr{Cvoid}), dev(Op.H, lindblad_of(Op)), B, ψ.ptr, d[]))
+    out = Vector{Float64}(undef, B)
+    check(c, ccall((:oqb_download, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Cvoid}, Csize_t), c, out, d[], 8B))
+    ccall((:oqb_free, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), c, d[])
+    out
+end
+
+"out[o, b] = tr(O_o ρ_b) (states n×n×B) or ψ_b'O_oψ_b (states n×1×B) for dense observables obs (n×n×nobs on the device)"
+function expect(obs::DeviceBatch, state::DeviceBatch)
+    c = state.c; B = size(state, 3); nobs = size(obs, 3)
+    d = Ref{Ptr{Cvoid}}(C_NULL)
+    check(c, ccall((:oqb_malloc, LIB), Cint, (Ptr{Cvoid}, Csize_t, Ref{Ptr{Cvoid}}), c, 16B * nobs, d))
+    check(c, ccall((:oqb_expect, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{Cvoid}, Cint, Ptr{Cvoid}, Cint, Ptr{Cvoid}),
+                   c, size(obs, 1), nobs, obs.ptr, B, state.ptr, size(state, 2) == 1 ? 1 : 0, d[]))
+    out = Matrix{ComplexF64}(undef, nobs, B)
+    check(c, ccall((:oqb_download, LIB), Cint, (Ptr{Cvoid}, Ptr{ComplexF64}, Ptr{Cvoid}, Csize_t), c, out, d[], 16B * nobs))
+    ccall((:oqb_free, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), c, d[])
+    out
+end
+
 # ---------------------------------------------------------------- multi-GPU: the ensemble-average reduce
 "one communicator per GPU of this process (ncclCommInitAll); use with Threads.@threads over devices, one ctx(device) per thread"
 function comm_init_all(ctxs::Vector{Ptr{Cvoid}})
@@ -395,5 +486,10 @@ function ensemble_expect_allreduce!(comm::Ptr{Cvoid}, out::Ptr{Cvoid}, obs::Devi
                    c, size(obs, 1), size(obs, 3), obs.ptr, size(ψ, 3), ψ.ptr, is_vector ? 1 : 0, out))
     check(c, ccall((:oqb_allreduce_obs, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Int64), comm, out, 2size(obs, 3)))
 end
+
+"per-schedule observables of ALL GPUs, rank-major (C5: one ncclAllGather per output point); send/recv are device pointers to count / count·nranks doubles"
+allgather_obs!(comm::Ptr{Cvoid}, send::Ptr{Cvoid}, recv::Ptr{Cvoid}, count::Integer, c=ctx()) =
+    check(c, ccall((:oqb_allgather_obs, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64), comm, send, recv, count))
+comm_destroy(comm::Ptr{Cvoid}) = ccall((:oqb_comm_destroy, LIB), Cint, (Ptr{Cvoid},), comm)
 
 end # module
