@@ -19,6 +19,7 @@
 #   lindblad_jump(Op{false,false}, ψ, p, t, uniforms::Matrix) with several Liouvillians + resample   trajectory_jump.jl:71-88
 #   the same methods for ConstantDenseHamiltonian / ConstantSparseHamiltonian (one term, coefficient 1)   dense_hamiltonian.jl:134-168
 #   redfield_vectorized!(cache, S, Λ)                                          redfield.jl:97-102
+#   lindblad_jump(Op{true,false}, ψ, p, t; uniforms) — ame_jump for a DaviesGenerator                 trajectory_jump.jl:14-51,64-69
 #   norm2(Op, ψ), expect(obs, state), free!(H)
 #   ensemble_expect_allreduce!(comm, out, obs, ψ), allgather_obs!               the ensemble-average reduce / per-schedule gather (SURVEY §8(e))
 # tests/test_julia_glue_static.py checks every ccall below against include/oqb.h (symbol exported, argument count, argument classes).
@@ -326,6 +327,40 @@ function device_gap_indices(Op::DiffEqLiouvillian{true,false}, p, t::Real)
     check(c, ccall((:oqb_ame_gaps_fetch, LIB), Cint, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}), plan[], gptr, a, b, a0, b0))
     uniq_a = [Int.(a[gptr[g]+1:gptr[g+1]]) for g in 1:nk[]]; uniq_b = [Int.(b[gptr[g]+1:gptr[g+1]]) for g in 1:nk[]]
     keys, uniq_a, uniq_b, Int.(a0), Int.(b0)
+end
+
+"lindblad_jump(Op::DiffEqLiouvillian{true,false}, ψ, p, t) on a batch — ame_jump for ONE DaviesGenerator (trajectory_jump.jl:14-51, :64-69).
+The probability slots are listed in the reference's order: for every unique positive gap (ascending) and coupling i, L₊ = sparse(a, b, σ_i[a,b])
+with rate γ(ω), then L₋ = sparse(b, a, σ_i[b,a]) with rate γ(−ω); then, per coupling, the zero-gap group with rate γ(0).  Returns the chosen
+slot per member (0-based); apply=true performs ψ ← v L v'ψ / ‖·‖."
+function lindblad_jump(Op::DiffEqLiouvillian{true,false}, ψ::DeviceBatch, p, t::Real; uniforms::Vector{Float64}, apply=false)
+    length(Op.opensys_eig) == 1 && Op.opensys_eig[1] isa DaviesGenerator || error("ame_jump is defined for one DaviesGenerator (trajectory_jump.jl:14)")
+    D = Op.opensys_eig[1]; K = length(D.coupling.mats); c = ψ.c; B = size(ψ, 3)
+    keys, ua, ub, a0, b0 = device_gap_indices(Op, p, t)                       # 1-based, reference order
+    slot_ptr = Int64[0]; term = Int32[]; rate = Float64[]
+    function slot!(i, rows, cols, r)                                         # entries sorted by (row, col), 0-based (coupling, row, col) triples
+        for j in sortperm(collect(zip(rows, cols)))
+            push!(term, i - 1, rows[j] - 1, cols[j] - 1)
+        end
+        push!(slot_ptr, length(term) ÷ 3); push!(rate, r)
+    end
+    for (g, w) in enumerate(keys), i in 1:K
+        slot!(i, ua[g], ub[g], D.γ(w)); slot!(i, ub[g], ua[g], D.γ(-w))
+    end
+    for i in 1:K
+        slot!(i, a0, b0, D.γ(0.0))
+    end
+    plan = Ref{Ptr{Cvoid}}(C_NULL)
+    check(c, ccall((:oqb_liouv_prepare, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ref{Ptr{Cvoid}}), liouv(Op), coef_rows(hf(Op.H), Float64[p(t)]), plan))
+    check(c, ccall((:oqb_ame_set_jump, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Int64}, Ptr{Int32}, Ptr{Float64}), plan[], length(rate), slot_ptr, term, rate))
+    du = device_copy(c, uniforms); dc = Ref{Ptr{Cvoid}}(C_NULL)
+    check(c, ccall((:oqb_malloc, LIB), Cint, (Ptr{Cvoid}, Csize_t, Ref{Ptr{Cvoid}}), c, 4B, dc))
+    check(c, ccall((:oqb_ame_jump, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cint),
+                   plan[], B, ψ.ptr, du, C_NULL, dc[], C_NULL, apply ? 1 : 0))
+    choice = Vector{Int32}(undef, B)
+    check(c, ccall((:oqb_download, LIB), Cint, (Ptr{Cvoid}, Ptr{Int32}, Ptr{Cvoid}, Csize_t), c, choice, dc[], 4B))
+    ccall((:oqb_free, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), c, du); ccall((:oqb_free, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), c, dc[])
+    choice
 end
 
 # ---------------------------------------------------------------- Redfield: apply step with Λ on the device
