@@ -159,3 +159,31 @@ def test_single_term_pauli_hamiltonian_is_recorded():
     got = stencil_commutator(u, [1.0], [H], st)
     ref = -1j * (H @ u - u @ H)
     assert np.linalg.norm(got - ref) / np.linalg.norm(ref) < 1e-13
+
+
+@pytest.mark.parametrize("nq", [3, 5])
+def test_fused_stencil_and_hadamard_formula_is_the_lindblad_rhs(nq):
+    """The whole one-pass RHS the stencil kernels evaluate for diagonal L_k with shared rates,
+        du = stencil commutator + G∘u,  G[r,c] = Σ_k γ_k (d_k[r] conj(d_k[c]) − ½(|d_k[r]|² + |d_k[c]|²)),
+    restated in numpy from the probe's tables against the oracle's literal loop (src/opensys/lindblad.jl:94-101 after
+    src/opensys/diffeq_liouvillian.jl:70-76)."""
+    n = 1 << nq
+    rng = np.random.default_rng(40 + nq)
+    Hd = pauli_sum(nq, [(-1.0 - 0.1 * q, {q: "X"}) for q in range(1, nq + 1)] + [(0.25, {q: "Y", q + 1: "Y"}) for q in range(1, nq)])
+    Hp = np.diag(rng.standard_normal(n)).astype(complex)
+    st = probe([Hd, Hp])
+    assert st["offdiag_term"] == 0 and len(st["masks"]) > 0
+    ds = [np.exp(1j * rng.standard_normal(n)) * rng.standard_normal(n) for _ in range(nq)]  # complex diagonal L_k
+    gam = [0.05 * (1 + k) for k in range(nq)]
+    fs = [lambda s: 1 - s, lambda s: s]
+    opo = O.DiffEqLiouvillian(O.DenseHamiltonian(fs, [Hd, Hp], unit="ħ"), [],
+                              [O.LindbladLiouvillian([O.Lindblad(g, np.diag(d)) for g, d in zip(gam, ds)])], n)
+    u = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))
+    tf, t = 10.0, 3.7
+    s = t / tf
+    G = np.zeros((n, n), dtype=complex)
+    for g, d in zip(gam, ds):
+        G += g * (np.outer(d, d.conj()) - 0.5 * (np.abs(d)[:, None] ** 2 + np.abs(d)[None, :] ** 2))
+    got = stencil_commutator(u, [f(s) for f in fs], [Hd, Hp], st) + G * u
+    ref = opo.rhs(u, O.ODEParams(None, tf), t)
+    assert np.linalg.norm(got - ref) / np.linalg.norm(ref) < 1e-13
