@@ -200,39 +200,83 @@ __global__ void hadamard_acc_split_kernel(int n, int nt, const c128* __restrict_
 }
 
 // Monomial L_k: (L_k u L_k')[a,c] = v_k[a] conj(v_k[c]) u[π_k(a), π_k(c)] — a gather of u instead of two n³ products.
-// One block per column c (π_k(c), v_k[c] are block-uniform), threads over the rows; u_b (n² entries) is read K times from L2.
-// with_anti: also −½ Σ_k γ_bk (lld_k[a] + lld_k[c]) u[a,c] (the anticommutator, when it was kept out of the GEMM operand).
-__global__ void lindblad_mono_sandwich_kernel(int n, int K, const int32_t* __restrict__ perm, const c128* __restrict__ val,
-                                              const double* __restrict__ lld, const double* __restrict__ gamma, int gamma_ld,
-                                              const c128* __restrict__ u, c128* __restrict__ du, int with_anti) {
-    const int cc = blockIdx.x;
+// One block per MONO_CB columns c, threads over the rows: everything that depends on the column only (π_k(c), γ_k conj(v_k[c]),
+// −½Σ_k γ_k lld_k[c]) is staged in shared memory once per block, everything that depends on the row only (π_k(a), v_k[a], the
+// row half of the anticommutator) is fetched once per thread and serves all MONO_CB columns; u_b is gathered K times from L2.
+// with_anti: also −½ Σ_k γ_bk (lld_k[a] + lld_k[c]) u[a,c] (the anticommutator, when it was kept out of the commutator's operand).
+constexpr int MONO_CB = 8;
+__global__ void __launch_bounds__(256) lindblad_mono_sandwich_kernel(int n, int K, const int32_t* __restrict__ perm, const c128* __restrict__ val,
+                                                                     const double* __restrict__ lld, const double* __restrict__ gamma, int gamma_ld,
+                                                                     const c128* __restrict__ u, c128* __restrict__ du, int with_anti) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    c128* s_w = reinterpret_cast<c128*>(smem_raw);                 // [K][CB]  γ_k conj(v_k[c])
+    double* s_anti = reinterpret_cast<double*>(s_w + (size_t)K * MONO_CB);  // [CB]  −½ Σ_k γ_k lld_k[c]
+    double* s_g = s_anti + MONO_CB;                                 // [K]
+    int* s_pc = reinterpret_cast<int*>(s_g + K);                    // [K][CB]  π_k(c), −1 = empty column (or c ≥ n)
+    const int c0 = blockIdx.x * MONO_CB;
     const long long b = blockIdx.y, nn = (long long)n * n;
     const c128* ub = u + b * nn;
     c128* dub = du + b * nn;
     const double* g = gamma + b * gamma_ld;
+    for (int t = threadIdx.x; t < K * MONO_CB; t += blockDim.x) {
+        const int k = t / MONO_CB, c = c0 + t % MONO_CB;
+        int pc = -1;
+        c128 w = make_double2(0.0, 0.0);
+        if (c < n) {
+            pc = perm[(size_t)k * n + c];
+            const c128 vc = val[(size_t)k * n + c];
+            w = make_double2(g[k] * vc.x, -g[k] * vc.y);
+        }
+        s_pc[t] = pc;
+        s_w[t] = w;
+    }
+    for (int k = threadIdx.x; k < K; k += blockDim.x) s_g[k] = g[k];
+    if (threadIdx.x < MONO_CB) {
+        const int c = c0 + threadIdx.x;
+        double acc = 0.0;
+        if (with_anti && c < n)
+            for (int k = 0; k < K; ++k) acc = fma(-0.5 * g[k], lld[(size_t)k * n + c], acc);
+        s_anti[threadIdx.x] = acc;
+    }
+    __syncthreads();
     for (int a = threadIdx.x; a < n; a += blockDim.x) {
-        double sr = 0.0, si = 0.0, anti = 0.0;
+        double sr[MONO_CB], si[MONO_CB];
+#pragma unroll
+        for (int j = 0; j < MONO_CB; ++j) sr[j] = si[j] = 0.0;
+        double anti_a = 0.0;
         for (int k = 0; k < K; ++k) {
-            const int pc = perm[(size_t)k * n + cc], pa = perm[(size_t)k * n + a];
-            const double gk = g[k];
-            if (with_anti) anti = fma(-0.5 * gk, lld[(size_t)k * n + a] + lld[(size_t)k * n + cc], anti);
-            if (pc < 0 || pa < 0) continue;
-            const c128 va = val[(size_t)k * n + a], vc = val[(size_t)k * n + cc];
-            const double wr = gk * (va.x * vc.x + va.y * vc.y), wi = gk * (va.y * vc.x - va.x * vc.y);  // γ v_a conj(v_c)
-            const c128 x = ub[pa + (long long)pc * n];
-            sr = fma(wr, x.x, sr); sr = fma(-wi, x.y, sr);
-            si = fma(wr, x.y, si); si = fma(wi, x.x, si);
+            if (with_anti) anti_a = fma(-0.5 * s_g[k], lld[(size_t)k * n + a], anti_a);
+            const int pa = perm[(size_t)k * n + a];
+            if (pa < 0) continue;
+            const c128 va = val[(size_t)k * n + a];
+#pragma unroll
+            for (int j = 0; j < MONO_CB; ++j) {
+                const int pc = s_pc[k * MONO_CB + j];
+                if (pc < 0) continue;
+                const c128 wc = s_w[k * MONO_CB + j];
+                const double wr = va.x * wc.x - va.y * wc.y, wi = va.x * wc.y + va.y * wc.x;  // γ v_a conj(v_c)
+                const c128 x = ub[pa + (long long)pc * n];
+                sr[j] = fma(wr, x.x, sr[j]); sr[j] = fma(-wi, x.y, sr[j]);
+                si[j] = fma(wr, x.y, si[j]); si[j] = fma(wi, x.x, si[j]);
+            }
         }
-        const long long e = a + (long long)cc * n;
-        c128 o = dub[e];
-        if (with_anti) {
-            const c128 x = ub[e];
-            sr = fma(anti, x.x, sr);
-            si = fma(anti, x.y, si);
+#pragma unroll
+        for (int j = 0; j < MONO_CB; ++j) {
+            const int c = c0 + j;
+            if (c >= n) break;
+            const long long e = a + (long long)c * n;
+            c128 o = dub[e];
+            double r = sr[j], i = si[j];
+            if (with_anti) {
+                const c128 x = ub[e];
+                const double f = anti_a + s_anti[j];
+                r = fma(f, x.x, r);
+                i = fma(f, x.y, i);
+            }
+            o.x += r;
+            o.y += i;
+            dub[e] = o;
         }
-        o.x += sr;
-        o.y += si;
-        dub[e] = o;
     }
 }
 
@@ -773,8 +817,9 @@ int dense_rhs_impl(oqb_dense* op, int nb, const double* coefH, int coef_shared, 
             } else if (use_mono) {
                 for (int m0 = 0; m0 < cnt; m0 += 65535) {
                     const int mc = cnt - m0 < 65535 ? cnt - m0 : 65535;
-                    dim3 grid((unsigned)n, mc);
-                    lindblad_mono_sandwich_kernel<<<grid, 256, 0, c->stream>>>(
+                    dim3 grid((unsigned)((n + MONO_CB - 1) / MONO_CB), mc);
+                    const size_t msm = (size_t)K * MONO_CB * (sizeof(c128) + sizeof(int)) + (size_t)(MONO_CB + K) * sizeof(double);
+                    lindblad_mono_sandwich_kernel<<<grid, 256, msm, c->stream>>>(
                         (int)n, K, op->d_mperm, op->d_mval, op->d_mlld, dg + (gamma_shared ? 0 : (long long)m0 * K), gamma_shared ? 0 : K,
                         ub + (long long)m0 * nn, dub + (long long)m0 * nn, anti);
                     OQB_LAUNCH_CHECK(c);
