@@ -548,3 +548,37 @@ def test_davies_groups_oracle_two_generators_full_rhs():
     O.DaviesGenerator(cs[2:], g2, s2).rhs_acc(X, rho, gi, v, 0.0)
     ref = v @ X @ v.conj().T
     assert np.linalg.norm(got - ref) <= 1e-13 * np.linalg.norm(ref)
+
+
+# ---- test/utilities/multi_qubits_construction.jl:3-15 — the builders every fixture of the parity tests goes through ----
+def test_fixture_builders_known_answers():
+    k = F.kron
+    assert np.array_equal(F.q_translate("ZZ+0.5ZI-XZ"), k(sz, sz) + 0.5 * k(sz, si) - k(sx, sz))           # :3
+    assert np.array_equal(F.single_clause(["x"], [2], 0.5, 2), 0.5 * k(si, sx))                             # :4
+    assert np.array_equal(F.single_clause(["z", "z"], [2, 3], -2, 4), -2 * k(si, sz, sz, si))               # :6
+    assert np.array_equal(F.single_clause([F.sp], [3], 0.1, 3), 0.1 * k(si, si, F.sp))                      # :7
+    assert np.array_equal(F.standard_driver(2), k(sx, si) + k(si, sx))                                      # :9
+    assert np.allclose(F.collective_operator("z", 3), k(sz, si, si) + k(si, sz, si) + k(si, si, sz))        # :11
+    assert np.allclose(F.local_field_term([-1.0, 0.5], [1, 3], 3), -1.0 * k(sz, si, si) + 0.5 * k(si, si, sz))   # :13
+    assert np.allclose(F.two_local_term([-1.0, 0.5], [[1, 3], [1, 2]], 3), -1.0 * k(sz, si, sz) + 0.5 * k(sz, sz, si))  # :15
+    # the diagonal short-cut used by the full-size configurations is the same operator
+    J, idx = [-1.0, 0.5, 0.25], [[1, 3], [1, 2], [2, 4]]
+    assert np.allclose(np.diag(F.ising_diag(4, J, idx)), F.two_local_term(J, idx, 4))
+    # σ₊ / σ₋ of src/math_util.jl:7-8
+    assert np.array_equal(F.sp, np.array([[0, 1], [0, 0]])) and np.array_equal(F.sm, F.sp.T)
+
+
+# ---- test/opensys/stochastic.jl:3-17 -------------------------------------------------------------
+def test_fluctuator_cache_known_answers():
+    """FluctuatorLiouvillian with ConstantCouplings(["Z"], unit=:ħ) and two fluctuators of amplitude b = [1, 1]: the noise
+    values are n = b .* (±1), so update_cache! gives −i Σ_k n_k σz and update_vectorized_cache! its superoperator form."""
+    p = O.ODEParams(None, 5.0, lambda tf, t: t / tf)
+    for signs in ([1, 1], [1, -1], [-1, -1]):
+        b0 = np.array([1.0, 1.0]) * np.array(signs)
+        fl = O.FluctuatorLiouvillian([sz], [b0.sum()])  # one coupling, n = sum(b0, dims=1) (src/opensys/stochastic.jl:55-57)
+        cache_exp = -1j * sum(b * sz for b in b0)                                                   # :8
+        cache = fl.update_cache_acc(np.zeros((2, 2), dtype=complex), p, 2.5)
+        assert np.allclose(cache, cache_exp)                                                         # :13
+        v = fl.update_vectorized_cache_acc(np.zeros((4, 4), dtype=complex), p, 2.5)
+        one = np.eye(2)
+        assert np.allclose(v, np.kron(one, cache_exp) - np.kron(cache_exp.T, one))                  # :17
