@@ -853,8 +853,11 @@ static void analyze_terms(const c128* Hm, int n, int nterms, TermStructure& ts) 
     ts.hdiag.assign((size_t)std::max(nterms, 1) * n, make_double2(0.0, 0.0));
     for (int i = 0; i < nterms; ++i) {
         bool diag = true;
-        for (size_t e = 0; e < nn && diag; ++e)
-            if (e % n != e / n && (Hm[i * nn + e].x != 0.0 || Hm[i * nn + e].y != 0.0)) diag = false;
+        for (int j = 0; j < n && diag; ++j) {
+            const c128* col = Hm + i * nn + (size_t)j * n;
+            for (int r = 0; r < n; ++r)
+                if (r != j && (col[r].x != 0.0 || col[r].y != 0.0)) { diag = false; break; }
+        }
         if (diag) {
             for (int r = 0; r < n; ++r) ts.hdiag[(size_t)i * n + r] = Hm[i * nn + (size_t)r * n + r];
         } else {
